@@ -1,0 +1,942 @@
+// oracle/hla_oracle.cpp — CPU ORACLE. TEST INFRASTRUCTURE ONLY.
+//
+// A single-threaded C++17 restatement of scHLAcount's read -> allele quantification path, used by tests/,
+// __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs as the CHECKER. Nothing under
+// schlacount_b200/ may include, link or call this file.
+//
+// What it restates (reference file:line, relative to /root/reference):
+//   * src/hla.rs:19-93     AlleleParser / Allele ordering            -> parse_allele(), allele_less()
+//   * src/hla.rs:102-209   read_hla_cds (tx-id numbering)             -> read_hla_cds()
+//   * src/hla.rs:230-264   make_hla_index allele-status filter        -> load_allele_status()
+//   * src/mapping.rs:118-229, 283-308  EqClassDb + intersect()        -> EqClassDb, merge_no_truncate()
+//   * src/mapping.rs:337-402 genotyping orientation policy            -> orc_geno_run()
+//   * src/mapping.rs:668-728 row layout / eq_class_to_gene            -> build_rows()
+//   * src/mapping.rs:740-807 counting 4-way policy                    -> orc_count_run()
+//   * src/mapping.rs:823-909 count()                                  -> count_scores()
+//   * src/em.rs:19-138, 232-336  EqClassCounts EmProblem, squarem, diffs -> EmProblem, squarem()
+//   * src/em.rs:361-434    genotype caller                            -> call_genotypes()
+//   * src/config.rs:4-21   thresholds
+// and, because the pinned git dependencies are NOT vendored in /root/reference (Cargo.toml:10-11,
+// Cargo.lock:600-602,619-621: debruijn_mapping @ae4aadbc, debruijn @9c7caf19, boomphf 0.5.2, bincode 1.1.4):
+//   * Pseudoaligner::map_read            -> map_read_to_nodes() / map_read()   
+//   * build_index (stranded k=24 dBG)    -> build_index()                      
+//   * bincode layout of Pseudoaligner    -> load_idx()                         
+//   * DnaString::from_acgt_bytes         -> base_code()
+//
+// PARITY PINNING: the reference binary cannot be built here (no rustc/cargo). The oracle is pinned instead on
+// the reference's own fixtures (tests/test_oracle_golden.py): test/test_allele_fasta.mtx and test/test_call.mtx
+// are reproduced exactly through the full path, and build_index() reproduces the node/colour set of the
+// committed test/fake_db/hla_nuc.fasta.idx. EM abundances themselves are NOT pinned by any reference test
+// (em.rs tests only print) — only the genotype calls are, indirectly, by test_call.mtx.
+// Choices the fixtures do not pin (named constants below): STRIDE, LEFT_EXTEND_FRACTION, N->A, merge order.
+
+#include <algorithm>
+#include <array>
+#include <tuple>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <set>
+#include <sstream>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+namespace orc {
+
+// ---- constants ------------------------------------------------------------------------------------------
+constexpr int K = 24;                          // PINNED by hla_nuc.fasta.idx (min node length 24)
+constexpr int ALLOWED_MISMATCH = 2;            // README.md:108 (goldens pin 1..4)
+constexpr int STRIDE = 1;                      // unpinned (1..3 reproduce goldens)
+constexpr double LEFT_EXTEND_FRACTION = 0.2;   // unpinned
+// src/config.rs:4-21
+constexpr size_t MIN_SCORE_CALL = 40;
+constexpr size_t MIN_SCORE_COUNT_PSEUDO = 60;
+constexpr double GENE_CONSENSUS_THRESHOLD = 0.5;
+constexpr double ALLELE_CONSENSUS_THRESHOLD = 0.1;
+constexpr size_t EM_ITERS = 2000;
+constexpr double EM_REL_TH = 5e-4;
+constexpr double EM_ABS_TH = 5e-3;
+constexpr double EM_CARE_TH = 1e-5;
+constexpr size_t MIN_READS_CALL = 100;
+constexpr double HOMOZYGOUS_TH = 0.15;
+constexpr size_t PAIRS_TO_OUTPUT = 5;
+constexpr size_t WEIGHTS_TO_OUTPUT = 10;
+
+static thread_local std::string g_err;
+
+// [EXT] DnaString::from_acgt_bytes: ACGT (either case) -> 0..3, everything else -> A.
+static inline uint8_t base_code(char c) {
+  switch (c) {
+    case 'A': case 'a': return 0;
+    case 'C': case 'c': return 1;
+    case 'G': case 'g': return 2;
+    case 'T': case 't': return 3;
+    default: return 0;
+  }
+}
+
+using Bases = std::vector<uint8_t>;  // one 2-bit code per byte: clarity over speed in the index, see Read below
+
+static Bases to_bases(const std::string& s) {
+  Bases b(s.size());
+  for (size_t i = 0; i < s.size(); i++) b[i] = base_code(s[i]);
+  return b;
+}
+
+// ---- exact k-mer dictionary (open addressing) --------------------------------------------------------------
+// The reference uses a boomphf MPHF + mandatory verification of the k-mer at (node, offset); any exact
+// dictionary is observationally equivalent.
+struct KmerDict {
+  std::vector<uint64_t> keys;  // kmer+1 (0 = empty)
+  std::vector<uint64_t> vals;  // node<<32 | offset
+  uint64_t mask = 0;
+  static inline uint64_t mix(uint64_t x) {
+    x ^= x >> 31; x *= 0x7fb5d329728ea185ULL; x ^= x >> 27; x *= 0x81dadef4bc2dd44dULL; x ^= x >> 33;
+    return x;
+  }
+  void init(size_t n) {
+    size_t cap = 16;
+    while (cap < n * 2 + 2) cap <<= 1;
+    keys.assign(cap, 0); vals.assign(cap, 0); mask = cap - 1;
+  }
+  void put(uint64_t kmer, uint32_t node, uint32_t off) {
+    uint64_t h = mix(kmer) & mask;
+    while (keys[h] != 0 && keys[h] != kmer + 1) h = (h + 1) & mask;
+    keys[h] = kmer + 1; vals[h] = (uint64_t(node) << 32) | off;
+  }
+  bool get(uint64_t kmer, uint32_t& node, uint32_t& off) const {
+    uint64_t h = mix(kmer) & mask;
+    while (keys[h] != 0) {
+      if (keys[h] == kmer + 1) { node = uint32_t(vals[h] >> 32); off = uint32_t(vals[h]); return true; }
+      h = (h + 1) & mask;
+    }
+    return false;
+  }
+};
+
+// ---- index -------------------------------------------------------------------------------------------------
+struct Index {
+  Bases seq;                          // all node sequences concatenated
+  std::vector<uint64_t> start;        // per node
+  std::vector<uint32_t> len;          // per node
+  std::vector<uint8_t> exts;          // per node: high nibble right mask, low nibble left mask (Appendix B)
+  std::vector<uint32_t> colour;       // per node colour id
+  std::vector<std::vector<uint32_t>> eq_classes;  // colour id -> sorted tx ids
+  std::vector<std::string> tx_names;
+  KmerDict dict;                      // every k-mer -> (node, offset)
+  std::unordered_map<uint64_t, uint32_t> first_kmer, last_kmer;  // left_order / right_order
+
+  uint64_t kmer_at(uint32_t node, uint32_t off) const {
+    uint64_t v = 0;
+    const uint8_t* p = &seq[start[node] + off];
+    for (int i = 0; i < K; i++) v = (v << 2) | p[i];
+    return v;
+  }
+  void finish() {  // rebuild dictionaries by enumerating every node offset (Appendix B)
+    size_t nk = 0;
+    for (size_t n = 0; n < len.size(); n++) nk += len[n] - K + 1;
+    dict.init(nk);
+    first_kmer.clear(); last_kmer.clear();
+    for (uint32_t n = 0; n < len.size(); n++) {
+      uint32_t cnt = len[n] - K + 1;
+      uint64_t v = kmer_at(n, 0);
+      const uint64_t m = (1ULL << (2 * K)) - 1;
+      for (uint32_t o = 0; o < cnt; o++) {
+        if (o) v = ((v << 2) | seq[start[n] + o + K - 1]) & m;
+        dict.put(v, n, o);
+        if (o == 0) first_kmer[v] = n;
+        if (o == cnt - 1) last_kmer[v] = n;
+      }
+    }
+  }
+};
+
+// ---- bincode loader for `Pseudoaligner<Kmer24>` ----------------------------------------
+struct Cursor {
+  const uint8_t* p; size_t n; size_t o = 0; bool ok = true;
+  uint64_t u64() { uint64_t v = 0; if (o + 8 > n) { ok = false; return 0; } memcpy(&v, p + o, 8); o += 8; return v; }
+  uint32_t u32() { uint32_t v = 0; if (o + 4 > n) { ok = false; return 0; } memcpy(&v, p + o, 4); o += 4; return v; }
+  uint8_t u8() { if (o + 1 > n) { ok = false; return 0; } return p[o++]; }
+  void skip(size_t k) { if (o + k > n) ok = false; else o += k; }
+};
+
+static void skip_mphf(Cursor& c) {
+  uint64_t nb = c.u64();                       // bitvecs: Vec<{bits:u64, vector:Vec<u64>}>
+  for (uint64_t i = 0; i < nb && c.ok; i++) { c.u64(); uint64_t w = c.u64(); c.skip(w * 8); }
+  uint64_t nr = c.u64();                       // ranks: Vec<Vec<u64>>
+  for (uint64_t i = 0; i < nr && c.ok; i++) { uint64_t w = c.u64(); c.skip(w * 8); }
+}
+
+static bool load_idx(const std::string& path, Index& ix) {
+  std::ifstream f(path, std::ios::binary);
+  if (!f) { g_err = "cannot open " + path; return false; }
+  std::vector<uint8_t> buf((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+  Cursor c{buf.data(), buf.size()};
+  uint64_t nw = c.u64();
+  std::vector<uint64_t> words(nw);
+  for (auto& w : words) w = c.u64();
+  uint64_t nbases = c.u64();
+  ix.seq.resize(nbases);
+  for (uint64_t i = 0; i < nbases; i++) ix.seq[i] = (words[i >> 5] >> (62 - 2 * (i & 31))) & 3;
+  uint64_t ns = c.u64(); ix.start.resize(ns); for (auto& v : ix.start) v = c.u64();
+  uint64_t nl = c.u64(); ix.len.resize(nl); for (auto& v : ix.len) v = c.u32();
+  uint64_t ne = c.u64(); ix.exts.resize(ne); for (auto& v : ix.exts) v = c.u8();
+  uint64_t nd = c.u64(); ix.colour.resize(nd); for (auto& v : ix.colour) v = c.u32();
+  uint8_t stranded = c.u8();
+  for (int pass = 0; pass < 2; pass++) {        // left_order, right_order: BoomHashMap<Kmer24,u32>
+    skip_mphf(c);
+    uint64_t nk = c.u64(); c.skip(nk * 8);
+    uint64_t nv = c.u64(); c.skip(nv * 4);
+  }
+  uint64_t nc = c.u64(); ix.eq_classes.resize(nc);
+  for (auto& cl : ix.eq_classes) { uint64_t m = c.u64(); cl.resize(m); for (auto& t : cl) t = c.u32(); }
+  skip_mphf(c);                                  // dbg_index: NoKeyBoomHashMap<Kmer24,(u32,u32)>
+  uint64_t nv = c.u64(); c.skip(nv * 8);
+  uint64_t nt = c.u64(); ix.tx_names.resize(nt);
+  for (auto& s : ix.tx_names) { uint64_t m = c.u64(); if (c.o + m > c.n) { c.ok = false; break; } s.assign((const char*)c.p + c.o, m); c.o += m; }
+  uint64_t nm = c.u64();
+  for (uint64_t i = 0; i < nm && c.ok; i++) { uint64_t a = c.u64(); c.skip(a); uint64_t b = c.u64(); c.skip(b); }
+  if (!c.ok || c.o != c.n) { g_err = "idx parse did not end at EOF"; return false; }
+  if (stranded != 1 || ns != nl || ns != ne || ns != nd) { g_err = "idx: unexpected shape"; return false; }
+  ix.finish();
+  return true;
+}
+
+// ---- build_index [EXT]: stranded k=24 coloured compacted de Bruijn graph ----------------------
+static void build_index(const std::vector<Bases>& seqs, const std::vector<std::string>& names, Index& ix) {
+  struct KInfo { uint32_t first_tx, first_pos; uint8_t lext = 0, rext = 0; uint32_t colour = 0; int32_t node = -1; };
+  std::unordered_map<uint64_t, uint32_t> kid;       // kmer -> dense id in first-occurrence order
+  std::vector<uint64_t> kmers; std::vector<KInfo> info;
+  std::vector<std::vector<uint32_t>> txs;            // per kmer: sorted tx list
+  const uint64_t m = (1ULL << (2 * K)) - 1;
+  for (uint32_t t = 0; t < seqs.size(); t++) {
+    const Bases& s = seqs[t];
+    if ((int)s.size() < K) continue;
+    uint64_t v = 0;
+    for (int i = 0; i < K - 1; i++) v = (v << 2) | s[i];
+    for (size_t i = 0; i + K <= s.size(); i++) {
+      v = ((v << 2) | s[i + K - 1]) & m;
+      auto it = kid.find(v);
+      uint32_t id;
+      if (it == kid.end()) {
+        id = kmers.size(); kid.emplace(v, id); kmers.push_back(v);
+        KInfo ki; ki.first_tx = t; ki.first_pos = i; info.push_back(ki); txs.emplace_back();
+      } else id = it->second;
+      if (txs[id].empty() || txs[id].back() != t) txs[id].push_back(t);
+      if (i > 0) info[id].lext |= 1 << s[i - 1];
+      if (i + K < s.size()) info[id].rext |= 1 << s[i + K];
+    }
+  }
+  // colours: intern tx lists
+  std::map<std::vector<uint32_t>, uint32_t> cmap;
+  ix.eq_classes.clear();
+  for (size_t i = 0; i < kmers.size(); i++) {
+    auto it = cmap.find(txs[i]);
+    if (it == cmap.end()) { it = cmap.emplace(txs[i], (uint32_t)ix.eq_classes.size()).first; ix.eq_classes.push_back(txs[i]); }
+    info[i].colour = it->second;
+  }
+  auto single = [](uint8_t mask) { return mask && !(mask & (mask - 1)); };
+  auto lowbit = [](uint8_t mask) { int b = 0; while (!(mask >> b & 1)) b++; return b; };
+  // A -> B mergeable iff A has one right ext, B has one left ext, same colour, A != B
+  auto succ = [&](uint32_t a) -> int64_t {
+    if (!single(info[a].rext)) return -1;
+    uint64_t bk = ((kmers[a] << 2) | lowbit(info[a].rext)) & m;
+    auto it = kid.find(bk);
+    if (it == kid.end()) return -1;
+    uint32_t b = it->second;
+    if (b == a || !single(info[b].lext) || info[b].colour != info[a].colour) return -1;
+    return b;
+  };
+  auto has_pred = [&](uint32_t b) -> bool {
+    if (!single(info[b].lext)) return false;
+    uint64_t pk = (kmers[b] >> 2) | (uint64_t(lowbit(info[b].lext)) << (2 * K - 2));
+    auto it = kid.find(pk);
+    if (it == kid.end()) return false;
+    return succ(it->second) == (int64_t)b;
+  };
+  ix.seq.clear(); ix.start.clear(); ix.len.clear(); ix.exts.clear(); ix.colour.clear();
+  auto emit = [&](uint32_t a) {
+    uint32_t node = ix.start.size();
+    ix.start.push_back(ix.seq.size());
+    for (int i = K - 1; i >= 0; i--) ix.seq.push_back((kmers[a] >> (2 * i)) & 3);
+    info[a].node = node;
+    uint32_t cur = a;
+    for (;;) {
+      int64_t b = succ(cur);
+      if (b < 0 || info[b].node >= 0) break;
+      ix.seq.push_back(kmers[b] & 3);
+      info[b].node = node; cur = b;
+    }
+    ix.len.push_back(ix.seq.size() - ix.start.back());
+    ix.exts.push_back((info[cur].rext << 4) | info[a].lext);
+    ix.colour.push_back(info[a].colour);
+  };
+  for (uint32_t a = 0; a < kmers.size(); a++) if (info[a].node < 0 && !has_pred(a)) emit(a);
+  for (uint32_t a = 0; a < kmers.size(); a++) if (info[a].node < 0) emit(a);   // pure cycles
+  ix.tx_names = names;
+  ix.finish();
+}
+
+// ---- hla.rs ---------------------------------------------------------------------------------------------------
+struct Allele { std::string gene; uint16_t f1 = 0; int32_t f2 = -1, f3 = -1, f4 = -1; std::string name; };
+
+// src/hla.rs:49-92: ^[A-Z0-9]+[*][0-9]+(:[0-9]+)*[A-Z]?$
+static bool parse_allele(const std::string& s, Allele& a) {
+  size_t i = 0, n = s.size();
+  while (i < n && (isupper((unsigned char)s[i]) || isdigit((unsigned char)s[i]))) i++;
+  if (i == 0 || i >= n || s[i] != '*') {
+    // the greedy [A-Z0-9]+ may need to backtrack only over chars that are not '*': there are none
+    return false;
+  }
+  std::string gene = s.substr(0, i);
+  size_t j = i + 1, st = j;
+  while (j < n && isdigit((unsigned char)s[j])) j++;
+  if (j == st) return false;
+  std::vector<uint32_t> f; f.push_back(std::stoul(s.substr(st, j - st)));
+  while (j < n && s[j] == ':') {
+    size_t st2 = j + 1, e = st2;
+    while (e < n && isdigit((unsigned char)s[e])) e++;
+    if (e == st2) return false;
+    f.push_back(std::stoul(s.substr(st2, e - st2)));
+    j = e;
+  }
+  if (j < n && isupper((unsigned char)s[j])) j++;
+  if (j != n) return false;
+  a.gene = gene; a.f1 = f[0];
+  a.f2 = f.size() > 1 ? (int32_t)f[1] : -1; a.f3 = f.size() > 2 ? (int32_t)f[2] : -1; a.f4 = f.size() > 3 ? (int32_t)f[3] : -1;
+  a.name = s;
+  return true;
+}
+// derive(Ord) on Allele: gene bytes, f1, f2, f3, f4 (None < Some), name
+static int allele_cmp(const Allele& x, const Allele& y) {
+  if (x.gene != y.gene) return x.gene < y.gene ? -1 : 1;
+  if (x.f1 != y.f1) return x.f1 < y.f1 ? -1 : 1;
+  if (x.f2 != y.f2) return x.f2 < y.f2 ? -1 : 1;
+  if (x.f3 != y.f3) return x.f3 < y.f3 ? -1 : 1;
+  if (x.f4 != y.f4) return x.f4 < y.f4 ? -1 : 1;
+  if (x.name != y.name) return x.name < y.name ? -1 : 1;
+  return 0;
+}
+
+struct FastaRec { std::string id, desc, seq; };
+static bool read_fasta(const std::string& path, std::vector<FastaRec>& out) {
+  std::ifstream f(path);
+  if (!f) { g_err = "cannot open " + path; return false; }
+  std::string line;
+  while (std::getline(f, line)) {
+    if (!line.empty() && line.back() == '\r') line.pop_back();
+    if (line.empty()) continue;
+    if (line[0] == '>') {
+      FastaRec r; size_t sp = line.find(' ');
+      r.id = line.substr(1, sp == std::string::npos ? std::string::npos : sp - 1);
+      r.desc = sp == std::string::npos ? "" : line.substr(sp + 1);
+      out.push_back(r);
+    } else if (!out.empty()) out.back().seq += line;
+  }
+  return true;
+}
+
+// src/hla.rs:102-209
+static bool read_hla_cds(const std::string& path, const std::set<std::string>& allele_set, bool use_filter,
+                         std::vector<Bases>& seqs, std::vector<std::string>& tx_ids) {
+  static const char* genes[] = {"A", "B", "C", "DRB1", "DPA1", "DPB1", "DQA1", "DQB1"};
+  std::vector<FastaRec> recs;
+  if (!read_fasta(path, recs)) return false;
+  struct H { Allele a; std::string tx_id, allele_str; Bases seq; };
+  std::vector<H> hlas;
+  for (auto& r : recs) {
+    if (r.desc.empty()) { g_err = "no HLA allele"; return false; }
+    std::string allele_str = r.desc.substr(0, r.desc.find(' '));
+    if (use_filter && !allele_set.count(allele_str)) continue;
+    Allele a;
+    if (!parse_allele(allele_str, a)) { g_err = "invalid allele string: " + allele_str; return false; }
+    bool keep = false;
+    for (auto g : genes) if (a.gene == g) keep = true;
+    if (keep) hlas.push_back(H{a, r.id, allele_str, to_bases(r.seq)});
+  }
+  std::sort(hlas.begin(), hlas.end(), [](const H& x, const H& y) {
+    int c = allele_cmp(x.a, y.a); if (c) return c < 0;
+    if (x.tx_id != y.tx_id) return x.tx_id < y.tx_id;
+    if (x.allele_str != y.allele_str) return x.allele_str < y.allele_str;
+    return x.seq < y.seq;   // DnaString Ord [EXT]; never reached for distinct names
+  });
+  using Key2 = std::tuple<std::string, uint16_t, int32_t>;
+  std::map<Key2, size_t> lengths;
+  if (!use_filter) {
+    for (size_t i = 0; i < hlas.size();) {
+      size_t j = i; Key2 k{hlas[i].a.gene, hlas[i].a.f1, hlas[i].a.f2}; size_t mx = 0;
+      while (j < hlas.size() && Key2{hlas[j].a.gene, hlas[j].a.f1, hlas[j].a.f2} == k) { mx = std::max(mx, hlas[j].seq.size()); j++; }
+      lengths[k] = mx;   // consecutive groups with the same key would overwrite; sorted input => one group per key
+      i = j;
+    }
+  }
+  for (size_t i = 0; i < hlas.size();) {
+    size_t j = i;
+    auto same3 = [&](const H& h) { return h.a.gene == hlas[i].a.gene && h.a.f1 == hlas[i].a.f1 && h.a.f2 == hlas[i].a.f2 && h.a.f3 == hlas[i].a.f3; };
+    while (j < hlas.size() && same3(hlas[j])) j++;
+    // stable sort by length then pop => the LAST among the longest
+    size_t best = i;
+    for (size_t q = i; q < j; q++) if (hlas[q].seq.size() >= hlas[best].seq.size()) best = q;
+    const H& h = hlas[best];
+    bool push = true;
+    if (!use_filter) push = h.seq.size() >= lengths[Key2{h.a.gene, h.a.f1, h.a.f2}];
+    if (push) { seqs.push_back(h.seq); tx_ids.push_back(h.allele_str); }
+    i = j;
+  }
+  return true;
+}
+
+// src/hla.rs:236-250 (csv with header row, '#' comments)
+static bool load_allele_status(const std::string& path, std::set<std::string>& out) {
+  std::ifstream f(path);
+  if (!f) { g_err = "cannot open " + path; return false; }
+  std::string line; bool header = true;
+  while (std::getline(f, line)) {
+    if (!line.empty() && line.back() == '\r') line.pop_back();
+    if (line.empty() || line[0] == '#') continue;
+    if (header) { header = false; continue; }
+    std::vector<std::string> c; std::stringstream ss(line); std::string x;
+    while (std::getline(ss, x, ',')) c.push_back(x);
+    if (c.size() < 8) continue;
+    if (c[0].rfind('N') == std::string::npos && c[3] == "Confirmed" && c[6] == "Full" && c[7] == "gDNA") out.insert(c[0]);
+  }
+  return true;
+}
+
+// ---- map_read [EXT] --------------------------------------------------------------------------
+struct ReadSeq { const uint8_t* b; int L; };  // 2-bit codes, one per byte
+
+static bool map_read_to_nodes(const Index& ix, ReadSeq r, std::vector<uint32_t>& nodes, size_t& cov_out) {
+  nodes.clear(); cov_out = 0;
+  const int L = r.L;
+  if (L < K) return false;
+  const int last = L - K;
+  int pos = 0; long cov = 0;
+  uint32_t node = 0, off = 0;
+  auto kmer_of = [&](int p) { uint64_t v = 0; for (int i = 0; i < K; i++) v = (v << 2) | r.b[p + i]; return v; };
+  auto find = [&]() -> bool {
+    while (pos <= last) {
+      if (ix.dict.get(kmer_of(pos), node, off)) return true;
+      pos += STRIDE;
+    }
+    return false;
+  };
+  bool hit = find();
+  // left extension
+  if (hit && pos >= (int)std::floor(LEFT_EXTEND_FRACTION * L)) {
+    int lp = pos - 1; uint32_t pn = node; long po = off > 0 ? (long)off - 1 : 0;
+    for (;;) {
+      int mm = (int)std::min<long>(lp + 1, po + 1); int matched = 0, snp = 0; bool brk = false;
+      const uint8_t* ns = &ix.seq[ix.start[pn]];
+      for (int i = 0; i < mm; i++) {
+        if (ns[po - i] != r.b[lp - i]) { snp++; if (snp > ALLOWED_MISMATCH) { brk = true; break; } }
+        matched++; cov++;
+      }
+      if (lp + 1 - matched == 0 || brk) break;
+      lp -= matched;
+      uint8_t b = r.b[lp];
+      if ((ix.exts[pn] & 0xF) >> b & 1) {
+        uint64_t pk = (ix.kmer_at(pn, 0) >> 2) | (uint64_t(b) << (2 * K - 2));
+        auto it = ix.last_kmer.find(pk);
+        if (it == ix.last_kmer.end()) break;   // cannot happen on a consistent index
+        pn = it->second; po = (long)ix.len[pn] - K; nodes.push_back(pn);
+      } else break;
+    }
+  }
+  if (pos <= last) {
+    for (;;) {
+      pos += K; cov += K; nodes.push_back(node);
+      uint32_t ro = off + K;
+      int mm = std::min<long>(L - pos, (long)ix.len[node] - ro); int matched = 0, snp = 0; bool brk = false;
+      const uint8_t* ns = &ix.seq[ix.start[node]];
+      for (int i = 0; i < mm; i++) {
+        if (ns[ro + i] != r.b[pos + i]) { snp++; if (snp > ALLOWED_MISMATCH) { brk = true; break; } }
+        matched++; cov++;
+      }
+      pos += matched;
+      if (pos >= L) break;
+      uint8_t b = r.b[pos];
+      if (!brk && ((ix.exts[node] >> 4) >> b & 1)) {
+        const uint64_t m = (1ULL << (2 * K)) - 1;
+        uint64_t nk = ((ix.kmer_at(node, ix.len[node] - K) << 2) | b) & m;
+        auto it = ix.first_kmer.find(nk);
+        if (it == ix.first_kmer.end()) break;  // cannot happen on a consistent index
+        node = it->second; off = 0;
+        pos -= K - 1; cov -= K - 1;
+      } else {
+        if (pos > last) break;
+        if (!find()) break;
+      }
+    }
+  }
+  if (nodes.empty()) return false;
+  cov_out = (size_t)cov;
+  return true;
+}
+
+// src/mapping.rs:283-308 — note: NO truncate
+static void merge_no_truncate(std::vector<uint32_t>& v1, const std::vector<uint32_t>& v2) {
+  if (v1.empty()) return;
+  if (v2.empty()) v1.clear();
+  size_t f = 0, i = 0, j = 0;
+  while (i < v1.size() && j < v2.size()) {
+    if (v1[i] < v2[j]) i++;
+    else if (v1[i] > v2[j]) j++;
+    else { std::swap(v1[f], v1[i]); i++; j++; f++; }
+  }
+}
+
+static bool map_read(const Index& ix, ReadSeq r, std::vector<uint32_t>& cls, size_t& cov, std::vector<uint32_t>& nodes) {
+  if (!map_read_to_nodes(ix, r, nodes, cov)) return false;
+  cls = ix.eq_classes[ix.colour[nodes.back()]];
+  for (size_t i = 0; i + 1 < nodes.size(); i++) merge_no_truncate(cls, ix.eq_classes[ix.colour[nodes[i]]]);
+  return true;
+}
+
+// bio::alphabets::dna::revcomp over the packed read's ASCII (N already A -> T)
+static void revcomp(const uint8_t* b, int L, std::vector<uint8_t>& out) {
+  out.resize(L);
+  for (int i = 0; i < L; i++) out[i] = 3 - b[L - 1 - i];
+}
+
+// ---- batch input: the same packed SoA the product ABI takes (include/hlacount.h) -------------------------------
+struct Batch {
+  const uint64_t* seq; uint32_t words_per_read; const uint16_t* len;
+  const uint32_t* cell; const uint32_t* umi; const uint8_t* flags; uint64_t n;
+};
+static inline void unpack(const Batch& b, uint64_t i, std::vector<uint8_t>& out) {
+  int L = b.len[i]; out.resize(L);
+  const uint64_t* w = b.seq + i * b.words_per_read;
+  for (int k = 0; k < L; k++) out[k] = (w[k >> 5] >> (62 - 2 * (k & 31))) & 3;
+}
+
+// ---- row layout (src/mapping.rs:668-728) -------------------------------------------------------------------------
+struct Rows {
+  std::vector<std::string> rownames;
+  std::map<std::vector<uint32_t>, std::pair<int, int>> eq_class_to_gene;  // class -> (gene idx, slot)
+  std::vector<uint32_t> gene_row0;                                         // genes_to_rownums
+  std::vector<std::string> gene_names;
+  size_t nrows = 0;
+};
+static void build_rows(const std::vector<std::string>& tx_names, Rows& rows) {
+  struct A { Allele a; uint32_t tx; };
+  std::vector<A> al;
+  for (uint32_t i = 0; i < tx_names.size(); i++) { Allele a; if (parse_allele(tx_names[i], a)) al.push_back({a, i}); }
+  std::stable_sort(al.begin(), al.end(), [](const A& x, const A& y) { return x.a.gene < y.a.gene; });
+  for (size_t i = 0; i < al.size();) {
+    size_t j = i; while (j < al.size() && al[j].a.gene == al[i].a.gene) j++;
+    int g = rows.gene_names.size();
+    rows.gene_names.push_back(al[i].a.gene); rows.gene_row0.push_back(rows.nrows);
+    rows.eq_class_to_gene[{al[i].tx}] = {g, 0};
+    if (j - i >= 2) {
+      rows.eq_class_to_gene[{al[i + 1].tx}] = {g, 1};
+      std::vector<uint32_t> x{al[i].tx, al[i + 1].tx}; std::sort(x.begin(), x.end());
+      rows.eq_class_to_gene[x] = {g, 2};
+      rows.nrows += 3;
+      rows.rownames.push_back(al[i].a.name); rows.rownames.push_back(al[i + 1].a.name); rows.rownames.push_back(al[i].a.gene);
+    } else { rows.nrows += 1; rows.rownames.push_back(al[i].a.name); }
+    i = j;
+  }
+}
+
+// ---- count() (src/mapping.rs:823-909) ----------------------------------------------------------------------------
+struct Score { uint32_t cell; uint32_t umi; int gene; int slot; };
+struct Entry { uint32_t row, col, val; };
+static void count_scores(std::vector<Score> scores, const Rows& rows, std::vector<Entry>& entries) {
+  std::stable_sort(scores.begin(), scores.end(), [](const Score& a, const Score& b) { return a.cell < b.cell; });
+  for (size_t i = 0; i < scores.size();) {
+    size_t j = i; while (j < scores.size() && scores[j].cell == scores[i].cell) j++;
+    std::vector<uint32_t> matrix_row(rows.nrows, 0);
+    std::map<uint32_t, std::vector<const Score*>> parsed;
+    for (size_t q = i; q < j; q++) parsed[scores[q].umi].push_back(&scores[q]);
+    for (auto& kv : parsed) {
+      double nreads = 0.0;
+      std::map<int, std::array<size_t, 3>> gene_frq;
+      for (auto* s : kv.second) { auto& f = gene_frq.emplace(s->gene, std::array<size_t, 3>{0, 0, 0}).first->second; if (s->slot < 3) f[s->slot]++; nreads += 1.0; }
+      int max_gene = -1; size_t max_allele = 0, max_reads = 0;
+      for (auto& gf : gene_frq) {
+        auto& frq = gf.second; size_t ng = frq[0] + frq[1] + frq[2];
+        if (ng > max_reads && (double)ng > GENE_CONSENSUS_THRESHOLD * nreads) {
+          max_gene = gf.first; max_reads = ng;
+          if ((double)frq[0] > ALLELE_CONSENSUS_THRESHOLD * nreads && ALLELE_CONSENSUS_THRESHOLD * nreads > (double)frq[1]) max_allele = 0;
+          else if ((double)frq[1] > ALLELE_CONSENSUS_THRESHOLD * nreads && ALLELE_CONSENSUS_THRESHOLD * nreads > (double)frq[0]) max_allele = 1;
+          else max_allele = 2;
+        }
+      }
+      if (max_gene >= 0) matrix_row[max_allele + rows.gene_row0[max_gene]] += 1;
+    }
+    for (uint32_t c = 0; c < matrix_row.size(); c++) if (matrix_row[c] > 0) entries.push_back({c, scores[i].cell, matrix_row[c]});
+    i = j;
+  }
+}
+
+// ---- EqClassDb (src/mapping.rs:118-229) ---------------------------------------------------------------------------
+struct EqClassDb {
+  std::map<std::vector<uint32_t>, uint32_t> eq_classes;     // class vector -> id (first-seen)
+  std::vector<const std::vector<uint32_t>*> by_id;
+  struct Bus { uint32_t bc, umi, cls; };
+  std::vector<Bus> counts;
+  void count(uint32_t bc, uint32_t umi, const std::vector<uint32_t>& cls) {
+    auto it = eq_classes.find(cls);
+    if (it == eq_classes.end()) { it = eq_classes.emplace(cls, (uint32_t)eq_classes.size()).first; by_id.push_back(&it->first); }
+    counts.push_back({bc, umi, it->second});
+  }
+};
+struct EqClassCounts {
+  size_t nitems = 0;
+  std::map<std::vector<uint32_t>, uint32_t> counts_reads, counts_umi;
+  uint32_t nreads = 0;
+  std::vector<size_t> reads_explained;
+};
+static void eq_class_counts(EqClassDb& db, size_t nitems, EqClassCounts& out) {
+  out = EqClassCounts(); out.nitems = nitems; out.reads_explained.assign(nitems, 0);
+  std::sort(db.counts.begin(), db.counts.end(), [](const EqClassDb::Bus& a, const EqClassDb::Bus& b) {
+    if (a.bc != b.bc) return a.bc < b.bc; if (a.umi != b.umi) return a.umi < b.umi; return a.cls < b.cls; });
+  std::vector<uint32_t> buf;
+  for (size_t i = 0; i < db.counts.size();) {
+    size_t j = i; while (j < db.counts.size() && db.counts[j].bc == db.counts[i].bc && db.counts[j].umi == db.counts[i].umi) j++;
+    buf.clear(); bool flag = false;
+    for (size_t q = i; q < j; q++) {
+      const std::vector<uint32_t>& cls = *db.by_id[db.counts[q].cls];
+      if (flag) merge_no_truncate(buf, cls); else { buf = cls; flag = true; }
+      out.nreads++;
+      for (uint32_t t : cls) out.reads_explained[t]++;
+      out.counts_reads[cls]++;
+    }
+    if (flag) { std::sort(buf.begin(), buf.end()); buf.erase(std::unique(buf.begin(), buf.end()), buf.end()); out.counts_umi[buf]++; }
+    i = j;
+  }
+}
+
+// ---- EM (src/em.rs:48-138, 232-336) -------------------------------------------------------------------------------
+struct EmClasses {                  // counts_umi flattened: CSR of tx ids + count per class
+  size_t nitems; std::vector<uint64_t> off; std::vector<uint32_t> tx; std::vector<uint32_t> cnt;
+};
+static void em_reg(std::vector<double>& th) {
+  double norm = 0.0;
+  for (auto& x : th) { double v = x; if (v > 1.0) v = 1.0; if (v < 0.0) v = 1e-15; x = v; norm += v; }
+  double inv = 1.0 / norm;
+  for (auto& x : th) x *= inv;
+}
+static void em_f(const EmClasses& p, const std::vector<double>& t1, std::vector<double>& t2) {
+  double total = 0.0;
+  std::fill(t2.begin(), t2.end(), 0.0);
+  for (size_t c = 0; c + 1 < p.off.size(); c++) {
+    double norm = 0.0;
+    for (uint64_t q = p.off[c]; q < p.off[c + 1]; q++) norm += t1[p.tx[q]];
+    for (uint64_t q = p.off[c]; q < p.off[c + 1]; q++) { double v = t1[p.tx[q]] / norm * (double)p.cnt[c]; t2[p.tx[q]] += v; total += v; }
+  }
+  for (size_t i = 0; i < p.nitems; i++) t2[i] = t2[i] / total;
+}
+static double em_ll(const EmClasses& p, const std::vector<double>& th) {
+  double ll = 0.0;
+  for (size_t c = 0; c + 1 < p.off.size(); c++) {
+    if (p.off[c] == p.off[c + 1]) continue;
+    double s = 0.0;
+    for (uint64_t q = p.off[c]; q < p.off[c + 1]; q++) s += th[p.tx[q]];
+    ll += (double)p.cnt[c] * std::log(s);
+  }
+  return ll;
+}
+static void em_diffs(const std::vector<double>& t1, const std::vector<double>& t2, double& max_rel, double& max_abs) {
+  max_rel = 0.0; max_abs = 0.0;
+  for (size_t i = 0; i < t1.size(); i++) {
+    double a = std::fabs(t1[i] - t2[i]); double r = a / t1[i];
+    if (a > max_abs) max_abs = a;
+    if (t2[i] > EM_CARE_TH && r > max_rel) max_rel = r;
+  }
+}
+static std::vector<double> squarem(const EmClasses& p, uint32_t& iters_out) {
+  size_t n = p.nitems;
+  std::vector<double> th0(n, 1.0 / (double)n), th1 = th0, th2 = th0, thsq = th0, r = th0, v = th0;
+  size_t iters = 0;
+  for (;;) {
+    em_f(p, th0, th1); em_f(p, th1, th2);
+    double rsq = 0.0, vsq = 0.0;
+    for (size_t i = 0; i < n; i++) { r[i] = th1[i] - th0[i]; rsq += r[i] * r[i]; v[i] = th2[i] - th1[i] - r[i]; vsq += v[i] * v[i]; }
+    double alpha = -std::sqrt(rsq) / std::sqrt(vsq);
+    int tries = 1; double lsq, l2;
+    for (;;) {
+      double asq = alpha * alpha;
+      for (size_t i = 0; i < n; i++) thsq[i] = th0[i] - 2.0 * alpha * r[i] + asq * v[i];
+      em_reg(thsq);
+      lsq = em_ll(p, thsq); l2 = em_ll(p, th2);
+      if (lsq > l2 || tries > 5) break;
+      alpha = (alpha + -1.0) / 2.0;
+      tries++;
+    }
+    double mr, ma;
+    if (lsq > l2) { em_diffs(th0, thsq, mr, ma); std::swap(th0, thsq); }
+    else { em_diffs(th0, th2, mr, ma); std::swap(th0, th2); }
+    iters++;
+    if ((ma < EM_ABS_TH && mr < EM_REL_TH) || iters > EM_ITERS) break;
+  }
+  iters_out = (uint32_t)iters;
+  return th0;
+}
+
+// ---- caller (src/em.rs:361-434) -----------------------------------------------------------------------------------------
+struct CallOut {
+  std::vector<uint32_t> called;                                     // tx ids, ascending
+  std::vector<std::tuple<uint32_t, double, double>> weights_rows;   // tx, em weight, explained fraction
+  std::vector<std::tuple<uint32_t, uint32_t, double>> pairs_rows;   // tx a, tx b, joint fraction
+};
+static uint32_t pair_reads_explained(const EqClassCounts& c, uint32_t a, uint32_t b) {
+  uint32_t e = 0;
+  for (auto& kv : c.counts_reads) {
+    bool has = false; for (uint32_t t : kv.first) if (t == a || t == b) { has = true; break; }
+    if (has) e += kv.second;
+  }
+  return e;
+}
+static void call_genotypes(const std::vector<std::string>& tx_names, const std::vector<double>& weights,
+                           const EqClassCounts& ecc, CallOut& out) {
+  struct W { uint32_t i; double w; std::string gene; size_t exp; };
+  std::vector<W> wn;
+  for (uint32_t i = 0; i < weights.size(); i++) wn.push_back({i, weights[i], tx_names[i].substr(0, tx_names[i].find('*')), ecc.reads_explained[i]});
+  std::stable_sort(wn.begin(), wn.end(), [](const W& a, const W& b) { return -a.w < -b.w; });
+  std::stable_sort(wn.begin(), wn.end(), [](const W& a, const W& b) { return a.gene < b.gene; });
+  std::set<uint32_t> called;
+  double nreads = (double)ecc.nreads;
+  for (size_t s = 0; s < wn.size();) {
+    size_t e = s; while (e < wn.size() && wn[e].gene == wn[s].gene) e++;
+    size_t written = 0;
+    for (size_t q = s; q < e; q++) {
+      if (wn[q].exp > MIN_READS_CALL) {
+        out.weights_rows.emplace_back(wn[q].i, wn[q].w, (double)(uint32_t)wn[q].exp / nreads);
+        written++; if (written == WEIGHTS_TO_OUTPUT) break;
+      } else break;
+    }
+    if (written == 0) { s = e; continue; }
+    struct P { uint32_t a, b; double joint, single; };
+    std::vector<P> pairs; bool stop = false;
+    for (size_t i = 0; i + 1 < written && !stop; i++)
+      for (size_t j = i + 1; j < written; j++) {
+        uint32_t ex = pair_reads_explained(ecc, wn[s + i].i, wn[s + j].i);
+        if (ex > (uint32_t)MIN_READS_CALL)
+          pairs.push_back({wn[s + i].i, wn[s + j].i, (double)ex / nreads, (double)(uint32_t)std::max(wn[s + i].exp, wn[s + j].exp) / nreads});
+        else { stop = true; break; }
+      }
+    if (!pairs.empty()) {
+      std::stable_sort(pairs.begin(), pairs.end(), [](const P& a, const P& b) { return -a.joint < -b.joint; });
+      for (size_t q = 0; q < std::min(PAIRS_TO_OUTPUT, pairs.size()); q++) out.pairs_rows.emplace_back(pairs[q].a, pairs[q].b, pairs[q].joint);
+      if (pairs[0].joint * HOMOZYGOUS_TH > pairs[0].joint - pairs[0].single) { called.insert(pairs[0].a); called.insert(pairs[0].b); }
+      else called.insert(wn[s].i);
+    } else called.insert(wn[s].i);
+    s = e;
+  }
+  out.called.assign(called.begin(), called.end());
+}
+
+struct GenoState { EqClassDb db; EqClassCounts ecc; bool finished = false; std::vector<double> theta; uint32_t iters = 0; CallOut call; };
+
+}  // namespace orc
+
+// ============================================================================================================
+// C face for ctypes
+// ============================================================================================================
+using namespace orc;
+extern "C" {
+
+const char* orc_last_error() { return g_err.c_str(); }
+
+void* orc_index_from_idx(const char* path) {
+  auto* ix = new Index();
+  if (!load_idx(path, *ix)) { delete ix; return nullptr; }
+  return ix;
+}
+// use_filter: 0 => read_hla_cds(.., false) (counting, mapping.rs:650,657); 1 => make_hla_index (hla.rs:230-264)
+void* orc_index_from_fasta(const char* fasta, int use_filter, const char* allele_status) {
+  std::set<std::string> aset;
+  if (use_filter && !load_allele_status(allele_status, aset)) return nullptr;
+  std::vector<Bases> seqs; std::vector<std::string> names;
+  if (!read_hla_cds(fasta, aset, use_filter != 0, seqs, names)) return nullptr;
+  auto* ix = new Index();
+  build_index(seqs, names, *ix);
+  return ix;
+}
+void orc_index_free(void* h) { delete (Index*)h; }
+uint32_t orc_index_n_nodes(void* h) { return ((Index*)h)->len.size(); }
+uint32_t orc_index_n_tx(void* h) { return ((Index*)h)->tx_names.size(); }
+uint32_t orc_index_n_colours(void* h) { return ((Index*)h)->eq_classes.size(); }
+uint64_t orc_index_n_bases(void* h) { return ((Index*)h)->seq.size(); }
+const char* orc_index_tx_name(void* h, uint32_t i) { return ((Index*)h)->tx_names[i].c_str(); }
+// node i: writes ASCII sequence into buf (cap), returns length; colour list via orc_index_node_colours
+uint32_t orc_index_node_seq(void* h, uint32_t i, char* buf, uint32_t cap) {
+  Index* ix = (Index*)h; uint32_t L = ix->len[i];
+  for (uint32_t k = 0; k < L && k < cap; k++) buf[k] = "ACGT"[ix->seq[ix->start[i] + k]];
+  return L;
+}
+uint32_t orc_index_node_exts(void* h, uint32_t i) { return ((Index*)h)->exts[i]; }
+uint32_t orc_index_node_colours(void* h, uint32_t i, uint32_t* out, uint32_t cap) {
+  Index* ix = (Index*)h; auto& c = ix->eq_classes[ix->colour[i]];
+  for (uint32_t k = 0; k < c.size() && k < cap; k++) out[k] = c[k];
+  return c.size();
+}
+
+// pack ASCII reads into the 2-bit MSB-first batch layout (from_acgt_bytes semantics)
+void orc_pack_ascii(const char* s, uint32_t L, uint64_t* words, uint32_t nwords) {
+  for (uint32_t w = 0; w < nwords; w++) words[w] = 0;
+  for (uint32_t i = 0; i < L; i++) words[i >> 5] |= uint64_t(base_code(s[i])) << (62 - 2 * (i & 31));
+}
+
+// single map_read on a packed read; rc!=0 maps the reverse complement. Returns 1 for Some.
+int orc_map_read(void* h, const uint64_t* words, uint32_t L, int rc, uint32_t* cls, uint32_t cls_cap, uint32_t* ncls,
+                 uint32_t* cov, uint32_t* nodes, uint32_t nodes_cap, uint32_t* nnodes) {
+  Index* ix = (Index*)h;
+  std::vector<uint8_t> b(L), r;
+  for (uint32_t k = 0; k < L; k++) b[k] = (words[k >> 5] >> (62 - 2 * (k & 31))) & 3;
+  if (rc) { revcomp(b.data(), L, r); b.swap(r); }
+  std::vector<uint32_t> c, nd; size_t cv = 0;
+  if (!map_read(*ix, ReadSeq{b.data(), (int)L}, c, cv, nd)) { *ncls = 0; *cov = 0; if (nnodes) *nnodes = 0; return 0; }
+  *ncls = c.size(); *cov = cv;
+  for (uint32_t k = 0; k < c.size() && k < cls_cap; k++) cls[k] = c[k];
+  if (nnodes) { *nnodes = nd.size(); for (uint32_t k = 0; k < nd.size() && k < nodes_cap; k++) nodes[k] = nd[k]; }
+  return 1;
+}
+
+// rows of the count matrix for a CDS index (mapping.rs:668-728)
+uint32_t orc_rows(void* cds, char* names_buf, uint32_t cap) {
+  Rows rows; build_rows(((Index*)cds)->tx_names, rows);
+  std::string s; for (auto& r : rows.rownames) { s += r; s += '\n'; }
+  if (names_buf && cap) { strncpy(names_buf, s.c_str(), cap - 1); names_buf[cap - 1] = 0; }
+  return rows.nrows;
+}
+
+// Counting path (mapping.rs:740-819). cell == 0xFFFFFFFF means "barcode not in the list".
+// code_out[i] (optional): 0xFF = not scored, else gene*3+slot. metrics[6] = num_reads, non_primary, not_cell_bc,
+// cds_align, gen_align, not_aligned. Returns number of entries written (cells ascending, rows ascending), or -1.
+int64_t orc_count_run(void* cds_h, void* gen_h, const uint64_t* seq, uint32_t words_per_read, const uint16_t* len,
+                      const uint32_t* cell, const uint32_t* umi, const uint8_t* flags, uint64_t n, int primary_only,
+                      uint32_t* rows_out, uint32_t* cols_out, uint32_t* vals_out, uint64_t cap, uint64_t* metrics,
+                      uint8_t* code_out, uint32_t* cov_out) {
+  Index* cds = (Index*)cds_h; Index* gen = (Index*)gen_h;
+  Batch b{seq, words_per_read, len, cell, umi, flags, n};
+  Rows rows; build_rows(cds->tx_names, rows);
+  uint64_t m[6] = {0, 0, 0, 0, 0, 0};
+  std::vector<Score> scores;
+  std::vector<uint8_t> fw, rv; std::vector<uint32_t> c0, c1, c2, c3, nd;
+  for (uint64_t i = 0; i < n; i++) {
+    if (code_out) code_out[i] = 0xFF;
+    if (cov_out) cov_out[i] = 0;
+    m[0]++;
+    bool primary = flags[i] & 1;
+    if (!primary) { m[1]++; if (primary_only) continue; }
+    if (cell[i] == 0xFFFFFFFFu) { m[2]++; continue; }
+    unpack(b, i, fw); revcomp(fw.data(), fw.size(), rv);
+    size_t v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+    bool a0 = map_read(*cds, ReadSeq{fw.data(), (int)fw.size()}, c0, v0, nd);
+    bool a2 = map_read(*gen, ReadSeq{fw.data(), (int)fw.size()}, c2, v2, nd);
+    bool a1 = map_read(*cds, ReadSeq{rv.data(), (int)rv.size()}, c1, v1, nd);
+    bool a3 = map_read(*gen, ReadSeq{rv.data(), (int)rv.size()}, c3, v3, nd);
+    const std::vector<uint32_t>* aln = a0 ? &c0 : nullptr; size_t cov = v0;
+    if (a0) { if (v0 > MIN_SCORE_COUNT_PSEUDO) m[3]++; }
+    else if (a1) { if (v1 > MIN_SCORE_COUNT_PSEUDO) { m[3]++; aln = &c1; cov = v1; } }
+    else if (a2) { if (v2 > MIN_SCORE_COUNT_PSEUDO) { m[4]++; aln = &c2; cov = v2; } }
+    else if (a3) { if (v3 > MIN_SCORE_COUNT_PSEUDO) { m[4]++; aln = &c3; cov = v3; } }
+    else m[5]++;
+    if (aln) {
+      if (cov_out) cov_out[i] = cov;
+      auto it = rows.eq_class_to_gene.find(*aln);
+      if (it != rows.eq_class_to_gene.end()) {
+        scores.push_back({cell[i], umi[i], it->second.first, it->second.second});
+        if (code_out) code_out[i] = it->second.first * 3 + it->second.second;
+      }
+    }
+  }
+  std::vector<Entry> entries; count_scores(scores, rows, entries);
+  if (metrics) memcpy(metrics, m, sizeof m);
+  if (entries.size() > cap) { g_err = "entry capacity too small"; return -1; }
+  for (size_t i = 0; i < entries.size(); i++) { rows_out[i] = entries[i].row; cols_out[i] = entries[i].col; vals_out[i] = entries[i].val; }
+  return entries.size();
+}
+
+// Genotyping path (mapping.rs:337-402): push batches in BAM order; forward_only = the --unmapped pass.
+void* orc_geno_new() { return new GenoState(); }
+void orc_geno_free(void* g) { delete (GenoState*)g; }
+// class_id_out[i]: first-seen class id or 0xFFFFFFFF if not counted; cov_out[i]: coverage (0 if None)
+void orc_geno_push(void* g, void* idx_h, const uint64_t* seq, uint32_t words_per_read, const uint16_t* len,
+                   const uint32_t* cell, const uint32_t* umi, uint64_t n, int forward_only,
+                   uint32_t* class_id_out, uint32_t* cov_out) {
+  GenoState* st = (GenoState*)g; Index* ix = (Index*)idx_h;
+  Batch b{seq, words_per_read, len, cell, umi, nullptr, n};
+  std::vector<uint8_t> fw, rv; std::vector<uint32_t> cls, nd;
+  for (uint64_t i = 0; i < n; i++) {
+    if (class_id_out) class_id_out[i] = 0xFFFFFFFFu;
+    if (cov_out) cov_out[i] = 0;
+    unpack(b, i, fw);
+    size_t cov = 0;
+    bool ok = map_read(*ix, ReadSeq{fw.data(), (int)fw.size()}, cls, cov, nd);
+    if (!ok && !forward_only) { revcomp(fw.data(), fw.size(), rv); ok = map_read(*ix, ReadSeq{rv.data(), (int)rv.size()}, cls, cov, nd); }
+    if (!ok) continue;
+    if (cov_out) cov_out[i] = cov;
+    if (cov > MIN_SCORE_CALL) {
+      st->db.count(cell[i], umi[i], cls);
+      if (class_id_out) class_id_out[i] = st->db.counts.back().cls;
+    }
+  }
+}
+// eq_class_counts (mapping.rs:169-228) with nitems = #tx
+void orc_geno_finish(void* g, uint32_t nitems) {
+  GenoState* st = (GenoState*)g;
+  eq_class_counts(st->db, nitems, st->ecc); st->finished = true;
+}
+uint32_t orc_geno_nreads(void* g) { return ((GenoState*)g)->ecc.nreads; }
+uint32_t orc_geno_n_read_classes(void* g) { return ((GenoState*)g)->db.eq_classes.size(); }
+void orc_geno_reads_explained(void* g, uint64_t* out) { auto& v = ((GenoState*)g)->ecc.reads_explained; for (size_t i = 0; i < v.size(); i++) out[i] = v[i]; }
+// which: 0 = counts_reads, 1 = counts_umi. Serialised in lexicographic class order as CSR.
+uint64_t orc_geno_table(void* g, int which, uint64_t* off, uint32_t* tx, uint32_t* cnt, uint64_t cap_classes, uint64_t cap_tx, uint64_t* n_tx_out) {
+  auto& m = which == 0 ? ((GenoState*)g)->ecc.counts_reads : ((GenoState*)g)->ecc.counts_umi;
+  uint64_t nt = 0; for (auto& kv : m) nt += kv.first.size();
+  if (n_tx_out) *n_tx_out = nt;
+  if (!off) return m.size();
+  if (m.size() > cap_classes || nt > cap_tx) return (uint64_t)-1;
+  uint64_t c = 0, q = 0; off[0] = 0;
+  for (auto& kv : m) { for (uint32_t t : kv.first) tx[q++] = t; cnt[c] = kv.second; off[++c] = q; }
+  return m.size();
+}
+
+// SQUAREM on an explicit class table (CSR)
+void orc_squarem(uint32_t nitems, uint64_t nclasses, const uint64_t* off, const uint32_t* tx, const uint32_t* cnt, double* theta_out, uint32_t* iters_out) {
+  EmClasses p; p.nitems = nitems; p.off.assign(off, off + nclasses + 1); p.tx.assign(tx, tx + off[nclasses]); p.cnt.assign(cnt, cnt + nclasses);
+  uint32_t it = 0; auto th = squarem(p, it);
+  for (uint32_t i = 0; i < nitems; i++) theta_out[i] = th[i];
+  if (iters_out) *iters_out = it;
+}
+
+// EM + caller on a finished geno state. called_out: tx ids; returns count. Rows of weights.tsv / pairs.tsv retrievable after.
+uint32_t orc_geno_call(void* g, void* idx_h, double* theta_out, uint32_t* iters_out, uint32_t* called_out, uint32_t cap) {
+  GenoState* st = (GenoState*)g; Index* ix = (Index*)idx_h;
+  EmClasses p; p.nitems = st->ecc.nitems; p.off.push_back(0);
+  for (auto& kv : st->ecc.counts_umi) { for (uint32_t t : kv.first) p.tx.push_back(t); p.cnt.push_back(kv.second); p.off.push_back(p.tx.size()); }
+  st->theta = squarem(p, st->iters);
+  st->call = CallOut(); call_genotypes(ix->tx_names, st->theta, st->ecc, st->call);
+  if (theta_out) for (size_t i = 0; i < st->theta.size(); i++) theta_out[i] = st->theta[i];
+  if (iters_out) *iters_out = st->iters;
+  for (uint32_t i = 0; i < st->call.called.size() && i < cap; i++) called_out[i] = st->call.called[i];
+  return st->call.called.size();
+}
+uint32_t orc_geno_weights_rows(void* g, uint32_t* tx, double* w, double* frac, uint32_t cap) {
+  auto& r = ((GenoState*)g)->call.weights_rows;
+  for (uint32_t i = 0; i < r.size() && i < cap; i++) { tx[i] = std::get<0>(r[i]); w[i] = std::get<1>(r[i]); frac[i] = std::get<2>(r[i]); }
+  return r.size();
+}
+uint32_t orc_geno_pairs_rows(void* g, uint32_t* a, uint32_t* b, double* frac, uint32_t cap) {
+  auto& r = ((GenoState*)g)->call.pairs_rows;
+  for (uint32_t i = 0; i < r.size() && i < cap; i++) { a[i] = std::get<0>(r[i]); b[i] = std::get<1>(r[i]); frac[i] = std::get<2>(r[i]); }
+  return r.size();
+}
+
+// allele parser KATs (hla.rs:272-316)
+int orc_parse_allele(const char* s, char* gene, uint32_t gene_cap, int32_t* f) {
+  Allele a; if (!parse_allele(s, a)) return 0;
+  strncpy(gene, a.gene.c_str(), gene_cap - 1); gene[gene_cap - 1] = 0;
+  f[0] = a.f1; f[1] = a.f2; f[2] = a.f3; f[3] = a.f4;
+  return 1;
+}
+
+}  // extern "C"
