@@ -1,0 +1,211 @@
+/* hlacount.h — C ABI of the B200-native scHLAcount quantification hot path.
+ *
+ * The reference (10XGenomics/scHLAcount, Rust) has no FFI; the seam this library drops into is the set of
+ * functions src/main.rs imports from src/mapping.rs and src/em.rs (main.rs:40-47):
+ *     mapping_wrapper        src/mapping.rs:310-405   (genotyping pseudoalignment -> EqClassDb)
+ *     map_and_count_pseudo   src/mapping.rs:640-821   (4-way pseudoalignment + count())
+ *     em_wrapper             src/em.rs:339-476        (eq_class_counts + squarem + caller)
+ * and, below them, the un-vendored debruijn_mapping calls they make (Pseudoaligner::map_read, build_index,
+ * utils::read_obj). Each entry point cites the reference interface it replaces. INTEGRATION.md shows the Rust
+ * `extern "C"` block + build.rs a maintainer would add.
+ *
+ * Conventions: every function returns 0 on success and a negative hlac_status on failure; hlac_last_error()
+ * returns a thread-local message. Handles are opaque. One session = one CUDA device + one stream; sessions are
+ * not thread-safe. There is NO CPU fallback: every compute entry point fails with HLAC_ERR_CUDA when no device
+ * is usable.
+ */
+#ifndef HLACOUNT_H_
+#define HLACOUNT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  HLAC_OK = 0,
+  HLAC_ERR_ARG = -1,
+  HLAC_ERR_IO = -2,
+  HLAC_ERR_FORMAT = -3,
+  HLAC_ERR_CUDA = -4,
+  HLAC_ERR_STATE = -5,
+  HLAC_ERR_LIMIT = -6
+} hlac_status;
+
+#define HLAC_NOT_A_CELL 0xFFFFFFFFu /* batch.cell value for "CB not in the barcode list" (mapping.rs:760-763) */
+#define HLAC_FLAG_PRIMARY 0x1u      /* batch.flags bit 0: !(secondary||supplementary) (mapping.rs:247-249)  */
+#define HLAC_CODE_NONE 0xFFu        /* per-read debug code: read not scored                                 */
+#define HLAC_K 24                   /* debruijn_mapping::config::KmerType = Kmer24 (pinned by the .idx)     */
+
+typedef struct hlac_index hlac_index; /* a Pseudoaligner<KmerType> resident on one device (mapping.rs:318)   */
+typedef struct hlac_count hlac_count; /* one map_and_count_pseudo run (mapping.rs:640-821)                   */
+typedef struct hlac_geno hlac_geno;   /* one mapping_wrapper run + its EqClassDb (mapping.rs:310-405)        */
+
+/* A batch of BamCrRead records (mapping.rs:64-75) in structure-of-arrays form. BAM decoding, region / CB / UB
+ * handling stay on the host (mapping.rs:231-279); this is what crosses to the GPU.
+ *   seq    n*words_per_read u64; read i = words [i*wpr, (i+1)*wpr). 2-bit codes A0 C1 G2 T3, base j of a read in
+ *          word j/32 at bits 63-2*(j%32)..62-2*(j%32) (same layout as debruijn::DnaString storage); anything that
+ *          is not ACGT is packed as A (DnaString::from_acgt_bytes). Bits beyond len must be zero.
+ *   len    read length in bases (<= 32*words_per_read)
+ *   cell   counting: matrix column (load_barcodes line index, main.rs:412-416) or HLAC_NOT_A_CELL;
+ *          genotyping: any injective barcode id
+ *   umi    any injective u32 key of the UB string (hlac_umi_key gives the packer the host driver uses)
+ *   flags  HLAC_FLAG_PRIMARY
+ * For hlac_*_push the pointers are HOST memory (pinned via hlac_host_alloc for full-speed copies); for
+ * hlac_*_push_device they are DEVICE pointers on the session's device. */
+typedef struct {
+  const uint64_t* seq;
+  const uint16_t* len;
+  const uint32_t* cell;
+  const uint32_t* umi;
+  const uint8_t* flags;
+  uint64_t n;
+  uint32_t words_per_read;
+} hlac_batch;
+
+typedef struct { /* mapping.rs:108-116 `Metrics` */
+  uint64_t num_reads, num_non_primary, num_not_cell_bc, num_cds_align, num_gen_align, num_not_aligned;
+} hlac_metrics;
+
+typedef struct { /* Vec<MatrixEntry> (mapping.rs:101-106), cells ascending then rows ascending (mapping.rs:897-906) */
+  uint32_t* row;
+  uint32_t* col;
+  uint32_t* val;
+  uint64_t n;
+  uint32_t nrows; /* matrix rows (mapping.rs:681-727) */
+} hlac_coo;
+
+typedef struct {
+  uint32_t n_nodes, n_tx, n_colours, lmer;
+  uint64_t n_bases, n_kmers, dict_slots, bitmap_bytes;
+} hlac_index_info;
+
+/* EqClassCounts + reads_explained (em.rs:19-25, mapping.rs:169-228). Classes are CSR over tx ids.
+ * `reads_*` = counts_reads (keys are the raw, possibly permuted read-level vectors), `umi_*` = counts_umi. */
+typedef struct {
+  uint32_t nitems;
+  uint32_t nreads;
+  uint64_t n_read_classes;
+  uint64_t* reads_off;
+  uint32_t* reads_tx;
+  uint32_t* reads_cnt;
+  uint64_t n_umi_classes;
+  uint64_t* umi_off;
+  uint32_t* umi_tx;
+  uint32_t* umi_cnt;
+  uint64_t* reads_explained; /* [nitems] */
+} hlac_class_tables;
+
+const char* hlac_last_error(void);
+int hlac_device_count(int* n);
+
+/* ---- index (replaces utils::read_obj(&hla_index), mapping.rs:318 / em.rs:346, and build_index, mapping.rs:652-662,
+ * hla.rs:258) ------------------------------------------------------------------------------------------------ */
+/* device = CUDA ordinal, or -1 for a host-only handle that supports inspection (hlac_index_get_info/_node/_tx_name)
+ * but is rejected by every compute entry point. */
+int hlac_index_from_idx_file(const char* path, int device, hlac_index** out); /* bincode Pseudoaligner<Kmer24> */
+/* read_hla_cds (hla.rs:102-209) + build_index. allele_status == NULL: counting mode (use_filter = false,
+ * mapping.rs:650,657); otherwise make_hla_index's filter (hla.rs:236-256). */
+int hlac_index_from_fasta(const char* fasta_path, const char* allele_status, int device, hlac_index** out);
+/* build_index::<Kmer24>(&seqs, &tx_names, _) on already-packed sequences (same 2-bit layout as hlac_batch.seq,
+ * sequence i starts at word seq_word_start[i]); names are NUL-terminated. */
+int hlac_index_from_sequences(const uint64_t* packed, const uint64_t* seq_word_start, const uint32_t* seq_len,
+                              const char* const* names, uint32_t n_seq, int device, hlac_index** out);
+int hlac_index_free(hlac_index*);
+int hlac_index_get_info(const hlac_index*, hlac_index_info* out);
+const char* hlac_index_tx_name(const hlac_index*, uint32_t i); /* Pseudoaligner.tx_names[i] */
+/* node export (parity checks against the .idx fixture): ASCII sequence, ext byte (high nibble right), colour list */
+int hlac_index_node(const hlac_index*, uint32_t node, char* seq, uint32_t seq_cap, uint32_t* len, uint32_t* exts,
+                    uint32_t* colours, uint32_t col_cap, uint32_t* n_col);
+
+/* ---- host-side helpers -------------------------------------------------------------------------------------- */
+int hlac_host_alloc(size_t bytes, void** out); /* pinned host memory for batches */
+int hlac_host_free(void* p);
+/* DnaString::from_acgt_bytes (mapping.rs:252): ASCII -> 2-bit words (nwords >= ceil(len/32)), padding zeroed */
+int hlac_pack_read(const char* ascii, uint32_t len, uint64_t* words, uint32_t nwords);
+/* injective u32 key of a UB string: <=15 ACGT bases -> (1<<2n)|2-bit value; anything else needs interning by the
+ * caller (returns HLAC_ERR_LIMIT) */
+int hlac_umi_key(const char* umi, uint32_t len, uint32_t* key);
+
+/* ---- counting: map_and_count_pseudo (mapping.rs:640-821) + count() (mapping.rs:823-909) ------------------------- */
+int hlac_count_new(hlac_index* cds, hlac_index* genomic, uint32_t n_cells, int primary_only, hlac_count** out);
+int hlac_count_free(hlac_count*);
+uint32_t hlac_count_nrows(const hlac_count*);                  /* nrows (mapping.rs:681) */
+const char* hlac_count_row_name(const hlac_count*, uint32_t i); /* rownames / labels.tsv (mapping.rs:699-725) */
+int hlac_count_reserve(hlac_count*, uint64_t total_reads);      /* optional: pre-size device buffers */
+int hlac_count_push(hlac_count*, const hlac_batch* host_batch); /* the hot loop mapping.rs:740-807, async */
+int hlac_count_push_device(hlac_count*, const hlac_batch* device_batch);
+int hlac_count_sync(hlac_count*);                               /* host batch buffers reusable after this */
+/* debug/parity: record per-read results (off by default), then fetch those of the LAST pushed batch:
+ * code = gene*3+slot or HLAC_CODE_NONE */
+int hlac_count_record_codes(hlac_count*, int on);
+int hlac_count_last_codes(hlac_count*, uint8_t* codes, uint64_t n);
+/* seed-filter counters since the last reset: l-mer bitmap tests and exact dictionary probes */
+int hlac_count_probe_stats(hlac_count*, uint64_t* bitmap_tests, uint64_t* dict_probes);
+/* count(): UMI consensus into the dense u32 [n_cells][nrows] matrix on the device; returns its device pointer so a
+ * caller sharding reads by barcode can all-reduce it (NCCL) before extracting entries. */
+int hlac_count_reduce(hlac_count*, uint32_t** dense_device, uint64_t* n_elems);
+int hlac_count_entries(hlac_count*, hlac_coo* out, hlac_metrics* metrics); /* after reduce (and optional all-reduce) */
+int hlac_count_finish(hlac_count*, hlac_coo* out, hlac_metrics* metrics);  /* reduce + entries */
+int hlac_count_reset(hlac_count*);                              /* drop accumulated reads, keep buffers */
+int hlac_coo_free(hlac_coo*);
+/* kernel timing of the session since the last reset, measured with CUDA events on the session stream:
+ * ms[0] = map kernel(s), ms[1] = sort, ms[2] = consensus, ms[3] = H2D copies. launches = kernels launched. */
+int hlac_count_timing(hlac_count*, float ms[4], uint64_t* launches);
+
+/* ---- genotyping: mapping_wrapper (mapping.rs:310-405) + em_wrapper's numeric half (em.rs:358-434) ---------------- */
+int hlac_geno_new(hlac_index* idx, hlac_geno** out);
+int hlac_geno_free(hlac_geno*);
+/* forward_only = the --unmapped pass (mapping.rs:380-393). Batches must be pushed in BAM order: class ids are
+ * first-seen ids (mapping.rs:147-154). */
+int hlac_geno_push(hlac_geno*, const hlac_batch* host_batch, int forward_only);
+int hlac_geno_push_device(hlac_geno*, const hlac_batch* device_batch, int forward_only);
+/* debug/parity for the LAST pushed batch: coverage (0 = None) and counted flag (cov > MIN_SCORE_CALL) */
+int hlac_geno_last_cov(hlac_geno*, uint32_t* cov, uint64_t n);
+/* EqClassDb::eq_class_counts (mapping.rs:169-228). Caller frees with hlac_class_tables_free. After this,
+ * hlac_geno_read_class_ids returns, for every read pushed so far, its first-seen eq_class_id or 0xFFFFFFFF. */
+int hlac_geno_finish(hlac_geno*, hlac_class_tables* out);
+int hlac_geno_read_class_ids(hlac_geno*, uint32_t* ids, uint64_t n);
+int hlac_class_tables_free(hlac_class_tables*);
+int hlac_geno_timing(hlac_geno*, float ms[4], uint64_t* launches);
+
+/* squarem(&eq_class_counts) (em.rs:232-311) on the device, f64. */
+int hlac_squarem(const hlac_class_tables* t, int device, double* theta_out, uint32_t* iters_out);
+/* the caller (em.rs:361-434): called tx ids ascending; weights.tsv / pairs.tsv rows in file order. */
+typedef struct {
+  uint32_t n_called;
+  uint32_t* called;
+  uint32_t n_weights;
+  uint32_t* w_tx;
+  double* w_em;
+  double* w_frac;
+  uint32_t n_pairs;
+  uint32_t* p_a;
+  uint32_t* p_b;
+  double* p_frac;
+} hlac_calls;
+int hlac_call_genotypes(const hlac_index* idx, const hlac_class_tables* t, const double* theta, hlac_calls* out);
+int hlac_calls_free(hlac_calls*);
+
+/* ---- the three reference entry points, whole (host driver in C++; BAM/FASTA I/O on the host) ---------------------- */
+/* mapping_wrapper(hla_index, outdir, bam, locus, use_unmapped) -> counts file path (mapping.rs:310-316).
+ * region: samtools-style "chr:start-end" or NULL. */
+int hlac_mapping_wrapper(const char* hla_index, const char* outdir, const char* bam, const char* region,
+                         int use_unmapped, int device, char* counts_path_out, size_t cap);
+/* em_wrapper(hla_index, hla_counts, cds_db, gen_db, outdir) -> (genomic, cds) paths (em.rs:339-345,475) */
+int hlac_em_wrapper(const char* hla_index, const char* hla_counts, const char* cds_db, const char* gen_db,
+                    const char* outdir, int device, char* gen_path_out, char* cds_path_out, size_t cap);
+/* map_and_count_pseudo(bam, out_dir, barcodes, locus, cds, genomic, primary_only) (mapping.rs:640-648);
+ * barcodes_path is the --cell-barcodes file (load_barcodes, main.rs:406-424). Writes labels.tsv into out_dir. */
+int hlac_map_and_count_pseudo(const char* bam, const char* out_dir, const char* barcodes_path, const char* region,
+                              const char* cds, const char* genomic, int primary_only, int device, hlac_coo* entries,
+                              hlac_metrics* metrics, uint32_t* n_cells_out);
+/* sc_hla_count's _main (main.rs:151-298): argv as the CLI takes it. */
+int hlac_main(int argc, const char* const* argv);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HLACOUNT_H_ */

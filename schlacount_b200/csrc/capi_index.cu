@@ -1,0 +1,145 @@
+// C ABI: error state, index construction, host helpers (include/hlacount.h). Product code.
+#include <cstring>
+#include <memory>
+
+#include "device_index.hpp"
+#include "hla_fasta.hpp"
+
+using namespace hlac;
+
+namespace hlac {
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& m) { g_last_error = m; }
+}  // namespace hlac
+
+#define HLAC_API_BEGIN try {
+#define HLAC_API_END                                                                         \
+  }                                                                                          \
+  catch (const hlac::Error& e) { hlac::set_last_error(e.what()); return e.code; }           \
+  catch (const std::exception& e) { hlac::set_last_error(e.what()); return HLAC_ERR_STATE; } \
+  return HLAC_OK;
+
+extern "C" {
+
+const char* hlac_last_error(void) { return g_last_error.c_str(); }
+
+int hlac_device_count(int* n) {
+  HLAC_API_BEGIN
+  if (!n) throw Error(HLAC_ERR_ARG, "null argument");
+  int c = 0;
+  if (cudaGetDeviceCount(&c) != cudaSuccess) c = 0;
+  *n = c;
+  HLAC_API_END
+}
+
+int hlac_index_from_idx_file(const char* path, int device, hlac_index** out) {
+  HLAC_API_BEGIN
+  if (!path || !out) throw Error(HLAC_ERR_ARG, "null argument");
+  auto ix = std::make_unique<hlac_index>();
+  HostIndex::load_idx(path, ix->host);
+  ix->upload(device);
+  *out = ix.release();
+  HLAC_API_END
+}
+
+int hlac_index_from_fasta(const char* fasta_path, const char* allele_status, int device, hlac_index** out) {
+  HLAC_API_BEGIN
+  if (!fasta_path || !out) throw Error(HLAC_ERR_ARG, "null argument");
+  std::set<std::string> keep;
+  if (allele_status) keep = load_allele_status(allele_status);
+  std::vector<Bases> seqs; std::vector<std::string> names;
+  read_hla_cds(fasta_path, keep, allele_status != nullptr, seqs, names);
+  auto ix = std::make_unique<hlac_index>();
+  HostIndex::build(seqs, names, ix->host);
+  ix->upload(device);
+  *out = ix.release();
+  HLAC_API_END
+}
+
+int hlac_index_from_sequences(const uint64_t* packed, const uint64_t* seq_word_start, const uint32_t* seq_len,
+                              const char* const* names, uint32_t n_seq, int device, hlac_index** out) {
+  HLAC_API_BEGIN
+  if (!packed || !seq_word_start || !seq_len || !names || !out) throw Error(HLAC_ERR_ARG, "null argument");
+  std::vector<Bases> seqs(n_seq); std::vector<std::string> nm(n_seq);
+  for (uint32_t i = 0; i < n_seq; i++) {
+    seqs[i].resize(seq_len[i]);
+    const uint64_t* w = packed + seq_word_start[i];
+    for (uint32_t j = 0; j < seq_len[i]; j++) seqs[i][j] = (w[j >> 5] >> (62 - 2 * (j & 31))) & 3;
+    nm[i] = names[i];
+  }
+  auto ix = std::make_unique<hlac_index>();
+  HostIndex::build(seqs, nm, ix->host);
+  ix->upload(device);
+  *out = ix.release();
+  HLAC_API_END
+}
+
+int hlac_index_free(hlac_index* ix) {
+  if (ix) { if (ix->device >= 0) cudaSetDevice(ix->device); delete ix; }
+  return HLAC_OK;
+}
+
+int hlac_index_get_info(const hlac_index* ix, hlac_index_info* o) {
+  HLAC_API_BEGIN
+  if (!ix || !o) throw Error(HLAC_ERR_ARG, "null argument");
+  o->n_nodes = ix->host.n_nodes(); o->n_tx = (uint32_t)ix->host.tx_names.size(); o->n_colours = ix->host.n_colours();
+  o->lmer = ix->host.lmer; o->n_bases = ix->host.n_bases; o->n_kmers = ix->host.n_kmers;
+  o->dict_slots = 1ull << ix->host.dict_bits; o->bitmap_bytes = ix->host.bitmap.size() * 4;
+  HLAC_API_END
+}
+
+const char* hlac_index_tx_name(const hlac_index* ix, uint32_t i) {
+  return (ix && i < ix->host.tx_names.size()) ? ix->host.tx_names[i].c_str() : nullptr;
+}
+
+int hlac_index_node(const hlac_index* ix, uint32_t node, char* seq, uint32_t seq_cap, uint32_t* len, uint32_t* exts,
+                    uint32_t* colours, uint32_t col_cap, uint32_t* n_col) {
+  HLAC_API_BEGIN
+  if (!ix || node >= ix->host.n_nodes()) throw Error(HLAC_ERR_ARG, "bad node");
+  const HostIndex& h = ix->host;
+  if (len) *len = h.len[node];
+  if (exts) *exts = h.exts[node];
+  if (seq) for (uint32_t i = 0; i < h.len[node] && i < seq_cap; i++) seq[i] = "ACGT"[h.base((uint64_t)h.start[node] + i)];
+  const uint64_t a = h.col_off[h.colour[node]], b = h.col_off[h.colour[node] + 1];
+  if (n_col) *n_col = (uint32_t)(b - a);
+  if (colours) for (uint64_t i = a; i < b && i - a < col_cap; i++) colours[i - a] = h.col_tx[i];
+  HLAC_API_END
+}
+
+int hlac_host_alloc(size_t bytes, void** out) {
+  HLAC_API_BEGIN
+  if (!out) throw Error(HLAC_ERR_ARG, "null argument");
+  HLAC_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable));
+  HLAC_API_END
+}
+int hlac_host_free(void* p) {
+  HLAC_API_BEGIN
+  if (p) HLAC_CUDA(cudaFreeHost(p));
+  HLAC_API_END
+}
+
+int hlac_pack_read(const char* ascii, uint32_t len, uint64_t* words, uint32_t nwords) {
+  HLAC_API_BEGIN
+  if (!ascii || !words) throw Error(HLAC_ERR_ARG, "null argument");
+  if ((uint64_t)nwords * 32 < len) throw Error(HLAC_ERR_ARG, "read longer than 32*nwords");
+  memset(words, 0, (size_t)nwords * 8);
+  for (uint32_t i = 0; i < len; i++) words[i >> 5] |= (uint64_t)base_code(ascii[i]) << (62 - 2 * (i & 31));
+  HLAC_API_END
+}
+
+int hlac_umi_key(const char* umi, uint32_t len, uint32_t* key) {
+  HLAC_API_BEGIN
+  if (!umi || !key) throw Error(HLAC_ERR_ARG, "null argument");
+  if (len > 15) throw Error(HLAC_ERR_LIMIT, "UMI longer than 15 bases needs interning");
+  uint32_t v = 1;
+  for (uint32_t i = 0; i < len; i++) {
+    uint32_t c;
+    switch (umi[i]) { case 'A': c = 0; break; case 'C': c = 1; break; case 'G': c = 2; break; case 'T': c = 3; break;
+      default: throw Error(HLAC_ERR_LIMIT, "non-ACGT UMI needs interning"); }
+    v = (v << 2) | c;
+  }
+  *key = v;
+  HLAC_API_END
+}
+
+}  // extern "C"

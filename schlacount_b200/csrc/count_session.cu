@@ -1,0 +1,512 @@
+// Counting session: map_and_count_pseudo's hot loop (src/mapping.rs:740-807) and count() (src/mapping.rs:823-909)
+// on the GPU.
+//
+//   K1  k_count_map     one thread per read: filters (mapping.rs:752-763), lazy 4-way map_read policy
+//                       (mapping.rs:765-793), class -> (gene, slot) (mapping.rs:795-806), emits one packed 64-bit key
+//                       (cell | umi | code) per scored read through a warp-aggregated append.
+//   K3a cub radix sort  keys by (cell, umi)  — the "group by cell then UMI" of mapping.rs:829-841
+//   K3b k_consensus     one thread per (cell, UMI) run: gene majority + allele decision (mapping.rs:843-896)
+//                       accumulated into a dense u32 [n_cells][nrows] matrix.
+//
+// Laziness: the reference evaluates all four map_read calls eagerly but only consumes them through the if/else-if
+// chain at mapping.rs:772-793; map_read is pure, so evaluating a call only when the chain reaches it yields the
+// same `aln` and the same metrics.
+//
+// Class handling: eq_class_to_gene (mapping.rs:679-696) only holds [a1], [a2] and sorted [a1,a2] per gene, and the
+// reference's class is the LAST visited node's colour list permuted by no-truncate merges (mapping.rs:283-308
+// semantics inside the pinned map_read; SURVEY.md finding #2). For a 1-element list the merges are no-ops; for a
+// 2-element sorted list [p,q] they can only ever swap it to [q,p] (which then misses the table), and that happens
+// iff some other visited node's colour contains q but not p. So per colour we precompute `cinfo`: the code it
+// yields as a final class and a per-gene "would swap" mask; the walk ORs the masks.
+#include <cub/device/device_radix_sort.cuh>
+
+#include <algorithm>
+#include <cstring>
+#include <memory>
+#include <vector>
+
+#include "device_index.hpp"
+#include "hla_fasta.hpp"
+
+using namespace hlac;
+
+namespace {
+
+constexpr int MAP_THREADS = 256;
+constexpr uint32_t CODE_NONE5 = 31;   // 5-bit "no code"
+constexpr int CODE_BITS = 5;
+constexpr int UMI_BITS = 32;
+
+struct CountMapArgs {
+  DevIndexView cds, gen;
+  const uint32_t* cinfo_cds;   // per colour of the CDS index
+  const uint32_t* cinfo_gen;   // per colour of the genomic index
+  const uint64_t* seq;
+  const uint16_t* len;
+  const uint32_t* cell;
+  const uint32_t* umi;
+  const uint8_t* flags;
+  uint64_t n;
+  uint32_t wpr;                // u64 words per read
+  uint32_t nw;                 // u32 words per strand row in shared memory (2*wpr + 2)
+  uint32_t row_stride;         // u32 words per thread (both strands, odd)
+  int primary_only;
+  uint64_t* keys;
+  unsigned long long* cursor;  // number of keys appended so far
+  unsigned long long* metrics; // [6] + [2] seed-filter tests / dictionary probes
+  uint8_t* codes;              // optional per-read debug output
+};
+
+struct CountVis {
+  const uint32_t* cinfo;
+  uint32_t swap_or = 0, last = CODE_NONE5;
+  __device__ __forceinline__ void visit(uint32_t colour, uint32_t) {
+    const uint32_t ci = __ldg(cinfo + colour);
+    swap_or |= ci >> 8;
+    last = ci;
+  }
+  __device__ __forceinline__ uint32_t code() const {
+    const uint32_t c = last & 31u;
+    if (c == CODE_NONE5) return c;
+    if (c % 3 == 2 && ((swap_or >> (c / 3)) & 1u)) return CODE_NONE5;   // [p,q] was permuted to [q,p]
+    return c;
+  }
+};
+
+struct SharedWords {
+  const uint32_t* p;
+  __device__ __forceinline__ uint32_t operator[](int i) const { return p[i]; }
+};
+struct BitmapShared {
+  const uint32_t* p;
+  __device__ __forceinline__ uint32_t operator()(uint32_t i) const { return p[i]; }
+};
+struct BitmapGlobal {
+  const uint32_t* p;
+  __device__ __forceinline__ uint32_t operator()(uint32_t i) const { return __ldg(p + i); }
+};
+
+template <bool SMEM_BM>
+__global__ void __launch_bounds__(MAP_THREADS) k_count_map(const CountMapArgs a) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  uint32_t* rows = smem;
+  if (SMEM_BM) {
+    const uint32_t nb = a.cds.bitmap_words + a.gen.bitmap_words;
+    for (uint32_t i = threadIdx.x; i < a.cds.bitmap_words; i += MAP_THREADS) smem[i] = __ldg(a.cds.bitmap + i);
+    for (uint32_t i = threadIdx.x; i < a.gen.bitmap_words; i += MAP_THREADS) smem[a.cds.bitmap_words + i] = __ldg(a.gen.bitmap + i);
+    rows = smem + nb;
+  }
+  uint32_t* fw = rows + threadIdx.x * a.row_stride;
+  uint32_t* rc = fw + a.nw;
+  unsigned long long m_reads = 0, m_nonprim = 0, m_notcell = 0, m_cds = 0, m_gen = 0, m_none = 0;
+  uint32_t n_tests = 0, n_probes = 0;
+  const unsigned lane = threadIdx.x & 31;
+  const uint64_t per_block = MAP_THREADS;
+  for (uint64_t base = (uint64_t)blockIdx.x * per_block; base < a.n; base += (uint64_t)gridDim.x * per_block) {
+    __syncthreads();   // rows of the previous iteration are dead; bitmaps are loaded
+    // coalesced block load of the reads into per-thread rows
+    const uint64_t nread = min((uint64_t)per_block, a.n - base);
+    const uint64_t nwords = nread * a.wpr;
+    for (uint64_t g = threadIdx.x; g < nwords; g += MAP_THREADS) {
+      const uint64_t v = __ldg(a.seq + base * a.wpr + g);
+      const uint32_t t = (uint32_t)(g / a.wpr), w = (uint32_t)(g % a.wpr);
+      uint32_t* r = rows + t * a.row_stride;
+      r[2 * w] = (uint32_t)(v >> 32);
+      r[2 * w + 1] = (uint32_t)v;
+    }
+    fw[2 * a.wpr] = 0; fw[2 * a.wpr + 1] = 0;
+    __syncthreads();
+    const uint64_t i = base + threadIdx.x;
+    uint32_t code = CODE_NONE5;
+    uint64_t key = 0;
+    if (i < a.n) {
+      m_reads++;
+      const bool primary = a.flags[i] & HLAC_FLAG_PRIMARY;
+      const uint32_t cell = a.cell[i];
+      if (!primary) m_nonprim++;
+      if (primary || !a.primary_only) {
+        if (cell == HLAC_NOT_A_CELL) m_notcell++;
+        else {
+          const int L = a.len[i];
+          bool found = false;
+#pragma unroll 1
+          for (int p = 0; p < 4; p++) {   // cds fwd, cds rev, genomic fwd, genomic rev (mapping.rs:772-790)
+            if (p == 1) make_revcomp(SharedWords{fw}, rc, L, (int)a.nw);
+            const DevIndexView& ix = p < 2 ? a.cds : a.gen;
+            CountVis vis{p < 2 ? a.cinfo_cds : a.cinfo_gen};
+            SharedWords rd{(p & 1) ? rc : fw};
+            uint32_t cov = 0;
+            if (SMEM_BM) found = map_read_walk(ix, rd, BitmapShared{smem + (p < 2 ? 0 : a.cds.bitmap_words)}, L, vis, cov, n_tests, n_probes);
+            else found = map_read_walk(ix, rd, BitmapGlobal{ix.bitmap}, L, vis, cov, n_tests, n_probes);
+            if (found) {
+              const bool good = cov > MIN_SCORE_COUNT_PSEUDO;
+              if (good) { if (p < 2) m_cds++; else m_gen++; }
+              if (p == 0 || good) code = vis.code();   // a CDS-forward hit is used whatever its coverage (mapping.rs:772-775)
+              break;
+            }
+          }
+          if (!found) m_none++;
+          if (code != CODE_NONE5) key = ((uint64_t)cell << (UMI_BITS + CODE_BITS)) | ((uint64_t)a.umi[i] << CODE_BITS) | code;
+        }
+      }
+      if (a.codes) a.codes[i] = code == CODE_NONE5 ? (uint8_t)HLAC_CODE_NONE : (uint8_t)code;
+    }
+    // warp-aggregated append of the scored reads' keys
+    __syncwarp();
+    const unsigned ballot = __ballot_sync(0xFFFFFFFFu, code != CODE_NONE5);
+    if (ballot) {
+      unsigned long long at = 0;
+      if (lane == 0) at = atomicAdd(a.cursor, (unsigned long long)__popc(ballot));
+      at = __shfl_sync(0xFFFFFFFFu, at, 0);
+      if (code != CODE_NONE5) a.keys[at + __popc(ballot & ((1u << lane) - 1))] = key;
+    }
+  }
+  // metrics: warp reduce then one atomic per counter per warp
+  unsigned long long m[8] = {m_reads, m_nonprim, m_notcell, m_cds, m_gen, m_none, n_tests, n_probes};
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    unsigned long long v = m[k];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, o);
+    if (lane == 0 && v) atomicAdd(a.metrics + k, v);
+  }
+}
+
+// count() (mapping.rs:842-896) for one (cell, UMI) run of the sorted keys.
+__global__ void k_consensus(const uint64_t* __restrict__ keys, uint64_t n, uint32_t* __restrict__ dense, uint32_t nrows,
+                            const uint32_t* __restrict__ gene_row0) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t k0 = keys[i], grp = k0 >> CODE_BITS;
+  if (i > 0 && (keys[i - 1] >> CODE_BITS) == grp) return;   // not a run head
+  // pass 1: majority-vote candidate gene (only a gene with > 50 % of the UMI's reads can win, mapping.rs:874-875)
+  uint32_t cand = 0, votes = 0, nreads = 0;
+  for (uint64_t j = i; j < n; j++) {
+    const uint64_t k = keys[j];
+    if ((k >> CODE_BITS) != grp) break;
+    const uint32_t g = (uint32_t)(k & 31u) / 3;
+    if (votes == 0) { cand = g; votes = 1; }
+    else if (g == cand) votes++;
+    else votes--;
+    nreads++;
+  }
+  // pass 2: the candidate's (allele 1, allele 2, gene) counts
+  uint32_t f[3] = {0, 0, 0};
+  for (uint64_t j = i; j < i + nreads; j++) {
+    const uint32_t c = (uint32_t)(keys[j] & 31u);
+    if (c / 3 == cand) f[c % 3]++;
+  }
+  const double nr = (double)nreads;
+  const uint32_t ng = f[0] + f[1] + f[2];
+  if (!((double)ng > GENE_CONSENSUS_THRESHOLD * nr)) return;
+  uint32_t slot;
+  if ((double)f[0] > ALLELE_CONSENSUS_THRESHOLD * nr && ALLELE_CONSENSUS_THRESHOLD * nr > (double)f[1]) slot = 0;
+  else if ((double)f[1] > ALLELE_CONSENSUS_THRESHOLD * nr && ALLELE_CONSENSUS_THRESHOLD * nr > (double)f[0]) slot = 1;
+  else slot = 2;
+  const uint32_t cell = (uint32_t)(k0 >> (UMI_BITS + CODE_BITS));
+  atomicAdd(dense + (size_t)cell * nrows + gene_row0[cand] + slot, 1u);
+}
+
+// per-colour info word for the counting kernel: bits 0-4 code (gene*3+slot or 31), bits 8-15 per-gene swap mask
+std::vector<uint32_t> make_cinfo(const HostIndex& ix, const RowLayout& rows) {
+  std::vector<uint32_t> out(ix.n_colours());
+  for (uint32_t c = 0; c < ix.n_colours(); c++) {
+    const uint32_t* tx = &ix.col_tx[ix.col_off[c]];
+    const size_t n = ix.col_off[c + 1] - ix.col_off[c];
+    auto has = [&](uint32_t t) { return std::binary_search(tx, tx + n, t); };
+    uint32_t code = CODE_NONE5, swap = 0;
+    for (uint32_t g = 0; g < rows.n_genes; g++) {
+      const uint32_t a1 = rows.a1[g], a2 = rows.a2[g];
+      if (n == 1 && tx[0] == a1) code = g * 3 + 0;
+      if (a2 != NONE32) {
+        if (n == 1 && tx[0] == a2) code = g * 3 + 1;
+        const uint32_t lo = std::min(a1, a2), hi = std::max(a1, a2);
+        if (n == 2 && tx[0] == lo && tx[1] == hi) code = g * 3 + 2;
+        if (has(hi) && !has(lo)) swap |= 1u << g;
+      }
+    }
+    out[c] = code | (swap << 8);
+  }
+  return out;
+}
+
+}  // namespace
+
+struct hlac_count {
+  hlac_index* cds = nullptr;
+  hlac_index* gen = nullptr;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  RowLayout rows;
+  uint32_t n_cells = 0;
+  int primary_only = 0;
+  DevBuf<uint32_t> cinfo_cds, cinfo_gen, gene_row0, dense;
+  DevBuf<uint64_t> keys, keys_sorted, st_seq;
+  DevBuf<uint16_t> st_len;
+  DevBuf<uint32_t> st_cell, st_umi;
+  DevBuf<uint8_t> st_flags, codes;
+  DevBuf<unsigned long long> counters;   // [0] cursor, [1..8] metrics
+  DevBuf<uint8_t> cub_tmp;
+  uint64_t reads_pushed = 0, last_n = 0;
+  bool smem_bm = false;
+  size_t bitmap_smem_bytes = 0;
+  int blocks_per_sm = 1, n_sm = 1;
+  bool want_codes = false;
+  bool reduced = false;
+  uint64_t n_keys = 0;
+  // timing
+  struct Ev { cudaEvent_t a, b; int kind; };
+  std::vector<Ev> events;
+  float ms[4] = {0, 0, 0, 0};
+  uint64_t launches = 0;
+
+  ~hlac_count() {
+    for (auto& e : events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    if (stream) cudaStreamDestroy(stream);
+  }
+  Ev& begin(int kind) {
+    Ev e; e.kind = kind;
+    HLAC_CUDA(cudaEventCreate(&e.a)); HLAC_CUDA(cudaEventCreate(&e.b));
+    HLAC_CUDA(cudaEventRecord(e.a, stream));
+    events.push_back(e);
+    return events.back();
+  }
+  void end(Ev& e) { HLAC_CUDA(cudaEventRecord(e.b, stream)); }
+  void drain_events() {
+    for (auto& e : events) {
+      float t = 0; HLAC_CUDA(cudaEventSynchronize(e.b)); HLAC_CUDA(cudaEventElapsedTime(&t, e.a, e.b));
+      ms[e.kind] += t; cudaEventDestroy(e.a); cudaEventDestroy(e.b);
+    }
+    events.clear();
+  }
+  void reset() {
+    HLAC_CUDA(cudaMemsetAsync(counters.p, 0, 9 * sizeof(unsigned long long), stream));
+    reads_pushed = 0; last_n = 0; reduced = false; n_keys = 0;
+    drain_events(); ms[0] = ms[1] = ms[2] = ms[3] = 0; launches = 0;
+  }
+
+  void launch_map(const hlac_batch& b /* device pointers */) {
+    if (b.n == 0) return;
+    if (b.words_per_read == 0 || b.words_per_read > 16) throw Error(HLAC_ERR_ARG, "words_per_read must be 1..16");
+    keys.reserve(reads_pushed + b.n, stream, true, reads_pushed);
+    if (want_codes) codes.reserve(b.n, stream);
+    CountMapArgs a{};
+    a.cds = cds->view; a.gen = gen->view;
+    a.cinfo_cds = cinfo_cds.p; a.cinfo_gen = cinfo_gen.p;
+    a.seq = b.seq; a.len = b.len; a.cell = b.cell; a.umi = b.umi; a.flags = b.flags;
+    a.n = b.n; a.wpr = b.words_per_read; a.nw = 2 * b.words_per_read + 2; a.row_stride = (2 * a.nw) | 1;
+    a.primary_only = primary_only;
+    a.keys = keys.p; a.cursor = counters.p; a.metrics = counters.p + 1;
+    a.codes = want_codes ? codes.p : nullptr;
+    const size_t smem = (smem_bm ? bitmap_smem_bytes : 0) + (size_t)MAP_THREADS * a.row_stride * 4;
+    auto kern = smem_bm ? k_count_map<true> : k_count_map<false>;
+    HLAC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    HLAC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, MAP_THREADS, smem));
+    if (occ < 1) throw Error(HLAC_ERR_LIMIT, "count map kernel does not fit on the device");
+    const uint64_t need = (b.n + MAP_THREADS - 1) / MAP_THREADS;
+    const unsigned grid = (unsigned)std::min<uint64_t>(need, (uint64_t)n_sm * occ);
+    Ev& e = begin(0);
+    kern<<<grid, MAP_THREADS, smem, stream>>>(a);
+    HLAC_CUDA(cudaGetLastError());
+    end(e);
+    launches++;
+    reads_pushed += b.n; last_n = b.n; reduced = false;
+  }
+};
+
+extern "C" {
+
+int hlac_count_new(hlac_index* cds, hlac_index* genomic, uint32_t n_cells, int primary_only, hlac_count** out) try {
+  if (!cds || !genomic || !out) throw Error(HLAC_ERR_ARG, "null argument");
+  if (cds->device < 0 || genomic->device < 0) throw Error(HLAC_ERR_CUDA, "index is host-only (device -1): counting needs a CUDA device, there is no CPU fallback");
+  if (cds->device != genomic->device) throw Error(HLAC_ERR_ARG, "CDS and genomic index live on different devices");
+  if (n_cells == 0 || n_cells >= (1u << 27)) throw Error(HLAC_ERR_LIMIT, "n_cells must be in 1..2^27-1");
+  auto s = std::make_unique<hlac_count>();
+  s->cds = cds; s->gen = genomic; s->device = cds->device; s->n_cells = n_cells; s->primary_only = primary_only;
+  DeviceGuard g(s->device);
+  s->rows = build_row_layout(cds->host.tx_names);
+  if (s->rows.n_genes > 8) throw Error(HLAC_ERR_LIMIT, "more than 8 genes in the CDS FASTA");
+  HLAC_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+  auto ci = make_cinfo(cds->host, s->rows); s->cinfo_cds.upload(ci.data(), ci.size(), s->stream);
+  auto gi = make_cinfo(genomic->host, s->rows); s->cinfo_gen.upload(gi.data(), gi.size(), s->stream);
+  std::vector<uint32_t> r0 = s->rows.gene_row0; r0.resize(8, 0);
+  s->gene_row0.upload(r0.data(), r0.size(), s->stream);
+  s->counters.reserve(16, s->stream);
+  HLAC_CUDA(cudaMemsetAsync(s->counters.p, 0, 16 * sizeof(unsigned long long), s->stream));
+  s->dense.reserve((size_t)n_cells * std::max<uint32_t>(s->rows.nrows, 1), s->stream);
+  cudaDeviceProp prop; HLAC_CUDA(cudaGetDeviceProperties(&prop, s->device));
+  s->n_sm = prop.multiProcessorCount;
+  s->bitmap_smem_bytes = ((size_t)cds->view.bitmap_words + genomic->view.bitmap_words) * 4;
+  s->smem_bm = s->bitmap_smem_bytes <= 96 * 1024;
+  HLAC_CUDA(cudaStreamSynchronize(s->stream));
+  *out = s.release();
+  return HLAC_OK;
+} catch (const Error& e) { set_last_error(e.what()); return e.code; } catch (const std::exception& e) { set_last_error(e.what()); return HLAC_ERR_STATE; }
+
+int hlac_count_free(hlac_count* s) {
+  if (s) { cudaSetDevice(s->device); delete s; }
+  return HLAC_OK;
+}
+uint32_t hlac_count_nrows(const hlac_count* s) { return s ? s->rows.nrows : 0; }
+const char* hlac_count_row_name(const hlac_count* s, uint32_t i) { return (s && i < s->rows.rownames.size()) ? s->rows.rownames[i].c_str() : nullptr; }
+
+int hlac_count_reserve(hlac_count* s, uint64_t total_reads) try {
+  if (!s) throw Error(HLAC_ERR_ARG, "null session");
+  DeviceGuard g(s->device);
+  s->keys.reserve(total_reads, s->stream, true, s->reads_pushed);
+  s->keys_sorted.reserve(total_reads, s->stream);
+  return HLAC_OK;
+} catch (const Error& e) { set_last_error(e.what()); return e.code; }
+
+int hlac_count_push_device(hlac_count* s, const hlac_batch* b) try {
+  if (!s || !b) throw Error(HLAC_ERR_ARG, "null argument");
+  DeviceGuard g(s->device);
+  s->launch_map(*b);
+  return HLAC_OK;
+} catch (const Error& e) { set_last_error(e.what()); return e.code; }
+
+int hlac_count_push(hlac_count* s, const hlac_batch* b) try {
+  if (!s || !b) throw Error(HLAC_ERR_ARG, "null argument");
+  if (b->n == 0) return HLAC_OK;
+  DeviceGuard g(s->device);
+  auto& e = s->begin(3);
+  s->st_seq.upload(b->seq, b->n * b->words_per_read, s->stream);
+  s->st_len.upload(b->len, b->n, s->stream);
+  s->st_cell.upload(b->cell, b->n, s->stream);
+  s->st_umi.upload(b->umi, b->n, s->stream);
+  s->st_flags.upload(b->flags, b->n, s->stream);
+  s->end(e);
+  hlac_batch d = *b;
+  d.seq = s->st_seq.p; d.len = s->st_len.p; d.cell = s->st_cell.p; d.umi = s->st_umi.p; d.flags = s->st_flags.p;
+  s->launch_map(d);
+  return HLAC_OK;
+} catch (const Error& e) { set_last_error(e.what()); return e.code; }
+
+int hlac_count_sync(hlac_count* s) try {
+  if (!s) throw Error(HLAC_ERR_ARG, "null session");
+  DeviceGuard g(s->device);
+  HLAC_CUDA(cudaStreamSynchronize(s->stream));
+  return HLAC_OK;
+} catch (const Error& e) { set_last_error(e.what()); return e.code; }
+
+int hlac_count_record_codes(hlac_count* s, int on) {
+  if (!s) { set_last_error("null session"); return HLAC_ERR_ARG; }
+  s->want_codes = on != 0;
+  return HLAC_OK;
+}
+
+int hlac_count_last_codes(hlac_count* s, uint8_t* codes, uint64_t n) try {
+  if (!s || !codes) throw Error(HLAC_ERR_ARG, "null argument");
+  DeviceGuard g(s->device);
+  if (!s->want_codes) throw Error(HLAC_ERR_STATE, "per-read codes are not being recorded (hlac_count_record_codes)");
+  if (n != s->last_n) throw Error(HLAC_ERR_ARG, "n does not match the last pushed batch");
+  HLAC_CUDA(cudaMemcpyAsync(codes, s->codes.p, n, cudaMemcpyDeviceToHost, s->stream));
+  HLAC_CUDA(cudaStreamSynchronize(s->stream));
+  return HLAC_OK;
+} catch (const Error& e) { set_last_error(e.what()); return e.code; }
+
+int hlac_count_reduce(hlac_count* s, uint32_t** dense_device, uint64_t* n_elems) try {
+  if (!s) throw Error(HLAC_ERR_ARG, "null session");
+  DeviceGuard g(s->device);
+  const size_t nd = (size_t)s->n_cells * std::max<uint32_t>(s->rows.nrows, 1);
+  unsigned long long nk = 0;
+  HLAC_CUDA(cudaMemcpyAsync(&nk, s->counters.p, sizeof nk, cudaMemcpyDeviceToHost, s->stream));
+  HLAC_CUDA(cudaMemsetAsync(s->dense.p, 0, nd * sizeof(uint32_t), s->stream));
+  HLAC_CUDA(cudaStreamSynchronize(s->stream));
+  s->n_keys = nk;
+  if (nk > 0) {
+    s->keys_sorted.reserve(nk, s->stream);
+    int cell_bits = 1;
+    while ((1ull << cell_bits) < s->n_cells) cell_bits++;
+    const int end_bit = CODE_BITS + UMI_BITS + cell_bits;
+    size_t tmp = 0;
+    HLAC_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tmp, s->keys.p, s->keys_sorted.p, (uint64_t)nk, CODE_BITS, end_bit, s->stream));
+    s->cub_tmp.reserve(tmp, s->stream);
+    auto& e1 = s->begin(1);
+    HLAC_CUDA(cub::DeviceRadixSort::SortKeys(s->cub_tmp.p, tmp, s->keys.p, s->keys_sorted.p, (uint64_t)nk, CODE_BITS, end_bit, s->stream));
+    s->end(e1);
+    auto& e2 = s->begin(2);
+    k_consensus<<<(unsigned)((nk + 255) / 256), 256, 0, s->stream>>>(s->keys_sorted.p, nk, s->dense.p, s->rows.nrows, s->gene_row0.p);
+    HLAC_CUDA(cudaGetLastError());
+    s->end(e2);
+    s->launches += 2;   // cub's own sort passes are library kernels; counted as one launch here plus ours
+  }
+  s->reduced = true;
+  if (dense_device) *dense_device = s->dense.p;
+  if (n_elems) *n_elems = nd;
+  HLAC_CUDA(cudaStreamSynchronize(s->stream));
+  return HLAC_OK;
+} catch (const Error& e) { set_last_error(e.what()); return e.code; }
+
+int hlac_count_entries(hlac_count* s, hlac_coo* out, hlac_metrics* metrics) try {
+  if (!s) throw Error(HLAC_ERR_ARG, "null session");
+  if (!s->reduced) throw Error(HLAC_ERR_STATE, "hlac_count_reduce has not run since the last push");
+  DeviceGuard g(s->device);
+  const uint32_t nrows = s->rows.nrows;
+  const size_t nd = (size_t)s->n_cells * std::max<uint32_t>(nrows, 1);
+  std::vector<uint32_t> dense(nd);
+  unsigned long long ctr[9];
+  HLAC_CUDA(cudaMemcpyAsync(dense.data(), s->dense.p, nd * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+  HLAC_CUDA(cudaMemcpyAsync(ctr, s->counters.p, sizeof ctr, cudaMemcpyDeviceToHost, s->stream));
+  HLAC_CUDA(cudaStreamSynchronize(s->stream));
+  if (metrics) {
+    metrics->num_reads = ctr[1]; metrics->num_non_primary = ctr[2]; metrics->num_not_cell_bc = ctr[3];
+    metrics->num_cds_align = ctr[4]; metrics->num_gen_align = ctr[5]; metrics->num_not_aligned = ctr[6];
+  }
+  if (out) {
+    size_t nnz = 0;
+    for (size_t i = 0; i < nd; i++) nnz += dense[i] != 0;
+    out->n = nnz; out->nrows = nrows;
+    out->row = (uint32_t*)malloc(std::max<size_t>(nnz, 1) * 4);
+    out->col = (uint32_t*)malloc(std::max<size_t>(nnz, 1) * 4);
+    out->val = (uint32_t*)malloc(std::max<size_t>(nnz, 1) * 4);
+    size_t k = 0;
+    for (uint32_t c = 0; c < s->n_cells; c++)        // cells ascending, rows ascending (mapping.rs:829-832, 897-906)
+      for (uint32_t r = 0; r < nrows; r++) {
+        const uint32_t v = dense[(size_t)c * nrows + r];
+        if (v) { out->row[k] = r; out->col[k] = c; out->val[k] = v; k++; }
+      }
+  }
+  return HLAC_OK;
+} catch (const Error& e) { set_last_error(e.what()); return e.code; }
+
+int hlac_count_finish(hlac_count* s, hlac_coo* out, hlac_metrics* metrics) {
+  int rc = hlac_count_reduce(s, nullptr, nullptr);
+  if (rc != HLAC_OK) return rc;
+  return hlac_count_entries(s, out, metrics);
+}
+
+int hlac_count_reset(hlac_count* s) try {
+  if (!s) throw Error(HLAC_ERR_ARG, "null session");
+  DeviceGuard g(s->device);
+  s->reset();
+  return HLAC_OK;
+} catch (const Error& e) { set_last_error(e.what()); return e.code; }
+
+int hlac_coo_free(hlac_coo* c) {
+  if (c) { free(c->row); free(c->col); free(c->val); c->row = c->col = c->val = nullptr; c->n = 0; }
+  return HLAC_OK;
+}
+
+int hlac_count_timing(hlac_count* s, float ms[4], uint64_t* launches) try {
+  if (!s) throw Error(HLAC_ERR_ARG, "null session");
+  DeviceGuard g(s->device);
+  s->drain_events();
+  if (ms) for (int i = 0; i < 4; i++) ms[i] = s->ms[i];
+  if (launches) *launches = s->launches;
+  return HLAC_OK;
+} catch (const Error& e) { set_last_error(e.what()); return e.code; }
+
+// seed-filter counters since the last reset: l-mer bitmap tests and dictionary probes (SURVEY.md §8d "probes/read")
+int hlac_count_probe_stats(hlac_count* s, uint64_t* bitmap_tests, uint64_t* dict_probes) try {
+  if (!s) throw Error(HLAC_ERR_ARG, "null session");
+  DeviceGuard g(s->device);
+  unsigned long long c[2];
+  HLAC_CUDA(cudaMemcpyAsync(c, s->counters.p + 7, sizeof c, cudaMemcpyDeviceToHost, s->stream));
+  HLAC_CUDA(cudaStreamSynchronize(s->stream));
+  if (bitmap_tests) *bitmap_tests = c[0];
+  if (dict_probes) *dict_probes = c[1];
+  return HLAC_OK;
+} catch (const Error& e) { set_last_error(e.what()); return e.code; }
+
+}  // extern "C"

@@ -1,0 +1,38 @@
+#include "device_index.hpp"
+
+#include <vector>
+
+using namespace hlac;
+
+void hlac_index::upload(int dev) {
+  if (dev == -1) { device = -1; return; }   // host-only handle: inspection (hlac_index_node/info) but no compute
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    throw Error(HLAC_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+  if (dev < 0 || dev >= ndev) throw Error(HLAC_ERR_ARG, "bad device ordinal");
+  device = dev;
+  DeviceGuard g(dev);
+  const uint32_t nn = host.n_nodes();
+  std::vector<uint32_t> rec((size_t)nn * 12);
+  for (uint32_t i = 0; i < nn; i++) {
+    uint32_t* r = &rec[(size_t)i * 12];
+    r[0] = host.start[i]; r[1] = host.len[i]; r[2] = host.exts[i]; r[3] = host.colour[i];
+    for (int b = 0; b < 4; b++) { r[4 + b] = host.radj[(size_t)i * 4 + b]; r[8 + b] = host.ladj[(size_t)i * 4 + b]; }
+  }
+  seq32.upload(host.seq32.data(), host.seq32.size());
+  dict.upload(host.dict.data(), host.dict.size());
+  nodes.upload(rec.data(), rec.size());
+  bitmap.upload(host.bitmap.data(), host.bitmap.size());
+  col_tx.upload(host.col_tx.data(), host.col_tx.size());
+  col_off.upload(host.col_off.data(), host.col_off.size());
+  HLAC_CUDA(cudaDeviceSynchronize());
+  view.seq32 = seq32.p;
+  view.nodes = reinterpret_cast<const uint4*>(nodes.p);
+  view.dict = reinterpret_cast<const uint4*>(dict.p);
+  view.bitmap = bitmap.p;
+  view.dict_bits = host.dict_bits;
+  view.dict_mask = (1u << host.dict_bits) - 1;
+  view.lmer = host.lmer;
+  view.bitmap_words = (uint32_t)host.bitmap.size();
+  view.n_nodes = nn;
+}

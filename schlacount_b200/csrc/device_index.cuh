@@ -1,0 +1,216 @@
+// Device-side view of a HostIndex and the per-read pseudoalignment walk (the `map_read` kernel body).
+//
+// Replaces [EXT] debruijn_mapping::pseudoaligner::Pseudoaligner::map_read (call sites src/mapping.rs:341,351,383,
+// 765-770; algorithm: SURVEY.md Appendix A). Design (B200-first, not a translation):
+//   * the MPHF + verify lookup becomes an exact open-addressing dictionary of 16-byte slots (one LDG.128 per probe);
+//   * the linear seed scan becomes a skip-scan: an l-mer presence bitmap (shared memory for small indexes, L2 for
+//     large ones) proves "no dictionary k-mer covers this l-mer", which lets the scan jump K-l+1 positions at once.
+//     It is only a necessary-condition filter; every candidate is still verified in the exact dictionary, so the
+//     first hit position is identical to the reference's position-by-position scan (the scan is stateless);
+//   * graph edges are a precomputed adjacency table instead of hashing the extended terminal k-mer;
+//   * base-by-base extension becomes 16-base XOR/popcount chunks with exact "stop at the 3rd mismatch" semantics.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "common.hpp"
+
+namespace hlac {
+
+static_assert(SEED_STRIDE == 1, "the skip-scan seed filter assumes every read position is a seed candidate");
+
+struct DevIndexView {
+  const uint32_t* seq32;     // node sequences, 16 bases per word
+  const uint4* nodes;        // 3 per node: {start, len, exts, colour} {radj[4]} {ladj[4]}
+  const uint4* dict;         // {kmer lo, kmer hi, node, offset}; hi == NONE32: empty
+  const uint32_t* bitmap;    // l-mer presence bits (global copy)
+  uint32_t dict_mask;
+  uint32_t dict_bits;
+  uint32_t lmer;
+  uint32_t bitmap_words;
+  uint32_t n_nodes;
+};
+
+// (w[i] : w[i+1]) << 2*(pos%16), high word: the 16 bases starting at `pos`
+template <typename P>
+__device__ __forceinline__ uint32_t ext16(P w, int pos) {
+  const int i = pos >> 4;
+  return __funnelshift_l(w[i + 1], w[i], (pos & 15) * 2);
+}
+template <typename P>
+__device__ __forceinline__ uint64_t kmer48(P w, int pos) {
+  const int i = pos >> 4, s = (pos & 15) * 2;
+  const uint32_t a = w[i], b = w[i + 1], c = w[i + 2];
+  const uint32_t hi = __funnelshift_l(b, a, s), lo = __funnelshift_l(c, b, s);
+  return (((uint64_t)hi << 32) | lo) >> (64 - 2 * K);
+}
+template <typename P>
+__device__ __forceinline__ uint32_t base_at(P w, int pos) {
+  return (w[pos >> 4] >> (30 - 2 * (pos & 15))) & 3u;
+}
+
+// read-only global words through the non-coherent path
+struct GWords {
+  const uint32_t* p;
+  __device__ __forceinline__ uint32_t operator[](int i) const { return __ldg(p + i); }
+};
+
+__device__ __forceinline__ bool dict_get(const DevIndexView& ix, uint64_t kmer, uint32_t& node, uint32_t& off) {
+  uint32_t h = (uint32_t)((kmer * 0x9E3779B97F4A7C15ULL) >> (64 - ix.dict_bits));
+  const uint32_t lo = (uint32_t)kmer, hi = (uint32_t)(kmer >> 32);
+  for (;;) {
+    const uint4 s = __ldg(ix.dict + h);
+    if (s.y == NONE32) return false;
+    if (s.x == lo && s.y == hi) { node = s.z; off = s.w; return true; }
+    h = (h + 1) & ix.dict_mask;
+  }
+}
+
+// Seed scan: first pos' >= pos (pos' <= last) whose k-mer is in the dictionary. BM(idx) returns one bitmap word.
+template <typename RD, typename BM>
+__device__ __forceinline__ bool find_seed(const DevIndexView& ix, RD rd, BM bm, int& pos, int last, uint32_t& node,
+                                          uint32_t& off, uint32_t& n_tests, uint32_t& n_probes) {
+  const int l = (int)ix.lmer;
+  const int sh = 32 - 2 * l;
+  while (pos <= last) {
+    int o = K - l;
+    bool pass = true;
+    for (;;) {
+      const uint32_t v = ext16(rd, pos + o) >> sh;
+      n_tests++;
+      if (!((bm(v >> 5) >> (v & 31)) & 1u)) { pos += o + 1; pass = false; break; }   // no k-mer can cover this l-mer
+      if (o == 0) break;
+      o = o > l ? o - l : 0;
+    }
+    if (!pass) continue;
+    n_probes++;
+    if (dict_get(ix, kmer48(rd, pos), node, off)) return true;
+    pos += 1;
+  }
+  return false;
+}
+
+// Compare read[rpos .. rpos+m) with node bases [g .. g+m): number of bases consumed before the (ALLOWED+1)-th
+// mismatch (tolerated mismatches count as consumed, the breaking one does not). brk = budget exceeded.
+template <typename RD>
+__device__ __forceinline__ int extend_cmp(RD rd, int rpos, const uint32_t* seq32, uint32_t g, int m, bool& brk) {
+  int matched = 0, snp = 0;
+  brk = false;
+  GWords ns{seq32};
+  while (matched < m) {
+    const int c = min(16, m - matched);
+    uint32_t x = ext16(rd, rpos + matched) ^ ext16(ns, (int)(g + matched));
+    x = (x | (x >> 1)) & 0x55555555u;
+    if (c < 16) x &= ~(0xFFFFFFFFu >> (2 * c));
+    const int pc = __popc(x);
+    if (snp + pc > ALLOWED_MISMATCH) {
+      for (int t = snp; t < ALLOWED_MISMATCH; t++) x &= ~(0x80000000u >> __clz(x));
+      matched += __clz(x) >> 1;
+      brk = true;
+      break;
+    }
+    snp += pc;
+    matched += c;
+  }
+  return matched;
+}
+
+// map_read_to_nodes. V::visit(colour, node) is called for every visited node in the
+// reference's push order (left-extension nodes first, then the forward walk); the last call is the class-defining
+// node. Returns false for None; cov = coverage.
+template <typename RD, typename BM, typename V>
+__device__ __forceinline__ bool map_read_walk(const DevIndexView& ix, RD rd, BM bm, int L, V& vis, uint32_t& cov_out,
+                                              uint32_t& n_tests, uint32_t& n_probes) {
+  if (L < K) return false;
+  const int last = L - K;
+  int pos = 0;
+  int cov = 0;
+  uint32_t node = 0, off = 0;
+  if (!find_seed(ix, rd, bm, pos, last, node, off, n_tests, n_probes)) return false;
+  uint4 n0 = __ldg(ix.nodes + 3 * (size_t)node);
+  // ---- left extension: only when the first seed sits at or beyond floor(0.2*L) ----
+  if (pos >= (L * LEFT_EXTEND_NUM) / LEFT_EXTEND_DEN) {
+    int lp = pos - 1;
+    uint32_t pn = node;
+    uint4 p0 = n0;
+    int po = off > 0 ? (int)off - 1 : 0;
+    GWords ns{ix.seq32};
+    for (;;) {
+      const int m = min(lp + 1, po + 1);
+      int matched = 0, snp = 0;
+      bool brk = false;
+      for (int i = 0; i < m; i++) {
+        if (base_at(ns, (int)p0.x + po - i) != base_at(rd, lp - i)) {
+          if (++snp > ALLOWED_MISMATCH) { brk = true; break; }
+        }
+        matched++;
+      }
+      cov += matched;
+      if (lp + 1 - matched == 0 || brk) break;
+      lp -= matched;
+      const uint32_t b = base_at(rd, lp);
+      const uint4 la = __ldg(ix.nodes + 3 * (size_t)pn + 2);
+      const uint32_t nxt = b == 0 ? la.x : b == 1 ? la.y : b == 2 ? la.z : la.w;
+      if (nxt == NONE32) break;
+      pn = nxt;
+      p0 = __ldg(ix.nodes + 3 * (size_t)pn);
+      po = (int)p0.y - K;
+      vis.visit(p0.w, pn);
+    }
+  }
+  // ---- forward walk ----
+  for (;;) {
+    pos += K;
+    cov += K;
+    vis.visit(n0.w, node);
+    const int ro = (int)off + K;
+    const int m = min(L - pos, (int)n0.y - ro);
+    bool brk;
+    const int matched = extend_cmp(rd, pos, ix.seq32, n0.x + ro, m, brk);
+    cov += matched;
+    pos += matched;
+    if (pos >= L) break;
+    uint32_t nxt = NONE32;
+    if (!brk) {
+      const uint32_t b = base_at(rd, pos);
+      const uint4 ra = __ldg(ix.nodes + 3 * (size_t)node + 1);
+      nxt = b == 0 ? ra.x : b == 1 ? ra.y : b == 2 ? ra.z : ra.w;
+    }
+    if (nxt != NONE32) {
+      node = nxt;
+      off = 0;
+      pos -= K - 1;
+      cov -= K - 1;
+    } else {
+      if (pos > last) break;
+      if (!find_seed(ix, rd, bm, pos, last, node, off, n_tests, n_probes)) break;
+    }
+    n0 = __ldg(ix.nodes + 3 * (size_t)node);
+  }
+  cov_out = (uint32_t)cov;
+  return true;
+}
+
+// 2-bit reverse complement of 16 packed bases
+__device__ __forceinline__ uint32_t revcomp16(uint32_t v) {
+  uint32_t r = __brev(~v);
+  return ((r & 0x55555555u) << 1) | ((r >> 1) & 0x55555555u);
+}
+
+// Fill the reverse-complement row from the forward row (both 16 bases per word, nw words, zero padded).
+// bio::alphabets::dna::revcomp over the packed read (mapping.rs:351-353, 767-768): N was already packed as A.
+template <typename P>
+__device__ __forceinline__ void make_revcomp(P fwd, uint32_t* rc, int L, int nw) {
+  for (int j = 0; j < nw; j++) {
+    const int st = L - 16 * (j + 1);
+    uint32_t out = 0;
+    if (st >= 0) out = revcomp16(ext16(fwd, st));
+    else if (st > -16) {
+      const int nb = 16 + st;                                  // valid bases in this last partial word
+      out = revcomp16(ext16(fwd, 0) >> (2 * (16 - nb))) & ~(0xFFFFFFFFu >> (2 * nb));
+    }
+    rc[j] = out;
+  }
+}
+
+}  // namespace hlac

@@ -1,0 +1,15 @@
+// An index resident on one device: HostIndex + its device buffers (the `hlac_index` handle). Product code.
+#pragma once
+#include "cuda_util.hpp"
+#include "device_index.cuh"
+#include "host_index.hpp"
+
+struct hlac_index {
+  hlac::HostIndex host;
+  int device = 0;
+  hlac::DevBuf<uint32_t> seq32, dict, nodes, bitmap;
+  hlac::DevBuf<uint32_t> col_tx;
+  hlac::DevBuf<uint64_t> col_off;
+  hlac::DevIndexView view{};
+  void upload(int dev);
+};

@@ -1,0 +1,115 @@
+"""GPU parity for the counting path: CUDA kernels (through the C ABI) vs the CPU oracle and the reference golden.
+Replaces map_and_count_pseudo's hot loop + count() (src/mapping.rs:740-909)."""
+import os
+
+import numpy as np
+import pytest
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def sb():
+    import schlacount_b200
+    return schlacount_b200
+
+
+@pytest.fixture(scope="module")
+def abc(sb, orc):
+    cf, gf = os.path.join(H.FIX, "cds_ABC.fa"), os.path.join(H.FIX, "genomic_ABC.fa")
+    return dict(gc=sb.Index.from_fasta(cf), gg=sb.Index.from_fasta(gf), oc=orc.Index.from_fasta(cf),
+                og=orc.Index.from_fasta(gf))
+
+
+def _run_gpu(sb, abc, batch, n_cells, primary_only=False, splits=1):
+    s = sb.CountSession(abc["gc"], abc["gg"], n_cells, primary_only)
+    s.record_codes(True)
+    seq, lens, cell, umi, flags = batch
+    n = len(lens)
+    codes = []
+    bounds = np.linspace(0, n, splits + 1).astype(int)
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        s.push(seq[a:b], lens[a:b], cell[a:b], umi[a:b], flags[a:b])
+        if b > a:
+            codes.append(s.last_codes(b - a))
+    ent, met = s.finish()
+    return ent, met, (np.concatenate(codes) if codes else np.zeros(0, np.uint8)), s
+
+
+def test_golden_allele_fasta_gpu(sb, orc, abc, fixture_reads):
+    """src/main.rs:432-466 through the CUDA path: count matrix == test/test_allele_fasta.mtx, per-read codes == oracle."""
+    bc = H.load_barcodes(os.path.join(H.FIX, "barcodes1.tsv"))
+    batch = H.make_batch(fixture_reads, bc, pack=sb.pack_reads)
+    ent, met, codes, s = _run_gpu(sb, abc, batch, len(bc))
+    nr, nc, gold = H.read_mtx(os.path.join(H.FIX, "test_allele_fasta.mtx"))
+    assert s.nrows == nr and sorted(ent) == gold
+    ref = orc.count_run(abc["oc"], abc["og"], *batch, want_codes=True)
+    assert ent == ref["entries"] and met == ref["metrics"]
+    assert np.array_equal(codes, ref["codes"])
+    assert s.row_names == abc["oc"].rows()
+
+
+def test_fixture_all_barcodes_gpu(sb, orc, abc, fixture_reads):
+    bc = H.load_barcodes(os.path.join(H.FIX, "barcodes7.tsv"))
+    batch = H.make_batch(fixture_reads, bc, pack=sb.pack_reads)
+    for primary_only in (False, True):
+        ent, met, codes, _ = _run_gpu(sb, abc, batch, len(bc), primary_only, splits=3)
+        ref = orc.count_run(abc["oc"], abc["og"], *batch, primary_only=primary_only, want_codes=True)
+        assert ent == ref["entries"] and met == ref["metrics"] and np.array_equal(codes, ref["codes"])
+
+
+@pytest.mark.parametrize("n,cells,seed", [(200_000, 1000, 7), (50_000, 3, 8)])
+def test_synthetic_parity(sb, orc, abc, n, cells, seed):
+    from tools import synth
+    cds, gen = synth.fixture_alleles()
+    r = synth.make_reads(n, [s for _, s in cds], [s for _, s in gen], cells, seed)
+    batch = (r["seq"], r["len"], r["cell"], r["umi"], r["flags"])
+    ent, met, codes, s = _run_gpu(sb, abc, batch, cells, splits=2)
+    ref = orc.count_run(abc["oc"], abc["og"], *batch, want_codes=True)
+    assert np.array_equal(codes, ref["codes"])
+    assert met == ref["metrics"]
+    assert ent == ref["entries"]
+    assert sum(v for _, _, v in ent) > 0
+
+
+def test_edge_cases(sb, orc, abc):
+    """empty batch, reads shorter than K, ragged lengths in one batch, N bases, everything filtered."""
+    cds, gen = __import__("tools.synth", fromlist=["x"]).fixture_alleles()
+    a = cds[0][1]
+    g = gen[3][1]
+    rc = lambda s: s[::-1].translate(str.maketrans("ACGT", "TGCA"))
+    seqs = [a[:23], a[:24], a[100:250], rc(a[300:420]), g[1500:1640], "ACGT" * 30, a[10:101].replace("G", "N", 2),
+            a[500:530] + "T" + a[531:600], "", a[700:760] + g[2000:2040]]
+    reads = [(s, b"AAACCTGAGACCACGA-1" if i % 3 else b"XX", b"ACGTACGTAC" if i % 2 else b"TTTTTTTTTT", i != 4)
+             for i, s in enumerate(seqs)]
+    bc = {b"AAACCTGAGACCACGA-1": 0, b"XX": 1}
+    batch = H.make_batch(reads, bc, pack=sb.pack_reads)
+    assert batch[0].shape[1] == 5
+    ent, met, codes, s = _run_gpu(sb, abc, batch, 2)
+    ref = orc.count_run(abc["oc"], abc["og"], *batch, want_codes=True)
+    assert np.array_equal(codes, ref["codes"]) and met == ref["metrics"] and ent == ref["entries"]
+    # empty session / empty batch
+    s2 = sb.CountSession(abc["gc"], abc["gg"], 2)
+    s2.push(batch[0][:0], batch[1][:0], batch[2][:0], batch[3][:0], batch[4][:0])
+    ent2, met2 = s2.finish()
+    assert ent2 == [] and met2 == [0] * 6
+    # nothing in the barcode list
+    none = (batch[0], batch[1], np.full(len(seqs), H.NOT_A_CELL, np.uint32), batch[3], batch[4])
+    ent3, met3, codes3, _ = _run_gpu(sb, abc, none, 2)
+    assert ent3 == [] and met3[2] == len(seqs) and (codes3 == 255).all()
+
+
+def test_reset_and_repeat(sb, abc, fixture_reads):
+    bc = H.load_barcodes(os.path.join(H.FIX, "barcodes7.tsv"))
+    batch = H.make_batch(fixture_reads, bc, pack=sb.pack_reads)
+    s = sb.CountSession(abc["gc"], abc["gg"], len(bc))
+    s.push(*batch)
+    e1, m1 = s.finish()
+    s.reset()
+    s.push(*batch)
+    e2, m2 = s.finish()
+    assert e1 == e2 and m1 == m2
+    t = s.timing()
+    assert t["launches"] >= 2 and t["map_ms"] > 0
