@@ -134,6 +134,9 @@ int hlac_count_new(hlac_index* cds, hlac_index* genomic, uint32_t n_cells, int p
 int hlac_count_free(hlac_count*);
 uint32_t hlac_count_nrows(const hlac_count*);                  /* nrows (mapping.rs:681) */
 const char* hlac_count_row_name(const hlac_count*, uint32_t i); /* rownames / labels.tsv (mapping.rs:699-725) */
+/* run the session on a caller-owned CUDA stream (cudaStream_t / CUstream passed as void*; NULL = legacy default
+ * stream) so that the caller can time it with its own events and order it against its own work */
+int hlac_count_set_stream(hlac_count*, void* cuda_stream);
 int hlac_count_reserve(hlac_count*, uint64_t total_reads);      /* optional: pre-size device buffers */
 int hlac_count_push(hlac_count*, const hlac_batch* host_batch); /* the hot loop mapping.rs:740-807, async */
 int hlac_count_push_device(hlac_count*, const hlac_batch* device_batch);
@@ -162,8 +165,14 @@ int hlac_geno_free(hlac_geno*);
  * first-seen ids (mapping.rs:147-154). */
 int hlac_geno_push(hlac_geno*, const hlac_batch* host_batch, int forward_only);
 int hlac_geno_push_device(hlac_geno*, const hlac_batch* device_batch, int forward_only);
-/* debug/parity for the LAST pushed batch: coverage (0 = None) and counted flag (cov > MIN_SCORE_CALL) */
+/* debug/parity for the LAST pushed batch: coverage (0 = None) */
 int hlac_geno_last_cov(hlac_geno*, uint32_t* cov, uint64_t n);
+/* keep the path id of every read pushed (4 B/read) so that hlac_geno_read_class_ids works; call before the first push */
+int hlac_geno_record_reads(hlac_geno*, int on);
+/* counters: reads with Some(..) ("some_aln", mapping.rs:342), with cov > MIN_SCORE_CALL ("long_aln", :344), distinct
+ * colour paths interned, seed-filter bitmap tests and dictionary probes */
+int hlac_geno_stats(hlac_geno*, uint64_t* some_aln, uint64_t* long_aln, uint64_t* n_paths, uint64_t* bitmap_tests,
+                    uint64_t* dict_probes);
 /* EqClassDb::eq_class_counts (mapping.rs:169-228). Caller frees with hlac_class_tables_free. After this,
  * hlac_geno_read_class_ids returns, for every read pushed so far, its first-seen eq_class_id or 0xFFFFFFFF. */
 int hlac_geno_finish(hlac_geno*, hlac_class_tables* out);

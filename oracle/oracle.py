@@ -288,6 +288,21 @@ def squarem(nitems, classes):
     return theta, iters.value
 
 
+def squarem_ordered(nitems, keys, counts):
+    """squarem with the classes iterated in exactly the given order (the reference's HashMap order is unspecified)."""
+    off = np.zeros(len(keys) + 1, dtype=np.uint64)
+    tx = []
+    for i, k in enumerate(keys):
+        tx.extend(k)
+        off[i + 1] = len(tx)
+    tx = np.asarray(tx if tx else [0], dtype=np.uint32)
+    cnt = np.asarray(list(counts) if len(keys) else [0], dtype=np.uint32)
+    theta = np.zeros(nitems, dtype=np.float64)
+    iters = C.c_uint32()
+    lib().orc_squarem(nitems, len(keys), _p(off), _p(tx), _p(cnt), _p(theta), C.byref(iters))
+    return theta, iters.value
+
+
 def parse_allele(s):
     gene = C.create_string_buffer(64)
     f = np.zeros(4, dtype=np.int32)

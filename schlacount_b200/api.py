@@ -152,6 +152,9 @@ class CountSession:
     def row_names(self):
         return [lib().hlac_count_row_name(self.h, C.c_uint32(i)).decode() for i in range(self.nrows)]
 
+    def set_stream(self, stream_ptr):
+        check(lib().hlac_count_set_stream(self.h, C.c_void_p(stream_ptr)))
+
     def reserve(self, n):
         check(lib().hlac_count_reserve(self.h, C.c_uint64(n)))
 
@@ -185,9 +188,29 @@ class CountSession:
         coo = _lib.Coo()
         m = _lib.Metrics()
         check(lib().hlac_count_entries(self.h, C.byref(coo), C.byref(m)))
-        ent = [(coo.row[i], coo.col[i], coo.val[i]) for i in range(coo.n)]
+        n = int(coo.n)
+        if n:
+            rows = np.ctypeslib.as_array(coo.row, shape=(n,)).tolist()
+            cols = np.ctypeslib.as_array(coo.col, shape=(n,)).tolist()
+            vals = np.ctypeslib.as_array(coo.val, shape=(n,)).tolist()
+            ent = list(zip(rows, cols, vals))
+        else:
+            ent = []
         lib().hlac_coo_free(C.byref(coo))
         return ent, [getattr(m, k) for k, _ in _lib.Metrics._fields_]
+
+    def entries_arrays(self):
+        """Like entries() but as three numpy arrays (row, col, val) — no Python-object conversion."""
+        coo = _lib.Coo()
+        m = _lib.Metrics()
+        check(lib().hlac_count_entries(self.h, C.byref(coo), C.byref(m)))
+        n = int(coo.n)
+        if n:
+            out = tuple(np.ctypeslib.as_array(p, shape=(n,)).copy() for p in (coo.row, coo.col, coo.val))
+        else:
+            out = tuple(np.zeros(0, np.uint32) for _ in range(3))
+        lib().hlac_coo_free(C.byref(coo))
+        return out, [getattr(m, k) for k, _ in _lib.Metrics._fields_]
 
     def finish(self):
         self.reduce()
@@ -206,3 +229,121 @@ class CountSession:
         a, b = C.c_uint64(), C.c_uint64()
         check(lib().hlac_count_probe_stats(self.h, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+
+def _tables_to_py(t):
+    def csr(n, off, tx, cnt):
+        out = {}
+        for c in range(n):
+            out[tuple(tx[q] for q in range(off[c], off[c + 1]))] = cnt[c]
+        return out
+    reads_list = [(tuple(t.reads_tx[q] for q in range(t.reads_off[c], t.reads_off[c + 1])), t.reads_cnt[c])
+                  for c in range(t.n_read_classes)]
+    return dict(nitems=t.nitems, nreads=t.nreads, reads_classes=reads_list,
+                counts_reads=dict(reads_list), counts_umi=csr(t.n_umi_classes, t.umi_off, t.umi_tx, t.umi_cnt),
+                reads_explained=[t.reads_explained[i] for i in range(t.nitems)])
+
+
+class GenoSession:
+    """hlac_geno: one mapping_wrapper run (src/mapping.rs:310-405) and its EqClassDb."""
+
+    def __init__(self, index, record_reads=False):
+        self.h = C.c_void_p()
+        self.index = index
+        check(lib().hlac_geno_new(index.h, C.byref(self.h)))
+        self.tables = None
+        if record_reads:
+            check(lib().hlac_geno_record_reads(self.h, C.c_int(1)))
+
+    def close(self):
+        if getattr(self, "tables", None) is not None:
+            lib().hlac_class_tables_free(C.byref(self.tables))
+            self.tables = None
+        if getattr(self, "h", None):
+            lib().hlac_geno_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def push(self, seq, lens, cell, umi, forward_only=False):
+        n = len(lens)
+        flags = np.zeros(n, np.uint8) if isinstance(seq, np.ndarray) else None
+        if isinstance(seq, np.ndarray):
+            b, keep = make_batch(seq, lens, cell, umi, flags)
+            check(lib().hlac_geno_push(self.h, C.byref(b), C.c_int(int(forward_only))))
+        else:
+            wpr = seq.numel() // max(n, 1)
+            b = _lib.Batch(_vp(seq), _vp(lens), _vp(cell), _vp(umi), None, n, wpr)
+            check(lib().hlac_geno_push_device(self.h, C.byref(b), C.c_int(int(forward_only))))
+        self._n_last = n
+
+    def last_cov(self):
+        out = np.zeros(self._n_last, dtype=np.uint32)
+        check(lib().hlac_geno_last_cov(self.h, _vp(out), C.c_uint64(self._n_last)))
+        return out
+
+    def finish(self):
+        """-> dict(nitems, nreads, counts_reads, counts_umi, reads_explained, reads_classes [first-seen order])"""
+        if self.tables is not None:
+            lib().hlac_class_tables_free(C.byref(self.tables))
+        self.tables = _lib.ClassTables()
+        check(lib().hlac_geno_finish(self.h, C.byref(self.tables)))
+        return _tables_to_py(self.tables)
+
+    def read_class_ids(self, n):
+        out = np.zeros(n, dtype=np.uint32)
+        check(lib().hlac_geno_read_class_ids(self.h, _vp(out), C.c_uint64(n)))
+        return out
+
+    def stats(self):
+        v = [C.c_uint64() for _ in range(5)]
+        check(lib().hlac_geno_stats(self.h, *[C.byref(x) for x in v]))
+        return dict(zip(("some_aln", "long_aln", "n_paths", "bitmap_tests", "dict_probes"), [x.value for x in v]))
+
+    def timing(self):
+        ms = (C.c_float * 4)()
+        n = C.c_uint64()
+        check(lib().hlac_geno_timing(self.h, ms, C.byref(n)))
+        return dict(map_ms=ms[0], intern_ms=ms[1], finish_ms=ms[2], h2d_ms=ms[3], launches=n.value)
+
+    def squarem(self, device=0):
+        theta = np.zeros(self.tables.nitems, dtype=np.float64)
+        it = C.c_uint32()
+        check(lib().hlac_squarem(C.byref(self.tables), C.c_int(device), _vp(theta), C.byref(it)))
+        return theta, it.value
+
+    def call(self, theta):
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        c = _lib.Calls()
+        check(lib().hlac_call_genotypes(self.index.h, C.byref(self.tables), _vp(theta), C.byref(c)))
+        out = dict(called=[c.called[i] for i in range(c.n_called)],
+                   weights=[(c.w_tx[i], c.w_em[i], c.w_frac[i]) for i in range(c.n_weights)],
+                   pairs=[(c.p_a[i], c.p_b[i], c.p_frac[i]) for i in range(c.n_pairs)])
+        lib().hlac_calls_free(C.byref(c))
+        return out
+
+
+def squarem(nitems, classes, device=0):
+    """hlac_squarem on an explicit {class tuple: count} table (classes iterated in sorted order) -> (theta, iters)"""
+    keys = sorted(classes)
+    off = np.zeros(len(keys) + 1, dtype=np.uint64)
+    tx = []
+    for i, k in enumerate(keys):
+        tx.extend(k)
+        off[i + 1] = len(tx)
+    tx = np.asarray(tx if tx else [0], dtype=np.uint32)
+    cnt = np.asarray([classes[k] for k in keys] if keys else [0], dtype=np.uint32)
+    t = _lib.ClassTables()
+    t.nitems = nitems
+    t.n_umi_classes = len(keys)
+    t.umi_off = off.ctypes.data_as(C.POINTER(C.c_uint64))
+    t.umi_tx = tx.ctypes.data_as(C.POINTER(C.c_uint32))
+    t.umi_cnt = cnt.ctypes.data_as(C.POINTER(C.c_uint32))
+    theta = np.zeros(nitems, dtype=np.float64)
+    it = C.c_uint32()
+    check(lib().hlac_squarem(C.byref(t), C.c_int(device), _vp(theta), C.byref(it)))
+    return theta, it.value

@@ -236,14 +236,19 @@ struct hlac_count {
   hlac_index* gen = nullptr;
   int device = 0;
   cudaStream_t stream = nullptr;
+  bool own_stream = true;
   RowLayout rows;
   uint32_t n_cells = 0;
   int primary_only = 0;
   DevBuf<uint32_t> cinfo_cds, cinfo_gen, gene_row0, dense;
-  DevBuf<uint64_t> keys, keys_sorted, st_seq;
-  DevBuf<uint16_t> st_len;
-  DevBuf<uint32_t> st_cell, st_umi;
-  DevBuf<uint8_t> st_flags, codes;
+  DevBuf<uint64_t> keys, keys_sorted;
+  struct Stage {   // one staging set for host batches; two of them so the H2D of batch i+1 overlaps the kernel of batch i
+    DevBuf<uint64_t> seq; DevBuf<uint16_t> len; DevBuf<uint32_t> cell, umi; DevBuf<uint8_t> flags;
+    cudaEvent_t copied = nullptr, consumed = nullptr;
+  } stage[2];
+  cudaStream_t copy_stream = nullptr;
+  uint64_t n_push = 0;
+  DevBuf<uint8_t> codes;
   DevBuf<unsigned long long> counters;   // [0] cursor, [1..8] metrics
   DevBuf<uint8_t> cub_tmp;
   uint64_t reads_pushed = 0, last_n = 0;
@@ -252,6 +257,8 @@ struct hlac_count {
   int blocks_per_sm = 1, n_sm = 1;
   bool want_codes = false;
   bool reduced = false;
+  uint32_t cfg_wpr = 0;
+  int cfg_occ = 0;
   uint64_t n_keys = 0;
   // timing
   struct Ev { cudaEvent_t a, b; int kind; };
@@ -261,16 +268,18 @@ struct hlac_count {
 
   ~hlac_count() {
     for (auto& e : events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
-    if (stream) cudaStreamDestroy(stream);
+    for (auto& st : stage) { if (st.copied) cudaEventDestroy(st.copied); if (st.consumed) cudaEventDestroy(st.consumed); }
+    if (copy_stream) cudaStreamDestroy(copy_stream);
+    if (stream && own_stream) cudaStreamDestroy(stream);
   }
-  Ev& begin(int kind) {
+  Ev& begin(int kind, cudaStream_t on = nullptr) {
     Ev e; e.kind = kind;
     HLAC_CUDA(cudaEventCreate(&e.a)); HLAC_CUDA(cudaEventCreate(&e.b));
-    HLAC_CUDA(cudaEventRecord(e.a, stream));
+    HLAC_CUDA(cudaEventRecord(e.a, on ? on : stream));
     events.push_back(e);
     return events.back();
   }
-  void end(Ev& e) { HLAC_CUDA(cudaEventRecord(e.b, stream)); }
+  void end(Ev& e, cudaStream_t on = nullptr) { HLAC_CUDA(cudaEventRecord(e.b, on ? on : stream)); }
   void drain_events() {
     for (auto& e : events) {
       float t = 0; HLAC_CUDA(cudaEventSynchronize(e.b)); HLAC_CUDA(cudaEventElapsedTime(&t, e.a, e.b));
@@ -299,10 +308,13 @@ struct hlac_count {
     a.codes = want_codes ? codes.p : nullptr;
     const size_t smem = (smem_bm ? bitmap_smem_bytes : 0) + (size_t)MAP_THREADS * a.row_stride * 4;
     auto kern = smem_bm ? k_count_map<true> : k_count_map<false>;
-    HLAC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int occ = 0;
-    HLAC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, MAP_THREADS, smem));
-    if (occ < 1) throw Error(HLAC_ERR_LIMIT, "count map kernel does not fit on the device");
+    if (cfg_wpr != b.words_per_read) {
+      HLAC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      HLAC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cfg_occ, kern, MAP_THREADS, smem));
+      if (cfg_occ < 1) throw Error(HLAC_ERR_LIMIT, "count map kernel does not fit on the device");
+      cfg_wpr = b.words_per_read;
+    }
+    const int occ = cfg_occ;
     const uint64_t need = (b.n + MAP_THREADS - 1) / MAP_THREADS;
     const unsigned grid = (unsigned)std::min<uint64_t>(need, (uint64_t)n_sm * occ);
     Ev& e = begin(0);
@@ -369,23 +381,42 @@ int hlac_count_push(hlac_count* s, const hlac_batch* b) try {
   if (!s || !b) throw Error(HLAC_ERR_ARG, "null argument");
   if (b->n == 0) return HLAC_OK;
   DeviceGuard g(s->device);
-  auto& e = s->begin(3);
-  s->st_seq.upload(b->seq, b->n * b->words_per_read, s->stream);
-  s->st_len.upload(b->len, b->n, s->stream);
-  s->st_cell.upload(b->cell, b->n, s->stream);
-  s->st_umi.upload(b->umi, b->n, s->stream);
-  s->st_flags.upload(b->flags, b->n, s->stream);
-  s->end(e);
+  auto& st = s->stage[s->n_push++ & 1];
+  if (!s->copy_stream) HLAC_CUDA(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+  if (!st.copied) { HLAC_CUDA(cudaEventCreateWithFlags(&st.copied, cudaEventDisableTiming)); HLAC_CUDA(cudaEventCreateWithFlags(&st.consumed, cudaEventDisableTiming)); }
+  else HLAC_CUDA(cudaStreamWaitEvent(s->copy_stream, st.consumed, 0));   // the kernel that read this set two pushes ago
+  auto& e = s->begin(3, s->copy_stream);
+  st.seq.upload(b->seq, b->n * b->words_per_read, s->copy_stream);
+  st.len.upload(b->len, b->n, s->copy_stream);
+  st.cell.upload(b->cell, b->n, s->copy_stream);
+  st.umi.upload(b->umi, b->n, s->copy_stream);
+  st.flags.upload(b->flags, b->n, s->copy_stream);
+  s->end(e, s->copy_stream);
+  HLAC_CUDA(cudaEventRecord(st.copied, s->copy_stream));
+  HLAC_CUDA(cudaStreamWaitEvent(s->stream, st.copied, 0));
   hlac_batch d = *b;
-  d.seq = s->st_seq.p; d.len = s->st_len.p; d.cell = s->st_cell.p; d.umi = s->st_umi.p; d.flags = s->st_flags.p;
+  d.seq = st.seq.p; d.len = st.len.p; d.cell = st.cell.p; d.umi = st.umi.p; d.flags = st.flags.p;
   s->launch_map(d);
+  HLAC_CUDA(cudaEventRecord(st.consumed, s->stream));
   return HLAC_OK;
 } catch (const Error& e) { set_last_error(e.what()); return e.code; }
 
 int hlac_count_sync(hlac_count* s) try {
   if (!s) throw Error(HLAC_ERR_ARG, "null session");
   DeviceGuard g(s->device);
+  if (s->copy_stream) HLAC_CUDA(cudaStreamSynchronize(s->copy_stream));
   HLAC_CUDA(cudaStreamSynchronize(s->stream));
+  return HLAC_OK;
+} catch (const Error& e) { set_last_error(e.what()); return e.code; }
+
+int hlac_count_set_stream(hlac_count* s, void* cuda_stream) try {
+  if (!s) throw Error(HLAC_ERR_ARG, "null session");
+  DeviceGuard g(s->device);
+  HLAC_CUDA(cudaStreamSynchronize(s->stream));
+  s->drain_events();
+  if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
+  s->stream = (cudaStream_t)cuda_stream;
+  s->own_stream = false;
   return HLAC_OK;
 } catch (const Error& e) { set_last_error(e.what()); return e.code; }
 

@@ -1,0 +1,639 @@
+// Genotyping session: mapping_wrapper's hot loops (src/mapping.rs:337-402) and EqClassDb::{count, eq_class_counts}
+// (src/mapping.rs:128-228) on the GPU.
+//
+// The reference's per-read class is NOT a set: it is the colour list of the last visited node, permuted by the
+// no-truncate merge (mapping.rs:283-308 semantics inside the pinned map_read; SURVEY.md finding #2) against every
+// other visited node's colour list, in visit order. It is therefore a pure function of the read's ordered colour
+// PATH. Lists can be thousands of alleles long, so the kernels never materialise a class per read; they intern paths:
+//
+//   per push
+//   K1g k_geno_map        thread per read: fwd, else revcomp (unless forward_only) walk; emits coverage + two 64-bit
+//                         order-sensitive hashes of the colour path
+//   K2a k_intern_insert   counted reads (cov > MIN_SCORE_CALL) insert hash A into a global open-addressing table; the
+//                         CAS winner allocates a dense path id and registers itself as the path's representative
+//   K2b k_geno_paths      one thread per NEW path re-walks its representative read and writes the colour path
+//   K2c k_intern_lookup   counted reads look their path id up, atomicMin the path's first-seen ordinal, atomicAdd its
+//                         read count, and append a (barcode, umi, path id) record (EqClassDb::count, mapping.rs:128-163)
+//   at finish
+//   K3a k_resolve_paths   thread per distinct path: exact emulation of the merges -> class vector (+ its hash)
+//       host              interns equal vectors, orders classes by first-seen ordinal (= eq_class_id order,
+//                         mapping.rs:147-154), sums counts_reads, builds path -> class-rank table
+//   K3b radix sort + k_umi_min   group records by (barcode, umi); the UMI's class is the lowest class id among its
+//                         reads (mapping.rs:165-167,184-193), then sort+dedup on the host per distinct class
+//                         (mapping.rs:205-207); counts_umi histogram by atomicAdd
+#include <cub/device/device_radix_sort.cuh>
+
+#include <algorithm>
+#include <map>
+#include <memory>
+#include <unordered_map>
+#include <vector>
+
+#include "device_index.hpp"
+
+using namespace hlac;
+
+namespace {
+
+constexpr int GENO_THREADS = 256;
+
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {
+  x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ULL; x ^= x >> 27; x *= 0x94d049bb133111ebULL; x ^= x >> 31;
+  return x;
+}
+
+struct HashVis {   // order-sensitive hashes of the colour path
+  uint64_t a = 0xcbf29ce484222325ULL, b = 0x9e3779b97f4a7c15ULL;
+  uint32_t n = 0;
+  __device__ __forceinline__ void visit(uint32_t colour, uint32_t) {
+    a = (a ^ colour) * 0x100000001b3ULL; a ^= a >> 32;
+    b = mix64(b + colour + 0x632be59bd9b4e019ULL);
+    n++;
+  }
+  __device__ __forceinline__ void finish() {
+    a = mix64(a ^ n); if (a == 0) a = 1;   // 0 marks an empty table slot
+    b = mix64(b ^ ((uint64_t)n << 32));
+  }
+};
+struct CountVis2 { uint32_t n = 0; __device__ __forceinline__ void visit(uint32_t, uint32_t) { n++; } };
+struct WriteVis { uint32_t* out; uint32_t n = 0; __device__ __forceinline__ void visit(uint32_t colour, uint32_t) { out[n++] = colour; } };
+
+struct SharedWords {
+  const uint32_t* p;
+  __device__ __forceinline__ uint32_t operator[](int i) const { return p[i]; }
+};
+struct BitmapGlobal {
+  const uint32_t* p;
+  __device__ __forceinline__ uint32_t operator()(uint32_t i) const { return __ldg(p + i); }
+};
+
+struct GenoMapArgs {
+  DevIndexView ix;
+  const uint64_t* seq; const uint16_t* len;
+  uint64_t n; uint32_t wpr, nw, row_stride;
+  int forward_only;
+  uint32_t* cov;            // per read (0 = None)
+  uint64_t* hash_a; uint64_t* hash_b;
+  uint8_t* strand;          // 0 fwd, 1 revcomp (for the representative re-walk)
+  unsigned long long* stats;  // [0] some_aln, [1] long_aln, [2] bitmap tests, [3] dict probes
+};
+
+// loads read i of the batch into this thread's shared-memory row (forward strand, zero padded)
+__device__ __forceinline__ void load_read_row(const uint64_t* seq, uint64_t i, uint32_t wpr, uint32_t* fw) {
+  for (uint32_t w = 0; w < wpr; w++) {
+    const uint64_t v = __ldg(seq + i * wpr + w);
+    fw[2 * w] = (uint32_t)(v >> 32); fw[2 * w + 1] = (uint32_t)v;
+  }
+  fw[2 * wpr] = 0; fw[2 * wpr + 1] = 0;
+}
+
+__global__ void __launch_bounds__(GENO_THREADS) k_geno_map(const GenoMapArgs a) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  uint32_t* fw = smem + threadIdx.x * a.row_stride;
+  uint32_t* rc = fw + a.nw;
+  unsigned long long some = 0, lng = 0;
+  uint32_t n_tests = 0, n_probes = 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * GENO_THREADS + threadIdx.x; i < a.n; i += (uint64_t)gridDim.x * GENO_THREADS) {
+    load_read_row(a.seq, i, a.wpr, fw);
+    const int L = a.len[i];
+    uint32_t cov = 0; uint64_t ha = 0, hb = 0; uint8_t strand = 0;
+    bool found = false;
+#pragma unroll 1
+    for (int p = 0; p < 2; p++) {   // mapping.rs:341-363: forward, else reverse complement; unmapped pass forward only
+      if (p == 1) { if (a.forward_only) break; make_revcomp(SharedWords{fw}, rc, L, (int)a.nw); }
+      HashVis vis;
+      found = map_read_walk(a.ix, SharedWords{p ? rc : fw}, BitmapGlobal{a.ix.bitmap}, L, vis, cov, n_tests, n_probes);
+      if (found) { vis.finish(); ha = vis.a; hb = vis.b; strand = (uint8_t)p; break; }
+    }
+    if (!found) cov = 0;
+    a.cov[i] = cov; a.hash_a[i] = ha; a.hash_b[i] = hb; a.strand[i] = strand;
+    if (found) { some++; if (cov > MIN_SCORE_CALL) lng++; }
+  }
+  unsigned long long m[4] = {some, lng, n_tests, n_probes};
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    unsigned long long v = m[k];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(a.stats + k, v);
+  }
+}
+
+struct PathTable {
+  unsigned long long* keys;   // hash A, 0 = empty
+  uint32_t* ids;              // dense path id
+  uint64_t mask;
+};
+struct PathEntries {          // dense, indexed by path id
+  uint64_t* hash_b;
+  unsigned long long* first_ord;
+  uint32_t* count;
+  uint64_t* path_off;
+  uint32_t* path_len;
+  uint32_t* rep_read;         // batch-local index of the representative read (valid for paths new in this push)
+};
+
+__global__ void k_intern_insert(PathTable t, PathEntries e, const uint32_t* __restrict__ cov, const uint64_t* __restrict__ ha,
+                                const uint64_t* __restrict__ hb, uint64_t n, unsigned long long* n_entries) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || cov[i] <= MIN_SCORE_CALL) return;
+  const unsigned long long key = ha[i];
+  uint64_t h = mix64(key) & t.mask;
+  for (;;) {
+    const unsigned long long cur = t.keys[h];
+    if (cur == key) return;
+    if (cur == 0) {
+      const unsigned long long old = atomicCAS(t.keys + h, 0ULL, key);
+      if (old == 0) {   // winner: allocate the dense id and register as representative
+        const uint32_t id = (uint32_t)atomicAdd(n_entries, 1ULL);
+        t.ids[h] = id;
+        e.hash_b[id] = hb[i]; e.first_ord[id] = ~0ULL; e.count[id] = 0; e.rep_read[id] = (uint32_t)i;
+        e.path_off[id] = 0; e.path_len[id] = 0;
+        return;
+      }
+      if (old == key) return;
+    }
+    h = (h + 1) & t.mask;
+  }
+}
+
+struct GenoPathArgs {
+  DevIndexView ix;
+  const uint64_t* seq; const uint16_t* len; const uint8_t* strand;
+  uint32_t wpr, nw, row_stride;
+  PathEntries e;
+  uint32_t first_new, n_new;
+  uint32_t* arena; unsigned long long* arena_cursor;
+};
+
+__global__ void __launch_bounds__(GENO_THREADS) k_geno_paths(const GenoPathArgs a) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  uint32_t* fw = smem + threadIdx.x * a.row_stride;
+  uint32_t* rc = fw + a.nw;
+  const uint32_t k = blockIdx.x * GENO_THREADS + threadIdx.x;
+  if (k >= a.n_new) return;
+  const uint32_t id = a.first_new + k;
+  const uint64_t i = a.e.rep_read[id];
+  load_read_row(a.seq, i, a.wpr, fw);
+  const int L = a.len[i];
+  const bool rev = a.strand[i] != 0;
+  if (rev) make_revcomp(SharedWords{fw}, rc, L, (int)a.nw);
+  SharedWords rd{rev ? rc : fw};
+  uint32_t cov, t0 = 0, t1 = 0;
+  CountVis2 cv;
+  map_read_walk(a.ix, rd, BitmapGlobal{a.ix.bitmap}, L, cv, cov, t0, t1);
+  const unsigned long long off = atomicAdd(a.arena_cursor, (unsigned long long)cv.n);
+  WriteVis wv{a.arena + off};
+  map_read_walk(a.ix, rd, BitmapGlobal{a.ix.bitmap}, L, wv, cov, t0, t1);
+  a.e.path_off[id] = off; a.e.path_len[id] = cv.n;
+}
+
+struct Record { uint32_t bc, umi, path; };
+
+__global__ void k_intern_lookup(PathTable t, PathEntries e, const uint32_t* __restrict__ cov, const uint64_t* __restrict__ ha,
+                                const uint64_t* __restrict__ hb, const uint32_t* __restrict__ cell, const uint32_t* __restrict__ umi,
+                                uint64_t n, uint64_t ord0, uint64_t* rec_key, uint32_t* rec_path, unsigned long long* rec_cursor,
+                                uint32_t* read_path, unsigned long long* collisions) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned lane = threadIdx.x & 31;
+  bool counted = false; uint32_t id = NONE32;
+  if (i < n && cov[i] > MIN_SCORE_CALL) {
+    counted = true;
+    const unsigned long long key = ha[i];
+    uint64_t h = mix64(key) & t.mask;
+    while (t.keys[h] != key) h = (h + 1) & t.mask;
+    id = t.ids[h];
+    if (e.hash_b[id] != hb[i]) atomicAdd(collisions, 1ULL);
+    atomicMin(e.first_ord + id, (unsigned long long)(ord0 + i));
+    atomicAdd(e.count + id, 1u);
+  }
+  if (i < n && read_path) read_path[i] = id;
+  const unsigned ballot = __ballot_sync(0xFFFFFFFFu, counted);
+  if (ballot) {
+    unsigned long long at = 0;
+    if (lane == 0) at = atomicAdd(rec_cursor, (unsigned long long)__popc(ballot));
+    at = __shfl_sync(0xFFFFFFFFu, at, 0);
+    if (counted) {
+      const unsigned long long w = at + __popc(ballot & ((1u << lane) - 1));
+      rec_key[w] = ((uint64_t)cell[i] << 32) | umi[i];
+      rec_path[w] = id;
+    }
+  }
+}
+
+__global__ void k_rehash(const unsigned long long* __restrict__ okeys, const uint32_t* __restrict__ oids, uint64_t ocap, PathTable t) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ocap || okeys[i] == 0) return;
+  const unsigned long long key = okeys[i];
+  uint64_t h = mix64(key) & t.mask;
+  for (;;) {
+    if (atomicCAS(t.keys + h, 0ULL, key) == 0) { t.ids[h] = oids[i]; return; }
+    h = (h + 1) & t.mask;
+  }
+}
+
+// per path: length of its class vector = |colours[last colour of the path]|
+__global__ void k_class_len(const uint32_t* __restrict__ arena, const uint64_t* __restrict__ path_off, const uint32_t* __restrict__ path_len,
+                            const uint64_t* __restrict__ col_off, uint32_t n, uint32_t* out) {
+  const uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= n) return;
+  const uint32_t c = arena[path_off[id] + path_len[id] - 1];
+  out[id] = (uint32_t)(col_off[c + 1] - col_off[c]);
+}
+
+// Exact emulation of `v1 = colours[last]; for n in others (visit order): merge_no_truncate(v1, colours[n])`.
+__global__ void k_resolve_paths(const uint32_t* __restrict__ arena, const uint64_t* __restrict__ path_off, const uint32_t* __restrict__ path_len,
+                                const uint64_t* __restrict__ col_off, const uint32_t* __restrict__ col_tx, uint32_t n,
+                                const uint64_t* __restrict__ vec_off, uint32_t* vec, uint64_t* vec_hash) {
+  const uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= n) return;
+  const uint32_t* path = arena + path_off[id];
+  const uint32_t plen = path_len[id];
+  const uint32_t last = path[plen - 1];
+  uint32_t* v1 = vec + vec_off[id];
+  const uint32_t n1 = (uint32_t)(col_off[last + 1] - col_off[last]);
+  for (uint32_t k = 0; k < n1; k++) v1[k] = col_tx[col_off[last] + k];
+  for (uint32_t s = 0; s + 1 < plen; s++) {
+    const uint32_t c = path[s];
+    const uint32_t* v2 = col_tx + col_off[c];
+    const uint32_t n2 = (uint32_t)(col_off[c + 1] - col_off[c]);
+    uint32_t f = 0, i = 0, j = 0;
+    while (i < n1 && j < n2) {
+      const uint32_t x = v1[i], y = v2[j];
+      if (x < y) i++;
+      else if (x > y) j++;
+      else { v1[i] = v1[f]; v1[f] = x; i++; j++; f++; }
+    }
+  }
+  uint64_t h = 0xcbf29ce484222325ULL;
+  for (uint32_t k = 0; k < n1; k++) { h = (h ^ v1[k]) * 0x100000001b3ULL; h ^= h >> 32; }
+  vec_hash[id] = mix64(h ^ n1);
+}
+
+__global__ void k_map_rank(const uint32_t* __restrict__ rec_path, const uint32_t* __restrict__ rank_of_path, uint64_t n, uint32_t* out) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = rank_of_path[rec_path[i]];
+}
+
+// one thread per (barcode, umi) run of the sorted records: UMI class = lowest class rank among its reads
+__global__ void k_umi_min(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ ranks, uint64_t n, uint32_t* umi_hist) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t k = keys[i];
+  if (i > 0 && keys[i - 1] == k) return;
+  uint32_t best = ranks[i];
+  for (uint64_t j = i + 1; j < n && keys[j] == k; j++) best = min(best, ranks[j]);
+  atomicAdd(umi_hist + best, 1u);
+}
+
+}  // namespace
+
+struct hlac_geno {
+  hlac_index* idx = nullptr;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int n_sm = 1;
+  // staging + per-batch temporaries
+  DevBuf<uint64_t> st_seq, hash_a, hash_b;
+  DevBuf<uint16_t> st_len;
+  DevBuf<uint32_t> st_cell, st_umi, cov;
+  DevBuf<uint8_t> strand;
+  // path table
+  DevBuf<unsigned long long> t_keys; DevBuf<uint32_t> t_ids; uint64_t t_cap = 0;
+  DevBuf<uint64_t> e_hash_b, e_path_off; DevBuf<unsigned long long> e_first_ord; DevBuf<uint32_t> e_count, e_path_len, e_rep;
+  DevBuf<uint32_t> arena;
+  DevBuf<unsigned long long> ctr;   // [0] n_entries [1] arena cursor [2] rec cursor [3] collisions [4..7] stats
+  // records of counted reads
+  DevBuf<uint64_t> rec_key; DevBuf<uint32_t> rec_path;
+  DevBuf<uint32_t> read_path; bool record_reads = false;   // optional: path id of every read pushed
+  uint64_t reads_pushed = 0, last_n = 0, n_entries = 0, arena_used = 0, n_records_ub = 0;
+  // finish results kept for hlac_geno_read_class_ids
+  std::vector<uint32_t> class_of_path;
+  bool finished = false;
+  float ms[4] = {0, 0, 0, 0};
+  uint64_t launches = 0;
+  struct Ev { cudaEvent_t a, b; int kind; };
+  std::vector<Ev> events;
+
+  ~hlac_geno() {
+    for (auto& e : events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    if (stream) cudaStreamDestroy(stream);
+  }
+  size_t begin(int kind) {
+    Ev e; e.kind = kind;
+    HLAC_CUDA(cudaEventCreate(&e.a)); HLAC_CUDA(cudaEventCreate(&e.b));
+    HLAC_CUDA(cudaEventRecord(e.a, stream));
+    events.push_back(e);
+    return events.size() - 1;
+  }
+  void end(size_t k) { HLAC_CUDA(cudaEventRecord(events[k].b, stream)); }
+  void drain_events() {
+    for (auto& e : events) {
+      float t = 0; HLAC_CUDA(cudaEventSynchronize(e.b)); HLAC_CUDA(cudaEventElapsedTime(&t, e.a, e.b));
+      ms[e.kind] += t; cudaEventDestroy(e.a); cudaEventDestroy(e.b);
+    }
+    events.clear();
+  }
+  PathTable table() { return PathTable{t_keys.p, t_ids.p, t_cap - 1}; }
+  PathEntries entries() { return PathEntries{e_hash_b.p, e_first_ord.p, e_count.p, e_path_off.p, e_path_len.p, e_rep.p}; }
+
+  void ensure_table(uint64_t want_entries) {
+    uint64_t cap = t_cap ? t_cap : (1u << 16);
+    while (cap < want_entries * 2) cap <<= 1;
+    if (cap != t_cap) {
+      DevBuf<unsigned long long> nk; DevBuf<uint32_t> ni;
+      nk.reserve(cap, stream); ni.reserve(cap, stream);
+      HLAC_CUDA(cudaMemsetAsync(nk.p, 0, cap * sizeof(unsigned long long), stream));
+      if (t_cap) {
+        PathTable nt{nk.p, ni.p, cap - 1};
+        k_rehash<<<(unsigned)((t_cap + 255) / 256), 256, 0, stream>>>(t_keys.p, t_ids.p, t_cap, nt);
+        HLAC_CUDA(cudaGetLastError());
+        launches++;
+      }
+      HLAC_CUDA(cudaStreamSynchronize(stream));
+      std::swap(t_keys.p, nk.p); std::swap(t_keys.cap, nk.cap);
+      std::swap(t_ids.p, ni.p); std::swap(t_ids.cap, ni.cap);
+      t_cap = cap;
+    }
+    const size_t ne = want_entries;
+    e_hash_b.reserve(ne, stream, true, n_entries); e_path_off.reserve(ne, stream, true, n_entries);
+    e_first_ord.reserve(ne, stream, true, n_entries); e_count.reserve(ne, stream, true, n_entries);
+    e_path_len.reserve(ne, stream, true, n_entries); e_rep.reserve(ne, stream, true, n_entries);
+  }
+
+  void push_device(const hlac_batch& b, int forward_only) {
+    if (b.n == 0) return;
+    if (b.words_per_read == 0 || b.words_per_read > 16) throw Error(HLAC_ERR_ARG, "words_per_read must be 1..16");
+    if (b.n >= (1ull << 32)) throw Error(HLAC_ERR_LIMIT, "batch too large");
+    finished = false;
+    const uint64_t n = b.n;
+    cov.reserve(n, stream); hash_a.reserve(n, stream); hash_b.reserve(n, stream); strand.reserve(n, stream);
+    ensure_table(n_entries + n);
+    rec_key.reserve(n_records_ub + n, stream, true, n_records_ub);
+    rec_path.reserve(n_records_ub + n, stream, true, n_records_ub);
+    if (record_reads) read_path.reserve(reads_pushed + n, stream, true, reads_pushed);
+    GenoMapArgs a{};
+    a.ix = idx->view; a.seq = b.seq; a.len = b.len; a.n = n; a.wpr = b.words_per_read; a.nw = 2 * a.wpr + 2; a.row_stride = (2 * a.nw) | 1;
+    a.forward_only = forward_only; a.cov = cov.p; a.hash_a = hash_a.p; a.hash_b = hash_b.p; a.strand = strand.p; a.stats = ctr.p + 4;
+    const size_t smem = (size_t)GENO_THREADS * a.row_stride * 4;
+    HLAC_CUDA(cudaFuncSetAttribute(k_geno_map, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    HLAC_CUDA(cudaFuncSetAttribute(k_geno_paths, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 1;
+    HLAC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_geno_map, GENO_THREADS, smem));
+    const unsigned grid = (unsigned)std::min<uint64_t>((n + GENO_THREADS - 1) / GENO_THREADS, (uint64_t)n_sm * std::max(occ, 1));
+    size_t e0 = begin(0);
+    k_geno_map<<<grid, GENO_THREADS, smem, stream>>>(a);
+    HLAC_CUDA(cudaGetLastError());
+    end(e0);
+    size_t e1 = begin(1);
+    const unsigned g1 = (unsigned)((n + 255) / 256);
+    k_intern_insert<<<g1, 256, 0, stream>>>(table(), entries(), cov.p, hash_a.p, hash_b.p, n, ctr.p);
+    HLAC_CUDA(cudaGetLastError());
+    unsigned long long ne = 0;
+    HLAC_CUDA(cudaMemcpyAsync(&ne, ctr.p, sizeof ne, cudaMemcpyDeviceToHost, stream));
+    HLAC_CUDA(cudaStreamSynchronize(stream));
+    const uint32_t n_new = (uint32_t)(ne - n_entries);
+    launches += 2;
+    if (n_new) {
+      arena.reserve(arena_used + (uint64_t)n_new * 32 * b.words_per_read, stream, true, arena_used);   // a path has at most L nodes
+      GenoPathArgs p{};
+      p.ix = idx->view; p.seq = b.seq; p.len = b.len; p.strand = strand.p; p.wpr = a.wpr; p.nw = a.nw; p.row_stride = a.row_stride;
+      p.e = entries(); p.first_new = (uint32_t)n_entries; p.n_new = n_new; p.arena = arena.p; p.arena_cursor = ctr.p + 1;
+      k_geno_paths<<<(n_new + GENO_THREADS - 1) / GENO_THREADS, GENO_THREADS, smem, stream>>>(p);
+      HLAC_CUDA(cudaGetLastError());
+      launches++;
+    }
+    k_intern_lookup<<<g1, 256, 0, stream>>>(table(), entries(), cov.p, hash_a.p, hash_b.p, b.cell, b.umi, n, reads_pushed,
+                                            rec_key.p, rec_path.p, ctr.p + 2, record_reads ? read_path.p + reads_pushed : nullptr, ctr.p + 3);
+    HLAC_CUDA(cudaGetLastError());
+    launches++;
+    unsigned long long c2[3];
+    HLAC_CUDA(cudaMemcpyAsync(c2, ctr.p + 1, sizeof c2, cudaMemcpyDeviceToHost, stream));
+    end(e1);
+    HLAC_CUDA(cudaStreamSynchronize(stream));
+    n_entries = ne; arena_used = c2[0]; n_records_ub = c2[1];
+    if (c2[2]) throw Error(HLAC_ERR_STATE, "path hash collision detected (64-bit hash A equal, hash B different)");
+    reads_pushed += n; last_n = n;
+  }
+};
+
+extern "C" {
+
+int hlac_geno_new(hlac_index* idx, hlac_geno** out) try {
+  if (!idx || !out) throw Error(HLAC_ERR_ARG, "null argument");
+  if (idx->device < 0) throw Error(HLAC_ERR_CUDA, "index is host-only (device -1): genotyping needs a CUDA device, there is no CPU fallback");
+  auto s = std::make_unique<hlac_geno>();
+  s->idx = idx; s->device = idx->device;
+  DeviceGuard g(s->device);
+  HLAC_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+  s->ctr.reserve(16, s->stream);
+  HLAC_CUDA(cudaMemsetAsync(s->ctr.p, 0, 16 * sizeof(unsigned long long), s->stream));
+  cudaDeviceProp prop; HLAC_CUDA(cudaGetDeviceProperties(&prop, s->device));
+  s->n_sm = prop.multiProcessorCount;
+  HLAC_CUDA(cudaStreamSynchronize(s->stream));
+  *out = s.release();
+  return HLAC_OK;
+} catch (const Error& e) { set_last_error(e.what()); return e.code; } catch (const std::exception& e) { set_last_error(e.what()); return HLAC_ERR_STATE; }
+
+int hlac_geno_free(hlac_geno* s) {
+  if (s) { cudaSetDevice(s->device); delete s; }
+  return HLAC_OK;
+}
+
+int hlac_geno_record_reads(hlac_geno* s, int on) {
+  if (!s) { set_last_error("null session"); return HLAC_ERR_ARG; }
+  if (s->reads_pushed) { set_last_error("hlac_geno_record_reads must be called before the first push"); return HLAC_ERR_STATE; }
+  s->record_reads = on != 0;
+  return HLAC_OK;
+}
+
+int hlac_geno_push_device(hlac_geno* s, const hlac_batch* b, int forward_only) try {
+  if (!s || !b) throw Error(HLAC_ERR_ARG, "null argument");
+  DeviceGuard g(s->device);
+  s->push_device(*b, forward_only);
+  return HLAC_OK;
+} catch (const Error& e) { set_last_error(e.what()); return e.code; } catch (const std::exception& e) { set_last_error(e.what()); return HLAC_ERR_STATE; }
+
+int hlac_geno_push(hlac_geno* s, const hlac_batch* b, int forward_only) try {
+  if (!s || !b) throw Error(HLAC_ERR_ARG, "null argument");
+  if (b->n == 0) return HLAC_OK;
+  DeviceGuard g(s->device);
+  size_t e = s->begin(3);
+  s->st_seq.upload(b->seq, b->n * b->words_per_read, s->stream);
+  s->st_len.upload(b->len, b->n, s->stream);
+  s->st_cell.upload(b->cell, b->n, s->stream);
+  s->st_umi.upload(b->umi, b->n, s->stream);
+  s->end(e);
+  hlac_batch d = *b;
+  d.seq = s->st_seq.p; d.len = s->st_len.p; d.cell = s->st_cell.p; d.umi = s->st_umi.p; d.flags = nullptr;
+  s->push_device(d, forward_only);
+  return HLAC_OK;
+} catch (const Error& e) { set_last_error(e.what()); return e.code; } catch (const std::exception& e) { set_last_error(e.what()); return HLAC_ERR_STATE; }
+
+int hlac_geno_last_cov(hlac_geno* s, uint32_t* cov, uint64_t n) try {
+  if (!s || !cov) throw Error(HLAC_ERR_ARG, "null argument");
+  if (n != s->last_n) throw Error(HLAC_ERR_ARG, "n does not match the last pushed batch");
+  DeviceGuard g(s->device);
+  HLAC_CUDA(cudaMemcpyAsync(cov, s->cov.p, n * 4, cudaMemcpyDeviceToHost, s->stream));
+  HLAC_CUDA(cudaStreamSynchronize(s->stream));
+  return HLAC_OK;
+} catch (const Error& e) { set_last_error(e.what()); return e.code; }
+
+int hlac_geno_finish(hlac_geno* s, hlac_class_tables* out) try {
+  if (!s || !out) throw Error(HLAC_ERR_ARG, "null argument");
+  DeviceGuard g(s->device);
+  const HostIndex& hx = s->idx->host;
+  const uint32_t nitems = (uint32_t)hx.tx_names.size();
+  const uint32_t E = (uint32_t)s->n_entries;
+  const uint64_t R = s->n_records_ub;
+  memset(out, 0, sizeof *out);
+  out->nitems = nitems;
+  out->nreads = (uint32_t)R;
+  out->reads_explained = (uint64_t*)calloc(std::max<uint32_t>(nitems, 1), 8);
+  std::vector<std::vector<uint32_t>> cls_vec;      // class id (first-seen order) -> raw vector
+  std::vector<uint32_t> cls_reads;                 // counts_reads
+  std::vector<uint32_t> umi_hist;                  // UMIs whose lowest class is this class
+  s->class_of_path.assign(E, NONE32);
+  if (E) {
+    // ---- K3a: resolve every distinct path to its class vector ----
+    DevBuf<uint32_t> clen; clen.reserve(E, s->stream);
+    size_t ev = s->begin(2);
+    k_class_len<<<(E + 255) / 256, 256, 0, s->stream>>>(s->arena.p, s->e_path_off.p, s->e_path_len.p, s->idx->col_off.p, E, clen.p);
+    HLAC_CUDA(cudaGetLastError());
+    std::vector<uint32_t> hlen(E);
+    HLAC_CUDA(cudaMemcpyAsync(hlen.data(), clen.p, (size_t)E * 4, cudaMemcpyDeviceToHost, s->stream));
+    HLAC_CUDA(cudaStreamSynchronize(s->stream));
+    std::vector<uint64_t> voff(E + 1, 0);
+    for (uint32_t i = 0; i < E; i++) voff[i + 1] = voff[i] + hlen[i];
+    DevBuf<uint64_t> d_voff, d_vhash; DevBuf<uint32_t> d_vec;
+    d_voff.upload(voff.data(), E + 1, s->stream); d_vhash.reserve(E, s->stream); d_vec.reserve(std::max<uint64_t>(voff[E], 1), s->stream);
+    k_resolve_paths<<<(E + 127) / 128, 128, 0, s->stream>>>(s->arena.p, s->e_path_off.p, s->e_path_len.p, s->idx->col_off.p, s->idx->col_tx.p, E,
+                                                           d_voff.p, d_vec.p, d_vhash.p);
+    HLAC_CUDA(cudaGetLastError());
+    s->end(ev);
+    s->launches += 2;
+    std::vector<uint64_t> vhash(E), ford(E); std::vector<uint32_t> vec(std::max<uint64_t>(voff[E], 1)), cnt(E);
+    HLAC_CUDA(cudaMemcpyAsync(vhash.data(), d_vhash.p, (size_t)E * 8, cudaMemcpyDeviceToHost, s->stream));
+    HLAC_CUDA(cudaMemcpyAsync(vec.data(), d_vec.p, voff[E] * 4, cudaMemcpyDeviceToHost, s->stream));
+    HLAC_CUDA(cudaMemcpyAsync(ford.data(), s->e_first_ord.p, (size_t)E * 8, cudaMemcpyDeviceToHost, s->stream));
+    HLAC_CUDA(cudaMemcpyAsync(cnt.data(), s->e_count.p, (size_t)E * 4, cudaMemcpyDeviceToHost, s->stream));
+    HLAC_CUDA(cudaStreamSynchronize(s->stream));
+    // ---- host: intern equal vectors (exact compare), order classes by first-seen ordinal ----
+    struct Cls { uint32_t rep; uint64_t ord; uint32_t reads; };
+    std::vector<Cls> classes; std::vector<uint32_t> tmp_cls(E);
+    std::unordered_map<uint64_t, std::vector<uint32_t>> by_hash;
+    for (uint32_t p = 0; p < E; p++) {
+      auto& cand = by_hash[vhash[p]];
+      uint32_t found = NONE32;
+      for (uint32_t c : cand) {
+        const uint32_t r = classes[c].rep;
+        if (hlen[r] == hlen[p] && std::equal(vec.begin() + voff[p], vec.begin() + voff[p + 1], vec.begin() + voff[r])) { found = c; break; }
+      }
+      if (found == NONE32) { found = (uint32_t)classes.size(); classes.push_back({p, ford[p], 0}); cand.push_back(found); }
+      classes[found].ord = std::min(classes[found].ord, ford[p]);
+      classes[found].reads += cnt[p];
+      tmp_cls[p] = found;
+    }
+    std::vector<uint32_t> order(classes.size());
+    for (uint32_t i = 0; i < order.size(); i++) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return classes[a].ord < classes[b].ord; });
+    std::vector<uint32_t> rank(classes.size());
+    for (uint32_t r = 0; r < order.size(); r++) rank[order[r]] = r;
+    cls_vec.resize(classes.size()); cls_reads.resize(classes.size());
+    for (uint32_t c = 0; c < classes.size(); c++) {
+      const uint32_t r = classes[c].rep;
+      cls_vec[rank[c]].assign(vec.begin() + voff[r], vec.begin() + voff[r + 1]);
+      cls_reads[rank[c]] = classes[c].reads;
+    }
+    for (uint32_t p = 0; p < E; p++) s->class_of_path[p] = rank[tmp_cls[p]];
+    // ---- K3b: group records by (barcode, umi), lowest class id per UMI ----
+    umi_hist.assign(classes.size(), 0);
+    if (R) {
+      DevBuf<uint32_t> d_rank_of_path, d_ranks, d_ranks_sorted, d_hist; DevBuf<uint64_t> d_keys_sorted; DevBuf<uint8_t> tmp;
+      d_rank_of_path.upload(s->class_of_path.data(), E, s->stream);
+      d_ranks.reserve(R, s->stream); d_ranks_sorted.reserve(R, s->stream); d_keys_sorted.reserve(R, s->stream);
+      d_hist.reserve(classes.size(), s->stream);
+      HLAC_CUDA(cudaMemsetAsync(d_hist.p, 0, classes.size() * 4, s->stream));
+      size_t e3 = s->begin(2);
+      k_map_rank<<<(unsigned)((R + 255) / 256), 256, 0, s->stream>>>(s->rec_path.p, d_rank_of_path.p, R, d_ranks.p);
+      HLAC_CUDA(cudaGetLastError());
+      size_t tb = 0;
+      HLAC_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, s->rec_key.p, d_keys_sorted.p, d_ranks.p, d_ranks_sorted.p, R, 0, 64, s->stream));
+      tmp.reserve(tb, s->stream);
+      HLAC_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, s->rec_key.p, d_keys_sorted.p, d_ranks.p, d_ranks_sorted.p, R, 0, 64, s->stream));
+      k_umi_min<<<(unsigned)((R + 255) / 256), 256, 0, s->stream>>>(d_keys_sorted.p, d_ranks_sorted.p, R, d_hist.p);
+      HLAC_CUDA(cudaGetLastError());
+      s->end(e3);
+      s->launches += 3;
+      HLAC_CUDA(cudaMemcpyAsync(umi_hist.data(), d_hist.p, classes.size() * 4, cudaMemcpyDeviceToHost, s->stream));
+      HLAC_CUDA(cudaStreamSynchronize(s->stream));
+    }
+  }
+  // ---- assemble EqClassCounts (mapping.rs:199-209) ----
+  const size_t nc = cls_vec.size();
+  uint64_t ntx = 0; for (auto& v : cls_vec) ntx += v.size();
+  out->n_read_classes = nc;
+  out->reads_off = (uint64_t*)calloc(nc + 1, 8); out->reads_tx = (uint32_t*)calloc(std::max<uint64_t>(ntx, 1), 4); out->reads_cnt = (uint32_t*)calloc(std::max<size_t>(nc, 1), 4);
+  uint64_t q = 0;
+  for (size_t c = 0; c < nc; c++) {
+    for (uint32_t t : cls_vec[c]) { out->reads_tx[q++] = t; out->reads_explained[t] += cls_reads[c]; }
+    out->reads_off[c + 1] = q; out->reads_cnt[c] = cls_reads[c];
+  }
+  std::map<std::vector<uint32_t>, uint32_t> umi;   // key: sort + dedup of the UMI's class (mapping.rs:205-207)
+  for (size_t c = 0; c < nc; c++) if (umi_hist[c]) {
+    std::vector<uint32_t> k = cls_vec[c];
+    std::sort(k.begin(), k.end()); k.erase(std::unique(k.begin(), k.end()), k.end());
+    umi[k] += umi_hist[c];
+  }
+  uint64_t utx = 0; for (auto& kv : umi) utx += kv.first.size();
+  out->n_umi_classes = umi.size();
+  out->umi_off = (uint64_t*)calloc(umi.size() + 1, 8); out->umi_tx = (uint32_t*)calloc(std::max<uint64_t>(utx, 1), 4); out->umi_cnt = (uint32_t*)calloc(std::max<size_t>(umi.size(), 1), 4);
+  q = 0; size_t c = 0;
+  for (auto& kv : umi) { for (uint32_t t : kv.first) out->umi_tx[q++] = t; out->umi_cnt[c] = kv.second; out->umi_off[++c] = q; }
+  s->finished = true;
+  return HLAC_OK;
+} catch (const Error& e) { set_last_error(e.what()); return e.code; } catch (const std::exception& e) { set_last_error(e.what()); return HLAC_ERR_STATE; }
+
+int hlac_geno_read_class_ids(hlac_geno* s, uint32_t* ids, uint64_t n) try {
+  if (!s || !ids) throw Error(HLAC_ERR_ARG, "null argument");
+  if (!s->record_reads) throw Error(HLAC_ERR_STATE, "per-read path ids were not recorded (hlac_geno_record_reads)");
+  if (!s->finished) throw Error(HLAC_ERR_STATE, "hlac_geno_finish has not run");
+  if (n != s->reads_pushed) throw Error(HLAC_ERR_ARG, "n must equal the number of reads pushed");
+  DeviceGuard g(s->device);
+  HLAC_CUDA(cudaMemcpyAsync(ids, s->read_path.p, n * 4, cudaMemcpyDeviceToHost, s->stream));
+  HLAC_CUDA(cudaStreamSynchronize(s->stream));
+  for (uint64_t i = 0; i < n; i++) if (ids[i] != NONE32) ids[i] = s->class_of_path[ids[i]];
+  return HLAC_OK;
+} catch (const Error& e) { set_last_error(e.what()); return e.code; }
+
+int hlac_class_tables_free(hlac_class_tables* t) {
+  if (t) {
+    free(t->reads_off); free(t->reads_tx); free(t->reads_cnt); free(t->umi_off); free(t->umi_tx); free(t->umi_cnt); free(t->reads_explained);
+    memset(t, 0, sizeof *t);
+  }
+  return HLAC_OK;
+}
+
+int hlac_geno_timing(hlac_geno* s, float ms[4], uint64_t* launches) try {
+  if (!s) throw Error(HLAC_ERR_ARG, "null session");
+  DeviceGuard g(s->device);
+  s->drain_events();
+  if (ms) for (int i = 0; i < 4; i++) ms[i] = s->ms[i];
+  if (launches) *launches = s->launches;
+  return HLAC_OK;
+} catch (const Error& e) { set_last_error(e.what()); return e.code; }
+
+int hlac_geno_stats(hlac_geno* s, uint64_t* some_aln, uint64_t* long_aln, uint64_t* n_paths, uint64_t* bitmap_tests, uint64_t* dict_probes) try {
+  if (!s) throw Error(HLAC_ERR_ARG, "null session");
+  DeviceGuard g(s->device);
+  unsigned long long c[4];
+  HLAC_CUDA(cudaMemcpyAsync(c, s->ctr.p + 4, sizeof c, cudaMemcpyDeviceToHost, s->stream));
+  HLAC_CUDA(cudaStreamSynchronize(s->stream));
+  if (some_aln) *some_aln = c[0];
+  if (long_aln) *long_aln = c[1];
+  if (n_paths) *n_paths = s->n_entries;
+  if (bitmap_tests) *bitmap_tests = c[2];
+  if (dict_probes) *dict_probes = c[3];
+  return HLAC_OK;
+} catch (const Error& e) { set_last_error(e.what()); return e.code; }
+
+}  // extern "C"

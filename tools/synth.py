@@ -118,3 +118,58 @@ def config2(n_reads=10_000_000, n_cells=10_000, seed=20191101 + 2):
     cds, gen = fixture_alleles()
     reads = make_reads(n_reads, [s for _, s in cds], [s for _, s in gen], n_cells, seed)
     return os.path.join(FIX, "cds_ABC.fa"), os.path.join(FIX, "genomic_ABC.fa"), reads
+
+
+# ---- synthetic IMGT-like databases (configs 3-5) --------------------------------------------------------------------
+def _mutate(rng, seq, n_sub, lo, hi):
+    s = bytearray(seq.encode())
+    for p in rng.integers(lo, hi, size=n_sub):
+        s[p] = b"ACGT"[(b"ACGT".index(s[p]) + int(rng.integers(1, 4))) % 4]
+    return s.decode()
+
+
+def make_db(out_dir, n_per_gene, seed, genes=("A", "B", "C"), extra_genes=()):
+    """Writes hla_nuc.fasta, hla_gen.fasta, Allele_status.txt for a synthetic DB derived from the six fixture alleles.
+    Every allele is a fixture allele of its gene with 1-6 substitutions concentrated in the exon 2-3 stretch of the CDS
+    (positions 74-620) and, independently, in the genomic copy. `extra_genes` (e.g. DRB1, DQA1 ...) are fabricated from
+    the A/B/C templates by ~12 % divergence so that they behave as separate genes. Names follow src/hla.rs:49.
+    -> list of allele names in FASTA order."""
+    os.makedirs(out_dir, exist_ok=True)
+    rng = np.random.default_rng(seed)
+    cds, gen = fixture_alleles()
+    by_gene = {}
+    for (h, s), (_, g) in zip(cds, gen):
+        by_gene.setdefault(h.split(" ")[1].split("*")[0], []).append((s, g))
+    templates = dict(by_gene)
+    for k, eg in enumerate(extra_genes):
+        base = by_gene[("A", "B", "C")[k % 3]]
+        templates[eg] = [(_mutate(rng, s, len(s) // 8, 0, len(s)), _mutate(rng, g, len(g) // 8, 0, len(g))) for s, g in base]
+    nuc, gn, status, names = [], [], [], []
+    hid = 10000
+    for gene in list(genes) + list(extra_genes):
+        for i in range(n_per_gene):
+            s, g = templates[gene][i % len(templates[gene])]
+            if i >= len(templates[gene]):
+                k = int(rng.integers(1, 7))
+                s = _mutate(rng, s, k, 74, min(620, len(s)))
+                g = _mutate(rng, g, k, 200, len(g) - 200)
+            f1, f2, f3 = 1 + i // 400, 1 + (i // 20) % 20, 1 + i % 20
+            name = "%s*%02d:%02d:%02d" % (gene, f1, f2, f3)
+            hid += 1
+            nuc.append(("HLA:HLA%05d %s %d bp" % (hid, name, len(s)), s))
+            gn.append(("HLA:HLA%05d %s %d bp" % (hid, name, len(g)), g))
+            status.append("%s,1,1,Confirmed,1,%d,Full,gDNA" % (name, len(s)))
+            names.append(name)
+    write_fasta(os.path.join(out_dir, "hla_nuc.fasta"), nuc)
+    write_fasta(os.path.join(out_dir, "hla_gen.fasta"), gn)
+    with open(os.path.join(out_dir, "Allele_status.txt"), "w") as f:
+        f.write("# file: Allele_status.txt (synthetic)\nAllele,Cells,Groups,Confirmed,Start,End,Partial,Type\n")
+        f.write("\n".join(status) + "\n")
+    return names
+
+
+def reads_for_db(n, db_dir, donor, n_cells, seed, **kw):
+    """Reads simulated from the `donor` alleles (names) of a synthetic DB (genotyping input)."""
+    nuc = {h.split(" ")[1]: s for h, s in read_fasta(os.path.join(db_dir, "hla_nuc.fasta"))}
+    gn = {h.split(" ")[1]: s for h, s in read_fasta(os.path.join(db_dir, "hla_gen.fasta"))}
+    return make_reads(n, [nuc[a] for a in donor], [gn[a] for a in donor], n_cells, seed, **kw)
