@@ -211,6 +211,9 @@ int hlac_em_wrapper(const char* hla_index, const char* hla_counts, const char* c
 int hlac_map_and_count_pseudo(const char* bam, const char* out_dir, const char* barcodes_path, const char* region,
                               const char* cds, const char* genomic, int primary_only, int device, hlac_coo* entries,
                               hlac_metrics* metrics, uint32_t* n_cells_out);
+/* host BAM reader self-check (BamSeqReader, mapping.rs:231-279): count of CB+UB records in the selection and an
+ * FNV-1a checksum over (2-bit sequence, CB, UB, primary) in file order; region NULL = the unmapped tail ("*") */
+int hlac_bam_scan(const char* bam, const char* region, uint64_t* n_records, uint64_t* checksum);
 /* sc_hla_count's _main (main.rs:151-298): argv as the CLI takes it. */
 int hlac_main(int argc, const char* const* argv);
 

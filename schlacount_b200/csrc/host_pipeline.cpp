@@ -1,0 +1,418 @@
+// Host driver above the C ABI: the three entry points src/main.rs imports (mapping_wrapper, em_wrapper,
+// map_and_count_pseudo), load_barcodes, the output writers and sc_hla_count's _main. BAM/FASTA I/O, barcode and UMI
+// interning stay on the host; every map_read / count() / eq_class_counts / squarem call goes through the hlac_* GPU
+// sessions — there is no CPU implementation of those here.
+#include <sys/stat.h>
+#include <zlib.h>
+
+#include <algorithm>
+#include <charconv>
+#include <cmath>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <sstream>
+#include <unordered_map>
+
+#include "bam_reader.hpp"
+#include "common.hpp"
+#include "hla_fasta.hpp"
+
+using namespace hlac;
+
+namespace {
+
+bool path_exists(const std::string& p) { struct stat st; return stat(p.c_str(), &st) == 0; }
+void make_dirs(const std::string& p) {
+  std::string cur;
+  for (size_t i = 0; i <= p.size(); i++) {
+    if (i == p.size() || p[i] == '/') { if (!cur.empty() && !path_exists(cur)) { if (mkdir(cur.c_str(), 0777) != 0) throw Error(HLAC_ERR_IO, "cannot create directory " + cur); } }
+    if (i < p.size()) cur += p[i];
+  }
+}
+std::string join(const std::string& a, const std::string& b) { return a.empty() ? b : (a.back() == '/' ? a + b : a + "/" + b); }
+void info(const std::string& m) { std::cerr << "[INFO] " << m << std::endl; }
+
+void check(int rc) { if (rc != HLAC_OK) throw Error(rc, hlac_last_error()); }
+
+// src/locus.rs:26-48 — "chr:start-end" (commas allowed in numbers) or a bare contig
+struct Locus { std::string chrom; uint64_t start = 0, end = 1ull << 32; };
+Locus parse_locus(const std::string& s) {
+  Locus l;
+  size_t colon = s.rfind(':');
+  if (colon == std::string::npos) { l.chrom = s; return l; }
+  l.chrom = s.substr(0, colon);
+  std::string rest;
+  for (char c : s.substr(colon + 1)) if (c != ',') rest += c;
+  size_t dash = rest.find('-');
+  if (dash == std::string::npos || dash == 0 || dash + 1 >= rest.size()) throw Error(HLAC_ERR_ARG, "invalid locus: " + s);
+  for (char c : rest) if (c != '-' && (c < '0' || c > '9')) throw Error(HLAC_ERR_ARG, "invalid locus: " + s);
+  l.start = std::stoull(rest.substr(0, dash)); l.end = std::stoull(rest.substr(dash + 1));
+  return l;
+}
+
+// src/main.rs:406-424 + src/io.rs: column = line index, last occurrence wins, gzip sniffed
+std::unordered_map<std::string, uint32_t> load_barcodes(const std::string& path) {
+  gzFile g = gzopen(path.c_str(), "rb");   // gzopen reads plain files transparently
+  if (!g) throw Error(HLAC_ERR_IO, "cannot open barcode file " + path);
+  std::string data; char buf[1 << 16]; int k;
+  while ((k = gzread(g, buf, sizeof buf)) > 0) data.append(buf, k);
+  gzclose(g);
+  std::unordered_map<std::string, uint32_t> m;
+  uint32_t line = 0; size_t p = 0;
+  while (p < data.size()) {
+    size_t e = data.find('\n', p);
+    std::string l = data.substr(p, e == std::string::npos ? std::string::npos : e - p);
+    if (!l.empty() && l.back() == '\r') l.pop_back();
+    m[l] = line++;
+    if (e == std::string::npos) break;
+    p = e + 1;
+  }
+  if (m.empty()) throw Error(HLAC_ERR_FORMAT, "Loaded 0 barcodes. Is your barcode file gzipped or empty?");
+  return m;
+}
+
+// Rust `{}` for f64: shortest round-trip digits, never scientific
+std::string fmt_f64(double v) {
+  if (std::isnan(v)) return "NaN";
+  if (std::isinf(v)) return v > 0 ? "inf" : "-inf";
+  char buf[512];
+  auto r = std::to_chars(buf, buf + sizeof buf, v, std::chars_format::fixed);
+  return std::string(buf, r.ptr);
+}
+
+// pinned batch assembly for the GPU sessions
+struct BatchBuilder {
+  uint32_t wpr = 0; size_t cap; uint64_t n = 0;
+  uint64_t* seq = nullptr; uint16_t* len = nullptr; uint32_t* cell = nullptr; uint32_t* umi = nullptr; uint8_t* flags = nullptr;
+  std::unordered_map<std::string, uint32_t> umi_ids;   // UMIs that are not <=15 ACGT bases
+  explicit BatchBuilder(size_t capacity) : cap(capacity) {}
+  ~BatchBuilder() { release(); }
+  void release() { for (void* p : {(void*)seq, (void*)len, (void*)cell, (void*)umi, (void*)flags}) if (p) hlac_host_free(p); seq = nullptr; len = nullptr; cell = nullptr; umi = nullptr; flags = nullptr; }
+  void alloc(uint32_t words) {
+    release(); wpr = words;
+    check(hlac_host_alloc(cap * wpr * 8, (void**)&seq)); check(hlac_host_alloc(cap * 2, (void**)&len));
+    check(hlac_host_alloc(cap * 4, (void**)&cell)); check(hlac_host_alloc(cap * 4, (void**)&umi)); check(hlac_host_alloc(cap, (void**)&flags));
+  }
+  uint32_t umi_key(const std::string& u) {
+    uint32_t k;
+    if (hlac_umi_key(u.data(), (uint32_t)u.size(), &k) == HLAC_OK) return k;
+    auto it = umi_ids.find(u);
+    if (it == umi_ids.end()) it = umi_ids.emplace(u, 0x80000000u | (uint32_t)umi_ids.size()).first;
+    return it->second;
+  }
+  bool fits(size_t bases) const { return wpr && bases <= (size_t)wpr * 32 && n < cap; }
+  void add(const BamRecord& r, uint32_t cell_id) {
+    uint64_t* w = seq + n * wpr;
+    for (uint32_t i = 0; i < wpr; i++) w[i] = 0;
+    for (size_t i = 0; i < r.seq.size(); i++) w[i >> 5] |= (uint64_t)r.seq[i] << (62 - 2 * (i & 31));
+    len[n] = (uint16_t)r.seq.size(); cell[n] = cell_id; umi[n] = umi_key(r.umi); flags[n] = r.primary ? HLAC_FLAG_PRIMARY : 0;
+    n++;
+  }
+  hlac_batch batch() const { hlac_batch b{}; b.seq = seq; b.len = len; b.cell = cell; b.umi = umi; b.flags = flags; b.n = n; b.words_per_read = wpr; return b; }
+};
+
+// Streams the selected BAM records into a session through pinned batches. `flush` pushes one batch and syncs.
+template <typename CellFn, typename Flush>
+uint64_t stream_records(BamReader& bam, BatchBuilder& bb, CellFn cell_of, Flush flush) {
+  BamRecord rec; uint64_t total = 0;
+  while (bam.next(rec)) {
+    if (rec.seq.size() > 65535) throw Error(HLAC_ERR_LIMIT, "read longer than 65535 bases");
+    if (!bb.fits(rec.seq.size())) {
+      if (bb.n) { flush(); bb.n = 0; }
+      const uint32_t need = std::max<uint32_t>(3, (uint32_t)((rec.seq.size() + 31) / 32));
+      if (need > 16) throw Error(HLAC_ERR_LIMIT, "read longer than 512 bases");
+      if (need > bb.wpr) bb.alloc(need);
+    }
+    bb.add(rec, cell_of(rec));
+    total++;
+  }
+  if (bb.n) { flush(); bb.n = 0; }
+  return total;
+}
+
+constexpr const char* COUNTS_MAGIC = "HLACCNT1";
+
+void write_tables(const std::string& path, const hlac_class_tables& t) {
+  std::ofstream o(path, std::ios::binary);
+  if (!o) throw Error(HLAC_ERR_IO, "cannot write " + path);
+  auto w = [&](const void* p, size_t n) { o.write((const char*)p, n); };
+  w(COUNTS_MAGIC, 8); w(&t.nitems, 4); w(&t.nreads, 4);
+  w(&t.n_read_classes, 8); w(t.reads_off, (t.n_read_classes + 1) * 8);
+  const uint64_t nr = t.reads_off[t.n_read_classes]; w(t.reads_tx, nr * 4); w(t.reads_cnt, t.n_read_classes * 4);
+  w(&t.n_umi_classes, 8); w(t.umi_off, (t.n_umi_classes + 1) * 8);
+  const uint64_t nu = t.umi_off[t.n_umi_classes]; w(t.umi_tx, nu * 4); w(t.umi_cnt, t.n_umi_classes * 4);
+  w(t.reads_explained, (size_t)t.nitems * 8);
+}
+
+struct OwnedTables {
+  hlac_class_tables t{};
+  std::vector<uint64_t> roff, uoff, rex; std::vector<uint32_t> rtx, rcnt, utx, ucnt;
+};
+void read_tables(const std::string& path, OwnedTables& ot) {
+  std::ifstream f(path, std::ios::binary);
+  if (!f) throw Error(HLAC_ERR_IO, "cannot open " + path);
+  auto r = [&](void* p, size_t n) { f.read((char*)p, n); if ((size_t)f.gcount() != n) throw Error(HLAC_ERR_FORMAT, path + ": truncated counts file"); };
+  char magic[8]; r(magic, 8);
+  if (memcmp(magic, COUNTS_MAGIC, 8) != 0) throw Error(HLAC_ERR_FORMAT, path + ": not a counts file written by this library (the reference's bincode EqClassDb is not read)");
+  auto& t = ot.t;
+  r(&t.nitems, 4); r(&t.nreads, 4);
+  r(&t.n_read_classes, 8); ot.roff.resize(t.n_read_classes + 1); r(ot.roff.data(), ot.roff.size() * 8);
+  ot.rtx.resize(std::max<uint64_t>(ot.roff.back(), 1)); r(ot.rtx.data(), ot.roff.back() * 4); ot.rcnt.resize(std::max<uint64_t>(t.n_read_classes, 1)); r(ot.rcnt.data(), t.n_read_classes * 4);
+  r(&t.n_umi_classes, 8); ot.uoff.resize(t.n_umi_classes + 1); r(ot.uoff.data(), ot.uoff.size() * 8);
+  ot.utx.resize(std::max<uint64_t>(ot.uoff.back(), 1)); r(ot.utx.data(), ot.uoff.back() * 4); ot.ucnt.resize(std::max<uint64_t>(t.n_umi_classes, 1)); r(ot.ucnt.data(), t.n_umi_classes * 4);
+  ot.rex.resize(std::max<uint32_t>(t.nitems, 1)); r(ot.rex.data(), (size_t)t.nitems * 8);
+  t.reads_off = ot.roff.data(); t.reads_tx = ot.rtx.data(); t.reads_cnt = ot.rcnt.data();
+  t.umi_off = ot.uoff.data(); t.umi_tx = ot.utx.data(); t.umi_cnt = ot.ucnt.data(); t.reads_explained = ot.rex.data();
+}
+
+void copy_out(const std::string& s, char* out, size_t cap) {
+  if (!out || cap == 0) return;
+  if (s.size() + 1 > cap) throw Error(HLAC_ERR_ARG, "output path buffer too small");
+  memcpy(out, s.c_str(), s.size() + 1);
+}
+
+struct IndexHandle { hlac_index* p = nullptr; ~IndexHandle() { if (p) hlac_index_free(p); } };
+struct GenoHandle { hlac_geno* p = nullptr; ~GenoHandle() { if (p) hlac_geno_free(p); } };
+struct CountHandle { hlac_count* p = nullptr; ~CountHandle() { if (p) hlac_count_free(p); } };
+
+constexpr size_t BATCH_READS = 1 << 20;
+
+}  // namespace
+
+#define HLAC_API_TRY try {
+#define HLAC_API_CATCH                                                                       \
+  }                                                                                          \
+  catch (const hlac::Error& e) { hlac::set_last_error(e.what()); return e.code; }           \
+  catch (const std::exception& e) { hlac::set_last_error(e.what()); return HLAC_ERR_STATE; } \
+  return HLAC_OK;
+
+namespace {
+
+// mapping_wrapper's body (mapping.rs:320-404) on an index that is already resident on the device
+std::string mapping_impl(hlac_index* index, const char* outdir, const char* bam, const char* region, int use_unmapped) {
+  info("Mapping reads from BAM to database");
+  GenoHandle g; check(hlac_geno_new(index, &g.p));
+  BamReader reader(bam);
+  std::unordered_map<std::string, uint32_t> bc_ids;   // mapping_wrapper uses every barcode (no whitelist)
+  auto cell_of = [&](const BamRecord& r) { return bc_ids.emplace(r.barcode, (uint32_t)bc_ids.size()).first->second; };
+  BatchBuilder bb(BATCH_READS);
+  std::string counts = outdir;   // PathBuf::set_extension("counts.bin") (mapping.rs:328-329)
+  { size_t slash = counts.rfind('/'), dot = counts.rfind('.');
+    if (dot != std::string::npos && (slash == std::string::npos || dot > slash) && dot != slash + 1) counts.erase(dot);
+    counts += ".counts.bin"; }
+  auto report = [&](const char* what, uint64_t rid) {
+    uint64_t some = 0, lng = 0; check(hlac_geno_stats(g.p, &some, &lng, nullptr, nullptr, nullptr));
+    info("analyzed " + std::to_string(rid) + what + " reads. Mapped " + std::to_string(some) + ", used " + std::to_string(lng) +
+         " with score at least " + std::to_string(MIN_SCORE_CALL));
+  };
+  if (region) { Locus l = parse_locus(region); reader.fetch(l.chrom, l.start, l.end); }
+  else reader.fetch_unmapped();   // locus == None never happens from main.rs; keep the call total
+  uint64_t rid = stream_records(reader, bb, cell_of, [&] { hlac_batch b = bb.batch(); check(hlac_geno_push(g.p, &b, 0)); });
+  report("", rid);
+  if (use_unmapped) {
+    reader.fetch_unmapped();
+    uint64_t rid2 = stream_records(reader, bb, cell_of, [&] { hlac_batch b = bb.batch(); check(hlac_geno_push(g.p, &b, 1)); });
+    report(" unaligned", rid2);
+  }
+  hlac_class_tables t{};
+  check(hlac_geno_finish(g.p, &t));
+  struct Free { hlac_class_tables* t; ~Free() { hlac_class_tables_free(t); } } fr{&t};
+  write_tables(counts, t);
+  return counts;
+}
+
+// em_wrapper's body (em.rs:346-475) given the index handle (names only are needed from it)
+void em_impl(hlac_index* index, const char* hla_counts, const char* cds_db, const char* gen_db, const char* outdir, int device,
+             std::string& gen_name, std::string& cds_name) {
+  struct { hlac_index* p; } ix{index};
+  OwnedTables ot; read_tables(hla_counts, ot);
+  hlac_index_info inf; check(hlac_index_get_info(ix.p, &inf));
+  if (inf.n_tx != ot.t.nitems) throw Error(HLAC_ERR_ARG, "counts file does not match the index");
+  std::vector<double> theta(std::max<uint32_t>(ot.t.nitems, 1)); uint32_t iters = 0;
+  check(hlac_squarem(&ot.t, device, theta.data(), &iters));
+  hlac_calls calls{}; check(hlac_call_genotypes(ix.p, &ot.t, theta.data(), &calls));
+  struct Free { hlac_calls* c; ~Free() { hlac_calls_free(c); } } fr{&calls};
+  {
+    std::ofstream w(join(outdir, "weights.tsv")); if (!w) throw Error(HLAC_ERR_IO, "cannot write weights.tsv");
+    w << "allele_name\tem_weight\treads_explained\n";
+    for (uint32_t i = 0; i < calls.n_weights; i++) w << hlac_index_tx_name(ix.p, calls.w_tx[i]) << '\t' << fmt_f64(calls.w_em[i]) << '\t' << fmt_f64(calls.w_frac[i]) << '\n';
+    std::ofstream p(join(outdir, "pairs.tsv")); if (!p) throw Error(HLAC_ERR_IO, "cannot write pairs.tsv");
+    p << "allele_1\tallele_2\treads_explained\n";
+    for (uint32_t i = 0; i < calls.n_pairs; i++) p << hlac_index_tx_name(ix.p, calls.p_a[i]) << '\t' << hlac_index_tx_name(ix.p, calls.p_b[i]) << '\t' << fmt_f64(calls.p_frac[i]) << '\n';
+  }
+  std::set<std::string> called;
+  for (uint32_t i = 0; i < calls.n_called; i++) called.insert(hlac_index_tx_name(ix.p, calls.called[i]));
+  info("Writing CDS of " + std::to_string(called.size()) + " alleles to file");
+  gen_name = join(outdir, "gen_pseudoaln.fasta"); cds_name = join(outdir, "cds_pseudoaln.fasta");
+  auto filter = [&](const std::string& src, const std::string& dst) {   // em.rs:445-473
+    std::ofstream o(dst); if (!o) throw Error(HLAC_ERR_IO, "cannot write " + dst);
+    for (auto& rec : read_fasta(src)) {
+      if (rec.desc.empty()) throw Error(HLAC_ERR_FORMAT, "no HLA allele");
+      if (called.count(rec.desc.substr(0, rec.desc.find(' ')))) write_fasta_record(o, rec);
+    }
+  };
+  filter(cds_db, cds_name); filter(gen_db, gen_name);
+}
+
+}  // namespace
+
+extern "C" {
+
+// src/mapping.rs:310-405
+int hlac_mapping_wrapper(const char* hla_index, const char* outdir, const char* bam, const char* region, int use_unmapped,
+                         int device, char* counts_path_out, size_t cap) {
+  HLAC_API_TRY
+  if (!hla_index || !outdir || !bam) throw Error(HLAC_ERR_ARG, "null argument");
+  info("Reading database index from disk");
+  IndexHandle ix; check(hlac_index_from_idx_file(hla_index, device, &ix.p));
+  info("Finished reading index!");
+  copy_out(mapping_impl(ix.p, outdir, bam, region, use_unmapped), counts_path_out, cap);
+  HLAC_API_CATCH
+}
+
+// src/em.rs:339-476
+int hlac_em_wrapper(const char* hla_index, const char* hla_counts, const char* cds_db, const char* gen_db, const char* outdir,
+                    int device, char* gen_path_out, char* cds_path_out, size_t cap) {
+  HLAC_API_TRY
+  if (!hla_index || !hla_counts || !cds_db || !gen_db || !outdir) throw Error(HLAC_ERR_ARG, "null argument");
+  IndexHandle ix; check(hlac_index_from_idx_file(hla_index, -1, &ix.p));   // names only; the EM itself runs on `device`
+  std::string g, c;
+  em_impl(ix.p, hla_counts, cds_db, gen_db, outdir, device, g, c);
+  copy_out(g, gen_path_out, cap); copy_out(c, cds_path_out, cap);
+  HLAC_API_CATCH
+}
+
+// src/mapping.rs:640-821
+int hlac_map_and_count_pseudo(const char* bam, const char* out_dir, const char* barcodes_path, const char* region, const char* cds,
+                              const char* genomic, int primary_only, int device, hlac_coo* entries, hlac_metrics* metrics,
+                              uint32_t* n_cells_out) {
+  HLAC_API_TRY
+  if (!bam || !out_dir || !barcodes_path || !region || !cds || !genomic) throw Error(HLAC_ERR_ARG, "null argument");
+  IndexHandle gix, cix;
+  check(hlac_index_from_fasta(genomic, nullptr, device, &gix.p)); info("Built genome index for pseudoalignment");
+  check(hlac_index_from_fasta(cds, nullptr, device, &cix.p)); info("Built CDS index for pseudoalignment");
+  auto barcodes = load_barcodes(barcodes_path);
+  const uint32_t n_cells = (uint32_t)barcodes.size();
+  uint32_t max_col = 0; for (auto& kv : barcodes) max_col = std::max(max_col, kv.second);
+  if (max_col >= n_cells) throw Error(HLAC_ERR_ARG, "duplicate lines in the barcode file (a column index exceeds the number of distinct barcodes)");
+  CountHandle s; check(hlac_count_new(cix.p, gix.p, n_cells, primary_only, &s.p));
+  { std::ofstream lab(join(out_dir, "labels.tsv")); if (!lab) throw Error(HLAC_ERR_IO, "cannot write labels.tsv");
+    for (uint32_t i = 0; i < hlac_count_nrows(s.p); i++) lab << hlac_count_row_name(s.p, i) << '\n'; }
+  BamReader reader(bam);
+  Locus l = parse_locus(region); reader.fetch(l.chrom, l.start, l.end);
+  BatchBuilder bb(BATCH_READS);
+  auto cell_of = [&](const BamRecord& r) { auto it = barcodes.find(r.barcode); return it == barcodes.end() ? HLAC_NOT_A_CELL : it->second; };
+  stream_records(reader, bb, cell_of, [&] { hlac_batch b = bb.batch(); check(hlac_count_push(s.p, &b)); check(hlac_count_sync(s.p)); });
+  hlac_metrics m{}; check(hlac_count_finish(s.p, entries, &m));
+  if (metrics) *metrics = m;
+  if (n_cells_out) *n_cells_out = n_cells;
+  info("analyzed " + std::to_string(m.num_reads) + " reads. Mapped " + std::to_string(m.num_gen_align + m.num_cds_align) + " with score at least " + std::to_string(MIN_SCORE_COUNT_PSEUDO));
+  HLAC_API_CATCH
+}
+
+// Host-reader self check: number of CB+UB records the selection yields and an FNV-1a checksum over
+// (2-bit sequence, CB, UB, primary) in file order. region == NULL selects the unmapped tail ("*").
+int hlac_bam_scan(const char* bam, const char* region, uint64_t* n_records, uint64_t* checksum) {
+  HLAC_API_TRY
+  if (!bam) throw Error(HLAC_ERR_ARG, "null argument");
+  BamReader reader(bam);
+  if (region) { Locus l = parse_locus(region); reader.fetch(l.chrom, l.start, l.end); } else reader.fetch_unmapped();
+  uint64_t n = 0, h = 0xcbf29ce484222325ULL;
+  auto mixb = [&](uint8_t b) { h = (h ^ b) * 0x100000001b3ULL; };
+  BamRecord r;
+  while (reader.next(r)) {
+    for (uint8_t b : r.seq) mixb(b);
+    mixb(0xFF); for (char c : r.barcode) mixb((uint8_t)c);
+    mixb(0xFE); for (char c : r.umi) mixb((uint8_t)c);
+    mixb(r.primary ? 1 : 0);
+    n++;
+  }
+  if (n_records) *n_records = n;
+  if (checksum) *checksum = h;
+  HLAC_API_CATCH
+}
+
+// src/main.rs:151-298
+int hlac_main(int argc, const char* const* argv) {
+  HLAC_API_TRY
+  std::map<std::string, std::string> opt = {{"out_dir", "hla-typer-results"}, {"pl_tmp", "pseudoaligner_tmp"}, {"region", "6:28510120-33480577"},
+                                            {"log_level", "info"}, {"device", "0"}};
+  std::map<std::string, bool> flag;
+  static const std::map<std::string, std::string> names = {
+      {"-b", "bam"}, {"--bam", "bam"}, {"-c", "cell_barcodes"}, {"--cell-barcodes", "cell_barcodes"}, {"-o", "out_dir"}, {"--out-dir", "out_dir"},
+      {"--pl-tmp", "pl_tmp"}, {"-g", "fastagenomic"}, {"--fasta-genomic", "fastagenomic"}, {"-f", "fastacds"}, {"--fasta-cds", "fastacds"},
+      {"-d", "hladbdir"}, {"--hladb-dir", "hladbdir"}, {"-i", "hlaindex"}, {"--hla-index", "hlaindex"}, {"-r", "region"}, {"--region", "region"},
+      {"--log-level", "log_level"}, {"--device", "device"}};
+  static const std::map<std::string, std::string> flags = {{"--primary-alignments", "primary"}, {"--use-exact-count", "exact"}, {"--unmapped", "unmapped"}};
+  for (int i = 1; i < argc; i++) {
+    std::string a = argv[i];
+    if (flags.count(a)) { flag[flags.at(a)] = true; continue; }
+    std::string val; size_t eq = a.find('=');
+    if (a.rfind("--", 0) == 0 && eq != std::string::npos) { val = a.substr(eq + 1); a = a.substr(0, eq); }
+    else if (names.count(a)) { if (i + 1 >= argc) throw Error(HLAC_ERR_ARG, "missing value for " + a); val = argv[++i]; }
+    if (!names.count(a)) throw Error(HLAC_ERR_ARG, "unknown argument " + a);
+    opt[names.at(a)] = val;
+  }
+  if (!opt.count("bam")) throw Error(HLAC_ERR_ARG, "You must provide a BAM file");
+  if (!opt.count("cell_barcodes")) throw Error(HLAC_ERR_ARG, "You must provide a cell barcodes file");
+  if (opt["log_level"] != "info" && opt["log_level"] != "debug" && opt["log_level"] != "error") throw Error(HLAC_ERR_ARG, "Log level must be 'info', 'debug', or 'error'");
+  if (flag["exact"]) throw Error(HLAC_ERR_ARG, "--use-exact-count (banded Smith-Waterman, mapping.rs:407-637) is outside this build's hot path");
+  const int device = std::stoi(opt["device"]);
+  const std::string bam = opt["bam"], bcs = opt["cell_barcodes"], out_dir = opt["out_dir"], pl = opt["pl_tmp"];
+  // check_inputs_exist (main.rs:302-348)
+  for (auto& p : {bam, bcs}) if (!path_exists(p)) throw Error(HLAC_ERR_IO, "Input \"" + p + "\" does not exist");
+  if (bam.size() < 4 || bam.substr(bam.size() - 4) != ".bam") throw Error(HLAC_ERR_ARG, "BAM file did not end in .bam (CRAM is not supported by this build). Unable to validate");
+  if (!path_exists(bam + ".bai")) throw Error(HLAC_ERR_IO, "BAM index " + bam + ".bai does not exist");
+  if (path_exists(out_dir)) throw Error(HLAC_ERR_IO, "Specified output directory " + out_dir + " already exists");
+  make_dirs(out_dir);
+  Locus region = parse_locus(opt["region"]); (void)region;
+  std::string genomic = opt["fastagenomic"], cds = opt["fastacds"];
+  if (genomic.empty() || cds.empty()) {
+    if (path_exists(pl)) throw Error(HLAC_ERR_IO, "Specified tempdir " + pl + " already exists");
+    make_dirs(pl);
+    const std::string db = opt["hladbdir"];
+    if (db.empty()) throw Error(HLAC_ERR_ARG, "Must provide either -d (database directory) or both -g and -f (FASTA sequences).");
+    if (!path_exists(db)) throw Error(HLAC_ERR_IO, "IMGT-HLA database directory " + db + " does not exist");
+    for (auto f : {"hla_gen.fasta", "hla_nuc.fasta", "Allele_status.txt"}) if (!path_exists(join(db, f))) throw Error(HLAC_ERR_IO, std::string("IMGT-HLA database file ") + f + " does not exist");
+    const std::string index = opt["hlaindex"];
+    IndexHandle ix;
+    if (index.empty()) {
+      // make_hla_index (hla.rs:230-264): the index is built in memory; the bincode+boomphf `.idx` file the Rust
+      // reader expects is not emitted by this build, so there is nothing to reuse with -i.
+      info("Building index from fasta");
+      check(hlac_index_from_fasta(join(db, "hla_nuc.fasta").c_str(), join(db, "Allele_status.txt").c_str(), device, &ix.p));
+      info("Finished building index!");
+    } else {
+      if (!path_exists(index)) throw Error(HLAC_ERR_IO, "Pseudoalignment index " + index + " does not exist. Omit parameter -i to generate automatically.");
+      info("Reading database index from disk");
+      check(hlac_index_from_idx_file(index.c_str(), device, &ix.p));
+    }
+    const std::string counts = mapping_impl(ix.p, join(pl, "pseudoaligner").c_str(), bam.c_str(), opt["region"].c_str(), flag["unmapped"]);
+    em_impl(ix.p, counts.c_str(), join(db, "hla_nuc.fasta").c_str(), join(db, "hla_gen.fasta").c_str(), pl.c_str(), device, genomic, cds);
+  }
+  for (auto& p : {cds, genomic}) if (!path_exists(p)) throw Error(HLAC_ERR_IO, "Input file \"" + p + "\" does not exist");
+  hlac_coo coo{}; hlac_metrics m{}; uint32_t n_cells = 0;
+  check(hlac_map_and_count_pseudo(bam.c_str(), out_dir.c_str(), bcs.c_str(), opt["region"].c_str(), cds.c_str(), genomic.c_str(), flag["primary"], device, &coo, &m, &n_cells));
+  struct Free { hlac_coo* c; ~Free() { hlac_coo_free(c); } } fr{&coo};
+  info("Initialized a " + std::to_string(coo.nrows) + " features x " + std::to_string(n_cells) + " cell barcodes matrix.");
+  info("Number of alignments evaluated (with 'CB' and 'UB' tags): " + std::to_string(m.num_reads));
+  info(std::string(flag["primary"] ? "Number of alignments skipped due to not being primary: " : "Number of alignments that were not primary: ") + std::to_string(m.num_non_primary));
+  info("Number of alignments skipped due to not being associated with a cell barcode in the list provided: " + std::to_string(m.num_not_cell_bc));
+  info("Number of reads with no alignment score above threshold: " + std::to_string(m.num_not_aligned));
+  info("Number of alignments to CDS sequence: " + std::to_string(m.num_cds_align));
+  info("Number of alignments to genomic sequence: " + std::to_string(m.num_gen_align));
+  // sprs::io::write_matrix_market of the TriMat (main.rs:278-283): 1-based triplets in insertion order
+  { std::ofstream mm(join(out_dir, "count_matrix.mtx")); if (!mm) throw Error(HLAC_ERR_IO, "cannot write count_matrix.mtx");
+    mm << "%%MatrixMarket matrix coordinate integer general\n% written by sprs\n" << coo.nrows << ' ' << n_cells << ' ' << coo.n << '\n';
+    for (uint64_t i = 0; i < coo.n; i++) mm << coo.row[i] + 1 << ' ' << coo.col[i] + 1 << ' ' << coo.val[i] << '\n'; }
+  // summary.tsv: every row with its molecule total (main.rs:286-296); row names = labels.tsv
+  { std::vector<uint64_t> sums(coo.nrows, 0);
+    for (uint64_t i = 0; i < coo.n; i++) sums[coo.row[i]] += coo.val[i];
+    std::ifstream lab(join(out_dir, "labels.tsv")); std::ofstream sm(join(out_dir, "summary.tsv"));
+    std::string name; for (uint32_t r = 0; r < coo.nrows && std::getline(lab, name); r++) sm << name << '\t' << sums[r] << '\n'; }
+  HLAC_API_CATCH
+}
+
+}  // extern "C"

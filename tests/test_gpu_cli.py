@@ -1,0 +1,54 @@
+"""The reference's two end-to-end regression tests (src/main.rs:432-500) through the drop-in CLI `sc_hla_count`
+(C++ host driver + CUDA kernels): same flags, count_matrix.mtx compared with the reference's golden matrices."""
+import os
+import subprocess
+
+import pytest
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+BIN = os.path.join(H.ROOT, "schlacount_b200", "sc_hla_count")
+
+
+def _run(args, cwd):
+    return subprocess.run([BIN] + args, cwd=cwd, capture_output=True, text=True)
+
+
+def test_allele_fasta_cli(tmp_path):
+    r = _run(["-b", os.path.join(H.FIX, "test.bam"), "-g", os.path.join(H.FIX, "genomic_ABC.fa"), "-f",
+              os.path.join(H.FIX, "cds_ABC.fa"), "-c", os.path.join(H.FIX, "barcodes1.tsv"), "-o", str(tmp_path / "r"),
+              "--pl-tmp", str(tmp_path / "p")], tmp_path)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert H.read_mtx(tmp_path / "r" / "count_matrix.mtx") == H.read_mtx(os.path.join(H.FIX, "test_allele_fasta.mtx"))
+    # byte-level layout of the sprs writer (main.rs:282-283)
+    assert open(tmp_path / "r" / "count_matrix.mtx").read() == open(os.path.join(H.FIX, "test_allele_fasta.mtx")).read()
+    assert open(tmp_path / "r" / "labels.tsv").read().split() == ["A*02:01:154", "A*31:01:02:01", "A", "B*27:05:02:01",
+                                                                  "B*51:01:01:01", "B", "C*02:02:02:01", "C*14:02:01:01", "C"]
+    summ = [l.split("\t") for l in open(tmp_path / "r" / "summary.tsv").read().splitlines()]
+    assert [int(x[1]) for x in summ] == [9, 10, 1, 16, 23, 3, 12, 8, 3]
+    # out-dir must not pre-exist (main.rs:341-346)
+    r2 = _run(["-b", os.path.join(H.FIX, "test.bam"), "-g", os.path.join(H.FIX, "genomic_ABC.fa"), "-f",
+               os.path.join(H.FIX, "cds_ABC.fa"), "-c", os.path.join(H.FIX, "barcodes1.tsv"), "-o", str(tmp_path / "r")], tmp_path)
+    assert r2.returncode == 1 and "already exists" in r2.stdout
+
+
+@pytest.mark.parametrize("with_index", [True, False])
+def test_call_cli(tmp_path, with_index):
+    args = ["-b", os.path.join(H.FIX, "test.bam"), "-d", os.path.join(H.FIX, "fake_db"), "-c",
+            os.path.join(H.FIX, "barcodes0.tsv"), "-o", str(tmp_path / "r"), "--pl-tmp", str(tmp_path / "p")]
+    if with_index:
+        args += ["-i", os.path.join(H.FIX, "fake_db", "hla_nuc.fasta.idx")]
+    r = _run(args, tmp_path)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert H.read_mtx(tmp_path / "r" / "count_matrix.mtx") == H.read_mtx(os.path.join(H.FIX, "test_call.mtx")) == (5, 2, [(1, 0, 1)])
+    w = [l.split("\t") for l in open(tmp_path / "p" / "weights.tsv").read().splitlines()]
+    assert w[0] == ["allele_name", "em_weight", "reads_explained"]
+    assert [x[0] for x in w[1:]] == ["A*02:01:154", "A*31:01:02:01", "B*27:05:02:01", "B*51:01:01:01", "C*14:02:01:01", "C*02:02:02:01"]
+    assert abs(float(w[1][1]) - 0.208734716595) < 1e-9 and w[1][2] == "0.28994082840236685"
+    pr = [l.split("\t") for l in open(tmp_path / "p" / "pairs.tsv").read().splitlines()]
+    assert pr[1:] == [["A*02:01:154", "A*31:01:02:01", "0.34726331360946744"], ["B*27:05:02:01", "B*51:01:01:01", "0.5410502958579881"],
+                      ["C*14:02:01:01", "C*02:02:02:01", "0.4474852071005917"]]
+    called = [l.split(" ")[1] for l in open(tmp_path / "p" / "cds_pseudoaln.fasta") if l.startswith(">")]
+    assert called == ["A*02:01:154", "B*27:05:02:01", "C*02:02:02:01", "C*14:02:01:01"]
+    assert os.path.exists(tmp_path / "p" / "pseudoaligner.counts.bin") and os.path.exists(tmp_path / "p" / "gen_pseudoaln.fasta")

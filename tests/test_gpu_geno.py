@@ -102,8 +102,7 @@ def test_synthetic_db_genotyping(sb, orc, tmp_path, n_per_gene, n_reads, seed):
     keys = sorted(umi)
     rng = np.random.default_rng(seed)
     env = 0.0
-    for order in (keys[::-1], list(rng.permutation(len(keys)))):
-        ks = [keys[i] for i in order] if not isinstance(order[0], tuple) else order
+    for ks in (keys[::-1], [keys[i] for i in rng.permutation(len(keys))]):
         th2, _ = orc.squarem_ordered(len(theta), ks, [umi[k] for k in ks])
         env = max(env, float(np.abs(th2 - ref["theta"]).max()))
     tol = np.maximum(EM_RTOL * np.abs(ref["theta"]), 2.0 * env)

@@ -1,0 +1,123 @@
+"""CPU-side checks of the product library: it loads, exports every symbol include/hlacount.h declares, its host logic
+(index loader/builder, packer, BAM reader) agrees with the oracle / an independent decoder, and compute entry points
+refuse to run without a device (no CPU fallback). No GPU needed."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import helpers as H
+
+
+@pytest.fixture(scope="module")
+def sb():
+    import schlacount_b200
+    schlacount_b200.build()
+    return schlacount_b200
+
+
+def test_exports_every_declared_symbol(sb):
+    from schlacount_b200 import _lib
+    names = _lib.declared_symbols()
+    assert len(names) >= 45
+    L = _lib.lib()
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+
+
+def test_index_build_and_idx_loader_match_fixture(sb, orc):
+    idx = os.path.join(H.FIX, "fake_db", "hla_nuc.fasta.idx")
+    o = orc.Index.from_idx(idx)
+    a = sb.Index.from_idx(idx, device=-1)
+    b = sb.Index.from_fasta(os.path.join(H.FIX, "fake_db", "hla_nuc.fasta"),
+                            os.path.join(H.FIX, "fake_db", "Allele_status.txt"), device=-1)
+    c = sb.Index.from_fasta(os.path.join(H.FIX, "cds_ABC.fa"), device=-1)
+    assert a.nodes() == o.nodes()
+    assert sorted(b.nodes()) == sorted(o.nodes()) == sorted(c.nodes())
+    assert a.tx_names == b.tx_names == c.tx_names == o.tx_names
+    info = a.info
+    assert (info["n_nodes"], info["n_bases"], info["n_kmers"], info["n_colours"], info["n_tx"]) == (204, 8729, 4037, 39, 6)
+    g = sb.Index.from_fasta(os.path.join(H.FIX, "genomic_ABC.fa"), device=-1)
+    og = orc.Index.from_fasta(os.path.join(H.FIX, "genomic_ABC.fa"))
+    assert sorted(g.nodes()) == sorted(og.nodes()) and g.info["n_kmers"] == 14237
+
+
+def test_index_from_sequences_and_errors(sb, orc, tmp_path):
+    from tools import synth
+    cds, _ = synth.fixture_alleles()
+    names = [h.split(" ")[1] for h, _ in cds]
+    a = sb.Index.from_sequences([s for _, s in cds], names, device=-1)
+    # from_sequences keeps the given order (no read_hla_cds sort): compare as node/colour-name sets
+    o = orc.Index.from_fasta(os.path.join(H.FIX, "cds_ABC.fa"))
+    def named(ix, nodes):
+        tn = ix.tx_names
+        return sorted((s, e, tuple(sorted(tn[t] for t in c))) for s, e, c in nodes)
+    assert named(a, a.nodes()) == named(o, o.nodes())
+    with pytest.raises(sb.HlacError):
+        sb.Index.from_idx(tmp_path / "missing.idx", device=-1)
+    bad = tmp_path / "bad.idx"
+    bad.write_bytes(open(os.path.join(H.FIX, "fake_db", "hla_nuc.fasta.idx"), "rb").read()[:1000])
+    with pytest.raises(sb.HlacError):
+        sb.Index.from_idx(bad, device=-1)
+
+
+def test_packer_matches_oracle(sb, orc, fixture_reads):
+    seqs = [r[0] for r in fixture_reads[:200]] + ["", "ACGTN", "acgtnRYK" * 9, "T" * 97]
+    a, la = sb.pack_reads(seqs)
+    b, lb = orc.pack_reads(seqs)
+    assert np.array_equal(a, b) and np.array_equal(la, lb)
+
+
+def test_umi_key(sb):
+    L = sb.lib()
+    k = C.c_uint32()
+    assert L.hlac_umi_key(b"ACGT", C.c_uint32(4), C.byref(k)) == 0 and k.value == (1 << 8) | 0b00011011
+    assert k.value == H.umi_key(b"ACGT", {})
+    assert L.hlac_umi_key(b"ACGN", C.c_uint32(4), C.byref(k)) != 0
+    assert L.hlac_umi_key(b"A" * 16, C.c_uint32(16), C.byref(k)) != 0
+
+
+def test_bam_reader_matches_independent_decoder(sb, fixture_reads):
+    L = sb.lib()
+    n, h = C.c_uint64(), C.c_uint64()
+    bam = os.path.join(H.FIX, "test.bam").encode()
+    assert L.hlac_bam_scan(bam, b"6:28510120-33480577", C.byref(n), C.byref(h)) == 0
+
+    def checksum(reads):
+        x = 0xcbf29ce484222325
+        code = {"A": 0, "C": 1, "G": 2, "T": 3}
+        for seq, cb, ub, primary in reads:
+            for b in [code.get(c, 0) for c in seq] + [0xFF] + list(cb) + [0xFE] + list(ub) + [1 if primary else 0]:
+                x = ((x ^ b) * 0x100000001b3) & 0xFFFFFFFFFFFFFFFF
+        return x
+    assert n.value == len(fixture_reads) == 2864
+    assert h.value == checksum(fixture_reads)
+    # a narrower region must select exactly the overlapping records, in order
+    import bamlite
+    sub = list(bamlite.fetch(os.path.join(H.FIX, "test.bam"), "6", 31268749, 31272092))
+    assert 0 < len(sub) < 2864
+    assert L.hlac_bam_scan(bam, b"6:31268749-31272092", C.byref(n), C.byref(h)) == 0
+    assert n.value == len(sub) and h.value == checksum(sub)
+    # unmapped tail of the fixture is empty
+    assert L.hlac_bam_scan(bam, None, C.byref(n), C.byref(h)) == 0 and n.value == 0
+    assert L.hlac_bam_scan(bam, b"chr6:1-2", C.byref(n), C.byref(h)) != 0   # '6' vs 'chr6' (mapping.rs:54)
+
+
+def test_no_cpu_fallback(sb):
+    """Compute entry points must fail loudly without a CUDA device."""
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    cds = sb.Index.from_fasta(os.path.join(H.FIX, "cds_ABC.fa"), device=-1)
+    with pytest.raises(sb.HlacError):
+        sb.CountSession(cds, cds, 4)
+    with pytest.raises(sb.HlacError):
+        sb.GenoSession(cds)
+    if not has_gpu:
+        with pytest.raises(sb.HlacError):
+            sb.Index.from_fasta(os.path.join(H.FIX, "cds_ABC.fa"), device=0)
+        with pytest.raises(sb.HlacError):
+            sb.squarem(4, {(0,): 1})
