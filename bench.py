@@ -40,7 +40,7 @@ SORT_BYTES_PER_KEY = 36   # 12-B record read, written sorted, read by the segmen
 class ClockSampler(threading.Thread):
     """Samples SM clock / throttle reasons of one GPU through NVML while the timed region runs."""
 
-    def __init__(self, index, period=0.02):
+    def __init__(self, index, period=0.004):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
