@@ -32,7 +32,7 @@ using namespace hlac;
 
 namespace {
 
-constexpr int MAP_THREADS = 256;
+constexpr int MAP_THREADS = 512;
 constexpr uint32_t CODE_NONE5 = 31;   // 5-bit "no code"
 constexpr int CODE_BITS = 5;
 constexpr int UMI_BITS = 32;
@@ -86,9 +86,19 @@ struct BitmapGlobal {
   __device__ __forceinline__ uint32_t operator()(uint32_t i) const { return __ldg(p + i); }
 };
 
+// Staged block kernel. One tile = MAP_THREADS reads. Instead of letting every thread run its own read through the
+// whole 4-way chain (ncu on that version: 6.65 of 32 lanes active per issued instruction), the block moves the tile
+// through stages and compacts the surviving reads into dense task queues in shared memory between stages, so that
+// the lanes of a warp always execute the same kind of work:
+//   load    filters (mapping.rs:752-763), read rows into shared memory, queue q0
+//   scan p  p = cds-fwd, cds-rev, gen-fwd, gen-rev: first-seed skip-scan for the reads still without a seed
+//           (map_read is None iff its FIRST seed scan fails, so the laziness of mapping.rs:772-790 is a cascade of scans);
+//           reads that find a seed go to the walk queue, the others to the next scan queue (revcomp built at p = 1)
+//   walk    every read with a seed: left extension + forward walk + class code + coverage policy, key append
 template <bool SMEM_BM>
-__global__ void __launch_bounds__(MAP_THREADS) k_count_map(const CountMapArgs a) {
+__global__ void __launch_bounds__(MAP_THREADS, 2) k_count_map(const CountMapArgs a) {
   extern __shared__ __align__(16) uint32_t smem[];
+  __shared__ unsigned q_cnt[3];   // [0]/[1] ping-pong scan queues, [2] walk queue
   uint32_t* rows = smem;
   if (SMEM_BM) {
     const uint32_t nb = a.cds.bitmap_words + a.gen.bitmap_words;
@@ -96,69 +106,114 @@ __global__ void __launch_bounds__(MAP_THREADS) k_count_map(const CountMapArgs a)
     for (uint32_t i = threadIdx.x; i < a.gen.bitmap_words; i += MAP_THREADS) smem[a.cds.bitmap_words + i] = __ldg(a.gen.bitmap + i);
     rows = smem + nb;
   }
-  uint32_t* fw = rows + threadIdx.x * a.row_stride;
-  uint32_t* rc = fw + a.nw;
+  uint32_t* seed_node = rows + MAP_THREADS * a.row_stride;          // per slot
+  uint32_t* seed_info = seed_node + MAP_THREADS;                    // off(20) | pos(10) | phase(2)
+  uint16_t* q = reinterpret_cast<uint16_t*>(seed_info + MAP_THREADS);   // 3 queues of MAP_THREADS slots
   unsigned long long m_reads = 0, m_nonprim = 0, m_notcell = 0, m_cds = 0, m_gen = 0, m_none = 0;
   uint32_t n_tests = 0, n_probes = 0;
   const unsigned lane = threadIdx.x & 31;
-  const uint64_t per_block = MAP_THREADS;
-  for (uint64_t base = (uint64_t)blockIdx.x * per_block; base < a.n; base += (uint64_t)gridDim.x * per_block) {
-    __syncthreads();   // rows of the previous iteration are dead; bitmaps are loaded
-    // coalesced block load of the reads into per-thread rows
-    const uint64_t nread = min((uint64_t)per_block, a.n - base);
-    const uint64_t nwords = nread * a.wpr;
-    for (uint64_t g = threadIdx.x; g < nwords; g += MAP_THREADS) {
-      const uint64_t v = __ldg(a.seq + base * a.wpr + g);
-      const uint32_t t = (uint32_t)(g / a.wpr), w = (uint32_t)(g % a.wpr);
-      uint32_t* r = rows + t * a.row_stride;
-      r[2 * w] = (uint32_t)(v >> 32);
-      r[2 * w + 1] = (uint32_t)v;
-    }
-    fw[2 * a.wpr] = 0; fw[2 * a.wpr + 1] = 0;
+  auto push = [&](int which, bool pred, unsigned slot) {   // warp-aggregated append to a shared-memory queue
+    const unsigned ballot = __ballot_sync(0xFFFFFFFFu, pred);
+    if (!ballot) return;
+    unsigned at = 0;
+    if (lane == 0) at = atomicAdd(&q_cnt[which], (unsigned)__popc(ballot));
+    at = __shfl_sync(0xFFFFFFFFu, at, 0);
+    if (pred) q[which * MAP_THREADS + at + __popc(ballot & ((1u << lane) - 1))] = (uint16_t)slot;
+  };
+  for (uint64_t base = (uint64_t)blockIdx.x * MAP_THREADS; base < a.n; base += (uint64_t)gridDim.x * MAP_THREADS) {
+    __syncthreads();   // previous tile fully consumed (rows, queues, counters); bitmaps loaded
+    if (threadIdx.x < 3) q_cnt[threadIdx.x] = 0;
     __syncthreads();
-    const uint64_t i = base + threadIdx.x;
-    uint32_t code = CODE_NONE5;
-    uint64_t key = 0;
-    if (i < a.n) {
-      m_reads++;
-      const bool primary = a.flags[i] & HLAC_FLAG_PRIMARY;
-      const uint32_t cell = a.cell[i];
-      if (!primary) m_nonprim++;
-      if (primary || !a.primary_only) {
-        if (cell == HLAC_NOT_A_CELL) m_notcell++;
-        else {
-          const int L = a.len[i];
-          bool found = false;
-#pragma unroll 1
-          for (int p = 0; p < 4; p++) {   // cds fwd, cds rev, genomic fwd, genomic rev (mapping.rs:772-790)
-            if (p == 1) make_revcomp(SharedWords{fw}, rc, L, (int)a.nw);
-            const DevIndexView& ix = p < 2 ? a.cds : a.gen;
-            CountVis vis{p < 2 ? a.cinfo_cds : a.cinfo_gen};
-            SharedWords rd{(p & 1) ? rc : fw};
-            uint32_t cov = 0;
-            if (SMEM_BM) found = map_read_walk(ix, rd, BitmapShared{smem + (p < 2 ? 0 : a.cds.bitmap_words)}, L, vis, cov, n_tests, n_probes);
-            else found = map_read_walk(ix, rd, BitmapGlobal{ix.bitmap}, L, vis, cov, n_tests, n_probes);
-            if (found) {
-              const bool good = cov > MIN_SCORE_COUNT_PSEUDO;
-              if (good) { if (p < 2) m_cds++; else m_gen++; }
-              if (p == 0 || good) code = vis.code();   // a CDS-forward hit is used whatever its coverage (mapping.rs:772-775)
-              break;
+    // ---- load ----
+    {
+      const uint64_t i = base + threadIdx.x;
+      bool keep = false;
+      if (i < a.n) {
+        m_reads++;
+        const bool primary = a.flags[i] & HLAC_FLAG_PRIMARY;
+        if (!primary) m_nonprim++;
+        if (primary || !a.primary_only) {
+          if (__ldg(a.cell + i) == HLAC_NOT_A_CELL) m_notcell++;
+          else {
+            keep = true;
+            uint32_t* fw = rows + threadIdx.x * a.row_stride;
+            for (uint32_t w = 0; w < a.wpr; w++) {
+              const uint64_t v = __ldg(a.seq + i * a.wpr + w);
+              fw[2 * w] = (uint32_t)(v >> 32); fw[2 * w + 1] = (uint32_t)v;
             }
+            fw[2 * a.wpr] = 0; fw[2 * a.wpr + 1] = 0;
           }
-          if (!found) m_none++;
-          if (code != CODE_NONE5) key = ((uint64_t)cell << (UMI_BITS + CODE_BITS)) | ((uint64_t)a.umi[i] << CODE_BITS) | code;
+        }
+        if (a.codes) a.codes[i] = (uint8_t)HLAC_CODE_NONE;
+      }
+      push(0, keep, threadIdx.x);
+    }
+    __syncthreads();
+    // ---- scan cascade ----
+#pragma unroll 1
+    for (int p = 0; p < 4; p++) {
+      const int cur = p & 1, nxt = cur ^ 1;
+      const unsigned nt = q_cnt[cur];
+      bool found = false, task = threadIdx.x < nt;
+      unsigned slot = 0;
+      if (task) {
+        slot = q[cur * MAP_THREADS + threadIdx.x];
+        uint32_t* fw = rows + slot * a.row_stride;
+        uint32_t* rc = fw + a.nw;
+        const int L = __ldg(a.len + base + slot);
+        if (p == 1) make_revcomp(SharedWords{fw}, rc, L, (int)a.nw);
+        const DevIndexView& ix = p < 2 ? a.cds : a.gen;
+        SharedWords rd{(p & 1) ? rc : fw};
+        int pos = 0; uint32_t node = 0, off = 0;
+        if (L >= K) {
+          if (SMEM_BM) found = find_seed(ix, rd, BitmapShared{smem + (p < 2 ? 0 : a.cds.bitmap_words)}, pos, L - K, node, off, n_tests, n_probes);
+          else found = find_seed(ix, rd, BitmapGlobal{ix.bitmap}, pos, L - K, node, off, n_tests, n_probes);
+        }
+        if (found) { seed_node[slot] = node; seed_info[slot] = (off << 12) | ((uint32_t)pos << 2) | (uint32_t)p; }
+      }
+      __syncwarp();
+      push(2, task && found, slot);
+      push(nxt, task && !found, slot);
+      __syncthreads();
+      if (threadIdx.x == 0) q_cnt[cur] = 0;   // becomes the output queue of the next phase
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) m_none += q_cnt[0];   // all four None (mapping.rs:791-793); after p = 3 the survivors sit in queue 0
+    // ---- walk ----
+    {
+      const unsigned nt = q_cnt[2];
+      uint32_t code = CODE_NONE5;
+      uint64_t key = 0;
+      if (threadIdx.x < nt) {
+        const unsigned slot = q[2 * MAP_THREADS + threadIdx.x];
+        const uint64_t i = base + slot;
+        const uint32_t info = seed_info[slot];
+        const int p = (int)(info & 3u), pos = (int)((info >> 2) & 1023u);
+        const uint32_t off = info >> 12, node = seed_node[slot];
+        uint32_t* fw = rows + slot * a.row_stride;
+        const int L = __ldg(a.len + i);
+        const DevIndexView& ix = p < 2 ? a.cds : a.gen;
+        SharedWords rd{(p & 1) ? fw + a.nw : fw};
+        CountVis vis{p < 2 ? a.cinfo_cds : a.cinfo_gen};
+        uint32_t cov;
+        if (SMEM_BM) cov = walk_from_seed(ix, rd, BitmapShared{smem + (p < 2 ? 0 : a.cds.bitmap_words)}, L, pos, node, off, vis, n_tests, n_probes);
+        else cov = walk_from_seed(ix, rd, BitmapGlobal{ix.bitmap}, L, pos, node, off, vis, n_tests, n_probes);
+        const bool good = cov > MIN_SCORE_COUNT_PSEUDO;
+        if (good) { if (p < 2) m_cds++; else m_gen++; }
+        if (p == 0 || good) code = vis.code();   // a CDS-forward hit is used whatever its coverage (mapping.rs:772-775)
+        if (code != CODE_NONE5) {
+          key = ((uint64_t)__ldg(a.cell + i) << (UMI_BITS + CODE_BITS)) | ((uint64_t)__ldg(a.umi + i) << CODE_BITS) | code;
+          if (a.codes) a.codes[i] = (uint8_t)code;
         }
       }
-      if (a.codes) a.codes[i] = code == CODE_NONE5 ? (uint8_t)HLAC_CODE_NONE : (uint8_t)code;
-    }
-    // warp-aggregated append of the scored reads' keys
-    __syncwarp();
-    const unsigned ballot = __ballot_sync(0xFFFFFFFFu, code != CODE_NONE5);
-    if (ballot) {
-      unsigned long long at = 0;
-      if (lane == 0) at = atomicAdd(a.cursor, (unsigned long long)__popc(ballot));
-      at = __shfl_sync(0xFFFFFFFFu, at, 0);
-      if (code != CODE_NONE5) a.keys[at + __popc(ballot & ((1u << lane) - 1))] = key;
+      __syncwarp();
+      const unsigned ballot = __ballot_sync(0xFFFFFFFFu, code != CODE_NONE5);
+      if (ballot) {
+        unsigned long long at = 0;
+        if (lane == 0) at = atomicAdd(a.cursor, (unsigned long long)__popc(ballot));
+        at = __shfl_sync(0xFFFFFFFFu, at, 0);
+        if (code != CODE_NONE5) a.keys[at + __popc(ballot & ((1u << lane) - 1))] = key;
+      }
     }
   }
   // metrics: warp reduce then one atomic per counter per warp
@@ -306,7 +361,7 @@ struct hlac_count {
     a.primary_only = primary_only;
     a.keys = keys.p; a.cursor = counters.p; a.metrics = counters.p + 1;
     a.codes = want_codes ? codes.p : nullptr;
-    const size_t smem = (smem_bm ? bitmap_smem_bytes : 0) + (size_t)MAP_THREADS * a.row_stride * 4;
+    const size_t smem = (smem_bm ? bitmap_smem_bytes : 0) + (size_t)MAP_THREADS * a.row_stride * 4 + (size_t)MAP_THREADS * (4 + 4 + 3 * 2);
     auto kern = smem_bm ? k_count_map<true> : k_count_map<false>;
     if (cfg_wpr != b.words_per_read) {
       HLAC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -115,18 +115,14 @@ __device__ __forceinline__ int extend_cmp(RD rd, int rpos, const uint32_t* seq32
   return matched;
 }
 
-// map_read_to_nodes. V::visit(colour, node) is called for every visited node in the
-// reference's push order (left-extension nodes first, then the forward walk); the last call is the class-defining
-// node. Returns false for None; cov = coverage.
+// map_read_to_nodes after the first seed: optional left extension, then the forward walk.
+// (pos, node, off) is the first verified seed. V::visit(colour, node) is called for every visited node in the
+// reference's push order (left-extension nodes first, then the forward walk); the last call is the class-defining node.
 template <typename RD, typename BM, typename V>
-__device__ __forceinline__ bool map_read_walk(const DevIndexView& ix, RD rd, BM bm, int L, V& vis, uint32_t& cov_out,
-                                              uint32_t& n_tests, uint32_t& n_probes) {
-  if (L < K) return false;
+__device__ __forceinline__ uint32_t walk_from_seed(const DevIndexView& ix, RD rd, BM bm, int L, int pos, uint32_t node, uint32_t off,
+                                                   V& vis, uint32_t& n_tests, uint32_t& n_probes) {
   const int last = L - K;
-  int pos = 0;
   int cov = 0;
-  uint32_t node = 0, off = 0;
-  if (!find_seed(ix, rd, bm, pos, last, node, off, n_tests, n_probes)) return false;
   uint4 n0 = __ldg(ix.nodes + 3 * (size_t)node);
   // ---- left extension: only when the first seed sits at or beyond floor(0.2*L) ----
   if (pos >= (L * LEFT_EXTEND_NUM) / LEFT_EXTEND_DEN) {
@@ -187,7 +183,17 @@ __device__ __forceinline__ bool map_read_walk(const DevIndexView& ix, RD rd, BM 
     }
     n0 = __ldg(ix.nodes + 3 * (size_t)node);
   }
-  cov_out = (uint32_t)cov;
+  return (uint32_t)cov;
+}
+
+// map_read_to_nodes, whole: None iff the first seed scan finds nothing (or L < K).
+template <typename RD, typename BM, typename V>
+__device__ __forceinline__ bool map_read_walk(const DevIndexView& ix, RD rd, BM bm, int L, V& vis, uint32_t& cov_out,
+                                              uint32_t& n_tests, uint32_t& n_probes) {
+  int pos = 0;
+  uint32_t node = 0, off = 0;
+  if (L < K || !find_seed(ix, rd, bm, pos, L - K, node, off, n_tests, n_probes)) return false;
+  cov_out = walk_from_seed(ix, rd, bm, L, pos, node, off, vis, n_tests, n_probes);
   return true;
 }
 
