@@ -32,7 +32,6 @@ using namespace hlac;
 
 namespace {
 
-constexpr int MAP_THREADS = 512;
 constexpr uint32_t CODE_NONE5 = 31;   // 5-bit "no code"
 constexpr int CODE_BITS = 5;
 constexpr int UMI_BITS = 32;
@@ -86,112 +85,122 @@ struct BitmapGlobal {
   __device__ __forceinline__ uint32_t operator()(uint32_t i) const { return __ldg(p + i); }
 };
 
-// Staged block kernel. One tile = MAP_THREADS reads. Instead of letting every thread run its own read through the
-// whole 4-way chain (ncu on that version: 6.65 of 32 lanes active per issued instruction), the block moves the tile
-// through stages and compacts the surviving reads into dense task queues in shared memory between stages, so that
-// the lanes of a warp always execute the same kind of work:
-//   load    filters (mapping.rs:752-763), read rows into shared memory, queue q0
+// Warp-staged kernel. Each WARP owns a tile of 32*R reads and moves it through stages, compacting the surviving reads
+// into dense warp-private task queues in shared memory between stages, so that the lanes of a warp always execute the
+// same kind of work and no block-wide barrier is needed (ncu history in profiles/: thread-per-read version 6.65 of 32
+// lanes active per issued instruction; block-staged version 12.6 lanes but 30 % of stall samples on __syncthreads):
+//   load    filters (mapping.rs:752-763), read rows into shared memory, queue 0
 //   scan p  p = cds-fwd, cds-rev, gen-fwd, gen-rev: first-seed skip-scan for the reads still without a seed
 //           (map_read is None iff its FIRST seed scan fails, so the laziness of mapping.rs:772-790 is a cascade of scans);
 //           reads that find a seed go to the walk queue, the others to the next scan queue (revcomp built at p = 1)
 //   walk    every read with a seed: left extension + forward walk + class code + coverage policy, key append
-template <bool SMEM_BM>
-__global__ void __launch_bounds__(MAP_THREADS, 2) k_count_map(const CountMapArgs a) {
+// Queue counters are warp-uniform registers (every lane sees the same ballots), so the queues need no atomics.
+template <bool SMEM_BM, int R, int MAP_THREADS, int MINB = 1>
+__global__ void __launch_bounds__(MAP_THREADS, MINB) k_count_map(const CountMapArgs a) {
   extern __shared__ __align__(16) uint32_t smem[];
-  __shared__ unsigned q_cnt[3];   // [0]/[1] ping-pong scan queues, [2] walk queue
-  uint32_t* rows = smem;
+  constexpr int TILE = 32 * R;
+  uint32_t* wbase = smem;
   if (SMEM_BM) {
     const uint32_t nb = a.cds.bitmap_words + a.gen.bitmap_words;
     for (uint32_t i = threadIdx.x; i < a.cds.bitmap_words; i += MAP_THREADS) smem[i] = __ldg(a.cds.bitmap + i);
     for (uint32_t i = threadIdx.x; i < a.gen.bitmap_words; i += MAP_THREADS) smem[a.cds.bitmap_words + i] = __ldg(a.gen.bitmap + i);
-    rows = smem + nb;
+    wbase = smem + nb;
+    __syncthreads();   // the only block-wide barrier
   }
-  uint32_t* seed_node = rows + MAP_THREADS * a.row_stride;          // per slot
-  uint32_t* seed_info = seed_node + MAP_THREADS;                    // off(20) | pos(10) | phase(2)
-  uint16_t* q = reinterpret_cast<uint16_t*>(seed_info + MAP_THREADS);   // 3 queues of MAP_THREADS slots
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t per_warp = TILE * a.row_stride + TILE * 2 + TILE / 2 + 3 * TILE / 4;   // u32 words
+  uint32_t* rows = wbase + warp * per_warp;
+  uint32_t* seed_node = rows + TILE * a.row_stride;
+  uint32_t* seed_info = seed_node + TILE;                                   // off(20) | pos(10) | phase(2)
+  uint16_t* lens = reinterpret_cast<uint16_t*>(seed_info + TILE);
+  uint8_t* q = reinterpret_cast<uint8_t*>(lens + TILE);                     // 3 queues of TILE slots
   unsigned long long m_reads = 0, m_nonprim = 0, m_notcell = 0, m_cds = 0, m_gen = 0, m_none = 0;
   uint32_t n_tests = 0, n_probes = 0;
-  const unsigned lane = threadIdx.x & 31;
-  auto push = [&](int which, bool pred, unsigned slot) {   // warp-aggregated append to a shared-memory queue
-    const unsigned ballot = __ballot_sync(0xFFFFFFFFu, pred);
-    if (!ballot) return;
-    unsigned at = 0;
-    if (lane == 0) at = atomicAdd(&q_cnt[which], (unsigned)__popc(ballot));
-    at = __shfl_sync(0xFFFFFFFFu, at, 0);
-    if (pred) q[which * MAP_THREADS + at + __popc(ballot & ((1u << lane) - 1))] = (uint16_t)slot;
-  };
-  for (uint64_t base = (uint64_t)blockIdx.x * MAP_THREADS; base < a.n; base += (uint64_t)gridDim.x * MAP_THREADS) {
-    __syncthreads();   // previous tile fully consumed (rows, queues, counters); bitmaps loaded
-    if (threadIdx.x < 3) q_cnt[threadIdx.x] = 0;
-    __syncthreads();
-    // ---- load ----
-    {
-      const uint64_t i = base + threadIdx.x;
+  const uint64_t n_warps = (uint64_t)gridDim.x * (MAP_THREADS / 32);
+  for (uint64_t tile = (uint64_t)blockIdx.x * (MAP_THREADS / 32) + warp; tile * TILE < a.n; tile += n_warps) {
+    const uint64_t base = tile * TILE;
+    unsigned cnt0 = 0, cnt1 = 0, cntw = 0;   // warp-uniform queue lengths
+    __syncwarp();
+    // ---- load: all global loads of a read are issued before any is consumed ----
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      const unsigned slot = r * 32 + lane;
+      const uint64_t i = base + slot;
       bool keep = false;
       if (i < a.n) {
+        const uint8_t fl = __ldg(a.flags + i);
+        const uint32_t cell = __ldg(a.cell + i);
+        const uint16_t L = __ldg(a.len + i);
+        uint32_t* fw = rows + slot * a.row_stride;
+        for (uint32_t w = 0; w < a.wpr; w++) {
+          const uint64_t v = __ldg(a.seq + i * a.wpr + w);
+          fw[2 * w] = (uint32_t)(v >> 32); fw[2 * w + 1] = (uint32_t)v;
+        }
+        fw[2 * a.wpr] = 0; fw[2 * a.wpr + 1] = 0;
+        lens[slot] = L;
         m_reads++;
-        const bool primary = a.flags[i] & HLAC_FLAG_PRIMARY;
+        const bool primary = fl & HLAC_FLAG_PRIMARY;
         if (!primary) m_nonprim++;
         if (primary || !a.primary_only) {
-          if (__ldg(a.cell + i) == HLAC_NOT_A_CELL) m_notcell++;
-          else {
-            keep = true;
-            uint32_t* fw = rows + threadIdx.x * a.row_stride;
-            for (uint32_t w = 0; w < a.wpr; w++) {
-              const uint64_t v = __ldg(a.seq + i * a.wpr + w);
-              fw[2 * w] = (uint32_t)(v >> 32); fw[2 * w + 1] = (uint32_t)v;
-            }
-            fw[2 * a.wpr] = 0; fw[2 * a.wpr + 1] = 0;
-          }
+          if (cell == HLAC_NOT_A_CELL) m_notcell++;
+          else keep = true;
         }
         if (a.codes) a.codes[i] = (uint8_t)HLAC_CODE_NONE;
       }
-      push(0, keep, threadIdx.x);
+      const unsigned ballot = __ballot_sync(0xFFFFFFFFu, keep);
+      if (keep) q[cnt0 + __popc(ballot & ((1u << lane) - 1))] = (uint8_t)slot;
+      cnt0 += __popc(ballot);
     }
-    __syncthreads();
+    __syncwarp();
     // ---- scan cascade ----
 #pragma unroll 1
     for (int p = 0; p < 4; p++) {
-      const int cur = p & 1, nxt = cur ^ 1;
-      const unsigned nt = q_cnt[cur];
-      bool found = false, task = threadIdx.x < nt;
-      unsigned slot = 0;
-      if (task) {
-        slot = q[cur * MAP_THREADS + threadIdx.x];
-        uint32_t* fw = rows + slot * a.row_stride;
-        uint32_t* rc = fw + a.nw;
-        const int L = __ldg(a.len + base + slot);
-        if (p == 1) make_revcomp(SharedWords{fw}, rc, L, (int)a.nw);
-        const DevIndexView& ix = p < 2 ? a.cds : a.gen;
-        SharedWords rd{(p & 1) ? rc : fw};
-        int pos = 0; uint32_t node = 0, off = 0;
-        if (L >= K) {
-          if (SMEM_BM) found = find_seed(ix, rd, BitmapShared{smem + (p < 2 ? 0 : a.cds.bitmap_words)}, pos, L - K, node, off, n_tests, n_probes);
-          else found = find_seed(ix, rd, BitmapGlobal{ix.bitmap}, pos, L - K, node, off, n_tests, n_probes);
+      const unsigned nt = (p & 1) ? cnt1 : cnt0;
+      uint8_t* qc = q + ((p & 1) ? TILE : 0);
+      uint8_t* qn = q + ((p & 1) ? 0 : TILE);
+      unsigned cntn = 0;
+      const DevIndexView& ix = p < 2 ? a.cds : a.gen;
+      for (unsigned t0 = 0; t0 < nt; t0 += 32) {
+        const bool task = t0 + lane < nt;
+        bool found = false;
+        unsigned slot = 0;
+        if (task) {
+          slot = qc[t0 + lane];
+          uint32_t* fw = rows + slot * a.row_stride;
+          uint32_t* rc = fw + a.nw;
+          const int L = lens[slot];
+          if (p == 1) make_revcomp(SharedWords{fw}, rc, L, (int)a.nw);
+          SharedWords rd{(p & 1) ? rc : fw};
+          int pos = 0; uint32_t node = 0, off = 0;
+          if (L >= K) {
+            if (SMEM_BM) found = find_seed(ix, rd, BitmapShared{smem + (p < 2 ? 0 : a.cds.bitmap_words)}, pos, L - K, node, off, n_tests, n_probes);
+            else found = find_seed(ix, rd, BitmapGlobal{ix.bitmap}, pos, L - K, node, off, n_tests, n_probes);
+          }
+          if (found) { seed_node[slot] = node; seed_info[slot] = (off << 12) | ((uint32_t)pos << 2) | (uint32_t)p; }
         }
-        if (found) { seed_node[slot] = node; seed_info[slot] = (off << 12) | ((uint32_t)pos << 2) | (uint32_t)p; }
+        __syncwarp();
+        const unsigned bf = __ballot_sync(0xFFFFFFFFu, task && found), bn = __ballot_sync(0xFFFFFFFFu, task && !found);
+        const unsigned below = (1u << lane) - 1;
+        if (task && found) q[2 * TILE + cntw + __popc(bf & below)] = (uint8_t)slot;
+        if (task && !found) qn[cntn + __popc(bn & below)] = (uint8_t)slot;
+        cntw += __popc(bf); cntn += __popc(bn);
       }
+      if (p & 1) { cnt0 = cntn; cnt1 = 0; } else { cnt1 = cntn; cnt0 = 0; }
       __syncwarp();
-      push(2, task && found, slot);
-      push(nxt, task && !found, slot);
-      __syncthreads();
-      if (threadIdx.x == 0) q_cnt[cur] = 0;   // becomes the output queue of the next phase
-      __syncthreads();
     }
-    if (threadIdx.x == 0) m_none += q_cnt[0];   // all four None (mapping.rs:791-793); after p = 3 the survivors sit in queue 0
+    if (lane == 0) m_none += cnt0;   // all four None (mapping.rs:791-793): survivors of p = 3 sit in queue 0
     // ---- walk ----
-    {
-      const unsigned nt = q_cnt[2];
+    for (unsigned t0 = 0; t0 < cntw; t0 += 32) {
       uint32_t code = CODE_NONE5;
       uint64_t key = 0;
-      if (threadIdx.x < nt) {
-        const unsigned slot = q[2 * MAP_THREADS + threadIdx.x];
+      if (t0 + lane < cntw) {
+        const unsigned slot = q[2 * TILE + t0 + lane];
         const uint64_t i = base + slot;
         const uint32_t info = seed_info[slot];
         const int p = (int)(info & 3u), pos = (int)((info >> 2) & 1023u);
         const uint32_t off = info >> 12, node = seed_node[slot];
         uint32_t* fw = rows + slot * a.row_stride;
-        const int L = __ldg(a.len + i);
+        const int L = lens[slot];
         const DevIndexView& ix = p < 2 ? a.cds : a.gen;
         SharedWords rd{(p & 1) ? fw + a.nw : fw};
         CountVis vis{p < 2 ? a.cinfo_cds : a.cinfo_gen};
@@ -313,7 +322,9 @@ struct hlac_count {
   bool want_codes = false;
   bool reduced = false;
   uint32_t cfg_wpr = 0;
-  int cfg_occ = 0;
+  int cfg_occ = 0, cfg_r = 0, cfg_threads = 0;
+  bool cfg_bm = false;
+  void* cfg_kern = nullptr;
   uint64_t n_keys = 0;
   // timing
   struct Ev { cudaEvent_t a, b; int kind; };
@@ -361,16 +372,47 @@ struct hlac_count {
     a.primary_only = primary_only;
     a.keys = keys.p; a.cursor = counters.p; a.metrics = counters.p + 1;
     a.codes = want_codes ? codes.p : nullptr;
-    const size_t smem = (smem_bm ? bitmap_smem_bytes : 0) + (size_t)MAP_THREADS * a.row_stride * 4 + (size_t)MAP_THREADS * (4 + 4 + 3 * 2);
-    auto kern = smem_bm ? k_count_map<true> : k_count_map<false>;
+    // launch shape: (bitmaps in shared memory?, reads per lane per warp tile R, threads per block). Defaults below;
+    // HLAC_COUNT_SHAPE="smem,R,threads" overrides them for tuning runs.
+    using Kern = void (*)(const CountMapArgs);
+    auto smem_for = [&](bool bm, int r, int threads) {
+      const size_t per_warp_words = (size_t)32 * r * a.row_stride + 32 * r * 2 + 32 * r / 2 + 3 * 32 * r / 4;
+      return (bm ? bitmap_smem_bytes : 0) + (threads / 32) * per_warp_words * 4;
+    };
     if (cfg_wpr != b.words_per_read) {
-      HLAC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      HLAC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cfg_occ, kern, MAP_THREADS, smem));
+      struct Shape { bool bm; int r, threads; Kern k; int minb = 1; };
+      static const Shape shapes[] = {
+#define HLAC_SHAPE(BM, RR, TT) {BM, RR, TT, k_count_map<BM, RR, TT>}
+          // defaults first: measured best on B200 (profiles/r01_count_map_tuning.md) — occupancy beats tile size
+          HLAC_SHAPE(true, 2, 1024), HLAC_SHAPE(true, 1, 512), HLAC_SHAPE(true, 1, 256), HLAC_SHAPE(true, 4, 512), HLAC_SHAPE(true, 2, 512),
+          HLAC_SHAPE(false, 2, 128), HLAC_SHAPE(false, 1, 128), HLAC_SHAPE(false, 2, 256), HLAC_SHAPE(false, 1, 256), HLAC_SHAPE(false, 4, 128),
+          HLAC_SHAPE(true, 4, 256), HLAC_SHAPE(true, 8, 256), HLAC_SHAPE(false, 4, 256), HLAC_SHAPE(false, 8, 128),
+          {false, 1, 128, k_count_map<false, 1, 128, 12>, 12}, {false, 1, 128, k_count_map<false, 1, 128, 16>, 16},
+          {true, 1, 512, k_count_map<true, 1, 512, 3>, 3}};
+#undef HLAC_SHAPE
+      const Shape* pick = nullptr;
+      int want_bm = -1, want_r = 0, want_t = 0, want_minb = 1;
+      if (const char* e = getenv("HLAC_COUNT_SHAPE")) sscanf(e, "%d,%d,%d,%d", &want_bm, &want_r, &want_t, &want_minb);
+      for (const Shape& sh : shapes) {
+        if (want_bm >= 0) { if ((int)sh.bm != want_bm || sh.r != want_r || sh.threads != want_t || sh.minb != want_minb) continue; }
+        else if (sh.minb != 1) continue;
+        else if (sh.bm != smem_bm) continue;
+        if (sh.bm && !smem_bm) continue;
+        if (smem_for(sh.bm, sh.r, sh.threads) > 227 * 1024) continue;
+        pick = &sh; break;
+      }
+      if (!pick) throw Error(HLAC_ERR_LIMIT, "no launch shape of the count kernel fits (reads too long, or bad HLAC_COUNT_SHAPE)");
+      cfg_bm = pick->bm; cfg_r = pick->r; cfg_threads = pick->threads; cfg_kern = (void*)pick->k;
+      HLAC_CUDA(cudaFuncSetAttribute(pick->k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(cfg_bm, cfg_r, cfg_threads)));
+      HLAC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cfg_occ, pick->k, cfg_threads, smem_for(cfg_bm, cfg_r, cfg_threads)));
       if (cfg_occ < 1) throw Error(HLAC_ERR_LIMIT, "count map kernel does not fit on the device");
       cfg_wpr = b.words_per_read;
     }
+    Kern kern = (Kern)cfg_kern;
+    const size_t smem = smem_for(cfg_bm, cfg_r, cfg_threads);
+    const int MAP_R = cfg_r, MAP_THREADS = cfg_threads;
     const int occ = cfg_occ;
-    const uint64_t need = (b.n + MAP_THREADS - 1) / MAP_THREADS;
+    const uint64_t need = (b.n + (uint64_t)MAP_THREADS * MAP_R - 1) / ((uint64_t)MAP_THREADS * MAP_R);
     const unsigned grid = (unsigned)std::min<uint64_t>(need, (uint64_t)n_sm * occ);
     Ev& e = begin(0);
     kern<<<grid, MAP_THREADS, smem, stream>>>(a);
