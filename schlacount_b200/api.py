@@ -286,12 +286,18 @@ class GenoSession:
         check(lib().hlac_geno_last_cov(self.h, _vp(out), C.c_uint64(self._n_last)))
         return out
 
-    def finish(self):
-        """-> dict(nitems, nreads, counts_reads, counts_umi, reads_explained, reads_classes [first-seen order])"""
+    def finish(self, raw=False):
+        """-> dict(nitems, nreads, counts_reads, counts_umi, reads_explained, reads_classes [first-seen order]);
+        raw=True skips the (slow) conversion of the class tables to Python objects and returns only the sizes."""
         if self.tables is not None:
             lib().hlac_class_tables_free(C.byref(self.tables))
         self.tables = _lib.ClassTables()
         check(lib().hlac_geno_finish(self.h, C.byref(self.tables)))
+        if raw:
+            t = self.tables
+            return dict(nitems=t.nitems, nreads=t.nreads, n_read_classes=t.n_read_classes, n_umi_classes=t.n_umi_classes,
+                        reads_nnz=t.reads_off[t.n_read_classes] if t.n_read_classes else 0,
+                        umi_nnz=t.umi_off[t.n_umi_classes] if t.n_umi_classes else 0)
         return _tables_to_py(self.tables)
 
     def read_class_ids(self, n):

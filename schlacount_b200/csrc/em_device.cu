@@ -226,14 +226,34 @@ int hlac_call_genotypes(const hlac_index* idx, const hlac_class_tables* t, const
   for (uint32_t i = 0; i < t->nitems; i++) wn.push_back({i, theta[i], names[i].substr(0, names[i].find('*')), t->reads_explained[i]});
   std::stable_sort(wn.begin(), wn.end(), [](const W& a, const W& b) { return -a.w < -b.w; });        // em.rs:370
   std::stable_sort(wn.begin(), wn.end(), [](const W& a, const W& b) { return a.gene < b.gene; });    // em.rs:371
-  auto pair_explained = [&](uint32_t a, uint32_t b) {   // em.rs:36-44
-    uint32_t e = 0;
-    for (uint64_t c = 0; c < t->n_read_classes; c++) {
-      bool has = false;
-      for (uint64_t q = t->reads_off[c]; q < t->reads_off[c + 1] && !has; q++) has = t->reads_tx[q] == a || t->reads_tx[q] == b;
-      if (has) e += t->reads_cnt[c];
+  // pair_reads_explained (em.rs:36-44) = reads in classes containing a or b. The reference rescans every class per
+  // pair; here one pass builds, for the few candidate alleles only (<= WEIGHTS_TO_OUTPUT per gene), the list of
+  // classes containing each, and a pair is explained[a] + explained[b] - (reads in classes containing both).
+  std::vector<int32_t> cand_of(t->nitems, -1); std::vector<uint32_t> cands;
+  for (size_t s = 0; s < wn.size();) {
+    size_t e = s; while (e < wn.size() && wn[e].gene == wn[s].gene) e++;
+    size_t k = 0;
+    for (size_t q = s; q < e && wn[q].exp > MIN_READS_CALL && k < WEIGHTS_TO_OUTPUT; q++, k++) { cand_of[wn[q].i] = (int32_t)cands.size(); cands.push_back(wn[q].i); }
+    s = e;
+  }
+  std::vector<std::vector<uint32_t>> cls_of(cands.size());
+  for (uint64_t c = 0; c < t->n_read_classes; c++) {
+    for (uint64_t q = t->reads_off[c]; q < t->reads_off[c + 1]; q++) {
+      const int32_t k = cand_of[t->reads_tx[q]];
+      if (k >= 0 && (cls_of[k].empty() || cls_of[k].back() != (uint32_t)c)) cls_of[k].push_back((uint32_t)c);
     }
-    return e;
+  }
+  auto pair_explained = [&](uint32_t a, uint32_t b) {
+    const auto& la = cls_of[cand_of[a]]; const auto& lb = cls_of[cand_of[b]];
+    uint64_t e = 0; size_t i = 0, j = 0;
+    while (i < la.size() || j < lb.size()) {   // union of two ascending class lists
+      uint32_t c;
+      if (j >= lb.size() || (i < la.size() && la[i] < lb[j])) c = la[i++];
+      else if (i >= la.size() || lb[j] < la[i]) c = lb[j++];
+      else { c = la[i]; i++; j++; }
+      e += t->reads_cnt[c];
+    }
+    return (uint32_t)e;
   };
   const double nreads = (double)t->nreads;
   std::set<uint32_t> called;
