@@ -8,7 +8,9 @@
 //     It is only a necessary-condition filter; every candidate is still verified in the exact dictionary, so the
 //     first hit position is identical to the reference's position-by-position scan (the scan is stateless);
 //   * graph edges are a precomputed adjacency table instead of hashing the extended terminal k-mer;
-//   * base-by-base extension becomes 16-base XOR/popcount chunks with exact "stop at the 3rd mismatch" semantics.
+//   * base-by-base extension becomes 16-base XOR/popcount chunks with exact "stop at the 3rd mismatch" semantics,
+//     in ONE flat loop (compare a chunk, then hop / re-seed if the node is exhausted) so that the lanes of a warp,
+//     each on its own read, do not serialise on nested loops with different trip counts.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -76,47 +78,20 @@ __device__ __forceinline__ bool find_seed(const DevIndexView& ix, RD rd, BM bm, 
                                           uint32_t& off, uint32_t& n_tests, uint32_t& n_probes) {
   const int l = (int)ix.lmer;
   const int sh = 32 - 2 * l;
+  const int o0 = K - l;
+  int o = o0;
+  // one flat loop, one l-mer test per iteration (no nested per-window loop: lanes of a warp advance independently)
   while (pos <= last) {
-    int o = K - l;
-    bool pass = true;
-    for (;;) {
-      const uint32_t v = ext16(rd, pos + o) >> sh;
-      n_tests++;
-      if (!((bm(v >> 5) >> (v & 31)) & 1u)) { pos += o + 1; pass = false; break; }   // no k-mer can cover this l-mer
-      if (o == 0) break;
-      o = o > l ? o - l : 0;
-    }
-    if (!pass) continue;
+    const uint32_t v = ext16(rd, pos + o) >> sh;
+    n_tests++;
+    if (!((bm(v >> 5) >> (v & 31)) & 1u)) { pos += o + 1; o = o0; continue; }   // no k-mer can cover this l-mer
+    if (o != 0) { o = o > l ? o - l : 0; continue; }
     n_probes++;
     if (dict_get(ix, kmer48(rd, pos), node, off)) return true;
     pos += 1;
+    o = o0;
   }
   return false;
-}
-
-// Compare read[rpos .. rpos+m) with node bases [g .. g+m): number of bases consumed before the (ALLOWED+1)-th
-// mismatch (tolerated mismatches count as consumed, the breaking one does not). brk = budget exceeded.
-template <typename RD>
-__device__ __forceinline__ int extend_cmp(RD rd, int rpos, const uint32_t* seq32, uint32_t g, int m, bool& brk) {
-  int matched = 0, snp = 0;
-  brk = false;
-  GWords ns{seq32};
-  while (matched < m) {
-    const int c = min(16, m - matched);
-    uint32_t x = ext16(rd, rpos + matched) ^ ext16(ns, (int)(g + matched));
-    x = (x | (x >> 1)) & 0x55555555u;
-    if (c < 16) x &= ~(0xFFFFFFFFu >> (2 * c));
-    const int pc = __popc(x);
-    if (snp + pc > ALLOWED_MISMATCH) {
-      for (int t = snp; t < ALLOWED_MISMATCH; t++) x &= ~(0x80000000u >> __clz(x));
-      matched += __clz(x) >> 1;
-      brk = true;
-      break;
-    }
-    snp += pc;
-    matched += c;
-  }
-  return matched;
 }
 
 // map_read_to_nodes after the first seed: optional left extension, then the forward walk.
@@ -158,34 +133,57 @@ __device__ __forceinline__ uint32_t walk_from_seed(const DevIndexView& ix, RD rd
       vis.visit(p0.w, pn);
     }
   }
-  // ---- forward walk ----
+  // ---- forward walk, flattened: one loop whose body compares <= 16 bases inside the current node and then, if the node
+  // is exhausted (or the per-node mismatch budget is), takes the edge or re-seeds. Equivalent to the reference's
+  // node loop with an inner base loop: a hop is `pos -= K-1; cov -= K-1` followed by `pos += K; cov += K` = +1/+1,
+  // the per-node budget `snp` resets at every node entry, tolerated mismatches count as covered, the breaking one
+  // does not. ----
+  GWords ns{ix.seq32};
+  pos += K;
+  cov += K;
+  vis.visit(n0.w, node);
+  uint32_t g = n0.x + off + K;          // next node base to compare
+  int rem = (int)n0.y - (int)off - K;   // bases left in the node
+  int snp = 0;
   for (;;) {
-    pos += K;
-    cov += K;
-    vis.visit(n0.w, node);
-    const int ro = (int)off + K;
-    const int m = min(L - pos, (int)n0.y - ro);
-    bool brk;
-    const int matched = extend_cmp(rd, pos, ix.seq32, n0.x + ro, m, brk);
-    cov += matched;
-    pos += matched;
+    const int c = min(min(16, L - pos), rem);
+    bool brk = false;
+    if (c > 0) {
+      uint32_t x = ext16(rd, pos) ^ ext16(ns, (int)g);
+      x = (x | (x >> 1)) & 0x55555555u;
+      if (c < 16) x &= ~(0xFFFFFFFFu >> (2 * c));
+      const int pc = __popc(x);
+      if (snp + pc > ALLOWED_MISMATCH) {
+        for (int t = snp; t < ALLOWED_MISMATCH; t++) x &= ~(0x80000000u >> __clz(x));
+        const int adv = __clz(x) >> 1;
+        pos += adv; cov += adv;
+        brk = true;
+      } else {
+        snp += pc; pos += c; cov += c; g += c; rem -= c;
+      }
+    }
     if (pos >= L) break;
+    if (!brk && rem > 0) continue;
     uint32_t nxt = NONE32;
     if (!brk) {
       const uint32_t b = base_at(rd, pos);
       const uint4 ra = __ldg(ix.nodes + 3 * (size_t)node + 1);
       nxt = b == 0 ? ra.x : b == 1 ? ra.y : b == 2 ? ra.z : ra.w;
     }
-    if (nxt != NONE32) {
+    if (nxt != NONE32) {                 // exact base at the node boundary selects the edge
       node = nxt;
-      off = 0;
-      pos -= K - 1;
-      cov -= K - 1;
-    } else {
+      n0 = __ldg(ix.nodes + 3 * (size_t)node);
+      pos += 1; cov += 1;
+      g = n0.x + K; rem = (int)n0.y - K;
+    } else {                             // re-seed scanning forward from the current position
       if (pos > last) break;
       if (!find_seed(ix, rd, bm, pos, last, node, off, n_tests, n_probes)) break;
+      n0 = __ldg(ix.nodes + 3 * (size_t)node);
+      pos += K; cov += K;
+      g = n0.x + off + K; rem = (int)n0.y - (int)off - K;
     }
-    n0 = __ldg(ix.nodes + 3 * (size_t)node);
+    snp = 0;
+    vis.visit(n0.w, node);
   }
   return (uint32_t)cov;
 }
