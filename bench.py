@@ -35,6 +35,9 @@ SEED = 20191101 + 2
 # algorithmic HBM bytes per read: map stage 32 B in (24 B 2-bit sequence + 4 B cell + 4 B UMI) + 4 B out
 MAP_BYTES_PER_READ = 36
 SORT_BYTES_PER_KEY = 36   # 12-B record read, written sorted, read by the segmented reduce
+# dram__bytes_read.sum + dram__bytes_write.sum of k_count_map per read, from the `ncu --set full` capture
+# profiles/r01_count_map_v3_ncu_digest.txt (70.75 MB + 1.78 MB over 2 M reads); scaled to the reads of one launch
+MAP_DRAM_BYTES_PER_READ_NCU = (70.749696e6 + 1.777152e6) / 2_000_000
 
 
 class ClockSampler(threading.Thread):
@@ -281,7 +284,9 @@ def main():
         peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         map_gbs = n * MAP_BYTES_PER_READ / (tm_dev["map_ms"] / 1e3) / 1e9 if tm_dev["map_ms"] > 0 else None
         roof = {"bound": "hbm", "kernel": "k_count_map", "achieved": map_gbs, "peak": peak, "unit": "GB/s",
-                "frac": (map_gbs / peak) if map_gbs else None, "traffic": None, "peak_source": peak_src,
+                "frac": (map_gbs / peak) if map_gbs else None, "traffic": MAP_DRAM_BYTES_PER_READ_NCU * n,
+                "traffic_source": "ncu --set full, profiles/r01_count_map_v3_ncu_digest.txt (bytes/read x reads per launch)",
+                "peak_source": peak_src,
                 "algorithmic_bytes_per_read": MAP_BYTES_PER_READ, "launch_ms": tm_dev["map_ms"],
                 "note": "map kernel is issue/latency-bound by design (SURVEY.md §8d); see profiles/"}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
