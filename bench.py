@@ -288,7 +288,8 @@ def main():
                 "traffic_source": "ncu --set full, profiles/r01_count_map_v3_ncu_digest.txt (bytes/read x reads per launch)",
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_read": MAP_BYTES_PER_READ, "launch_ms": tm_dev["map_ms"],
-                "note": "map kernel is issue/latency-bound by design (SURVEY.md §8d); see profiles/"}
+                "note": "DRAM traffic equals the algorithmic bytes; the kernel is issue/latency-bound (64 % issue-active, 12 of 32 lanes "
+                        "active per instruction) — DESIGN.md §5, profiles/"}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": per_step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u64", "data": "synthetic", "config": config,
