@@ -50,9 +50,10 @@ struct CountMapArgs {
   uint32_t nw;                 // u32 words per strand row in shared memory (2*wpr + 2)
   uint32_t row_stride;         // u32 words per thread (both strands, odd)
   int primary_only;
+  uint32_t n_cells;            // cell indices >= n_cells are a caller error: dropped and counted in metrics[8]
   uint64_t* keys;
   unsigned long long* cursor;  // number of keys appended so far
-  unsigned long long* metrics; // [6] + [2] seed-filter tests / dictionary probes
+  unsigned long long* metrics; // [6] + [2] seed-filter tests / dictionary probes + [1] out-of-range cell indices
   uint8_t* codes;              // optional per-read debug output
 };
 
@@ -114,7 +115,7 @@ __global__ void __launch_bounds__(MAP_THREADS, MINB) k_count_map(const CountMapA
   uint32_t* seed_info = seed_node + TILE;                                   // off(20) | pos(10) | phase(2)
   uint16_t* lens = reinterpret_cast<uint16_t*>(seed_info + TILE);
   uint8_t* q = reinterpret_cast<uint8_t*>(lens + TILE);                     // 3 queues of TILE slots
-  unsigned long long m_reads = 0, m_nonprim = 0, m_notcell = 0, m_cds = 0, m_gen = 0, m_none = 0;
+  unsigned long long m_reads = 0, m_nonprim = 0, m_notcell = 0, m_cds = 0, m_gen = 0, m_none = 0, m_badcell = 0;
   uint32_t n_tests = 0, n_probes = 0;
   const uint64_t n_warps = (uint64_t)gridDim.x * (MAP_THREADS / 32);
   for (uint64_t tile = (uint64_t)blockIdx.x * (MAP_THREADS / 32) + warp; tile * TILE < a.n; tile += n_warps) {
@@ -130,7 +131,7 @@ __global__ void __launch_bounds__(MAP_THREADS, MINB) k_count_map(const CountMapA
       if (i < a.n) {
         const uint8_t fl = __ldg(a.flags + i);
         const uint32_t cell = __ldg(a.cell + i);
-        const uint16_t L = __ldg(a.len + i);
+        const uint16_t L = (uint16_t)min((uint32_t)__ldg(a.len + i), 32u * a.wpr);   // never read past the packed words
         uint32_t* fw = rows + slot * a.row_stride;
         for (uint32_t w = 0; w < a.wpr; w++) {
           const uint64_t v = __ldg(a.seq + i * a.wpr + w);
@@ -143,6 +144,7 @@ __global__ void __launch_bounds__(MAP_THREADS, MINB) k_count_map(const CountMapA
         if (!primary) m_nonprim++;
         if (primary || !a.primary_only) {
           if (cell == HLAC_NOT_A_CELL) m_notcell++;
+          else if (cell >= a.n_cells) m_badcell++;
           else keep = true;
         }
         if (a.codes) a.codes[i] = (uint8_t)HLAC_CODE_NONE;
@@ -226,9 +228,9 @@ __global__ void __launch_bounds__(MAP_THREADS, MINB) k_count_map(const CountMapA
     }
   }
   // metrics: warp reduce then one atomic per counter per warp
-  unsigned long long m[8] = {m_reads, m_nonprim, m_notcell, m_cds, m_gen, m_none, n_tests, n_probes};
+  unsigned long long m[9] = {m_reads, m_nonprim, m_notcell, m_cds, m_gen, m_none, n_tests, n_probes, m_badcell};
 #pragma unroll
-  for (int k = 0; k < 8; k++) {
+  for (int k = 0; k < 9; k++) {
     unsigned long long v = m[k];
     for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, o);
     if (lane == 0 && v) atomicAdd(a.metrics + k, v);
@@ -354,7 +356,7 @@ struct hlac_count {
     events.clear();
   }
   void reset() {
-    HLAC_CUDA(cudaMemsetAsync(counters.p, 0, 9 * sizeof(unsigned long long), stream));
+    HLAC_CUDA(cudaMemsetAsync(counters.p, 0, 10 * sizeof(unsigned long long), stream));
     reads_pushed = 0; last_n = 0; reduced = false; n_keys = 0;
     drain_events(); ms[0] = ms[1] = ms[2] = ms[3] = 0; launches = 0;
   }
@@ -369,7 +371,7 @@ struct hlac_count {
     a.cinfo_cds = cinfo_cds.p; a.cinfo_gen = cinfo_gen.p;
     a.seq = b.seq; a.len = b.len; a.cell = b.cell; a.umi = b.umi; a.flags = b.flags;
     a.n = b.n; a.wpr = b.words_per_read; a.nw = 2 * b.words_per_read + 2; a.row_stride = (2 * a.nw) | 1;
-    a.primary_only = primary_only;
+    a.primary_only = primary_only; a.n_cells = n_cells;
     a.keys = keys.p; a.cursor = counters.p; a.metrics = counters.p + 1;
     a.codes = want_codes ? codes.p : nullptr;
     // launch shape: (bitmaps in shared memory?, reads per lane per warp tile R, threads per block). Defaults below;
@@ -573,10 +575,11 @@ int hlac_count_entries(hlac_count* s, hlac_coo* out, hlac_metrics* metrics) try 
   const uint32_t nrows = s->rows.nrows;
   const size_t nd = (size_t)s->n_cells * std::max<uint32_t>(nrows, 1);
   std::vector<uint32_t> dense(nd);
-  unsigned long long ctr[9];
+  unsigned long long ctr[10];
   HLAC_CUDA(cudaMemcpyAsync(dense.data(), s->dense.p, nd * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
   HLAC_CUDA(cudaMemcpyAsync(ctr, s->counters.p, sizeof ctr, cudaMemcpyDeviceToHost, s->stream));
   HLAC_CUDA(cudaStreamSynchronize(s->stream));
+  if (ctr[9]) throw Error(HLAC_ERR_ARG, std::to_string(ctr[9]) + " reads carried a cell index >= n_cells (the reference panics in TriMat::add_triplet, main.rs:279)");
   if (metrics) {
     metrics->num_reads = ctr[1]; metrics->num_non_primary = ctr[2]; metrics->num_not_cell_bc = ctr[3];
     metrics->num_cds_align = ctr[4]; metrics->num_gen_align = ctr[5]; metrics->num_not_aligned = ctr[6];

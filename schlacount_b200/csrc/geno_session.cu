@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(GENO_THREADS) k_geno_map(const GenoMapArgs a) 
   uint32_t n_tests = 0, n_probes = 0;
   for (uint64_t i = (uint64_t)blockIdx.x * GENO_THREADS + threadIdx.x; i < a.n; i += (uint64_t)gridDim.x * GENO_THREADS) {
     load_read_row(a.seq, i, a.wpr, fw);
-    const int L = a.len[i];
+    const int L = min((int)a.len[i], (int)(32 * a.wpr));   // never read past the packed words
     uint32_t cov = 0; uint64_t ha = 0, hb = 0; uint8_t strand = 0;
     bool found = false;
 #pragma unroll 1
@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(GENO_THREADS) k_geno_paths(const GenoPathArgs 
   const uint32_t id = a.first_new + k;
   const uint64_t i = a.e.rep_read[id];
   load_read_row(a.seq, i, a.wpr, fw);
-  const int L = a.len[i];
+  const int L = min((int)a.len[i], (int)(32 * a.wpr));
   const bool rev = a.strand[i] != 0;
   if (rev) make_revcomp(SharedWords{fw}, rc, L, (int)a.nw);
   SharedWords rd{rev ? rc : fw};

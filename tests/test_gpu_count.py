@@ -113,3 +113,49 @@ def test_reset_and_repeat(sb, abc, fixture_reads):
     assert e1 == e2 and m1 == m2
     t = s.timing()
     assert t["launches"] >= 2 and t["map_ms"] > 0
+
+
+def test_abi_argument_errors(sb, abc):
+    """Errors surface as negative status + message, never as a crash or a silent fallback."""
+    import ctypes as C
+    L = sb.lib()
+    assert L.hlac_count_new(None, None, C.c_uint32(1), C.c_int(0), C.byref(C.c_void_p())) != 0
+    assert b"null" in L.hlac_last_error()
+    with pytest.raises(sb.HlacError):
+        sb.CountSession(abc["gc"], abc["gg"], 0)
+    s = sb.CountSession(abc["gc"], abc["gg"], 4)
+    with pytest.raises(sb.HlacError):        # entries before reduce
+        s.entries()
+    with pytest.raises(sb.HlacError):        # codes were not being recorded
+        s.last_codes(1)
+    # a cell index >= n_cells is a caller error and must be reported, not written out of bounds
+    seq, lens = sb.pack_reads(["ACGT" * 23])
+    s.push(seq, lens, np.array([7], np.uint32), np.array([1], np.uint32), np.array([1], np.uint8))
+    with pytest.raises(sb.HlacError, match="cell index"):
+        s.finish()
+
+
+def test_long_reads_and_interned_umis(sb, orc, abc):
+    """150/250 bp reads (wpr 5 and 8, smaller shared-memory tiles) and UMI keys with bit 31 set."""
+    from tools import synth
+    cds, gen = synth.fixture_alleles()
+    rng = np.random.default_rng(5)
+    rc = lambda s: s[::-1].translate(str.maketrans("ACGT", "TGCA"))
+    for L in (150, 250):
+        reads = []
+        for i in range(3000):
+            src = (cds if rng.random() < 0.7 else gen)[int(rng.integers(0, 6))][1]
+            st = int(rng.integers(0, len(src) - L))
+            s = list(src[st:st + L])
+            for p in rng.integers(0, L, size=int(rng.integers(0, 4))):
+                s[p] = "ACGT"[int(rng.integers(0, 4))]
+            s = "".join(s)
+            reads.append((rc(s) if rng.random() < 0.5 else s, b"c%d" % int(rng.integers(0, 9)),
+                          b"NNACGTNN%d" % int(rng.integers(0, 40)), True))
+        bc = {b"c%d" % i: i for i in range(9)}
+        batch = H.make_batch(reads, bc, pack=sb.pack_reads)
+        assert (batch[3] >> 31).all()
+        ent, met, codes, _ = _run_gpu(sb, abc, batch, 9)
+        ref = orc.count_run(abc["oc"], abc["og"], *batch, want_codes=True)
+        assert np.array_equal(codes, ref["codes"]) and met == ref["metrics"] and ent == ref["entries"]
+        assert len(ent) > 20
