@@ -87,27 +87,87 @@ __device__ __forceinline__ void load_read_row(const uint64_t* seq, uint64_t i, u
   fw[2 * wpr] = 0; fw[2 * wpr + 1] = 0;
 }
 
+// Warp-staged like k_count_map (count_session.cu): each warp owns a tile of 32*GENO_R reads; load -> forward seed scan
+// -> (survivors) reverse-complement seed scan -> dense walk queue. mapping.rs:341-363: forward, else reverse
+// complement; the unmapped pass (forward_only) never tries the reverse complement (mapping.rs:383).
+constexpr int GENO_R = 2;
 __global__ void __launch_bounds__(GENO_THREADS) k_geno_map(const GenoMapArgs a) {
   extern __shared__ __align__(16) uint32_t smem[];
-  uint32_t* fw = smem + threadIdx.x * a.row_stride;
-  uint32_t* rc = fw + a.nw;
+  constexpr int TILE = 32 * GENO_R;
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t per_warp = TILE * a.row_stride + TILE * 2 + TILE / 2 + 3 * TILE / 4;   // u32 words
+  uint32_t* rows = smem + warp * per_warp;
+  uint32_t* seed_node = rows + TILE * a.row_stride;
+  uint32_t* seed_info = seed_node + TILE;                                   // off(20) | pos(10) | strand(1)
+  uint16_t* lens = reinterpret_cast<uint16_t*>(seed_info + TILE);
+  uint8_t* q = reinterpret_cast<uint8_t*>(lens + TILE);                     // [0] scan fwd, [1] scan rev, [2] walk
   unsigned long long some = 0, lng = 0;
   uint32_t n_tests = 0, n_probes = 0;
-  for (uint64_t i = (uint64_t)blockIdx.x * GENO_THREADS + threadIdx.x; i < a.n; i += (uint64_t)gridDim.x * GENO_THREADS) {
-    load_read_row(a.seq, i, a.wpr, fw);
-    const int L = min((int)a.len[i], (int)(32 * a.wpr));   // never read past the packed words
-    uint32_t cov = 0; uint64_t ha = 0, hb = 0; uint8_t strand = 0;
-    bool found = false;
-#pragma unroll 1
-    for (int p = 0; p < 2; p++) {   // mapping.rs:341-363: forward, else reverse complement; unmapped pass forward only
-      if (p == 1) { if (a.forward_only) break; make_revcomp(SharedWords{fw}, rc, L, (int)a.nw); }
-      HashVis vis;
-      found = map_read_walk(a.ix, SharedWords{p ? rc : fw}, BitmapGlobal{a.ix.bitmap}, L, vis, cov, n_tests, n_probes);
-      if (found) { vis.finish(); ha = vis.a; hb = vis.b; strand = (uint8_t)p; break; }
+  BitmapGlobal bm{a.ix.bitmap};
+  const uint64_t n_warps = (uint64_t)gridDim.x * (GENO_THREADS / 32);
+  for (uint64_t tile = (uint64_t)blockIdx.x * (GENO_THREADS / 32) + warp; tile * TILE < a.n; tile += n_warps) {
+    const uint64_t base = tile * TILE;
+    unsigned cnt0 = 0, cnt1 = 0, cntw = 0;
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < GENO_R; r++) {
+      const unsigned slot = r * 32 + lane;
+      const uint64_t i = base + slot;
+      const bool valid = i < a.n;
+      if (valid) {
+        load_read_row(a.seq, i, a.wpr, rows + slot * a.row_stride);
+        lens[slot] = (uint16_t)min((uint32_t)a.len[i], 32u * a.wpr);   // never read past the packed words
+        a.cov[i] = 0; a.hash_a[i] = 0; a.hash_b[i] = 0; a.strand[i] = 0;
+      }
+      const unsigned ballot = __ballot_sync(0xFFFFFFFFu, valid);
+      if (valid) q[cnt0 + __popc(ballot & ((1u << lane) - 1))] = (uint8_t)slot;
+      cnt0 += __popc(ballot);
     }
-    if (!found) cov = 0;
-    a.cov[i] = cov; a.hash_a[i] = ha; a.hash_b[i] = hb; a.strand[i] = strand;
-    if (found) { some++; if (cov > MIN_SCORE_CALL) lng++; }
+    __syncwarp();
+#pragma unroll 1
+    for (int p = 0; p < 2; p++) {
+      if (p == 1 && a.forward_only) break;
+      const unsigned nt = p ? cnt1 : cnt0;
+      const uint8_t* qc = q + (p ? TILE : 0);
+      for (unsigned t0 = 0; t0 < nt; t0 += 32) {
+        const bool task = t0 + lane < nt;
+        bool found = false;
+        unsigned slot = 0;
+        if (task) {
+          slot = qc[t0 + lane];
+          uint32_t* fw = rows + slot * a.row_stride;
+          uint32_t* rc = fw + a.nw;
+          const int L = lens[slot];
+          if (p == 1) make_revcomp(SharedWords{fw}, rc, L, (int)a.nw);
+          int pos = 0; uint32_t node = 0, off = 0;
+          if (L >= K) found = find_seed(a.ix, SharedWords{p ? rc : fw}, bm, pos, L - K, node, off, n_tests, n_probes);
+          if (found) { seed_node[slot] = node; seed_info[slot] = (off << 12) | ((uint32_t)pos << 2) | (uint32_t)p; }
+        }
+        __syncwarp();
+        const unsigned bf = __ballot_sync(0xFFFFFFFFu, task && found), bn = __ballot_sync(0xFFFFFFFFu, task && !found);
+        const unsigned below = (1u << lane) - 1;
+        if (task && found) q[2 * TILE + cntw + __popc(bf & below)] = (uint8_t)slot;
+        if (p == 0 && task && !found) q[TILE + cnt1 + __popc(bn & below)] = (uint8_t)slot;
+        cntw += __popc(bf);
+        if (p == 0) cnt1 += __popc(bn);
+      }
+      __syncwarp();
+    }
+    for (unsigned t0 = 0; t0 < cntw; t0 += 32) {
+      if (t0 + lane < cntw) {
+        const unsigned slot = q[2 * TILE + t0 + lane];
+        const uint64_t i = base + slot;
+        const uint32_t info = seed_info[slot];
+        const int p = (int)(info & 3u), pos = (int)((info >> 2) & 1023u);
+        uint32_t* fw = rows + slot * a.row_stride;
+        HashVis vis;
+        const uint32_t cov = walk_from_seed(a.ix, SharedWords{p ? fw + a.nw : fw}, bm, (int)lens[slot], pos, seed_node[slot], info >> 12, vis, n_tests, n_probes);
+        vis.finish();
+        a.cov[i] = cov; a.hash_a[i] = vis.a; a.hash_b[i] = vis.b; a.strand[i] = (uint8_t)p;
+        some++;
+        if (cov > MIN_SCORE_CALL) lng++;
+      }
+    }
   }
   unsigned long long m[4] = {some, lng, n_tests, n_probes};
 #pragma unroll
@@ -374,12 +434,16 @@ struct hlac_geno {
     GenoMapArgs a{};
     a.ix = idx->view; a.seq = b.seq; a.len = b.len; a.n = n; a.wpr = b.words_per_read; a.nw = 2 * a.wpr + 2; a.row_stride = (2 * a.nw) | 1;
     a.forward_only = forward_only; a.cov = cov.p; a.hash_a = hash_a.p; a.hash_b = hash_b.p; a.strand = strand.p; a.stats = ctr.p + 4;
-    const size_t smem = (size_t)GENO_THREADS * a.row_stride * 4;
+    const size_t smem_paths = (size_t)GENO_THREADS * a.row_stride * 4;   // k_geno_paths: one row pair per thread
+    const size_t per_warp_words = (size_t)32 * GENO_R * a.row_stride + 32 * GENO_R * 2 + 32 * GENO_R / 2 + 3 * 32 * GENO_R / 4;
+    const size_t smem = (GENO_THREADS / 32) * per_warp_words * 4;
+    if (smem > 227 * 1024) throw Error(HLAC_ERR_LIMIT, "reads too long for the shared-memory tile of the genotyping kernel");
     HLAC_CUDA(cudaFuncSetAttribute(k_geno_map, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    HLAC_CUDA(cudaFuncSetAttribute(k_geno_paths, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    HLAC_CUDA(cudaFuncSetAttribute(k_geno_paths, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_paths));
     int occ = 1;
     HLAC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_geno_map, GENO_THREADS, smem));
-    const unsigned grid = (unsigned)std::min<uint64_t>((n + GENO_THREADS - 1) / GENO_THREADS, (uint64_t)n_sm * std::max(occ, 1));
+    const uint64_t per_block = (uint64_t)GENO_THREADS * GENO_R;
+    const unsigned grid = (unsigned)std::min<uint64_t>((n + per_block - 1) / per_block, (uint64_t)n_sm * std::max(occ, 1));
     size_t e0 = begin(0);
     k_geno_map<<<grid, GENO_THREADS, smem, stream>>>(a);
     HLAC_CUDA(cudaGetLastError());
@@ -398,7 +462,7 @@ struct hlac_geno {
       GenoPathArgs p{};
       p.ix = idx->view; p.seq = b.seq; p.len = b.len; p.strand = strand.p; p.wpr = a.wpr; p.nw = a.nw; p.row_stride = a.row_stride;
       p.e = entries(); p.first_new = (uint32_t)n_entries; p.n_new = n_new; p.arena = arena.p; p.arena_cursor = ctr.p + 1;
-      k_geno_paths<<<(n_new + GENO_THREADS - 1) / GENO_THREADS, GENO_THREADS, smem, stream>>>(p);
+      k_geno_paths<<<(n_new + GENO_THREADS - 1) / GENO_THREADS, GENO_THREADS, smem_paths, stream>>>(p);
       HLAC_CUDA(cudaGetLastError());
       launches++;
     }
