@@ -63,6 +63,9 @@ typedef struct {
   const uint8_t* flags;
   uint64_t n;
   uint32_t words_per_read;
+  /* genotyping only, optional (NULL = position in the push stream): global ordinal of each read in BAM order, for a
+   * session that sees only a shard of the stream (first-seen class ids are global, mapping.rs:147-154) */
+  const uint64_t* ordinal;
 } hlac_batch;
 
 typedef struct { /* mapping.rs:108-116 `Metrics` */
@@ -177,6 +180,27 @@ int hlac_geno_stats(hlac_geno*, uint64_t* some_aln, uint64_t* long_aln, uint64_t
  * hlac_geno_read_class_ids returns, for every read pushed so far, its first-seen eq_class_id or 0xFFFFFFFF. */
 int hlac_geno_finish(hlac_geno*, hlac_class_tables* out);
 int hlac_geno_read_class_ids(hlac_geno*, uint32_t* ids, uint64_t n);
+/* hlac_geno_finish in two halves, for multi-GPU runs: _begin resolves the classes and leaves the per-class UMI
+ * histogram (u32[n_classes], classes in first-seen order) on the device so that ranks can all-reduce it; _end reads
+ * it back and assembles the tables. */
+int hlac_geno_finish_begin(hlac_geno*, uint32_t** umi_hist_device, uint64_t* n_classes);
+int hlac_geno_finish_end(hlac_geno*, hlac_class_tables* out);
+/* the distinct colour paths a session has interned: hash pair, first-seen ordinal, read count, colour ids (CSR).
+ * Multi-GPU (reads partitioned by barcode): every rank exports, all ranks gather the parts, build the
+ * identical union with hlac_paths_merge and adopt it with hlac_geno_import_paths before hlac_geno_finish_begin. */
+typedef struct {
+  uint64_t n_paths;
+  uint64_t* hash_a;
+  uint64_t* hash_b;
+  uint64_t* first_ord;
+  uint32_t* count;
+  uint64_t* off; /* n_paths + 1 */
+  uint32_t* colours;
+} hlac_paths;
+int hlac_geno_export_paths(hlac_geno*, hlac_paths* out);
+int hlac_paths_merge(const hlac_paths* parts, uint32_t n_parts, hlac_paths* out);
+int hlac_geno_import_paths(hlac_geno*, const hlac_paths* merged);
+int hlac_paths_free(hlac_paths*);
 int hlac_class_tables_free(hlac_class_tables*);
 int hlac_geno_timing(hlac_geno*, float ms[4], uint64_t* launches);
 

@@ -31,7 +31,7 @@ def declared_symbols():
 
 class Batch(C.Structure):
     _fields_ = [("seq", C.c_void_p), ("len", C.c_void_p), ("cell", C.c_void_p), ("umi", C.c_void_p),
-                ("flags", C.c_void_p), ("n", C.c_uint64), ("words_per_read", C.c_uint32)]
+                ("flags", C.c_void_p), ("n", C.c_uint64), ("words_per_read", C.c_uint32), ("ordinal", C.c_void_p)]
 
 
 class Metrics(C.Structure):
@@ -57,6 +57,12 @@ class ClassTables(C.Structure):
                 ("n_umi_classes", C.c_uint64), ("umi_off", C.POINTER(C.c_uint64)),
                 ("umi_tx", C.POINTER(C.c_uint32)), ("umi_cnt", C.POINTER(C.c_uint32)),
                 ("reads_explained", C.POINTER(C.c_uint64))]
+
+
+class Paths(C.Structure):
+    _fields_ = [("n_paths", C.c_uint64), ("hash_a", C.POINTER(C.c_uint64)), ("hash_b", C.POINTER(C.c_uint64)),
+                ("first_ord", C.POINTER(C.c_uint64)), ("count", C.POINTER(C.c_uint32)), ("off", C.POINTER(C.c_uint64)),
+                ("colours", C.POINTER(C.c_uint32))]
 
 
 class Calls(C.Structure):

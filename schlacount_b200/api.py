@@ -120,7 +120,7 @@ def make_batch(seq, lens, cell, umi, flags):
         wpr = seq.size // max(n, 1)
     else:
         wpr = seq.numel() // max(n, 1)
-    b = _lib.Batch(_vp(seq), _vp(lens), _vp(cell), _vp(umi), _vp(flags), n, wpr)
+    b = _lib.Batch(_vp(seq), _vp(lens), _vp(cell), _vp(umi), _vp(flags), n, wpr, None)
     return b, (seq, lens, cell, umi, flags)
 
 
@@ -269,17 +269,79 @@ class GenoSession:
         except Exception:
             pass
 
-    def push(self, seq, lens, cell, umi, forward_only=False):
+    def push(self, seq, lens, cell, umi, forward_only=False, ordinal=None):
+        """ordinal (optional u64 per read): global position in BAM order when this session only sees a shard."""
         n = len(lens)
         flags = np.zeros(n, np.uint8) if isinstance(seq, np.ndarray) else None
         if isinstance(seq, np.ndarray):
             b, keep = make_batch(seq, lens, cell, umi, flags)
+            if ordinal is not None:
+                ordinal = np.ascontiguousarray(ordinal, dtype=np.uint64)
+                b.ordinal = _vp(ordinal)
             check(lib().hlac_geno_push(self.h, C.byref(b), C.c_int(int(forward_only))))
         else:
             wpr = seq.numel() // max(n, 1)
-            b = _lib.Batch(_vp(seq), _vp(lens), _vp(cell), _vp(umi), None, n, wpr)
+            b = _lib.Batch(_vp(seq), _vp(lens), _vp(cell), _vp(umi), None, n, wpr, _vp(ordinal))
             check(lib().hlac_geno_push_device(self.h, C.byref(b), C.c_int(int(forward_only))))
         self._n_last = n
+
+    # ---- multi-GPU merge (SURVEY.md 8e) ----
+    def export_paths(self):
+        """-> dict of numpy arrays (hash_a, hash_b, first_ord, count, off, colours): picklable, for an all-gather"""
+        p = _lib.Paths()
+        check(lib().hlac_geno_export_paths(self.h, C.byref(p)))
+        n = int(p.n_paths)
+        tot = int(p.off[n]) if n else 0
+        out = dict(hash_a=np.ctypeslib.as_array(p.hash_a, shape=(max(n, 1),))[:n].copy(),
+                   hash_b=np.ctypeslib.as_array(p.hash_b, shape=(max(n, 1),))[:n].copy(),
+                   first_ord=np.ctypeslib.as_array(p.first_ord, shape=(max(n, 1),))[:n].copy(),
+                   count=np.ctypeslib.as_array(p.count, shape=(max(n, 1),))[:n].copy(),
+                   off=np.ctypeslib.as_array(p.off, shape=(n + 1,)).copy(),
+                   colours=np.ctypeslib.as_array(p.colours, shape=(max(tot, 1),))[:tot].copy())
+        lib().hlac_paths_free(C.byref(p))
+        return out
+
+    def import_merged_paths(self, parts):
+        """parts: list of export_paths() dicts from every rank (same order on every rank). Builds the union and adopts it."""
+        arr = (_lib.Paths * len(parts))()
+        keep = []
+        for k, d in enumerate(parts):
+            a = {x: np.ascontiguousarray(d[x]) for x in d}
+            for x in ("hash_a", "hash_b", "first_ord", "off"):
+                a[x] = a[x].astype(np.uint64, copy=False)
+            for x in ("count", "colours"):
+                a[x] = a[x].astype(np.uint32, copy=False)
+                if a[x].size == 0:
+                    a[x] = np.zeros(1, np.uint32)
+            keep.append(a)
+            arr[k].n_paths = len(d["hash_a"])
+            for x, t in (("hash_a", C.c_uint64), ("hash_b", C.c_uint64), ("first_ord", C.c_uint64), ("off", C.c_uint64),
+                         ("count", C.c_uint32), ("colours", C.c_uint32)):
+                setattr(arr[k], x, a[x].ctypes.data_as(C.POINTER(t)))
+        merged = _lib.Paths()
+        check(lib().hlac_paths_merge(arr, C.c_uint32(len(parts)), C.byref(merged)))
+        try:
+            check(lib().hlac_geno_import_paths(self.h, C.byref(merged)))
+            return int(merged.n_paths)
+        finally:
+            lib().hlac_paths_free(C.byref(merged))
+
+    def finish_begin(self):
+        """-> (device pointer of the u32 per-class UMI histogram, n_classes): all-reduce it across ranks, then finish_end()"""
+        p = C.c_void_p()
+        n = C.c_uint64()
+        check(lib().hlac_geno_finish_begin(self.h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def finish_end(self, raw=False):
+        if self.tables is not None:
+            lib().hlac_class_tables_free(C.byref(self.tables))
+        self.tables = _lib.ClassTables()
+        check(lib().hlac_geno_finish_end(self.h, C.byref(self.tables)))
+        if raw:
+            t = self.tables
+            return dict(nitems=t.nitems, nreads=t.nreads, n_read_classes=t.n_read_classes, n_umi_classes=t.n_umi_classes)
+        return _tables_to_py(self.tables)
 
     def last_cov(self):
         out = np.zeros(self._n_last, dtype=np.uint32)

@@ -184,6 +184,7 @@ struct PathTable {
   uint64_t mask;
 };
 struct PathEntries {          // dense, indexed by path id
+  uint64_t* hash_a;
   uint64_t* hash_b;
   unsigned long long* first_ord;
   uint32_t* count;
@@ -206,7 +207,7 @@ __global__ void k_intern_insert(PathTable t, PathEntries e, const uint32_t* __re
       if (old == 0) {   // winner: allocate the dense id and register as representative
         const uint32_t id = (uint32_t)atomicAdd(n_entries, 1ULL);
         t.ids[h] = id;
-        e.hash_b[id] = hb[i]; e.first_ord[id] = ~0ULL; e.count[id] = 0; e.rep_read[id] = (uint32_t)i;
+        e.hash_a[id] = key; e.hash_b[id] = hb[i]; e.first_ord[id] = ~0ULL; e.count[id] = 0; e.rep_read[id] = (uint32_t)i;
         e.path_off[id] = 0; e.path_len[id] = 0;
         return;
       }
@@ -251,7 +252,7 @@ struct Record { uint32_t bc, umi, path; };
 
 __global__ void k_intern_lookup(PathTable t, PathEntries e, const uint32_t* __restrict__ cov, const uint64_t* __restrict__ ha,
                                 const uint64_t* __restrict__ hb, const uint32_t* __restrict__ cell, const uint32_t* __restrict__ umi,
-                                uint64_t n, uint64_t ord0, uint64_t* rec_key, uint32_t* rec_path, unsigned long long* rec_cursor,
+                                uint64_t n, uint64_t ord0, const uint64_t* __restrict__ ordinal, uint64_t* rec_key, uint32_t* rec_path, unsigned long long* rec_cursor,
                                 uint32_t* read_path, unsigned long long* collisions) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned lane = threadIdx.x & 31;
@@ -263,7 +264,7 @@ __global__ void k_intern_lookup(PathTable t, PathEntries e, const uint32_t* __re
     while (t.keys[h] != key) h = (h + 1) & t.mask;
     id = t.ids[h];
     if (e.hash_b[id] != hb[i]) atomicAdd(collisions, 1ULL);
-    atomicMin(e.first_ord + id, (unsigned long long)(ord0 + i));
+    atomicMin(e.first_ord + id, (unsigned long long)(ordinal ? ordinal[i] : ord0 + i));
     atomicAdd(e.count + id, 1u);
   }
   if (i < n && read_path) read_path[i] = id;
@@ -289,6 +290,22 @@ __global__ void k_rehash(const unsigned long long* __restrict__ okeys, const uin
     if (atomicCAS(t.keys + h, 0ULL, key) == 0) { t.ids[h] = oids[i]; return; }
     h = (h + 1) & t.mask;
   }
+}
+
+// rebuild the table from dense entries (after hlac_geno_import_paths)
+__global__ void k_table_build(PathTable t, const uint64_t* __restrict__ hash_a, uint32_t n) {
+  const uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= n) return;
+  const unsigned long long key = hash_a[id];
+  uint64_t h = mix64(key) & t.mask;
+  for (;;) {
+    if (atomicCAS(t.keys + h, 0ULL, key) == 0) { t.ids[h] = id; return; }
+    h = (h + 1) & t.mask;
+  }
+}
+__global__ void k_remap(uint32_t* ids, uint64_t n, const uint32_t* __restrict__ map) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && ids[i] != NONE32) ids[i] = map[ids[i]];
 }
 
 // per path: length of its class vector = |colours[last colour of the path]|
@@ -356,10 +373,11 @@ struct hlac_geno {
   DevBuf<uint64_t> st_seq, hash_a, hash_b;
   DevBuf<uint16_t> st_len;
   DevBuf<uint32_t> st_cell, st_umi, cov;
+  DevBuf<uint64_t> st_ord;
   DevBuf<uint8_t> strand;
   // path table
   DevBuf<unsigned long long> t_keys; DevBuf<uint32_t> t_ids; uint64_t t_cap = 0;
-  DevBuf<uint64_t> e_hash_b, e_path_off; DevBuf<unsigned long long> e_first_ord; DevBuf<uint32_t> e_count, e_path_len, e_rep;
+  DevBuf<uint64_t> e_hash_a, e_hash_b, e_path_off; DevBuf<unsigned long long> e_first_ord; DevBuf<uint32_t> e_count, e_path_len, e_rep;
   DevBuf<uint32_t> arena;
   DevBuf<unsigned long long> ctr;   // [0] n_entries [1] arena cursor [2] rec cursor [3] collisions [4..7] stats
   // records of counted reads
@@ -369,6 +387,8 @@ struct hlac_geno {
   // finish results kept for hlac_geno_read_class_ids
   std::vector<uint32_t> class_of_path;
   bool finished = false;
+  // between hlac_geno_finish_begin and _end
+  std::vector<std::vector<uint32_t>> fin_cls_vec; std::vector<uint32_t> fin_cls_reads; DevBuf<uint32_t> fin_hist; bool fin_begun = false;
   float ms[4] = {0, 0, 0, 0};
   uint64_t launches = 0;
   struct Ev { cudaEvent_t a, b; int kind; };
@@ -394,7 +414,7 @@ struct hlac_geno {
     events.clear();
   }
   PathTable table() { return PathTable{t_keys.p, t_ids.p, t_cap - 1}; }
-  PathEntries entries() { return PathEntries{e_hash_b.p, e_first_ord.p, e_count.p, e_path_off.p, e_path_len.p, e_rep.p}; }
+  PathEntries entries() { return PathEntries{e_hash_a.p, e_hash_b.p, e_first_ord.p, e_count.p, e_path_off.p, e_path_len.p, e_rep.p}; }
 
   void ensure_table(uint64_t want_entries) {
     uint64_t cap = t_cap ? t_cap : (1u << 16);
@@ -415,7 +435,7 @@ struct hlac_geno {
       t_cap = cap;
     }
     const size_t ne = want_entries;
-    e_hash_b.reserve(ne, stream, true, n_entries); e_path_off.reserve(ne, stream, true, n_entries);
+    e_hash_a.reserve(ne, stream, true, n_entries); e_hash_b.reserve(ne, stream, true, n_entries); e_path_off.reserve(ne, stream, true, n_entries);
     e_first_ord.reserve(ne, stream, true, n_entries); e_count.reserve(ne, stream, true, n_entries);
     e_path_len.reserve(ne, stream, true, n_entries); e_rep.reserve(ne, stream, true, n_entries);
   }
@@ -466,7 +486,7 @@ struct hlac_geno {
       HLAC_CUDA(cudaGetLastError());
       launches++;
     }
-    k_intern_lookup<<<g1, 256, 0, stream>>>(table(), entries(), cov.p, hash_a.p, hash_b.p, b.cell, b.umi, n, reads_pushed,
+    k_intern_lookup<<<g1, 256, 0, stream>>>(table(), entries(), cov.p, hash_a.p, hash_b.p, b.cell, b.umi, n, reads_pushed, b.ordinal,
                                             rec_key.p, rec_path.p, ctr.p + 2, record_reads ? read_path.p + reads_pushed : nullptr, ctr.p + 3);
     HLAC_CUDA(cudaGetLastError());
     launches++;
@@ -526,9 +546,11 @@ int hlac_geno_push(hlac_geno* s, const hlac_batch* b, int forward_only) try {
   s->st_len.upload(b->len, b->n, s->stream);
   s->st_cell.upload(b->cell, b->n, s->stream);
   s->st_umi.upload(b->umi, b->n, s->stream);
+  if (b->ordinal) s->st_ord.upload(b->ordinal, b->n, s->stream);
   s->end(e);
   hlac_batch d = *b;
   d.seq = s->st_seq.p; d.len = s->st_len.p; d.cell = s->st_cell.p; d.umi = s->st_umi.p; d.flags = nullptr;
+  d.ordinal = b->ordinal ? s->st_ord.p : nullptr;
   s->push_device(d, forward_only);
   return HLAC_OK;
 } catch (const Error& e) { set_last_error(e.what()); return e.code; } catch (const std::exception& e) { set_last_error(e.what()); return HLAC_ERR_STATE; }
@@ -542,20 +564,17 @@ int hlac_geno_last_cov(hlac_geno* s, uint32_t* cov, uint64_t n) try {
   return HLAC_OK;
 } catch (const Error& e) { set_last_error(e.what()); return e.code; }
 
-int hlac_geno_finish(hlac_geno* s, hlac_class_tables* out) try {
-  if (!s || !out) throw Error(HLAC_ERR_ARG, "null argument");
+int hlac_geno_finish_begin(hlac_geno* s, uint32_t** umi_hist_device, uint64_t* n_classes) try {
+  if (!s) throw Error(HLAC_ERR_ARG, "null argument");
   DeviceGuard g(s->device);
   const HostIndex& hx = s->idx->host;
   const uint32_t nitems = (uint32_t)hx.tx_names.size();
   const uint32_t E = (uint32_t)s->n_entries;
   const uint64_t R = s->n_records_ub;
-  memset(out, 0, sizeof *out);
-  out->nitems = nitems;
-  out->nreads = (uint32_t)R;
-  out->reads_explained = (uint64_t*)calloc(std::max<uint32_t>(nitems, 1), 8);
-  std::vector<std::vector<uint32_t>> cls_vec;      // class id (first-seen order) -> raw vector
-  std::vector<uint32_t> cls_reads;                 // counts_reads
-  std::vector<uint32_t> umi_hist;                  // UMIs whose lowest class is this class
+  (void)nitems;
+  auto& cls_vec = s->fin_cls_vec;      // class id (first-seen order) -> raw vector
+  auto& cls_reads = s->fin_cls_reads;  // counts_reads
+  cls_vec.clear(); cls_reads.clear();
   s->class_of_path.assign(E, NONE32);
   if (E) {
     // ---- K3a: resolve every distinct path to its class vector ----
@@ -610,13 +629,13 @@ int hlac_geno_finish(hlac_geno* s, hlac_class_tables* out) try {
     }
     for (uint32_t p = 0; p < E; p++) s->class_of_path[p] = rank[tmp_cls[p]];
     // ---- K3b: group records by (barcode, umi), lowest class id per UMI ----
-    umi_hist.assign(classes.size(), 0);
+    s->fin_hist.reserve(std::max<size_t>(classes.size(), 1), s->stream);
+    HLAC_CUDA(cudaMemsetAsync(s->fin_hist.p, 0, std::max<size_t>(classes.size(), 1) * 4, s->stream));
     if (R) {
-      DevBuf<uint32_t> d_rank_of_path, d_ranks, d_ranks_sorted, d_hist; DevBuf<uint64_t> d_keys_sorted; DevBuf<uint8_t> tmp;
+      DevBuf<uint32_t> d_rank_of_path, d_ranks, d_ranks_sorted; DevBuf<uint64_t> d_keys_sorted; DevBuf<uint8_t> tmp;
+      uint32_t* const hist = s->fin_hist.p;
       d_rank_of_path.upload(s->class_of_path.data(), E, s->stream);
       d_ranks.reserve(R, s->stream); d_ranks_sorted.reserve(R, s->stream); d_keys_sorted.reserve(R, s->stream);
-      d_hist.reserve(classes.size(), s->stream);
-      HLAC_CUDA(cudaMemsetAsync(d_hist.p, 0, classes.size() * 4, s->stream));
       size_t e3 = s->begin(2);
       k_map_rank<<<(unsigned)((R + 255) / 256), 256, 0, s->stream>>>(s->rec_path.p, d_rank_of_path.p, R, d_ranks.p);
       HLAC_CUDA(cudaGetLastError());
@@ -624,14 +643,35 @@ int hlac_geno_finish(hlac_geno* s, hlac_class_tables* out) try {
       HLAC_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, s->rec_key.p, d_keys_sorted.p, d_ranks.p, d_ranks_sorted.p, R, 0, 64, s->stream));
       tmp.reserve(tb, s->stream);
       HLAC_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, s->rec_key.p, d_keys_sorted.p, d_ranks.p, d_ranks_sorted.p, R, 0, 64, s->stream));
-      k_umi_min<<<(unsigned)((R + 255) / 256), 256, 0, s->stream>>>(d_keys_sorted.p, d_ranks_sorted.p, R, d_hist.p);
+      k_umi_min<<<(unsigned)((R + 255) / 256), 256, 0, s->stream>>>(d_keys_sorted.p, d_ranks_sorted.p, R, hist);
       HLAC_CUDA(cudaGetLastError());
       s->end(e3);
       s->launches += 3;
-      HLAC_CUDA(cudaMemcpyAsync(umi_hist.data(), d_hist.p, classes.size() * 4, cudaMemcpyDeviceToHost, s->stream));
       HLAC_CUDA(cudaStreamSynchronize(s->stream));
     }
   }
+  if (!E) { s->fin_hist.reserve(1, s->stream); HLAC_CUDA(cudaMemsetAsync(s->fin_hist.p, 0, 4, s->stream)); HLAC_CUDA(cudaStreamSynchronize(s->stream)); }
+  s->fin_begun = true;
+  if (umi_hist_device) *umi_hist_device = s->fin_hist.p;
+  if (n_classes) *n_classes = cls_vec.size();
+  return HLAC_OK;
+} catch (const Error& e) { set_last_error(e.what()); return e.code; } catch (const std::exception& e) { set_last_error(e.what()); return HLAC_ERR_STATE; }
+
+// Second half of eq_class_counts: reads the (possibly all-reduced) per-class UMI histogram back and assembles the tables.
+int hlac_geno_finish_end(hlac_geno* s, hlac_class_tables* out) try {
+  if (!s || !out) throw Error(HLAC_ERR_ARG, "null argument");
+  if (!s->fin_begun) throw Error(HLAC_ERR_STATE, "hlac_geno_finish_begin has not run");
+  DeviceGuard g(s->device);
+  auto& cls_vec = s->fin_cls_vec; auto& cls_reads = s->fin_cls_reads;
+  const uint32_t nitems = (uint32_t)s->idx->host.tx_names.size();
+  std::vector<uint32_t> umi_hist(std::max<size_t>(cls_vec.size(), 1), 0);
+  HLAC_CUDA(cudaMemcpyAsync(umi_hist.data(), s->fin_hist.p, umi_hist.size() * 4, cudaMemcpyDeviceToHost, s->stream));
+  HLAC_CUDA(cudaStreamSynchronize(s->stream));
+  memset(out, 0, sizeof *out);
+  out->nitems = nitems;
+  uint64_t total_reads = 0; for (uint32_t c : cls_reads) total_reads += c;
+  out->nreads = (uint32_t)total_reads;   // total_reads (mapping.rs:195): every counted read, over all ranks after a path merge
+  out->reads_explained = (uint64_t*)calloc(std::max<uint32_t>(nitems, 1), 8);
   // ---- assemble EqClassCounts (mapping.rs:199-209) ----
   const size_t nc = cls_vec.size();
   uint64_t ntx = 0; for (auto& v : cls_vec) ntx += v.size();
@@ -653,9 +693,125 @@ int hlac_geno_finish(hlac_geno* s, hlac_class_tables* out) try {
   out->umi_off = (uint64_t*)calloc(umi.size() + 1, 8); out->umi_tx = (uint32_t*)calloc(std::max<uint64_t>(utx, 1), 4); out->umi_cnt = (uint32_t*)calloc(std::max<size_t>(umi.size(), 1), 4);
   q = 0; size_t c = 0;
   for (auto& kv : umi) { for (uint32_t t : kv.first) out->umi_tx[q++] = t; out->umi_cnt[c] = kv.second; out->umi_off[++c] = q; }
-  s->finished = true;
+  s->finished = true; s->fin_begun = false;
   return HLAC_OK;
 } catch (const Error& e) { set_last_error(e.what()); return e.code; } catch (const std::exception& e) { set_last_error(e.what()); return HLAC_ERR_STATE; }
+
+int hlac_geno_finish(hlac_geno* s, hlac_class_tables* out) {
+  int rc = hlac_geno_finish_begin(s, nullptr, nullptr);
+  if (rc != HLAC_OK) return rc;
+  return hlac_geno_finish_end(s, out);
+}
+
+// ---- multi-GPU merge of the interned paths ----------------------------------------------------
+// Reads are partitioned by barcode, so every (barcode, UMI) group is complete on one rank, but class identity and the
+// first-seen class order are global. Ranks exchange their distinct colour paths (tiny: a few ids each), every rank
+// builds the same union (hlac_paths_merge), adopts it (hlac_geno_import_paths) and then only the per-class UMI
+// histogram needs an all-reduce between hlac_geno_finish_begin and hlac_geno_finish_end.
+int hlac_geno_export_paths(hlac_geno* s, hlac_paths* out) try {
+  if (!s || !out) throw Error(HLAC_ERR_ARG, "null argument");
+  DeviceGuard g(s->device);
+  const uint64_t E = s->n_entries;
+  memset(out, 0, sizeof *out);
+  out->n_paths = E;
+  out->hash_a = (uint64_t*)calloc(std::max<uint64_t>(E, 1), 8); out->hash_b = (uint64_t*)calloc(std::max<uint64_t>(E, 1), 8);
+  out->first_ord = (uint64_t*)calloc(std::max<uint64_t>(E, 1), 8); out->count = (uint32_t*)calloc(std::max<uint64_t>(E, 1), 4);
+  out->off = (uint64_t*)calloc(E + 1, 8);
+  std::vector<uint64_t> poff(E); std::vector<uint32_t> plen(E), arena(std::max<uint64_t>(s->arena_used, 1));
+  if (E) {
+    HLAC_CUDA(cudaMemcpyAsync(out->hash_a, s->e_hash_a.p, E * 8, cudaMemcpyDeviceToHost, s->stream));
+    HLAC_CUDA(cudaMemcpyAsync(out->hash_b, s->e_hash_b.p, E * 8, cudaMemcpyDeviceToHost, s->stream));
+    HLAC_CUDA(cudaMemcpyAsync(out->first_ord, s->e_first_ord.p, E * 8, cudaMemcpyDeviceToHost, s->stream));
+    HLAC_CUDA(cudaMemcpyAsync(out->count, s->e_count.p, E * 4, cudaMemcpyDeviceToHost, s->stream));
+    HLAC_CUDA(cudaMemcpyAsync(poff.data(), s->e_path_off.p, E * 8, cudaMemcpyDeviceToHost, s->stream));
+    HLAC_CUDA(cudaMemcpyAsync(plen.data(), s->e_path_len.p, E * 4, cudaMemcpyDeviceToHost, s->stream));
+    HLAC_CUDA(cudaMemcpyAsync(arena.data(), s->arena.p, s->arena_used * 4, cudaMemcpyDeviceToHost, s->stream));
+    HLAC_CUDA(cudaStreamSynchronize(s->stream));
+  }
+  for (uint64_t i = 0; i < E; i++) out->off[i + 1] = out->off[i] + plen[i];
+  out->colours = (uint32_t*)calloc(std::max<uint64_t>(out->off[E], 1), 4);
+  for (uint64_t i = 0; i < E; i++) memcpy(out->colours + out->off[i], arena.data() + poff[i], (size_t)plen[i] * 4);
+  return HLAC_OK;
+} catch (const Error& e) { set_last_error(e.what()); return e.code; } catch (const std::exception& e) { set_last_error(e.what()); return HLAC_ERR_STATE; }
+
+int hlac_paths_merge(const hlac_paths* parts, uint32_t n_parts, hlac_paths* out) try {
+  if (!parts || !out) throw Error(HLAC_ERR_ARG, "null argument");
+  struct Ref { uint32_t part; uint64_t idx; uint64_t ord; uint64_t count; };
+  std::map<uint64_t, Ref> uni;   // ordered by hash A: every rank builds the identical union
+  for (uint32_t p = 0; p < n_parts; p++)
+    for (uint64_t i = 0; i < parts[p].n_paths; i++) {
+      const hlac_paths& P = parts[p];
+      auto it = uni.find(P.hash_a[i]);
+      if (it == uni.end()) { uni.emplace(P.hash_a[i], Ref{p, i, P.first_ord[i], P.count[i]}); continue; }
+      const hlac_paths& Q = parts[it->second.part]; const uint64_t j = it->second.idx;
+      const uint64_t la = P.off[i + 1] - P.off[i], lb = Q.off[j + 1] - Q.off[j];
+      if (P.hash_b[i] != Q.hash_b[j] || la != lb || memcmp(P.colours + P.off[i], Q.colours + Q.off[j], la * 4) != 0)
+        throw Error(HLAC_ERR_STATE, "path hash collision detected while merging ranks");
+      it->second.ord = std::min(it->second.ord, P.first_ord[i]);
+      it->second.count += P.count[i];
+    }
+  const uint64_t E = uni.size();
+  memset(out, 0, sizeof *out);
+  out->n_paths = E;
+  out->hash_a = (uint64_t*)calloc(std::max<uint64_t>(E, 1), 8); out->hash_b = (uint64_t*)calloc(std::max<uint64_t>(E, 1), 8);
+  out->first_ord = (uint64_t*)calloc(std::max<uint64_t>(E, 1), 8); out->count = (uint32_t*)calloc(std::max<uint64_t>(E, 1), 4);
+  out->off = (uint64_t*)calloc(E + 1, 8);
+  uint64_t k = 0, tot = 0;
+  for (auto& kv : uni) { const hlac_paths& P = parts[kv.second.part]; tot += P.off[kv.second.idx + 1] - P.off[kv.second.idx]; }
+  out->colours = (uint32_t*)calloc(std::max<uint64_t>(tot, 1), 4);
+  for (auto& kv : uni) {
+    const hlac_paths& P = parts[kv.second.part]; const uint64_t i = kv.second.idx, l = P.off[i + 1] - P.off[i];
+    if (kv.second.count > 0xFFFFFFFFull) throw Error(HLAC_ERR_LIMIT, "more than 2^32 reads on one path");
+    out->hash_a[k] = kv.first; out->hash_b[k] = P.hash_b[i]; out->first_ord[k] = kv.second.ord; out->count[k] = (uint32_t)kv.second.count;
+    memcpy(out->colours + out->off[k], P.colours + P.off[i], l * 4);
+    out->off[k + 1] = out->off[k] + l;
+    k++;
+  }
+  return HLAC_OK;
+} catch (const Error& e) { set_last_error(e.what()); return e.code; } catch (const std::exception& e) { set_last_error(e.what()); return HLAC_ERR_STATE; }
+
+int hlac_geno_import_paths(hlac_geno* s, const hlac_paths* m) try {
+  if (!s || !m) throw Error(HLAC_ERR_ARG, "null argument");
+  DeviceGuard g(s->device);
+  // local id -> merged id
+  const uint64_t E0 = s->n_entries, E = m->n_paths;
+  if (E >= 0xFFFFFFFFull) throw Error(HLAC_ERR_LIMIT, "too many distinct paths");
+  std::vector<uint64_t> local_a(std::max<uint64_t>(E0, 1));
+  if (E0) { HLAC_CUDA(cudaMemcpyAsync(local_a.data(), s->e_hash_a.p, E0 * 8, cudaMemcpyDeviceToHost, s->stream)); HLAC_CUDA(cudaStreamSynchronize(s->stream)); }
+  std::vector<uint32_t> map(std::max<uint64_t>(E0, 1));
+  for (uint64_t i = 0; i < E0; i++) {
+    const uint64_t* it = std::lower_bound(m->hash_a, m->hash_a + E, local_a[i]);   // merged paths are sorted by hash A
+    if (it == m->hash_a + E || *it != local_a[i]) throw Error(HLAC_ERR_ARG, "merged path set does not contain this session's paths");
+    map[i] = (uint32_t)(it - m->hash_a);
+  }
+  DevBuf<uint32_t> d_map; d_map.upload(map.data(), map.size(), s->stream);
+  if (s->n_records_ub) k_remap<<<(unsigned)((s->n_records_ub + 255) / 256), 256, 0, s->stream>>>(s->rec_path.p, s->n_records_ub, d_map.p);
+  if (s->record_reads && s->reads_pushed) k_remap<<<(unsigned)((s->reads_pushed + 255) / 256), 256, 0, s->stream>>>(s->read_path.p, s->reads_pushed, d_map.p);
+  HLAC_CUDA(cudaGetLastError());
+  HLAC_CUDA(cudaStreamSynchronize(s->stream));
+  // adopt the merged entries
+  s->n_entries = 0;   // nothing to keep while growing
+  s->ensure_table(std::max<uint64_t>(E, 1));
+  std::vector<uint32_t> plen(std::max<uint64_t>(E, 1)), rep(std::max<uint64_t>(E, 1), 0);
+  for (uint64_t i = 0; i < E; i++) plen[i] = (uint32_t)(m->off[i + 1] - m->off[i]);
+  s->e_hash_a.upload(m->hash_a, E, s->stream); s->e_hash_b.upload(m->hash_b, E, s->stream);
+  s->e_first_ord.upload((const unsigned long long*)m->first_ord, E, s->stream); s->e_count.upload(m->count, E, s->stream);
+  s->e_path_off.upload(m->off, E, s->stream); s->e_path_len.upload(plen.data(), E, s->stream); s->e_rep.upload(rep.data(), E, s->stream);
+  s->arena.upload(m->colours, std::max<uint64_t>(m->off[E], 1), s->stream);
+  HLAC_CUDA(cudaMemsetAsync(s->t_keys.p, 0, s->t_cap * sizeof(unsigned long long), s->stream));
+  if (E) k_table_build<<<(unsigned)((E + 255) / 256), 256, 0, s->stream>>>(s->table(), s->e_hash_a.p, (uint32_t)E);
+  HLAC_CUDA(cudaGetLastError());
+  unsigned long long c2[2] = {E, m->off[E]};
+  HLAC_CUDA(cudaMemcpyAsync(s->ctr.p, c2, sizeof c2, cudaMemcpyHostToDevice, s->stream));
+  HLAC_CUDA(cudaStreamSynchronize(s->stream));
+  s->n_entries = E; s->arena_used = m->off[E]; s->finished = false; s->launches += 3;
+  return HLAC_OK;
+} catch (const Error& e) { set_last_error(e.what()); return e.code; } catch (const std::exception& e) { set_last_error(e.what()); return HLAC_ERR_STATE; }
+
+int hlac_paths_free(hlac_paths* p) {
+  if (p) { free(p->hash_a); free(p->hash_b); free(p->first_ord); free(p->count); free(p->off); free(p->colours); memset(p, 0, sizeof *p); }
+  return HLAC_OK;
+}
 
 int hlac_geno_read_class_ids(hlac_geno* s, uint32_t* ids, uint64_t n) try {
   if (!s || !ids) throw Error(HLAC_ERR_ARG, "null argument");

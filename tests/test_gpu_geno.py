@@ -119,3 +119,63 @@ def test_empty_geno(sb, orc):
     g = sb.GenoSession(sb.Index.from_idx(p))
     t = g.finish()
     assert t["nreads"] == 0 and t["counts_reads"] == {} and t["counts_umi"] == {} and t["reads_explained"] == [0] * 6
+
+
+def _device_u32(ptr, n):
+    import torch
+
+    class _W:
+        __cuda_array_interface__ = {"shape": (max(n, 1),), "typestr": "<i4", "data": (ptr, False), "version": 2}
+    return torch.as_tensor(_W(), device="cuda")
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_multi_rank_path_merge_equals_single_session(sb, orc, tmp_path, world):
+    """SURVEY.md 8e for genotyping, emulated on one GPU with `world` sessions: reads partitioned by barcode (global
+    ordinals kept), paths exported / merged / imported, per-class UMI histograms summed between finish_begin and
+    finish_end — every rank must end with exactly the single-session (= oracle) tables."""
+    from tools import synth
+    db = str(tmp_path / "db")
+    names = synth.make_db(db, 80, 21)
+    donor = [names[1], names[50], names[85], names[120], names[170], names[230]]
+    r = synth.reads_for_db(40_000, db, donor, 300, 21)
+    fa, st = os.path.join(db, "hla_nuc.fasta"), os.path.join(db, "Allele_status.txt")
+    gix, oix = sb.Index.from_fasta(fa, st), orc.Index.from_fasta(fa, st)
+    o = orc.Geno(oix)
+    o.push(r["seq"], r["len"], r["cell"], r["umi"])
+    o.finish()
+    n = len(r["len"])
+    ordinal = np.arange(n, dtype=np.uint64)
+    sess = []
+    for rank in range(world):
+        m = (r["cell"] % world) == rank
+        g = sb.GenoSession(gix)
+        idx = np.nonzero(m)[0]
+        for part in np.array_split(idx, 2):   # two pushes per rank
+            g.push(r["seq"][part], r["len"][part], r["cell"][part], r["umi"][part], ordinal=ordinal[part])
+        sess.append(g)
+    parts = [g.export_paths() for g in sess]
+    assert sum(int(p["count"].sum()) for p in parts) == o.nreads
+    for g in sess:
+        g.import_merged_paths(parts)
+    hists = []
+    for g in sess:
+        ptr, nc = g.finish_begin()
+        hists.append(_device_u32(ptr, nc))
+    assert len({h.numel() for h in hists}) == 1
+    total = sum(hists[1:], hists[0].clone())    # the all-reduce(sum)
+    for h in hists:
+        h.copy_(total)
+    single = sb.GenoSession(gix)
+    single.push(r["seq"], r["len"], r["cell"], r["umi"])
+    ts = single.finish()
+    for g in sess:
+        t = g.finish_end()
+        assert t["nreads"] == o.nreads
+        assert t["counts_reads"] == o.table("reads")
+        assert t["counts_umi"] == o.table("umi")
+        assert t["reads_explained"] == o.reads_explained().tolist()
+        assert t["reads_classes"] == ts["reads_classes"]   # class order (first-seen eq_class ids) is global too
+        theta, iters = g.squarem()
+        ref = single.squarem()
+        assert iters == ref[1] and np.array_equal(theta, ref[0])   # same tables, same deterministic EM
