@@ -182,7 +182,8 @@ int hlac_geno_finish(hlac_geno*, hlac_class_tables* out);
 int hlac_geno_read_class_ids(hlac_geno*, uint32_t* ids, uint64_t n);
 /* hlac_geno_finish in two halves, for multi-GPU runs: _begin resolves the classes and leaves the per-class UMI
  * histogram (u32[n_classes], classes in first-seen order) on the device so that ranks can all-reduce it; _end reads
- * it back and assembles the tables. */
+ * it back and assembles the tables. _begin returns with the histogram complete; the caller's all-reduce must have
+ * completed (stream-synchronised) before _end is called: the session reads it on its own stream. */
 int hlac_geno_finish_begin(hlac_geno*, uint32_t** umi_hist_device, uint64_t* n_classes);
 int hlac_geno_finish_end(hlac_geno*, hlac_class_tables* out);
 /* the distinct colour paths a session has interned: hash pair, first-seen ordinal, read count, colour ids (CSR).

@@ -166,6 +166,8 @@ def test_multi_rank_path_merge_equals_single_session(sb, orc, tmp_path, world):
     total = sum(hists[1:], hists[0].clone())    # the all-reduce(sum)
     for h in hists:
         h.copy_(total)
+    import torch
+    torch.cuda.synchronize()   # the sessions read the histogram back on their own streams
     single = sb.GenoSession(gix)
     single.push(r["seq"], r["len"], r["cell"], r["umi"])
     ts = single.finish()

@@ -65,6 +65,7 @@ else:
 ptr, nc = g.finish_begin()
 if world > 1:
     dist.all_reduce(torch.as_tensor(_W(ptr, nc), device=dev))
+    torch.cuda.synchronize()   # the session reads the histogram back on its own stream
 tab = g.finish_end(raw=True)
 t_fin = time.time() - t0
 theta, iters = g.squarem(device=local)
@@ -75,6 +76,8 @@ if rank == 0:
     ref, _ = run(np.ones(n, bool))
     rt = ref.finish(raw=True)
     rtheta, riters = ref.squarem(device=local)
+    out["single_gpu"] = dict(tables=rt, em_iters=riters, max_abs_theta_diff=float(np.abs(rtheta - theta).max()),
+                             called=[gix.tx_names[i] for i in ref.call(rtheta)["called"]])
     out["matches_single_gpu"] = bool(rt["nreads"] == tab["nreads"] and rt["n_read_classes"] == tab["n_read_classes"]
                                      and rt["n_umi_classes"] == tab["n_umi_classes"] and riters == iters
                                      and np.array_equal(rtheta, theta) and ref.call(rtheta)["called"] == call["called"])
