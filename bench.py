@@ -161,7 +161,7 @@ def main():
         v = n / per
         line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": config,
+                "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": v, "unit": UNIT, "cores": procs, "kind": "port",
                                  "sample": "first %d reads of the step's %d, partitioned by barcode over %d processes "
                                            "(the reference itself is single-threaded)" % (n, args.reads, procs)},
@@ -256,7 +256,7 @@ def main():
 
     # NOTE sess.timing() accumulates since the last reset(): the last step's kernel times are what it returns.
     ms_dev, wall_dev, tm_dev, clocks, out_dev = timed(step_device, args.steps, max(args.warmup, 3))
-    ms_e2e, wall_e2e, tm_e2e, clocks_e2e, out_e2e = timed(step_e2e, args.steps, 1)
+    ms_e2e, wall_e2e, tm_e2e, clocks_e2e, out_e2e = timed(step_e2e, args.steps, max(args.warmup, 3))
     ent, met = out_dev
     if rank == 0:
         assert all(np.array_equal(a, b) for a, b in zip(ent, out_e2e[0])), "device-resident and host-fed passes disagree"
@@ -292,15 +292,17 @@ def main():
                         "active per instruction) — DESIGN.md §5, profiles/"}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": per_step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "u64", "data": "synthetic", "config": config,
+                "dtype": "u32", "data": "synthetic", "config": config,
                 "e2e": {"value": total_reads / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": in_bytes,
                         "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_ms, "h2d_ms": tm_e2e["h2d_ms"]},
-                "gpu_launches": int(tm_dev["launches"]) * args.steps,
+                # our own kernels in the timed region: k_count_map + k_consensus per step; the radix sort between them is
+                # cub (library): histogram + exclusive-sum + one onesweep pass per 8 key bits
+                "gpu_launches": 2 * args.steps, "library_launches": (2 + (32 + max(1, (n_cells_total - 1).bit_length()) + 7) // 8) * args.steps,
                 "kernels_ms_last_step": kern, "roofline": roof, "clocks": clocks, "clocks_e2e": clocks_e2e,
                 "wall_ms_per_step": wall_dev / args.steps * 1e3,
                 "result": {"matrix_entries": int(len(ent[0])), "molecules": nkeys, "metrics": met}}
         # CPU baseline: the oracle (port) on a bounded sample of the same workload, one core like the reference
-        if world == 1 or True:
+        if world == 1:
             from oracle import oracle as orc
             orc.build()
             ns = min(n, args.cpu_sample)

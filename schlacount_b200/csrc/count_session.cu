@@ -38,8 +38,6 @@ constexpr int UMI_BITS = 32;
 
 struct CountMapArgs {
   DevIndexView cds, gen;
-  const uint32_t* cinfo_cds;   // per colour of the CDS index
-  const uint32_t* cinfo_gen;   // per colour of the genomic index
   const uint64_t* seq;
   const uint16_t* len;
   const uint32_t* cell;
@@ -57,11 +55,11 @@ struct CountMapArgs {
   uint8_t* codes;              // optional per-read debug output
 };
 
+// The session keeps its own copy of each index's node table in which the colour id (word 3 of the node record) is
+// replaced by that colour's cinfo word, so a node visit needs no dependent table lookup.
 struct CountVis {
-  const uint32_t* cinfo;
   uint32_t swap_or = 0, last = CODE_NONE5;
-  __device__ __forceinline__ void visit(uint32_t colour, uint32_t) {
-    const uint32_t ci = __ldg(cinfo + colour);
+  __device__ __forceinline__ void visit(uint32_t ci, uint32_t) {
     swap_or |= ci >> 8;
     last = ci;
   }
@@ -205,7 +203,7 @@ __global__ void __launch_bounds__(MAP_THREADS, MINB) k_count_map(const CountMapA
         const int L = lens[slot];
         const DevIndexView& ix = p < 2 ? a.cds : a.gen;
         SharedWords rd{(p & 1) ? fw + a.nw : fw};
-        CountVis vis{p < 2 ? a.cinfo_cds : a.cinfo_gen};
+        CountVis vis;
         uint32_t cov;
         if (SMEM_BM) cov = walk_from_seed(ix, rd, BitmapShared{smem + (p < 2 ? 0 : a.cds.bitmap_words)}, L, pos, node, off, vis, n_tests, n_probes);
         else cov = walk_from_seed(ix, rd, BitmapGlobal{ix.bitmap}, L, pos, node, off, vis, n_tests, n_probes);
@@ -306,7 +304,7 @@ struct hlac_count {
   RowLayout rows;
   uint32_t n_cells = 0;
   int primary_only = 0;
-  DevBuf<uint32_t> cinfo_cds, cinfo_gen, gene_row0, dense;
+  DevBuf<uint32_t> nodes_cds, nodes_gen, gene_row0, dense;   // node tables with cinfo in place of the colour id
   DevBuf<uint64_t> keys, keys_sorted;
   struct Stage {   // one staging set for host batches; two of them so the H2D of batch i+1 overlaps the kernel of batch i
     DevBuf<uint64_t> seq; DevBuf<uint16_t> len; DevBuf<uint32_t> cell, umi; DevBuf<uint8_t> flags;
@@ -368,7 +366,7 @@ struct hlac_count {
     if (want_codes) codes.reserve(b.n, stream);
     CountMapArgs a{};
     a.cds = cds->view; a.gen = gen->view;
-    a.cinfo_cds = cinfo_cds.p; a.cinfo_gen = cinfo_gen.p;
+    a.cds.nodes = reinterpret_cast<const uint4*>(nodes_cds.p); a.gen.nodes = reinterpret_cast<const uint4*>(nodes_gen.p);
     a.seq = b.seq; a.len = b.len; a.cell = b.cell; a.umi = b.umi; a.flags = b.flags;
     a.n = b.n; a.wpr = b.words_per_read; a.nw = 2 * b.words_per_read + 2; a.row_stride = (2 * a.nw) | 1;
     a.primary_only = primary_only; a.n_cells = n_cells;
@@ -438,8 +436,17 @@ int hlac_count_new(hlac_index* cds, hlac_index* genomic, uint32_t n_cells, int p
   s->rows = build_row_layout(cds->host.tx_names);
   if (s->rows.n_genes > 8) throw Error(HLAC_ERR_LIMIT, "more than 8 genes in the CDS FASTA");
   HLAC_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
-  auto ci = make_cinfo(cds->host, s->rows); s->cinfo_cds.upload(ci.data(), ci.size(), s->stream);
-  auto gi = make_cinfo(genomic->host, s->rows); s->cinfo_gen.upload(gi.data(), gi.size(), s->stream);
+  auto node_table = [&](const HostIndex& h, DevBuf<uint32_t>& dst) {
+    const auto ci = make_cinfo(h, s->rows);
+    std::vector<uint32_t> rec((size_t)h.n_nodes() * 12);
+    for (uint32_t i = 0; i < h.n_nodes(); i++) {
+      uint32_t* r = &rec[(size_t)i * 12];
+      r[0] = h.start[i]; r[1] = h.len[i]; r[2] = h.exts[i]; r[3] = ci[h.colour[i]];
+      for (int b = 0; b < 4; b++) { r[4 + b] = h.radj[(size_t)i * 4 + b]; r[8 + b] = h.ladj[(size_t)i * 4 + b]; }
+    }
+    dst.upload(rec.data(), rec.size(), s->stream);
+  };
+  node_table(cds->host, s->nodes_cds); node_table(genomic->host, s->nodes_gen);
   std::vector<uint32_t> r0 = s->rows.gene_row0; r0.resize(8, 0);
   s->gene_row0.upload(r0.data(), r0.size(), s->stream);
   s->counters.reserve(16, s->stream);
@@ -469,8 +476,14 @@ int hlac_count_reserve(hlac_count* s, uint64_t total_reads) try {
   return HLAC_OK;
 } catch (const Error& e) { set_last_error(e.what()); return e.code; }
 
+static void validate_batch(const hlac_batch* b) {
+  if (b->n && (!b->seq || !b->len || !b->cell || !b->umi || !b->flags)) throw Error(HLAC_ERR_ARG, "batch has a null array");
+  if (b->n >= (1ull << 40)) throw Error(HLAC_ERR_LIMIT, "batch too large");
+}
+
 int hlac_count_push_device(hlac_count* s, const hlac_batch* b) try {
   if (!s || !b) throw Error(HLAC_ERR_ARG, "null argument");
+  validate_batch(b);
   DeviceGuard g(s->device);
   s->launch_map(*b);
   return HLAC_OK;
@@ -478,6 +491,7 @@ int hlac_count_push_device(hlac_count* s, const hlac_batch* b) try {
 
 int hlac_count_push(hlac_count* s, const hlac_batch* b) try {
   if (!s || !b) throw Error(HLAC_ERR_ARG, "null argument");
+  validate_batch(b);
   if (b->n == 0) return HLAC_OK;
   DeviceGuard g(s->device);
   auto& st = s->stage[s->n_push++ & 1];
@@ -559,7 +573,7 @@ int hlac_count_reduce(hlac_count* s, uint32_t** dense_device, uint64_t* n_elems)
     k_consensus<<<(unsigned)((nk + 255) / 256), 256, 0, s->stream>>>(s->keys_sorted.p, nk, s->dense.p, s->rows.nrows, s->gene_row0.p);
     HLAC_CUDA(cudaGetLastError());
     s->end(e2);
-    s->launches += 2;   // cub's own sort passes are library kernels; counted as one launch here plus ours
+    s->launches += 1;   // k_consensus; the cub sort passes are library kernels and not counted
   }
   s->reduced = true;
   if (dense_device) *dense_device = s->dense.p;

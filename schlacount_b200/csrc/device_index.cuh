@@ -103,6 +103,7 @@ __device__ __forceinline__ uint32_t walk_from_seed(const DevIndexView& ix, RD rd
   const int last = L - K;
   int cov = 0;
   uint4 n0 = __ldg(ix.nodes + 3 * (size_t)node);
+  uint4 ra = __ldg(ix.nodes + 3 * (size_t)node + 1);   // right-edge table, fetched with the node so its latency hides behind the compare
   // ---- left extension: only when the first seed sits at or beyond floor(0.2*L) ----
   if (pos >= (L * LEFT_EXTEND_NUM) / LEFT_EXTEND_DEN) {
     int lp = pos - 1;
@@ -167,18 +168,19 @@ __device__ __forceinline__ uint32_t walk_from_seed(const DevIndexView& ix, RD rd
     uint32_t nxt = NONE32;
     if (!brk) {
       const uint32_t b = base_at(rd, pos);
-      const uint4 ra = __ldg(ix.nodes + 3 * (size_t)node + 1);
       nxt = b == 0 ? ra.x : b == 1 ? ra.y : b == 2 ? ra.z : ra.w;
     }
     if (nxt != NONE32) {                 // exact base at the node boundary selects the edge
       node = nxt;
       n0 = __ldg(ix.nodes + 3 * (size_t)node);
+      ra = __ldg(ix.nodes + 3 * (size_t)node + 1);
       pos += 1; cov += 1;
       g = n0.x + K; rem = (int)n0.y - K;
     } else {                             // re-seed scanning forward from the current position
       if (pos > last) break;
       if (!find_seed(ix, rd, bm, pos, last, node, off, n_tests, n_probes)) break;
       n0 = __ldg(ix.nodes + 3 * (size_t)node);
+      ra = __ldg(ix.nodes + 3 * (size_t)node + 1);
       pos += K; cov += K;
       g = n0.x + off + K; rem = (int)n0.y - (int)off - K;
     }

@@ -442,6 +442,7 @@ struct hlac_geno {
 
   void push_device(const hlac_batch& b, int forward_only) {
     if (b.n == 0) return;
+    if (!b.seq || !b.len || !b.cell || !b.umi) throw Error(HLAC_ERR_ARG, "batch has a null array");
     if (b.words_per_read == 0 || b.words_per_read > 16) throw Error(HLAC_ERR_ARG, "words_per_read must be 1..16");
     if (b.n >= (1ull << 32)) throw Error(HLAC_ERR_LIMIT, "batch too large");
     finished = false;
