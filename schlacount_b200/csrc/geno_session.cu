@@ -24,6 +24,8 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
+#include <cstdio>
+#include <ctime>
 #include <map>
 #include <memory>
 #include <unordered_map>
@@ -310,17 +312,18 @@ __global__ void k_remap(uint32_t* ids, uint64_t n, const uint32_t* __restrict__ 
 
 // per path: length of its class vector = |colours[last colour of the path]|
 __global__ void k_class_len(const uint32_t* __restrict__ arena, const uint64_t* __restrict__ path_off, const uint32_t* __restrict__ path_len,
-                            const uint64_t* __restrict__ col_off, uint32_t n, uint32_t* out) {
+                            const uint64_t* __restrict__ col_off, uint32_t n, uint32_t* out, uint32_t* last_colour) {
   const uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
   if (id >= n) return;
   const uint32_t c = arena[path_off[id] + path_len[id] - 1];
   out[id] = (uint32_t)(col_off[c + 1] - col_off[c]);
+  last_colour[id] = c;
 }
 
 // Exact emulation of `v1 = colours[last]; for n in others (visit order): merge_no_truncate(v1, colours[n])`.
 __global__ void k_resolve_paths(const uint32_t* __restrict__ arena, const uint64_t* __restrict__ path_off, const uint32_t* __restrict__ path_len,
                                 const uint64_t* __restrict__ col_off, const uint32_t* __restrict__ col_tx, uint32_t n,
-                                const uint64_t* __restrict__ vec_off, uint32_t* vec, uint64_t* vec_hash) {
+                                const uint64_t* __restrict__ vec_off, uint32_t* vec, uint64_t* vec_hash, uint64_t* vec_hash2) {
   const uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
   if (id >= n) return;
   const uint32_t* path = arena + path_off[id];
@@ -341,9 +344,43 @@ __global__ void k_resolve_paths(const uint32_t* __restrict__ arena, const uint64
       else { v1[i] = v1[f]; v1[f] = x; i++; j++; f++; }
     }
   }
-  uint64_t h = 0xcbf29ce484222325ULL;
-  for (uint32_t k = 0; k < n1; k++) { h = (h ^ v1[k]) * 0x100000001b3ULL; h ^= h >> 32; }
+  uint64_t h = 0xcbf29ce484222325ULL, h2 = 0x9e3779b97f4a7c15ULL;
+  for (uint32_t k = 0; k < n1; k++) { h = (h ^ v1[k]) * 0x100000001b3ULL; h ^= h >> 32; h2 = mix64(h2 + v1[k] + 0x632be59bd9b4e019ULL); }
   vec_hash[id] = mix64(h ^ n1);
+  vec_hash2[id] = h2;
+}
+
+// every path's vector must equal its class representative's vector element by element (interning is by hash)
+__global__ void k_verify_classes(const uint32_t* __restrict__ vec, const uint64_t* __restrict__ vec_off, const uint32_t* __restrict__ rep_of_path,
+                                 uint32_t n, unsigned long long* mismatches) {
+  const uint32_t p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned lane = threadIdx.x & 31;
+  if (p >= n) return;
+  const uint32_t r = rep_of_path[p];
+  if (r == p) return;
+  const uint64_t a = vec_off[p], b = vec_off[r], len = vec_off[p + 1] - a;
+  bool bad = (vec_off[r + 1] - b) != len;
+  for (uint64_t k = lane; k < len && !bad; k += 32) bad = vec[a + k] != vec[b + k];
+  if (__any_sync(0xFFFFFFFFu, bad) && lane == 0) atomicAdd(mismatches, 1ULL);
+}
+
+// counts_reads in class order: one block per class copies its representative's vector to its final place
+__global__ void k_gather_classes(const uint32_t* __restrict__ vec, const uint64_t* __restrict__ src_off, const uint64_t* __restrict__ dst_off,
+                                 uint32_t* out) {
+  const uint32_t c = blockIdx.x;
+  const uint64_t a = src_off[c], b = dst_off[c], len = dst_off[c + 1] - b;
+  for (uint64_t k = threadIdx.x; k < len; k += blockDim.x) out[b + k] = vec[a + k];
+}
+
+// reads_explained[t] += reads of every class whose (sorted) member list is colour list `col` (mapping.rs:196-198)
+__global__ void k_reads_explained(const uint32_t* __restrict__ cols, const unsigned long long* __restrict__ totals, uint32_t n,
+                                  const uint64_t* __restrict__ col_off, const uint32_t* __restrict__ col_tx, unsigned long long* expl) {
+  const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned lane = threadIdx.x & 31;
+  if (i >= n) return;
+  const uint32_t c = cols[i];
+  const unsigned long long t = totals[i];
+  for (uint64_t q = col_off[c] + lane; q < col_off[c + 1]; q += 32) atomicAdd(expl + col_tx[q], t);
 }
 
 __global__ void k_map_rank(const uint32_t* __restrict__ rec_path, const uint32_t* __restrict__ rank_of_path, uint64_t n, uint32_t* out) {
@@ -388,7 +425,8 @@ struct hlac_geno {
   std::vector<uint32_t> class_of_path;
   bool finished = false;
   // between hlac_geno_finish_begin and _end
-  std::vector<std::vector<uint32_t>> fin_cls_vec; std::vector<uint32_t> fin_cls_reads; DevBuf<uint32_t> fin_hist; bool fin_begun = false;
+  std::vector<uint64_t> fin_src_off; std::vector<uint32_t> fin_cls_len, fin_cls_reads, fin_cls_colour;   // per class, first-seen order
+  DevBuf<uint32_t> fin_hist, fin_dvec; bool fin_begun = false;
   float ms[4] = {0, 0, 0, 0};
   uint64_t launches = 0;
   struct Ev { cudaEvent_t a, b; int kind; };
@@ -565,70 +603,94 @@ int hlac_geno_last_cov(hlac_geno* s, uint32_t* cov, uint64_t n) try {
   return HLAC_OK;
 } catch (const Error& e) { set_last_error(e.what()); return e.code; }
 
+static double now_s() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + ts.tv_nsec * 1e-9; }
+#define HLAC_TICK(label) do { if (dbg) { double t_ = now_s(); fprintf(stderr, "[hlac timing] %-28s %.3f s\n", label, t_ - t_last); t_last = t_; } } while (0)
+
 int hlac_geno_finish_begin(hlac_geno* s, uint32_t** umi_hist_device, uint64_t* n_classes) try {
   if (!s) throw Error(HLAC_ERR_ARG, "null argument");
   DeviceGuard g(s->device);
+  const bool dbg = getenv("HLAC_DEBUG_TIMING") != nullptr; double t_last = now_s();
   const HostIndex& hx = s->idx->host;
   const uint32_t nitems = (uint32_t)hx.tx_names.size();
   const uint32_t E = (uint32_t)s->n_entries;
   const uint64_t R = s->n_records_ub;
   (void)nitems;
-  auto& cls_vec = s->fin_cls_vec;      // class id (first-seen order) -> raw vector
   auto& cls_reads = s->fin_cls_reads;  // counts_reads
-  cls_vec.clear(); cls_reads.clear();
+  cls_reads.clear(); s->fin_cls_colour.clear(); s->fin_src_off.clear(); s->fin_cls_len.clear();
   s->class_of_path.assign(E, NONE32);
+  size_t n_classes_out = 0;
   if (E) {
-    // ---- K3a: resolve every distinct path to its class vector ----
-    DevBuf<uint32_t> clen; clen.reserve(E, s->stream);
+    // ---- K3a: resolve every distinct path to its class vector (kept on the device) ----
+    DevBuf<uint32_t> clen, clast; clen.reserve(E, s->stream); clast.reserve(E, s->stream);
     size_t ev = s->begin(2);
-    k_class_len<<<(E + 255) / 256, 256, 0, s->stream>>>(s->arena.p, s->e_path_off.p, s->e_path_len.p, s->idx->col_off.p, E, clen.p);
+    k_class_len<<<(E + 255) / 256, 256, 0, s->stream>>>(s->arena.p, s->e_path_off.p, s->e_path_len.p, s->idx->col_off.p, E, clen.p, clast.p);
     HLAC_CUDA(cudaGetLastError());
-    std::vector<uint32_t> hlen(E);
+    std::vector<uint32_t> hlen(E), hlast(E);
     HLAC_CUDA(cudaMemcpyAsync(hlen.data(), clen.p, (size_t)E * 4, cudaMemcpyDeviceToHost, s->stream));
+    HLAC_CUDA(cudaMemcpyAsync(hlast.data(), clast.p, (size_t)E * 4, cudaMemcpyDeviceToHost, s->stream));
     HLAC_CUDA(cudaStreamSynchronize(s->stream));
     std::vector<uint64_t> voff(E + 1, 0);
     for (uint32_t i = 0; i < E; i++) voff[i + 1] = voff[i] + hlen[i];
-    DevBuf<uint64_t> d_voff, d_vhash; DevBuf<uint32_t> d_vec;
-    d_voff.upload(voff.data(), E + 1, s->stream); d_vhash.reserve(E, s->stream); d_vec.reserve(std::max<uint64_t>(voff[E], 1), s->stream);
+    DevBuf<uint64_t> d_voff, d_vhash, d_vhash2;
+    d_voff.upload(voff.data(), E + 1, s->stream); d_vhash.reserve(E, s->stream); d_vhash2.reserve(E, s->stream);
+    s->fin_dvec.reserve(std::max<uint64_t>(voff[E], 1), s->stream);
     k_resolve_paths<<<(E + 127) / 128, 128, 0, s->stream>>>(s->arena.p, s->e_path_off.p, s->e_path_len.p, s->idx->col_off.p, s->idx->col_tx.p, E,
-                                                           d_voff.p, d_vec.p, d_vhash.p);
+                                                           d_voff.p, s->fin_dvec.p, d_vhash.p, d_vhash2.p);
     HLAC_CUDA(cudaGetLastError());
     s->end(ev);
     s->launches += 2;
-    std::vector<uint64_t> vhash(E), ford(E); std::vector<uint32_t> vec(std::max<uint64_t>(voff[E], 1)), cnt(E);
+    std::vector<uint64_t> vhash(E), vhash2(E), ford(E); std::vector<uint32_t> cnt(E);
     HLAC_CUDA(cudaMemcpyAsync(vhash.data(), d_vhash.p, (size_t)E * 8, cudaMemcpyDeviceToHost, s->stream));
-    HLAC_CUDA(cudaMemcpyAsync(vec.data(), d_vec.p, voff[E] * 4, cudaMemcpyDeviceToHost, s->stream));
+    HLAC_CUDA(cudaMemcpyAsync(vhash2.data(), d_vhash2.p, (size_t)E * 8, cudaMemcpyDeviceToHost, s->stream));
     HLAC_CUDA(cudaMemcpyAsync(ford.data(), s->e_first_ord.p, (size_t)E * 8, cudaMemcpyDeviceToHost, s->stream));
     HLAC_CUDA(cudaMemcpyAsync(cnt.data(), s->e_count.p, (size_t)E * 4, cudaMemcpyDeviceToHost, s->stream));
     HLAC_CUDA(cudaStreamSynchronize(s->stream));
-    // ---- host: intern equal vectors (exact compare), order classes by first-seen ordinal ----
+    HLAC_TICK("resolve paths");
+    // ---- host: intern equal vectors by (hash pair, length, last colour); exact equality is verified on the device ----
     struct Cls { uint32_t rep; uint64_t ord; uint32_t reads; };
-    std::vector<Cls> classes; std::vector<uint32_t> tmp_cls(E);
+    std::vector<Cls> classes; std::vector<uint32_t> tmp_cls(E), rep_of_path(E);
     std::unordered_map<uint64_t, std::vector<uint32_t>> by_hash;
     for (uint32_t p = 0; p < E; p++) {
       auto& cand = by_hash[vhash[p]];
       uint32_t found = NONE32;
       for (uint32_t c : cand) {
         const uint32_t r = classes[c].rep;
-        if (hlen[r] == hlen[p] && std::equal(vec.begin() + voff[p], vec.begin() + voff[p + 1], vec.begin() + voff[r])) { found = c; break; }
+        if (vhash2[r] == vhash2[p] && hlen[r] == hlen[p] && hlast[r] == hlast[p]) { found = c; break; }
       }
       if (found == NONE32) { found = (uint32_t)classes.size(); classes.push_back({p, ford[p], 0}); cand.push_back(found); }
       classes[found].ord = std::min(classes[found].ord, ford[p]);
       classes[found].reads += cnt[p];
       tmp_cls[p] = found;
+      rep_of_path[p] = classes[found].rep;
+    }
+    {
+      DevBuf<uint32_t> d_rep; DevBuf<unsigned long long> d_bad;
+      d_rep.upload(rep_of_path.data(), E, s->stream); d_bad.reserve(1, s->stream);
+      HLAC_CUDA(cudaMemsetAsync(d_bad.p, 0, 8, s->stream));
+      k_verify_classes<<<(unsigned)(((uint64_t)E * 32 + 255) / 256), 256, 0, s->stream>>>(s->fin_dvec.p, d_voff.p, d_rep.p, E, d_bad.p);
+      HLAC_CUDA(cudaGetLastError());
+      unsigned long long bad = 0;
+      HLAC_CUDA(cudaMemcpyAsync(&bad, d_bad.p, 8, cudaMemcpyDeviceToHost, s->stream));
+      HLAC_CUDA(cudaStreamSynchronize(s->stream));
+      s->launches++;
+      if (bad) throw Error(HLAC_ERR_STATE, "class vector hash collision detected");
     }
     std::vector<uint32_t> order(classes.size());
     for (uint32_t i = 0; i < order.size(); i++) order[i] = i;
     std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return classes[a].ord < classes[b].ord; });
     std::vector<uint32_t> rank(classes.size());
     for (uint32_t r = 0; r < order.size(); r++) rank[order[r]] = r;
-    cls_vec.resize(classes.size()); cls_reads.resize(classes.size());
+    cls_reads.resize(classes.size()); s->fin_cls_colour.resize(classes.size()); s->fin_src_off.resize(classes.size()); s->fin_cls_len.resize(classes.size());
     for (uint32_t c = 0; c < classes.size(); c++) {
       const uint32_t r = classes[c].rep;
-      cls_vec[rank[c]].assign(vec.begin() + voff[r], vec.begin() + voff[r + 1]);
+      s->fin_cls_colour[rank[c]] = hlast[r];
+      s->fin_src_off[rank[c]] = voff[r];
+      s->fin_cls_len[rank[c]] = hlen[r];
       cls_reads[rank[c]] = classes[c].reads;
     }
     for (uint32_t p = 0; p < E; p++) s->class_of_path[p] = rank[tmp_cls[p]];
+    n_classes_out = classes.size();
+    HLAC_TICK("intern + verify + order classes");
     // ---- K3b: group records by (barcode, umi), lowest class id per UMI ----
     s->fin_hist.reserve(std::max<size_t>(classes.size(), 1), s->stream);
     HLAC_CUDA(cudaMemsetAsync(s->fin_hist.p, 0, std::max<size_t>(classes.size(), 1) * 4, s->stream));
@@ -651,10 +713,11 @@ int hlac_geno_finish_begin(hlac_geno* s, uint32_t** umi_hist_device, uint64_t* n
       HLAC_CUDA(cudaStreamSynchronize(s->stream));
     }
   }
+  HLAC_TICK("sort records + umi min");
   if (!E) { s->fin_hist.reserve(1, s->stream); HLAC_CUDA(cudaMemsetAsync(s->fin_hist.p, 0, 4, s->stream)); HLAC_CUDA(cudaStreamSynchronize(s->stream)); }
   s->fin_begun = true;
   if (umi_hist_device) *umi_hist_device = s->fin_hist.p;
-  if (n_classes) *n_classes = cls_vec.size();
+  if (n_classes) *n_classes = n_classes_out;
   return HLAC_OK;
 } catch (const Error& e) { set_last_error(e.what()); return e.code; } catch (const std::exception& e) { set_last_error(e.what()); return HLAC_ERR_STATE; }
 
@@ -663,9 +726,12 @@ int hlac_geno_finish_end(hlac_geno* s, hlac_class_tables* out) try {
   if (!s || !out) throw Error(HLAC_ERR_ARG, "null argument");
   if (!s->fin_begun) throw Error(HLAC_ERR_STATE, "hlac_geno_finish_begin has not run");
   DeviceGuard g(s->device);
-  auto& cls_vec = s->fin_cls_vec; auto& cls_reads = s->fin_cls_reads;
-  const uint32_t nitems = (uint32_t)s->idx->host.tx_names.size();
-  std::vector<uint32_t> umi_hist(std::max<size_t>(cls_vec.size(), 1), 0);
+  const bool dbg = getenv("HLAC_DEBUG_TIMING") != nullptr; double t_last = now_s();
+  auto& cls_reads = s->fin_cls_reads;
+  const size_t nc = cls_reads.size();
+  const HostIndex& hx = s->idx->host;
+  const uint32_t nitems = (uint32_t)hx.tx_names.size();
+  std::vector<uint32_t> umi_hist(std::max<size_t>(nc, 1), 0);
   HLAC_CUDA(cudaMemcpyAsync(umi_hist.data(), s->fin_hist.p, umi_hist.size() * 4, cudaMemcpyDeviceToHost, s->stream));
   HLAC_CUDA(cudaStreamSynchronize(s->stream));
   memset(out, 0, sizeof *out);
@@ -673,27 +739,57 @@ int hlac_geno_finish_end(hlac_geno* s, hlac_class_tables* out) try {
   uint64_t total_reads = 0; for (uint32_t c : cls_reads) total_reads += c;
   out->nreads = (uint32_t)total_reads;   // total_reads (mapping.rs:195): every counted read, over all ranks after a path merge
   out->reads_explained = (uint64_t*)calloc(std::max<uint32_t>(nitems, 1), 8);
-  // ---- assemble EqClassCounts (mapping.rs:199-209) ----
-  const size_t nc = cls_vec.size();
-  uint64_t ntx = 0; for (auto& v : cls_vec) ntx += v.size();
+  // ---- counts_reads (mapping.rs:199-201): class vectors gathered into first-seen order on the device, one D2H ----
   out->n_read_classes = nc;
-  out->reads_off = (uint64_t*)calloc(nc + 1, 8); out->reads_tx = (uint32_t*)calloc(std::max<uint64_t>(ntx, 1), 4); out->reads_cnt = (uint32_t*)calloc(std::max<size_t>(nc, 1), 4);
+  out->reads_off = (uint64_t*)calloc(nc + 1, 8); out->reads_cnt = (uint32_t*)calloc(std::max<size_t>(nc, 1), 4);
+  for (size_t c = 0; c < nc; c++) { out->reads_off[c + 1] = out->reads_off[c] + s->fin_cls_len[c]; out->reads_cnt[c] = cls_reads[c]; }
+  const uint64_t ntx = out->reads_off[nc];
+  // large tables go to pinned host memory: a pageable 4 GB D2H was measured at < 1 GB/s (page faults under the DMA staging)
+  if (ntx * 4 >= (64ull << 20)) HLAC_CUDA(cudaHostAlloc((void**)&out->reads_tx, ntx * 4, cudaHostAllocDefault));
+  else out->reads_tx = (uint32_t*)malloc(std::max<uint64_t>(ntx, 1) * 4);
+  if (nc) {
+    DevBuf<uint64_t> d_src, d_dst; DevBuf<uint32_t> d_out;
+    d_src.upload(s->fin_src_off.data(), nc, s->stream); d_dst.upload(out->reads_off, nc + 1, s->stream); d_out.reserve(std::max<uint64_t>(ntx, 1), s->stream);
+    k_gather_classes<<<(unsigned)nc, 256, 0, s->stream>>>(s->fin_dvec.p, d_src.p, d_dst.p, d_out.p);
+    HLAC_CUDA(cudaGetLastError());
+    HLAC_CUDA(cudaMemcpyAsync(out->reads_tx, d_out.p, ntx * 4, cudaMemcpyDeviceToHost, s->stream));
+    // reads_explained (mapping.rs:196-198): per colour totals, then one pass over the used colour lists on the device
+    std::map<uint32_t, unsigned long long> per_colour;
+    for (size_t c = 0; c < nc; c++) per_colour[s->fin_cls_colour[c]] += cls_reads[c];
+    std::vector<uint32_t> cols; std::vector<unsigned long long> tots;
+    for (auto& kv : per_colour) { cols.push_back(kv.first); tots.push_back(kv.second); }
+    DevBuf<uint32_t> d_cols; DevBuf<unsigned long long> d_tots, d_expl;
+    d_cols.upload(cols.data(), cols.size(), s->stream); d_tots.upload(tots.data(), tots.size(), s->stream); d_expl.reserve(std::max<uint32_t>(nitems, 1), s->stream);
+    HLAC_CUDA(cudaMemsetAsync(d_expl.p, 0, (size_t)std::max<uint32_t>(nitems, 1) * 8, s->stream));
+    k_reads_explained<<<(unsigned)((cols.size() * 32 + 255) / 256), 256, 0, s->stream>>>(d_cols.p, d_tots.p, (uint32_t)cols.size(), s->idx->col_off.p, s->idx->col_tx.p, d_expl.p);
+    HLAC_CUDA(cudaGetLastError());
+    HLAC_CUDA(cudaMemcpyAsync(out->reads_explained, d_expl.p, (size_t)nitems * 8, cudaMemcpyDeviceToHost, s->stream));
+    HLAC_CUDA(cudaStreamSynchronize(s->stream));
+    s->launches += 2;
+  }
   uint64_t q = 0;
-  for (size_t c = 0; c < nc; c++) {
-    for (uint32_t t : cls_vec[c]) { out->reads_tx[q++] = t; out->reads_explained[t] += cls_reads[c]; }
-    out->reads_off[c + 1] = q; out->reads_cnt[c] = cls_reads[c];
-  }
-  std::map<std::vector<uint32_t>, uint32_t> umi;   // key: sort + dedup of the UMI's class (mapping.rs:205-207)
-  for (size_t c = 0; c < nc; c++) if (umi_hist[c]) {
-    std::vector<uint32_t> k = cls_vec[c];
-    std::sort(k.begin(), k.end()); k.erase(std::unique(k.begin(), k.end()), k.end());
-    umi[k] += umi_hist[c];
-  }
-  uint64_t utx = 0; for (auto& kv : umi) utx += kv.first.size();
-  out->n_umi_classes = umi.size();
-  out->umi_off = (uint64_t*)calloc(umi.size() + 1, 8); out->umi_tx = (uint32_t*)calloc(std::max<uint64_t>(utx, 1), 4); out->umi_cnt = (uint32_t*)calloc(std::max<size_t>(umi.size(), 1), 4);
+  HLAC_TICK("assemble counts_reads");
+  // counts_umi key = sort + dedup of the UMI's class (mapping.rs:205-207). A class vector is a permutation of the
+  // colour list of its path's last node, and colour lists are sorted, duplicate-free and pairwise distinct, so the key
+  // IS that colour list: accumulate per colour id, then emit in lexicographic order of the lists.
+  std::map<uint32_t, uint64_t> by_colour;
+  for (size_t c = 0; c < nc; c++) if (umi_hist[c]) by_colour[s->fin_cls_colour[c]] += umi_hist[c];
+  std::vector<uint32_t> used; used.reserve(by_colour.size());
+  for (auto& kv : by_colour) used.push_back(kv.first);
+  std::sort(used.begin(), used.end(), [&](uint32_t a, uint32_t b) {
+    return std::lexicographical_compare(hx.col_tx.begin() + hx.col_off[a], hx.col_tx.begin() + hx.col_off[a + 1],
+                                        hx.col_tx.begin() + hx.col_off[b], hx.col_tx.begin() + hx.col_off[b + 1]);
+  });
+  uint64_t utx = 0; for (uint32_t c : used) utx += hx.col_off[c + 1] - hx.col_off[c];
+  out->n_umi_classes = used.size();
+  out->umi_off = (uint64_t*)calloc(used.size() + 1, 8); out->umi_tx = (uint32_t*)calloc(std::max<uint64_t>(utx, 1), 4); out->umi_cnt = (uint32_t*)calloc(std::max<size_t>(used.size(), 1), 4);
   q = 0; size_t c = 0;
-  for (auto& kv : umi) { for (uint32_t t : kv.first) out->umi_tx[q++] = t; out->umi_cnt[c] = kv.second; out->umi_off[++c] = q; }
+  for (uint32_t col : used) {
+    const size_t len = hx.col_off[col + 1] - hx.col_off[col];
+    memcpy(out->umi_tx + q, hx.col_tx.data() + hx.col_off[col], len * 4);
+    q += len; out->umi_cnt[c] = (uint32_t)by_colour[col]; out->umi_off[++c] = q;
+  }
+  HLAC_TICK("assemble counts_umi");
   s->finished = true; s->fin_begun = false;
   return HLAC_OK;
 } catch (const Error& e) { set_last_error(e.what()); return e.code; } catch (const std::exception& e) { set_last_error(e.what()); return HLAC_ERR_STATE; }
@@ -828,6 +924,9 @@ int hlac_geno_read_class_ids(hlac_geno* s, uint32_t* ids, uint64_t n) try {
 
 int hlac_class_tables_free(hlac_class_tables* t) {
   if (t) {
+    cudaPointerAttributes at{};
+    if (t->reads_tx && cudaPointerGetAttributes(&at, t->reads_tx) == cudaSuccess && at.type == cudaMemoryTypeHost) { cudaFreeHost(t->reads_tx); t->reads_tx = nullptr; }
+    else cudaGetLastError();
     free(t->reads_off); free(t->reads_tx); free(t->reads_cnt); free(t->umi_off); free(t->umi_tx); free(t->umi_cnt); free(t->reads_explained);
     memset(t, 0, sizeof *t);
   }
