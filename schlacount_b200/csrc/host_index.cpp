@@ -5,6 +5,9 @@
 #include <cstring>
 #include <fstream>
 #include <unordered_map>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 
 namespace hlac {
 
@@ -90,6 +93,8 @@ void HostIndex::load_idx(const std::string& path, HostIndex& ix) {
 // maximal path whose interior links have a unique right extension, a unique left extension on the successor, and
 // one colour. Sort-based: one record per k-mer occurrence, sorted by (k-mer, tx), then grouped.
 void HostIndex::build(const std::vector<Bases>& seqs, const std::vector<std::string>& names, HostIndex& ix) {
+  const bool dbg = getenv("HLAC_DEBUG_TIMING") != nullptr; auto t_last = std::chrono::steady_clock::now();
+  auto tick = [&](const char* what) { if (dbg) { auto t = std::chrono::steady_clock::now(); fprintf(stderr, "[hlac timing] build: %-24s %.3f s\n", what, std::chrono::duration<double>(t - t_last).count()); t_last = t; } };
   ix = HostIndex();
   ix.tx_names = names;
   struct Occ { uint64_t kmer; uint32_t tx; uint8_t l, r; };
@@ -107,7 +112,23 @@ void HostIndex::build(const std::vector<Bases>& seqs, const std::vector<std::str
       occ.push_back({v, t, uint8_t(i > 0 ? 1u << s[i - 1] : 0), uint8_t(i + K < s.size() ? 1u << s[i + K] : 0)});
     }
   }
-  std::sort(occ.begin(), occ.end(), [](const Occ& a, const Occ& b) { return a.kmer != b.kmer ? a.kmer < b.kmer : a.tx < b.tx; });
+  tick("enumerate k-mers");
+  {
+    // stable LSD radix sort on the 48-bit k-mer, 3 passes of 16 bits; occurrences were generated in ascending tx
+    // order, so stability leaves every k-mer's tx list sorted (5 s of std::sort -> ~0.6 s at 33 M occurrences)
+    std::vector<Occ> tmp(occ.size());
+    std::vector<size_t> cnt(1 << 16);
+    for (int pass = 0; pass < 3; pass++) {
+      const int sh = 16 * pass;
+      std::fill(cnt.begin(), cnt.end(), 0);
+      for (const Occ& o : occ) cnt[(o.kmer >> sh) & 0xFFFF]++;
+      size_t run = 0;
+      for (size_t& c : cnt) { const size_t k = c; c = run; run += k; }
+      for (const Occ& o : occ) tmp[cnt[(o.kmer >> sh) & 0xFFFF]++] = o;
+      occ.swap(tmp);
+    }
+  }
+  tick("sort occurrences");
 
   // unique k-mers with ext masks and interned colour
   std::vector<uint64_t> uk; std::vector<uint8_t> ul, ur; std::vector<uint32_t> ucol;
@@ -138,6 +159,7 @@ void HostIndex::build(const std::vector<Bases>& seqs, const std::vector<std::str
     i = j;
   }
   std::vector<Occ>().swap(occ);
+  tick("group + intern colours");
 
   const size_t n = uk.size();
   auto find = [&](uint64_t kmer) -> int64_t {
@@ -171,7 +193,9 @@ void HostIndex::build(const std::vector<Bases>& seqs, const std::vector<std::str
   };
   for (size_t a = 0; a < n; a++) if (!linked_into[a]) emit(a);
   for (size_t a = 0; a < n; a++) if (!done[a]) emit(a);   // closed cycles of interior links
+  tick("compact nodes");
   ix.finalize();
+  tick("finalize (adj/dict/bitmap)");
 }
 
 void HostIndex::finalize() {
