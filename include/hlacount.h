@@ -77,7 +77,8 @@ typedef struct { /* Vec<MatrixEntry> (mapping.rs:101-106), cells ascending then 
   uint32_t* col;
   uint32_t* val;
   uint64_t n;
-  uint32_t nrows; /* matrix rows (mapping.rs:681-727) */
+  uint32_t nrows;    /* matrix rows (mapping.rs:681-727) */
+  uint32_t borrowed; /* 1: the arrays belong to the session (pinned), valid until its next _entries/_reset/_free */
 } hlac_coo;
 
 typedef struct {

@@ -41,7 +41,7 @@ class Metrics(C.Structure):
 
 class Coo(C.Structure):
     _fields_ = [("row", C.POINTER(C.c_uint32)), ("col", C.POINTER(C.c_uint32)), ("val", C.POINTER(C.c_uint32)),
-                ("n", C.c_uint64), ("nrows", C.c_uint32)]
+                ("n", C.c_uint64), ("nrows", C.c_uint32), ("borrowed", C.c_uint32)]
 
 
 class IndexInfo(C.Structure):

@@ -199,14 +199,17 @@ class CountSession:
         lib().hlac_coo_free(C.byref(coo))
         return ent, [getattr(m, k) for k, _ in _lib.Metrics._fields_]
 
-    def entries_arrays(self):
-        """Like entries() but as three numpy arrays (row, col, val) — no Python-object conversion."""
+    def entries_arrays(self, copy=True):
+        """Like entries() but as three numpy arrays (row, col, val) — no Python-object conversion. copy=False returns
+        views of the session's pinned result buffer (valid until the next entries/reset on this session)."""
         coo = _lib.Coo()
         m = _lib.Metrics()
         check(lib().hlac_count_entries(self.h, C.byref(coo), C.byref(m)))
         n = int(coo.n)
         if n:
-            out = tuple(np.ctypeslib.as_array(p, shape=(n,)).copy() for p in (coo.row, coo.col, coo.val))
+            out = tuple(np.ctypeslib.as_array(p, shape=(n,)) for p in (coo.row, coo.col, coo.val))
+            if copy:
+                out = tuple(a.copy() for a in out)
         else:
             out = tuple(np.zeros(0, np.uint32) for _ in range(3))
         lib().hlac_coo_free(C.byref(coo))

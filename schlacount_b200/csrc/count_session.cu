@@ -270,6 +270,64 @@ __global__ void k_consensus(const uint64_t* __restrict__ keys, uint64_t n, uint3
   atomicAdd(dense + (size_t)cell * nrows + gene_row0[cand] + slot, 1u);
 }
 
+// ---- dense matrix -> COO on the device (cells ascending, rows ascending = linear order of the dense array) ----
+constexpr int COO_THREADS = 256, COO_PER_THREAD = 8, COO_TILE = COO_THREADS * COO_PER_THREAD;
+__global__ void k_coo_count(const uint32_t* __restrict__ dense, uint64_t n, uint32_t* block_nnz) {
+  __shared__ uint32_t warp_cnt[COO_THREADS / 32];
+  const uint64_t base = (uint64_t)blockIdx.x * COO_TILE + (uint64_t)threadIdx.x * COO_PER_THREAD;
+  uint32_t c = 0;
+#pragma unroll
+  for (int k = 0; k < COO_PER_THREAD; k++) if (base + k < n && dense[base + k]) c++;
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xFFFFFFFFu, c, o);
+  if ((threadIdx.x & 31) == 0) warp_cnt[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) { uint32_t t = 0; for (int w = 0; w < COO_THREADS / 32; w++) t += warp_cnt[w]; block_nnz[blockIdx.x] = t; }
+}
+// single block: exclusive scan of the per-block counts; total to block_off[nblocks]
+__global__ void k_coo_scan(const uint32_t* __restrict__ block_nnz, uint32_t nblocks, uint64_t* block_off) {
+  __shared__ uint64_t carry;
+  __shared__ uint64_t part[1024];
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (uint32_t b0 = 0; b0 < nblocks; b0 += 1024) {
+    const uint32_t i = b0 + threadIdx.x;
+    const uint64_t v = i < nblocks ? block_nnz[i] : 0;
+    part[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {   // Hillis-Steele inclusive scan
+      const uint64_t add = threadIdx.x >= (unsigned)o ? part[threadIdx.x - o] : 0;
+      __syncthreads();
+      part[threadIdx.x] += add;
+      __syncthreads();
+    }
+    if (i < nblocks) block_off[i] = carry + part[threadIdx.x] - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry += part[1023];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) block_off[nblocks] = carry;
+}
+__global__ void k_coo_write(const uint32_t* __restrict__ dense, uint64_t n, uint32_t nrows, const uint64_t* __restrict__ block_off,
+                            uint32_t* row, uint32_t* col, uint32_t* val) {
+  __shared__ uint32_t warp_off[COO_THREADS / 32];
+  const uint64_t base = (uint64_t)blockIdx.x * COO_TILE + (uint64_t)threadIdx.x * COO_PER_THREAD;
+  uint32_t v[COO_PER_THREAD]; uint32_t c = 0;
+#pragma unroll
+  for (int k = 0; k < COO_PER_THREAD; k++) { v[k] = base + k < n ? dense[base + k] : 0; c += v[k] != 0; }
+  uint32_t incl = c;   // inclusive scan of the per-thread counts inside the warp
+  for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if ((threadIdx.x & 31) >= (unsigned)o) incl += t; }
+  if ((threadIdx.x & 31) == 31) warp_off[threadIdx.x >> 5] = incl;
+  __syncthreads();
+  uint32_t woff = 0;
+  for (unsigned w = 0; w < (threadIdx.x >> 5); w++) woff += warp_off[w];
+  uint64_t at = block_off[blockIdx.x] + woff + incl - c;
+#pragma unroll
+  for (int k = 0; k < COO_PER_THREAD; k++) if (v[k]) {
+    const uint64_t e = base + k;
+    row[at] = (uint32_t)(e % nrows); col[at] = (uint32_t)(e / nrows); val[at] = v[k]; at++;
+  }
+}
+
 // per-colour info word for the counting kernel: bits 0-4 code (gene*3+slot or 31), bits 8-15 per-gene swap mask
 std::vector<uint32_t> make_cinfo(const HostIndex& ix, const RowLayout& rows) {
   std::vector<uint32_t> out(ix.n_colours());
@@ -313,6 +371,8 @@ struct hlac_count {
   cudaStream_t copy_stream = nullptr;
   uint64_t n_push = 0;
   DevBuf<uint8_t> codes;
+  DevBuf<uint32_t> coo_block_nnz, coo_dev; DevBuf<uint64_t> coo_block_off;   // device-side COO extraction
+  uint32_t* coo_host = nullptr; size_t coo_host_cap = 0;                      // pinned, 3 arrays back to back, session-owned
   DevBuf<unsigned long long> counters;   // [0] cursor, [1..8] metrics
   DevBuf<uint8_t> cub_tmp;
   uint64_t reads_pushed = 0, last_n = 0;
@@ -334,6 +394,7 @@ struct hlac_count {
 
   ~hlac_count() {
     for (auto& e : events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    if (coo_host) cudaFreeHost(coo_host);
     for (auto& st : stage) { if (st.copied) cudaEventDestroy(st.copied); if (st.consumed) cudaEventDestroy(st.consumed); }
     if (copy_stream) cudaStreamDestroy(copy_stream);
     if (stream && own_stream) cudaStreamDestroy(stream);
@@ -587,11 +648,34 @@ int hlac_count_entries(hlac_count* s, hlac_coo* out, hlac_metrics* metrics) try 
   if (!s->reduced) throw Error(HLAC_ERR_STATE, "hlac_count_reduce has not run since the last push");
   DeviceGuard g(s->device);
   const uint32_t nrows = s->rows.nrows;
-  const size_t nd = (size_t)s->n_cells * std::max<uint32_t>(nrows, 1);
-  std::vector<uint32_t> dense(nd);
+  const uint64_t nd = (uint64_t)s->n_cells * std::max<uint32_t>(nrows, 1);
   unsigned long long ctr[10];
-  HLAC_CUDA(cudaMemcpyAsync(dense.data(), s->dense.p, nd * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
   HLAC_CUDA(cudaMemcpyAsync(ctr, s->counters.p, sizeof ctr, cudaMemcpyDeviceToHost, s->stream));
+  uint64_t nnz = 0;
+  if (out && nrows) {
+    // dense -> COO on the device: per-block non-zero counts, one-block scan, ordered write; only the non-zeros cross PCIe
+    const uint32_t nb = (uint32_t)((nd + COO_TILE - 1) / COO_TILE);
+    s->coo_block_nnz.reserve(nb, s->stream); s->coo_block_off.reserve(nb + 1, s->stream);
+    k_coo_count<<<nb, COO_THREADS, 0, s->stream>>>(s->dense.p, nd, s->coo_block_nnz.p);
+    k_coo_scan<<<1, 1024, 0, s->stream>>>(s->coo_block_nnz.p, nb, s->coo_block_off.p);
+    HLAC_CUDA(cudaGetLastError());
+    HLAC_CUDA(cudaMemcpyAsync(&nnz, s->coo_block_off.p + nb, 8, cudaMemcpyDeviceToHost, s->stream));
+    HLAC_CUDA(cudaStreamSynchronize(s->stream));
+    if (nnz) {
+      s->coo_dev.reserve(3 * nnz, s->stream);
+      if (s->coo_host_cap < 3 * nnz) {
+        if (s->coo_host) cudaFreeHost(s->coo_host);
+        s->coo_host = nullptr; s->coo_host_cap = 0;
+        const size_t cap = 3 * nnz + 3 * nnz / 4 + 1024;
+        HLAC_CUDA(cudaHostAlloc((void**)&s->coo_host, cap * 4, cudaHostAllocDefault));
+        s->coo_host_cap = cap;
+      }
+      k_coo_write<<<nb, COO_THREADS, 0, s->stream>>>(s->dense.p, nd, nrows, s->coo_block_off.p, s->coo_dev.p, s->coo_dev.p + nnz, s->coo_dev.p + 2 * nnz);
+      HLAC_CUDA(cudaGetLastError());
+      HLAC_CUDA(cudaMemcpyAsync(s->coo_host, s->coo_dev.p, 3 * nnz * 4, cudaMemcpyDeviceToHost, s->stream));
+    }
+    s->launches += 3;
+  }
   HLAC_CUDA(cudaStreamSynchronize(s->stream));
   if (ctr[9]) throw Error(HLAC_ERR_ARG, std::to_string(ctr[9]) + " reads carried a cell index >= n_cells (the reference panics in TriMat::add_triplet, main.rs:279)");
   if (metrics) {
@@ -599,18 +683,10 @@ int hlac_count_entries(hlac_count* s, hlac_coo* out, hlac_metrics* metrics) try 
     metrics->num_cds_align = ctr[4]; metrics->num_gen_align = ctr[5]; metrics->num_not_aligned = ctr[6];
   }
   if (out) {
-    size_t nnz = 0;
-    for (size_t i = 0; i < nd; i++) nnz += dense[i] != 0;
-    out->n = nnz; out->nrows = nrows;
-    out->row = (uint32_t*)malloc(std::max<size_t>(nnz, 1) * 4);
-    out->col = (uint32_t*)malloc(std::max<size_t>(nnz, 1) * 4);
-    out->val = (uint32_t*)malloc(std::max<size_t>(nnz, 1) * 4);
-    size_t k = 0;
-    for (uint32_t c = 0; c < s->n_cells; c++)        // cells ascending, rows ascending (mapping.rs:829-832, 897-906)
-      for (uint32_t r = 0; r < nrows; r++) {
-        const uint32_t v = dense[(size_t)c * nrows + r];
-        if (v) { out->row[k] = r; out->col[k] = c; out->val[k] = v; k++; }
-      }
+    // the arrays live in the session's pinned buffer: valid until the next hlac_count_entries / _reset / _free on this
+    // session; hlac_coo_free does not free borrowed arrays
+    out->n = nnz; out->nrows = nrows; out->borrowed = 1;
+    out->row = s->coo_host; out->col = s->coo_host ? s->coo_host + nnz : nullptr; out->val = s->coo_host ? s->coo_host + 2 * nnz : nullptr;
   }
   return HLAC_OK;
 } catch (const Error& e) { set_last_error(e.what()); return e.code; }
@@ -629,7 +705,7 @@ int hlac_count_reset(hlac_count* s) try {
 } catch (const Error& e) { set_last_error(e.what()); return e.code; }
 
 int hlac_coo_free(hlac_coo* c) {
-  if (c) { free(c->row); free(c->col); free(c->val); c->row = c->col = c->val = nullptr; c->n = 0; }
+  if (c) { if (!c->borrowed) { free(c->row); free(c->col); free(c->val); } c->row = c->col = c->val = nullptr; c->n = 0; }
   return HLAC_OK;
 }
 

@@ -305,7 +305,13 @@ int hlac_map_and_count_pseudo(const char* bam, const char* out_dir, const char* 
   BatchBuilder bb(BATCH_READS);
   auto cell_of = [&](const BamRecord& r) { auto it = barcodes.find(r.barcode); return it == barcodes.end() ? HLAC_NOT_A_CELL : it->second; };
   stream_records(reader, bb, cell_of, [&] { hlac_batch b = bb.batch(); check(hlac_count_push(s.p, &b)); check(hlac_count_sync(s.p)); });
-  hlac_metrics m{}; check(hlac_count_finish(s.p, entries, &m));
+  hlac_metrics m{}; hlac_coo tmp{}; check(hlac_count_finish(s.p, &tmp, &m));
+  if (entries) {   // the session (and its pinned result buffer) ends with this call: hand out owned copies
+    *entries = tmp; entries->borrowed = 0;
+    const size_t bytes = std::max<uint64_t>(tmp.n, 1) * 4;
+    entries->row = (uint32_t*)malloc(bytes); entries->col = (uint32_t*)malloc(bytes); entries->val = (uint32_t*)malloc(bytes);
+    if (tmp.n) { memcpy(entries->row, tmp.row, tmp.n * 4); memcpy(entries->col, tmp.col, tmp.n * 4); memcpy(entries->val, tmp.val, tmp.n * 4); }
+  }
   if (metrics) *metrics = m;
   if (n_cells_out) *n_cells_out = n_cells;
   info("analyzed " + std::to_string(m.num_reads) + " reads. Mapped " + std::to_string(m.num_gen_align + m.num_cds_align) + " with score at least " + std::to_string(MIN_SCORE_COUNT_PSEUDO));
