@@ -3,19 +3,77 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <condition_variable>
+#include <cstdlib>
 #include <cstring>
+#include <functional>
+#include <mutex>
+#include <queue>
+#include <thread>
 
 namespace hlac {
 
 namespace {
 template <typename T>
 T rd(const uint8_t* p) { T v; memcpy(&v, p, sizeof(T)); return v; }
+
+std::vector<uint8_t> inflate_block(const std::vector<uint8_t>& cdata, uint32_t isize) {
+  std::vector<uint8_t> out(isize);
+  if (isize) {
+    z_stream zs{};
+    zs.next_in = const_cast<Bytef*>(cdata.data()); zs.avail_in = (uInt)cdata.size(); zs.next_out = out.data(); zs.avail_out = isize;
+    if (inflateInit2(&zs, -15) != Z_OK) throw Error(HLAC_ERR_FORMAT, "inflateInit2 failed");
+    const int rc = inflate(&zs, Z_FINISH);
+    inflateEnd(&zs);
+    if (rc != Z_STREAM_END) throw Error(HLAC_ERR_FORMAT, "BGZF inflate failed");
+  }
+  return out;
+}
 }  // namespace
+
+// Fixed pool of inflate workers (BAM ingest off the critical path). HLAC_BAM_THREADS overrides the
+// worker count; 0 or 1 inflates inline.
+class InflatePool {
+ public:
+  InflatePool() {
+    unsigned n = std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+    if (const char* e = getenv("HLAC_BAM_THREADS")) n = (unsigned)std::max(0, atoi(e));
+    if (n > 1) for (unsigned i = 0; i < n; i++) workers_.emplace_back([this] { run(); });
+  }
+  ~InflatePool() {
+    { std::lock_guard<std::mutex> l(m_); stop_ = true; }
+    cv_.notify_all();
+    for (auto& t : workers_) t.join();
+  }
+  size_t depth() const { return workers_.empty() ? 1 : workers_.size() * 4; }
+  std::future<std::vector<uint8_t>> submit(std::vector<uint8_t> cdata, uint32_t isize) {
+    auto task = std::make_shared<std::packaged_task<std::vector<uint8_t>()>>([c = std::move(cdata), isize] { return inflate_block(c, isize); });
+    auto fut = task->get_future();
+    if (workers_.empty()) (*task)();
+    else { { std::lock_guard<std::mutex> l(m_); q_.push([task] { (*task)(); }); } cv_.notify_one(); }
+    return fut;
+  }
+
+ private:
+  void run() {
+    for (;;) {
+      std::function<void()> job;
+      { std::unique_lock<std::mutex> l(m_); cv_.wait(l, [this] { return stop_ || !q_.empty(); }); if (stop_ && q_.empty()) return; job = std::move(q_.front()); q_.pop(); }
+      job();
+    }
+  }
+  std::vector<std::thread> workers_;
+  std::queue<std::function<void()>> q_;
+  std::mutex m_;
+  std::condition_variable cv_;
+  bool stop_ = false;
+};
 
 BamReader::BamReader(const std::string& path) {
   f_ = fopen(path.c_str(), "rb");
   if (!f_) throw Error(HLAC_ERR_IO, "cannot open BAM " + path);
-  next_coff_ = 0;
+  pool_ = std::make_unique<InflatePool>();
+  next_coff_ = 0; read_coff_ = 0;
   block_.clear(); block_pos_ = 0;
   uint8_t magic[4];
   if (!read_bytes(magic, 4) || memcmp(magic, "BAM\1", 4) != 0) throw Error(HLAC_ERR_FORMAT, path + " is not a BAM file");
@@ -63,13 +121,14 @@ BamReader::BamReader(const std::string& path) {
   }
 }
 
-BamReader::~BamReader() { if (f_) fclose(f_); }
+BamReader::~BamReader() { pending_.clear(); pool_.reset(); if (f_) fclose(f_); }
 
-bool BamReader::read_block() {
+bool BamReader::enqueue_block() {
+  if (raw_eof_) return false;
   uint8_t hdr[18];
-  if (fseeko(f_, (off_t)next_coff_, SEEK_SET) != 0) return false;
+  if (fseeko(f_, (off_t)read_coff_, SEEK_SET) != 0) { raw_eof_ = true; return false; }
   size_t k = fread(hdr, 1, 18, f_);
-  if (k == 0) return false;
+  if (k == 0) { raw_eof_ = true; return false; }
   if (k < 18 || hdr[0] != 31 || hdr[1] != 139 || !(hdr[3] & 4)) throw Error(HLAC_ERR_FORMAT, "bad BGZF block header");
   uint16_t xlen = rd<uint16_t>(&hdr[10]);
   // the BC subfield is normally first (SI1=66, SI2=67, SLEN=2); handle the general case
@@ -82,21 +141,27 @@ bool BamReader::read_block() {
     if (extra[p] == 66 && extra[p + 1] == 67 && slen == 2) bsize = rd<uint16_t>(&extra[p + 4]) + 1;
     p += 4 + slen;
   }
-  if (bsize < 0) throw Error(HLAC_ERR_FORMAT, "BGZF block without BSIZE");
-  size_t clen = bsize - 12 - xlen - 8;
-  cbuf_.resize(clen + 8);
-  if (fread(cbuf_.data(), 1, clen + 8, f_) != clen + 8) throw Error(HLAC_ERR_FORMAT, "BGZF truncated");
-  uint32_t isize = rd<uint32_t>(&cbuf_[clen + 4]);
-  block_.resize(isize);
-  if (isize) {
-    z_stream zs{}; zs.next_in = cbuf_.data(); zs.avail_in = (uInt)clen; zs.next_out = block_.data(); zs.avail_out = isize;
-    if (inflateInit2(&zs, -15) != Z_OK) throw Error(HLAC_ERR_FORMAT, "inflateInit2 failed");
-    int rc = inflate(&zs, Z_FINISH);
-    inflateEnd(&zs);
-    if (rc != Z_STREAM_END) throw Error(HLAC_ERR_FORMAT, "BGZF inflate failed");
-  }
-  block_coff_ = next_coff_;
-  next_coff_ += bsize;
+  if (bsize < 0 || bsize < 12 + xlen + 8) throw Error(HLAC_ERR_FORMAT, "BGZF block without a valid BSIZE");
+  const size_t clen = bsize - 12 - xlen - 8;
+  std::vector<uint8_t> cdata(clen + 8);
+  if (fread(cdata.data(), 1, clen + 8, f_) != clen + 8) throw Error(HLAC_ERR_FORMAT, "BGZF truncated");
+  const uint32_t isize = rd<uint32_t>(&cdata[clen + 4]);
+  cdata.resize(clen);
+  Pending pd; pd.coff = read_coff_; pd.bsize = (uint64_t)bsize;
+  pd.data = pool_->submit(std::move(cdata), isize);
+  pending_.push_back(std::move(pd));
+  read_coff_ += bsize;
+  return true;
+}
+
+bool BamReader::read_block() {
+  while (pending_.size() < pool_->depth() && enqueue_block()) {}
+  if (pending_.empty()) return false;
+  Pending pd = std::move(pending_.front());
+  pending_.pop_front();
+  block_ = pd.data.get();   // rethrows an inflate error
+  block_coff_ = pd.coff;
+  next_coff_ = pd.coff + pd.bsize;
   block_pos_ = 0;
   return true;
 }
@@ -113,7 +178,8 @@ bool BamReader::read_bytes(void* dst, size_t n) {
 }
 
 void BamReader::seek_virtual(uint64_t voff) {
-  next_coff_ = voff >> 16;
+  pending_.clear();   // drop the blocks inflated ahead of the old position
+  next_coff_ = read_coff_ = voff >> 16; raw_eof_ = false;
   block_.clear(); block_pos_ = 0;
   if ((voff & 0xFFFF) != 0) {
     if (!read_block()) throw Error(HLAC_ERR_FORMAT, "bad virtual offset");

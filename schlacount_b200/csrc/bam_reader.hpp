@@ -3,6 +3,9 @@
 #pragma once
 #include <cstdint>
 #include <cstdio>
+#include <deque>
+#include <future>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -16,6 +19,8 @@ struct BamRecord {          // what BamCrRead needs (mapping.rs:64-75)
   bool primary = true;      // !(secondary || supplementary) (mapping.rs:247-249)
 };
 
+class InflatePool;   // worker threads that inflate BGZF blocks ahead of the record parser
+
 class BamReader {
  public:
   explicit BamReader(const std::string& path);   // opens path and path + ".bai"
@@ -28,7 +33,13 @@ class BamReader {
   const std::vector<std::string>& ref_names() const { return ref_names_; }
 
  private:
-  bool read_block();                              // inflate the next BGZF block into block_
+  bool read_block();                              // next inflated BGZF block into block_ (blocks are inflated ahead, in parallel)
+  struct Pending { uint64_t coff, bsize; std::future<std::vector<uint8_t>> data; };
+  bool enqueue_block();                           // read one raw block at read_coff_ and hand it to the pool
+  std::deque<Pending> pending_;
+  std::unique_ptr<InflatePool> pool_;
+  uint64_t read_coff_ = 0;                        // file offset of the next raw block to read
+  bool raw_eof_ = false;
   bool read_bytes(void* dst, size_t n);
   void seek_virtual(uint64_t voff);
   FILE* f_ = nullptr;
