@@ -159,3 +159,37 @@ def test_long_reads_and_interned_umis(sb, orc, abc):
         ref = orc.count_run(abc["oc"], abc["og"], *batch, want_codes=True)
         assert np.array_equal(codes, ref["codes"]) and met == ref["metrics"] and ent == ref["entries"]
         assert len(ent) > 20
+
+
+def test_row_layout_many_genes(sb, orc, tmp_path):
+    """mapping.rs:668-728 beyond the A/B/C fixture: 8 genes (config 4 shape), a gene with a single allele (1 row), a gene
+    with three alleles (the third is in the index but has no row), 100 k barcodes; reads from every allele."""
+    from tools import synth
+    db = str(tmp_path / "db")
+    names = synth.make_db(db, 3, 77, extra_genes=("DRB1", "DPA1", "DPB1", "DQA1", "DQB1"))
+    nuc = dict((h.split(" ")[1], (h, s)) for h, s in synth.read_fasta(os.path.join(db, "hla_nuc.fasta")))
+    gen = dict((h.split(" ")[1], (h, s)) for h, s in synth.read_fasta(os.path.join(db, "hla_gen.fasta")))
+    keep = []
+    for g in ("A", "B", "C", "DRB1", "DPA1", "DPB1", "DQA1", "DQB1"):
+        al = [n for n in names if n.startswith(g + "*")]
+        keep += al[:1] if g == "C" else al[:3] if g == "B" else al[:2]
+    cf, gf = str(tmp_path / "cds.fa"), str(tmp_path / "gen.fa")
+    synth.write_fasta(cf, [nuc[a] for a in keep])
+    synth.write_fasta(gf, [gen[a] for a in keep])
+    gc, gg = sb.Index.from_fasta(cf), sb.Index.from_fasta(gf)
+    oc, og = orc.Index.from_fasta(cf), orc.Index.from_fasta(gf)
+    rows = oc.rows()
+    assert len(rows) == 3 * 7 + 1 and rows.count("C") == 0 and "B" in rows
+    n_cells = 100_000
+    r = synth.make_reads(150_000, [nuc[a][1] for a in keep], [gen[a][1] for a in keep], n_cells, 78)
+    batch = (r["seq"], r["len"], r["cell"], r["umi"], r["flags"])
+    s = sb.CountSession(gc, gg, n_cells)
+    assert s.row_names == rows and s.nrows == 22
+    s.record_codes(True)
+    s.push(*batch)
+    codes = s.last_codes(len(r["len"]))
+    ent, met = s.finish()
+    ref = orc.count_run(oc, og, *batch, want_codes=True)
+    assert np.array_equal(codes, ref["codes"]) and met == ref["metrics"] and ent == ref["entries"]
+    used = set(np.unique(codes).tolist()) - {255}
+    assert len(used) >= 15 and max(used) <= 23    # alleles and gene-level rows of many genes were hit
