@@ -280,7 +280,7 @@ def main():
     e2e_ms = ms_e2e / args.steps
     # host-side gaps (sync for the key count, COO extraction) are inside both event-bracketed regions
     in_bytes = sum(int(v.nbytes) for v in hn.values())
-    d2h_bytes = n_cells_total * nrows * 4 + 9 * 8 + 8
+    d2h_bytes = (3 * 4 * len(out_dev[0][0]) + 10 * 8 + 8 + 8) if rank == 0 else 0   # COO triplets + counters + key count + nnz
 
     line = None
     if rank == 0:
