@@ -94,17 +94,11 @@ __device__ __forceinline__ bool find_seed(const DevIndexView& ix, RD rd, BM bm, 
   return false;
 }
 
-// map_read_to_nodes after the first seed (SURVEY.md Appendix A): optional left extension, then the forward walk.
-// (pos, node, off) is the first verified seed. V::visit(colour, node) is called for every visited node in the
-// reference's push order (left-extension nodes first, then the forward walk); the last call is the class-defining node.
-template <typename RD, typename BM, typename V>
-__device__ __forceinline__ uint32_t walk_from_seed(const DevIndexView& ix, RD rd, BM bm, int L, int pos, uint32_t node, uint32_t off,
-                                                   V& vis, uint32_t& n_tests, uint32_t& n_probes) {
-  const int last = L - K;
+// Left extension: only when the first seed sits at or beyond floor(0.2*L). Walks the read
+// leftwards from the seed through predecessor nodes; returns the coverage it adds and visits the nodes it enters.
+template <typename RD, typename V>
+__device__ __forceinline__ int left_extend(const DevIndexView& ix, RD rd, int L, int pos, uint32_t node, uint32_t off, const uint4& n0, V& vis) {
   int cov = 0;
-  uint4 n0 = __ldg(ix.nodes + 3 * (size_t)node);
-  uint4 ra = __ldg(ix.nodes + 3 * (size_t)node + 1);   // right-edge table, fetched with the node so its latency hides behind the compare
-  // ---- left extension: only when the first seed sits at or beyond floor(0.2*L) ----
   if (pos >= (L * LEFT_EXTEND_NUM) / LEFT_EXTEND_DEN) {
     int lp = pos - 1;
     uint32_t pn = node;
@@ -134,6 +128,20 @@ __device__ __forceinline__ uint32_t walk_from_seed(const DevIndexView& ix, RD rd
       vis.visit(p0.w, pn);
     }
   }
+  return cov;
+}
+
+// map_read_to_nodes after the first seed (SURVEY.md Appendix A): optional left extension, then the forward walk.
+// (pos, node, off) is the first verified seed. V::visit(colour, node) is called for every visited node in the
+// reference's push order (left-extension nodes first, then the forward walk); the last call is the class-defining node.
+template <typename RD, typename BM, typename V>
+__device__ __forceinline__ uint32_t walk_from_seed(const DevIndexView& ix, RD rd, BM bm, int L, int pos, uint32_t node, uint32_t off,
+                                                   V& vis, uint32_t& n_tests, uint32_t& n_probes) {
+  const int last = L - K;
+  int cov = 0;
+  uint4 n0 = __ldg(ix.nodes + 3 * (size_t)node);
+  uint4 ra = __ldg(ix.nodes + 3 * (size_t)node + 1);   // right-edge table, fetched with the node so its latency hides behind the compare
+  cov += left_extend(ix, rd, L, pos, node, off, n0, vis);
   // ---- forward walk, flattened: one loop whose body compares <= 16 bases inside the current node and then, if the node
   // is exhausted (or the per-node mismatch budget is), takes the edge or re-seeds. Equivalent to the reference's
   // node loop with an inner base loop: a hop is `pos -= K-1; cov -= K-1` followed by `pos += K; cov += K` = +1/+1,
