@@ -78,19 +78,34 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(s)}
 
 
-def gen_shard(n_reads, n_cells_total, rank, world, seed):
+def allele_set(genes, workdir=None):
+    """-> (cds fasta path, genomic fasta path, cds seqs, genomic seqs). genes=3: the six fixture alleles (config 2);
+    genes=8: two synthetic alleles for each of the 8 admissible genes (config 4 shape, src/hla.rs:108-117)."""
+    from tools import synth
+    if genes == 3:
+        cds, gen = synth.fixture_alleles()
+        return (os.path.join(synth.FIX, "cds_ABC.fa"), os.path.join(synth.FIX, "genomic_ABC.fa"),
+                [s for _, s in cds], [s for _, s in gen])
+    import tempfile
+    d = workdir or os.path.join(tempfile.gettempdir(), "hlac_bench_genes%d_%d" % (genes, os.getpid()))
+    synth.make_db(d, 2, SEED, extra_genes=("DRB1", "DPA1", "DPB1", "DQA1", "DQB1")[:genes - 3])
+    cds, gen = synth.read_fasta(os.path.join(d, "hla_nuc.fasta")), synth.read_fasta(os.path.join(d, "hla_gen.fasta"))
+    return os.path.join(d, "hla_nuc.fasta"), os.path.join(d, "hla_gen.fasta"), [s for _, s in cds], [s for _, s in gen]
+
+
+def gen_shard(n_reads, n_cells_total, rank, world, seed, alleles=None):
     """Rank's shard: cells of this rank are {c : c % world == rank} (partition by barcode)."""
     from tools import synth
-    cds, gen = synth.fixture_alleles()
+    cds_s, gen_s = (alleles[2], alleles[3]) if alleles else [[s for _, s in x] for x in synth.fixture_alleles()]
     local_cells = (n_cells_total - rank + world - 1) // world
-    r = synth.make_reads(n_reads, [s for _, s in cds], [s for _, s in gen], local_cells, seed + 1000 * rank)
+    r = synth.make_reads(n_reads, cds_s, gen_s, local_cells, seed + 1000 * rank)
     ok = r["cell"] != synth.NOT_A_CELL
     r["cell"][ok] = r["cell"][ok] * world + rank
     return r
 
 
 def oracle_worker(args):
-    cf, gf, arrs = args
+    cf, gf, arrs = args[:3]
     from oracle import oracle as orc
     cds, gen = orc.Index.from_fasta(cf), orc.Index.from_fasta(gf)
     t = time.perf_counter()
@@ -98,12 +113,12 @@ def oracle_worker(args):
     return time.perf_counter() - t, res["entries"], res["metrics"]
 
 
-def run_oracle(r, n, procs):
+def run_oracle(r, n, procs, fastas=None):
     """The reference's CPU path (oracle port) on the first n reads, partitioned by barcode over `procs` processes
     (the reference itself is single-threaded; running one instance per barcode subset is how it would be spread over
     cores). Returns (seconds of the slowest worker, entries)."""
     from tools import synth
-    cf, gf = os.path.join(synth.FIX, "cds_ABC.fa"), os.path.join(synth.FIX, "genomic_ABC.fa")
+    cf, gf = fastas or (os.path.join(synth.FIX, "cds_ABC.fa"), os.path.join(synth.FIX, "genomic_ABC.fa"))
     sl = {k: v[:n] for k, v in r.items()}
     if procs <= 1:
         dt, ent, met = oracle_worker((cf, gf, (sl["seq"], sl["len"], sl["cell"], sl["umi"], sl["flags"])))
@@ -132,13 +147,16 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=1_500_000, help="reads of the workload timed on the CPU oracle")
     ap.add_argument("--ref-procs", type=int, default=0, help="--impl reference: worker processes (0 = all cores)")
     ap.add_argument("--chunk", type=int, default=1_000_000, help="e2e push chunk in reads (0 = whole batch)")
+    ap.add_argument("--genes", type=int, default=3, choices=[3, 4, 5, 6, 7, 8],
+                    help="3 = the six fixture alleles (config 2); 8 = 2 synthetic alleles x 8 genes (config 4 shape)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    config = {"workload": "config2: synthetic 5' GEX, %d reads x 91 bp per GPU, %d barcodes per GPU, 6 CDS + 6 genomic "
-                          "alleles (HLA-A/B/C), known-genotype counting" % (args.reads, args.cells),
+    config = {"workload": "%s: synthetic 5' GEX, %d reads x 91 bp per GPU, %d barcodes per GPU, %d CDS + %d genomic "
+                          "alleles (%d genes x 2), known-genotype counting" % ("config2" if args.genes == 3 else "config4-shape",
+                                                                               args.reads, args.cells, 2 * args.genes, 2 * args.genes, args.genes),
               "reads_per_gpu": args.reads, "barcodes_per_gpu": args.cells, "parallelism": "reads sharded by barcode x%d" % world,
               "l2": "inputs (%.0f MB/step) exceed the 126 MB L2; no explicit flush" % (args.reads * 35 / 1e6),
               "seed": SEED}
@@ -148,12 +166,13 @@ def main():
             return 0
         procs = args.ref_procs or (os.cpu_count() or 1)
         n = min(args.reads, args.cpu_sample * max(1, procs // 2))
-        r = gen_shard(n, args.cells, 0, 1, SEED)
+        al = allele_set(args.genes)
+        r = gen_shard(n, args.cells, 0, 1, SEED, al)
         from oracle import oracle as orc
         orc.build()
         times = []
         for i in range(args.warmup + args.steps):
-            dt, _ = run_oracle(r, n, procs)
+            dt, _ = run_oracle(r, n, procs, al[:2])
             if i >= args.warmup:
                 times.append(dt)
         per = sum(times) / len(times)
@@ -190,9 +209,10 @@ def main():
             os.dup2(saved, 1)
             os.close(saved)
     n_cells_total = args.cells * world
-    r = gen_shard(args.reads, n_cells_total, rank, world, SEED)
+    al = allele_set(args.genes)
+    r = gen_shard(args.reads, n_cells_total, rank, world, SEED, al)
     n = args.reads
-    cf, gf = os.path.join(synth.FIX, "cds_ABC.fa"), os.path.join(synth.FIX, "genomic_ABC.fa")
+    cf, gf = al[0], al[1]
     gc, gg = sb.Index.from_fasta(cf, device=local_rank), sb.Index.from_fasta(gf, device=local_rank)
     sess = sb.CountSession(gc, gg, n_cells_total)
     stream = torch.cuda.current_stream()
@@ -319,7 +339,7 @@ def main():
             from oracle import oracle as orc
             orc.build()
             ns = min(n, args.cpu_sample)
-            dt, ent_cpu = run_oracle(r, ns, 1)
+            dt, ent_cpu = run_oracle(r, ns, 1, al[:2])
             line["cpu_baseline"] = {"value": ns / dt, "unit": UNIT, "cores": 1, "kind": "port",
                                     "sample": "first %d reads of rank 0's shard, single thread (the reference is single-threaded)" % ns}
         print(json.dumps(line))
