@@ -328,9 +328,10 @@ def main():
                 "dtype": "u32", "data": "synthetic", "config": config,
                 "e2e": {"value": total_reads / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": in_bytes,
                         "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_ms, "h2d_ms": tm_e2e["h2d_ms"]},
-                # our own kernels in the timed region: k_count_map + k_consensus per step; the radix sort between them is
+                # our own kernels in the timed region per step (device-resident loop); the radix sort between them is
                 # cub (library): histogram + exclusive-sum + one onesweep pass per 8 key bits
-                "gpu_launches": 2 * args.steps, "library_launches": (2 + (32 + max(1, (n_cells_total - 1).bit_length()) + 7) // 8) * args.steps,
+                "gpu_launches": 5 * args.steps,   # k_count_map, k_consensus, k_coo_count, k_coo_scan, k_coo_write
+                "library_launches": (2 + (int(r["umi"].max()).bit_length() + max(1, (n_cells_total - 1).bit_length()) + 7) // 8) * args.steps,
                 "kernels_ms_last_step": kern, "roofline": roof, "clocks": clocks, "clocks_e2e": clocks_e2e,
                 "wall_ms_per_step": wall_dev / args.steps * 1e3,
                 "result": {"matrix_entries": int(len(ent[0])), "molecules": nkeys, "metrics": met}}

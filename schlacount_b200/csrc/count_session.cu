@@ -48,10 +48,11 @@ struct CountMapArgs {
   uint32_t nw;                 // u32 words per strand row in shared memory (2*wpr + 2)
   uint32_t row_stride;         // u32 words per thread (both strands, odd)
   int primary_only;
+  uint32_t cell_bits;          // key layout: umi << (5 + cell_bits) | cell << 5 | code
   uint32_t n_cells;            // cell indices >= n_cells are a caller error: dropped and counted in metrics[8]
   uint64_t* keys;
   unsigned long long* cursor;  // number of keys appended so far
-  unsigned long long* metrics; // [6] + [2] seed-filter tests / dictionary probes + [1] out-of-range cell indices
+  unsigned long long* metrics; // [6] + [2] seed-filter tests / dictionary probes + [1] out-of-range cell indices + [1] max UMI key
   uint8_t* codes;              // optional per-read debug output
 };
 
@@ -114,7 +115,7 @@ __global__ void __launch_bounds__(MAP_THREADS, MINB) k_count_map(const CountMapA
   uint16_t* lens = reinterpret_cast<uint16_t*>(seed_info + TILE);
   uint8_t* q = reinterpret_cast<uint8_t*>(lens + TILE);                     // 3 queues of TILE slots
   unsigned long long m_reads = 0, m_nonprim = 0, m_notcell = 0, m_cds = 0, m_gen = 0, m_none = 0, m_badcell = 0;
-  uint32_t n_tests = 0, n_probes = 0;
+  uint32_t n_tests = 0, n_probes = 0, umi_max = 0;
   const uint64_t n_warps = (uint64_t)gridDim.x * (MAP_THREADS / 32);
   for (uint64_t tile = (uint64_t)blockIdx.x * (MAP_THREADS / 32) + warp; tile * TILE < a.n; tile += n_warps) {
     const uint64_t base = tile * TILE;
@@ -211,7 +212,9 @@ __global__ void __launch_bounds__(MAP_THREADS, MINB) k_count_map(const CountMapA
         if (good) { if (p < 2) m_cds++; else m_gen++; }
         if (p == 0 || good) code = vis.code();   // a CDS-forward hit is used whatever its coverage (mapping.rs:772-775)
         if (code != CODE_NONE5) {
-          key = ((uint64_t)__ldg(a.cell + i) << (UMI_BITS + CODE_BITS)) | ((uint64_t)__ldg(a.umi + i) << CODE_BITS) | code;
+          const uint32_t um = __ldg(a.umi + i);
+          umi_max = max(umi_max, um);
+          key = ((uint64_t)um << (CODE_BITS + a.cell_bits)) | ((uint64_t)__ldg(a.cell + i) << CODE_BITS) | code;
           if (a.codes) a.codes[i] = (uint8_t)code;
         }
       }
@@ -233,11 +236,13 @@ __global__ void __launch_bounds__(MAP_THREADS, MINB) k_count_map(const CountMapA
     for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, o);
     if (lane == 0 && v) atomicAdd(a.metrics + k, v);
   }
+  for (int o = 16; o > 0; o >>= 1) umi_max = max(umi_max, __shfl_down_sync(0xFFFFFFFFu, umi_max, o));
+  if (lane == 0 && umi_max) atomicMax(a.metrics + 9, (unsigned long long)umi_max);   // how many UMI bits the sort must cover
 }
 
 // count() (mapping.rs:842-896) for one (cell, UMI) run of the sorted keys.
 __global__ void k_consensus(const uint64_t* __restrict__ keys, uint64_t n, uint32_t* __restrict__ dense, uint32_t nrows,
-                            const uint32_t* __restrict__ gene_row0) {
+                            const uint32_t* __restrict__ gene_row0, uint32_t cell_bits) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint64_t k0 = keys[i], grp = k0 >> CODE_BITS;
@@ -266,7 +271,7 @@ __global__ void k_consensus(const uint64_t* __restrict__ keys, uint64_t n, uint3
   if ((double)f[0] > ALLELE_CONSENSUS_THRESHOLD * nr && ALLELE_CONSENSUS_THRESHOLD * nr > (double)f[1]) slot = 0;
   else if ((double)f[1] > ALLELE_CONSENSUS_THRESHOLD * nr && ALLELE_CONSENSUS_THRESHOLD * nr > (double)f[0]) slot = 1;
   else slot = 2;
-  const uint32_t cell = (uint32_t)(k0 >> (UMI_BITS + CODE_BITS));
+  const uint32_t cell = (uint32_t)(k0 >> CODE_BITS) & ((1u << cell_bits) - 1u);
   atomicAdd(dense + (size_t)cell * nrows + gene_row0[cand] + slot, 1u);
 }
 
@@ -381,6 +386,7 @@ struct hlac_count {
   int blocks_per_sm = 1, n_sm = 1;
   bool want_codes = false;
   bool reduced = false;
+  uint32_t cell_bits = 1;
   uint32_t cfg_wpr = 0;
   int cfg_occ = 0, cfg_r = 0, cfg_threads = 0;
   bool cfg_bm = false;
@@ -415,7 +421,7 @@ struct hlac_count {
     events.clear();
   }
   void reset() {
-    HLAC_CUDA(cudaMemsetAsync(counters.p, 0, 10 * sizeof(unsigned long long), stream));
+    HLAC_CUDA(cudaMemsetAsync(counters.p, 0, 11 * sizeof(unsigned long long), stream));
     reads_pushed = 0; last_n = 0; reduced = false; n_keys = 0;
     drain_events(); ms[0] = ms[1] = ms[2] = ms[3] = 0; launches = 0;
   }
@@ -430,7 +436,7 @@ struct hlac_count {
     a.cds.nodes = reinterpret_cast<const uint4*>(nodes_cds.p); a.gen.nodes = reinterpret_cast<const uint4*>(nodes_gen.p);
     a.seq = b.seq; a.len = b.len; a.cell = b.cell; a.umi = b.umi; a.flags = b.flags;
     a.n = b.n; a.wpr = b.words_per_read; a.nw = 2 * b.words_per_read + 2; a.row_stride = (2 * a.nw) | 1;
-    a.primary_only = primary_only; a.n_cells = n_cells;
+    a.primary_only = primary_only; a.n_cells = n_cells; a.cell_bits = cell_bits;
     a.keys = keys.p; a.cursor = counters.p; a.metrics = counters.p + 1;
     a.codes = want_codes ? codes.p : nullptr;
     // launch shape: (bitmaps in shared memory?, reads per lane per warp tile R, threads per block). Defaults below;
@@ -493,6 +499,7 @@ int hlac_count_new(hlac_index* cds, hlac_index* genomic, uint32_t n_cells, int p
   if (n_cells == 0 || n_cells >= (1u << 27)) throw Error(HLAC_ERR_LIMIT, "n_cells must be in 1..2^27-1");
   auto s = std::make_unique<hlac_count>();
   s->cds = cds; s->gen = genomic; s->device = cds->device; s->n_cells = n_cells; s->primary_only = primary_only;
+  while ((1ull << s->cell_bits) < n_cells) s->cell_bits++;
   DeviceGuard g(s->device);
   s->rows = build_row_layout(cds->host.tx_names);
   if (s->rows.n_genes > 8) throw Error(HLAC_ERR_LIMIT, "more than 8 genes in the CDS FASTA");
@@ -614,16 +621,18 @@ int hlac_count_reduce(hlac_count* s, uint32_t** dense_device, uint64_t* n_elems)
   if (!s) throw Error(HLAC_ERR_ARG, "null session");
   DeviceGuard g(s->device);
   const size_t nd = (size_t)s->n_cells * std::max<uint32_t>(s->rows.nrows, 1);
-  unsigned long long nk = 0;
+  unsigned long long nk = 0, umi_max = 0;
   HLAC_CUDA(cudaMemcpyAsync(&nk, s->counters.p, sizeof nk, cudaMemcpyDeviceToHost, s->stream));
+  HLAC_CUDA(cudaMemcpyAsync(&umi_max, s->counters.p + 10, sizeof umi_max, cudaMemcpyDeviceToHost, s->stream));
   HLAC_CUDA(cudaMemsetAsync(s->dense.p, 0, nd * sizeof(uint32_t), s->stream));
   HLAC_CUDA(cudaStreamSynchronize(s->stream));
   s->n_keys = nk;
   if (nk > 0) {
     s->keys_sorted.reserve(nk, s->stream);
-    int cell_bits = 1;
-    while ((1ull << cell_bits) < s->n_cells) cell_bits++;
-    const int end_bit = CODE_BITS + UMI_BITS + cell_bits;
+    // keys are umi << (5 + cell_bits) | cell << 5 | code: only the UMI bits actually seen need sorting (10-bp UMIs: 21)
+    int umi_bits = 1;
+    while (umi_bits < UMI_BITS && (umi_max >> umi_bits)) umi_bits++;
+    const int end_bit = CODE_BITS + (int)s->cell_bits + umi_bits;
     size_t tmp = 0;
     HLAC_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tmp, s->keys.p, s->keys_sorted.p, (uint64_t)nk, CODE_BITS, end_bit, s->stream));
     s->cub_tmp.reserve(tmp, s->stream);
@@ -631,7 +640,7 @@ int hlac_count_reduce(hlac_count* s, uint32_t** dense_device, uint64_t* n_elems)
     HLAC_CUDA(cub::DeviceRadixSort::SortKeys(s->cub_tmp.p, tmp, s->keys.p, s->keys_sorted.p, (uint64_t)nk, CODE_BITS, end_bit, s->stream));
     s->end(e1);
     auto& e2 = s->begin(2);
-    k_consensus<<<(unsigned)((nk + 255) / 256), 256, 0, s->stream>>>(s->keys_sorted.p, nk, s->dense.p, s->rows.nrows, s->gene_row0.p);
+    k_consensus<<<(unsigned)((nk + 255) / 256), 256, 0, s->stream>>>(s->keys_sorted.p, nk, s->dense.p, s->rows.nrows, s->gene_row0.p, s->cell_bits);
     HLAC_CUDA(cudaGetLastError());
     s->end(e2);
     s->launches += 1;   // k_consensus; the cub sort passes are library kernels and not counted
