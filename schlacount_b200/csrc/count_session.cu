@@ -406,6 +406,7 @@ struct hlac_count {
     if (stream && own_stream) cudaStreamDestroy(stream);
   }
   Ev& begin(int kind, cudaStream_t on = nullptr) {
+    if (events.size() >= 512) drain_events();   // long streaming runs: keep the number of live events bounded
     Ev e; e.kind = kind;
     HLAC_CUDA(cudaEventCreate(&e.a)); HLAC_CUDA(cudaEventCreate(&e.b));
     HLAC_CUDA(cudaEventRecord(e.a, on ? on : stream));

@@ -437,6 +437,7 @@ struct hlac_geno {
     if (stream) cudaStreamDestroy(stream);
   }
   size_t begin(int kind) {
+    if (events.size() >= 512) drain_events();   // long streaming runs: keep the number of live events bounded
     Ev e; e.kind = kind;
     HLAC_CUDA(cudaEventCreate(&e.a)); HLAC_CUDA(cudaEventCreate(&e.b));
     HLAC_CUDA(cudaEventRecord(e.a, stream));
