@@ -36,24 +36,37 @@ void info(const std::string& m) { std::cerr << "[INFO] " << m << std::endl; }
 
 void check(int rc) { if (rc != HLAC_OK) throw Error(rc, hlac_last_error()); }
 
-// src/locus.rs:26-48 — "chr:start-end" (commas allowed in numbers) or a bare contig
-struct Locus { std::string chrom; uint64_t start = 0, end = 1ull << 32; };
+// src/locus.rs:29-48 — regex ^(.*):([0-9,]+)(-|..)([0-9,]+)$ : greedy contig up to the last colon that lets the rest
+// match, start and end may contain commas, the separator is '-' or ANY two characters (the reference's unescaped "..").
+struct Locus { std::string chrom; uint64_t start = 0, end = 0; };
 Locus parse_locus(const std::string& s) {
-  Locus l;
-  size_t colon = s.rfind(':');
-  if (colon == std::string::npos) { l.chrom = s; return l; }
-  l.chrom = s.substr(0, colon);
-  std::string rest;
-  for (char c : s.substr(colon + 1)) if (c != ',') rest += c;
-  size_t dash = rest.find('-');
-  if (dash == std::string::npos || dash == 0 || dash + 1 >= rest.size()) throw Error(HLAC_ERR_ARG, "invalid locus: " + s);
-  for (char c : rest) if (c != '-' && (c < '0' || c > '9')) throw Error(HLAC_ERR_ARG, "invalid locus: " + s);
-  l.start = std::stoull(rest.substr(0, dash)); l.end = std::stoull(rest.substr(dash + 1));
-  return l;
+  auto numeric = [](const std::string& t) { if (t.empty()) return false; for (char c : t) if (!((c >= '0' && c <= '9') || c == ',')) return false; return true; };
+  auto value = [&](std::string t) {
+    t.erase(std::remove(t.begin(), t.end(), ','), t.end());
+    if (t.empty() || t.size() > 10 || std::stoull(t) > 0xFFFFFFFFull) throw Error(HLAC_ERR_ARG, "invalid locus: " + s);   // u32::from_str(..).unwrap()
+    return (uint64_t)std::stoull(t);
+  };
+  for (size_t colon = s.rfind(':'); colon != std::string::npos; colon = colon ? s.rfind(':', colon - 1) : std::string::npos) {
+    const std::string rest = s.substr(colon + 1);
+    size_t run = 0;
+    while (run < rest.size() && ((rest[run] >= '0' && rest[run] <= '9') || rest[run] == ',')) run++;
+    for (size_t n2 = run; n2 >= 1; n2--) {   // group 2 is greedy, then backtracks
+      for (size_t sep : {size_t(1), size_t(2)}) {
+        if (sep == 1 && (n2 >= rest.size() || rest[n2] != '-')) continue;
+        if (n2 + sep >= rest.size() || !numeric(rest.substr(n2 + sep))) continue;
+        Locus l; l.chrom = s.substr(0, colon); l.start = value(rest.substr(0, n2)); l.end = value(rest.substr(n2 + sep));
+        return l;
+      }
+    }
+    if (colon == 0) break;
+  }
+  throw Error(HLAC_ERR_ARG, "invalid locus: " + s);
 }
 
 // src/main.rs:406-424 + src/io.rs: column = line index, last occurrence wins, gzip sniffed
 std::unordered_map<std::string, uint32_t> load_barcodes(const std::string& path) {
+  { struct stat st; if (stat(path.c_str(), &st) != 0) throw Error(HLAC_ERR_IO, "Error opening file: \"" + path + "\"");
+    if (st.st_size < 4) throw Error(HLAC_ERR_IO, "failed to fill whole buffer"); }   // io.rs:20 read_exact of the 4 sniff bytes
   gzFile g = gzopen(path.c_str(), "rb");   // gzopen reads plain files transparently
   if (!g) throw Error(HLAC_ERR_IO, "cannot open barcode file " + path);
   std::string data; char buf[1 << 16]; int k;

@@ -121,3 +121,15 @@ def test_no_cpu_fallback(sb):
             sb.Index.from_fasta(os.path.join(H.FIX, "cds_ABC.fa"), device=0)
         with pytest.raises(sb.HlacError):
             sb.squarem(4, {(0,): 1})
+
+
+def test_locus_parsing_follows_the_reference_regex(sb):
+    """src/locus.rs:29-48: ^(.*):([0-9,]+)(-|..)([0-9,]+)$ — commas allowed, '-' or ANY two characters as separator."""
+    L = sb.lib()
+    n, h = C.c_uint64(), C.c_uint64()
+    bam = os.path.join(H.FIX, "test.bam").encode()
+    for good in (b"6:28510120-33480577", b"6:28,510,120-33,480,577", b"6:28510120..33480577", b"6:28510120xy33480577"):
+        assert L.hlac_bam_scan(bam, good, C.byref(n), C.byref(h)) == 0 and n.value == 2864, good
+    for bad in (b"6", b"6:100", b"6:-200", b"6:100-", b"6:100-2x0", b"6:99999999999-5"):
+        assert L.hlac_bam_scan(bam, bad, C.byref(n), C.byref(h)) != 0, bad
+        assert b"invalid locus" in L.hlac_last_error()
