@@ -1,4 +1,6 @@
 // C ABI: error state, index construction, host helpers (include/hlacount.h). Product code.
+#include <cub/device/device_radix_sort.cuh>
+
 #include <cstring>
 #include <memory>
 
@@ -18,6 +20,25 @@ void set_last_error(const std::string& m) { g_last_error = m; }
   catch (const hlac::Error& e) { hlac::set_last_error(e.what()); return e.code; }           \
   catch (const std::exception& e) { hlac::set_last_error(e.what()); return HLAC_ERR_STATE; } \
   return HLAC_OK;
+
+namespace {
+// build_index's dominant step on the device: stable radix sort of the (k-mer, payload) occurrence pairs
+void device_sort_pairs(uint64_t* keys, uint64_t* vals, size_t n) {
+  DevBuf<uint64_t> k0, k1, v0, v1; DevBuf<uint8_t> tmp;
+  k0.upload(keys, n); v0.upload(vals, n); k1.reserve(n); v1.reserve(n);
+  size_t bytes = 0;
+  HLAC_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, k0.p, k1.p, v0.p, v1.p, (uint64_t)n, 0, 2 * K));
+  tmp.reserve(bytes);
+  HLAC_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, k0.p, k1.p, v0.p, v1.p, (uint64_t)n, 0, 2 * K));
+  HLAC_CUDA(cudaMemcpy(keys, k1.p, n * 8, cudaMemcpyDeviceToHost));
+  HLAC_CUDA(cudaMemcpy(vals, v1.p, n * 8, cudaMemcpyDeviceToHost));
+}
+HostIndex::PairSorter sorter_for(int device) {
+  int ndev = 0;
+  if (device < 0 || cudaGetDeviceCount(&ndev) != cudaSuccess || device >= ndev) return nullptr;
+  return device_sort_pairs;
+}
+}  // namespace
 
 extern "C" {
 
@@ -50,7 +71,8 @@ int hlac_index_from_fasta(const char* fasta_path, const char* allele_status, int
   std::vector<Bases> seqs; std::vector<std::string> names;
   read_hla_cds(fasta_path, keep, allele_status != nullptr, seqs, names);
   auto ix = std::make_unique<hlac_index>();
-  HostIndex::build(seqs, names, ix->host);
+  { std::unique_ptr<DeviceGuard> g; if (sorter_for(device)) g = std::make_unique<DeviceGuard>(device);
+    HostIndex::build(seqs, names, ix->host, sorter_for(device)); }
   ix->upload(device);
   *out = ix.release();
   HLAC_API_END
@@ -68,7 +90,8 @@ int hlac_index_from_sequences(const uint64_t* packed, const uint64_t* seq_word_s
     nm[i] = names[i];
   }
   auto ix = std::make_unique<hlac_index>();
-  HostIndex::build(seqs, nm, ix->host);
+  { std::unique_ptr<DeviceGuard> g; if (sorter_for(device)) g = std::make_unique<DeviceGuard>(device);
+    HostIndex::build(seqs, nm, ix->host, sorter_for(device)); }
   ix->upload(device);
   *out = ix.release();
   HLAC_API_END

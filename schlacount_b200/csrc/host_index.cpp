@@ -92,16 +92,16 @@ void HostIndex::load_idx(const std::string& path, HostIndex& ix) {
 // build_index::<Kmer24> [EXT] — stranded k=24 coloured compacted de Bruijn graph: a node is a
 // maximal path whose interior links have a unique right extension, a unique left extension on the successor, and
 // one colour. Sort-based: one record per k-mer occurrence, sorted by (k-mer, tx), then grouped.
-void HostIndex::build(const std::vector<Bases>& seqs, const std::vector<std::string>& names, HostIndex& ix) {
+void HostIndex::build(const std::vector<Bases>& seqs, const std::vector<std::string>& names, HostIndex& ix, PairSorter sorter) {
   const bool dbg = getenv("HLAC_DEBUG_TIMING") != nullptr; auto t_last = std::chrono::steady_clock::now();
   auto tick = [&](const char* what) { if (dbg) { auto t = std::chrono::steady_clock::now(); fprintf(stderr, "[hlac timing] build: %-24s %.3f s\n", what, std::chrono::duration<double>(t - t_last).count()); t_last = t; } };
   ix = HostIndex();
   ix.tx_names = names;
-  struct Occ { uint64_t kmer; uint32_t tx; uint8_t l, r; };
-  std::vector<Occ> occ;
+  // one (k-mer, payload) pair per occurrence; payload = tx << 16 | left-ext mask << 8 | right-ext mask
+  std::vector<uint64_t> okey, oval;
   size_t total = 0;
   for (auto& s : seqs) if (s.size() >= (size_t)K) total += s.size() - K + 1;
-  occ.reserve(total);
+  okey.reserve(total); oval.reserve(total);
   for (uint32_t t = 0; t < seqs.size(); t++) {
     const Bases& s = seqs[t];
     if (s.size() < (size_t)K) continue;
@@ -109,23 +109,25 @@ void HostIndex::build(const std::vector<Bases>& seqs, const std::vector<std::str
     for (int i = 0; i < K - 1; i++) v = (v << 2) | s[i];
     for (size_t i = 0; i + K <= s.size(); i++) {
       v = ((v << 2) | s[i + K - 1]) & KMER_MASK;
-      occ.push_back({v, t, uint8_t(i > 0 ? 1u << s[i - 1] : 0), uint8_t(i + K < s.size() ? 1u << s[i + K] : 0)});
+      okey.push_back(v);
+      oval.push_back(((uint64_t)t << 16) | (uint64_t)(i > 0 ? 1u << s[i - 1] : 0) << 8 | (uint64_t)(i + K < s.size() ? 1u << s[i + K] : 0));
     }
   }
   tick("enumerate k-mers");
-  {
-    // stable LSD radix sort on the 48-bit k-mer, 3 passes of 16 bits; occurrences were generated in ascending tx
-    // order, so stability leaves every k-mer's tx list sorted (5 s of std::sort -> ~0.6 s at 33 M occurrences)
-    std::vector<Occ> tmp(occ.size());
+  // stable sort by k-mer: occurrences were generated in ascending tx order, so stability leaves every k-mer's tx list
+  // sorted. On a device-resident build the caller supplies a GPU radix sort; otherwise an LSD radix sort on the host.
+  if (sorter && total >= (1u << 16)) sorter(okey.data(), oval.data(), total);
+  else {
+    std::vector<uint64_t> tk(total), tv(total);
     std::vector<size_t> cnt(1 << 16);
     for (int pass = 0; pass < 3; pass++) {
       const int sh = 16 * pass;
       std::fill(cnt.begin(), cnt.end(), 0);
-      for (const Occ& o : occ) cnt[(o.kmer >> sh) & 0xFFFF]++;
+      for (size_t i = 0; i < total; i++) cnt[(okey[i] >> sh) & 0xFFFF]++;
       size_t run = 0;
       for (size_t& c : cnt) { const size_t k = c; c = run; run += k; }
-      for (const Occ& o : occ) tmp[cnt[(o.kmer >> sh) & 0xFFFF]++] = o;
-      occ.swap(tmp);
+      for (size_t i = 0; i < total; i++) { const size_t d = cnt[(okey[i] >> sh) & 0xFFFF]++; tk[d] = okey[i]; tv[d] = oval[i]; }
+      okey.swap(tk); oval.swap(tv);
     }
   }
   tick("sort occurrences");
@@ -135,12 +137,13 @@ void HostIndex::build(const std::vector<Bases>& seqs, const std::vector<std::str
   std::unordered_map<uint64_t, std::vector<uint32_t>> by_hash;   // hash(tx list) -> candidate colour ids
   ix.col_off.assign(1, 0);
   std::vector<uint32_t> txl;
-  for (size_t i = 0; i < occ.size();) {
+  for (size_t i = 0; i < total;) {
     size_t j = i; uint8_t l = 0, r = 0; txl.clear();
     uint64_t h = 0xcbf29ce484222325ULL;
-    while (j < occ.size() && occ[j].kmer == occ[i].kmer) {
-      l |= occ[j].l; r |= occ[j].r;
-      if (txl.empty() || txl.back() != occ[j].tx) { txl.push_back(occ[j].tx); h = (h ^ occ[j].tx) * 0x100000001b3ULL; h ^= h >> 29; }
+    while (j < total && okey[j] == okey[i]) {
+      const uint32_t tx = (uint32_t)(oval[j] >> 16);
+      l |= (uint8_t)(oval[j] >> 8); r |= (uint8_t)oval[j];
+      if (txl.empty() || txl.back() != tx) { txl.push_back(tx); h = (h ^ tx) * 0x100000001b3ULL; h ^= h >> 29; }
       j++;
     }
     uint32_t cid = NONE32;
@@ -155,10 +158,10 @@ void HostIndex::build(const std::vector<Bases>& seqs, const std::vector<std::str
       ix.col_off.push_back(ix.col_tx.size());
       cand.push_back(cid);
     }
-    uk.push_back(occ[i].kmer); ul.push_back(l); ur.push_back(r); ucol.push_back(cid);
+    uk.push_back(okey[i]); ul.push_back(l); ur.push_back(r); ucol.push_back(cid);
     i = j;
   }
-  std::vector<Occ>().swap(occ);
+  std::vector<uint64_t>().swap(okey); std::vector<uint64_t>().swap(oval);
   tick("group + intern colours");
 
   const size_t n = uk.size();

@@ -39,7 +39,9 @@ struct HostIndex {
   void finalize();                                // adjacency, dictionary, l-mer bitmap
 
   static void load_idx(const std::string& path, HostIndex& out);   // bincode (Appendix B)
-  static void build(const std::vector<Bases>& seqs, const std::vector<std::string>& names, HostIndex& out);  // build_index
+  // stable sort of (key, value) pairs by key; build() uses it for the k-mer occurrences when given (a device sort)
+  using PairSorter = void (*)(uint64_t* keys, uint64_t* vals, size_t n);
+  static void build(const std::vector<Bases>& seqs, const std::vector<std::string>& names, HostIndex& out, PairSorter sorter = nullptr);  // build_index
 };
 
 // multiplicative hash shared by host build and device probe
