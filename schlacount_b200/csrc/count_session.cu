@@ -543,7 +543,7 @@ int hlac_count_reserve(hlac_count* s, uint64_t total_reads) try {
   s->keys.reserve(total_reads, s->stream, true, s->reads_pushed);
   s->keys_sorted.reserve(total_reads, s->stream);
   return HLAC_OK;
-} catch (const Error& e) { set_last_error(e.what()); return e.code; }
+} catch (const Error& e) { set_last_error(e.what()); return e.code; } catch (const std::exception& e) { set_last_error(e.what()); return HLAC_ERR_STATE; }
 
 static void validate_batch(const hlac_batch* b) {
   if (b->n && (!b->seq || !b->len || !b->cell || !b->umi || !b->flags)) throw Error(HLAC_ERR_ARG, "batch has a null array");
@@ -556,7 +556,7 @@ int hlac_count_push_device(hlac_count* s, const hlac_batch* b) try {
   DeviceGuard g(s->device);
   s->launch_map(*b);
   return HLAC_OK;
-} catch (const Error& e) { set_last_error(e.what()); return e.code; }
+} catch (const Error& e) { set_last_error(e.what()); return e.code; } catch (const std::exception& e) { set_last_error(e.what()); return HLAC_ERR_STATE; }
 
 int hlac_count_push(hlac_count* s, const hlac_batch* b) try {
   if (!s || !b) throw Error(HLAC_ERR_ARG, "null argument");
@@ -581,7 +581,7 @@ int hlac_count_push(hlac_count* s, const hlac_batch* b) try {
   s->launch_map(d);
   HLAC_CUDA(cudaEventRecord(st.consumed, s->stream));
   return HLAC_OK;
-} catch (const Error& e) { set_last_error(e.what()); return e.code; }
+} catch (const Error& e) { set_last_error(e.what()); return e.code; } catch (const std::exception& e) { set_last_error(e.what()); return HLAC_ERR_STATE; }
 
 int hlac_count_sync(hlac_count* s) try {
   if (!s) throw Error(HLAC_ERR_ARG, "null session");
@@ -589,7 +589,7 @@ int hlac_count_sync(hlac_count* s) try {
   if (s->copy_stream) HLAC_CUDA(cudaStreamSynchronize(s->copy_stream));
   HLAC_CUDA(cudaStreamSynchronize(s->stream));
   return HLAC_OK;
-} catch (const Error& e) { set_last_error(e.what()); return e.code; }
+} catch (const Error& e) { set_last_error(e.what()); return e.code; } catch (const std::exception& e) { set_last_error(e.what()); return HLAC_ERR_STATE; }
 
 int hlac_count_set_stream(hlac_count* s, void* cuda_stream) try {
   if (!s) throw Error(HLAC_ERR_ARG, "null session");
@@ -600,7 +600,7 @@ int hlac_count_set_stream(hlac_count* s, void* cuda_stream) try {
   s->stream = (cudaStream_t)cuda_stream;
   s->own_stream = false;
   return HLAC_OK;
-} catch (const Error& e) { set_last_error(e.what()); return e.code; }
+} catch (const Error& e) { set_last_error(e.what()); return e.code; } catch (const std::exception& e) { set_last_error(e.what()); return HLAC_ERR_STATE; }
 
 int hlac_count_record_codes(hlac_count* s, int on) {
   if (!s) { set_last_error("null session"); return HLAC_ERR_ARG; }
@@ -616,7 +616,7 @@ int hlac_count_last_codes(hlac_count* s, uint8_t* codes, uint64_t n) try {
   HLAC_CUDA(cudaMemcpyAsync(codes, s->codes.p, n, cudaMemcpyDeviceToHost, s->stream));
   HLAC_CUDA(cudaStreamSynchronize(s->stream));
   return HLAC_OK;
-} catch (const Error& e) { set_last_error(e.what()); return e.code; }
+} catch (const Error& e) { set_last_error(e.what()); return e.code; } catch (const std::exception& e) { set_last_error(e.what()); return HLAC_ERR_STATE; }
 
 int hlac_count_reduce(hlac_count* s, uint32_t** dense_device, uint64_t* n_elems) try {
   if (!s) throw Error(HLAC_ERR_ARG, "null session");
@@ -651,7 +651,7 @@ int hlac_count_reduce(hlac_count* s, uint32_t** dense_device, uint64_t* n_elems)
   if (n_elems) *n_elems = nd;
   HLAC_CUDA(cudaStreamSynchronize(s->stream));
   return HLAC_OK;
-} catch (const Error& e) { set_last_error(e.what()); return e.code; }
+} catch (const Error& e) { set_last_error(e.what()); return e.code; } catch (const std::exception& e) { set_last_error(e.what()); return HLAC_ERR_STATE; }
 
 int hlac_count_entries(hlac_count* s, hlac_coo* out, hlac_metrics* metrics) try {
   if (!s) throw Error(HLAC_ERR_ARG, "null session");
@@ -699,7 +699,7 @@ int hlac_count_entries(hlac_count* s, hlac_coo* out, hlac_metrics* metrics) try 
     out->row = s->coo_host; out->col = s->coo_host ? s->coo_host + nnz : nullptr; out->val = s->coo_host ? s->coo_host + 2 * nnz : nullptr;
   }
   return HLAC_OK;
-} catch (const Error& e) { set_last_error(e.what()); return e.code; }
+} catch (const Error& e) { set_last_error(e.what()); return e.code; } catch (const std::exception& e) { set_last_error(e.what()); return HLAC_ERR_STATE; }
 
 int hlac_count_finish(hlac_count* s, hlac_coo* out, hlac_metrics* metrics) {
   int rc = hlac_count_reduce(s, nullptr, nullptr);
@@ -712,7 +712,7 @@ int hlac_count_reset(hlac_count* s) try {
   DeviceGuard g(s->device);
   s->reset();
   return HLAC_OK;
-} catch (const Error& e) { set_last_error(e.what()); return e.code; }
+} catch (const Error& e) { set_last_error(e.what()); return e.code; } catch (const std::exception& e) { set_last_error(e.what()); return HLAC_ERR_STATE; }
 
 int hlac_coo_free(hlac_coo* c) {
   if (c) { if (!c->borrowed) { free(c->row); free(c->col); free(c->val); } c->row = c->col = c->val = nullptr; c->n = 0; }
@@ -726,7 +726,7 @@ int hlac_count_timing(hlac_count* s, float ms[4], uint64_t* launches) try {
   if (ms) for (int i = 0; i < 4; i++) ms[i] = s->ms[i];
   if (launches) *launches = s->launches;
   return HLAC_OK;
-} catch (const Error& e) { set_last_error(e.what()); return e.code; }
+} catch (const Error& e) { set_last_error(e.what()); return e.code; } catch (const std::exception& e) { set_last_error(e.what()); return HLAC_ERR_STATE; }
 
 // seed-filter counters since the last reset: l-mer bitmap tests and dictionary probes (SURVEY.md §8d "probes/read")
 int hlac_count_probe_stats(hlac_count* s, uint64_t* bitmap_tests, uint64_t* dict_probes) try {
@@ -738,6 +738,6 @@ int hlac_count_probe_stats(hlac_count* s, uint64_t* bitmap_tests, uint64_t* dict
   if (bitmap_tests) *bitmap_tests = c[0];
   if (dict_probes) *dict_probes = c[1];
   return HLAC_OK;
-} catch (const Error& e) { set_last_error(e.what()); return e.code; }
+} catch (const Error& e) { set_last_error(e.what()); return e.code; } catch (const std::exception& e) { set_last_error(e.what()); return HLAC_ERR_STATE; }
 
 }  // extern "C"

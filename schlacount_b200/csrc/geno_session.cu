@@ -602,7 +602,7 @@ int hlac_geno_last_cov(hlac_geno* s, uint32_t* cov, uint64_t n) try {
   HLAC_CUDA(cudaMemcpyAsync(cov, s->cov.p, n * 4, cudaMemcpyDeviceToHost, s->stream));
   HLAC_CUDA(cudaStreamSynchronize(s->stream));
   return HLAC_OK;
-} catch (const Error& e) { set_last_error(e.what()); return e.code; }
+} catch (const Error& e) { set_last_error(e.what()); return e.code; } catch (const std::exception& e) { set_last_error(e.what()); return HLAC_ERR_STATE; }
 
 static double now_s() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + ts.tv_nsec * 1e-9; }
 #define HLAC_TICK(label) do { if (dbg) { double t_ = now_s(); fprintf(stderr, "[hlac timing] %-28s %.3f s\n", label, t_ - t_last); t_last = t_; } } while (0)
@@ -921,7 +921,7 @@ int hlac_geno_read_class_ids(hlac_geno* s, uint32_t* ids, uint64_t n) try {
   HLAC_CUDA(cudaStreamSynchronize(s->stream));
   for (uint64_t i = 0; i < n; i++) if (ids[i] != NONE32) ids[i] = s->class_of_path[ids[i]];
   return HLAC_OK;
-} catch (const Error& e) { set_last_error(e.what()); return e.code; }
+} catch (const Error& e) { set_last_error(e.what()); return e.code; } catch (const std::exception& e) { set_last_error(e.what()); return HLAC_ERR_STATE; }
 
 int hlac_class_tables_free(hlac_class_tables* t) {
   if (t) {
@@ -941,7 +941,7 @@ int hlac_geno_timing(hlac_geno* s, float ms[4], uint64_t* launches) try {
   if (ms) for (int i = 0; i < 4; i++) ms[i] = s->ms[i];
   if (launches) *launches = s->launches;
   return HLAC_OK;
-} catch (const Error& e) { set_last_error(e.what()); return e.code; }
+} catch (const Error& e) { set_last_error(e.what()); return e.code; } catch (const std::exception& e) { set_last_error(e.what()); return HLAC_ERR_STATE; }
 
 int hlac_geno_stats(hlac_geno* s, uint64_t* some_aln, uint64_t* long_aln, uint64_t* n_paths, uint64_t* bitmap_tests, uint64_t* dict_probes) try {
   if (!s) throw Error(HLAC_ERR_ARG, "null session");
@@ -955,6 +955,6 @@ int hlac_geno_stats(hlac_geno* s, uint64_t* some_aln, uint64_t* long_aln, uint64
   if (bitmap_tests) *bitmap_tests = c[2];
   if (dict_probes) *dict_probes = c[3];
   return HLAC_OK;
-} catch (const Error& e) { set_last_error(e.what()); return e.code; }
+} catch (const Error& e) { set_last_error(e.what()); return e.code; } catch (const std::exception& e) { set_last_error(e.what()); return HLAC_ERR_STATE; }
 
 }  // extern "C"
