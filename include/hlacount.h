@@ -204,6 +204,11 @@ int hlac_paths_merge(const hlac_paths* parts, uint32_t n_parts, hlac_paths* out)
 int hlac_geno_import_paths(hlac_geno*, const hlac_paths* merged);
 int hlac_paths_free(hlac_paths*);
 int hlac_class_tables_free(hlac_class_tables*);
+/* lean mode: hlac_geno_finish leaves counts_reads on the device (reads_off / reads_tx / reads_cnt are NULL,
+ * n_read_classes is still reported); counts_umi, reads_explained and nreads are produced as usual. The reference's
+ * EqClassCounts.counts_reads is only consumed by pair_reads_explained (em.rs:36-44), which hlac_geno_call evaluates
+ * on the device-resident class vectors. */
+int hlac_geno_set_lean(hlac_geno*, int on);
 int hlac_geno_timing(hlac_geno*, float ms[4], uint64_t* launches);
 
 /* squarem(&eq_class_counts) (em.rs:232-311) on the device, f64. */
@@ -223,6 +228,8 @@ typedef struct {
 } hlac_calls;
 int hlac_call_genotypes(const hlac_index* idx, const hlac_class_tables* t, const double* theta, hlac_calls* out);
 int hlac_calls_free(hlac_calls*);
+/* the same caller on a finished session (works with lean tables): pair overlaps from the class vectors on the device */
+int hlac_geno_call(hlac_geno*, const hlac_class_tables* t, const double* theta, hlac_calls* out);
 
 /* ---- the three reference entry points, whole (host driver in C++; BAM/FASTA I/O on the host) ---------------------- */
 /* mapping_wrapper(hla_index, outdir, bam, locus, use_unmapped) -> counts file path (mapping.rs:310-316).

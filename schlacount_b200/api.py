@@ -241,7 +241,7 @@ def _tables_to_py(t):
             out[tuple(tx[q] for q in range(off[c], off[c + 1]))] = cnt[c]
         return out
     reads_list = [(tuple(t.reads_tx[q] for q in range(t.reads_off[c], t.reads_off[c + 1])), t.reads_cnt[c])
-                  for c in range(t.n_read_classes)]
+                  for c in range(t.n_read_classes)] if t.reads_off else []
     return dict(nitems=t.nitems, nreads=t.nreads, reads_classes=reads_list,
                 counts_reads=dict(reads_list), counts_umi=csr(t.n_umi_classes, t.umi_off, t.umi_tx, t.umi_cnt),
                 reads_explained=[t.reads_explained[i] for i in range(t.nitems)])
@@ -250,11 +250,14 @@ def _tables_to_py(t):
 class GenoSession:
     """hlac_geno: one mapping_wrapper run (src/mapping.rs:310-405) and its EqClassDb."""
 
-    def __init__(self, index, record_reads=False):
+    def __init__(self, index, record_reads=False, lean=False):
         self.h = C.c_void_p()
         self.index = index
         check(lib().hlac_geno_new(index.h, C.byref(self.h)))
         self.tables = None
+        self.lean = lean
+        if lean:
+            check(lib().hlac_geno_set_lean(self.h, C.c_int(1)))
         if record_reads:
             check(lib().hlac_geno_record_reads(self.h, C.c_int(1)))
 
@@ -361,7 +364,7 @@ class GenoSession:
         if raw:
             t = self.tables
             return dict(nitems=t.nitems, nreads=t.nreads, n_read_classes=t.n_read_classes, n_umi_classes=t.n_umi_classes,
-                        reads_nnz=t.reads_off[t.n_read_classes] if t.n_read_classes else 0,
+                        reads_nnz=t.reads_off[t.n_read_classes] if (t.n_read_classes and t.reads_off) else 0,
                         umi_nnz=t.umi_off[t.n_umi_classes] if t.n_umi_classes else 0)
         return _tables_to_py(self.tables)
 
@@ -387,10 +390,15 @@ class GenoSession:
         check(lib().hlac_squarem(C.byref(self.tables), C.c_int(device), _vp(theta), C.byref(it)))
         return theta, it.value
 
-    def call(self, theta):
+    def call(self, theta, on_device=None):
+        """the caller (em.rs:361-434). on_device=True (default in lean mode) evaluates pair overlaps on the class vectors
+        still resident on the GPU (hlac_geno_call); otherwise from the host tables (hlac_call_genotypes)."""
         theta = np.ascontiguousarray(theta, dtype=np.float64)
         c = _lib.Calls()
-        check(lib().hlac_call_genotypes(self.index.h, C.byref(self.tables), _vp(theta), C.byref(c)))
+        if on_device if on_device is not None else self.lean:
+            check(lib().hlac_geno_call(self.h, C.byref(self.tables), _vp(theta), C.byref(c)))
+        else:
+            check(lib().hlac_call_genotypes(self.index.h, C.byref(self.tables), _vp(theta), C.byref(c)))
         out = dict(called=[c.called[i] for i in range(c.n_called)],
                    weights=[(c.w_tx[i], c.w_em[i], c.w_frac[i]) for i in range(c.n_weights)],
                    pairs=[(c.p_a[i], c.p_b[i], c.p_frac[i]) for i in range(c.n_pairs)])

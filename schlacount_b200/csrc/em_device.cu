@@ -12,6 +12,7 @@
 #include <set>
 #include <vector>
 
+#include "caller.hpp"
 #include "device_index.hpp"
 
 using namespace hlac;
@@ -216,35 +217,24 @@ int hlac_squarem(const hlac_class_tables* t, int device, double* theta_out, uint
   return HLAC_OK;
 } catch (const Error& e) { set_last_error(e.what()); return e.code; } catch (const std::exception& e) { set_last_error(e.what()); return HLAC_ERR_STATE; }
 
-// The caller (em.rs:361-434). Host logic over nitems weights and the counts_reads table.
+// The caller (em.rs:361-434) on explicit tables: pair_reads_explained from the counts_reads CSR.
 int hlac_call_genotypes(const hlac_index* idx, const hlac_class_tables* t, const double* theta, hlac_calls* out) try {
   if (!idx || !t || !theta || !out) throw Error(HLAC_ERR_ARG, "null argument");
   const auto& names = idx->host.tx_names;
   if (names.size() != t->nitems) throw Error(HLAC_ERR_ARG, "class tables do not match the index");
-  struct W { uint32_t i; double w; std::string gene; uint64_t exp; };
-  std::vector<W> wn;
-  for (uint32_t i = 0; i < t->nitems; i++) wn.push_back({i, theta[i], names[i].substr(0, names[i].find('*')), t->reads_explained[i]});
-  std::stable_sort(wn.begin(), wn.end(), [](const W& a, const W& b) { return -a.w < -b.w; });        // em.rs:370
-  std::stable_sort(wn.begin(), wn.end(), [](const W& a, const W& b) { return a.gene < b.gene; });    // em.rs:371
+  if (t->n_read_classes && !t->reads_off) throw Error(HLAC_ERR_ARG, "tables were produced in lean mode (no counts_reads): use hlac_geno_call on the session");
+  const Ranked rk = rank_alleles(names, t->nitems, t->reads_explained, theta);
   // pair_reads_explained (em.rs:36-44) = reads in classes containing a or b. The reference rescans every class per
   // pair; here one pass builds, for the few candidate alleles only (<= WEIGHTS_TO_OUTPUT per gene), the list of
-  // classes containing each, and a pair is explained[a] + explained[b] - (reads in classes containing both).
-  std::vector<int32_t> cand_of(t->nitems, -1); std::vector<uint32_t> cands;
-  for (size_t s = 0; s < wn.size();) {
-    size_t e = s; while (e < wn.size() && wn[e].gene == wn[s].gene) e++;
-    size_t k = 0;
-    for (size_t q = s; q < e && wn[q].exp > MIN_READS_CALL && k < WEIGHTS_TO_OUTPUT; q++, k++) { cand_of[wn[q].i] = (int32_t)cands.size(); cands.push_back(wn[q].i); }
-    s = e;
-  }
-  std::vector<std::vector<uint32_t>> cls_of(cands.size());
-  for (uint64_t c = 0; c < t->n_read_classes; c++) {
+  // classes containing each, and a pair is the read total over the union of the two ascending class lists.
+  std::vector<std::vector<uint32_t>> cls_of(rk.cands.size());
+  for (uint64_t c = 0; c < t->n_read_classes; c++)
     for (uint64_t q = t->reads_off[c]; q < t->reads_off[c + 1]; q++) {
-      const int32_t k = cand_of[t->reads_tx[q]];
+      const int32_t k = rk.cand_of[t->reads_tx[q]];
       if (k >= 0 && (cls_of[k].empty() || cls_of[k].back() != (uint32_t)c)) cls_of[k].push_back((uint32_t)c);
     }
-  }
   auto pair_explained = [&](uint32_t a, uint32_t b) {
-    const auto& la = cls_of[cand_of[a]]; const auto& lb = cls_of[cand_of[b]];
+    const auto& la = cls_of[rk.cand_of[a]]; const auto& lb = cls_of[rk.cand_of[b]];
     uint64_t e = 0; size_t i = 0, j = 0;
     while (i < la.size() || j < lb.size()) {   // union of two ascending class lists
       uint32_t c;
@@ -255,42 +245,7 @@ int hlac_call_genotypes(const hlac_index* idx, const hlac_class_tables* t, const
     }
     return (uint32_t)e;
   };
-  const double nreads = (double)t->nreads;
-  std::set<uint32_t> called;
-  std::vector<uint32_t> wtx, pa, pb; std::vector<double> wem, wfr, pfr;
-  for (size_t s = 0; s < wn.size();) {
-    size_t e = s; while (e < wn.size() && wn[e].gene == wn[s].gene) e++;
-    size_t written = 0;
-    for (size_t q = s; q < e; q++) {
-      if (wn[q].exp <= MIN_READS_CALL) break;
-      wtx.push_back(wn[q].i); wem.push_back(wn[q].w); wfr.push_back((double)(uint32_t)wn[q].exp / nreads);
-      if (++written == WEIGHTS_TO_OUTPUT) break;
-    }
-    if (written) {
-      struct P { uint32_t a, b; double joint, single; };
-      std::vector<P> pairs; bool stop = false;
-      for (size_t i = 0; i + 1 < written && !stop; i++)
-        for (size_t j = i + 1; j < written; j++) {
-          const uint32_t ex = pair_explained(wn[s + i].i, wn[s + j].i);
-          if (ex > MIN_READS_CALL) pairs.push_back({wn[s + i].i, wn[s + j].i, (double)ex / nreads, (double)(uint32_t)std::max(wn[s + i].exp, wn[s + j].exp) / nreads});
-          else { stop = true; break; }
-        }
-      if (!pairs.empty()) {
-        std::stable_sort(pairs.begin(), pairs.end(), [](const P& a, const P& b) { return -a.joint < -b.joint; });
-        for (size_t q = 0; q < std::min<size_t>(PAIRS_TO_OUTPUT, pairs.size()); q++) { pa.push_back(pairs[q].a); pb.push_back(pairs[q].b); pfr.push_back(pairs[q].joint); }
-        if (pairs[0].joint * HOMOZYGOUS_TH > pairs[0].joint - pairs[0].single) { called.insert(pairs[0].a); called.insert(pairs[0].b); }
-        else called.insert(wn[s].i);
-      } else called.insert(wn[s].i);
-    }
-    s = e;
-  }
-  memset(out, 0, sizeof *out);
-  auto dup32 = [](const std::vector<uint32_t>& v) { uint32_t* p = (uint32_t*)malloc(std::max<size_t>(v.size(), 1) * 4); if (!v.empty()) memcpy(p, v.data(), v.size() * 4); return p; };
-  auto dupd = [](const std::vector<double>& v) { double* p = (double*)malloc(std::max<size_t>(v.size(), 1) * 8); if (!v.empty()) memcpy(p, v.data(), v.size() * 8); return p; };
-  std::vector<uint32_t> cv(called.begin(), called.end());
-  out->n_called = (uint32_t)cv.size(); out->called = dup32(cv);
-  out->n_weights = (uint32_t)wtx.size(); out->w_tx = dup32(wtx); out->w_em = dupd(wem); out->w_frac = dupd(wfr);
-  out->n_pairs = (uint32_t)pa.size(); out->p_a = dup32(pa); out->p_b = dup32(pb); out->p_frac = dupd(pfr);
+  call_from_ranked(rk, t->nreads, pair_explained, out);
   return HLAC_OK;
 } catch (const Error& e) { set_last_error(e.what()); return e.code; } catch (const std::exception& e) { set_last_error(e.what()); return HLAC_ERR_STATE; }
 

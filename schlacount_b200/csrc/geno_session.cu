@@ -31,6 +31,7 @@
 #include <unordered_map>
 #include <vector>
 
+#include "caller.hpp"
 #include "device_index.hpp"
 
 using namespace hlac;
@@ -372,6 +373,22 @@ __global__ void k_gather_classes(const uint32_t* __restrict__ vec, const uint64_
   for (uint64_t k = threadIdx.x; k < len; k += blockDim.x) out[b + k] = vec[a + k];
 }
 
+// per class: which of the (<= 128) candidate alleles it contains -> 128-bit mask; one warp per class
+__global__ void k_class_cand_mask(const uint32_t* __restrict__ vec, const uint64_t* __restrict__ src_off, const uint32_t* __restrict__ len,
+                                  uint32_t n, const uint8_t* __restrict__ cand_idx, uint64_t* mask) {
+  const uint32_t c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned lane = threadIdx.x & 31;
+  if (c >= n) return;
+  const uint32_t* v = vec + src_off[c];
+  uint64_t lo = 0, hi = 0;
+  for (uint32_t k = lane; k < len[c]; k += 32) {
+    const uint8_t ci = cand_idx[v[k]];
+    if (ci < 64) lo |= 1ull << ci; else if (ci < 128) hi |= 1ull << (ci - 64);
+  }
+  for (int o = 16; o > 0; o >>= 1) { lo |= __shfl_down_sync(0xFFFFFFFFu, lo, o); hi |= __shfl_down_sync(0xFFFFFFFFu, hi, o); }
+  if (lane == 0) { mask[2 * (size_t)c] = lo; mask[2 * (size_t)c + 1] = hi; }
+}
+
 // reads_explained[t] += reads of every class whose (sorted) member list is colour list `col` (mapping.rs:196-198)
 __global__ void k_reads_explained(const uint32_t* __restrict__ cols, const unsigned long long* __restrict__ totals, uint32_t n,
                                   const uint64_t* __restrict__ col_off, const uint32_t* __restrict__ col_tx, unsigned long long* expl) {
@@ -419,7 +436,8 @@ struct hlac_geno {
   DevBuf<unsigned long long> ctr;   // [0] n_entries [1] arena cursor [2] rec cursor [3] collisions [4..7] stats
   // records of counted reads
   DevBuf<uint64_t> rec_key; DevBuf<uint32_t> rec_path;
-  DevBuf<uint32_t> read_path; bool record_reads = false;   // optional: path id of every read pushed
+  DevBuf<uint32_t> read_path; bool record_reads = false;
+  bool lean = false;   // finish does not materialise counts_reads on the host (hlac_geno_set_lean)   // optional: path id of every read pushed
   uint64_t reads_pushed = 0, last_n = 0, n_entries = 0, arena_used = 0, n_records_ub = 0;
   // finish results kept for hlac_geno_read_class_ids
   std::vector<uint32_t> class_of_path;
@@ -745,15 +763,19 @@ int hlac_geno_finish_end(hlac_geno* s, hlac_class_tables* out) try {
   out->reads_off = (uint64_t*)calloc(nc + 1, 8); out->reads_cnt = (uint32_t*)calloc(std::max<size_t>(nc, 1), 4);
   for (size_t c = 0; c < nc; c++) { out->reads_off[c + 1] = out->reads_off[c] + s->fin_cls_len[c]; out->reads_cnt[c] = cls_reads[c]; }
   const uint64_t ntx = out->reads_off[nc];
+  if (s->lean) { free(out->reads_off); free(out->reads_cnt); out->reads_off = nullptr; out->reads_cnt = nullptr; }
   // large tables go to pinned host memory: a pageable 4 GB D2H was measured at < 1 GB/s (page faults under the DMA staging)
-  if (ntx * 4 >= (64ull << 20)) HLAC_CUDA(cudaHostAlloc((void**)&out->reads_tx, ntx * 4, cudaHostAllocDefault));
+  if (s->lean) out->reads_tx = nullptr;
+  else if (ntx * 4 >= (64ull << 20)) HLAC_CUDA(cudaHostAlloc((void**)&out->reads_tx, ntx * 4, cudaHostAllocDefault));
   else out->reads_tx = (uint32_t*)malloc(std::max<uint64_t>(ntx, 1) * 4);
   if (nc) {
     DevBuf<uint64_t> d_src, d_dst; DevBuf<uint32_t> d_out;
-    d_src.upload(s->fin_src_off.data(), nc, s->stream); d_dst.upload(out->reads_off, nc + 1, s->stream); d_out.reserve(std::max<uint64_t>(ntx, 1), s->stream);
-    k_gather_classes<<<(unsigned)nc, 256, 0, s->stream>>>(s->fin_dvec.p, d_src.p, d_dst.p, d_out.p);
-    HLAC_CUDA(cudaGetLastError());
-    HLAC_CUDA(cudaMemcpyAsync(out->reads_tx, d_out.p, ntx * 4, cudaMemcpyDeviceToHost, s->stream));
+    if (!s->lean) {
+      d_src.upload(s->fin_src_off.data(), nc, s->stream); d_dst.upload(out->reads_off, nc + 1, s->stream); d_out.reserve(std::max<uint64_t>(ntx, 1), s->stream);
+      k_gather_classes<<<(unsigned)nc, 256, 0, s->stream>>>(s->fin_dvec.p, d_src.p, d_dst.p, d_out.p);
+      HLAC_CUDA(cudaGetLastError());
+      HLAC_CUDA(cudaMemcpyAsync(out->reads_tx, d_out.p, ntx * 4, cudaMemcpyDeviceToHost, s->stream));
+    }
     // reads_explained (mapping.rs:196-198): per colour totals, then one pass over the used colour lists on the device
     std::map<uint32_t, unsigned long long> per_colour;
     for (size_t c = 0; c < nc; c++) per_colour[s->fin_cls_colour[c]] += cls_reads[c];
@@ -800,6 +822,48 @@ int hlac_geno_finish(hlac_geno* s, hlac_class_tables* out) {
   if (rc != HLAC_OK) return rc;
   return hlac_geno_finish_end(s, out);
 }
+
+int hlac_geno_set_lean(hlac_geno* s, int on) {
+  if (!s) { set_last_error("null session"); return HLAC_ERR_ARG; }
+  s->lean = on != 0;
+  return HLAC_OK;
+}
+
+// The caller (em.rs:361-434) on a finished session: pair_reads_explained (em.rs:36-44) is computed from the class
+// vectors that are still on the device (one warp per class marks which candidate alleles it contains), so it also
+// works in lean mode where counts_reads never reaches the host.
+int hlac_geno_call(hlac_geno* s, const hlac_class_tables* t, const double* theta, hlac_calls* out) try {
+  if (!s || !t || !theta || !out) throw Error(HLAC_ERR_ARG, "null argument");
+  if (!s->finished) throw Error(HLAC_ERR_STATE, "hlac_geno_finish has not run");
+  DeviceGuard g(s->device);
+  const auto& names = s->idx->host.tx_names;
+  if (names.size() != t->nitems) throw Error(HLAC_ERR_ARG, "class tables do not match the index");
+  const Ranked rk = rank_alleles(names, t->nitems, t->reads_explained, theta);
+  if (rk.cands.size() > 128) throw Error(HLAC_ERR_LIMIT, "more than 128 candidate alleles");
+  const size_t nc = s->fin_cls_reads.size();
+  std::vector<uint64_t> mask(std::max<size_t>(2 * nc, 2), 0);
+  if (nc && !rk.cands.empty()) {
+    std::vector<uint8_t> cand_idx(t->nitems, 0xFF);
+    for (size_t k = 0; k < rk.cands.size(); k++) cand_idx[rk.cands[k]] = (uint8_t)k;
+    DevBuf<uint8_t> d_ci; DevBuf<uint64_t> d_src, d_mask; DevBuf<uint32_t> d_len;
+    d_ci.upload(cand_idx.data(), cand_idx.size(), s->stream); d_src.upload(s->fin_src_off.data(), nc, s->stream);
+    d_len.upload(s->fin_cls_len.data(), nc, s->stream); d_mask.reserve(2 * nc, s->stream);
+    k_class_cand_mask<<<(unsigned)((nc * 32 + 255) / 256), 256, 0, s->stream>>>(s->fin_dvec.p, d_src.p, d_len.p, (uint32_t)nc, d_ci.p, d_mask.p);
+    HLAC_CUDA(cudaGetLastError());
+    HLAC_CUDA(cudaMemcpyAsync(mask.data(), d_mask.p, 2 * nc * 8, cudaMemcpyDeviceToHost, s->stream));
+    HLAC_CUDA(cudaStreamSynchronize(s->stream));
+    s->launches++;
+  }
+  auto pair_explained = [&](uint32_t a, uint32_t b) {
+    const int ka = rk.cand_of[a], kb = rk.cand_of[b];
+    const uint64_t lo = (ka < 64 ? 1ull << ka : 0) | (kb < 64 ? 1ull << kb : 0), hi = (ka >= 64 ? 1ull << (ka - 64) : 0) | (kb >= 64 ? 1ull << (kb - 64) : 0);
+    uint64_t e = 0;
+    for (size_t c = 0; c < nc; c++) if ((mask[2 * c] & lo) | (mask[2 * c + 1] & hi)) e += s->fin_cls_reads[c];
+    return (uint32_t)e;
+  };
+  call_from_ranked(rk, t->nreads, pair_explained, out);
+  return HLAC_OK;
+} catch (const Error& e) { set_last_error(e.what()); return e.code; } catch (const std::exception& e) { set_last_error(e.what()); return HLAC_ERR_STATE; }
 
 // ---- multi-GPU merge of the interned paths ----------------------------------------------------
 // Reads are partitioned by barcode, so every (barcode, UMI) group is complete on one rank, but class identity and the

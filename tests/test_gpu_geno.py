@@ -181,3 +181,34 @@ def test_multi_rank_path_merge_equals_single_session(sb, orc, tmp_path, world):
         theta, iters = g.squarem()
         ref = single.squarem()
         assert iters == ref[1] and np.array_equal(theta, ref[0])   # same tables, same deterministic EM
+
+
+def test_lean_finish_and_device_caller(sb, orc, tmp_path):
+    """Lean mode leaves counts_reads on the device; counts_umi / reads_explained / nreads, EM and the calls (pair overlaps
+    evaluated on the device-resident class vectors) must equal the full-table path and the oracle."""
+    from tools import synth
+    db = str(tmp_path / "db")
+    names = synth.make_db(db, 120, 31)
+    donor = [names[2], names[70], names[125], names[200], names[250], names[355]]
+    r = synth.reads_for_db(80_000, db, donor, 400, 31)
+    fa, st = os.path.join(db, "hla_nuc.fasta"), os.path.join(db, "Allele_status.txt")
+    gix, oix = sb.Index.from_fasta(fa, st), orc.Index.from_fasta(fa, st)
+    o = orc.Geno(oix)
+    o.push(r["seq"], r["len"], r["cell"], r["umi"])
+    o.finish()
+    ref = o.call()
+    full, lean = sb.GenoSession(gix), sb.GenoSession(gix, lean=True)
+    for g in (full, lean):
+        g.push(r["seq"], r["len"], r["cell"], r["umi"])
+    tf, tl = full.finish(), lean.finish()
+    assert tl["counts_reads"] == {} and tl["counts_umi"] == tf["counts_umi"] == o.table("umi")
+    assert tl["reads_explained"] == tf["reads_explained"] == o.reads_explained().tolist() and tl["nreads"] == tf["nreads"] == o.nreads
+    th_f, it_f = full.squarem()
+    th_l, it_l = lean.squarem()
+    assert it_f == it_l and np.array_equal(th_f, th_l)
+    c_host, c_dev_full, c_dev_lean = full.call(th_f, on_device=False), full.call(th_f, on_device=True), lean.call(th_l)
+    assert c_host == c_dev_full == c_dev_lean
+    assert c_host["called"] == ref["called"] and [p[:2] for p in c_host["pairs"]] == [p[:2] for p in ref["pairs"]]
+    assert len(c_host["pairs"]) >= 2
+    with pytest.raises(sb.HlacError):
+        lean.call(th_l, on_device=False)    # lean tables cannot feed the host-table caller

@@ -19,6 +19,7 @@ from tools import synth  # noqa: E402
 npg = int(sys.argv[1]) if len(sys.argv) > 1 else 10000
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 2_000_000
 ncheck = int(sys.argv[3]) if len(sys.argv) > 3 else 20000
+lean = (int(sys.argv[4]) if len(sys.argv) > 4 else 1) != 0   # leave counts_reads on the device (hlac_geno_set_lean)
 seed = 20191101 + 3
 db = tempfile.mkdtemp(prefix="hladb_")
 t0 = time.time()
@@ -32,9 +33,9 @@ gix = sb.Index.from_fasta(fa, st)
 t_build = time.time() - t0
 view = {np.dtype("uint64"): np.int64, np.dtype("uint16"): np.int16, np.dtype("uint32"): np.int32, np.dtype("uint8"): np.uint8}
 d = {k: torch.from_numpy(v.view(view[v.dtype])).cuda() for k, v in r.items()}
-out = {"alleles": len(names), "reads": n, "index": gix.info, "gen_s": t_gen, "index_build_s": t_build}
+out = {"alleles": len(names), "reads": n, "lean": lean, "index": gix.info, "gen_s": t_gen, "index_build_s": t_build}
 for rep in range(2):
-    g = sb.GenoSession(gix)
+    g = sb.GenoSession(gix, lean=lean)
     torch.cuda.synchronize()
     t0 = time.time()
     g.push(d["seq"], d["len"], d["cell"], d["umi"])

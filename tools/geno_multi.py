@@ -40,7 +40,7 @@ cell[cell == synth.NOT_A_CELL] = 0     # genotyping uses every barcode; keep ids
 
 
 def run(mask):
-    g = sb.GenoSession(gix)
+    g = sb.GenoSession(gix, lean=True)   # counts_reads stays on the device; the caller runs on the device-resident vectors
     t0 = time.time()
     for lo, hi, fo in ((0, n - n_tail, False), (n - n_tail, n, True)):
         idx = np.nonzero(mask[lo:hi])[0] + lo
