@@ -104,6 +104,9 @@ typedef struct {
 
 const char* hlac_last_error(void);
 int hlac_device_count(int* n);
+/* sizeof of hlac_batch, hlac_metrics, hlac_coo, hlac_index_info, hlac_class_tables, hlac_paths, hlac_calls, so that a
+ * binding (Rust repr(C), ctypes) can assert its own layouts against the library it loaded */
+int hlac_abi_sizes(uint32_t* out, uint32_t cap);
 
 /* ---- index (replaces utils::read_obj(&hla_index), mapping.rs:318 / em.rs:346, and build_index, mapping.rs:652-662,
  * hla.rs:258) ------------------------------------------------------------------------------------------------ */

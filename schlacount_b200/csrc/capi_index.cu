@@ -44,6 +44,15 @@ extern "C" {
 
 const char* hlac_last_error(void) { return g_last_error.c_str(); }
 
+// sizeof of every struct that crosses the ABI, in header order (bindings check their own layouts against this)
+int hlac_abi_sizes(uint32_t* out, uint32_t cap) {
+  const uint32_t v[] = {(uint32_t)sizeof(hlac_batch), (uint32_t)sizeof(hlac_metrics), (uint32_t)sizeof(hlac_coo), (uint32_t)sizeof(hlac_index_info),
+                        (uint32_t)sizeof(hlac_class_tables), (uint32_t)sizeof(hlac_paths), (uint32_t)sizeof(hlac_calls)};
+  if (!out || cap < 7) { set_last_error("hlac_abi_sizes needs room for 7 values"); return HLAC_ERR_ARG; }
+  for (int i = 0; i < 7; i++) out[i] = v[i];
+  return HLAC_OK;
+}
+
 int hlac_device_count(int* n) {
   HLAC_API_BEGIN
   if (!n) throw Error(HLAC_ERR_ARG, "null argument");

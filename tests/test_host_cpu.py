@@ -133,3 +133,12 @@ def test_locus_parsing_follows_the_reference_regex(sb):
     for bad in (b"6", b"6:100", b"6:-200", b"6:100-", b"6:100-2x0", b"6:99999999999-5"):
         assert L.hlac_bam_scan(bam, bad, C.byref(n), C.byref(h)) != 0, bad
         assert b"invalid locus" in L.hlac_last_error()
+
+
+def test_ctypes_layouts_match_the_library(sb):
+    """The ctypes mirrors of the ABI structs must have the sizes the compiled header has (guards against drift)."""
+    from schlacount_b200 import _lib
+    out = (C.c_uint32 * 7)()
+    assert sb.lib().hlac_abi_sizes(out, C.c_uint32(7)) == 0
+    mine = [C.sizeof(x) for x in (_lib.Batch, _lib.Metrics, _lib.Coo, _lib.IndexInfo, _lib.ClassTables, _lib.Paths, _lib.Calls)]
+    assert list(out) == mine
