@@ -45,17 +45,22 @@ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
   return x;
 }
 
-struct HashVis {   // order-sensitive hashes of the colour path
-  uint64_t a = 0xcbf29ce484222325ULL, b = 0x9e3779b97f4a7c15ULL;
+struct HashVis {   // order-sensitive hashes of the colour path: four 32-bit multiplicative accumulators (one IMAD each
+                   // per visited node; the 64-bit mixes this replaced were 25 % of k_geno_map's instructions), avalanched
+                   // once at the end into the 2 x 64-bit identity of the path
+  uint32_t a0 = 0x811c9dc5u, a1 = 0x9e3779b9u, b0 = 0x85ebca6bu, b1 = 0xc2b2ae35u;
+  uint64_t a = 0, b = 0;
   uint32_t n = 0;
   __device__ __forceinline__ void visit(uint32_t colour, uint32_t) {
-    a = (a ^ colour) * 0x100000001b3ULL; a ^= a >> 32;
-    b = mix64(b + colour + 0x632be59bd9b4e019ULL);
+    a0 = (a0 ^ colour) * 0x01000193u;
+    a1 = (a1 + colour) * 0xcc9e2d51u + 0x1b873593u;
+    b0 = (b0 ^ (colour + n)) * 0x9e3779b1u;
+    b1 = (b1 + __funnelshift_l(colour, colour, 13)) * 0x85ebca77u + n;
     n++;
   }
   __device__ __forceinline__ void finish() {
-    a = mix64(a ^ n); if (a == 0) a = 1;   // 0 marks an empty table slot
-    b = mix64(b ^ ((uint64_t)n << 32));
+    a = mix64((((uint64_t)a0 << 32) | a1) ^ n); if (a == 0) a = 1;   // 0 marks an empty table slot
+    b = mix64((((uint64_t)b0 << 32) | b1) ^ ((uint64_t)n << 32));
   }
 };
 struct CountVis2 { uint32_t n = 0; __device__ __forceinline__ void visit(uint32_t, uint32_t) { n++; } };
@@ -653,7 +658,8 @@ int hlac_geno_finish_begin(hlac_geno* s, uint32_t** umi_hist_device, uint64_t* n
     DevBuf<uint64_t> d_voff, d_vhash, d_vhash2;
     d_voff.upload(voff.data(), E + 1, s->stream); d_vhash.reserve(E, s->stream); d_vhash2.reserve(E, s->stream);
     s->fin_dvec.reserve(std::max<uint64_t>(voff[E], 1), s->stream);
-    k_resolve_paths<<<(E + 127) / 128, 128, 0, s->stream>>>(s->arena.p, s->e_path_off.p, s->e_path_len.p, s->idx->col_off.p, s->idx->col_tx.p, E,
+    const int rb = getenv("HLAC_RESOLVE_BLOCK") ? atoi(getenv("HLAC_RESOLVE_BLOCK")) : 128;
+    k_resolve_paths<<<(E + rb - 1) / rb, rb, 0, s->stream>>>(s->arena.p, s->e_path_off.p, s->e_path_len.p, s->idx->col_off.p, s->idx->col_tx.p, E,
                                                            d_voff.p, s->fin_dvec.p, d_vhash.p, d_vhash2.p);
     HLAC_CUDA(cudaGetLastError());
     s->end(ev);
