@@ -326,6 +326,11 @@ __global__ void k_class_len(const uint32_t* __restrict__ arena, const uint64_t* 
   last_colour[id] = c;
 }
 
+// order-sensitive but additive hashes of a class vector (position-keyed, so a block can reduce them in parallel);
+// only used to find interning candidates — equality is verified element by element by k_verify_classes
+__device__ __forceinline__ uint64_t vec_h1(uint32_t x, uint32_t i) { return mix64(((uint64_t)x << 32) | i); }
+__device__ __forceinline__ uint64_t vec_h2(uint32_t x, uint32_t i) { return mix64((((uint64_t)i << 32) | x) ^ 0x9e3779b97f4a7c15ULL); }
+
 // Exact emulation of `v1 = colours[last]; for n in others (visit order): merge_no_truncate(v1, colours[n])`.
 __global__ void k_resolve_paths(const uint32_t* __restrict__ arena, const uint64_t* __restrict__ path_off, const uint32_t* __restrict__ path_len,
                                 const uint64_t* __restrict__ col_off, const uint32_t* __restrict__ col_tx, uint32_t n,
@@ -350,10 +355,129 @@ __global__ void k_resolve_paths(const uint32_t* __restrict__ arena, const uint64
       else { v1[i] = v1[f]; v1[f] = x; i++; j++; f++; }
     }
   }
-  uint64_t h = 0xcbf29ce484222325ULL, h2 = 0x9e3779b97f4a7c15ULL;
-  for (uint32_t k = 0; k < n1; k++) { h = (h ^ v1[k]) * 0x100000001b3ULL; h ^= h >> 32; h2 = mix64(h2 + v1[k] + 0x632be59bd9b4e019ULL); }
-  vec_hash[id] = mix64(h ^ n1);
+  uint64_t h = 0, h2 = 0;
+  for (uint32_t k = 0; k < n1; k++) { h += vec_h1(v1[k], k); h2 += vec_h2(v1[k], k); }
+  vec_hash[id] = h;
   vec_hash2[id] = h2;
+}
+
+// The same emulation, data-parallel: one thread block per path, the vector in shared memory. It rests on a property of
+// the reference's no-truncate merge (verified against brute force): walking v1 against a sorted v2,
+// element i is a match IFF v1[i] is in v2 AND v1[i] is a left-to-right maximum of v1 (the second pointer is a running
+// maximum of ranks, so any earlier larger element has already carried it past v1[i]). The r-th match moves to
+// position r; the element it displaces ends at the match position whose chain (m -> rank of the match sitting at m)
+// leads back to it. So one merge = bitset membership + prefix-maximum scan + prefix sum + a gather.
+constexpr int RES_THREADS = 256, RES_ITEMS = 4;
+template <typename T>   // T = uint16_t when every tx id fits in 16 bits (halves the shared memory), else uint32_t
+__global__ void __launch_bounds__(RES_THREADS) k_resolve_paths_par(const uint32_t* __restrict__ arena, const uint64_t* __restrict__ path_off,
+    const uint32_t* __restrict__ path_len, const uint64_t* __restrict__ col_off, const uint32_t* __restrict__ col_tx, uint32_t n_paths,
+    const uint64_t* __restrict__ vec_off, uint32_t* vec, uint64_t* vec_hash, uint64_t* vec_hash2, uint32_t n_max, uint32_t bitset_words,
+    unsigned int* next_path, const uint32_t* __restrict__ ids) {
+  extern __shared__ __align__(16) uint32_t sm[];
+  uint32_t* bits = sm;                                // membership bitset of the current v2 over tx ids
+  T* A = reinterpret_cast<T*>(bits + bitset_words);   // current vector
+  T* B = A + n_max;                                   // next vector
+  uint16_t* rk = reinterpret_cast<uint16_t*>(B + n_max);   // per position: rank + 1 of the match sitting there, 0 if none
+  __shared__ uint32_t w_max[2][RES_THREADS / 32], w_cnt[2][RES_THREADS / 32], w_last[2][RES_THREADS / 32];
+  __shared__ unsigned int s_id;
+  __shared__ unsigned long long s_h[2][RES_THREADS / 32];
+  const unsigned t = threadIdx.x, lane = t & 31, w = t >> 5;
+  for (;;) {
+    __syncthreads();
+    if (t == 0) s_id = atomicAdd(next_path, 1u);
+    __syncthreads();
+    if (s_id >= n_paths) return;
+    const uint32_t id = ids[s_id];   // n_paths = length of this launch's id list
+    const uint32_t* path = arena + path_off[id];
+    const uint32_t plen = path_len[id];
+    const uint32_t last = path[plen - 1];
+    const uint32_t n = (uint32_t)(col_off[last + 1] - col_off[last]);
+    for (uint32_t k = t; k < n; k += RES_THREADS) A[k] = (T)col_tx[col_off[last] + k];
+    for (uint32_t sidx = 0; sidx + 1 < plen; sidx++) {
+      const uint32_t c = path[sidx];
+      const uint32_t* v2 = col_tx + col_off[c];
+      const uint32_t n2 = (uint32_t)(col_off[c + 1] - col_off[c]);
+      for (uint32_t k = t; k < bitset_words; k += RES_THREADS) bits[k] = 0;
+      __syncthreads();   // also orders the A writes of the previous merge / the load
+      for (uint32_t k = t; k < n2; k += RES_THREADS) { const uint32_t x = v2[k]; atomicOr(&bits[x >> 5], 1u << (x & 31)); }
+      __syncthreads();
+      // matches: left-to-right maxima of A that are members of v2. The r-th match is scattered to B[r] right away.
+      // Each thread owns RES_ITEMS consecutive elements of a tile (thread-local scan, then warp and block scans).
+      uint32_t carry = 0, base = 0, last_pos = 0;   // values are compared as x + 1 so that 0 means "nothing yet"
+      int par = 0;
+      for (uint32_t t0 = 0; t0 < n; t0 += RES_THREADS * RES_ITEMS, par ^= 1) {
+        const uint32_t i0 = t0 + t * RES_ITEMS;
+        uint32_t x[RES_ITEMS], pm[RES_ITEMS];   // values, thread-local inclusive prefix maxima of (value + 1)
+        uint32_t run = 0;
+#pragma unroll
+        for (int k = 0; k < RES_ITEMS; k++) { x[k] = i0 + k < n ? (uint32_t)A[i0 + k] : 0u; run = max(run, i0 + k < n ? x[k] + 1 : 0u); pm[k] = run; }
+        uint32_t v = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, v, o); if (lane >= (unsigned)o) v = max(v, u); }
+        uint32_t before = __shfl_up_sync(0xFFFFFFFFu, v, 1);
+        if (lane == 0) before = 0;
+        if (lane == 31) w_max[par][w] = v;
+        __syncthreads();
+        uint32_t excl = max(carry, before), tile_max = carry;
+#pragma unroll
+        for (unsigned k = 0; k < RES_THREADS / 32; k++) { if (k < w) excl = max(excl, w_max[par][k]); tile_max = max(tile_max, w_max[par][k]); }
+        unsigned mflags = 0, cnt = 0;
+        uint32_t my_last = 0;
+#pragma unroll
+        for (int k = 0; k < RES_ITEMS; k++) {
+          const uint32_t prev = k ? max(excl, pm[k - 1]) : excl;
+          const bool match = i0 + k < n && x[k] + 1 > prev && ((bits[x[k] >> 5] >> (x[k] & 31)) & 1u);
+          if (match) { mflags |= 1u << k; cnt++; my_last = i0 + k + 1; }
+        }
+        uint32_t incl = cnt;   // warp inclusive scan of the per-thread match counts
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= (unsigned)o) incl += u; }
+        uint32_t wl = my_last;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) wl = max(wl, __shfl_down_sync(0xFFFFFFFFu, wl, o));
+        if (lane == 31) w_cnt[par][w] = incl;
+        if (lane == 0) w_last[par][w] = wl;
+        __syncthreads();
+        uint32_t rank = base + incl - cnt, tile_cnt = 0;
+#pragma unroll
+        for (unsigned k = 0; k < RES_THREADS / 32; k++) { if (k < w) rank += w_cnt[par][k]; tile_cnt += w_cnt[par][k]; last_pos = max(last_pos, w_last[par][k]); }
+#pragma unroll
+        for (int k = 0; k < RES_ITEMS; k++) if (i0 + k < n) {
+          const bool match = (mflags >> k) & 1u;
+          rk[i0 + k] = match ? (uint16_t)(rank + 1) : (uint16_t)0;
+          if (match) { B[rank] = (T)x[k]; rank++; }
+        }
+        carry = tile_max; base += tile_cnt;
+      }
+      __syncthreads();
+      const uint32_t M = base;
+      if (M == 0 || last_pos == M) continue;   // nothing moves: the matches already occupy 0..M-1 (last_pos = last match position + 1)
+      for (uint32_t i = M + t; i < n; i += RES_THREADS) {
+        uint32_t out;
+        if (rk[i]) {                                       // a match left from here: the displaced element arrives
+          uint32_t m = rk[i] - 1u;
+          while (rk[m] && (uint32_t)(rk[m] - 1u) < m) m = rk[m] - 1u;
+          out = A[m];
+        } else out = A[i];
+        B[i] = (T)out;
+      }
+      __syncthreads();
+      T* tmp = A; A = B; B = tmp;
+    }
+    __syncthreads();
+    // write the vector out and hash it
+    uint32_t* dst = vec + vec_off[id];
+    unsigned long long h1 = 0, h2 = 0;
+    for (uint32_t k = t; k < n; k += RES_THREADS) { const uint32_t x = A[k]; dst[k] = x; h1 += vec_h1(x, k); h2 += vec_h2(x, k); }
+    for (int o = 16; o > 0; o >>= 1) { h1 += __shfl_down_sync(0xFFFFFFFFu, h1, o); h2 += __shfl_down_sync(0xFFFFFFFFu, h2, o); }
+    if (lane == 0) { s_h[0][w] = h1; s_h[1][w] = h2; }
+    __syncthreads();
+    if (t == 0) {
+      unsigned long long a = 0, b = 0;
+      for (unsigned k = 0; k < RES_THREADS / 32; k++) { a += s_h[0][k]; b += s_h[1][k]; }
+      vec_hash[id] = a; vec_hash2[id] = b;
+    }
+  }
 }
 
 // every path's vector must equal its class representative's vector element by element (interning is by hash)
@@ -658,9 +782,48 @@ int hlac_geno_finish_begin(hlac_geno* s, uint32_t** umi_hist_device, uint64_t* n
     DevBuf<uint64_t> d_voff, d_vhash, d_vhash2;
     d_voff.upload(voff.data(), E + 1, s->stream); d_vhash.reserve(E, s->stream); d_vhash2.reserve(E, s->stream);
     s->fin_dvec.reserve(std::max<uint64_t>(voff[E], 1), s->stream);
-    const int rb = getenv("HLAC_RESOLVE_BLOCK") ? atoi(getenv("HLAC_RESOLVE_BLOCK")) : 128;
-    k_resolve_paths<<<(E + rb - 1) / rb, rb, 0, s->stream>>>(s->arena.p, s->e_path_off.p, s->e_path_len.p, s->idx->col_off.p, s->idx->col_tx.p, E,
-                                                           d_voff.p, s->fin_dvec.p, d_vhash.p, d_vhash2.p);
+    {
+      uint32_t n_max = 1;
+      for (uint32_t i = 0; i < E; i++) n_max = std::max(n_max, hlen[i]);
+      const uint32_t bitset_words = ((uint32_t)hx.tx_names.size() + 31) / 32;
+      const bool narrow = hx.tx_names.size() <= 65535;   // tx ids fit in 16 bits
+      const size_t smem_par = (size_t)bitset_words * 4 + (size_t)n_max * (narrow ? 2 + 2 + 2 : 4 + 4 + 2) + 16;
+      const char* force = getenv("HLAC_RESOLVE");   // "seq" / "par" for testing both kernels
+      const bool par_ok = n_max < 65535 && smem_par <= 220 * 1024;
+      if (par_ok && !(force && std::string(force) == "seq")) {
+        // data-parallel merges, one block per path, dynamic scheduling. Paths are grouped by vector length so that the
+        // bulk of (short) vectors runs with a small shared-memory footprint = several blocks per SM.
+        auto kern = narrow ? k_resolve_paths_par<uint16_t> : k_resolve_paths_par<uint32_t>;
+        const size_t per_elem = narrow ? 2 + 2 + 2 : 4 + 4 + 2;
+        std::vector<uint32_t> caps;
+        for (uint32_t cap = n_max; ; cap = (cap + 1) / 2) { caps.push_back(cap); if (cap <= 2048 || caps.size() == 4) break; }
+        std::vector<std::vector<uint32_t>> groups(caps.size());
+        for (uint32_t i = 0; i < E; i++) { size_t gsel = 0; while (gsel + 1 < caps.size() && hlen[i] <= caps[gsel + 1]) gsel++; groups[gsel].push_back(i); }
+        DevBuf<unsigned int> d_next; d_next.reserve(caps.size(), s->stream);
+        HLAC_CUDA(cudaMemsetAsync(d_next.p, 0, caps.size() * 4, s->stream));
+        std::vector<std::unique_ptr<DevBuf<uint32_t>>> d_ids;
+        for (size_t gsel = caps.size(); gsel-- > 0;) {   // short vectors first
+          if (groups[gsel].empty()) continue;
+          const size_t smem_g = (size_t)bitset_words * 4 + (size_t)caps[gsel] * per_elem + 16;
+          HLAC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_par));
+          int occ = 1;
+          HLAC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, RES_THREADS, smem_g));
+          d_ids.emplace_back(new DevBuf<uint32_t>());
+          d_ids.back()->upload(groups[gsel].data(), groups[gsel].size(), s->stream);
+          const unsigned grid = (unsigned)std::min<uint64_t>(groups[gsel].size(), (uint64_t)s->n_sm * std::max(occ, 1));
+          kern<<<grid, RES_THREADS, smem_g, s->stream>>>(s->arena.p, s->e_path_off.p, s->e_path_len.p, s->idx->col_off.p, s->idx->col_tx.p,
+                                                        (uint32_t)groups[gsel].size(), d_voff.p, s->fin_dvec.p, d_vhash.p, d_vhash2.p, caps[gsel],
+                                                        bitset_words, d_next.p + gsel, d_ids.back()->p);
+          HLAC_CUDA(cudaGetLastError());
+          s->launches++;
+        }
+        HLAC_CUDA(cudaStreamSynchronize(s->stream));   // d_next / d_ids go out of scope
+      } else {
+        if (force && std::string(force) == "par") throw Error(HLAC_ERR_LIMIT, "HLAC_RESOLVE=par but the class vectors do not fit in shared memory");
+        k_resolve_paths<<<(E + 127) / 128, 128, 0, s->stream>>>(s->arena.p, s->e_path_off.p, s->e_path_len.p, s->idx->col_off.p, s->idx->col_tx.p, E,
+                                                               d_voff.p, s->fin_dvec.p, d_vhash.p, d_vhash2.p);
+      }
+    }
     HLAC_CUDA(cudaGetLastError());
     s->end(ev);
     s->launches += 2;
