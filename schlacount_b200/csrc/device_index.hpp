@@ -10,6 +10,8 @@ struct hlac_index {
   hlac::DevBuf<uint32_t> seq32, dict, nodes, bitmap;
   hlac::DevBuf<uint32_t> col_tx;
   hlac::DevBuf<uint64_t> col_off;
+  hlac::DevBuf<uint32_t> col_bits;   // per colour: membership bitset over tx ids (built on first use by the genotyping finish)
+  uint32_t col_bits_words = 0;
   hlac::DevIndexView view{};
   void upload(int dev);
 };

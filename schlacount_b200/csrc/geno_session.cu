@@ -367,12 +367,22 @@ __global__ void k_resolve_paths(const uint32_t* __restrict__ arena, const uint64
 // maximum of ranks, so any earlier larger element has already carried it past v1[i]). The r-th match moves to
 // position r; the element it displaces ends at the match position whose chain (m -> rank of the match sitting at m)
 // leads back to it. So one merge = bitset membership + prefix-maximum scan + prefix sum + a gather.
-constexpr int RES_THREADS = 256, RES_ITEMS = 4;
+// per colour: membership bitset over tx ids, one warp per colour (built once per index)
+__global__ void k_colour_bitsets(const uint64_t* __restrict__ col_off, const uint32_t* __restrict__ col_tx, uint32_t n_colours,
+                                 uint32_t words, uint32_t* bits) {
+  const uint32_t c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned lane = threadIdx.x & 31;
+  if (c >= n_colours) return;
+  uint32_t* b = bits + (size_t)c * words;
+  for (uint64_t q = col_off[c] + lane; q < col_off[c + 1]; q += 32) { const uint32_t x = col_tx[q]; atomicOr(&b[x >> 5], 1u << (x & 31)); }
+}
+
+constexpr int RES_THREADS = 256, RES_ITEMS = 8;
 template <typename T>   // T = uint16_t when every tx id fits in 16 bits (halves the shared memory), else uint32_t
 __global__ void __launch_bounds__(RES_THREADS) k_resolve_paths_par(const uint32_t* __restrict__ arena, const uint64_t* __restrict__ path_off,
     const uint32_t* __restrict__ path_len, const uint64_t* __restrict__ col_off, const uint32_t* __restrict__ col_tx, uint32_t n_paths,
     const uint64_t* __restrict__ vec_off, uint32_t* vec, uint64_t* vec_hash, uint64_t* vec_hash2, uint32_t n_max, uint32_t bitset_words,
-    unsigned int* next_path, const uint32_t* __restrict__ ids) {
+    unsigned int* next_path, const uint32_t* __restrict__ ids, const uint32_t* __restrict__ col_bits) {
   extern __shared__ __align__(16) uint32_t sm[];
   uint32_t* bits = sm;                                // membership bitset of the current v2 over tx ids
   T* A = reinterpret_cast<T*>(bits + bitset_words);   // current vector
@@ -397,9 +407,15 @@ __global__ void __launch_bounds__(RES_THREADS) k_resolve_paths_par(const uint32_
       const uint32_t c = path[sidx];
       const uint32_t* v2 = col_tx + col_off[c];
       const uint32_t n2 = (uint32_t)(col_off[c + 1] - col_off[c]);
-      for (uint32_t k = t; k < bitset_words; k += RES_THREADS) bits[k] = 0;
-      __syncthreads();   // also orders the A writes of the previous merge / the load
-      for (uint32_t k = t; k < n2; k += RES_THREADS) { const uint32_t x = v2[k]; atomicOr(&bits[x >> 5], 1u << (x & 31)); }
+      __syncthreads();   // the previous merge has finished with `bits`; orders the A writes of the previous merge / the load
+      if (col_bits) {    // membership bitset of this colour, precomputed once per index: a coalesced copy
+        const uint32_t* src = col_bits + (size_t)c * bitset_words;
+        for (uint32_t k = t; k < bitset_words; k += RES_THREADS) bits[k] = src[k];
+      } else {
+        for (uint32_t k = t; k < bitset_words; k += RES_THREADS) bits[k] = 0;
+        __syncthreads();
+        for (uint32_t k = t; k < n2; k += RES_THREADS) { const uint32_t x = v2[k]; atomicOr(&bits[x >> 5], 1u << (x & 31)); }
+      }
       __syncthreads();
       // matches: left-to-right maxima of A that are members of v2. The r-th match is scattered to B[r] right away.
       // Each thread owns RES_ITEMS consecutive elements of a tile (thread-local scan, then warp and block scans).
@@ -795,6 +811,18 @@ int hlac_geno_finish_begin(hlac_geno* s, uint32_t** umi_hist_device, uint64_t* n
         // bulk of (short) vectors runs with a small shared-memory footprint = several blocks per SM.
         auto kern = narrow ? k_resolve_paths_par<uint16_t> : k_resolve_paths_par<uint32_t>;
         const size_t per_elem = narrow ? 2 + 2 + 2 : 4 + 4 + 2;
+        // colour membership bitsets: once per index, if they fit comfortably (n_colours x ceil(n_tx/32) words)
+        hlac_index* ixp = s->idx;
+        const uint32_t ncol = hx.n_colours();
+        if (!ixp->col_bits.p && (size_t)ncol * bitset_words * 4 <= (size_t)4 << 30 && !getenv("HLAC_NO_COLOUR_BITSETS")) {
+          ixp->col_bits.reserve((size_t)ncol * bitset_words, s->stream);
+          HLAC_CUDA(cudaMemsetAsync(ixp->col_bits.p, 0, (size_t)ncol * bitset_words * 4, s->stream));
+          k_colour_bitsets<<<(unsigned)(((uint64_t)ncol * 32 + 255) / 256), 256, 0, s->stream>>>(ixp->col_off.p, ixp->col_tx.p, ncol, bitset_words, ixp->col_bits.p);
+          HLAC_CUDA(cudaGetLastError());
+          ixp->col_bits_words = bitset_words;
+          s->launches++;
+        }
+        const uint32_t* col_bits = (ixp->col_bits.p && ixp->col_bits_words == bitset_words) ? ixp->col_bits.p : nullptr;
         std::vector<uint32_t> caps;
         for (uint32_t cap = n_max; ; cap = (cap + 1) / 2) { caps.push_back(cap); if (cap <= 2048 || caps.size() == 4) break; }
         std::vector<std::vector<uint32_t>> groups(caps.size());
@@ -813,7 +841,7 @@ int hlac_geno_finish_begin(hlac_geno* s, uint32_t** umi_hist_device, uint64_t* n
           const unsigned grid = (unsigned)std::min<uint64_t>(groups[gsel].size(), (uint64_t)s->n_sm * std::max(occ, 1));
           kern<<<grid, RES_THREADS, smem_g, s->stream>>>(s->arena.p, s->e_path_off.p, s->e_path_len.p, s->idx->col_off.p, s->idx->col_tx.p,
                                                         (uint32_t)groups[gsel].size(), d_voff.p, s->fin_dvec.p, d_vhash.p, d_vhash2.p, caps[gsel],
-                                                        bitset_words, d_next.p + gsel, d_ids.back()->p);
+                                                        bitset_words, d_next.p + gsel, d_ids.back()->p, col_bits);
           HLAC_CUDA(cudaGetLastError());
           s->launches++;
         }
