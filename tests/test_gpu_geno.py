@@ -212,3 +212,23 @@ def test_lean_finish_and_device_caller(sb, orc, tmp_path):
     assert len(c_host["pairs"]) >= 2
     with pytest.raises(sb.HlacError):
         lean.call(th_l, on_device=False)    # lean tables cannot feed the host-table caller
+
+
+@pytest.mark.parametrize("variant", ["par", "par_inline_bitsets", "seq"])
+def test_resolve_kernel_variants_agree(sb, orc, tmp_path, monkeypatch, variant):
+    """The three path-resolution code paths (data-parallel with precomputed colour bitsets, data-parallel building the
+    bitset per merge, sequential fallback) must give the oracle's tables."""
+    from tools import synth
+    if variant == "seq":
+        monkeypatch.setenv("HLAC_RESOLVE", "seq")
+    else:
+        monkeypatch.setenv("HLAC_RESOLVE", "par")
+        if variant == "par_inline_bitsets":
+            monkeypatch.setenv("HLAC_NO_COLOUR_BITSETS", "1")
+    db = str(tmp_path / "db")
+    names = synth.make_db(db, 150, 41)
+    donor = [names[5], names[90], names[155], names[260], names[310], names[440]]
+    r = synth.reads_for_db(50_000, db, donor, 300, 41)
+    fa, st = os.path.join(db, "hla_nuc.fasta"), os.path.join(db, "Allele_status.txt")
+    gix, oix = sb.Index.from_fasta(fa, st), orc.Index.from_fasta(fa, st)
+    _compare(sb, orc, gix, oix, (r["seq"], r["len"], r["cell"], r["umi"]), splits=2)
