@@ -377,17 +377,20 @@ __global__ void k_colour_bitsets(const uint64_t* __restrict__ col_off, const uin
   for (uint64_t q = col_off[c] + lane; q < col_off[c + 1]; q += 32) { const uint32_t x = col_tx[q]; atomicOr(&b[x >> 5], 1u << (x & 31)); }
 }
 
-constexpr int RES_THREADS = 256, RES_ITEMS = 8;
-template <typename T>   // T = uint16_t when every tx id fits in 16 bits (halves the shared memory), else uint32_t
+constexpr int RES_ITEMS = 8;
+// T = uint16_t when every tx id fits in 16 bits (halves the shared memory), else uint32_t. 256 threads per block: 1024-thread
+// blocks for the long vectors (which only fit one or two blocks per SM) were measured slower (0.44 s vs 0.33 s).
+template <typename T, int RES_THREADS>
 __global__ void __launch_bounds__(RES_THREADS) k_resolve_paths_par(const uint32_t* __restrict__ arena, const uint64_t* __restrict__ path_off,
     const uint32_t* __restrict__ path_len, const uint64_t* __restrict__ col_off, const uint32_t* __restrict__ col_tx, uint32_t n_paths,
     const uint64_t* __restrict__ vec_off, uint32_t* vec, uint64_t* vec_hash, uint64_t* vec_hash2, uint32_t n_max, uint32_t bitset_words,
     unsigned int* next_path, const uint32_t* __restrict__ ids, const uint32_t* __restrict__ col_bits) {
   extern __shared__ __align__(16) uint32_t sm[];
   uint32_t* bits = sm;                                // membership bitset of the current v2 over tx ids
-  T* A = reinterpret_cast<T*>(bits + bitset_words);   // current vector
-  T* B = A + n_max;                                   // next vector
-  uint16_t* rk = reinterpret_cast<uint16_t*>(B + n_max);   // per position: rank + 1 of the match sitting there, 0 if none
+  const uint32_t n_pad = (n_max + 7u) & ~7u;          // 16-byte aligned arrays, readable in whole 8-element groups
+  T* A = reinterpret_cast<T*>(bits + ((bitset_words + 3u) & ~3u));   // current vector
+  T* B = A + n_pad;                                   // next vector
+  uint16_t* rk = reinterpret_cast<uint16_t*>(B + n_pad);   // per position: rank + 1 of the match sitting there, 0 if none
   __shared__ uint32_t w_max[2][RES_THREADS / 32], w_cnt[2][RES_THREADS / 32], w_last[2][RES_THREADS / 32];
   __shared__ unsigned int s_id;
   __shared__ unsigned long long s_h[2][RES_THREADS / 32];
@@ -426,7 +429,18 @@ __global__ void __launch_bounds__(RES_THREADS) k_resolve_paths_par(const uint32_
         uint32_t x[RES_ITEMS], pm[RES_ITEMS];   // values, thread-local inclusive prefix maxima of (value + 1)
         uint32_t run = 0;
 #pragma unroll
-        for (int k = 0; k < RES_ITEMS; k++) { x[k] = i0 + k < n ? (uint32_t)A[i0 + k] : 0u; run = max(run, i0 + k < n ? x[k] + 1 : 0u); pm[k] = run; }
+        for (int k = 0; k < RES_ITEMS; k++) x[k] = 0u;
+        if (i0 < n) {   // RES_ITEMS consecutive elements as 128-bit shared-memory loads (conflict-free; the tail past n is padding)
+          if (sizeof(T) == 2) {
+            const uint4 q = *reinterpret_cast<const uint4*>(A + i0);
+            x[0] = q.x & 0xFFFFu; x[1] = q.x >> 16; x[2] = q.y & 0xFFFFu; x[3] = q.y >> 16; x[4] = q.z & 0xFFFFu; x[5] = q.z >> 16; x[6] = q.w & 0xFFFFu; x[7] = q.w >> 16;
+          } else {
+            const uint4 q0 = *reinterpret_cast<const uint4*>(A + i0), q1 = *reinterpret_cast<const uint4*>(A + i0 + 4);
+            x[0] = q0.x; x[1] = q0.y; x[2] = q0.z; x[3] = q0.w; x[4] = q1.x; x[5] = q1.y; x[6] = q1.z; x[7] = q1.w;
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < RES_ITEMS; k++) { run = max(run, i0 + k < n ? x[k] + 1 : 0u); pm[k] = run; }
         uint32_t v = run;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, v, o); if (lane >= (unsigned)o) v = max(v, u); }
@@ -457,12 +471,14 @@ __global__ void __launch_bounds__(RES_THREADS) k_resolve_paths_par(const uint32_
         uint32_t rank = base + incl - cnt, tile_cnt = 0;
 #pragma unroll
         for (unsigned k = 0; k < RES_THREADS / 32; k++) { if (k < w) rank += w_cnt[par][k]; tile_cnt += w_cnt[par][k]; last_pos = max(last_pos, w_last[par][k]); }
+        uint32_t rkv[RES_ITEMS];
 #pragma unroll
-        for (int k = 0; k < RES_ITEMS; k++) if (i0 + k < n) {
+        for (int k = 0; k < RES_ITEMS; k++) {
           const bool match = (mflags >> k) & 1u;
-          rk[i0 + k] = match ? (uint16_t)(rank + 1) : (uint16_t)0;
+          rkv[k] = match ? rank + 1 : 0u;
           if (match) { B[rank] = (T)x[k]; rank++; }
         }
+        if (i0 < n) *reinterpret_cast<uint4*>(rk + i0) = make_uint4(rkv[0] | (rkv[1] << 16), rkv[2] | (rkv[3] << 16), rkv[4] | (rkv[5] << 16), rkv[6] | (rkv[7] << 16));
         carry = tile_max; base += tile_cnt;
       }
       __syncthreads();
@@ -803,14 +819,15 @@ int hlac_geno_finish_begin(hlac_geno* s, uint32_t** umi_hist_device, uint64_t* n
       for (uint32_t i = 0; i < E; i++) n_max = std::max(n_max, hlen[i]);
       const uint32_t bitset_words = ((uint32_t)hx.tx_names.size() + 31) / 32;
       const bool narrow = hx.tx_names.size() <= 65535;   // tx ids fit in 16 bits
-      const size_t smem_par = (size_t)bitset_words * 4 + (size_t)n_max * (narrow ? 2 + 2 + 2 : 4 + 4 + 2) + 16;
+      auto smem_for = [&](uint32_t cap) { return (size_t)((bitset_words + 3u) & ~3u) * 4 + (size_t)((cap + 7u) & ~7u) * (narrow ? 2 + 2 + 2 : 4 + 4 + 2) + 16; };
+      const size_t smem_par = smem_for(n_max);
       const char* force = getenv("HLAC_RESOLVE");   // "seq" / "par" for testing both kernels
       const bool par_ok = n_max < 65535 && smem_par <= 220 * 1024;
       if (par_ok && !(force && std::string(force) == "seq")) {
         // data-parallel merges, one block per path, dynamic scheduling. Paths are grouped by vector length so that the
         // bulk of (short) vectors runs with a small shared-memory footprint = several blocks per SM.
-        auto kern = narrow ? k_resolve_paths_par<uint16_t> : k_resolve_paths_par<uint32_t>;
-        const size_t per_elem = narrow ? 2 + 2 + 2 : 4 + 4 + 2;
+        constexpr int RES_THREADS = 256;
+        auto kern = narrow ? k_resolve_paths_par<uint16_t, RES_THREADS> : k_resolve_paths_par<uint32_t, RES_THREADS>;
         // colour membership bitsets: once per index, if they fit comfortably (n_colours x ceil(n_tx/32) words)
         hlac_index* ixp = s->idx;
         const uint32_t ncol = hx.n_colours();
@@ -832,7 +849,7 @@ int hlac_geno_finish_begin(hlac_geno* s, uint32_t** umi_hist_device, uint64_t* n
         std::vector<std::unique_ptr<DevBuf<uint32_t>>> d_ids;
         for (size_t gsel = caps.size(); gsel-- > 0;) {   // short vectors first
           if (groups[gsel].empty()) continue;
-          const size_t smem_g = (size_t)bitset_words * 4 + (size_t)caps[gsel] * per_elem + 16;
+          const size_t smem_g = smem_for(caps[gsel]);
           HLAC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_par));
           int occ = 1;
           HLAC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, RES_THREADS, smem_g));
