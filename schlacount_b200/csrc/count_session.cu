@@ -240,6 +240,177 @@ __global__ void __launch_bounds__(MAP_THREADS, MINB) k_count_map(const CountMapA
   if (lane == 0 && umi_max) atomicMax(a.metrics + 9, (unsigned long long)umi_max);   // how many UMI bits the sort must cover
 }
 
+// Queue-staged variant of the same kernel (shape R = 0). Instead of moving one fixed tile through the stages, each
+// warp keeps a pool of NS read slots and two warp-private task queues that persist across refills: SCAN entries are
+// (slot, p) with p = the orientation/index the chain of mapping.rs:772-790 has reached, WALK entries are slots with
+// a seed. A round of either kind only runs when 32 tasks are waiting (or the warp's input is exhausted), so every
+// round starts with all lanes busy whatever fraction of the reads survives each stage; scan rounds mix the four
+// orientations (same code, per-lane operands). The warp streams a contiguous range of the batch and refills the
+// pool with as many reads as there are free slots.
+template <bool SMEM_BM, int MAP_THREADS, int MINB>
+__global__ void __launch_bounds__(MAP_THREADS, MINB) k_count_map_q(const CountMapArgs a) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  constexpr int NS = 64;
+  uint32_t* wbase = smem;
+  if (SMEM_BM) {
+    const uint32_t nb = a.cds.bitmap_words + a.gen.bitmap_words;
+    for (uint32_t i = threadIdx.x; i < a.cds.bitmap_words; i += MAP_THREADS) smem[i] = __ldg(a.cds.bitmap + i);
+    for (uint32_t i = threadIdx.x; i < a.gen.bitmap_words; i += MAP_THREADS) smem[a.cds.bitmap_words + i] = __ldg(a.gen.bitmap + i);
+    wbase = smem + nb;
+    __syncthreads();
+  }
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned below = (1u << lane) - 1;
+  const uint32_t per_warp = NS * a.row_stride + NS * 3 + NS / 2 + 3 * NS / 4;   // u32 words
+  uint32_t* rows = wbase + warp * per_warp;
+  uint32_t* seed_node = rows + NS * a.row_stride;
+  uint32_t* seed_info = seed_node + NS;                                     // off(20) | pos(10) | p(2)
+  uint32_t* ridx = seed_info + NS;                                          // read index within the batch
+  uint16_t* lens = reinterpret_cast<uint16_t*>(ridx + NS);
+  uint8_t* qs = reinterpret_cast<uint8_t*>(lens + NS);                      // scan queue: slot | p << 6
+  uint8_t* qw = qs + NS;                                                    // walk queue
+  uint8_t* fr = qw + NS;                                                    // free-slot stack
+  fr[lane] = (uint8_t)lane; fr[lane + 32] = (uint8_t)(lane + 32);
+  unsigned ns = 0, nwk = 0, nfree = NS;                                     // warp-uniform
+  unsigned long long m_reads = 0, m_nonprim = 0, m_notcell = 0, m_cds = 0, m_gen = 0, m_none = 0, m_badcell = 0;
+  uint32_t n_tests = 0, n_probes = 0, umi_max = 0;
+  const uint64_t n_warps = (uint64_t)gridDim.x * (MAP_THREADS / 32);
+  const uint64_t per = (a.n + n_warps - 1) / n_warps;
+  uint64_t cur = min(a.n, ((uint64_t)blockIdx.x * (MAP_THREADS / 32) + warp) * per);
+  const uint64_t hi = min(a.n, cur + per);
+  __syncwarp();
+  for (;;) {
+    const bool more = cur < hi;
+    int what;   // 0 walk, 1 scan, 2 refill
+    if (nwk >= 32) what = 0;
+    else if (ns >= 32) what = 1;
+    else if (more) what = 2;
+    else if (ns > 0) what = 1;
+    else if (nwk > 0) what = 0;
+    else break;
+    if (what == 2) {
+      // ---- refill: filters (mapping.rs:752-763) + read rows into free slots ----
+      const unsigned c = (unsigned)min((uint64_t)min(32u, nfree), hi - cur);
+      bool keep = false;
+      unsigned slot = 0;
+      if (lane < c) {
+        const uint64_t i = cur + lane;
+        slot = fr[nfree - c + lane];
+        const uint8_t fl = __ldg(a.flags + i);
+        const uint32_t cell = __ldg(a.cell + i);
+        const uint16_t L = (uint16_t)min((uint32_t)__ldg(a.len + i), 32u * a.wpr);
+        uint32_t* fw = rows + slot * a.row_stride;
+        for (uint32_t w = 0; w < a.wpr; w++) {
+          const uint64_t v = __ldg(a.seq + i * a.wpr + w);
+          fw[2 * w] = (uint32_t)(v >> 32); fw[2 * w + 1] = (uint32_t)v;
+        }
+        fw[2 * a.wpr] = 0; fw[2 * a.wpr + 1] = 0;
+        lens[slot] = L; ridx[slot] = (uint32_t)i;
+        make_revcomp(SharedWords{fw}, fw + a.nw, L, (int)a.nw);   // here every lane is busy; in a mixed scan round only the p = 1 lanes would be
+        m_reads++;
+        const bool primary = fl & HLAC_FLAG_PRIMARY;
+        if (!primary) m_nonprim++;
+        if (primary || !a.primary_only) {
+          if (cell == HLAC_NOT_A_CELL) m_notcell++;
+          else if (cell >= a.n_cells) m_badcell++;
+          else keep = true;
+        }
+        if (a.codes) a.codes[i] = (uint8_t)HLAC_CODE_NONE;
+      }
+      __syncwarp();
+      nfree -= c; cur += c;
+      const unsigned bk = __ballot_sync(0xFFFFFFFFu, keep), bd = __ballot_sync(0xFFFFFFFFu, lane < c && !keep);
+      if (keep) qs[ns + __popc(bk & below)] = (uint8_t)slot;                 // p = 0
+      if (lane < c && !keep) fr[nfree + __popc(bd & below)] = (uint8_t)slot;
+      ns += __popc(bk); nfree += __popc(bd);
+      __syncwarp();
+    } else if (what == 1) {
+      // ---- scan round: first-seed skip-scan of (slot, p) ----
+      const unsigned cnt = min(32u, ns), qb = ns - cnt;
+      const bool task = lane < cnt;
+      bool found = false;
+      unsigned slot = 0, p = 0;
+      if (task) {
+        const unsigned e = qs[qb + lane];
+        slot = e & 63u; p = e >> 6;
+        uint32_t* fw = rows + slot * a.row_stride;
+        const int L = lens[slot];
+        SharedWords rd{(p & 1) ? fw + a.nw : fw};
+        const DevIndexView& ix = p < 2 ? a.cds : a.gen;
+        int pos = 0; uint32_t node = 0, off = 0;
+        if (L >= K) {
+          if (SMEM_BM) found = find_seed(ix, rd, BitmapShared{smem + (p < 2 ? 0 : a.cds.bitmap_words)}, pos, L - K, node, off, n_tests, n_probes);
+          else found = find_seed(ix, rd, BitmapGlobal{ix.bitmap}, pos, L - K, node, off, n_tests, n_probes);
+        }
+        if (found) { seed_node[slot] = node; seed_info[slot] = (off << 12) | ((uint32_t)pos << 2) | p; }
+      }
+      __syncwarp();
+      ns = qb;
+      const bool again = task && !found && p < 3, dead = task && !found && p == 3;
+      const unsigned bf = __ballot_sync(0xFFFFFFFFu, task && found), bn = __ballot_sync(0xFFFFFFFFu, again),
+                     bz = __ballot_sync(0xFFFFFFFFu, dead);
+      if (task && found) qw[nwk + __popc(bf & below)] = (uint8_t)slot;
+      if (again) qs[ns + __popc(bn & below)] = (uint8_t)(slot | ((p + 1) << 6));
+      if (dead) fr[nfree + __popc(bz & below)] = (uint8_t)slot;             // all four None (mapping.rs:791-793)
+      nwk += __popc(bf); ns += __popc(bn); nfree += __popc(bz);
+      if (lane == 0) m_none += __popc(bz);
+      __syncwarp();
+    } else {
+      // ---- walk round: left extension + forward walk + class code + coverage policy, key append ----
+      const unsigned cnt = min(32u, nwk), qb = nwk - cnt;
+      const bool task = lane < cnt;
+      uint32_t code = CODE_NONE5;
+      uint64_t key = 0;
+      unsigned slot = 0;
+      if (task) {
+        slot = qw[qb + lane];
+        const uint64_t i = ridx[slot];
+        const uint32_t info = seed_info[slot];
+        const int p = (int)(info & 3u), pos = (int)((info >> 2) & 1023u);
+        const uint32_t off = info >> 12, node = seed_node[slot];
+        uint32_t* fw = rows + slot * a.row_stride;
+        const int L = lens[slot];
+        const DevIndexView& ix = p < 2 ? a.cds : a.gen;
+        SharedWords rd{(p & 1) ? fw + a.nw : fw};
+        CountVis vis;
+        uint32_t cov;
+        if (SMEM_BM) cov = walk_from_seed(ix, rd, BitmapShared{smem + (p < 2 ? 0 : a.cds.bitmap_words)}, L, pos, node, off, vis, n_tests, n_probes);
+        else cov = walk_from_seed(ix, rd, BitmapGlobal{ix.bitmap}, L, pos, node, off, vis, n_tests, n_probes);
+        const bool good = cov > MIN_SCORE_COUNT_PSEUDO;
+        if (good) { if (p < 2) m_cds++; else m_gen++; }
+        if (p == 0 || good) code = vis.code();   // a CDS-forward hit is used whatever its coverage (mapping.rs:772-775)
+        if (code != CODE_NONE5) {
+          const uint32_t um = __ldg(a.umi + i);
+          umi_max = max(umi_max, um);
+          key = ((uint64_t)um << (CODE_BITS + a.cell_bits)) | ((uint64_t)__ldg(a.cell + i) << CODE_BITS) | code;
+          if (a.codes) a.codes[i] = (uint8_t)code;
+        }
+      }
+      __syncwarp();
+      nwk = qb;
+      if (task) fr[nfree + lane] = (uint8_t)slot;
+      nfree += cnt;
+      const unsigned ballot = __ballot_sync(0xFFFFFFFFu, code != CODE_NONE5);
+      if (ballot) {
+        unsigned long long at = 0;
+        if (lane == 0) at = atomicAdd(a.cursor, (unsigned long long)__popc(ballot));
+        at = __shfl_sync(0xFFFFFFFFu, at, 0);
+        if (code != CODE_NONE5) a.keys[at + __popc(ballot & below)] = key;
+      }
+      __syncwarp();
+    }
+  }
+  unsigned long long m[9] = {m_reads, m_nonprim, m_notcell, m_cds, m_gen, m_none, n_tests, n_probes, m_badcell};
+#pragma unroll
+  for (int k = 0; k < 9; k++) {
+    unsigned long long v = m[k];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, o);
+    if (lane == 0 && v) atomicAdd(a.metrics + k, v);
+  }
+  for (int o = 16; o > 0; o >>= 1) umi_max = max(umi_max, __shfl_down_sync(0xFFFFFFFFu, umi_max, o));
+  if (lane == 0 && umi_max) atomicMax(a.metrics + 9, (unsigned long long)umi_max);
+}
+
 // count() (mapping.rs:842-896) for one (cell, UMI) run of the sorted keys.
 __global__ void k_consensus(const uint64_t* __restrict__ keys, uint64_t n, uint32_t* __restrict__ dense, uint32_t nrows,
                             const uint32_t* __restrict__ gene_row0, uint32_t cell_bits) {
@@ -444,14 +615,18 @@ struct hlac_count {
     // HLAC_COUNT_SHAPE="smem,R,threads" overrides them for tuning runs.
     using Kern = void (*)(const CountMapArgs);
     auto smem_for = [&](bool bm, int r, int threads) {
-      const size_t per_warp_words = (size_t)32 * r * a.row_stride + 32 * r * 2 + 32 * r / 2 + 3 * 32 * r / 4;
+      const size_t per_warp_words = r == 0 ? (size_t)64 * a.row_stride + 64 * 3 + 64 / 2 + 3 * 64 / 4   // queue-staged kernel
+                                           : (size_t)32 * r * a.row_stride + 32 * r * 2 + 32 * r / 2 + 3 * 32 * r / 4;
       return (bm ? bitmap_smem_bytes : 0) + (threads / 32) * per_warp_words * 4;
     };
     if (cfg_wpr != b.words_per_read) {
       struct Shape { bool bm; int r, threads; Kern k; int minb = 1; };
       static const Shape shapes[] = {
 #define HLAC_SHAPE(BM, RR, TT) {BM, RR, TT, k_count_map<BM, RR, TT>}
-          // defaults first: measured best on B200 (profiles/r01_count_map_tuning.md) — occupancy beats tile size
+          // defaults first: measured best on B200 (profiles/r01_count_map_tuning.md) — the queue-staged kernel (R = 0) at
+          // 1024 resident threads per SM, then the tile-staged shapes (occupancy beats tile size)
+          {true, 0, 1024, k_count_map_q<true, 1024, 1>}, {true, 0, 512, k_count_map_q<true, 512, 2>},
+          {false, 0, 256, k_count_map_q<false, 256, 4>}, {false, 0, 128, k_count_map_q<false, 128, 8>},
           HLAC_SHAPE(true, 2, 1024), HLAC_SHAPE(true, 1, 512), HLAC_SHAPE(true, 1, 256), HLAC_SHAPE(true, 4, 512), HLAC_SHAPE(true, 2, 512),
           HLAC_SHAPE(false, 2, 128), HLAC_SHAPE(false, 1, 128), HLAC_SHAPE(false, 2, 256), HLAC_SHAPE(false, 1, 256), HLAC_SHAPE(false, 4, 128),
           HLAC_SHAPE(true, 4, 256), HLAC_SHAPE(true, 8, 256), HLAC_SHAPE(false, 4, 256), HLAC_SHAPE(false, 8, 128),
@@ -478,7 +653,8 @@ struct hlac_count {
     }
     Kern kern = (Kern)cfg_kern;
     const size_t smem = smem_for(cfg_bm, cfg_r, cfg_threads);
-    const int MAP_R = cfg_r, MAP_THREADS = cfg_threads;
+    const int MAP_R = cfg_r ? cfg_r : 2, MAP_THREADS = cfg_threads;
+    if (cfg_r == 0 && b.n >= (1ull << 32)) throw Error(HLAC_ERR_LIMIT, "the queue-staged count kernel takes batches below 2^32 reads");
     const int occ = cfg_occ;
     const uint64_t need = (b.n + (uint64_t)MAP_THREADS * MAP_R - 1) / ((uint64_t)MAP_THREADS * MAP_R);
     const unsigned grid = (unsigned)std::min<uint64_t>(need, (uint64_t)n_sm * occ);

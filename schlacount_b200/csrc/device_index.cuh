@@ -72,7 +72,8 @@ __device__ __forceinline__ bool dict_get(const DevIndexView& ix, uint64_t kmer, 
 // A window [p, p+K) can only match if every l-mer inside it is present in the index; l-mers are tested right to left
 // and an absent one at offset o rules out every window covering it: the scan jumps o+1 positions.
 // (A variant that tested four jump targets speculatively per round was measured slower on B200: 15.6 instead of 9.6
-// bitmap tests per read and more registers; see profiles/r01_count_map_tuning.md.)
+// bitmap tests per read and more registers; so was a warp-synchronous loop whose condition is a vote — every iteration
+// then waits for the few lanes that probe the dictionary; see profiles/r01_count_map_tuning.md.)
 template <typename RD, typename BM>
 __device__ __forceinline__ bool find_seed(const DevIndexView& ix, RD rd, BM bm, int& pos, int last, uint32_t& node,
                                           uint32_t& off, uint32_t& n_tests, uint32_t& n_probes) {
