@@ -104,7 +104,8 @@ typedef struct {
 
 const char* hlac_last_error(void);
 int hlac_device_count(int* n);
-/* sizeof of hlac_batch, hlac_metrics, hlac_coo, hlac_index_info, hlac_class_tables, hlac_paths, hlac_calls, so that a
+/* sizeof of hlac_batch, hlac_metrics, hlac_coo, hlac_index_info, hlac_class_tables, hlac_paths, hlac_calls (cap >= 7)
+ * and hlac_eqclassdb (written if cap >= 8), so that a
  * binding (Rust repr(C), ctypes) can assert its own layouts against the library it loaded */
 int hlac_abi_sizes(uint32_t* out, uint32_t cap);
 
@@ -234,9 +235,39 @@ int hlac_calls_free(hlac_calls*);
 /* the same caller on a finished session (works with lean tables): pair overlaps from the class vectors on the device */
 int hlac_geno_call(hlac_geno*, const hlac_class_tables* t, const double* theta, hlac_calls* out);
 
+/* ---- the reference's counts file (replaces utils::write_obj(&eq_counts, ..) mapping.rs:403 and
+ * utils::read_obj(&hla_counts) em.rs:347): bincode 1.x of EqClassDb (mapping.rs:84-90). Strings by id as CSR. ---- */
+typedef struct {
+  uint32_t n_barcodes;
+  uint64_t* barcode_off; /* n_barcodes + 1 */
+  uint8_t* barcode_bytes;
+  uint32_t n_umis;
+  uint64_t* umi_off;
+  uint8_t* umi_bytes;
+  uint32_t n_classes;  /* eq_classes: class vector by eq_class_id (first-seen order), as map_read returned it */
+  uint64_t* class_off; /* n_classes + 1 */
+  uint32_t* class_tx;
+  uint64_t n_counts;   /* Vec<BusCount>: one triple per counted read, in read order */
+  uint32_t* bc;
+  uint32_t* umi;
+  uint32_t* cls;
+} hlac_eqclassdb;
+int hlac_eqclassdb_read(const char* path, hlac_eqclassdb* out);  /* host only; caller frees with hlac_eqclassdb_free */
+int hlac_eqclassdb_write(const char* path, const hlac_eqclassdb* db); /* host only; HashMaps emitted in id order */
+int hlac_eqclassdb_free(hlac_eqclassdb*);
+/* EqClassDb::eq_class_counts(nitems) (mapping.rs:169-228) on the device for a loaded triple list */
+int hlac_eqclassdb_counts(const hlac_eqclassdb* db, uint32_t nitems, int device, hlac_class_tables* out);
+/* the EqClassDb of a finished genotyping session (hlac_geno_record_reads must have been on, not lean): the caller
+ * supplies what the session never sees - for every read pushed, in push order, an index into its own barcode and UMI
+ * string tables (CSR) - and gets ids renumbered in first-counted order like EqClassDb::count (mapping.rs:128-163). */
+int hlac_geno_eqclassdb(hlac_geno*, const hlac_class_tables* t, const uint32_t* read_bc, const uint32_t* read_umi,
+                        uint64_t n_reads, const uint64_t* bc_off, const uint8_t* bc_bytes, uint32_t n_bc,
+                        const uint64_t* umi_off, const uint8_t* umi_bytes, uint32_t n_umi, hlac_eqclassdb* out);
+
 /* ---- the three reference entry points, whole (host driver in C++; BAM/FASTA I/O on the host) ---------------------- */
 /* mapping_wrapper(hla_index, outdir, bam, locus, use_unmapped) -> counts file path (mapping.rs:310-316).
- * region: samtools-style "chr:start-end" or NULL. */
+ * region: samtools-style "chr:start-end" or NULL. The counts file is this library's table format (HLACCNT1) unless the
+ * environment has HLAC_COUNTS_FORMAT=bincode, which writes the reference's EqClassDb instead; hlac_em_wrapper reads both. */
 int hlac_mapping_wrapper(const char* hla_index, const char* outdir, const char* bam, const char* region,
                          int use_unmapped, int device, char* counts_path_out, size_t cap);
 /* em_wrapper(hla_index, hla_counts, cds_db, gen_db, outdir) -> (genomic, cds) paths (em.rs:339-345,475) */

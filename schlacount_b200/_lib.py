@@ -59,6 +59,14 @@ class ClassTables(C.Structure):
                 ("reads_explained", C.POINTER(C.c_uint64))]
 
 
+class EqClassDbC(C.Structure):
+    _fields_ = [("n_barcodes", C.c_uint32), ("barcode_off", C.POINTER(C.c_uint64)), ("barcode_bytes", C.POINTER(C.c_uint8)),
+                ("n_umis", C.c_uint32), ("umi_off", C.POINTER(C.c_uint64)), ("umi_bytes", C.POINTER(C.c_uint8)),
+                ("n_classes", C.c_uint32), ("class_off", C.POINTER(C.c_uint64)), ("class_tx", C.POINTER(C.c_uint32)),
+                ("n_counts", C.c_uint64), ("bc", C.POINTER(C.c_uint32)), ("umi", C.POINTER(C.c_uint32)),
+                ("cls", C.POINTER(C.c_uint32))]
+
+
 class Paths(C.Structure):
     _fields_ = [("n_paths", C.c_uint64), ("hash_a", C.POINTER(C.c_uint64)), ("hash_b", C.POINTER(C.c_uint64)),
                 ("first_ord", C.POINTER(C.c_uint64)), ("count", C.POINTER(C.c_uint32)), ("off", C.POINTER(C.c_uint64)),

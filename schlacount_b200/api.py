@@ -1,6 +1,7 @@
 """Python face of include/hlacount.h (ctypes). Mirrors the C ABI one to one; numpy arrays are host buffers,
 torch CUDA tensors (or raw device pointers) are device buffers."""
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -373,6 +374,27 @@ class GenoSession:
         check(lib().hlac_geno_read_class_ids(self.h, _vp(out), C.c_uint64(n)))
         return out
 
+    def eqclassdb(self, read_bc, read_umi, barcodes, umis):
+        """After finish() (record_reads=True, not lean): the reference's EqClassDb of this run. read_bc / read_umi index,
+        per pushed read in push order, into the `barcodes` / `umis` lists of bytes."""
+        read_bc, read_umi = (np.ascontiguousarray(a, dtype=np.uint32) for a in (read_bc, read_umi))
+
+        def csr(items):
+            off = np.zeros(len(items) + 1, dtype=np.uint64)
+            for i, x in enumerate(items):
+                off[i + 1] = off[i] + len(x)
+            return off, np.frombuffer(b"".join(items) or b"\0", dtype=np.uint8).copy()
+        boff, bby = csr(barcodes)
+        uoff, uby = csr(umis)
+        d = _lib.EqClassDbC()
+        check(lib().hlac_geno_eqclassdb(self.h, C.byref(self.tables), _vp(read_bc), _vp(read_umi), C.c_uint64(len(read_bc)),
+                                        _vp(boff), _vp(bby), C.c_uint32(len(barcodes)), _vp(uoff), _vp(uby),
+                                        C.c_uint32(len(umis)), C.byref(d)))
+        try:
+            return EqClassDb._from_c(d)
+        finally:
+            lib().hlac_eqclassdb_free(C.byref(d))
+
     def stats(self):
         v = [C.c_uint64() for _ in range(5)]
         check(lib().hlac_geno_stats(self.h, *[C.byref(x) for x in v]))
@@ -426,3 +448,73 @@ def squarem(nitems, classes, device=0):
     it = C.c_uint32()
     check(lib().hlac_squarem(C.byref(t), C.c_int(device), _vp(theta), C.byref(it)))
     return theta, it.value
+
+
+class EqClassDb:
+    """The reference's pseudoaligner.counts.bin (bincode EqClassDb, mapping.rs:84-90) as plain Python/numpy:
+    barcodes / umis = list of bytes by id, classes = list of tuples by eq_class_id, bc / umi / cls = u32 arrays (one
+    triple per counted read)."""
+
+    def __init__(self, barcodes, umis, classes, bc, umi, cls):
+        self.barcodes, self.umis, self.classes = list(barcodes), list(umis), [tuple(c) for c in classes]
+        self.bc, self.umi, self.cls = (np.ascontiguousarray(a, dtype=np.uint32) for a in (bc, umi, cls))
+
+    @staticmethod
+    def _strings(n, off, data):
+        raw = bytes(bytearray(data[0:off[n]])) if n and off[n] else b""
+        return [raw[off[i]:off[i + 1]] for i in range(n)]
+
+    @classmethod
+    def _from_c(cls, d):
+        n = d.n_counts
+        classes = [tuple(d.class_tx[q] for q in range(d.class_off[c], d.class_off[c + 1])) for c in range(d.n_classes)]
+        arr = lambda p: np.ctypeslib.as_array(p, shape=(n,)).copy() if n else np.zeros(0, np.uint32)
+        return cls(cls._strings(d.n_barcodes, d.barcode_off, d.barcode_bytes), cls._strings(d.n_umis, d.umi_off, d.umi_bytes),
+                   classes, arr(d.bc), arr(d.umi), arr(d.cls))
+
+    @classmethod
+    def read(cls, path):
+        d = _lib.EqClassDbC()
+        check(lib().hlac_eqclassdb_read(os.fsencode(path), C.byref(d)))
+        try:
+            return cls._from_c(d)
+        finally:
+            lib().hlac_eqclassdb_free(C.byref(d))
+
+    def _to_c(self):
+        keep = []
+
+        def csr_bytes(items):
+            off = np.zeros(len(items) + 1, dtype=np.uint64)
+            for i, x in enumerate(items):
+                off[i + 1] = off[i] + len(x)
+            data = np.frombuffer(b"".join(items) or b"\0", dtype=np.uint8).copy()
+            keep.extend([off, data])
+            return off.ctypes.data_as(C.POINTER(C.c_uint64)), data.ctypes.data_as(C.POINTER(C.c_uint8))
+        d = _lib.EqClassDbC()
+        d.n_barcodes, d.n_umis, d.n_classes, d.n_counts = len(self.barcodes), len(self.umis), len(self.classes), len(self.cls)
+        d.barcode_off, d.barcode_bytes = csr_bytes(self.barcodes)
+        d.umi_off, d.umi_bytes = csr_bytes(self.umis)
+        coff = np.zeros(len(self.classes) + 1, dtype=np.uint64)
+        for i, c in enumerate(self.classes):
+            coff[i + 1] = coff[i] + len(c)
+        ctx = np.asarray([t for c in self.classes for t in c] or [0], dtype=np.uint32)
+        pads = [a if len(a) else np.zeros(1, np.uint32) for a in (self.bc, self.umi, self.cls)]
+        keep.extend([coff, ctx] + pads)
+        d.class_off, d.class_tx = coff.ctypes.data_as(C.POINTER(C.c_uint64)), ctx.ctypes.data_as(C.POINTER(C.c_uint32))
+        d.bc, d.umi, d.cls = (a.ctypes.data_as(C.POINTER(C.c_uint32)) for a in pads)
+        return d, keep
+
+    def write(self, path):
+        d, keep = self._to_c()
+        check(lib().hlac_eqclassdb_write(os.fsencode(path), C.byref(d)))
+
+    def counts(self, nitems, device=0):
+        """EqClassDb::eq_class_counts(nitems) on the device -> the same dict GenoSession.finish() returns"""
+        d, keep = self._to_c()
+        t = _lib.ClassTables()
+        check(lib().hlac_eqclassdb_counts(C.byref(d), C.c_uint32(nitems), C.c_int(device), C.byref(t)))
+        try:
+            return _tables_to_py(t)
+        finally:
+            lib().hlac_class_tables_free(C.byref(t))

@@ -159,6 +159,13 @@ void write_tables(const std::string& path, const hlac_class_tables& t) {
   w(t.reads_explained, (size_t)t.nitems * 8);
 }
 
+bool is_own_counts_file(const std::string& path) {
+  std::ifstream f(path, std::ios::binary);
+  if (!f) throw Error(HLAC_ERR_IO, "cannot open " + path);
+  char magic[8] = {0}; f.read(magic, 8);
+  return f.gcount() == 8 && memcmp(magic, COUNTS_MAGIC, 8) == 0;
+}
+
 struct OwnedTables {
   hlac_class_tables t{};
   std::vector<uint64_t> roff, uoff, rex; std::vector<uint32_t> rtx, rcnt, utx, ucnt;
@@ -168,7 +175,7 @@ void read_tables(const std::string& path, OwnedTables& ot) {
   if (!f) throw Error(HLAC_ERR_IO, "cannot open " + path);
   auto r = [&](void* p, size_t n) { f.read((char*)p, n); if ((size_t)f.gcount() != n) throw Error(HLAC_ERR_FORMAT, path + ": truncated counts file"); };
   char magic[8]; r(magic, 8);
-  if (memcmp(magic, COUNTS_MAGIC, 8) != 0) throw Error(HLAC_ERR_FORMAT, path + ": not a counts file written by this library (the reference's bincode EqClassDb is not read)");
+  if (memcmp(magic, COUNTS_MAGIC, 8) != 0) throw Error(HLAC_ERR_FORMAT, path + ": not a counts file in this library's table format");
   auto& t = ot.t;
   r(&t.nitems, 4); r(&t.nreads, 4);
   r(&t.n_read_classes, 8); ot.roff.resize(t.n_read_classes + 1); r(ot.roff.data(), ot.roff.size() * 8);
@@ -207,9 +214,27 @@ namespace {
 std::string mapping_impl(hlac_index* index, const char* outdir, const char* bam, const char* region, int use_unmapped) {
   info("Mapping reads from BAM to database");
   GenoHandle g; check(hlac_geno_new(index, &g.p));
+  // HLAC_COUNTS_FORMAT=bincode: write the reference's EqClassDb (mapping.rs:403) instead of the table format; that needs
+  // the per-read class ids from the session and the barcode / UMI strings of every read from here
+  const char* fmt = getenv("HLAC_COUNTS_FORMAT");
+  const bool bincode = fmt && std::string(fmt) == "bincode";
+  if (fmt && !bincode && std::string(fmt) != "tables") throw Error(HLAC_ERR_ARG, "HLAC_COUNTS_FORMAT must be 'tables' or 'bincode'");
+  if (bincode) check(hlac_geno_record_reads(g.p, 1));
+  std::vector<uint32_t> read_bc, read_umi;             // bincode only: per read, index into bc_names / umi_names
+  std::vector<std::string> bc_names, umi_names;
+  std::unordered_map<std::string, uint32_t> umi_idx;
   BamReader reader(bam);
   std::unordered_map<std::string, uint32_t> bc_ids;   // mapping_wrapper uses every barcode (no whitelist)
-  auto cell_of = [&](const BamRecord& r) { return bc_ids.emplace(r.barcode, (uint32_t)bc_ids.size()).first->second; };
+  auto cell_of = [&](const BamRecord& r) {
+    const uint32_t id = bc_ids.emplace(r.barcode, (uint32_t)bc_ids.size()).first->second;
+    if (bincode) {
+      if (id == bc_names.size()) bc_names.push_back(r.barcode);
+      auto it = umi_idx.find(r.umi);
+      if (it == umi_idx.end()) { it = umi_idx.emplace(r.umi, (uint32_t)umi_names.size()).first; umi_names.push_back(r.umi); }
+      read_bc.push_back(id); read_umi.push_back(it->second);
+    }
+    return id;
+  };
   BatchBuilder bb(BATCH_READS);
   std::string counts = outdir;   // PathBuf::set_extension("counts.bin") (mapping.rs:328-329)
   { size_t slash = counts.rfind('/'), dot = counts.rfind('.');
@@ -232,7 +257,17 @@ std::string mapping_impl(hlac_index* index, const char* outdir, const char* bam,
   hlac_class_tables t{};
   check(hlac_geno_finish(g.p, &t));
   struct Free { hlac_class_tables* t; ~Free() { hlac_class_tables_free(t); } } fr{&t};
-  write_tables(counts, t);
+  if (bincode) {
+    auto csr = [](const std::vector<std::string>& v, std::vector<uint64_t>& off, std::string& bytes) {
+      off.assign(1, 0); for (auto& x : v) { bytes += x; off.push_back(bytes.size()); } };
+    std::vector<uint64_t> boff, uoff; std::string bbytes, ubytes;
+    csr(bc_names, boff, bbytes); csr(umi_names, uoff, ubytes);
+    hlac_eqclassdb db{};
+    check(hlac_geno_eqclassdb(g.p, &t, read_bc.data(), read_umi.data(), read_bc.size(), boff.data(), (const uint8_t*)bbytes.data(), (uint32_t)bc_names.size(),
+                              uoff.data(), (const uint8_t*)ubytes.data(), (uint32_t)umi_names.size(), &db));
+    struct FreeDb { hlac_eqclassdb* d; ~FreeDb() { hlac_eqclassdb_free(d); } } fdb{&db};
+    check(hlac_eqclassdb_write(counts.c_str(), &db));
+  } else write_tables(counts, t);
   return counts;
 }
 
@@ -240,8 +275,16 @@ std::string mapping_impl(hlac_index* index, const char* outdir, const char* bam,
 void em_impl(hlac_index* index, const char* hla_counts, const char* cds_db, const char* gen_db, const char* outdir, int device,
              std::string& gen_name, std::string& cds_name) {
   struct { hlac_index* p; } ix{index};
-  OwnedTables ot; read_tables(hla_counts, ot);
   hlac_index_info inf; check(hlac_index_get_info(ix.p, &inf));
+  OwnedTables ot;
+  struct FreeT { hlac_class_tables* t = nullptr; ~FreeT() { if (t) hlac_class_tables_free(t); } } free_t;
+  if (is_own_counts_file(hla_counts)) read_tables(hla_counts, ot);
+  else {   // the reference's bincode EqClassDb (em.rs:347): eq_class_counts runs on the device (em.rs:358)
+    hlac_eqclassdb db{}; check(hlac_eqclassdb_read(hla_counts, &db));
+    struct FreeDb { hlac_eqclassdb* d; ~FreeDb() { hlac_eqclassdb_free(d); } } fdb{&db};
+    check(hlac_eqclassdb_counts(&db, inf.n_tx, device, &ot.t));
+    free_t.t = &ot.t;
+  }
   if (inf.n_tx != ot.t.nitems) throw Error(HLAC_ERR_ARG, "counts file does not match the index");
   std::vector<double> theta(std::max<uint32_t>(ot.t.nitems, 1)); uint32_t iters = 0;
   check(hlac_squarem(&ot.t, device, theta.data(), &iters));

@@ -71,3 +71,59 @@ def make_batch(reads, barcodes=None, pack=None):
         umi[i] = umi_key(ub, ut)
         flags[i] = 1 if primary else 0
     return seq, lens, cell, umi, flags
+
+
+# ---- the reference's pseudoaligner.counts.bin: bincode 1.x of EqClassDb (src/mapping.rs:84-90), restated for the tests
+def write_eqclassdb_bincode(path, barcodes, umis, classes, triples, rng=None):
+    """barcodes / umis: {bytes: id}; classes: {tuple of tx ids: id}; triples: iterable of (barcode_id, umi_id, class_id).
+    HashMap entries are written in a shuffled order when `rng` is given (the reference's iteration order is arbitrary)."""
+    import struct
+
+    def items(d):
+        it = list(d.items())
+        if rng is not None:
+            rng.shuffle(it)
+        return it
+    out = bytearray()
+    for d in (barcodes, umis):
+        out += struct.pack("<Q", len(d))
+        for k, v in items(d):
+            out += struct.pack("<Q", len(k)) + bytes(k) + struct.pack("<I", v)
+    out += struct.pack("<Q", len(classes))
+    for k, v in items(classes):
+        out += struct.pack("<Q", len(k)) + struct.pack("<%dI" % len(k), *k) + struct.pack("<I", v)
+    triples = list(triples)
+    out += struct.pack("<Q", len(triples))
+    for t in triples:
+        out += struct.pack("<3I", *t)
+    open(path, "wb").write(bytes(out))
+
+
+def read_eqclassdb_bincode(path):
+    """-> (barcodes {bytes: id}, umis {bytes: id}, classes {tuple: id}, triples [(bc, umi, cls)]); asserts EOF."""
+    import struct
+    raw = open(path, "rb").read()
+    pos = 0
+
+    def take(fmt):
+        nonlocal pos
+        v = struct.unpack_from("<" + fmt, raw, pos)
+        pos += struct.calcsize("<" + fmt)
+        return v
+    maps = []
+    for _ in range(2):
+        d = {}
+        for _ in range(take("Q")[0]):
+            n = take("Q")[0]
+            k = raw[pos:pos + n]
+            pos += n
+            d[k] = take("I")[0]
+        maps.append(d)
+    classes = {}
+    for _ in range(take("Q")[0]):
+        n = take("Q")[0]
+        k = take("%dI" % n)
+        classes[tuple(k)] = take("I")[0]
+    triples = [take("3I") for _ in range(take("Q")[0])]
+    assert pos == len(raw), "trailing bytes"
+    return maps[0], maps[1], classes, triples

@@ -11,8 +11,8 @@ pytestmark = pytest.mark.gpu
 BIN = os.path.join(H.ROOT, "schlacount_b200", "sc_hla_count")
 
 
-def _run(args, cwd):
-    return subprocess.run([BIN] + args, cwd=cwd, capture_output=True, text=True)
+def _run(args, cwd, env=None):
+    return subprocess.run([BIN] + args, cwd=cwd, capture_output=True, text=True, env=dict(os.environ, **(env or {})))
 
 
 def test_allele_fasta_cli(tmp_path):
@@ -33,14 +33,18 @@ def test_allele_fasta_cli(tmp_path):
     assert r2.returncode == 1 and "already exists" in r2.stdout
 
 
-@pytest.mark.parametrize("with_index", [True, False])
-def test_call_cli(tmp_path, with_index):
+@pytest.mark.parametrize("with_index,counts_format", [(True, None), (False, None), (True, "bincode")])
+def test_call_cli(tmp_path, with_index, counts_format):
     args = ["-b", os.path.join(H.FIX, "test.bam"), "-d", os.path.join(H.FIX, "fake_db"), "-c",
             os.path.join(H.FIX, "barcodes0.tsv"), "-o", str(tmp_path / "r"), "--pl-tmp", str(tmp_path / "p")]
     if with_index:
         args += ["-i", os.path.join(H.FIX, "fake_db", "hla_nuc.fasta.idx")]
-    r = _run(args, tmp_path)
+    r = _run(args, tmp_path, {"HLAC_COUNTS_FORMAT": counts_format} if counts_format else None)
     assert r.returncode == 0, r.stdout + r.stderr
+    if counts_format == "bincode":   # the hand-over file is then the reference's EqClassDb (mapping.rs:403 -> em.rs:347)
+        bcs, umis, classes, triples = H.read_eqclassdb_bincode(tmp_path / "p" / "pseudoaligner.counts.bin")
+        assert len(triples) == 2704 and len(classes) == 98 and sorted(classes.values()) == list(range(98))
+        assert all(k.endswith(b"-1") for k in bcs) and all(len(k) == 10 for k in umis)
     assert H.read_mtx(tmp_path / "r" / "count_matrix.mtx") == H.read_mtx(os.path.join(H.FIX, "test_call.mtx")) == (5, 2, [(1, 0, 1)])
     w = [l.split("\t") for l in open(tmp_path / "p" / "weights.tsv").read().splitlines()]
     assert w[0] == ["allele_name", "em_weight", "reads_explained"]

@@ -232,3 +232,52 @@ def test_resolve_kernel_variants_agree(sb, orc, tmp_path, monkeypatch, variant):
     fa, st = os.path.join(db, "hla_nuc.fasta"), os.path.join(db, "Allele_status.txt")
     gix, oix = sb.Index.from_fasta(fa, st), orc.Index.from_fasta(fa, st)
     _compare(sb, orc, gix, oix, (r["seq"], r["len"], r["cell"], r["umi"]), splits=2)
+
+
+def test_eqclassdb_bincode_gpu(sb, orc, fixture_reads, tmp_path):
+    """The reference's counts file (bincode EqClassDb, src/mapping.rs:84-90,403 / src/em.rs:347) in both directions:
+    (1) a file assembled from the ORACLE's per-read classes (HashMap entries shuffled) -> eq_class_counts on the device
+    equals the oracle's tables; (2) the session's own EqClassDb equals the oracle's read for read."""
+    import random
+    p = os.path.join(H.FIX, "fake_db", "hla_nuc.fasta.idx")
+    gix, oix = sb.Index.from_idx(p), orc.Index.from_idx(p)
+    seq, lens, cell, umi, _ = H.make_batch(fixture_reads, None, pack=sb.pack_reads)
+    n = len(lens)
+    o = orc.Geno(oix)
+    ocid, ocov = o.push(seq, lens, cell, umi)
+    o.finish()
+    # what EqClassDb::count (mapping.rs:128-163) builds: strings and classes interned in first-counted order
+    bcs, umis, classes, triples = {}, {}, {}, []
+    for i in range(n):
+        if ocid[i] == 0xFFFFFFFF:
+            continue
+        hit = oix.map_read(seq[i], int(lens[i])) or oix.map_read(seq[i], int(lens[i]), rc=True)
+        cls = tuple(int(t) for t in hit[0])
+        assert classes.setdefault(cls, len(classes)) == ocid[i]
+        _, cb, ub, _ = fixture_reads[i]
+        triples.append((bcs.setdefault(cb, len(bcs)), umis.setdefault(ub, len(umis)), int(ocid[i])))
+    assert len(triples) == 2704 and len(classes) == 98
+    path = str(tmp_path / "pseudoaligner.counts.bin")
+    H.write_eqclassdb_bincode(path, bcs, umis, classes, triples, rng=random.Random(11))
+    t = sb.EqClassDb.read(path).counts(oix.n_tx)
+    assert t["nreads"] == o.nreads == 2704
+    assert t["counts_reads"] == o.table("reads") and t["counts_umi"] == o.table("umi")
+    assert t["reads_explained"] == o.reads_explained().tolist()
+    # (2) the GPU session's EqClassDb
+    g = sb.GenoSession(gix, record_reads=True)
+    g.push(seq, lens, cell, umi)
+    g.finish()
+    bc_names, umi_names, bi, ui = [], [], {}, {}
+    read_bc = [bi.setdefault(r[1], len(bi)) for r in fixture_reads]
+    read_umi = [ui.setdefault(r[2], len(ui)) for r in fixture_reads]
+    bc_names, umi_names = sorted(bi, key=bi.get), sorted(ui, key=ui.get)
+    db = g.eqclassdb(read_bc, read_umi, bc_names, umi_names)
+    out = str(tmp_path / "gpu.counts.bin")
+    db.write(out)
+    assert H.read_eqclassdb_bincode(out) == (bcs, umis, classes, [tuple(x) for x in triples])
+    # lean sessions keep the class vectors on the device: the export must refuse, not write an empty table
+    g2 = sb.GenoSession(gix, record_reads=True, lean=True)
+    g2.push(seq, lens, cell, umi)
+    g2.finish(raw=True)
+    with pytest.raises(sb.HlacError, match="lean"):
+        g2.eqclassdb(read_bc, read_umi, bc_names, umi_names)

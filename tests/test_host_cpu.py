@@ -138,7 +138,53 @@ def test_locus_parsing_follows_the_reference_regex(sb):
 def test_ctypes_layouts_match_the_library(sb):
     """The ctypes mirrors of the ABI structs must have the sizes the compiled header has (guards against drift)."""
     from schlacount_b200 import _lib
-    out = (C.c_uint32 * 7)()
-    assert sb.lib().hlac_abi_sizes(out, C.c_uint32(7)) == 0
-    mine = [C.sizeof(x) for x in (_lib.Batch, _lib.Metrics, _lib.Coo, _lib.IndexInfo, _lib.ClassTables, _lib.Paths, _lib.Calls)]
+    out = (C.c_uint32 * 8)()
+    assert sb.lib().hlac_abi_sizes(out, C.c_uint32(8)) == 0
+    mine = [C.sizeof(x) for x in (_lib.Batch, _lib.Metrics, _lib.Coo, _lib.IndexInfo, _lib.ClassTables, _lib.Paths, _lib.Calls,
+                                  _lib.EqClassDbC)]
     assert list(out) == mine
+    old = (C.c_uint32 * 7)()   # a binding built against the 7-value form still works
+    assert sb.lib().hlac_abi_sizes(old, C.c_uint32(7)) == 0 and list(old) == mine[:7]
+
+
+def test_eqclassdb_bincode_host(sb, tmp_path):
+    """pseudoaligner.counts.bin in the reference's format (bincode EqClassDb, src/mapping.rs:84-90,403; src/em.rs:347):
+    host reader/writer against an independent Python restatement of the format, incl. arbitrary HashMap order."""
+    import random
+    from schlacount_b200.api import EqClassDb
+    bcs = {b"AAACCTGAGACCACGA-1": 1, b"TTTGTCATCTTGTATC-1": 0, b"": 2}
+    umis = {b"ACGTACGTAC": 0, b"NNNNNNNNNN": 1}
+    classes = {(3, 1, 2): 0, (5,): 1, (): 2, tuple(range(300)): 3}
+    triples = [(1, 0, 0), (1, 0, 1), (0, 1, 3), (2, 1, 2), (1, 0, 0)]
+    p1 = str(tmp_path / "a.bin")
+    H.write_eqclassdb_bincode(p1, bcs, umis, classes, triples, rng=random.Random(5))
+    db = EqClassDb.read(p1)
+    assert db.barcodes == [b"TTTGTCATCTTGTATC-1", b"AAACCTGAGACCACGA-1", b""] and db.umis == [b"ACGTACGTAC", b"NNNNNNNNNN"]
+    assert db.classes == [(3, 1, 2), (5,), (), tuple(range(300))]
+    assert list(zip(db.bc.tolist(), db.umi.tolist(), db.cls.tolist())) == triples
+    p2 = str(tmp_path / "b.bin")
+    db.write(p2)
+    assert H.read_eqclassdb_bincode(p2) == (bcs, umis, classes, triples)
+    # an empty database
+    H.write_eqclassdb_bincode(p1, {}, {}, {}, [])
+    e = EqClassDb.read(p1)
+    assert e.barcodes == [] and e.classes == [] and len(e.cls) == 0
+    e.write(p2)
+    assert open(p2, "rb").read() == open(p1, "rb").read()
+    # malformed files are errors, not crashes
+    raw = open(str(tmp_path / "b.bin"), "rb").read()
+    H.write_eqclassdb_bincode(p1, bcs, umis, classes, triples)
+    raw = open(p1, "rb").read()
+    for bad in (raw[:-1], raw + b"\0", raw[:40], b"\xff" * 8 + raw[8:]):
+        open(p2, "wb").write(bad)
+        with pytest.raises(sb.HlacError):
+            EqClassDb.read(p2)
+    H.write_eqclassdb_bincode(p2, bcs, umis, classes, [(9, 0, 0)])      # barcode id out of range
+    with pytest.raises(sb.HlacError):
+        EqClassDb.read(p2)
+    H.write_eqclassdb_bincode(p2, bcs, umis, {(1,): 0, (2,): 0}, [])    # duplicate class id
+    with pytest.raises(sb.HlacError):
+        EqClassDb.read(p2)
+    # eq_class_counts is device work: no CPU fallback
+    with pytest.raises(sb.HlacError, match="no CPU fallback"):
+        db.counts(400, device=-1)
