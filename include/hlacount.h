@@ -122,6 +122,9 @@ int hlac_index_from_fasta(const char* fasta_path, const char* allele_status, int
 int hlac_index_from_sequences(const uint64_t* packed, const uint64_t* seq_word_start, const uint32_t* seq_len,
                               const char* const* names, uint32_t n_seq, int device, hlac_index** out);
 int hlac_index_free(hlac_index*);
+/* utils::write_obj(&index, hla_index) (hla.rs:260): the bincode Pseudoaligner<Kmer24> the reference reads with -i,
+ * including its three boomphf tables (host work, no device needed) */
+int hlac_index_write_idx(const hlac_index*, const char* path);
 int hlac_index_get_info(const hlac_index*, hlac_index_info* out);
 const char* hlac_index_tx_name(const hlac_index*, uint32_t i); /* Pseudoaligner.tx_names[i] */
 /* node export (parity checks against the .idx fixture): ASCII sequence, ext byte (high nibble right), colour list */

@@ -85,6 +85,9 @@ class Index:
         except Exception:
             pass
 
+    def write_idx(self, path):
+        check(lib().hlac_index_write_idx(self.h, os.fsencode(path)))
+
     @property
     def info(self):
         i = _lib.IndexInfo()

@@ -120,6 +120,13 @@ int hlac_index_get_info(const hlac_index* ix, hlac_index_info* o) {
   HLAC_API_END
 }
 
+int hlac_index_write_idx(const hlac_index* ix, const char* path) {
+  HLAC_API_BEGIN
+  if (!ix || !path) throw Error(HLAC_ERR_ARG, "null argument");
+  ix->host.write_idx(path);
+  HLAC_API_END
+}
+
 const char* hlac_index_tx_name(const hlac_index* ix, uint32_t i) {
   return (ix && i < ix->host.tx_names.size()) ? ix->host.tx_names[i].c_str() : nullptr;
 }

@@ -89,6 +89,142 @@ void HostIndex::load_idx(const std::string& path, HostIndex& ix) {
   ix.finalize();
 }
 
+// ---- .idx writer -----------------------------------------------------------------------------------------------------
+// [EXT] boomphf 0.5.2 (Cargo.lock:286-297) Mphf::new(gamma = 1.7, keys), restated from its published algorithm and
+// pinned on the committed fixture test/fake_db/hla_nuc.fasta.idx (all three tables reproduce bit for bit):
+//   level i: size = max(255, floor(1.7 * #keys left)); idx(key) = fastmod(fold32(wyhash(key, seed = 1 << 2i)), size);
+//   a bit is set where exactly one key lands, keys that collide go to the next level; ranks = cumulative popcount
+//   before every 8th word, running across levels. The key is hashed as its u64 storage (derive(Hash) -> write_u64):
+//   wyhash 0.3.0 for 8 bytes = wymum(wymum(seed ^ P0, swap32(x) ^ P1), 8 ^ P5).
+namespace {
+
+struct Mphf {
+  struct Level { uint64_t bits; std::vector<uint64_t> words; std::vector<uint64_t> ranks; };
+  std::vector<Level> levels;
+  static uint64_t wymum(uint64_t a, uint64_t b) { const unsigned __int128 r = (unsigned __int128)a * b; return (uint64_t)(r >> 64) ^ (uint64_t)r; }
+  static uint64_t slot(uint64_t key, uint32_t level, uint64_t size) {
+    const uint64_t x = (key << 32) | (key >> 32);
+    const uint64_t h = wymum(wymum(((uint64_t)1 << (2 * level)) ^ 0xa0761d6478bd642fULL, x ^ 0xe7037ed1a0b428dbULL), 8 ^ 0xeb44accab455d165ULL);
+    if (size < (1ULL << 32)) return ((uint64_t)((uint32_t)h ^ (uint32_t)(h >> 32)) * size) >> 32;
+    return h % size;
+  }
+  explicit Mphf(std::vector<uint64_t> keys) {
+    uint64_t pop = 0;
+    for (uint32_t level = 0;; level++) {
+      if (level > 31) throw Error(HLAC_ERR_LIMIT, "boomphf construction did not converge (duplicate keys?)");
+      Level lv;
+      lv.bits = std::max<uint64_t>(255, (uint64_t)(1.7 * (double)keys.size()));
+      const size_t nw = (lv.bits + 63) / 64;
+      lv.words.assign(nw, 0);
+      std::vector<uint64_t> collide(nw, 0);
+      for (uint64_t k : keys) {
+        const uint64_t i = slot(k, level, lv.bits), m = 1ULL << (i & 63);
+        if (collide[i >> 6] & m) continue;
+        if (lv.words[i >> 6] & m) collide[i >> 6] |= m; else lv.words[i >> 6] |= m;
+      }
+      std::vector<uint64_t> redo;
+      for (uint64_t k : keys) {
+        const uint64_t i = slot(k, level, lv.bits), m = 1ULL << (i & 63);
+        if (collide[i >> 6] & m) { redo.push_back(k); lv.words[i >> 6] &= ~m; }
+      }
+      for (size_t w = 0; w < nw; w++) { if (w % 8 == 0) lv.ranks.push_back(pop); pop += (uint64_t)__builtin_popcountll(lv.words[w]); }
+      levels.push_back(std::move(lv));
+      if (redo.empty()) break;
+      keys.swap(redo);
+    }
+  }
+  uint64_t hash(uint64_t key) const {
+    for (uint32_t l = 0; l < levels.size(); l++) {
+      const Level& lv = levels[l];
+      const uint64_t i = slot(key, l, lv.bits);
+      if (!((lv.words[i >> 6] >> (i & 63)) & 1)) continue;
+      uint64_t r = lv.ranks[i >> 9];
+      for (uint64_t w = (i >> 9) * 8; w < (i >> 6); w++) r += (uint64_t)__builtin_popcountll(lv.words[w]);
+      return r + (uint64_t)__builtin_popcountll(lv.words[i >> 6] & ((1ULL << (i & 63)) - 1));
+    }
+    throw Error(HLAC_ERR_STATE, "boomphf: key not in the set");
+  }
+};
+
+struct Writer {
+  std::string o;
+  void u8(uint8_t v) { o.push_back((char)v); }
+  void u32(uint32_t v) { o.append((const char*)&v, 4); }
+  void u64(uint64_t v) { o.append((const char*)&v, 8); }
+  void mphf(const Mphf& m) {
+    u64(m.levels.size());
+    for (auto& l : m.levels) { u64(l.bits); u64(l.words.size()); for (uint64_t w : l.words) u64(w); }
+    u64(m.levels.size());
+    for (auto& l : m.levels) { u64(l.ranks.size()); for (uint64_t r : l.ranks) u64(r); }
+  }
+};
+
+}  // namespace
+
+void HostIndex::write_idx(const std::string& path) const {
+  const uint32_t nn = n_nodes();
+  // every (node, offset) with its k-mer; the graph holds each k-mer once
+  std::vector<uint64_t> kmers; std::vector<uint32_t> k_node, k_off;
+  kmers.reserve(n_kmers); k_node.reserve(n_kmers); k_off.reserve(n_kmers);
+  for (uint32_t n = 0; n < nn; n++) {
+    uint64_t v = 0;
+    for (uint32_t j = 0; j < len[n]; j++) {
+      v = ((v << 2) | base((uint64_t)start[n] + j)) & KMER_MASK;
+      if (j + 1 >= (uint32_t)K) { kmers.push_back(v); k_node.push_back(n); k_off.push_back(j + 1 - K); }
+    }
+  }
+  const size_t nk = kmers.size();
+  // dbg_index: the reference orders k-mers by this MPHF while it compacts the graph, so node ids are the order in which
+  // nodes first appear when the k-mers are walked by hash value
+  Mphf all(kmers);
+  std::vector<uint32_t> at(nk);   // hash -> k-mer record
+  for (size_t i = 0; i < nk; i++) at[all.hash(kmers[i])] = (uint32_t)i;
+  std::vector<uint32_t> new_id(nn, NONE32), old_of; old_of.reserve(nn);
+  for (size_t h = 0; h < nk; h++) { const uint32_t n = k_node[at[h]]; if (new_id[n] == NONE32) { new_id[n] = (uint32_t)old_of.size(); old_of.push_back(n); } }
+  if (old_of.size() != nn) throw Error(HLAC_ERR_STATE, "index has a node without k-mers");
+  // colour ids: first appearance walking the k-mers in ascending order (the reference's k-mer collection pass)
+  std::vector<uint32_t> by_value(nk);
+  for (size_t i = 0; i < nk; i++) by_value[i] = (uint32_t)i;
+  std::sort(by_value.begin(), by_value.end(), [&](uint32_t a, uint32_t b) { return kmers[a] < kmers[b]; });
+  const uint32_t nc = n_colours();
+  std::vector<uint32_t> new_col(nc, NONE32), old_col; old_col.reserve(nc);
+  for (uint32_t i : by_value) { const uint32_t c = colour[k_node[i]]; if (new_col[c] == NONE32) { new_col[c] = (uint32_t)old_col.size(); old_col.push_back(c); } }
+  for (uint32_t c = 0; c < nc; c++) if (new_col[c] == NONE32) { new_col[c] = (uint32_t)old_col.size(); old_col.push_back(c); }   // unused colours last
+  Writer w;
+  {   // sequences: node strings concatenated in the new order, 32 bases per word
+    std::vector<uint64_t> words((n_bases + 31) / 32, 0);
+    uint64_t g = 0;
+    for (uint32_t n : old_of) for (uint32_t j = 0; j < len[n]; j++, g++) words[g >> 5] |= (uint64_t)base((uint64_t)start[n] + j) << (62 - 2 * (g & 31));
+    w.u64(words.size()); for (uint64_t x : words) w.u64(x);
+    w.u64(n_bases);
+    w.u64(nn); g = 0; for (uint32_t n : old_of) { w.u64(g); g += len[n]; }
+    w.u64(nn); for (uint32_t n : old_of) w.u32(len[n]);
+    w.u64(nn); for (uint32_t n : old_of) w.u8(exts[n]);
+    w.u64(nn); for (uint32_t n : old_of) w.u32(new_col[colour[n]]);
+    w.u8(1);   // stranded
+  }
+  for (int side = 0; side < 2; side++) {   // left_order / right_order: BoomHashMap<Kmer24, u32>, keys and values in hash order
+    std::vector<uint64_t> keys(nn);
+    for (uint32_t i = 0; i < nn; i++) { const uint32_t n = old_of[i]; keys[i] = kmer_at((uint64_t)start[n] + (side ? len[n] - K : 0)); }
+    Mphf m(keys);
+    std::vector<uint64_t> ko(nn); std::vector<uint32_t> vo(nn);
+    for (uint32_t i = 0; i < nn; i++) { const uint64_t h = m.hash(keys[i]); ko[h] = keys[i]; vo[h] = i; }
+    w.mphf(m);
+    w.u64(nn); for (uint64_t k : ko) w.u64(k);
+    w.u64(nn); for (uint32_t v : vo) w.u32(v);
+  }
+  w.u64(nc);
+  for (uint32_t c : old_col) { w.u64(col_off[c + 1] - col_off[c]); for (uint64_t q = col_off[c]; q < col_off[c + 1]; q++) w.u32(col_tx[q]); }
+  w.mphf(all);
+  w.u64(nk); for (size_t h = 0; h < nk; h++) { w.u32(new_id[k_node[at[h]]]); w.u32(k_off[at[h]]); }
+  w.u64(tx_names.size()); for (auto& t : tx_names) { w.u64(t.size()); w.o += t; }
+  w.u64(0);   // tx_gene_mapping: empty (hla.rs:257)
+  std::ofstream f(path, std::ios::binary);
+  if (!f) throw Error(HLAC_ERR_IO, "cannot write " + path);
+  f.write(w.o.data(), (std::streamsize)w.o.size());
+  if (!f) throw Error(HLAC_ERR_IO, "short write to " + path);
+}
+
 // build_index::<Kmer24> [EXT] — stranded k=24 coloured compacted de Bruijn graph: a node is a
 // maximal path whose interior links have a unique right extension, a unique left extension on the successor, and
 // one colour. Sort-based: one record per k-mer occurrence, sorted by (k-mer, tx), then grouped.

@@ -39,6 +39,10 @@ struct HostIndex {
   void finalize();                                // adjacency, dictionary, l-mer bitmap
 
   static void load_idx(const std::string& path, HostIndex& out);   // bincode (Appendix B)
+  // the same file, written: utils::write_obj(&index, hla_index) (hla.rs:260). Nodes, colours and the three boomphf
+  // tables are emitted in the reference's deterministic order, so the fixture's own inputs reproduce the fixture byte
+  // for byte (tests/test_host_cpu.py).
+  void write_idx(const std::string& path) const;
   // stable sort of (key, value) pairs by key; build() uses it for the k-mer occurrences when given (a device sort)
   using PairSorter = void (*)(uint64_t* keys, uint64_t* vals, size_t n);
   static void build(const std::vector<Bases>& seqs, const std::vector<std::string>& names, HostIndex& out, PairSorter sorter = nullptr);  // build_index

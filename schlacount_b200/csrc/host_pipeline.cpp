@@ -441,11 +441,13 @@ int hlac_main(int argc, const char* const* argv) {
     const std::string index = opt["hlaindex"];
     IndexHandle ix;
     if (index.empty()) {
-      // make_hla_index (hla.rs:230-264): the index is built in memory; the bincode+boomphf `.idx` file the Rust
-      // reader expects is not emitted by this build, so there is nothing to reuse with -i.
+      // make_hla_index (hla.rs:230-264; main.rs:198-201): build, then write <pl-tmp>/hla_nuc.fasta.idx for reuse with -i
       info("Building index from fasta");
       check(hlac_index_from_fasta(join(db, "hla_nuc.fasta").c_str(), join(db, "Allele_status.txt").c_str(), device, &ix.p));
       info("Finished building index!");
+      info("Writing index to disk");
+      check(hlac_index_write_idx(ix.p, join(pl, "hla_nuc.fasta.idx").c_str()));
+      info("Finished writing index!");
     } else {
       if (!path_exists(index)) throw Error(HLAC_ERR_IO, "Pseudoalignment index " + index + " does not exist. Omit parameter -i to generate automatically.");
       info("Reading database index from disk");

@@ -56,3 +56,5 @@ def test_call_cli(tmp_path, with_index, counts_format):
     called = [l.split(" ")[1] for l in open(tmp_path / "p" / "cds_pseudoaln.fasta") if l.startswith(">")]
     assert called == ["A*02:01:154", "B*27:05:02:01", "C*02:02:02:01", "C*14:02:01:01"]
     assert os.path.exists(tmp_path / "p" / "pseudoaligner.counts.bin") and os.path.exists(tmp_path / "p" / "gen_pseudoaln.fasta")
+    if not with_index:   # make_hla_index wrote the index next to the counts (main.rs:200-201): the reference's own file, bit for bit
+        assert open(tmp_path / "p" / "hla_nuc.fasta.idx", "rb").read() == open(os.path.join(H.FIX, "fake_db", "hla_nuc.fasta.idx"), "rb").read()

@@ -188,3 +188,25 @@ def test_eqclassdb_bincode_host(sb, tmp_path):
     # eq_class_counts is device work: no CPU fallback
     with pytest.raises(sb.HlacError, match="no CPU fallback"):
         db.counts(400, device=-1)
+
+
+def test_idx_writer_reproduces_fixture(sb, tmp_path):
+    """make_hla_index (src/hla.rs:230-264) end to end on the host: the fixture database's own FASTA + Allele_status.txt
+    -> read_hla_cds -> build_index -> write_obj must give the committed test/fake_db/hla_nuc.fasta.idx byte for byte
+    (node order, colour ids, exts, and the three boomphf 0.5.2 tables), and load -> write is the identity."""
+    db = os.path.join(H.FIX, "fake_db")
+    want = open(os.path.join(db, "hla_nuc.fasta.idx"), "rb").read()
+    built = sb.Index.from_fasta(os.path.join(db, "hla_nuc.fasta"), os.path.join(db, "Allele_status.txt"), device=-1)
+    p = str(tmp_path / "built.idx")
+    built.write_idx(p)
+    assert open(p, "rb").read() == want
+    loaded = sb.Index.from_idx(os.path.join(db, "hla_nuc.fasta.idx"), device=-1)
+    loaded.write_idx(p)
+    assert open(p, "rb").read() == want
+    # a different allele set: the written file must load back to the same graph
+    other = sb.Index.from_fasta(os.path.join(H.FIX, "genomic_ABC.fa"), device=-1)
+    other.write_idx(p)
+    back = sb.Index.from_idx(p, device=-1)
+    assert back.info == other.info and back.tx_names == other.tx_names
+    key = lambda n: (n[0], n[1], tuple(n[2]))
+    assert sorted(map(key, back.nodes())) == sorted(map(key, other.nodes()))
