@@ -37,7 +37,7 @@ MAP_BYTES_PER_READ = 36
 SORT_BYTES_PER_KEY = 36   # 12-B record read, written sorted, read by the segmented reduce
 # dram__bytes_read.sum + dram__bytes_write.sum of k_count_map per read, from the `ncu --set full` capture
 # profiles/r01_count_map_v3_ncu_digest.txt (70.75 MB + 1.78 MB over 2 M reads); scaled to the reads of one launch
-MAP_DRAM_BYTES_PER_READ_NCU = (70.749696e6 + 1.777152e6) / 2_000_000
+MAP_DRAM_BYTES_PER_READ_NCU = (70.790656e6 + 1.859072e6) / 2_000_000   # profiles/r01_count_map_v4_ncu_digest.txt
 
 
 class ClockSampler(threading.Thread):
@@ -93,14 +93,34 @@ def allele_set(genes, workdir=None):
     return os.path.join(d, "hla_nuc.fasta"), os.path.join(d, "hla_gen.fasta"), [s for _, s in cds], [s for _, s in gen]
 
 
-def gen_shard(n_reads, n_cells_total, rank, world, seed, alleles=None):
-    """Rank's shard: cells of this rank are {c : c % world == rank} (partition by barcode)."""
+def bind_near_gpu(index):
+    """Run this process on the CPUs NVML reports as local to GPU `index`, before any pinned buffer is allocated, so that
+    the host side of every H2D copy sits on the GPU's NUMA node (8 ranks copying at once otherwise share one socket's
+    memory and the inter-socket link). Best effort: returns the CPU count it bound to, or 0."""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(index)
+        words = nv.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return 0
+
+
+def gen_shard(n_reads, n_cells_total, rank, world, seed, alleles=None, local_ids=False):
+    """Rank's shard: cells of this rank are {c : c % world == rank} (partition by barcode). local_ids: leave the cell
+    indices shard-local (c // world): the rank's session then only holds its own columns."""
     from tools import synth
     cds_s, gen_s = (alleles[2], alleles[3]) if alleles else [[s for _, s in x] for x in synth.fixture_alleles()]
     local_cells = (n_cells_total - rank + world - 1) // world
     r = synth.make_reads(n_reads, cds_s, gen_s, local_cells, seed + 1000 * rank)
-    ok = r["cell"] != synth.NOT_A_CELL
-    r["cell"][ok] = r["cell"][ok] * world + rank
+    if not local_ids:
+        ok = r["cell"] != synth.NOT_A_CELL
+        r["cell"][ok] = r["cell"][ok] * world + rank
     return r
 
 
@@ -149,6 +169,10 @@ def main():
     ap.add_argument("--chunk", type=int, default=1_000_000, help="e2e push chunk in reads (0 = whole batch)")
     ap.add_argument("--genes", type=int, default=3, choices=[3, 4, 5, 6, 7, 8],
                     help="3 = the six fixture alleles (config 2); 8 = 2 synthetic alleles x 8 genes (config 4 shape)")
+    ap.add_argument("--merge", default="none", choices=["none", "allreduce"],
+                    help="N > 1: 'none' = every rank keeps the columns of its own barcodes (shard-local cell indices, no "
+                         "data-path collective); 'allreduce' = global cell indices, one NCCL all-reduce of the dense matrix, "
+                         "rank 0 extracts the whole COO")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -157,7 +181,8 @@ def main():
     config = {"workload": "%s: synthetic 5' GEX, %d reads x 91 bp per GPU, %d barcodes per GPU, %d CDS + %d genomic "
                           "alleles (%d genes x 2), known-genotype counting" % ("config2" if args.genes == 3 else "config4-shape",
                                                                                args.reads, args.cells, 2 * args.genes, 2 * args.genes, args.genes),
-              "reads_per_gpu": args.reads, "barcodes_per_gpu": args.cells, "parallelism": "reads sharded by barcode x%d" % world,
+              "reads_per_gpu": args.reads, "barcodes_per_gpu": args.cells, "parallelism": "reads sharded by barcode x%d%s" % (world, "" if world == 1 else (
+                  ", per-rank column blocks, no data-path collective" if args.merge == "none" else ", NCCL all-reduce of the dense matrix")),
               "l2": "inputs (%.0f MB/step) exceed the 126 MB L2; no explicit flush" % (args.reads * 35 / 1e6),
               "seed": SEED}
 
@@ -192,6 +217,7 @@ def main():
     import schlacount_b200 as sb
     from tools import synth
 
+    bound_cpus = bind_near_gpu(local_rank)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -208,9 +234,10 @@ def main():
             sys.stdout.flush()
             os.dup2(saved, 1)
             os.close(saved)
-    n_cells_total = args.cells * world
+    local = world > 1 and args.merge == "none"
+    n_cells_total = args.cells if local else args.cells * world   # columns one session holds
     al = allele_set(args.genes)
-    r = gen_shard(args.reads, n_cells_total, rank, world, SEED, al)
+    r = gen_shard(args.reads, args.cells * world, rank, world, SEED, al, local_ids=local)
     n = args.reads
     cf, gf = al[0], al[1]
     gc, gg = sb.Index.from_fasta(cf, device=local_rank), sb.Index.from_fasta(gf, device=local_rank)
@@ -226,10 +253,10 @@ def main():
 
     def finish_step():
         ptr, nelem = sess.reduce()
-        if world > 1:
+        if world > 1 and not local:
             t = torch.as_tensor(_Dense(ptr, nelem), device=dev)
             dist.all_reduce(t)
-        return sess.entries_arrays(copy=False) if rank == 0 else (None, None)
+        return sess.entries_arrays(copy=False) if (rank == 0 or local) else (None, None)
 
     # device-resident inputs
     d = {k: torch.from_numpy(v.view(np.int64) if v.dtype == np.uint64 else v.view(np.int16) if v.dtype == np.uint16
@@ -287,12 +314,18 @@ def main():
 
     # NOTE sess.timing() accumulates since the last reset(): the last step's kernel times are what it returns.
     ms_dev, wall_dev, tm_dev, clocks, out_dev = timed(step_device, args.steps, max(args.warmup, 3))
-    if rank == 0:   # the result arrays are views of the session's pinned buffer: keep a copy across the next loop
+    if rank == 0 or local:   # the result arrays are views of the session's pinned buffer: keep a copy across the next loop
         out_dev = (tuple(a.copy() for a in out_dev[0]), out_dev[1])
     ms_e2e, wall_e2e, tm_e2e, clocks_e2e, out_e2e = timed(step_e2e, args.steps, max(args.warmup, 3))
     ent, met = out_dev
-    if rank == 0:
+    if rank == 0 or local:
         assert all(np.array_equal(a, b) for a, b in zip(ent, out_e2e[0])), "device-resident and host-fed passes disagree"
+    n_entries, n_molecules = (int(len(ent[0])), int(ent[2].sum())) if ent is not None else (0, 0)
+    d2h_own = (3 * 4 * n_entries + 10 * 8 + 8 + 8) if ent is not None else 0   # COO triplets + counters + key count + nnz
+    if local:   # whole-job totals for the report (outside the timed regions): every rank holds its own column block
+        t = torch.tensor([n_entries, n_molecules, d2h_own] + list(met), device=dev, dtype=torch.int64)
+        dist.all_reduce(t)
+        n_entries, n_molecules, d2h_own, met = int(t[0]), int(t[1]), int(t[2]), [int(x) for x in t[3:]]
 
     total_reads = n * world
     per_step_ms = ms_dev / args.steps
@@ -300,12 +333,12 @@ def main():
     e2e_ms = ms_e2e / args.steps
     # host-side gaps (sync for the key count, COO extraction) are inside both event-bracketed regions
     in_bytes = sum(int(v.nbytes) for v in hn.values())
-    d2h_bytes = (3 * 4 * len(out_dev[0][0]) + 10 * 8 + 8 + 8) if rank == 0 else 0   # COO triplets + counters + key count + nnz
+    d2h_bytes = d2h_own
 
     line = None
     if rank == 0:
         scored = met[0] - met[1] * 0 - met[2] - met[5]
-        nkeys = int(ent[2].sum())
+        nkeys = n_molecules
         kern = {"map_ms": tm_dev["map_ms"], "sort_ms": tm_dev["sort_ms"], "consensus_ms": tm_dev["consensus_ms"]}
         # dominant kernel of OURS: the map kernel (the cub sort is library code and reported beside it)
         peaks = {}
@@ -318,10 +351,10 @@ def main():
         map_gbs = n * MAP_BYTES_PER_READ / (tm_dev["map_ms"] / 1e3) / 1e9 if tm_dev["map_ms"] > 0 else None
         roof = {"bound": "hbm", "kernel": "k_count_map", "achieved": map_gbs, "peak": peak, "unit": "GB/s",
                 "frac": (map_gbs / peak) if map_gbs else None, "traffic": MAP_DRAM_BYTES_PER_READ_NCU * n,
-                "traffic_source": "ncu --set full, profiles/r01_count_map_v3_ncu_digest.txt (bytes/read x reads per launch)",
+                "traffic_source": "ncu --set full, profiles/r01_count_map_v4_ncu_digest.txt (bytes/read x reads per launch)",
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_read": MAP_BYTES_PER_READ, "launch_ms": tm_dev["map_ms"],
-                "note": "DRAM traffic equals the algorithmic bytes; the kernel is issue/latency-bound (64 % issue-active, 12 of 32 lanes "
+                "note": "DRAM traffic equals the algorithmic bytes; the kernel is latency-bound (63 % issue-active, 14.7 of 32 lanes "
                         "active per instruction) — DESIGN.md §5, profiles/"}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": per_step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -334,7 +367,7 @@ def main():
                 "library_launches": (2 + (int(r["umi"].max()).bit_length() + max(1, (n_cells_total - 1).bit_length()) + 7) // 8) * args.steps,
                 "kernels_ms_last_step": kern, "roofline": roof, "clocks": clocks, "clocks_e2e": clocks_e2e,
                 "wall_ms_per_step": wall_dev / args.steps * 1e3,
-                "result": {"matrix_entries": int(len(ent[0])), "molecules": nkeys, "metrics": met}}
+                "result": {"matrix_entries": n_entries, "molecules": nkeys, "metrics": met}, "cpus_bound": bound_cpus}
         # CPU baseline: the oracle (port) on a bounded sample of the same workload, one core like the reference
         if world == 1:
             from oracle import oracle as orc
