@@ -322,10 +322,14 @@ def main():
         assert all(np.array_equal(a, b) for a, b in zip(ent, out_e2e[0])), "device-resident and host-fed passes disagree"
     n_entries, n_molecules = (int(len(ent[0])), int(ent[2].sum())) if ent is not None else (0, 0)
     d2h_own = (3 * 4 * n_entries + 10 * 8 + 8 + 8) if ent is not None else 0   # COO triplets + counters + key count + nnz
-    if local:   # whole-job totals for the report (outside the timed regions): every rank holds its own column block
-        t = torch.tensor([n_entries, n_molecules, d2h_own] + list(met), device=dev, dtype=torch.int64)
+    if world > 1:   # whole-job totals for the report (outside the timed regions)
+        if local:       # every rank holds its own column block
+            t = torch.tensor([n_entries, n_molecules, d2h_own], device=dev, dtype=torch.int64)
+            dist.all_reduce(t)
+            n_entries, n_molecules, d2h_own = int(t[0]), int(t[1]), int(t[2])
+        t = torch.tensor(list(met if met is not None else sess.entries_arrays(copy=False)[1]), device=dev, dtype=torch.int64)
         dist.all_reduce(t)
-        n_entries, n_molecules, d2h_own, met = int(t[0]), int(t[1]), int(t[2]), [int(x) for x in t[3:]]
+        met = [int(x) for x in t]
 
     total_reads = n * world
     per_step_ms = ms_dev / args.steps
@@ -359,7 +363,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": per_step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u32", "data": "synthetic", "config": config,
-                "e2e": {"value": total_reads / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": in_bytes,
+                "e2e": {"value": total_reads / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": in_bytes * world,
                         "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_ms, "h2d_ms": tm_e2e["h2d_ms"]},
                 # our own kernels in the timed region per step (device-resident loop); the radix sort between them is
                 # cub (library): histogram + exclusive-sum + one onesweep pass per 8 key bits
