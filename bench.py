@@ -97,6 +97,8 @@ def bind_near_gpu(index):
     """Run this process on the CPUs NVML reports as local to GPU `index`, before any pinned buffer is allocated, so that
     the host side of every H2D copy sits on the GPU's NUMA node (8 ranks copying at once otherwise share one socket's
     memory and the inter-socket link). Best effort: returns the CPU count it bound to, or 0."""
+    if os.environ.get("HLAC_BENCH_NO_BIND"):
+        return 0
     try:
         import pynvml as nv
         nv.nvmlInit()

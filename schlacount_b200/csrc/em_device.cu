@@ -5,11 +5,17 @@
 // The reference iterates a std HashMap (summation order unspecified, hence the 1e-6 tolerance); here the scatter is a
 // deterministic gather over the transposed CSR (one warp per tx, fixed tree order), so runs are reproducible.
 // No tensor cores: nothing here is a dense contraction.
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
+#include <ctime>
 #include <memory>
 #include <set>
+#include <string>
 #include <vector>
 
 #include "caller.hpp"
@@ -118,6 +124,206 @@ __global__ void k_diffs(const double* t1, const double* t2, uint32_t n, double* 
   }
 }
 
+// ---- the whole SQUAREM loop as ONE persistent cooperative kernel ---------------------------------------------------------
+// The multi-kernel host loop below costs ~19 launches and 4 host round trips per outer iteration (0.9 ms at 30 k alleles,
+// where one pass over the 12 M-entry class table is ~10 us of L2 traffic): launch- and sync-bound. Here one grid of
+// co-resident blocks (cudaLaunchCooperativeKernel) runs every phase of every iteration and meets at a grid barrier
+// between phases; scalars (totals, squared norms, likelihoods, diffs) are reduced deterministically - per-block partials
+// in a fixed thread -> item mapping, then every block sums the partials in the same order - so that all blocks take the
+// same branches of em.rs:263-307 without communicating the decision.
+struct SqArgs {
+  const uint64_t* off; const uint32_t* tx; const uint32_t* cnt;      // counts_umi CSR
+  const uint64_t* toff; const uint32_t* tcls;                        // transposed: tx -> classes
+  // both tables cut into segments of <= SQ_SEG entries so that one 30 k-member class (or one allele that is in 10 k
+  // classes) is spread over many warps instead of serialising one: segment s covers [seg_begin[s], min(seg_begin[s] +
+  // SQ_SEG, end of its row)); row r owns segments [row_seg[r], row_seg[r + 1])
+  const uint64_t* cseg_begin; const uint32_t* cseg_row; const uint64_t* crow_seg; uint64_t n_cseg;
+  const uint64_t* tseg_begin; const uint32_t* tseg_row; const uint64_t* trow_seg; uint64_t n_tseg;
+  uint32_t n; uint64_t nc;
+  double* th[4];                                                     // theta0, theta1, theta2, theta_sq (roles rotate)
+  double* r; double* v; double* norm;
+  double* cpart; double* tpart;                                      // per-segment partial sums
+  double* part;                                                      // [2][gridDim.x] block partials
+  unsigned* bar;                                                     // [0] arrivals, [1] generation
+  uint32_t* out;                                                     // [0] iterations, [1] index of the final theta buffer
+};
+constexpr uint32_t SQ_SEG = 1024;
+
+__device__ __forceinline__ void grid_barrier(unsigned* bar) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    volatile unsigned* vgen = bar + 1;
+    const unsigned gen = *vgen;
+    __threadfence();
+    if (atomicAdd(bar, 1u) == gridDim.x - 1) { bar[0] = 0; __threadfence(); atomicAdd(bar + 1, 1u); }
+    else while (*vgen == gen) {}
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// deterministic grid-wide sum (or max) of two per-thread values; contains one grid barrier; every thread of every block
+// returns the same pair
+template <bool MAX>
+__device__ __forceinline__ void grid_reduce2(const SqArgs& a, double x, double y, double& ox, double& oy) {
+  __shared__ double sx[32], sy[32], bx, by;
+  auto comb = [](double p, double q) { if (MAX) return q > p ? q : p; return p + q; };
+  for (int o = 16; o > 0; o >>= 1) { x = comb(x, __shfl_down_sync(0xFFFFFFFFu, x, o)); y = comb(y, __shfl_down_sync(0xFFFFFFFFu, y, o)); }
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if (lane == 0) { sx[warp] = x; sy[warp] = y; }
+  __syncthreads();
+  if (warp == 0) {
+    x = lane < nw ? sx[lane] : 0.0; y = lane < nw ? sy[lane] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) { x = comb(x, __shfl_down_sync(0xFFFFFFFFu, x, o)); y = comb(y, __shfl_down_sync(0xFFFFFFFFu, y, o)); }
+    if (lane == 0) { a.part[blockIdx.x] = x; a.part[gridDim.x + blockIdx.x] = y; }
+  }
+  grid_barrier(a.bar);
+  if (warp == 0) {
+    x = 0.0; y = 0.0;
+    for (unsigned b = lane; b < gridDim.x; b += 32) { x = comb(x, __ldcg(a.part + b)); y = comb(y, __ldcg(a.part + gridDim.x + b)); }
+    for (int o = 16; o > 0; o >>= 1) { x = comb(x, __shfl_down_sync(0xFFFFFFFFu, x, o)); y = comb(y, __shfl_down_sync(0xFFFFFFFFu, y, o)); }
+    if (lane == 0) { bx = x; by = y; }
+  }
+  __syncthreads();
+  ox = bx; oy = by;
+  __syncthreads();   // bx/by and part[] are reused by the next reduction
+}
+
+// class norms norm[c] = sum theta[tx] (em.rs:79-82) in two balanced phases with a grid barrier between them: one warp
+// per segment, then one thread per class adding its segments in order. Returns this thread's share of the
+// log-likelihood sum count * ln(norm) over non-empty classes (em.rs:119-137) when asked. norm[] is complete for other
+// blocks only after the caller's next grid barrier.
+__device__ __forceinline__ double sq_class_norm(const SqArgs& a, const double* theta, bool want_ll) {
+  const unsigned lane = threadIdx.x & 31;
+  const uint64_t gt = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t sg = gt >> 5; sg < a.n_cseg; sg += nthreads >> 5) {
+    const uint64_t b = __ldg(a.cseg_begin + sg), e = min(b + SQ_SEG, __ldg(a.off + __ldg(a.cseg_row + sg) + 1));
+    double s = 0.0;
+#pragma unroll 4
+    for (uint64_t q = b + lane; q < e; q += 32) s += theta[__ldg(a.tx + q)];   // plain loads: L1 is invalidated by the fence in grid_barrier
+    s = warp_sum(s);
+    if (lane == 0) a.cpart[sg] = s;
+  }
+  grid_barrier(a.bar);
+  double ll = 0.0;   // one warp per class, lanes over its segments: the partial loads are independent, not a latency chain
+  for (uint64_t c = gt >> 5; c < a.nc; c += nthreads >> 5) {
+    const uint64_t s0 = __ldg(a.crow_seg + c), s1 = __ldg(a.crow_seg + c + 1);
+    double s = 0.0;
+    for (uint64_t sg = s0 + lane; sg < s1; sg += 32) s += __ldcg(a.cpart + sg);
+    s = warp_sum(s);
+    if (lane == 0) { a.norm[c] = s; if (want_ll && s1 != s0) ll += (double)__ldg(a.cnt + c) * log(s); }
+  }
+  return ll;
+}
+
+// f() (em.rs:75-117) from theta `src` into `dst`: class norms | per-segment gather over the transposed table | per-allele
+// totals and their sum | dst = raw / total. The caller places a barrier before dst is read by other blocks.
+__device__ __forceinline__ void sq_f(const SqArgs& a, const double* src, double* dst, bool have_norm) {
+  if (!have_norm) {   // norm[] already holds src's class norms when src was the theta_sq whose likelihood was just taken
+    sq_class_norm(a, src, false);
+    grid_barrier(a.bar);
+  }
+  const unsigned lane = threadIdx.x & 31;
+  const uint64_t gt = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t sg = gt >> 5; sg < a.n_tseg; sg += nthreads >> 5) {
+    const uint32_t t = __ldg(a.tseg_row + sg);
+    const uint64_t b = __ldg(a.tseg_begin + sg), e = min(b + SQ_SEG, __ldg(a.toff + t + 1));
+    const double th = __ldcg(src + t);
+    double s = 0.0;
+#pragma unroll 4
+    for (uint64_t q = b + lane; q < e; q += 32) { const uint32_t c = __ldg(a.tcls + q); s += th / a.norm[c] * (double)__ldg(a.cnt + c); }
+    s = warp_sum(s);
+    if (lane == 0) a.tpart[sg] = s;
+  }
+  grid_barrier(a.bar);
+  double mine = 0.0;
+  for (uint64_t t = gt >> 5; t < a.n; t += nthreads >> 5) {
+    const uint64_t s0 = __ldg(a.trow_seg + t), s1 = __ldg(a.trow_seg + t + 1);
+    double s = 0.0;
+    for (uint64_t sg = s0 + lane; sg < s1; sg += 32) s += __ldcg(a.tpart + sg);
+    s = warp_sum(s);
+    if (lane == 0) { dst[t] = s; mine += s; }
+  }
+  double total, unused;
+  grid_reduce2<false>(a, mine, 0.0, total, unused);
+  for (uint64_t t = gt >> 5; t < a.n; t += nthreads >> 5) if (lane == 0) dst[t] = dst[t] / total;   // the same lane wrote dst[t] above
+}
+
+__global__ void __launch_bounds__(1024, 1) k_squarem(const SqArgs a) {
+  const uint64_t gt = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (uint64_t)gridDim.x * blockDim.x;
+  int i0 = 0, i1 = 1, i2 = 2, isq = 3;
+  uint32_t iters = 0;
+  bool have_norm = false;   // uniform over the grid: every block takes the same branches
+  for (;;) {
+    double* t0 = a.th[i0]; double* t1 = a.th[i1]; double* t2 = a.th[i2]; double* tsq = a.th[isq];
+    sq_f(a, t0, t1, have_norm);
+    grid_barrier(a.bar);
+    sq_f(a, t1, t2, false);
+    grid_barrier(a.bar);
+    double rs = 0.0, vs = 0.0;                                  // em.rs:255-261
+    for (uint64_t i = gt; i < a.n; i += nthreads) {
+      const double ri = __ldcg(t1 + i) - __ldcg(t0 + i), vi = __ldcg(t2 + i) - __ldcg(t1 + i) - ri;
+      a.r[i] = ri; a.v[i] = vi; rs += ri * ri; vs += vi * vi;
+    }
+    double rsq, vsq;
+    grid_reduce2<false>(a, rs, vs, rsq, vsq);
+    double alpha = -sqrt(rsq) / sqrt(vsq);                      // em.rs:263
+    double l2, lsq, unused;
+    grid_reduce2<false>(a, sq_class_norm(a, t2, true), 0.0, l2, unused);
+    int tries = 1;
+    for (;;) {                                                  // em.rs:268-289
+      const double asq = alpha * alpha;
+      double part = 0.0;
+      for (uint64_t i = gt; i < a.n; i += nthreads) {           // theta_sq = reg(t0 - 2 alpha r + alpha^2 v): clamp, then normalise
+        double x = __ldcg(t0 + i) - 2.0 * alpha * a.r[i] + asq * a.v[i];
+        if (x > 1.0) x = 1.0;
+        if (x < 0.0) x = 1e-15;
+        tsq[i] = x; part += x;
+      }
+      double nrm;
+      grid_reduce2<false>(a, part, 0.0, nrm, unused);
+      const double inv = 1.0 / nrm;
+      for (uint64_t i = gt; i < a.n; i += nthreads) tsq[i] *= inv;   // own elements
+      grid_barrier(a.bar);
+      grid_reduce2<false>(a, sq_class_norm(a, tsq, true), 0.0, lsq, unused);
+      if (lsq > l2 || tries > 5) break;
+      alpha = (alpha + -1.0) / 2.0;
+      tries++;
+    }
+    const double* chosen = lsq > l2 ? tsq : t2;
+    double mr = 0.0, ma = 0.0;                                  // diffs() em.rs:315-336
+    for (uint64_t i = gt; i < a.n; i += nthreads) {
+      const double o = __ldcg(t0 + i), nw_ = __ldcg(chosen + i);
+      const double d = fabs(o - nw_), rel = d / o;
+      if (d > ma) ma = d;
+      if (nw_ > EM_CARE_TH && rel > mr) mr = rel;
+    }
+    double rel_max, abs_max;
+    grid_reduce2<true>(a, mr, ma, rel_max, abs_max);
+    if (lsq > l2) { const int t = i0; i0 = isq; isq = t; } else { const int t = i0; i0 = i2; i2 = t; }
+    have_norm = lsq > l2;   // the last class-norm pass ran on theta_sq, which is the next theta0
+    iters++;
+    if ((abs_max < EM_ABS_TH && rel_max < EM_REL_TH) || iters > EM_ITERS) break;
+  }
+  if (gt == 0) { a.out[0] = iters; a.out[1] = (uint32_t)i0; }
+}
+
+// transposed table on the device: entry q of class c becomes the pair (tx[q], c); a stable radix sort by tx leaves every
+// allele's class list in ascending class order (= fixed summation order in the gather)
+__global__ void k_entry_class(const uint64_t* __restrict__ off, uint64_t nc, uint32_t* cls_of_entry) {
+  const uint64_t c = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (c >= nc) return;
+  for (uint64_t q = off[c] + (threadIdx.x & 31); q < off[c + 1]; q += 32) cls_of_entry[q] = (uint32_t)c;
+}
+__global__ void k_tx_hist(const uint32_t* __restrict__ tx, uint64_t nnz, uint32_t n, unsigned long long* hist1 /* [n + 1], slot t + 1 */,
+                          unsigned int* bad) {
+  const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nnz) return;
+  const uint32_t t = tx[q];
+  if (t >= n) { *bad = 1; return; }
+  atomicAdd(hist1 + t + 1, 1ull);
+}
+
 struct EmDevice {
   cudaStream_t st;
   uint32_t nitems; uint64_t nclasses, nnz;
@@ -145,6 +351,9 @@ struct EmDevice {
 
 }  // namespace
 
+static double em_now_s() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + ts.tv_nsec * 1e-9; }
+#define EM_TICK(label) do { if (dbg) { HLAC_CUDA(cudaStreamSynchronize(st)); double t_ = em_now_s(); fprintf(stderr, "[hlac timing] em: %-24s %.3f s\n", label, t_ - t_last); t_last = t_; } } while (0)
+
 extern "C" {
 
 int hlac_squarem(const hlac_class_tables* t, int device, double* theta_out, uint32_t* iters_out) try {
@@ -157,25 +366,96 @@ int hlac_squarem(const hlac_class_tables* t, int device, double* theta_out, uint
   if (n == 0) { if (iters_out) *iters_out = 0; return HLAC_OK; }
   const uint64_t nc = t->n_umi_classes;
   const uint64_t nnz = nc ? t->umi_off[nc] : 0;
+  const bool dbg = getenv("HLAC_DEBUG_TIMING") != nullptr; double t_last = em_now_s();
   cudaStream_t st; HLAC_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
   struct StreamGuard { cudaStream_t s; ~StreamGuard() { cudaStreamDestroy(s); } } sg{st};
   EmDevice em{}; em.st = st; em.nitems = n; em.nclasses = nc; em.nnz = nnz;
-  // transposed CSR: tx -> classes containing it (class order ascending => fixed summation order)
-  std::vector<uint64_t> toff(n + 1, 0); std::vector<uint32_t> tcls(std::max<uint64_t>(nnz, 1));
-  for (uint64_t q = 0; q < nnz; q++) { if (t->umi_tx[q] >= n) throw Error(HLAC_ERR_ARG, "tx id out of range"); toff[t->umi_tx[q] + 1]++; }
-  for (uint32_t i = 0; i < n; i++) toff[i + 1] += toff[i];
-  { std::vector<uint64_t> cur(toff.begin(), toff.end() - 1);
-    for (uint64_t c = 0; c < nc; c++) for (uint64_t q = t->umi_off[c]; q < t->umi_off[c + 1]; q++) tcls[cur[t->umi_tx[q]]++] = (uint32_t)c; }
   static const uint64_t zero_off[1] = {0}; static const uint32_t zero32[1] = {0};
   em.off.upload(nc ? t->umi_off : zero_off, nc + 1, st);
   em.tx.upload(nnz ? t->umi_tx : zero32, std::max<uint64_t>(nnz, 1), st);
   em.cnt.upload(nc ? t->umi_cnt : zero32, std::max<uint64_t>(nc, 1), st);
-  em.toff.upload(toff.data(), n + 1, st); em.tcls.upload(tcls.data(), tcls.size(), st);
+  EM_TICK("upload");
+  // transposed CSR: tx -> classes containing it (class order ascending => fixed summation order), built on the device
+  std::vector<uint64_t> toff(n + 1, 0);
+  em.toff.reserve(n + 1, st); em.tcls.reserve(std::max<uint64_t>(nnz, 1), st);
+  HLAC_CUDA(cudaMemsetAsync(em.toff.p, 0, ((size_t)n + 1) * 8, st));
+  if (nnz) {
+    DevBuf<uint32_t> cls_of_entry, keys_sorted; DevBuf<unsigned int> bad; DevBuf<uint8_t> tmp;
+    cls_of_entry.reserve(nnz, st); keys_sorted.reserve(nnz, st); bad.reserve(1, st);
+    HLAC_CUDA(cudaMemsetAsync(bad.p, 0, 4, st));
+    k_entry_class<<<(unsigned)((nc * 32 + 255) / 256), 256, 0, st>>>(em.off.p, nc, cls_of_entry.p);
+    k_tx_hist<<<(unsigned)((nnz + 255) / 256), 256, 0, st>>>(em.tx.p, nnz, n, reinterpret_cast<unsigned long long*>(em.toff.p), bad.p);
+    HLAC_CUDA(cudaGetLastError());
+    int bits = 1; while (bits < 32 && (1ull << bits) < n) bits++;
+    size_t tb = 0, tb2 = 0;
+    HLAC_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, em.tx.p, keys_sorted.p, cls_of_entry.p, em.tcls.p, nnz, 0, bits, st));
+    HLAC_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tb2, em.toff.p, em.toff.p, (size_t)n + 1, st));
+    tmp.reserve(std::max(tb, tb2), st);
+    HLAC_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, em.tx.p, keys_sorted.p, cls_of_entry.p, em.tcls.p, nnz, 0, bits, st));
+    HLAC_CUDA(cub::DeviceScan::InclusiveSum(tmp.p, tb2, em.toff.p, em.toff.p, (size_t)n + 1, st));
+    unsigned int hbad = 0;
+    HLAC_CUDA(cudaMemcpyAsync(&hbad, bad.p, 4, cudaMemcpyDeviceToHost, st));
+    HLAC_CUDA(cudaMemcpyAsync(toff.data(), em.toff.p, ((size_t)n + 1) * 8, cudaMemcpyDeviceToHost, st));
+    HLAC_CUDA(cudaStreamSynchronize(st));
+    if (hbad) throw Error(HLAC_ERR_ARG, "tx id out of range");
+  }
+  EM_TICK("transpose (device)");
   em.norm.reserve(std::max<uint64_t>(nc, 1), st); em.llt.reserve(std::max<uint64_t>(nc, 1), st); em.raw.reserve(n, st); em.scal.reserve(8, st);
   DevBuf<double> th0, th1, th2, thsq, r, v, rsq, vsq;
   for (auto* b : {&th0, &th1, &th2, &thsq, &r, &v, &rsq, &vsq}) b->reserve(n, st);
   std::vector<double> init(n, 1.0 / (double)n);   // em.rs:49-51
   th0.upload(init.data(), n, st);
+  const char* mode = getenv("HLAC_EM");   // "host": the multi-kernel host loop below (kept for A/B runs and tests)
+  if (!(mode && std::string(mode) == "host")) {
+    int coop = 0, n_sm = 1, occ = 0;
+    HLAC_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
+    HLAC_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
+    HLAC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_squarem, 1024, 0));
+    if (!coop || occ < 1) throw Error(HLAC_ERR_CUDA, "device cannot co-schedule the persistent SQUAREM kernel");
+    // enough blocks to give every warp a few classes / alleles, never more than are co-resident
+    const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)n_sm * occ, std::max<uint64_t>(1, (nnz / 32 + nc + n + 255) / 256));
+    struct Segs { std::vector<uint64_t> begin, row_seg; std::vector<uint32_t> row; };
+    auto cut = [](const uint64_t* off, uint64_t rows) {
+      Segs sg; sg.row_seg.assign(rows + 1, 0);
+      for (uint64_t r = 0; r < rows; r++) {
+        for (uint64_t b = off[r]; b < off[r + 1]; b += SQ_SEG) { sg.begin.push_back(b); sg.row.push_back((uint32_t)r); }
+        sg.row_seg[r + 1] = sg.begin.size();
+      }
+      return sg;
+    };
+    const Segs cs = cut(nc ? t->umi_off : zero_off, nc), ts = cut(toff.data(), n);
+    DevBuf<uint64_t> d_cb, d_crs, d_tb, d_trs; DevBuf<uint32_t> d_cr, d_tr; DevBuf<double> cpart, tpart;
+    static const uint64_t z64[1] = {0};
+    d_cb.upload(cs.begin.empty() ? z64 : cs.begin.data(), std::max<size_t>(cs.begin.size(), 1), st);
+    d_cr.upload(cs.row.empty() ? zero32 : cs.row.data(), std::max<size_t>(cs.row.size(), 1), st);
+    d_crs.upload(cs.row_seg.data(), cs.row_seg.size(), st);
+    d_tb.upload(ts.begin.empty() ? z64 : ts.begin.data(), std::max<size_t>(ts.begin.size(), 1), st);
+    d_tr.upload(ts.row.empty() ? zero32 : ts.row.data(), std::max<size_t>(ts.row.size(), 1), st);
+    d_trs.upload(ts.row_seg.data(), ts.row_seg.size(), st);
+    cpart.reserve(std::max<size_t>(cs.begin.size(), 1), st); tpart.reserve(std::max<size_t>(ts.begin.size(), 1), st);
+    DevBuf<double> part; DevBuf<unsigned> bar; DevBuf<uint32_t> outv;
+    part.reserve(2 * (size_t)grid, st); bar.reserve(2, st); outv.reserve(2, st);
+    HLAC_CUDA(cudaMemsetAsync(bar.p, 0, 2 * sizeof(unsigned), st));
+    SqArgs a{};
+    a.off = em.off.p; a.tx = em.tx.p; a.cnt = em.cnt.p; a.toff = em.toff.p; a.tcls = em.tcls.p; a.n = n; a.nc = nc;
+    a.th[0] = th0.p; a.th[1] = th1.p; a.th[2] = th2.p; a.th[3] = thsq.p; a.r = r.p; a.v = v.p; a.norm = em.norm.p;
+    a.cseg_begin = d_cb.p; a.cseg_row = d_cr.p; a.crow_seg = d_crs.p; a.n_cseg = cs.begin.size();
+    a.tseg_begin = d_tb.p; a.tseg_row = d_tr.p; a.trow_seg = d_trs.p; a.n_tseg = ts.begin.size();
+    a.cpart = cpart.p; a.tpart = tpart.p;
+    a.part = part.p; a.bar = bar.p; a.out = outv.p;
+    EM_TICK("segments");
+    void* params[] = {&a};
+    HLAC_CUDA(cudaLaunchCooperativeKernel((const void*)k_squarem, dim3(grid), dim3(1024), params, 0, st));
+    uint32_t res[2] = {0, 0};
+    HLAC_CUDA(cudaMemcpyAsync(res, outv.p, sizeof res, cudaMemcpyDeviceToHost, st));
+    HLAC_CUDA(cudaStreamSynchronize(st));
+    EM_TICK("k_squarem");
+    if (res[1] > 3) throw Error(HLAC_ERR_STATE, "SQUAREM kernel returned a bad buffer index");
+    HLAC_CUDA(cudaMemcpyAsync(theta_out, a.th[res[1]], (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    HLAC_CUDA(cudaStreamSynchronize(st));
+    if (iters_out) *iters_out = res[0];
+    return HLAC_OK;
+  }
   const unsigned gb = (n + 255) / 256;
   uint32_t iters = 0;
   double* p0 = th0.p; double* p1 = th1.p; double* p2 = th2.p; double* psq = thsq.p;

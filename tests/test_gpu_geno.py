@@ -281,3 +281,38 @@ def test_eqclassdb_bincode_gpu(sb, orc, fixture_reads, tmp_path):
     g2.finish(raw=True)
     with pytest.raises(sb.HlacError, match="lean"):
         g2.eqclassdb(read_bc, read_umi, bc_names, umi_names)
+
+
+def test_squarem_persistent_vs_host_loop(sb, orc, monkeypatch):
+    """hlac_squarem runs the whole loop as one persistent cooperative kernel; the multi-kernel host loop (HLAC_EM=host) is
+    the same arithmetic with different (both deterministic) reduction trees. On small problems they agree to rounding
+    and with the oracle; on long runs the accept/reject branches of em.rs:276-289 amplify rounding (the oracle itself
+    moves by ~5e-6 and a few iterations under a permutation of the class order, see test_synthetic_db), so there both
+    must stop within the convergence thresholds of each other and at the same likelihood."""
+    rng = np.random.default_rng(7)
+
+    def loglik(ds, th):
+        return sum(c * np.log(sum(th[t] for t in k)) for k, c in ds.items())
+    for nitems, nclasses, width in [(6, 19, 3), (300, 500, 40), (5000, 3000, 700)]:
+        ds = {}
+        for _ in range(nclasses):
+            k = tuple(sorted(set(rng.integers(0, nitems, size=rng.integers(1, width + 1)).tolist())))
+            ds[k] = ds.get(k, 0) + int(rng.integers(1, 50))
+        monkeypatch.delenv("HLAC_EM", raising=False)
+        th, it = sb.squarem(nitems, ds)
+        th_again, it_again = sb.squarem(nitems, ds)
+        assert it == it_again and np.array_equal(th, th_again), "the persistent kernel must be run-to-run deterministic"
+        monkeypatch.setenv("HLAC_EM", "host")
+        th_h, it_h = sb.squarem(nitems, ds)
+        monkeypatch.delenv("HLAC_EM", raising=False)
+        assert abs(th.sum() - 1.0) < 1e-9
+        if nitems == 6:
+            rth, rit = orc.squarem(nitems, ds)
+            assert it == it_h == rit
+            np.testing.assert_allclose(th, th_h, rtol=1e-9, atol=1e-15)
+            np.testing.assert_allclose(th, rth, rtol=EM_RTOL, atol=1e-14)
+        else:
+            assert abs(it - it_h) <= max(5, it_h // 4), (it, it_h)   # long runs: the stop iteration moves with the rounding
+            assert np.abs(th - th_h).max() < 5e-3                      # EM_ABS_TH
+            l, lh = loglik(ds, th), loglik(ds, th_h)
+            assert abs(l - lh) <= 1e-6 * abs(lh), (l, lh)
