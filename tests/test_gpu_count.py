@@ -193,3 +193,26 @@ def test_row_layout_many_genes(sb, orc, tmp_path):
     assert np.array_equal(codes, ref["codes"]) and met == ref["metrics"] and ent == ref["entries"]
     used = set(np.unique(codes).tolist()) - {255}
     assert len(used) >= 15 and max(used) <= 23    # alleles and gene-level rows of many genes were hit
+
+
+@pytest.mark.parametrize("cells", [64, 2, 1, 3000])
+def test_deep_umis(sb, orc, abc, cells):
+    """count() (src/mapping.rs:823-909) with many reads per UMI: few distinct UMIs per cell, so that majority votes, ties,
+    the 10 % allele rule and UMIs without any winning gene all occur; also reduce -> push -> reduce on one session."""
+    from tools import synth
+    cds, gen = synth.fixture_alleles()
+    r = synth.make_reads(40000, [s for _, s in cds], [s for _, s in gen], cells, 99 + cells, err=0.01)
+    rng = np.random.default_rng(5)
+    r["umi"] = (r["umi"] & 0x3F) | 0x100000
+    r["cell"][rng.random(len(r["cell"])) < 0.02] = H.NOT_A_CELL
+    batch = (r["seq"], r["len"], r["cell"], r["umi"], r["flags"])
+    ent, met, codes, s = _run_gpu(sb, abc, batch, cells, splits=3)
+    ref = orc.count_run(abc["oc"], abc["og"], *batch, want_codes=True)
+    assert np.array_equal(codes, ref["codes"]) and met == ref["metrics"]
+    assert ent == ref["entries"] and (len(ent) > 0 or cells < 64)
+    # reduce again after another push: counts accumulate over the whole session
+    s.push(*batch)
+    ent2, met2 = s.finish()
+    both = tuple(np.concatenate([x, x]) for x in batch)
+    ref2 = orc.count_run(abc["oc"], abc["og"], *both)
+    assert ent2 == ref2["entries"] and met2 == ref2["metrics"]
