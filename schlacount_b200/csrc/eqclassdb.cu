@@ -188,6 +188,7 @@ int hlac_eqclassdb_counts(const hlac_eqclassdb* db, uint32_t nitems, int device,
   if (n >= NONE32) throw Error(HLAC_ERR_LIMIT, "nreads is a u32 in the reference (mapping.rs:174)");
   const uint64_t ntx = nc ? db->class_off[nc] : 0;
   for (uint64_t q = 0; q < ntx; q++) if (db->class_tx[q] >= nitems) throw Error(HLAC_ERR_ARG, "counts file does not match the index (class member out of range)");
+  for (uint64_t i = 0; i < n; i++) if (db->cls[i] >= nc) throw Error(HLAC_ERR_ARG, "BusCount eq_class_id out of range");   // ids index device arrays
   DeviceGuard g(device);
   cudaStream_t stream; HLAC_CUDA(cudaStreamCreate(&stream));
   struct SG { cudaStream_t s; ~SG() { cudaStreamDestroy(s); } } sg{stream};
