@@ -826,11 +826,8 @@ int hlac_geno_finish_begin(hlac_geno* s, uint32_t** umi_hist_device, uint64_t* n
       if (par_ok && !(force && std::string(force) == "seq")) {
         // data-parallel merges, one block per path, dynamic scheduling. Paths are grouped by vector length so that the
         // bulk of (short) vectors runs with a small shared-memory footprint = several blocks per SM.
-        // 256 threads per block; 512 for the groups whose vectors leave room for only one or two blocks per SM (more warps
-        // to hide the shared-memory and barrier latency; 1024 was measured slower: the per-warp partials are combined serially)
-        auto kern256 = narrow ? k_resolve_paths_par<uint16_t, 256> : k_resolve_paths_par<uint32_t, 256>;
-        auto kern512 = narrow ? k_resolve_paths_par<uint16_t, 512> : k_resolve_paths_par<uint32_t, 512>;
-        const char* thr_env = getenv("HLAC_RESOLVE_THREADS");   // "256" / "512": force one shape (tuning)
+        constexpr int RES_THREADS = 256;   // measured: 512 threads for the long-vector groups changes nothing (0.404 vs 0.409 s), 1024 is slower
+        auto kern = narrow ? k_resolve_paths_par<uint16_t, RES_THREADS> : k_resolve_paths_par<uint32_t, RES_THREADS>;
         // colour membership bitsets: once per index, if they fit comfortably (n_colours x ceil(n_tx/32) words)
         hlac_index* ixp = s->idx;
         const uint32_t ncol = hx.n_colours();
@@ -853,14 +850,9 @@ int hlac_geno_finish_begin(hlac_geno* s, uint32_t** umi_hist_device, uint64_t* n
         for (size_t gsel = caps.size(); gsel-- > 0;) {   // short vectors first
           if (groups[gsel].empty()) continue;
           const size_t smem_g = smem_for(caps[gsel]);
-          HLAC_CUDA(cudaFuncSetAttribute(kern256, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_par));
-          HLAC_CUDA(cudaFuncSetAttribute(kern512, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_par));
+          HLAC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_par));
           int occ = 1;
-          HLAC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern256, 256, smem_g));
-          const bool wide = thr_env ? atoi(thr_env) == 512 : occ <= 2;
-          auto kern = wide ? kern512 : kern256;
-          const int RES_THREADS = wide ? 512 : 256;
-          if (wide) HLAC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern512, 512, smem_g));
+          HLAC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, RES_THREADS, smem_g));
           d_ids.emplace_back(new DevBuf<uint32_t>());
           d_ids.back()->upload(groups[gsel].data(), groups[gsel].size(), s->stream);
           const unsigned grid = (unsigned)std::min<uint64_t>(groups[gsel].size(), (uint64_t)s->n_sm * std::max(occ, 1));
