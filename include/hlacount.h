@@ -284,6 +284,9 @@ int hlac_map_and_count_pseudo(const char* bam, const char* out_dir, const char* 
 /* host BAM reader self-check (BamSeqReader, mapping.rs:231-279): count of CB+UB records in the selection and an
  * FNV-1a checksum over (2-bit sequence, CB, UB, primary) in file order; region NULL = the unmapped tail ("*") */
 int hlac_bam_scan(const char* bam, const char* region, uint64_t* n_records, uint64_t* checksum);
+/* the batch path of the wrappers (records framed sequentially, parsed and packed on a pool of host threads, appended in
+ * file order): record count and FNV-1a over (2-bit words carrying bases, len, first-seen barcode id, UMI key, flags) */
+int hlac_bam_batch_checksum(const char* bam, const char* region, uint64_t* n_records, uint64_t* checksum);
 /* sc_hla_count's _main (main.rs:151-298): argv as the CLI takes it. */
 int hlac_main(int argc, const char* const* argv);
 

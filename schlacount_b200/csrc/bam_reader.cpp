@@ -45,7 +45,9 @@ class InflatePool {
     cv_.notify_all();
     for (auto& t : workers_) t.join();
   }
-  size_t depth() const { return workers_.empty() ? 1 : workers_.size() * 4; }
+  // blocks inflated ahead of the consumer: enough (32 MB inflated) to keep the workers busy while the host driver parses
+  // and appends the previous chunk of records
+  size_t depth() const { return workers_.empty() ? 1 : std::max<size_t>(workers_.size() * 4, 512); }
   std::future<std::vector<uint8_t>> submit(std::vector<uint8_t> cdata, uint32_t isize) {
     auto task = std::make_shared<std::packaged_task<std::vector<uint8_t>()>>([c = std::move(cdata), isize] { return inflate_block(c, isize); });
     auto fut = task->get_future();
@@ -126,7 +128,10 @@ BamReader::~BamReader() { pending_.clear(); pool_.reset(); if (f_) fclose(f_); }
 bool BamReader::enqueue_block() {
   if (raw_eof_) return false;
   uint8_t hdr[18];
-  if (fseeko(f_, (off_t)read_coff_, SEEK_SET) != 0) { raw_eof_ = true; return false; }
+  if (file_pos_ != read_coff_) {   // sequential reads need no seek (a seek drops the stdio buffer)
+    if (fseeko(f_, (off_t)read_coff_, SEEK_SET) != 0) { raw_eof_ = true; return false; }
+    file_pos_ = read_coff_;
+  }
   size_t k = fread(hdr, 1, 18, f_);
   if (k == 0) { raw_eof_ = true; return false; }
   if (k < 18 || hdr[0] != 31 || hdr[1] != 139 || !(hdr[3] & 4)) throw Error(HLAC_ERR_FORMAT, "bad BGZF block header");
@@ -151,6 +156,7 @@ bool BamReader::enqueue_block() {
   pd.data = pool_->submit(std::move(cdata), isize);
   pending_.push_back(std::move(pd));
   read_coff_ += bsize;
+  file_pos_ = read_coff_;
   return true;
 }
 
@@ -181,6 +187,7 @@ void BamReader::seek_virtual(uint64_t voff) {
   pending_.clear();   // drop the blocks inflated ahead of the old position
   next_coff_ = read_coff_ = voff >> 16; raw_eof_ = false;
   block_.clear(); block_pos_ = 0;
+  carry_.clear(); one_.recs.clear(); one_pos_ = 0;
   if ((voff & 0xFFFF) != 0) {
     if (!read_block()) throw Error(HLAC_ERR_FORMAT, "bad virtual offset");
     block_pos_ = std::min<size_t>(voff & 0xFFFF, block_.size());
@@ -209,65 +216,116 @@ void BamReader::fetch_unmapped() {
   seek_virtual(unmapped_voff_);
 }
 
-bool BamReader::next(BamRecord& out) {
-  static const uint8_t nt16_to_2bit[16] = {0, 0, 1, 0, 2, 0, 0, 0, 3, 0, 0, 0, 0, 0, 0, 0};   // "=ACMGRSVTWYHKDBN"
-  while (!done_) {
-    int32_t bs;
-    if (!read_bytes(&bs, 4)) { done_ = true; break; }
+size_t BamReader::frame(Chunk& chunk, size_t max_records) {
+  std::vector<uint8_t>& buf = chunk.buf;
+  chunk.recs.clear();
+  buf.clear();
+  buf.swap(carry_);                               // the tail the previous chunk could not use (possibly a partial record)
+  std::vector<std::pair<size_t, size_t>> found;   // offsets: the buffer may still grow (and move) while framing
+  size_t at = 0;
+  auto fill = [&](size_t need_to) {               // make buf hold at least need_to bytes; false at end of file
+    while (buf.size() < need_to) {
+      if (block_pos_ == block_.size()) { if (!read_block()) return false; if (block_.empty()) continue; }
+      buf.insert(buf.end(), block_.begin() + (ptrdiff_t)block_pos_, block_.end());
+      block_pos_ = block_.size();
+    }
+    return true;
+  };
+  while (!done_ && found.size() < max_records) {
+    if (!fill(at + 4)) { if (buf.size() > at) throw Error(HLAC_ERR_FORMAT, "BAM record truncated"); done_ = true; break; }
+    const int32_t bs = rd<int32_t>(buf.data() + at);
     if (bs < 32) throw Error(HLAC_ERR_FORMAT, "bad BAM record size");
-    rec_.resize(bs);
-    if (!read_bytes(rec_.data(), bs)) throw Error(HLAC_ERR_FORMAT, "BAM record truncated");
-    const uint8_t* r = rec_.data();
+    if (!fill(at + 4 + (size_t)bs)) throw Error(HLAC_ERR_FORMAT, "BAM record truncated");
+    const uint8_t* r = buf.data() + at + 4;
     const int32_t tid = rd<int32_t>(r), pos = rd<int32_t>(r + 4);
-    const uint8_t l_name = r[8];
-    const uint16_t n_cigar = rd<uint16_t>(r + 12), flag = rd<uint16_t>(r + 14);
-    const int32_t l_seq = rd<int32_t>(r + 16);
+    at += 4 + (size_t)bs;
     if (sel_tid_ >= 0) {
       if (tid > sel_tid_ || tid < 0 || (tid == sel_tid_ && pos >= sel_end_)) { done_ = true; break; }   // coordinate sorted
       if (tid < sel_tid_) continue;
     } else if (tid != -1) continue;
-    size_t p = 32 + l_name;
-    if (p + 4ull * n_cigar + (l_seq + 1) / 2 + l_seq > (size_t)bs) throw Error(HLAC_ERR_FORMAT, "BAM record fields overrun");
-    if (sel_tid_ >= 0) {
-      int64_t ref_len = 0;
-      for (uint16_t c = 0; c < n_cigar; c++) {
-        uint32_t op = rd<uint32_t>(r + p + 4 * c);
-        uint32_t k = op & 15;
-        if (k == 0 || k == 2 || k == 3 || k == 7 || k == 8) ref_len += op >> 4;
-      }
-      const int64_t endpos = pos + (ref_len > 0 ? ref_len : 1);
-      if (!(pos < sel_end_ && endpos > sel_beg_)) continue;
+    found.emplace_back(at - (size_t)bs, (size_t)bs);
+  }
+  if (!done_ && at < buf.size()) carry_.assign(buf.begin() + (ptrdiff_t)at, buf.end());
+  chunk.recs.reserve(found.size());
+  for (auto& f : found) chunk.recs.push_back({buf.data() + f.first, f.second});
+  return chunk.recs.size();
+}
+
+bool BamReader::parse(const uint8_t* r, size_t bs, RecView& out) const {
+  const int32_t pos = rd<int32_t>(r + 4);
+  const uint8_t l_name = r[8];
+  const uint16_t n_cigar = rd<uint16_t>(r + 12), flag = rd<uint16_t>(r + 14);
+  const int32_t l_seq = rd<int32_t>(r + 16);
+  size_t p = 32 + (size_t)l_name;
+  if (l_seq < 0 || p + 4ull * n_cigar + ((size_t)l_seq + 1) / 2 + (size_t)l_seq > bs) throw Error(HLAC_ERR_FORMAT, "BAM record fields overrun");
+  if (sel_tid_ >= 0) {
+    int64_t ref_len = 0;
+    for (uint16_t c = 0; c < n_cigar; c++) {
+      const uint32_t op = rd<uint32_t>(r + p + 4 * c), k = op & 15;
+      if (k == 0 || k == 2 || k == 3 || k == 7 || k == 8) ref_len += op >> 4;
     }
-    p += 4ull * n_cigar;
-    const uint8_t* sq = r + p;
-    p += (l_seq + 1) / 2 + l_seq;
-    // aux: only CB:Z and UB:Z matter (config.rs:17-18)
-    bool has_cb = false, has_ub = false;
-    while (p + 3 <= (size_t)bs) {
-      const char t0 = r[p], t1 = r[p + 1], ty = r[p + 2];
-      p += 3;
-      if (ty == 'Z' || ty == 'H') {
-        size_t e = p; while (e < (size_t)bs && r[e]) e++;
-        if (ty == 'Z' && t0 == 'C' && t1 == 'B') { out.barcode.assign((const char*)r + p, e - p); has_cb = true; }
-        if (ty == 'Z' && t0 == 'U' && t1 == 'B') { out.umi.assign((const char*)r + p, e - p); has_ub = true; }
-        p = e + 1;
-      } else if (ty == 'A' || ty == 'c' || ty == 'C') p += 1;
-      else if (ty == 's' || ty == 'S') p += 2;
-      else if (ty == 'i' || ty == 'I' || ty == 'f') p += 4;
-      else if (ty == 'B') {
-        if (p + 5 > (size_t)bs) break;
-        const char sub = r[p]; const int32_t cnt = rd<int32_t>(r + p + 1);
-        const int w = (sub == 'c' || sub == 'C') ? 1 : (sub == 's' || sub == 'S') ? 2 : 4;
-        p += 5 + (size_t)cnt * w;
-      } else throw Error(HLAC_ERR_FORMAT, "bad BAM aux type");
-    }
-    if (!has_cb || !has_ub) continue;   // mapping.rs:254-270
-    out.seq.resize(l_seq);
-    for (int32_t i = 0; i < l_seq; i++) out.seq[i] = nt16_to_2bit[(sq[i >> 1] >> ((i & 1) ? 0 : 4)) & 15];
-    out.primary = !((flag & 0x100) || (flag & 0x800));
+    const int64_t endpos = pos + (ref_len > 0 ? ref_len : 1);
+    if (!(pos < sel_end_ && endpos > sel_beg_)) return false;
+  }
+  p += 4ull * n_cigar;
+  out.seq4 = r + p; out.l_seq = l_seq;
+  p += ((size_t)l_seq + 1) / 2 + (size_t)l_seq;
+  // aux: only CB:Z and UB:Z matter (config.rs:17-18)
+  bool has_cb = false, has_ub = false;
+  while (p + 3 <= bs) {
+    const char t0 = (char)r[p], t1 = (char)r[p + 1], ty = (char)r[p + 2];
+    p += 3;
+    if (ty == 'Z' || ty == 'H') {
+      const void* z = memchr(r + p, 0, bs - p);
+      const size_t e = z ? (size_t)((const uint8_t*)z - r) : bs;
+      if (ty == 'Z' && t0 == 'C' && t1 == 'B') { out.cb = (const char*)r + p; out.cb_len = (uint32_t)(e - p); has_cb = true; }
+      if (ty == 'Z' && t0 == 'U' && t1 == 'B') { out.ub = (const char*)r + p; out.ub_len = (uint32_t)(e - p); has_ub = true; }
+      p = e + 1;
+    } else if (ty == 'A' || ty == 'c' || ty == 'C') p += 1;
+    else if (ty == 's' || ty == 'S') p += 2;
+    else if (ty == 'i' || ty == 'I' || ty == 'f') p += 4;
+    else if (ty == 'B') {
+      if (p + 5 > bs) break;
+      const char sub = (char)r[p]; const int32_t cnt = rd<int32_t>(r + p + 1);
+      const int w = (sub == 'c' || sub == 'C') ? 1 : (sub == 's' || sub == 'S') ? 2 : 4;
+      p += 5 + (size_t)cnt * w;
+    } else throw Error(HLAC_ERR_FORMAT, "bad BAM aux type");
+  }
+  if (!has_cb || !has_ub) return false;   // mapping.rs:254-270
+  out.primary = !((flag & 0x100) || (flag & 0x800));
+  return true;
+}
+
+void BamReader::pack_2bit(const uint8_t* seq4, int32_t l_seq, uint64_t* words, uint32_t nwords) {
+  // one table lookup per byte = two bases: "=ACMGRSVTWYHKDBN" -> A C G T = 0 1 2 3, everything else 0
+  static const struct Lut { uint8_t v[256]; Lut() { static const uint8_t n2[16] = {0, 0, 1, 0, 2, 0, 0, 0, 3, 0, 0, 0, 0, 0, 0, 0};
+                                                     for (int b = 0; b < 256; b++) v[b] = (uint8_t)((n2[b >> 4] << 2) | n2[b & 15]); } } lut;
+  for (uint32_t w = 0; w < nwords; w++) words[w] = 0;
+  const int32_t full = l_seq >> 1;   // bytes holding two bases
+  for (int32_t b = 0; b < full; b++) {
+    const int32_t i = 2 * b;
+    if ((uint32_t)(i >> 5) >= nwords) return;
+    words[i >> 5] |= (uint64_t)lut.v[seq4[b]] << (60 - 2 * (i & 31));
+  }
+  if ((l_seq & 1) && (uint32_t)((l_seq - 1) >> 5) < nwords) {
+    const int32_t i = l_seq - 1;
+    words[i >> 5] |= (uint64_t)(lut.v[seq4[full]] >> 2) << (62 - 2 * (i & 31));
+  }
+}
+
+bool BamReader::next(BamRecord& out) {
+  static const uint8_t nt16_to_2bit[16] = {0, 0, 1, 0, 2, 0, 0, 0, 3, 0, 0, 0, 0, 0, 0, 0};   // "=ACMGRSVTWYHKDBN"
+  for (;;) {
+    if (one_pos_ == one_.recs.size()) { one_pos_ = 0; if (frame(one_, 4096) == 0) { one_.recs.clear(); return false; } }
+    const RawRec rr = one_.recs[one_pos_++];
+    RecView v;
+    if (!parse(rr.p, rr.n, v)) continue;
+    out.barcode.assign(v.cb, v.cb_len); out.umi.assign(v.ub, v.ub_len);
+    out.seq.resize(v.l_seq);
+    for (int32_t i = 0; i < v.l_seq; i++) out.seq[i] = nt16_to_2bit[(v.seq4[i >> 1] >> ((i & 1) ? 0 : 4)) & 15];
+    out.primary = v.primary;
     return true;
   }
-  return false;
 }
 
 }  // namespace hlac

@@ -32,6 +32,29 @@ class BamReader {
   bool next(BamRecord& out);
   const std::vector<std::string>& ref_names() const { return ref_names_; }
 
+  // ---- the same selection in two halves, so that the expensive half can run on many threads -------------------------
+  // frame(): find up to max_records raw records of the selection (fixed-field filters only: reference id, position
+  // beyond the region end). Whole inflated blocks are appended to the chunk's buffer and the record boundaries are walked
+  // in place: recs[i] = {pointer to record i's body (after its block_size word), size}, pointing into chunk.buf. The bytes
+  // of a record cut by the end of the chunk are carried over to the next call. Sequential and cheap (one memcpy per 64 KB
+  // block); uses the reader's state, so one frame() at a time - but it may run on its own thread while other threads
+  // parse() the previous chunk. Returns the number of records found; 0 at the end of the selection.
+  struct RawRec { const uint8_t* p; size_t n; };
+  struct Chunk { std::vector<uint8_t> buf; std::vector<RawRec> recs; };
+  size_t frame(Chunk& chunk, size_t max_records);
+  // parse(): overlap test (CIGAR) and the CB / UB aux scan of one framed record. const and thread-safe. false = the
+  // reference drops the record (no overlap with the region, or CB / UB missing: mapping.rs:254-270).
+  struct RecView {
+    const uint8_t* seq4 = nullptr;   // BAM 4-bit bases, two per byte
+    int32_t l_seq = 0;
+    const char* cb = nullptr; uint32_t cb_len = 0;
+    const char* ub = nullptr; uint32_t ub_len = 0;
+    bool primary = true;
+  };
+  bool parse(const uint8_t* rec, size_t size, RecView& out) const;
+  // 4-bit BAM bases -> 2-bit words (32 bases per u64, first base in the top bits; anything but ACGT -> A), nwords zero padded
+  static void pack_2bit(const uint8_t* seq4, int32_t l_seq, uint64_t* words, uint32_t nwords);
+
  private:
   bool read_block();                              // next inflated BGZF block into block_ (blocks are inflated ahead, in parallel)
   struct Pending { uint64_t coff, bsize; std::future<std::vector<uint8_t>> data; };
@@ -40,10 +63,13 @@ class BamReader {
   std::unique_ptr<InflatePool> pool_;
   uint64_t read_coff_ = 0;                        // file offset of the next raw block to read
   bool raw_eof_ = false;
+  uint64_t file_pos_ = ~0ull;                     // where the FILE* stands (~0: unknown)
   bool read_bytes(void* dst, size_t n);
   void seek_virtual(uint64_t voff);
   FILE* f_ = nullptr;
-  std::vector<uint8_t> block_, cbuf_, rec_;
+  std::vector<uint8_t> block_, cbuf_, rec_, carry_;   // carry_: inflated bytes framed past the last chunk's final record
+  Chunk one_;                                     // next(): records framed ahead
+  size_t one_pos_ = 0;
   size_t block_pos_ = 0;
   uint64_t first_record_voff_ = 0, block_coff_ = 0, next_coff_ = 0;
   std::vector<std::string> ref_names_;

@@ -9,13 +9,16 @@
 #include <charconv>
 #include <cmath>
 #include <cstring>
+#include <ctime>
 #include <fstream>
+#include <future>
 #include <iostream>
 #include <map>
 #include <sstream>
 #include <unordered_map>
 
 #include "bam_reader.hpp"
+#include "worker_pool.hpp"
 #include "common.hpp"
 #include "hla_fasta.hpp"
 
@@ -100,13 +103,17 @@ struct BatchBuilder {
   uint32_t wpr = 0; size_t cap; uint64_t n = 0;
   uint64_t* seq = nullptr; uint16_t* len = nullptr; uint32_t* cell = nullptr; uint32_t* umi = nullptr; uint8_t* flags = nullptr;
   std::unordered_map<std::string, uint32_t> umi_ids;   // UMIs that are not <=15 ACGT bases
-  explicit BatchBuilder(size_t capacity) : cap(capacity) {}
+  bool pinned;   // page-locked buffers for the H2D copies; pageable for the host-only self-check
+  explicit BatchBuilder(size_t capacity, bool pinned_ = true) : cap(capacity), pinned(pinned_) {}
   ~BatchBuilder() { release(); }
-  void release() { for (void* p : {(void*)seq, (void*)len, (void*)cell, (void*)umi, (void*)flags}) if (p) hlac_host_free(p); seq = nullptr; len = nullptr; cell = nullptr; umi = nullptr; flags = nullptr; }
+  void release() {
+    for (void* p : {(void*)seq, (void*)len, (void*)cell, (void*)umi, (void*)flags}) if (p) { if (pinned) hlac_host_free(p); else free(p); }
+    seq = nullptr; len = nullptr; cell = nullptr; umi = nullptr; flags = nullptr;
+  }
   void alloc(uint32_t words) {
     release(); wpr = words;
-    check(hlac_host_alloc(cap * wpr * 8, (void**)&seq)); check(hlac_host_alloc(cap * 2, (void**)&len));
-    check(hlac_host_alloc(cap * 4, (void**)&cell)); check(hlac_host_alloc(cap * 4, (void**)&umi)); check(hlac_host_alloc(cap, (void**)&flags));
+    auto get = [&](size_t bytes, void** out) { if (pinned) check(hlac_host_alloc(bytes, out)); else if (!(*out = malloc(bytes))) throw Error(HLAC_ERR_IO, "out of memory"); };
+    get(cap * wpr * 8, (void**)&seq); get(cap * 2, (void**)&len); get(cap * 4, (void**)&cell); get(cap * 4, (void**)&umi); get(cap, (void**)&flags);
   }
   uint32_t umi_key(const std::string& u) {
     uint32_t k;
@@ -127,19 +134,99 @@ struct BatchBuilder {
 };
 
 // Streams the selected BAM records into a session through pinned batches. `flush` pushes one batch and syncs.
-template <typename CellFn, typename Flush>
-uint64_t stream_records(BamReader& bam, BatchBuilder& bb, CellFn cell_of, Flush flush) {
-  BamRecord rec; uint64_t total = 0;
-  while (bam.next(rec)) {
-    if (rec.seq.size() > 65535) throw Error(HLAC_ERR_LIMIT, "read longer than 65535 bases");
-    if (!bb.fits(rec.seq.size())) {
-      if (bb.n) { flush(); bb.n = 0; }
-      const uint32_t need = std::max<uint32_t>(3, (uint32_t)((rec.seq.size() + 31) / 32));
-      if (need > 16) throw Error(HLAC_ERR_LIMIT, "read longer than 512 bases");
-      if (need > bb.wpr) bb.alloc(need);
+// The reader frames raw records sequentially (a copy), then a pool of host threads does the expensive part per record
+// - overlap test, CB / UB aux scan, UMI key, 4-bit -> 2-bit packing, and the barcode lookup when `cell_of` is a pure
+// function (the counting whitelist) - and one thread appends the survivors to the batch in file order. cell_of(cb, ub)
+// with side effects (first-seen barcode ids in mapping_wrapper) runs in that ordered append instead.
+struct StrRef { const char* p; uint32_t n; std::string str() const { return std::string(p, n); } };
+
+WorkerPool& host_pool() {
+  static WorkerPool pool([] {
+    unsigned n = std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+    if (const char* e = getenv("HLAC_BAM_THREADS")) n = (unsigned)std::max(1, atoi(e));
+    return n; }());
+  return pool;
+}
+
+// cell_try(cb): optional read-only pre-lookup for a cell_of with side effects - it runs on the parser threads while nothing
+// is being inserted and returns CELL_UNKNOWN when the ordered append has to call cell_of (a barcode not seen before).
+constexpr uint32_t CELL_UNKNOWN = 0xFFFFFFFEu;
+struct NoCellTry { uint32_t operator()(StrRef) const { return CELL_UNKNOWN; } };
+
+template <typename CellFn, typename Flush, typename CellTry = NoCellTry>
+uint64_t stream_records(BamReader& bam, BatchBuilder& bb, CellFn cell_of, Flush flush, bool cell_of_is_pure, CellTry cell_try = CellTry()) {
+  constexpr size_t CHUNK = 1 << 16, GRAIN = 1024;
+  constexpr uint32_t UMI_INTERN = 0xFFFFFFFFu;
+  WorkerPool& pool = host_pool();
+  std::vector<uint8_t> ok; std::vector<uint64_t> words; std::vector<BamReader::RecView> views; std::vector<uint32_t> ukey, cells;
+  uint64_t total = 0;
+  const bool dbg = getenv("HLAC_DEBUG_TIMING") != nullptr;
+  double t_frame = 0, t_parse = 0, t_pack = 0, t_append = 0, t_work = 0;
+  auto now = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + ts.tv_nsec * 1e-9; };
+  struct Report { bool on; double &a, &b, &c, &d, &e; ~Report() { if (on) fprintf(stderr, "[hlac timing] ingest: wait for frames %.3f s (framing itself %.3f s on the helper thread), parse %.3f s, pack %.3f s, append %.3f s\n", a, e, b, c, d); } } report{dbg, t_frame, t_parse, t_pack, t_append, t_work};
+  // two chunks in flight: while this thread and the pool parse / append chunk k (and the session maps the batch it flushes),
+  // a helper thread frames chunk k + 1 (which is also what keeps the inflate workers fed)
+  BamReader::Chunk chunks[2];
+  int cur = 0;
+  double t0 = now();
+  size_t n = bam.frame(chunks[0], CHUNK);
+  t_frame += now() - t0;
+  for (; n > 0; cur ^= 1) {
+    const std::vector<BamReader::RawRec>& recs = chunks[cur].recs;
+    std::future<size_t> next = std::async(std::launch::async, [&bam, &chunks, cur, &t_work, &now] { const double a = now(); const size_t k = bam.frame(chunks[cur ^ 1], CHUNK); t_work += now() - a; return k; });
+    struct Join { std::future<size_t>& f; ~Join() { if (f.valid()) f.wait(); } } join{next};   // never leave the helper running behind an exception
+    t0 = now();
+    views.resize(n); ok.assign(n, 0); ukey.resize(n); cells.resize(n);
+    pool.for_ranges(n, GRAIN, [&](size_t b, size_t e) {
+      for (size_t i = b; i < e; i++) {
+        BamReader::RecView& v = views[i];
+        if (!bam.parse(recs[i].p, recs[i].n, v)) continue;
+        if (v.l_seq > 65535) throw Error(HLAC_ERR_LIMIT, "read longer than 65535 bases");
+        if (v.l_seq > 512) throw Error(HLAC_ERR_LIMIT, "read longer than 512 bases");
+        ok[i] = 1;
+        uint32_t k = UMI_INTERN;   // hlac_umi_key: <= 15 ACGT bases -> (1 << 2n) | 2-bit value, anything else is interned
+        if (v.ub_len <= 15) {
+          k = 1;
+          for (uint32_t j = 0; j < v.ub_len; j++) {
+            const char c = v.ub[j];
+            const uint32_t code = c == 'A' ? 0u : c == 'C' ? 1u : c == 'G' ? 2u : c == 'T' ? 3u : 4u;
+            if (code > 3) { k = UMI_INTERN; break; }
+            k = (k << 2) | code;
+          }
+        }
+        ukey[i] = k;
+        cells[i] = cell_of_is_pure ? cell_of(StrRef{v.cb, v.cb_len}, StrRef{v.ub, v.ub_len}) : cell_try(StrRef{v.cb, v.cb_len});
+      }
+    });
+    t_parse += now() - t0; t0 = now();
+    uint32_t need = 3;
+    for (size_t i = 0; i < n; i++) if (ok[i]) need = std::max<uint32_t>(need, (uint32_t)((views[i].l_seq + 31) / 32));
+    words.resize(n * (size_t)need);
+    pool.for_ranges(n, GRAIN, [&](size_t b, size_t e) {
+      for (size_t i = b; i < e; i++) if (ok[i]) BamReader::pack_2bit(views[i].seq4, views[i].l_seq, words.data() + i * need, need);
+    });
+    t_pack += now() - t0; t0 = now();
+    for (size_t i = 0; i < n; i++) {
+      if (!ok[i]) continue;
+      const BamReader::RecView& v = views[i];
+      if (!bb.fits((size_t)v.l_seq)) {
+        if (bb.n) { flush(); bb.n = 0; }
+        const uint32_t want = std::max<uint32_t>(3, (uint32_t)((v.l_seq + 31) / 32));
+        if (want > bb.wpr) bb.alloc(want);
+      }
+      uint64_t* w = bb.seq + bb.n * bb.wpr;
+      const uint32_t have = (uint32_t)((v.l_seq + 31) / 32);   // words carrying bases; the rest of both rows is zero
+      for (uint32_t j = 0; j < bb.wpr; j++) w[j] = j < have ? words[i * need + j] : 0;
+      bb.len[bb.n] = (uint16_t)v.l_seq;
+      bb.cell[bb.n] = (cell_of_is_pure || cells[i] != CELL_UNKNOWN) ? cells[i] : cell_of(StrRef{v.cb, v.cb_len}, StrRef{v.ub, v.ub_len});
+      bb.umi[bb.n] = ukey[i] != UMI_INTERN ? ukey[i] : bb.umi_key(std::string(v.ub, v.ub_len));
+      bb.flags[bb.n] = v.primary ? HLAC_FLAG_PRIMARY : 0;
+      bb.n++;
+      total++;
     }
-    bb.add(rec, cell_of(rec));
-    total++;
+    t_append += now() - t0; t0 = now();
+    n = next.get();
+    t_frame += now() - t0;   // time spent WAITING for the next chunk
   }
   if (bb.n) { flush(); bb.n = 0; }
   return total;
@@ -225,12 +312,15 @@ std::string mapping_impl(hlac_index* index, const char* outdir, const char* bam,
   std::unordered_map<std::string, uint32_t> umi_idx;
   BamReader reader(bam);
   std::unordered_map<std::string, uint32_t> bc_ids;   // mapping_wrapper uses every barcode (no whitelist)
-  auto cell_of = [&](const BamRecord& r) {
-    const uint32_t id = bc_ids.emplace(r.barcode, (uint32_t)bc_ids.size()).first->second;
+  std::string key;   // reused buffer: one hash lookup per record, no allocation
+  auto cell_of = [&](StrRef cb, StrRef ub) {
+    key.assign(cb.p, cb.n);
+    const uint32_t id = bc_ids.emplace(key, (uint32_t)bc_ids.size()).first->second;
     if (bincode) {
-      if (id == bc_names.size()) bc_names.push_back(r.barcode);
-      auto it = umi_idx.find(r.umi);
-      if (it == umi_idx.end()) { it = umi_idx.emplace(r.umi, (uint32_t)umi_names.size()).first; umi_names.push_back(r.umi); }
+      if (id == bc_names.size()) bc_names.push_back(key);
+      key.assign(ub.p, ub.n);
+      auto it = umi_idx.find(key);
+      if (it == umi_idx.end()) { it = umi_idx.emplace(key, (uint32_t)umi_names.size()).first; umi_names.push_back(key); }
       read_bc.push_back(id); read_umi.push_back(it->second);
     }
     return id;
@@ -247,11 +337,14 @@ std::string mapping_impl(hlac_index* index, const char* outdir, const char* bam,
   };
   if (region) { Locus l = parse_locus(region); reader.fetch(l.chrom, l.start, l.end); }
   else reader.fetch_unmapped();   // locus == None never happens from main.rs; keep the call total
-  uint64_t rid = stream_records(reader, bb, cell_of, [&] { hlac_batch b = bb.batch(); check(hlac_geno_push(g.p, &b, 0)); });
+  // barcodes seen in earlier chunks are resolved on the parser threads (read-only lookups; inserts only happen in the ordered
+  // append, between two parallel stages); the bincode hand-over needs every record to pass through cell_of
+  auto cell_try = [&](StrRef cb) { if (bincode) return CELL_UNKNOWN; auto it = bc_ids.find(cb.str()); return it == bc_ids.end() ? CELL_UNKNOWN : it->second; };
+  uint64_t rid = stream_records(reader, bb, cell_of, [&] { hlac_batch b = bb.batch(); check(hlac_geno_push(g.p, &b, 0)); }, false, cell_try);
   report("", rid);
   if (use_unmapped) {
     reader.fetch_unmapped();
-    uint64_t rid2 = stream_records(reader, bb, cell_of, [&] { hlac_batch b = bb.batch(); check(hlac_geno_push(g.p, &b, 1)); });
+    uint64_t rid2 = stream_records(reader, bb, cell_of, [&] { hlac_batch b = bb.batch(); check(hlac_geno_push(g.p, &b, 1)); }, false, cell_try);
     report(" unaligned", rid2);
   }
   hlac_class_tables t{};
@@ -359,8 +452,9 @@ int hlac_map_and_count_pseudo(const char* bam, const char* out_dir, const char* 
   BamReader reader(bam);
   Locus l = parse_locus(region); reader.fetch(l.chrom, l.start, l.end);
   BatchBuilder bb(BATCH_READS);
-  auto cell_of = [&](const BamRecord& r) { auto it = barcodes.find(r.barcode); return it == barcodes.end() ? HLAC_NOT_A_CELL : it->second; };
-  stream_records(reader, bb, cell_of, [&] { hlac_batch b = bb.batch(); check(hlac_count_push(s.p, &b)); check(hlac_count_sync(s.p)); });
+  // the whitelist is read-only here: the lookup is a pure function and runs on the parser threads
+  auto cell_of = [&](StrRef cb, StrRef) { auto it = barcodes.find(cb.str()); return it == barcodes.end() ? HLAC_NOT_A_CELL : it->second; };
+  stream_records(reader, bb, cell_of, [&] { hlac_batch b = bb.batch(); check(hlac_count_push(s.p, &b)); check(hlac_count_sync(s.p)); }, true);
   hlac_metrics m{}; hlac_coo tmp{}; check(hlac_count_finish(s.p, &tmp, &m));
   if (entries) {   // the session (and its pinned result buffer) ends with this call: hand out owned copies
     *entries = tmp; entries->borrowed = 0;
@@ -393,6 +487,41 @@ int hlac_bam_scan(const char* bam, const char* region, uint64_t* n_records, uint
   }
   if (n_records) *n_records = n;
   if (checksum) *checksum = h;
+  HLAC_API_CATCH
+}
+
+// Self-check of the batch path the wrappers use (frame -> parallel parse / pack -> ordered append): FNV-1a over what the
+// sessions receive per record - the 2-bit words that carry bases, length, cell (first-seen barcode id, as mapping_wrapper
+// numbers them), UMI key, flags - in file order. Runs the selection twice, with the barcode lookup in the ordered append
+// and (using the ids of the first run) on the parser threads; both must agree.
+int hlac_bam_batch_checksum(const char* bam, const char* region, uint64_t* n_records, uint64_t* checksum) {
+  HLAC_API_TRY
+  if (!bam) throw Error(HLAC_ERR_ARG, "null argument");
+  std::unordered_map<std::string, uint32_t> ids;
+  uint64_t sums[2] = {0, 0}, counts[2] = {0, 0};
+  for (int pass = 0; pass < (checksum ? 2 : 1); pass++) {   // checksum == NULL: one pass, nothing hashed (ingest timing)
+    BamReader reader(bam);
+    if (region) { Locus l = parse_locus(region); reader.fetch(l.chrom, l.start, l.end); } else reader.fetch_unmapped();
+    BatchBuilder bb(1 << 10, false);   // small pageable batches: several flushes even on the fixture, no device needed
+    uint64_t h = 0xcbf29ce484222325ULL;
+    auto mix = [&](const void* p, size_t k) { const uint8_t* b = (const uint8_t*)p; for (size_t i = 0; i < k; i++) h = (h ^ b[i]) * 0x100000001b3ULL; };
+    auto flush = [&] {
+      if (!checksum) return;
+      for (uint64_t i = 0; i < bb.n; i++) {
+        mix(bb.seq + i * bb.wpr, (size_t)((bb.len[i] + 31) / 32) * 8);
+        for (uint32_t j = (bb.len[i] + 31) / 32; j < bb.wpr; j++) if (bb.seq[i * bb.wpr + j]) throw Error(HLAC_ERR_STATE, "padding words are not zero");
+        mix(bb.len + i, 2); mix(bb.cell + i, 4); mix(bb.umi + i, 4); mix(bb.flags + i, 1);
+      }
+    };
+    std::string key;
+    if (pass == 0) counts[0] = stream_records(reader, bb, [&](StrRef cb, StrRef) { key.assign(cb.p, cb.n); return ids.emplace(key, (uint32_t)ids.size()).first->second; }, flush, false,
+                                              [&](StrRef cb) { auto it = ids.find(cb.str()); return it == ids.end() ? CELL_UNKNOWN : it->second; });
+    else counts[1] = stream_records(reader, bb, [&](StrRef cb, StrRef) { return ids.at(cb.str()); }, flush, true);
+    sums[pass] = h;
+  }
+  if (checksum && (sums[0] != sums[1] || counts[0] != counts[1])) throw Error(HLAC_ERR_STATE, "ordered and parallel barcode lookups disagree");
+  if (n_records) *n_records = counts[0];
+  if (checksum) *checksum = sums[0];
   HLAC_API_CATCH
 }
 

@@ -104,6 +104,49 @@ def test_bam_reader_matches_independent_decoder(sb, fixture_reads):
     assert L.hlac_bam_scan(bam, b"chr6:1-2", C.byref(n), C.byref(h)) != 0   # '6' vs 'chr6' (mapping.rs:54)
 
 
+def _batch_checksum(reads, pack):
+    """what hlac_bam_batch_checksum hashes, from an independent decode: the batch H.make_batch builds"""
+    seq, lens, cell, umi, flags = H.make_batch(reads, None, pack=pack)
+    x = 0xcbf29ce484222325
+    for i in range(len(lens)):
+        nw = (int(lens[i]) + 31) // 32
+        data = seq[i, :nw].astype("<u8").tobytes() + int(lens[i]).to_bytes(2, "little") + int(cell[i]).to_bytes(4, "little") \
+            + int(umi[i]).to_bytes(4, "little") + bytes([int(flags[i])])
+        for b in data:
+            x = ((x ^ b) * 0x100000001b3) & 0xFFFFFFFFFFFFFFFF
+    return x
+
+
+def test_bam_batch_path_matches_independent_decoder(sb, fixture_reads, tmp_path):
+    """The wrappers' ingest (records framed sequentially, parsed / packed on host threads, appended in file order) must
+    hand the sessions exactly the batch an independent decode of the BAM gives: 2-bit words, lengths, first-seen barcode
+    ids, UMI keys, flags - on the reference's fixture and on a synthetic BAM with dropped records and an unmapped tail."""
+    import bamlite
+    L = sb.lib()
+    n, h = C.c_uint64(), C.c_uint64()
+    bam = os.path.join(H.FIX, "test.bam").encode()
+    for threads in ("1", "3"):
+        os.environ["HLAC_BAM_THREADS"] = threads   # read when the reader / pool is created
+        assert L.hlac_bam_batch_checksum(bam, b"6:28510120-33480577", C.byref(n), C.byref(h)) == 0, L.hlac_last_error()
+        assert n.value == 2864 and h.value == _batch_checksum(fixture_reads, sb.pack_reads)
+    os.environ.pop("HLAC_BAM_THREADS")
+    sub = list(bamlite.fetch(os.path.join(H.FIX, "test.bam"), "6", 31268749, 31272092))
+    assert L.hlac_bam_batch_checksum(bam, b"6:31268749-31272092", C.byref(n), C.byref(h)) == 0
+    assert n.value == len(sub) and h.value == _batch_checksum(sub, sb.pack_reads)
+    import subprocess
+    import sys
+    syn = str(tmp_path / "syn.bam")
+    subprocess.check_call([sys.executable, os.path.join(H.ROOT, "tools", "make_bam.py"), syn, "6000", "700"], stdout=subprocess.DEVNULL)
+    mapped = list(bamlite.fetch(syn, "6", 28510120, 33480577))
+    assert 5000 < len(mapped) < 6000                      # every 97th record has no UB and is dropped
+    assert L.hlac_bam_batch_checksum(syn.encode(), b"6:28510120-33480577", C.byref(n), C.byref(h)) == 0, L.hlac_last_error()
+    assert n.value == len(mapped) and h.value == _batch_checksum(mapped, sb.pack_reads)
+    tail = list(bamlite.fetch_unmapped(syn))
+    assert 600 < len(tail) < 700
+    assert L.hlac_bam_batch_checksum(syn.encode(), None, C.byref(n), C.byref(h)) == 0
+    assert n.value == len(tail) and h.value == _batch_checksum(tail, sb.pack_reads)
+
+
 def test_no_cpu_fallback(sb):
     """Compute entry points must fail loudly without a CUDA device."""
     try:
