@@ -171,6 +171,9 @@ def main():
     ap.add_argument("--chunk", type=int, default=1_000_000, help="e2e push chunk in reads (0 = whole batch)")
     ap.add_argument("--genes", type=int, default=3, choices=[3, 4, 5, 6, 7, 8],
                     help="3 = the six fixture alleles (config 2); 8 = 2 synthetic alleles x 8 genes (config 4 shape)")
+    ap.add_argument("--e2e-format", default="packed", choices=["packed", "soa"],
+                    help="host input format of the end-to-end leg: packed 32-byte records (hlac_count_push_packed) or the five "
+                         "SoA arrays (hlac_count_push, 35 B/read)")
     ap.add_argument("--merge", default="none", choices=["none", "allreduce"],
                     help="N > 1: 'none' = every rank keeps the columns of its own barcodes (shard-local cell indices, no "
                          "data-path collective); 'allreduce' = global cell indices, one NCCL all-reduce of the dense matrix, "
@@ -277,12 +280,24 @@ def main():
           "umi": hn["umi"].view(np.uint32), "flags": hn["flags"]}
     chunk = args.chunk or n
 
-    def step_e2e():
+    def step_e2e_soa():
         sess.reset()
         for a in range(0, n, chunk):
             b = min(n, a + chunk)
             sess.push(hn["seq"][a:b], hn["len"][a:b], hn["cell"][a:b], hn["umi"][a:b], hn["flags"][a:b])
         return finish_step()
+
+    # the same batch as packed records (hlac_packed_batch: 32 B per 91-bp read, one H2D copy per push), in pinned memory
+    hrec_t = torch.from_numpy(sb.pack_records(hn["seq"], hn["len"], hn["cell"], hn["umi"], hn["flags"]).view(np.int64)).pin_memory()
+    hrec = hrec_t.numpy().view(np.uint64)
+
+    def step_e2e_packed():
+        sess.reset()
+        for a in range(0, n, chunk):
+            sess.push_packed(hrec[a:min(n, a + chunk)])
+        return finish_step()
+
+    step_e2e = step_e2e_packed if args.e2e_format == "packed" else step_e2e_soa
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
@@ -338,7 +353,7 @@ def main():
     value = total_reads / (per_step_ms / 1e3)
     e2e_ms = ms_e2e / args.steps
     # host-side gaps (sync for the key count, COO extraction) are inside both event-bracketed regions
-    in_bytes = sum(int(v.nbytes) for v in hn.values())
+    in_bytes = int(hrec.nbytes) if args.e2e_format == "packed" else sum(int(v.nbytes) for v in hn.values())
     d2h_bytes = d2h_own
 
     line = None
@@ -366,7 +381,9 @@ def main():
                 "ms_per_step": per_step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u32", "data": "synthetic", "config": config,
                 "e2e": {"value": total_reads / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": in_bytes * world,
-                        "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_ms, "h2d_ms": tm_e2e["h2d_ms"]},
+                        "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_ms, "h2d_ms": tm_e2e["h2d_ms"],
+                        "input_format": "packed records, %d B/read (hlac_count_push_packed)" % (in_bytes // n) if args.e2e_format == "packed"
+                        else "five SoA arrays, %d B/read (hlac_count_push)" % (in_bytes // n)},
                 # our own kernels in the timed region per step (device-resident loop); the radix sort between them is
                 # cub (library): histogram + exclusive-sum + one onesweep pass per 8 key bits
                 "gpu_launches": 5 * args.steps,   # k_count_map, k_consensus, k_coo_count, k_coo_scan, k_coo_write

@@ -68,6 +68,21 @@ typedef struct {
   const uint64_t* ordinal;
 } hlac_batch;
 
+/* The same records for the counting path as ONE array of fixed-size records (words_per_read + 1 u64 per read): the
+ * sequence words as in hlac_batch.seq, then a meta word
+ *     umi << 32 | primary << 31 | len << 23 | cell        (len <= 255 bases; cell 23 bits, HLAC_PACKED_NOT_A_CELL)
+ * 32 bytes per 91-bp read instead of the 35 of the five SoA arrays, and one host-to-device copy per push instead of
+ * five - the counting path end to end is bound by exactly that copy. hlac_pack_records converts an hlac_batch. */
+#define HLAC_PACKED_NOT_A_CELL 0x7FFFFFu
+#define HLAC_PACKED_META(umi, primary, len, cell) \
+  (((uint64_t)(uint32_t)(umi) << 32) | ((uint64_t)((primary) ? 1u : 0u) << 31) | ((uint64_t)((len) & 0xFFu) << 23) | \
+   (uint64_t)((cell) & 0x7FFFFFu))
+typedef struct {
+  const uint64_t* rec; /* n * (words_per_read + 1) u64 */
+  uint64_t n;
+  uint32_t words_per_read;
+} hlac_packed_batch;
+
 typedef struct { /* mapping.rs:108-116 `Metrics` */
   uint64_t num_reads, num_non_primary, num_not_cell_bc, num_cds_align, num_gen_align, num_not_aligned;
 } hlac_metrics;
@@ -151,6 +166,13 @@ int hlac_count_set_stream(hlac_count*, void* cuda_stream);
 int hlac_count_reserve(hlac_count*, uint64_t total_reads);      /* optional: pre-size device buffers */
 int hlac_count_push(hlac_count*, const hlac_batch* host_batch); /* the hot loop mapping.rs:740-807, async */
 int hlac_count_push_device(hlac_count*, const hlac_batch* device_batch);
+/* the same push for packed records (sessions with n_cells < HLAC_PACKED_NOT_A_CELL); rec is HOST memory for _push_packed,
+ * DEVICE memory for _push_packed_device. Results are identical to pushing the equivalent hlac_batch. */
+int hlac_count_push_packed(hlac_count*, const hlac_packed_batch* host_batch);
+int hlac_count_push_packed_device(hlac_count*, const hlac_packed_batch* device_batch);
+/* host helper: hlac_batch (host pointers, len <= 255, cell < HLAC_PACKED_NOT_A_CELL or HLAC_NOT_A_CELL) -> packed records;
+ * rec must hold b->n * (b->words_per_read + 1) u64 */
+int hlac_pack_records(const hlac_batch* b, uint64_t* rec);
 int hlac_count_sync(hlac_count*);                               /* host batch buffers reusable after this */
 /* debug/parity: record per-read results (off by default), then fetch those of the LAST pushed batch:
  * code = gene*3+slot or HLAC_CODE_NONE */

@@ -34,6 +34,10 @@ class Batch(C.Structure):
                 ("flags", C.c_void_p), ("n", C.c_uint64), ("words_per_read", C.c_uint32), ("ordinal", C.c_void_p)]
 
 
+class PackedBatch(C.Structure):
+    _fields_ = [("rec", C.c_void_p), ("n", C.c_uint64), ("words_per_read", C.c_uint32)]
+
+
 class Metrics(C.Structure):
     _fields_ = [(k, C.c_uint64) for k in ("num_reads", "num_non_primary", "num_not_cell_bc", "num_cds_align",
                                           "num_gen_align", "num_not_aligned")]

@@ -128,6 +128,18 @@ def make_batch(seq, lens, cell, umi, flags):
     return b, (seq, lens, cell, umi, flags)
 
 
+PACKED_NOT_A_CELL = 0x7FFFFF
+
+
+def pack_records(seq, lens, cell, umi, flags):
+    """hlac_pack_records: the five SoA arrays -> one u64 [n, wpr + 1] array of packed records (sequence words, then
+    umi << 32 | primary << 31 | len << 23 | cell)."""
+    b, keep = make_batch(seq, lens, cell, umi, flags)
+    rec = np.zeros((int(b.n), int(b.words_per_read) + 1), dtype=np.uint64)
+    check(lib().hlac_pack_records(C.byref(b), _vp(rec)))
+    return rec
+
+
 class CountSession:
     """hlac_count: one map_and_count_pseudo run (src/mapping.rs:640-821)."""
 
@@ -172,6 +184,21 @@ class CountSession:
             check(lib().hlac_count_push(self.h, C.byref(b)))
         else:
             check(lib().hlac_count_push_device(self.h, C.byref(b)))
+
+    def push_packed(self, rec, n=None, words_per_read=None):
+        """packed records (pack_records): a numpy u64 [n, wpr + 1] array = host buffer, a torch CUDA tensor = device buffer"""
+        pb = _lib.PackedBatch()
+        if isinstance(rec, np.ndarray):
+            rec = np.ascontiguousarray(rec, dtype=np.uint64)
+            pb.n, pb.words_per_read = rec.shape[0], rec.shape[1] - 1
+            pb.rec = rec.ctypes.data
+            check(lib().hlac_count_push_packed(self.h, C.byref(pb)))
+        else:
+            pb.n = rec.shape[0] if n is None else n
+            pb.words_per_read = (rec.shape[1] - 1) if words_per_read is None else words_per_read
+            pb.rec = rec.data_ptr()
+            check(lib().hlac_count_push_packed_device(self.h, C.byref(pb)))
+        self._keep = rec
 
     def sync(self):
         check(lib().hlac_count_sync(self.h))

@@ -54,6 +54,7 @@ struct CountMapArgs {
   unsigned long long* cursor;  // number of keys appended so far
   unsigned long long* metrics; // [6] + [2] seed-filter tests / dictionary probes + [1] out-of-range cell indices + [1] max UMI key
   uint8_t* codes;              // optional per-read debug output
+  const uint64_t* rec;         // packed records (hlac_packed_batch) instead of the five arrays above, or NULL
 };
 
 // The session keeps its own copy of each index's node table in which the colour id (word 3 of the node record) is
@@ -247,7 +248,7 @@ __global__ void __launch_bounds__(MAP_THREADS, MINB) k_count_map(const CountMapA
 // round starts with all lanes busy whatever fraction of the reads survives each stage; scan rounds mix the four
 // orientations (same code, per-lane operands). The warp streams a contiguous range of the batch and refills the
 // pool with as many reads as there are free slots.
-template <bool SMEM_BM, int MAP_THREADS, int MINB>
+template <bool SMEM_BM, int MAP_THREADS, int MINB, bool PACKED>
 __global__ void __launch_bounds__(MAP_THREADS, MINB) k_count_map_q(const CountMapArgs a) {
   extern __shared__ __align__(16) uint32_t smem[];
   constexpr int NS = 64;
@@ -296,12 +297,23 @@ __global__ void __launch_bounds__(MAP_THREADS, MINB) k_count_map_q(const CountMa
       if (lane < c) {
         const uint64_t i = cur + lane;
         slot = fr[nfree - c + lane];
-        const uint8_t fl = __ldg(a.flags + i);
-        const uint32_t cell = __ldg(a.cell + i);
-        const uint16_t L = (uint16_t)min((uint32_t)__ldg(a.len + i), 32u * a.wpr);
+        uint8_t fl; uint32_t cell; uint16_t L;
+        const uint64_t* words;
+        if (PACKED) {   // one record per read: sequence words, then umi | primary | len | cell
+          words = a.rec + i * (a.wpr + 1);
+          const uint32_t meta = (uint32_t)__ldg(words + a.wpr);
+          fl = (meta >> 31) ? HLAC_FLAG_PRIMARY : 0;
+          cell = meta & HLAC_PACKED_NOT_A_CELL; if (cell == HLAC_PACKED_NOT_A_CELL) cell = HLAC_NOT_A_CELL;
+          L = (uint16_t)min((meta >> 23) & 0xFFu, 32u * a.wpr);
+        } else {
+          words = a.seq + i * a.wpr;
+          fl = __ldg(a.flags + i);
+          cell = __ldg(a.cell + i);
+          L = (uint16_t)min((uint32_t)__ldg(a.len + i), 32u * a.wpr);
+        }
         uint32_t* fw = rows + slot * a.row_stride;
         for (uint32_t w = 0; w < a.wpr; w++) {
-          const uint64_t v = __ldg(a.seq + i * a.wpr + w);
+          const uint64_t v = __ldg(words + w);
           fw[2 * w] = (uint32_t)(v >> 32); fw[2 * w + 1] = (uint32_t)v;
         }
         fw[2 * a.wpr] = 0; fw[2 * a.wpr + 1] = 0;
@@ -380,9 +392,11 @@ __global__ void __launch_bounds__(MAP_THREADS, MINB) k_count_map_q(const CountMa
         if (good) { if (p < 2) m_cds++; else m_gen++; }
         if (p == 0 || good) code = vis.code();   // a CDS-forward hit is used whatever its coverage (mapping.rs:772-775)
         if (code != CODE_NONE5) {
-          const uint32_t um = __ldg(a.umi + i);
+          uint32_t um, cl;
+          if (PACKED) { const uint64_t meta = __ldg(a.rec + i * (a.wpr + 1) + a.wpr); um = (uint32_t)(meta >> 32); cl = (uint32_t)meta & HLAC_PACKED_NOT_A_CELL; }
+          else { um = __ldg(a.umi + i); cl = __ldg(a.cell + i); }
           umi_max = max(umi_max, um);
-          key = ((uint64_t)um << (CODE_BITS + a.cell_bits)) | ((uint64_t)__ldg(a.cell + i) << CODE_BITS) | code;
+          key = ((uint64_t)um << (CODE_BITS + a.cell_bits)) | ((uint64_t)cl << CODE_BITS) | code;
           if (a.codes) a.codes[i] = (uint8_t)code;
         }
       }
@@ -541,7 +555,7 @@ struct hlac_count {
   DevBuf<uint32_t> nodes_cds, nodes_gen, gene_row0, dense;   // node tables with cinfo in place of the colour id
   DevBuf<uint64_t> keys, keys_sorted;
   struct Stage {   // one staging set for host batches; two of them so the H2D of batch i+1 overlaps the kernel of batch i
-    DevBuf<uint64_t> seq; DevBuf<uint16_t> len; DevBuf<uint32_t> cell, umi; DevBuf<uint8_t> flags;
+    DevBuf<uint64_t> seq, rec; DevBuf<uint16_t> len; DevBuf<uint32_t> cell, umi; DevBuf<uint8_t> flags;
     cudaEvent_t copied = nullptr, consumed = nullptr;
   } stage[2];
   cudaStream_t copy_stream = nullptr;
@@ -561,7 +575,7 @@ struct hlac_count {
   uint32_t cfg_wpr = 0;
   int cfg_occ = 0, cfg_r = 0, cfg_threads = 0;
   bool cfg_bm = false;
-  void* cfg_kern = nullptr;
+  void* cfg_kern = nullptr; void* cfg_kern_packed = nullptr;
   uint64_t n_keys = 0;
   // timing
   struct Ev { cudaEvent_t a, b; int kind; };
@@ -598,7 +612,7 @@ struct hlac_count {
     drain_events(); ms[0] = ms[1] = ms[2] = ms[3] = 0; launches = 0;
   }
 
-  void launch_map(const hlac_batch& b /* device pointers */) {
+  void launch_map(const hlac_batch& b /* device pointers */, const uint64_t* rec = nullptr /* packed records instead of b's arrays */) {
     if (b.n == 0) return;
     if (b.words_per_read == 0 || b.words_per_read > 16) throw Error(HLAC_ERR_ARG, "words_per_read must be 1..16");
     keys.reserve(reads_pushed + b.n, stream, true, reads_pushed);
@@ -611,6 +625,7 @@ struct hlac_count {
     a.primary_only = primary_only; a.n_cells = n_cells; a.cell_bits = cell_bits;
     a.keys = keys.p; a.cursor = counters.p; a.metrics = counters.p + 1;
     a.codes = want_codes ? codes.p : nullptr;
+    a.rec = rec;
     // launch shape: (bitmaps in shared memory?, reads per lane per warp tile R, threads per block). Defaults below;
     // HLAC_COUNT_SHAPE="smem,R,threads" overrides them for tuning runs.
     using Kern = void (*)(const CountMapArgs);
@@ -620,13 +635,14 @@ struct hlac_count {
       return (bm ? bitmap_smem_bytes : 0) + (threads / 32) * per_warp_words * 4;
     };
     if (cfg_wpr != b.words_per_read) {
-      struct Shape { bool bm; int r, threads; Kern k; int minb = 1; };
+      struct Shape { bool bm; int r, threads; Kern k; int minb = 1; Kern k_packed = nullptr; };
       static const Shape shapes[] = {
 #define HLAC_SHAPE(BM, RR, TT) {BM, RR, TT, k_count_map<BM, RR, TT>}
           // defaults first: measured best on B200 (profiles/r01_count_map_tuning.md) — the queue-staged kernel (R = 0) at
           // 1024 resident threads per SM, then the tile-staged shapes (occupancy beats tile size)
-          {true, 0, 1024, k_count_map_q<true, 1024, 1>}, {true, 0, 512, k_count_map_q<true, 512, 2>},
-          {false, 0, 256, k_count_map_q<false, 256, 4>}, {false, 0, 128, k_count_map_q<false, 128, 8>},
+#define HLAC_QSHAPE(BM, TT, MB) {BM, 0, TT, k_count_map_q<BM, TT, MB, false>, 1, k_count_map_q<BM, TT, MB, true>}
+          HLAC_QSHAPE(true, 1024, 1), HLAC_QSHAPE(true, 512, 2), HLAC_QSHAPE(false, 256, 4), HLAC_QSHAPE(false, 128, 8),
+#undef HLAC_QSHAPE
           HLAC_SHAPE(true, 2, 1024), HLAC_SHAPE(true, 1, 512), HLAC_SHAPE(true, 1, 256), HLAC_SHAPE(true, 4, 512), HLAC_SHAPE(true, 2, 512),
           HLAC_SHAPE(false, 2, 128), HLAC_SHAPE(false, 1, 128), HLAC_SHAPE(false, 2, 256), HLAC_SHAPE(false, 1, 256), HLAC_SHAPE(false, 4, 128),
           HLAC_SHAPE(true, 4, 256), HLAC_SHAPE(true, 8, 256), HLAC_SHAPE(false, 4, 256), HLAC_SHAPE(false, 8, 128),
@@ -645,13 +661,15 @@ struct hlac_count {
         pick = &sh; break;
       }
       if (!pick) throw Error(HLAC_ERR_LIMIT, "no launch shape of the count kernel fits (reads too long, or bad HLAC_COUNT_SHAPE)");
-      cfg_bm = pick->bm; cfg_r = pick->r; cfg_threads = pick->threads; cfg_kern = (void*)pick->k;
+      cfg_bm = pick->bm; cfg_r = pick->r; cfg_threads = pick->threads; cfg_kern = (void*)pick->k; cfg_kern_packed = (void*)pick->k_packed;
+      if (pick->k_packed) HLAC_CUDA(cudaFuncSetAttribute(pick->k_packed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(cfg_bm, cfg_r, cfg_threads)));
       HLAC_CUDA(cudaFuncSetAttribute(pick->k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(cfg_bm, cfg_r, cfg_threads)));
       HLAC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cfg_occ, pick->k, cfg_threads, smem_for(cfg_bm, cfg_r, cfg_threads)));
       if (cfg_occ < 1) throw Error(HLAC_ERR_LIMIT, "count map kernel does not fit on the device");
       cfg_wpr = b.words_per_read;
     }
-    Kern kern = (Kern)cfg_kern;
+    if (rec && !cfg_kern_packed) throw Error(HLAC_ERR_ARG, "packed records need the queue-staged count kernel (HLAC_COUNT_SHAPE selects a tile-staged shape)");
+    Kern kern = (Kern)(rec ? cfg_kern_packed : cfg_kern);
     const size_t smem = smem_for(cfg_bm, cfg_r, cfg_threads);
     const int MAP_R = cfg_r ? cfg_r : 2, MAP_THREADS = cfg_threads;
     if (cfg_r == 0 && b.n >= (1ull << 32)) throw Error(HLAC_ERR_LIMIT, "the queue-staged count kernel takes batches below 2^32 reads");
@@ -756,6 +774,58 @@ int hlac_count_push(hlac_count* s, const hlac_batch* b) try {
   d.seq = st.seq.p; d.len = st.len.p; d.cell = st.cell.p; d.umi = st.umi.p; d.flags = st.flags.p;
   s->launch_map(d);
   HLAC_CUDA(cudaEventRecord(st.consumed, s->stream));
+  return HLAC_OK;
+} catch (const Error& e) { set_last_error(e.what()); return e.code; } catch (const std::exception& e) { set_last_error(e.what()); return HLAC_ERR_STATE; }
+
+static void validate_packed(const hlac_count* s, const hlac_packed_batch* b) {
+  if (b->n && !b->rec) throw Error(HLAC_ERR_ARG, "null record array");
+  if (b->n && (b->words_per_read == 0 || b->words_per_read > 7)) throw Error(HLAC_ERR_ARG, "packed records hold reads of <= 224 bases (words_per_read 1..7; len is an 8-bit field)");
+  if (b->n >= (1ull << 32)) throw Error(HLAC_ERR_LIMIT, "batch too large");
+  if (s->n_cells >= HLAC_PACKED_NOT_A_CELL) throw Error(HLAC_ERR_LIMIT, "packed records carry 23-bit cell indices: n_cells must be below 8388607");
+}
+
+int hlac_count_push_packed_device(hlac_count* s, const hlac_packed_batch* b) try {
+  if (!s || !b) throw Error(HLAC_ERR_ARG, "null argument");
+  validate_packed(s, b);
+  DeviceGuard g(s->device);
+  hlac_batch d{}; d.n = b->n; d.words_per_read = b->words_per_read;
+  s->launch_map(d, b->rec);
+  return HLAC_OK;
+} catch (const Error& e) { set_last_error(e.what()); return e.code; } catch (const std::exception& e) { set_last_error(e.what()); return HLAC_ERR_STATE; }
+
+int hlac_count_push_packed(hlac_count* s, const hlac_packed_batch* b) try {
+  if (!s || !b) throw Error(HLAC_ERR_ARG, "null argument");
+  validate_packed(s, b);
+  if (b->n == 0) return HLAC_OK;
+  DeviceGuard g(s->device);
+  auto& st = s->stage[s->n_push++ & 1];
+  if (!s->copy_stream) HLAC_CUDA(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+  if (!st.copied) { HLAC_CUDA(cudaEventCreateWithFlags(&st.copied, cudaEventDisableTiming)); HLAC_CUDA(cudaEventCreateWithFlags(&st.consumed, cudaEventDisableTiming)); }
+  else HLAC_CUDA(cudaStreamWaitEvent(s->copy_stream, st.consumed, 0));   // the kernel that read this set two pushes ago
+  auto& e = s->begin(3, s->copy_stream);
+  st.rec.upload(b->rec, b->n * (b->words_per_read + 1), s->copy_stream);   // ONE copy per push
+  s->end(e, s->copy_stream);
+  HLAC_CUDA(cudaEventRecord(st.copied, s->copy_stream));
+  HLAC_CUDA(cudaStreamWaitEvent(s->stream, st.copied, 0));
+  hlac_batch d{}; d.n = b->n; d.words_per_read = b->words_per_read;
+  s->launch_map(d, st.rec.p);
+  HLAC_CUDA(cudaEventRecord(st.consumed, s->stream));
+  return HLAC_OK;
+} catch (const Error& e) { set_last_error(e.what()); return e.code; } catch (const std::exception& e) { set_last_error(e.what()); return HLAC_ERR_STATE; }
+
+int hlac_pack_records(const hlac_batch* b, uint64_t* rec) try {
+  if (!b || (b->n && (!rec || !b->seq || !b->len || !b->cell || !b->umi || !b->flags))) throw Error(HLAC_ERR_ARG, "null argument");
+  const uint32_t wpr = b->words_per_read;
+  if (b->n && (wpr == 0 || wpr > 7)) throw Error(HLAC_ERR_ARG, "packed records hold reads of <= 224 bases (words_per_read 1..7)");
+  for (uint64_t i = 0; i < b->n; i++) {
+    if (b->len[i] > 255) throw Error(HLAC_ERR_LIMIT, "read longer than 255 bases does not fit a packed record");
+    uint32_t cell = b->cell[i];
+    if (cell == HLAC_NOT_A_CELL) cell = HLAC_PACKED_NOT_A_CELL;
+    else if (cell >= HLAC_PACKED_NOT_A_CELL) throw Error(HLAC_ERR_LIMIT, "cell index does not fit the 23-bit field of a packed record");
+    uint64_t* r = rec + i * (wpr + 1);
+    for (uint32_t w = 0; w < wpr; w++) r[w] = b->seq[i * wpr + w];
+    r[wpr] = HLAC_PACKED_META(b->umi[i], b->flags[i] & HLAC_FLAG_PRIMARY, b->len[i], cell);
+  }
   return HLAC_OK;
 } catch (const Error& e) { set_last_error(e.what()); return e.code; } catch (const std::exception& e) { set_last_error(e.what()); return HLAC_ERR_STATE; }
 

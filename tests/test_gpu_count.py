@@ -216,3 +216,32 @@ def test_deep_umis(sb, orc, abc, cells):
     both = tuple(np.concatenate([x, x]) for x in batch)
     ref2 = orc.count_run(abc["oc"], abc["og"], *both)
     assert ent2 == ref2["entries"] and met2 == ref2["metrics"]
+
+
+def test_packed_records_equal_soa(sb, orc, abc, fixture_reads):
+    """hlac_count_push_packed (one 32-byte record per read, one H2D copy per push) must give exactly what the five-array
+    push gives: fixture reads with --primary-alignments semantics, synthetic reads in three pushes, host and device buffers."""
+    import torch
+    from tools import synth
+    bc = H.load_barcodes(os.path.join(H.FIX, "barcodes7.tsv"))
+    batch = H.make_batch(fixture_reads, bc, pack=sb.pack_reads)
+    cds, gen = synth.fixture_alleles()
+    r = synth.make_reads(60000, [s for _, s in cds], [s for _, s in gen], 300, 21)
+    for (b, ncell, primary_only) in ((batch, len(bc), True), (batch, len(bc), False),
+                                     ((r["seq"], r["len"], r["cell"], r["umi"], r["flags"]), 300, False)):
+        ref = orc.count_run(abc["oc"], abc["og"], *b, primary_only=primary_only, want_codes=True)
+        rec = sb.pack_records(*b)
+        for device in (False, True):
+            s = sb.CountSession(abc["gc"], abc["gg"], ncell, primary_only)
+            s.record_codes(True)
+            codes = []
+            for part in np.array_split(np.arange(len(rec)), 3):
+                chunk = rec[part[0]:part[-1] + 1]
+                s.push_packed(torch.from_numpy(chunk.view(np.int64)).cuda() if device else chunk)
+                codes.append(s.last_codes(len(chunk)))
+            ent, met = s.finish()
+            assert np.array_equal(np.concatenate(codes), ref["codes"]) and met == ref["metrics"] and ent == ref["entries"]
+    # 23-bit cell field: sessions with more columns must use the five-array push
+    big = sb.CountSession(abc["gc"], abc["gg"], (1 << 23))
+    with pytest.raises(sb.HlacError, match="23-bit"):
+        big.push_packed(rec[:10])

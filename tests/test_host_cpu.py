@@ -253,3 +253,25 @@ def test_idx_writer_reproduces_fixture(sb, tmp_path):
     assert back.info == other.info and back.tx_names == other.tx_names
     key = lambda n: (n[0], n[1], tuple(n[2]))
     assert sorted(map(key, back.nodes())) == sorted(map(key, other.nodes()))
+
+
+def test_pack_records_layout(sb):
+    """hlac_pack_records: sequence words, then umi << 32 | primary << 31 | len << 23 | cell (include/hlacount.h)."""
+    rng = np.random.default_rng(3)
+    n, wpr = 50, 3
+    seq = rng.integers(0, 1 << 63, size=(n, wpr), dtype=np.uint64)
+    lens = rng.integers(0, 97, size=n).astype(np.uint16)
+    cell = rng.integers(0, 5000, size=n).astype(np.uint32)
+    cell[::7] = sb.NOT_A_CELL
+    umi = rng.integers(0, 1 << 32, size=n, dtype=np.uint64).astype(np.uint32)
+    flags = rng.integers(0, 2, size=n).astype(np.uint8)
+    rec = sb.pack_records(seq, lens, cell, umi, flags)
+    assert rec.shape == (n, wpr + 1) and np.array_equal(rec[:, :wpr], seq)
+    c23 = np.where(cell == sb.NOT_A_CELL, sb.PACKED_NOT_A_CELL, cell).astype(np.uint64)
+    meta = (umi.astype(np.uint64) << np.uint64(32)) | (flags.astype(np.uint64) << np.uint64(31)) | (lens.astype(np.uint64) << np.uint64(23)) | c23
+    assert np.array_equal(rec[:, wpr], meta)
+    assert sb.pack_records(seq[:0], lens[:0], cell[:0], umi[:0], flags[:0]).shape[0] == 0
+    with pytest.raises(sb.HlacError):   # 8-bit length field
+        sb.pack_records(np.zeros((1, 7), np.uint64), np.array([256], np.uint16), cell[:1], umi[:1], flags[:1])
+    with pytest.raises(sb.HlacError):   # 23-bit cell field
+        sb.pack_records(seq[:1], lens[:1], np.array([1 << 23], np.uint32), umi[:1], flags[:1])
