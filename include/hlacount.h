@@ -173,6 +173,10 @@ int hlac_count_push_packed_device(hlac_count*, const hlac_packed_batch* device_b
 /* host helper: hlac_batch (host pointers, len <= 255, cell < HLAC_PACKED_NOT_A_CELL or HLAC_NOT_A_CELL) -> packed records;
  * rec must hold b->n * (b->words_per_read + 1) u64 */
 int hlac_pack_records(const hlac_batch* b, uint64_t* rec);
+/* reads the host driver dropped itself because their barcode is not in the whitelist (never scored, mapping.rs:760-763):
+ * they only count in the metrics - n_reads into num_reads, n_non_primary into num_non_primary (mapping.rs:752-757),
+ * n_not_cell into num_not_cell_bc (reads that reach mapping.rs:760: primary, or any when primary_only is off) */
+int hlac_count_add_filtered(hlac_count*, uint64_t n_reads, uint64_t n_non_primary, uint64_t n_not_cell);
 int hlac_count_sync(hlac_count*);                               /* host batch buffers reusable after this */
 /* debug/parity: record per-read results (off by default), then fetch those of the LAST pushed batch:
  * code = gene*3+slot or HLAC_CODE_NONE */

@@ -554,6 +554,7 @@ struct hlac_count {
   int primary_only = 0;
   DevBuf<uint32_t> nodes_cds, nodes_gen, gene_row0, dense;   // node tables with cinfo in place of the colour id
   DevBuf<uint64_t> keys, keys_sorted;
+  uint64_t host_reads = 0, host_non_primary = 0, host_not_cell = 0;   // reads the host driver filtered out itself (hlac_count_add_filtered)
   struct Stage {   // one staging set for host batches; two of them so the H2D of batch i+1 overlaps the kernel of batch i
     DevBuf<uint64_t> seq, rec; DevBuf<uint16_t> len; DevBuf<uint32_t> cell, umi; DevBuf<uint8_t> flags;
     cudaEvent_t copied = nullptr, consumed = nullptr;
@@ -608,7 +609,7 @@ struct hlac_count {
   }
   void reset() {
     HLAC_CUDA(cudaMemsetAsync(counters.p, 0, 11 * sizeof(unsigned long long), stream));
-    reads_pushed = 0; last_n = 0; reduced = false; n_keys = 0;
+    reads_pushed = 0; last_n = 0; reduced = false; n_keys = 0; host_reads = host_non_primary = host_not_cell = 0;
     drain_events(); ms[0] = ms[1] = ms[2] = ms[3] = 0; launches = 0;
   }
 
@@ -935,7 +936,7 @@ int hlac_count_entries(hlac_count* s, hlac_coo* out, hlac_metrics* metrics) try 
   HLAC_CUDA(cudaStreamSynchronize(s->stream));
   if (ctr[9]) throw Error(HLAC_ERR_ARG, std::to_string(ctr[9]) + " reads carried a cell index >= n_cells (the reference panics in TriMat::add_triplet, main.rs:279)");
   if (metrics) {
-    metrics->num_reads = ctr[1]; metrics->num_non_primary = ctr[2]; metrics->num_not_cell_bc = ctr[3];
+    metrics->num_reads = ctr[1] + s->host_reads; metrics->num_non_primary = ctr[2] + s->host_non_primary; metrics->num_not_cell_bc = ctr[3] + s->host_not_cell;
     metrics->num_cds_align = ctr[4]; metrics->num_gen_align = ctr[5]; metrics->num_not_aligned = ctr[6];
   }
   if (out) {
@@ -946,6 +947,14 @@ int hlac_count_entries(hlac_count* s, hlac_coo* out, hlac_metrics* metrics) try 
   }
   return HLAC_OK;
 } catch (const Error& e) { set_last_error(e.what()); return e.code; } catch (const std::exception& e) { set_last_error(e.what()); return HLAC_ERR_STATE; }
+
+// Reads whose barcode is not in the whitelist are never scored (mapping.rs:760-763): a host driver may drop them before the
+// device and report only how they count in the metrics.
+int hlac_count_add_filtered(hlac_count* s, uint64_t n_reads, uint64_t n_non_primary, uint64_t n_not_cell) {
+  if (!s) { set_last_error("null session"); return HLAC_ERR_ARG; }
+  s->host_reads += n_reads; s->host_non_primary += n_non_primary; s->host_not_cell += n_not_cell;
+  return HLAC_OK;
+}
 
 int hlac_count_finish(hlac_count* s, hlac_coo* out, hlac_metrics* metrics) {
   int rc = hlac_count_reduce(s, nullptr, nullptr);

@@ -153,8 +153,14 @@ WorkerPool& host_pool() {
 constexpr uint32_t CELL_UNKNOWN = 0xFFFFFFFEu;
 struct NoCellTry { uint32_t operator()(StrRef) const { return CELL_UNKNOWN; } };
 
+// Counting only: reads whose barcode is not in the whitelist are never scored (mapping.rs:760-763), so the driver keeps them
+// off the PCIe link and the GPU and only accounts for them (mapping.rs:752-763), see hlac_count_add_filtered.
+struct HostFilter { bool primary_only = false; uint64_t n_reads = 0, n_non_primary = 0, n_not_cell = 0; };
+
 template <typename CellFn, typename Flush, typename CellTry = NoCellTry>
-uint64_t stream_records(BamReader& bam, BatchBuilder& bb, CellFn cell_of, Flush flush, bool cell_of_is_pure, CellTry cell_try = CellTry()) {
+uint64_t stream_records(BamReader& bam, BatchBuilder& bb, CellFn cell_of, Flush flush, bool cell_of_is_pure, CellTry cell_try = CellTry(),
+                        HostFilter* filter = nullptr) {
+  if (filter && !cell_of_is_pure) throw Error(HLAC_ERR_STATE, "the host filter needs a pure barcode lookup");
   constexpr size_t CHUNK = 1 << 16, GRAIN = 1024;
   constexpr uint32_t UMI_INTERN = 0xFFFFFFFFu;
   WorkerPool& pool = host_pool();
@@ -203,12 +209,19 @@ uint64_t stream_records(BamReader& bam, BatchBuilder& bb, CellFn cell_of, Flush 
     for (size_t i = 0; i < n; i++) if (ok[i]) need = std::max<uint32_t>(need, (uint32_t)((views[i].l_seq + 31) / 32));
     words.resize(n * (size_t)need);
     pool.for_ranges(n, GRAIN, [&](size_t b, size_t e) {
-      for (size_t i = b; i < e; i++) if (ok[i]) BamReader::pack_2bit(views[i].seq4, views[i].l_seq, words.data() + i * need, need);
+      for (size_t i = b; i < e; i++)
+        if (ok[i] && !(filter && cells[i] == HLAC_NOT_A_CELL)) BamReader::pack_2bit(views[i].seq4, views[i].l_seq, words.data() + i * need, need);
     });
     t_pack += now() - t0; t0 = now();
     for (size_t i = 0; i < n; i++) {
       if (!ok[i]) continue;
       const BamReader::RecView& v = views[i];
+      if (filter && cells[i] == HLAC_NOT_A_CELL) {
+        filter->n_reads++; total++;
+        if (!v.primary) filter->n_non_primary++;
+        if (v.primary || !filter->primary_only) filter->n_not_cell++;
+        continue;
+      }
       if (!bb.fits((size_t)v.l_seq)) {
         if (bb.n) { flush(); bb.n = 0; }
         const uint32_t want = std::max<uint32_t>(3, (uint32_t)((v.l_seq + 31) / 32));
@@ -454,7 +467,9 @@ int hlac_map_and_count_pseudo(const char* bam, const char* out_dir, const char* 
   BatchBuilder bb(BATCH_READS);
   // the whitelist is read-only here: the lookup is a pure function and runs on the parser threads
   auto cell_of = [&](StrRef cb, StrRef) { auto it = barcodes.find(cb.str()); return it == barcodes.end() ? HLAC_NOT_A_CELL : it->second; };
-  stream_records(reader, bb, cell_of, [&] { hlac_batch b = bb.batch(); check(hlac_count_push(s.p, &b)); check(hlac_count_sync(s.p)); }, true);
+  HostFilter filt; filt.primary_only = primary_only != 0;
+  stream_records(reader, bb, cell_of, [&] { hlac_batch b = bb.batch(); check(hlac_count_push(s.p, &b)); check(hlac_count_sync(s.p)); }, true, NoCellTry(), &filt);
+  check(hlac_count_add_filtered(s.p, filt.n_reads, filt.n_non_primary, filt.n_not_cell));
   hlac_metrics m{}; hlac_coo tmp{}; check(hlac_count_finish(s.p, &tmp, &m));
   if (entries) {   // the session (and its pinned result buffer) ends with this call: hand out owned copies
     *entries = tmp; entries->borrowed = 0;

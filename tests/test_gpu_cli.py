@@ -27,6 +27,30 @@ def test_allele_fasta_cli(tmp_path):
                                                                   "B*51:01:01:01", "B", "C*02:02:02:01", "C*14:02:01:01", "C"]
     summ = [l.split("\t") for l in open(tmp_path / "r" / "summary.tsv").read().splitlines()]
     assert [int(x[1]) for x in summ] == [9, 10, 1, 16, 23, 3, 12, 8, 3]
+    # the Metrics block (main.rs:253-276); reads outside the whitelist are filtered and accounted for on the host
+    log = r.stdout + r.stderr
+    for text, want in (("evaluated (with 'CB' and 'UB' tags): ", 2864), ("that were not primary: ", 203),
+                       ("not being associated with a cell barcode in the list provided: ", 2184),
+                       ("no alignment score above threshold: ", 1), ("alignments to CDS sequence: ", 643),
+                       ("alignments to genomic sequence: ", 23)):
+        assert text + str(want) in log, (text, log)
+    rp = _run(["-b", os.path.join(H.FIX, "test.bam"), "-g", os.path.join(H.FIX, "genomic_ABC.fa"), "-f",
+               os.path.join(H.FIX, "cds_ABC.fa"), "-c", os.path.join(H.FIX, "barcodes7.tsv"), "-o", str(tmp_path / "rp"),
+               "--primary-alignments"], tmp_path)
+    assert rp.returncode == 0, rp.stdout + rp.stderr
+    from oracle import oracle as orc
+    import schlacount_b200 as sb
+    import bamlite
+    orc.build()
+    reads = list(bamlite.fetch(os.path.join(H.FIX, "test.bam"), *H.DEFAULT_REGION))
+    bc = H.load_barcodes(os.path.join(H.FIX, "barcodes7.tsv"))
+    ref = orc.count_run(orc.Index.from_fasta(os.path.join(H.FIX, "cds_ABC.fa")), orc.Index.from_fasta(os.path.join(H.FIX, "genomic_ABC.fa")),
+                        *H.make_batch(reads, bc, pack=sb.pack_reads), primary_only=True)
+    m = ref["metrics"]
+    logp = rp.stdout + rp.stderr
+    assert "evaluated (with 'CB' and 'UB' tags): %d" % m[0] in logp and "skipped due to not being primary: %d" % m[1] in logp
+    assert "in the list provided: %d" % m[2] in logp and "score above threshold: %d" % m[5] in logp
+    assert sorted(H.read_mtx(tmp_path / "rp" / "count_matrix.mtx")[2]) == sorted(ref["entries"])
     # out-dir must not pre-exist (main.rs:341-346)
     r2 = _run(["-b", os.path.join(H.FIX, "test.bam"), "-g", os.path.join(H.FIX, "genomic_ABC.fa"), "-f",
                os.path.join(H.FIX, "cds_ABC.fa"), "-c", os.path.join(H.FIX, "barcodes1.tsv"), "-o", str(tmp_path / "r")], tmp_path)
