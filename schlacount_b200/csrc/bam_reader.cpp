@@ -239,11 +239,13 @@ size_t BamReader::frame(Chunk& chunk, size_t max_records) {
     const uint8_t* r = buf.data() + at + 4;
     const int32_t tid = rd<int32_t>(r), pos = rd<int32_t>(r + 4);
     at += 4 + (size_t)bs;
+    bool keep = true;
     if (sel_tid_ >= 0) {
       if (tid > sel_tid_ || tid < 0 || (tid == sel_tid_ && pos >= sel_end_)) { done_ = true; break; }   // coordinate sorted
-      if (tid < sel_tid_) continue;
-    } else if (tid != -1) continue;
-    found.emplace_back(at - (size_t)bs, (size_t)bs);
+      if (tid < sel_tid_) keep = false;
+    } else if (tid != -1) keep = false;
+    if (keep) found.emplace_back(at - (size_t)bs, (size_t)bs);
+    else if (found.empty() && at >= (1u << 20)) { buf.erase(buf.begin(), buf.begin() + (ptrdiff_t)at); at = 0; }   // a long run of records before the selection: do not hoard it
   }
   if (!done_ && at < buf.size()) carry_.assign(buf.begin() + (ptrdiff_t)at, buf.end());
   chunk.recs.reserve(found.size());

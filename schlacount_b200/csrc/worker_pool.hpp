@@ -1,6 +1,7 @@
 // Fixed pool of host threads with one operation: run fn(i) for i in [0, n) and wait. Used by the host driver to parse
 // BAM records in parallel (BAM ingest off the critical path). Product code.
 #pragma once
+#include <algorithm>
 #include <atomic>
 #include <condition_variable>
 #include <exception>

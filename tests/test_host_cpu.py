@@ -136,7 +136,7 @@ def test_bam_batch_path_matches_independent_decoder(sb, fixture_reads, tmp_path)
     import subprocess
     import sys
     syn = str(tmp_path / "syn.bam")
-    subprocess.check_call([sys.executable, os.path.join(H.ROOT, "tools", "make_bam.py"), syn, "6000", "700"], stdout=subprocess.DEVNULL)
+    subprocess.check_call([sys.executable, os.path.join(H.ROOT, "tools", "make_bam.py"), syn, "6000", "700", "9000"], stdout=subprocess.DEVNULL)   # 9000 records (2.7 MB) on contig "1" come first and must be skipped
     mapped = list(bamlite.fetch(syn, "6", 28510120, 33480577))
     assert 5000 < len(mapped) < 6000                      # every 97th record has no UB and is dropped
     assert L.hlac_bam_batch_checksum(syn.encode(), b"6:28510120-33480577", C.byref(n), C.byref(h)) == 0, L.hlac_last_error()

@@ -3,7 +3,9 @@ CLI end to end at sizes the fixture does not reach. Records look like 10x 5' GEX
 the tag set Cell Ranger writes (CB, UB plus the ones the reader has to skip), a few records without CB/UB and an
 unmapped tail. The index puts every chunk in bin 0 (always selected by reg2bin) and points every linear-index window at the first record,
 which is all fetch() needs (a valid, if unselective, index).
-   python tools/make_bam.py out.bam [n_records=1000000] [n_unmapped=0]"""
+   python tools/make_bam.py out.bam [n_records=1000000] [n_unmapped=0] [n_on_contig_1=0]
+The optional records on contig "1" precede the selection and have to be skipped by a fetch on "6" (the linear index
+points at the start of the file)."""
 import os
 import struct
 import sys
@@ -74,6 +76,7 @@ def main():
     out = sys.argv[1]
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 1_000_000
     n_un = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+    n_before = int(sys.argv[4]) if len(sys.argv) > 4 else 0
     rng = np.random.default_rng(20191101)
     cds, gen = synth.fixture_alleles()
     r = synth.make_reads(n + n_un, [s for _, s in cds], [s for _, s in gen], 5000, 20191101, frac_not_cell=0.0)
@@ -85,6 +88,8 @@ def main():
     for nm, ln in refs:
         w.write(struct.pack("<i", len(nm) + 1) + nm.encode() + b"\0" + struct.pack("<i", ln))
     first = w.tell()
+    for i in range(n_before):
+        w.write(record(0, 1000 + 50 * i, 0, "ACGT" * 22 + "ACG", b"b%d" % i, b"AAACCCGGGTTTACGT-1", b"ACGTACGTAC"))
     pos = np.sort(rng.integers(29_900_000, 31_400_000, size=n))
     for i in range(n + n_un):
         codes = [(int(r["seq"][i][k >> 5]) >> (62 - 2 * (k & 31))) & 3 for k in range(91)]
@@ -108,7 +113,10 @@ def main():
     # .bai: per reference n_bin, bins (bin id, n_chunk, chunks), n_intv, ioffsets; everything in bin 0 of reference 1 ("6")
     with open(out + ".bai", "wb") as f:
         f.write(b"BAI\x01" + struct.pack("<i", len(refs)))
-        f.write(struct.pack("<ii", 0, 0))                                   # reference "1": nothing
+        if n_before:                                                        # reference "1": its records, bin 0 + linear index
+            f.write(struct.pack("<i", 1) + struct.pack("<Ii", 0, 1) + struct.pack("<QQ", first, first) + struct.pack("<i", 1) + struct.pack("<Q", first))
+        else:
+            f.write(struct.pack("<ii", 0, 0))                               # reference "1": nothing
         n_intv = (int(pos[-1]) >> 14) + 1   # linear index: every 16 kb window starts at the first record (a valid lower bound)
         f.write(struct.pack("<i", 1) + struct.pack("<Ii", 0, 1) + struct.pack("<QQ", first, mapped_end) + struct.pack("<i", n_intv))
         f.write(struct.pack("<%dQ" % n_intv, *([first] * n_intv)))
