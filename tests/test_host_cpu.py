@@ -275,3 +275,29 @@ def test_pack_records_layout(sb):
         sb.pack_records(np.zeros((1, 7), np.uint64), np.array([256], np.uint16), cell[:1], umi[:1], flags[:1])
     with pytest.raises(sb.HlacError):   # 23-bit cell field
         sb.pack_records(seq[:1], lens[:1], np.array([1 << 23], np.uint32), umi[:1], flags[:1])
+
+
+def test_bam_reader_rejects_damaged_files(sb, tmp_path):
+    """Truncated or corrupted BAM / BAI input must surface as an error status from the ABI (serial and batch paths),
+    never as a crash or a silently shorter result."""
+    L = sb.lib()
+    n, h = C.c_uint64(), C.c_uint64()
+    src = os.path.join(H.FIX, "test.bam")
+    raw, bai = open(src, "rb").read(), open(src + ".bai", "rb").read()
+    region = b"6:28510120-33480577"
+
+    def write(name, bam_bytes, bai_bytes=bai):
+        p = str(tmp_path / name)
+        open(p, "wb").write(bam_bytes)
+        if bai_bytes is not None:
+            open(p + ".bai", "wb").write(bai_bytes)
+        return p.encode()
+    for fn in (L.hlac_bam_scan, L.hlac_bam_batch_checksum):
+        assert fn(write("ok.bam", raw), region, C.byref(n), C.byref(h)) == 0 and n.value == 2864
+        assert fn(write("cut.bam", raw[:len(raw) // 2 + 7]), region, C.byref(n), C.byref(h)) != 0       # cut inside a BGZF block
+        flipped = bytearray(raw); flipped[len(raw) // 3] ^= 0x5A                                         # damaged deflate stream / CRC-less payload
+        fn(write("flip.bam", bytes(flipped)), region, C.byref(n), C.byref(h))   # may or may not still inflate (no CRC check); must not crash
+        assert fn(write("noidx.bam", raw, None), region, C.byref(n), C.byref(h)) != 0 and b".bai" in L.hlac_last_error()
+        assert fn(write("badidx.bam", raw, bai[:40]), region, C.byref(n), C.byref(h)) != 0
+        assert fn(write("notbam.bam", b"\x1f\x8b" + b"\0" * 100), region, C.byref(n), C.byref(h)) != 0
+        assert fn(write("ok.bam", raw), b"6:notanumber", C.byref(n), C.byref(h)) != 0                    # locus parse error (locus.rs)
