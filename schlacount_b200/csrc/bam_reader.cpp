@@ -17,7 +17,7 @@ namespace {
 template <typename T>
 T rd(const uint8_t* p) { T v; memcpy(&v, p, sizeof(T)); return v; }
 
-std::vector<uint8_t> inflate_block(const std::vector<uint8_t>& cdata, uint32_t isize) {
+std::vector<uint8_t> inflate_block(const std::vector<uint8_t>& cdata, uint32_t isize, uint32_t crc) {
   std::vector<uint8_t> out(isize);
   if (isize) {
     z_stream zs{};
@@ -27,6 +27,7 @@ std::vector<uint8_t> inflate_block(const std::vector<uint8_t>& cdata, uint32_t i
     inflateEnd(&zs);
     if (rc != Z_STREAM_END) throw Error(HLAC_ERR_FORMAT, "BGZF inflate failed");
   }
+  if ((uint32_t)crc32(crc32(0L, Z_NULL, 0), out.data(), (uInt)out.size()) != crc) throw Error(HLAC_ERR_FORMAT, "BGZF block fails its CRC32");
   return out;
 }
 }  // namespace
@@ -48,8 +49,8 @@ class InflatePool {
   // blocks inflated ahead of the consumer: enough (32 MB inflated) to keep the workers busy while the host driver parses
   // and appends the previous chunk of records
   size_t depth() const { return workers_.empty() ? 1 : std::max<size_t>(workers_.size() * 4, 512); }
-  std::future<std::vector<uint8_t>> submit(std::vector<uint8_t> cdata, uint32_t isize) {
-    auto task = std::make_shared<std::packaged_task<std::vector<uint8_t>()>>([c = std::move(cdata), isize] { return inflate_block(c, isize); });
+  std::future<std::vector<uint8_t>> submit(std::vector<uint8_t> cdata, uint32_t isize, uint32_t crc) {
+    auto task = std::make_shared<std::packaged_task<std::vector<uint8_t>()>>([c = std::move(cdata), isize, crc] { return inflate_block(c, isize, crc); });
     auto fut = task->get_future();
     if (workers_.empty()) (*task)();
     else { { std::lock_guard<std::mutex> l(m_); q_.push([task] { (*task)(); }); } cv_.notify_one(); }
@@ -150,10 +151,10 @@ bool BamReader::enqueue_block() {
   const size_t clen = bsize - 12 - xlen - 8;
   std::vector<uint8_t> cdata(clen + 8);
   if (fread(cdata.data(), 1, clen + 8, f_) != clen + 8) throw Error(HLAC_ERR_FORMAT, "BGZF truncated");
-  const uint32_t isize = rd<uint32_t>(&cdata[clen + 4]);
+  const uint32_t crc = rd<uint32_t>(&cdata[clen]), isize = rd<uint32_t>(&cdata[clen + 4]);
   cdata.resize(clen);
   Pending pd; pd.coff = read_coff_; pd.bsize = (uint64_t)bsize;
-  pd.data = pool_->submit(std::move(cdata), isize);
+  pd.data = pool_->submit(std::move(cdata), isize, crc);
   pending_.push_back(std::move(pd));
   read_coff_ += bsize;
   file_pos_ = read_coff_;
