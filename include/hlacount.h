@@ -120,7 +120,7 @@ typedef struct {
 const char* hlac_last_error(void);
 int hlac_device_count(int* n);
 /* sizeof of hlac_batch, hlac_metrics, hlac_coo, hlac_index_info, hlac_class_tables, hlac_paths, hlac_calls (cap >= 7)
- * and hlac_eqclassdb (written if cap >= 8), so that a
+ * and hlac_eqclassdb, hlac_packed_batch (written if cap >= 8 / 9), so that a
  * binding (Rust repr(C), ctypes) can assert its own layouts against the library it loaded */
 int hlac_abi_sizes(uint32_t* out, uint32_t cap);
 

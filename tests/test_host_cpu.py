@@ -181,10 +181,10 @@ def test_locus_parsing_follows_the_reference_regex(sb):
 def test_ctypes_layouts_match_the_library(sb):
     """The ctypes mirrors of the ABI structs must have the sizes the compiled header has (guards against drift)."""
     from schlacount_b200 import _lib
-    out = (C.c_uint32 * 8)()
-    assert sb.lib().hlac_abi_sizes(out, C.c_uint32(8)) == 0
+    out = (C.c_uint32 * 9)()
+    assert sb.lib().hlac_abi_sizes(out, C.c_uint32(9)) == 0
     mine = [C.sizeof(x) for x in (_lib.Batch, _lib.Metrics, _lib.Coo, _lib.IndexInfo, _lib.ClassTables, _lib.Paths, _lib.Calls,
-                                  _lib.EqClassDbC)]
+                                  _lib.EqClassDbC, _lib.PackedBatch)]
     assert list(out) == mine
     old = (C.c_uint32 * 7)()   # a binding built against the 7-value form still works
     assert sb.lib().hlac_abi_sizes(old, C.c_uint32(7)) == 0 and list(old) == mine[:7]
