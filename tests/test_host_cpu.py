@@ -301,3 +301,23 @@ def test_bam_reader_rejects_damaged_files(sb, tmp_path):
         assert fn(write("badidx.bam", raw, bai[:40]), region, C.byref(n), C.byref(h)) != 0
         assert fn(write("notbam.bam", b"\x1f\x8b" + b"\0" * 100), region, C.byref(n), C.byref(h)) != 0
         assert fn(write("ok.bam", raw), b"6:notanumber", C.byref(n), C.byref(h)) != 0                    # locus parse error (locus.rs)
+
+
+def test_index_build_equals_oracle_on_synthetic_db(sb, orc, tmp_path):
+    """build_index on a 600-allele synthetic IMGT-like database: the product's sort-based host builder and
+    the oracle's restatement must produce the same graph (node sequences, extension masks, colour lists) and tx order, and
+    the written .idx must load back to it."""
+    from tools import synth
+    db = str(tmp_path / "db")
+    os.makedirs(db)
+    synth.make_db(db, 200, 31337)
+    fa, st = os.path.join(db, "hla_nuc.fasta"), os.path.join(db, "Allele_status.txt")
+    mine, ref = sb.Index.from_fasta(fa, st, device=-1), orc.Index.from_fasta(fa, st)
+    assert mine.tx_names == ref.tx_names and mine.info["n_tx"] == 600
+    key = lambda n: (n[0], n[1], tuple(n[2]))
+    want = sorted(map(key, ref.nodes()))
+    assert sorted(map(key, mine.nodes())) == want and len(want) == mine.info["n_nodes"] > 1000
+    p = str(tmp_path / "x.idx")
+    mine.write_idx(p)
+    assert sorted(map(key, sb.Index.from_idx(p, device=-1).nodes())) == want
+    assert sorted(map(key, orc.Index.from_idx(p).nodes())) == want      # the oracle's own bincode reader accepts the file
