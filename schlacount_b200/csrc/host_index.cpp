@@ -1,9 +1,13 @@
 // HostIndex: .idx loader (bincode layout), sort-based build_index, derived GPU structures.
 #include "host_index.hpp"
+#include "worker_pool.hpp"
 
 #include <algorithm>
+#include <atomic>
 #include <cstring>
 #include <fstream>
+#include <memory>
+#include <thread>
 #include <unordered_map>
 #include <chrono>
 #include <cstdio>
@@ -234,27 +238,44 @@ void HostIndex::build(const std::vector<Bases>& seqs, const std::vector<std::str
   ix = HostIndex();
   ix.tx_names = names;
   // one (k-mer, payload) pair per occurrence; payload = tx << 16 | left-ext mask << 8 | right-ext mask
-  std::vector<uint64_t> okey, oval;
-  size_t total = 0;
-  for (auto& s : seqs) if (s.size() >= (size_t)K) total += s.size() - K + 1;
-  okey.reserve(total); oval.reserve(total);
-  for (uint32_t t = 0; t < seqs.size(); t++) {
-    const Bases& s = seqs[t];
-    if (s.size() < (size_t)K) continue;
-    uint64_t v = 0;
-    for (int i = 0; i < K - 1; i++) v = (v << 2) | s[i];
-    for (size_t i = 0; i + K <= s.size(); i++) {
-      v = ((v << 2) | s[i + K - 1]) & KMER_MASK;
-      okey.push_back(v);
-      oval.push_back(((uint64_t)t << 16) | (uint64_t)(i > 0 ? 1u << s[i - 1] : 0) << 8 | (uint64_t)(i + K < s.size() ? 1u << s[i + K] : 0));
+  // host threads for the embarrassingly parallel passes (enumeration, per-k-mer grouping); HLAC_HOST_THREADS overrides
+  unsigned n_threads = std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+  if (const char* e = getenv("HLAC_HOST_THREADS")) n_threads = (unsigned)std::max(1, atoi(e));
+  WorkerPool pool(n_threads);
+  // occurrence arrays: plain uninitialised storage, so that the first touch (page faults) happens on the worker threads
+  struct Raw {
+    std::unique_ptr<uint64_t[]> p; size_t n = 0;
+    void alloc(size_t k) { p.reset(new uint64_t[k ? k : 1]); n = k; }
+    uint64_t* data() { return p.get(); }
+    uint64_t& operator[](size_t i) { return p[i]; }
+    const uint64_t& operator[](size_t i) const { return p[i]; }
+    void swap(Raw& o) { p.swap(o.p); std::swap(n, o.n); }
+    void release() { p.reset(); n = 0; }
+  } okey, oval;
+  std::vector<size_t> first(seqs.size() + 1, 0);   // occurrences are laid out in ascending tx order (the stable sort relies on it)
+  for (size_t t = 0; t < seqs.size(); t++) first[t + 1] = first[t] + (seqs[t].size() >= (size_t)K ? seqs[t].size() - K + 1 : 0);
+  const size_t total = first[seqs.size()];
+  okey.alloc(total); oval.alloc(total);
+  pool.for_ranges(seqs.size(), 32, [&](size_t tb, size_t te) {
+    for (size_t t = tb; t < te; t++) {
+      const Bases& s = seqs[t];
+      if (s.size() < (size_t)K) continue;
+      uint64_t v = 0;
+      for (int i = 0; i < K - 1; i++) v = (v << 2) | s[i];
+      size_t at = first[t];
+      for (size_t i = 0; i + K <= s.size(); i++, at++) {
+        v = ((v << 2) | s[i + K - 1]) & KMER_MASK;
+        okey[at] = v;
+        oval[at] = ((uint64_t)t << 16) | (uint64_t)(i > 0 ? 1u << s[i - 1] : 0) << 8 | (uint64_t)(i + K < s.size() ? 1u << s[i + K] : 0);
+      }
     }
-  }
+  });
   tick("enumerate k-mers");
   // stable sort by k-mer: occurrences were generated in ascending tx order, so stability leaves every k-mer's tx list
   // sorted. On a device-resident build the caller supplies a GPU radix sort; otherwise an LSD radix sort on the host.
   if (sorter && total >= (1u << 16)) sorter(okey.data(), oval.data(), total);
   else {
-    std::vector<uint64_t> tk(total), tv(total);
+    Raw tk, tv; tk.alloc(total); tv.alloc(total);
     std::vector<size_t> cnt(1 << 16);
     for (int pass = 0; pass < 3; pass++) {
       const int sh = 16 * pass;
@@ -268,36 +289,79 @@ void HostIndex::build(const std::vector<Bases>& seqs, const std::vector<std::str
   }
   tick("sort occurrences");
 
-  // unique k-mers with ext masks and interned colour
+  // unique k-mers with ext masks and interned colour. Parallel part: the sorted occurrences are cut into chunks at k-mer
+  // boundaries and every chunk summarises its k-mers (ext masks, occurrence range, length and hash of the de-duplicated tx
+  // list). Sequential part: colour ids in first-appearance order over the sorted k-mers, comparing tx lists only on a hash hit.
+  struct Uniq { uint64_t kmer, hash; size_t b, e; uint32_t ntx; uint8_t l, r; };
+  const size_t n_chunks = std::max<size_t>(1, std::min<size_t>(pool.size() * 8, total / 4096 + 1));
+  std::vector<size_t> cut(n_chunks + 1, total);
+  cut[0] = 0;
+  for (size_t c = 1; c < n_chunks; c++) { size_t b = c * (total / n_chunks); while (b < total && b > 0 && okey[b] == okey[b - 1]) b++; cut[c] = std::max(b, cut[c - 1]); }
+  std::vector<std::vector<Uniq>> parts(n_chunks);
+  pool.for_ranges(n_chunks, 1, [&](size_t cb, size_t ce) {
+    for (size_t c = cb; c < ce; c++) {
+      std::vector<Uniq>& out = parts[c];
+      for (size_t i = cut[c]; i < cut[c + 1];) {
+        Uniq u{okey[i], 0xcbf29ce484222325ULL, i, i, 0, 0, 0};
+        uint32_t prev = NONE32;
+        size_t j = i;
+        while (j < total && okey[j] == u.kmer) {
+          const uint32_t tx = (uint32_t)(oval[j] >> 16);
+          u.l |= (uint8_t)(oval[j] >> 8); u.r |= (uint8_t)oval[j];
+          if (tx != prev) { prev = tx; u.ntx++; u.hash = (u.hash ^ tx) * 0x100000001b3ULL; u.hash ^= u.hash >> 29; }
+          j++;
+        }
+        u.e = j;
+        out.push_back(u);
+        i = j;
+      }
+    }
+  });
   std::vector<uint64_t> uk; std::vector<uint8_t> ul, ur; std::vector<uint32_t> ucol;
+  size_t nu = 0;
+  for (auto& pt : parts) nu += pt.size();
+  uk.reserve(nu); ul.reserve(nu); ur.reserve(nu); ucol.reserve(nu);
+  std::vector<const Uniq*> all; all.reserve(nu);
+  for (auto& pt : parts) for (const Uniq& u : pt) all.push_back(&u);
+  // sequential: colour id = first appearance of (hash, list length) over the sorted k-mers; rep[c] = the k-mer that defined colour c
   std::unordered_map<uint64_t, std::vector<uint32_t>> by_hash;   // hash(tx list) -> candidate colour ids
+  std::vector<uint32_t> rep;
   ix.col_off.assign(1, 0);
-  std::vector<uint32_t> txl;
-  for (size_t i = 0; i < total;) {
-    size_t j = i; uint8_t l = 0, r = 0; txl.clear();
-    uint64_t h = 0xcbf29ce484222325ULL;
-    while (j < total && okey[j] == okey[i]) {
-      const uint32_t tx = (uint32_t)(oval[j] >> 16);
-      l |= (uint8_t)(oval[j] >> 8); r |= (uint8_t)oval[j];
-      if (txl.empty() || txl.back() != tx) { txl.push_back(tx); h = (h ^ tx) * 0x100000001b3ULL; h ^= h >> 29; }
-      j++;
-    }
+  for (size_t q = 0; q < nu; q++) {
+    const Uniq& u = *all[q];
     uint32_t cid = NONE32;
-    auto& cand = by_hash[h];
-    for (uint32_t c : cand) {
-      size_t n = ix.col_off[c + 1] - ix.col_off[c];
-      if (n == txl.size() && std::equal(txl.begin(), txl.end(), ix.col_tx.begin() + ix.col_off[c])) { cid = c; break; }
-    }
-    if (cid == NONE32) {
-      cid = (uint32_t)ix.col_off.size() - 1;
-      ix.col_tx.insert(ix.col_tx.end(), txl.begin(), txl.end());
-      ix.col_off.push_back(ix.col_tx.size());
-      cand.push_back(cid);
-    }
-    uk.push_back(okey[i]); ul.push_back(l); ur.push_back(r); ucol.push_back(cid);
-    i = j;
+    auto& cand = by_hash[u.hash];
+    for (uint32_t c : cand) if (all[rep[c]]->ntx == u.ntx) { cid = c; break; }
+    if (cid == NONE32) { cid = (uint32_t)rep.size(); rep.push_back((uint32_t)q); cand.push_back(cid); ix.col_off.push_back(ix.col_off.back() + u.ntx); }
+    uk.push_back(u.kmer); ul.push_back(u.l); ur.push_back(u.r); ucol.push_back(cid);
   }
-  std::vector<uint64_t>().swap(okey); std::vector<uint64_t>().swap(oval);
+  // parallel: materialise every colour from its defining k-mer, then verify every k-mer's tx list against its colour (a
+  // 64-bit hash + length collision between different lists would otherwise merge two colours silently)
+  ix.col_tx.resize(ix.col_off.back());
+  pool.for_ranges(rep.size(), 64, [&](size_t cb, size_t ce) {
+    for (size_t c = cb; c < ce; c++) {
+      const Uniq& u = *all[rep[c]];
+      uint32_t* dst = ix.col_tx.data() + ix.col_off[c]; uint32_t prev = NONE32;
+      for (size_t j = u.b; j < u.e; j++) { const uint32_t tx = (uint32_t)(oval[j] >> 16); if (tx != prev) { prev = tx; *dst++ = tx; } }
+    }
+  });
+  std::atomic<bool> collision{false};
+  pool.for_ranges(nu, 2048, [&](size_t qb, size_t qe) {
+    for (size_t q = qb; q < qe; q++) {
+      const Uniq& u = *all[q];
+      if (rep[ucol[q]] == q) continue;
+      const uint32_t* have = ix.col_tx.data() + ix.col_off[ucol[q]];
+      size_t k = 0; uint32_t prev = NONE32;
+      for (size_t j = u.b; j < u.e; j++) {
+        const uint32_t tx = (uint32_t)(oval[j] >> 16);
+        if (tx == prev) continue;
+        prev = tx;
+        if (have[k++] != tx) { collision = true; return; }
+      }
+    }
+  });
+  if (collision) throw Error(HLAC_ERR_STATE, "tx-list hash collision while interning colours");
+  okey.release(); oval.release();
   tick("group + intern colours");
 
   const size_t n = uk.size();
