@@ -110,9 +110,13 @@ int hlac_eqclassdb_read(const char* path, hlac_eqclassdb* out) {
   HLAC_API_TRY
   if (!path || !out) throw Error(HLAC_ERR_ARG, "null argument");
   memset(out, 0, sizeof *out);
-  std::ifstream f(path, std::ios::binary);
+  std::ifstream f(path, std::ios::binary | std::ios::ate);
   if (!f) throw Error(HLAC_ERR_IO, std::string("cannot open ") + path);
-  std::string data((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+  const std::streamoff fsize = f.tellg();
+  if (fsize < 0) throw Error(HLAC_ERR_IO, std::string("cannot size ") + path);
+  std::string data((size_t)fsize, '\0');
+  f.seekg(0);
+  if (fsize && !f.read(&data[0], fsize)) throw Error(HLAC_ERR_IO, std::string("cannot read ") + path);
   const std::string spath(path);
   Cursor c{(const uint8_t*)data.data(), (const uint8_t*)data.data() + data.size(), spath};
   struct Guard { hlac_eqclassdb* d; bool ok = false; ~Guard() { if (!ok) hlac_eqclassdb_free(d); } } guard{out};

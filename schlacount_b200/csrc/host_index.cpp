@@ -47,9 +47,13 @@ void skip_mphf(Reader& r) {
 }  // namespace
 
 void HostIndex::load_idx(const std::string& path, HostIndex& ix) {
-  std::ifstream f(path, std::ios::binary);
+  std::ifstream f(path, std::ios::binary | std::ios::ate);
   if (!f) throw Error(HLAC_ERR_IO, "cannot open index file " + path);
-  std::vector<uint8_t> buf((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+  const std::streamoff fsize = f.tellg();
+  if (fsize < 0) throw Error(HLAC_ERR_IO, "cannot size index file " + path);
+  std::vector<uint8_t> buf((size_t)fsize);
+  f.seekg(0);
+  if (fsize && !f.read((char*)buf.data(), fsize)) throw Error(HLAC_ERR_IO, "cannot read index file " + path);
   Reader r{buf.data(), buf.size()};
   ix = HostIndex();
   uint64_t nw = r.count(8);
@@ -71,9 +75,13 @@ void HostIndex::load_idx(const std::string& path, HostIndex& ix) {
   }
   uint64_t nc = r.count(8);
   ix.col_off.assign(1, 0);
-  for (uint64_t c = 0; c < nc; c++) {
-    uint64_t m = r.count(4);
-    for (uint64_t i = 0; i < m; i++) ix.col_tx.push_back(r.u32());
+  for (uint64_t c = 0; c < nc; c++) {   // each list is contiguous little-endian u32: one bulk copy
+    const uint64_t m = r.count(4);
+    r.need(m * 4);
+    const size_t at = ix.col_tx.size();
+    ix.col_tx.resize(at + m);
+    if (m) memcpy(ix.col_tx.data() + at, r.p + r.o, m * 4);
+    r.o += m * 4;
     ix.col_off.push_back(ix.col_tx.size());
   }
   skip_mphf(r);                            // dbg_index : NoKeyBoomHashMap<Kmer24,(u32,u32)>
