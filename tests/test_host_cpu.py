@@ -321,3 +321,14 @@ def test_index_build_equals_oracle_on_synthetic_db(sb, orc, tmp_path):
     mine.write_idx(p)
     assert sorted(map(key, sb.Index.from_idx(p, device=-1).nodes())) == want
     assert sorted(map(key, orc.Index.from_idx(p).nodes())) == want      # the oracle's own bincode reader accepts the file
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/hlacount.h is the drop-in boundary: it must be consumable by a C compiler (and so by bindgen / cgo-style
+    tools), not only by the C++ that implements it."""
+    import subprocess
+    src = tmp_path / "use_header.c"
+    src.write_text('#include "hlacount.h"\nint main(void) { hlac_batch b; hlac_packed_batch p; hlac_eqclassdb d; (void)b; (void)p; (void)d;\n'
+                   '  return (int)(HLAC_PACKED_META(1u, 1, 91, 5) >> 63); }\n')
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(H.ROOT, "include"),
+                           "-fsyntax-only", str(src)])
