@@ -1,9 +1,9 @@
 // Counting session: map_and_count_pseudo's hot loop (src/mapping.rs:740-807) and count() (src/mapping.rs:823-909)
 // on the GPU.
 //
-//   K1  k_count_map     one thread per read: filters (mapping.rs:752-763), lazy 4-way map_read policy
-//                       (mapping.rs:765-793), class -> (gene, slot) (mapping.rs:795-806), emits one packed 64-bit key
-//                       (cell | umi | code) per scored read through a warp-aggregated append.
+//   K1  k_count_map_q   queue-staged (default; k_count_map = the earlier tile-staged form): filters (mapping.rs:752-763),
+//                       lazy 4-way map_read policy (mapping.rs:765-793), class -> (gene, slot) (mapping.rs:795-806), emits one
+//                       packed 64-bit key (umi | cell | code) per scored read through a warp-aggregated append.
 //   K3a cub radix sort  keys by (cell, umi)  — the "group by cell then UMI" of mapping.rs:829-841
 //   K3b k_consensus     one thread per (cell, UMI) run: gene majority + allele decision (mapping.rs:843-896)
 //                       accumulated into a dense u32 [n_cells][nrows] matrix.
