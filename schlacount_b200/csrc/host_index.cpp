@@ -283,15 +283,26 @@ void HostIndex::build(const std::vector<Bases>& seqs, const std::vector<std::str
   // sorted. On a device-resident build the caller supplies a GPU radix sort; otherwise an LSD radix sort on the host.
   if (sorter && total >= (1u << 16)) sorter(okey.data(), oval.data(), total);
   else {
+    // host LSD radix sort, 3 passes of 16 bits, stable: every thread histograms and then scatters its own contiguous chunk
+    // into bucket ranges laid out chunk after chunk
     Raw tk, tv; tk.alloc(total); tv.alloc(total);
-    std::vector<size_t> cnt(1 << 16);
+    const size_t nch = std::max<size_t>(1, std::min<size_t>(pool.size(), total / (1u << 16) + 1));
+    std::vector<std::vector<size_t>> cnt(nch, std::vector<size_t>(1 << 16));
+    auto lo = [&](size_t c) { return c * (total / nch) + std::min(c, total % nch); };
     for (int pass = 0; pass < 3; pass++) {
       const int sh = 16 * pass;
-      std::fill(cnt.begin(), cnt.end(), 0);
-      for (size_t i = 0; i < total; i++) cnt[(okey[i] >> sh) & 0xFFFF]++;
+      pool.for_ranges(nch, 1, [&](size_t cb, size_t ce) {
+        for (size_t c = cb; c < ce; c++) {
+          std::fill(cnt[c].begin(), cnt[c].end(), 0);
+          for (size_t i = lo(c); i < lo(c + 1); i++) cnt[c][(okey[i] >> sh) & 0xFFFF]++;
+        }
+      });
       size_t run = 0;
-      for (size_t& c : cnt) { const size_t k = c; c = run; run += k; }
-      for (size_t i = 0; i < total; i++) { const size_t d = cnt[(okey[i] >> sh) & 0xFFFF]++; tk[d] = okey[i]; tv[d] = oval[i]; }
+      for (size_t b = 0; b < (1u << 16); b++) for (size_t c = 0; c < nch; c++) { const size_t k = cnt[c][b]; cnt[c][b] = run; run += k; }
+      pool.for_ranges(nch, 1, [&](size_t cb, size_t ce) {
+        for (size_t c = cb; c < ce; c++)
+          for (size_t i = lo(c); i < lo(c + 1); i++) { const size_t d = cnt[c][(okey[i] >> sh) & 0xFFFF]++; tk[d] = okey[i]; tv[d] = oval[i]; }
+      });
       okey.swap(tk); oval.swap(tv);
     }
   }
