@@ -3,13 +3,19 @@
 
 Workload (N=1): BASELINE config 2 — synthetic 5' GEX, 10 M reads x 91 bp, 10 k barcodes, HLA-A/B/C known-genotype
 counting against the six fixture alleles (CDS + genomic). One step = one full pass of the hot path over the whole
-read set: k_count_map (4-way lazy map_read + class -> gene/slot) -> radix sort of (cell, UMI) keys -> k_consensus ->
-dense count matrix (-> NCCL all-reduce when N > 1) -> COO entries on the host.
-  value : reads/s with the packed batch already resident in HBM (timed with CUDA events on the session stream).
-  e2e   : the same through hlac_count_push with pinned HOST buffers: H2D of every input byte and D2H of the result
-          inside the timed region.
-N > 1: reads are partitioned by barcode, every rank maps its own 10 M-read shard (weak scaling), the
-per-rank dense matrices have disjoint columns and are summed with one NCCL all-reduce.
+read set, ending with ONE assembled result on the host: k_count_map_q (4-way lazy map_read + class -> gene/slot, keys
+appended to per-molecule hash buckets) -> k_group_consensus (shared-memory grouping + count()) -> dense count matrix
+(-> summed over the ranks through the library's own NCCL communicator when N > 1: hlac_count_attach_comm) -> ordered COO
+triplets + metrics written into host-mapped memory; the host synchronises once per step.
+  value : reads/s with the batch already resident in HBM (timed with CUDA events on the session stream).
+  e2e   : the same through hlac_count_push_packed with pinned HOST buffers: H2D of every input byte and the result on
+          the host inside the timed region.
+N > 1: reads are partitioned by barcode, every rank maps its own 10 M-read shard (weak scaling) against
+GLOBAL column indices; hlac_count_finish merges inside the timed region (--merge reduce: dense matrices summed onto rank
+0, which extracts the whole matrix; allreduce: every rank ends with the whole matrix; none: shard-local column blocks, no
+collective - the round-1 number). After the timed region the assembled matrix is checked against the CPU oracle on a
+sample of whole cells of every rank.
+A second record ("geno") times BASELINE config 3 - genotyping against a ~30 k-allele synthetic DB - on rank 0.
 --impl reference: the CPU oracle (a port of the reference; the Rust reference cannot be built in this image) on the
 host cores, on a bounded sample of the same workload.
 """
@@ -35,9 +41,9 @@ SEED = 20191101 + 2
 # algorithmic HBM bytes per read: map stage 32 B in (24 B 2-bit sequence + 4 B cell + 4 B UMI) + 4 B out
 MAP_BYTES_PER_READ = 36
 SORT_BYTES_PER_KEY = 36   # 12-B record read, written sorted, read by the segmented reduce
-# dram__bytes_read.sum + dram__bytes_write.sum of k_count_map per read, from the `ncu --set full` capture
-# profiles/r01_count_map_v3_ncu_digest.txt (70.75 MB + 1.78 MB over 2 M reads); scaled to the reads of one launch
-MAP_DRAM_BYTES_PER_READ_NCU = (70.790656e6 + 1.859072e6) / 2_000_000   # profiles/r01_count_map_v4_ncu_digest.txt
+STEP_BYTES_PER_READ = 72   # map 36 B + grouping 36 B per read
+# measured DRAM traffic of the dominant kernel: written by tools/ncu_digest.py from the latest `ncu --set full` capture
+NCU_TRAFFIC_JSON = os.path.join(ROOT, "profiles", "r02_count_map_traffic.json")
 
 
 class ClockSampler(threading.Thread):
@@ -158,6 +164,119 @@ def run_oracle(r, n, procs, fastas=None):
     return max(o[0] for o in outs), ent
 
 
+def geno_record(args, device, hbm_peak):
+    """BASELINE config 3 on one GPU: genotyping against a synthetic IMGT-like DB (8 genes x --geno-alleles-per-gene alleles
+    derived from the fixture alleles, class I + class II), --geno-reads reads of a 12-allele donor: pseudoalignment + path
+    interning, eq_class_counts (path resolution, UMI grouping), SQUAREM, caller. Reads/s are whole-pipeline numbers for the
+    genotyping half of the reference (mapping_wrapper + em_wrapper, src/mapping.rs:310-405, src/em.rs:339-476)."""
+    import tempfile
+
+    import torch
+
+    import schlacount_b200 as sb
+    from oracle import oracle as orc
+    from tools import synth
+    npg, n = args.geno_alleles_per_gene, args.geno_reads
+    seed = 20191101 + 3
+    db = os.path.join(tempfile.gettempdir(), "hlac_bench_db_%d_%d" % (npg, os.getpid()))
+    t0 = time.perf_counter()
+    names = synth.make_db(db, npg, seed, extra_genes=("DRB1", "DPA1", "DPB1", "DQA1", "DQB1"))
+    donor = [names[g * npg + o] for g in range(8) for o in ((3 + 17 * g) % npg, (npg // 2 + 29 * g) % npg)][:12] + \
+            [names[6 * npg + 5], names[7 * npg + 11]]
+    r = synth.reads_for_db(n, db, donor, 10000, seed)
+    t_gen = time.perf_counter() - t0
+    fa, st = os.path.join(db, "hla_nuc.fasta"), os.path.join(db, "Allele_status.txt")
+    t0 = time.perf_counter()
+    gix = sb.Index.from_fasta(fa, st, device=device)
+    t_build = time.perf_counter() - t0
+    dev = torch.device("cuda", device)
+    u2i = {np.dtype("uint64"): np.int64, np.dtype("uint16"): np.int16, np.dtype("uint32"): np.int32, np.dtype("uint8"): np.uint8}
+    d = {k: torch.from_numpy(v.view(u2i[v.dtype])).to(dev) for k, v in r.items()}
+    hp = {k: torch.from_numpy(v.view(u2i[v.dtype])).pin_memory() for k, v in r.items() if k != "flags"}
+    hn = {k: v.numpy().view(r[k].dtype) for k, v in hp.items()}
+    best = None
+    for rep in range(3):   # rep 0 warms up (kernel attributes, the per-index colour bitsets, allocations)
+        rec = {}
+        for leg in ("device", "host"):
+            g = sb.GenoSession(gix, lean=True)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            if leg == "device":
+                g.push(d["seq"], d["len"], d["cell"], d["umi"])
+            else:
+                for a in range(0, n, 1_000_000):
+                    b = min(n, a + 1_000_000)
+                    g.push(hn["seq"][a:b], hn["len"][a:b], hn["cell"][a:b], hn["umi"][a:b])
+            torch.cuda.synchronize()
+            t_push = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            tab = g.finish(raw=True)
+            t_fin = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            theta, iters = g.squarem(device=device)
+            t_em = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            call = g.call(theta)
+            t_call = time.perf_counter() - t0
+            tm, stt = g.timing(), g.stats()
+            rec[leg] = dict(push_s=t_push, finish_s=t_fin, em_s=t_em, call_s=t_call, total_s=t_push + t_fin + t_em + t_call,
+                            timing_ms=tm, stats=stt, tables=tab, em_iters=iters, called=[gix.tx_names[i] for i in call["called"]],
+                            resolve=g.resolve_stats())
+            g.close()
+        if rep and (best is None or rec["device"]["total_s"] < best["device"]["total_s"]):
+            best = rec
+    dv, ho = best["device"], best["host"]
+    rs = dv["resolve"]
+    out = {"workload": "config3: genotyping, %d alleles (8 genes, class I + II) synthetic IMGT-like DB, %d reads x 91 bp, 12-allele donor, "
+                       "lean tables (counts_reads stays on the device)" % (len(names), n),
+           "metric": "reads pseudoaligned+genotyped/sec", "unit": UNIT,
+           "value": n / dv["total_s"], "e2e": {"value": n / ho["total_s"], "unit": UNIT,
+                                               "h2d_bytes_per_step": int(sum(v.nbytes for v in hn.values())), "ms_per_step": ho["total_s"] * 1e3},
+           "stages_ms": {"map": dv["timing_ms"]["map_ms"], "intern": dv["timing_ms"]["intern_ms"], "push_wall": dv["push_s"] * 1e3,
+                         "finish_wall": dv["finish_s"] * 1e3, "finish_kernels": dv["timing_ms"]["finish_ms"],
+                         "squarem_wall": dv["em_s"] * 1e3, "call_wall": dv["call_s"] * 1e3},
+           "map_reads_per_s": n / (dv["timing_ms"]["map_ms"] / 1e3), "em_iters": dv["em_iters"], "called": dv["called"], "donor": sorted(set(donor)),
+           "index": dict(gix.info, build_s=t_build), "tables": dv["tables"], "stats": dv["stats"], "data_gen_s": t_gen,
+           "gpu_launches": int(dv["timing_ms"]["launches"])}
+    if rs and rs.get("ms", 0) > 0:
+        gbs = rs["bytes"] / (rs["ms"] / 1e3) / 1e9
+        out["roofline"] = {"kernel": "k_resolve_paths_*", "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                           "launch_ms": rs["ms"], "traffic": None,
+                           "algorithmic_bytes": rs["bytes"], "merges": rs["merges"], "element_steps": rs["element_steps"],
+                           "element_steps_per_s": rs["element_steps"] / (rs["ms"] / 1e3),
+                           "note": "algorithmic bytes = per merge one colour membership bitset + per path its colour ids in and its class vector out; "
+                                   "the vectors live in shared memory, so the kernel is bound by shared-memory scans and barriers, not HBM"}
+    # CPU baseline + parity: the oracle on the first reads of the same stream
+    ns = 20000
+    orc.build()
+    oix = orc.Index.from_fasta(fa, st)
+    o = orc.Geno(oix)
+    t0 = time.perf_counter()
+    ci, cv = o.push(r["seq"][:ns], r["len"][:ns], r["cell"][:ns], r["umi"][:ns])
+    o.finish()
+    ocall = o.call()
+    dt = time.perf_counter() - t0
+    g2 = sb.GenoSession(gix, record_reads=True, lean=True)
+    g2.push(r["seq"][:ns], r["len"][:ns], r["cell"][:ns], r["umi"][:ns])
+    t2 = g2.finish()
+    th2, it2 = g2.squarem(device=device)
+    ok = bool(np.array_equal(g2.last_cov(), cv) and np.array_equal(g2.read_class_ids(ns), ci) and t2["counts_umi"] == o.table("umi")
+              and t2["reads_explained"] == o.reads_explained().tolist() and t2["nreads"] == o.nreads
+              and g2.call(th2)["called"] == ocall["called"])
+    assert ok, "genotyping sample differs from the CPU oracle"
+    out["cpu_baseline"] = {"value": ns / dt, "unit": UNIT, "cores": 1, "kind": "port",
+                           "sample": "first %d reads of the stream through map + eq_class_counts + SQUAREM (%d iterations) + caller, single thread; "
+                                     "per-read coverage and class ids, counts_umi, reads_explained and the calls equal the GPU's" % (ns, ocall["iters"])}
+    return out
+
+
+def cell_sample_mask(r, k, n_cells):
+    """reads of the cells c with c % stride == 0 ... — a self-contained sub-problem (count() never mixes cells), plus the same
+    share of the reads outside the whitelist, so that the sample is a scaled-down copy of the workload"""
+    idx = np.arange(len(r["cell"]))
+    return np.where(r["cell"] == 0xFFFFFFFF, idx % n_cells < k, r["cell"] < k)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -174,21 +293,30 @@ def main():
     ap.add_argument("--e2e-format", default="packed", choices=["packed", "soa"],
                     help="host input format of the end-to-end leg: packed 32-byte records (hlac_count_push_packed) or the five "
                          "SoA arrays (hlac_count_push, 35 B/read)")
-    ap.add_argument("--merge", default="none", choices=["none", "allreduce"],
-                    help="N > 1: 'none' = every rank keeps the columns of its own barcodes (shard-local cell indices, no "
-                         "data-path collective); 'allreduce' = global cell indices, one NCCL all-reduce of the dense matrix, "
-                         "rank 0 extracts the whole COO")
+    ap.add_argument("--merge", default="reduce", choices=["reduce", "allreduce", "none"],
+                    help="N > 1: 'reduce' = global columns, the ranks' dense matrices summed onto rank 0 inside hlac_count_finish "
+                         "(library-owned NCCL communicator), rank 0 extracts the whole COO; 'allreduce' = every rank ends with the "
+                         "whole matrix; 'none' = shard-local column blocks, no data-path collective")
+    ap.add_argument("--geno", default="auto", choices=["auto", "on", "off"],
+                    help="config-3 genotyping record (rank 0): auto = on for the default workload")
+    ap.add_argument("--geno-alleles-per-gene", type=int, default=3750, help="x 8 genes = 30 000 alleles (config 3)")
+    ap.add_argument("--geno-reads", type=int, default=2_000_000)
+    ap.add_argument("--parity-cells", type=int, default=6, help="N > 1: cells per rank whose assembled columns are checked against the oracle")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    merge = args.merge if world > 1 else "single"
     config = {"workload": "%s: synthetic 5' GEX, %d reads x 91 bp per GPU, %d barcodes per GPU, %d CDS + %d genomic "
                           "alleles (%d genes x 2), known-genotype counting" % ("config2" if args.genes == 3 else "config4-shape",
                                                                                args.reads, args.cells, 2 * args.genes, 2 * args.genes, args.genes),
-              "reads_per_gpu": args.reads, "barcodes_per_gpu": args.cells, "parallelism": "reads sharded by barcode x%d%s" % (world, "" if world == 1 else (
-                  ", per-rank column blocks, no data-path collective" if args.merge == "none" else ", NCCL all-reduce of the dense matrix")),
-              "l2": "inputs (%.0f MB/step) exceed the 126 MB L2; no explicit flush" % (args.reads * 35 / 1e6),
+              "reads_per_gpu": args.reads, "barcodes_per_gpu": args.cells,
+              "parallelism": "reads sharded by barcode x%d%s" % (world, {
+                  "single": "", "none": ", per-rank column blocks, no data-path collective",
+                  "reduce": ", one matrix assembled on rank 0: ncclReduce of the dense matrices inside hlac_count_finish",
+                  "allreduce": ", every rank assembles the whole matrix: ncclAllReduce inside hlac_count_finish"}[merge]),
+              "l2": "inputs (%.0f MB/step) exceed the 126 MB L2; no explicit flush" % (args.reads * 32 / 1e6),
               "seed": SEED}
 
     if args.impl == "reference":
@@ -225,9 +353,10 @@ def main():
     bound_cpus = bind_near_gpu(local_rank)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    comm = None
     if world > 1:
-        # NCCL prints its version banner on stdout when the communicator is created (first collective); keep stdout
-        # clean for the single JSON line by pointing fd 1 at stderr while that happens.
+        # NCCL prints its version banner on stdout when a communicator is created; keep stdout clean for the single JSON
+        # line by pointing fd 1 at stderr while that happens.
         sys.stdout.flush()
         saved = os.dup(1)
         os.dup2(2, 1)
@@ -235,11 +364,13 @@ def main():
             dist.init_process_group("nccl", device_id=dev)
             dist.all_reduce(torch.zeros(1, device=dev))
             torch.cuda.synchronize()
+            if merge != "none":
+                comm = sb.Comm.from_torch_distributed(local_rank)   # the library's own communicator; torch only carries the id
         finally:
             sys.stdout.flush()
             os.dup2(saved, 1)
             os.close(saved)
-    local = world > 1 and args.merge == "none"
+    local = merge == "none"
     n_cells_total = args.cells if local else args.cells * world   # columns one session holds
     al = allele_set(args.genes)
     r = gen_shard(args.reads, args.cells * world, rank, world, SEED, al, local_ids=local)
@@ -250,54 +381,47 @@ def main():
     stream = torch.cuda.current_stream()
     sess.set_stream(stream.cuda_stream)
     sess.reserve(n)
+    if comm is not None:
+        sess.attach_comm(comm, 0 if merge == "reduce" else -1)
     nrows = sess.nrows
+    has_result = rank == 0 or merge in ("none", "allreduce")
 
-    class _Dense:   # torch view of the session's dense count matrix (for the NCCL all-reduce)
-        def __init__(self, ptr, nelem):
-            self.__cuda_array_interface__ = {"shape": (nelem,), "typestr": "<i4", "data": (ptr, False), "version": 2}
+    def finish_step():   # ONE call: grouping + consensus (+ merge over the ranks) + COO + metrics, one host synchronisation
+        return sess.finish_arrays(copy=False)
 
-    def finish_step():
-        ptr, nelem = sess.reduce()
-        if world > 1 and not local:
-            t = torch.as_tensor(_Dense(ptr, nelem), device=dev)
-            dist.all_reduce(t)
-        return sess.entries_arrays(copy=False) if (rank == 0 or local) else (None, None)
-
-    # device-resident inputs
-    d = {k: torch.from_numpy(v.view(np.int64) if v.dtype == np.uint64 else v.view(np.int16) if v.dtype == np.uint16
-                             else v.view(np.int32) if v.dtype == np.uint32 else v).to(dev) for k, v in r.items()}
+    # device-resident inputs (packed records: the format the end-to-end leg ships)
+    u2i = {np.dtype("uint64"): np.int64, np.dtype("uint16"): np.int16, np.dtype("uint32"): np.int32, np.dtype("uint8"): np.uint8}
+    rec_np = sb.pack_records(r["seq"], r["len"], r["cell"], r["umi"], r["flags"])
+    drec = torch.from_numpy(rec_np.view(np.int64)).to(dev)
 
     def step_device():
         sess.reset()
-        sess.push(d["seq"], d["len"], d["cell"], d["umi"], d["flags"])
+        sess.push_packed(drec)
         return finish_step()
 
     # pinned host inputs
-    h = {k: torch.from_numpy(v.view(np.int64) if v.dtype == np.uint64 else v.view(np.int16) if v.dtype == np.uint16
-                             else v.view(np.int32) if v.dtype == np.uint32 else v).pin_memory() for k, v in r.items()}
-    hn = {k: v.numpy() for k, v in h.items()}
-    hn = {"seq": hn["seq"].view(np.uint64), "len": hn["len"].view(np.uint16), "cell": hn["cell"].view(np.uint32),
-          "umi": hn["umi"].view(np.uint32), "flags": hn["flags"]}
     chunk = args.chunk or n
+    if args.e2e_format == "soa":
+        h = {k: torch.from_numpy(v.view(u2i[v.dtype])).pin_memory() for k, v in r.items()}
+        hn = {k: v.numpy().view(r[k].dtype) for k, v in h.items()}
+        in_bytes = sum(int(v.nbytes) for v in hn.values())
 
-    def step_e2e_soa():
-        sess.reset()
-        for a in range(0, n, chunk):
-            b = min(n, a + chunk)
-            sess.push(hn["seq"][a:b], hn["len"][a:b], hn["cell"][a:b], hn["umi"][a:b], hn["flags"][a:b])
-        return finish_step()
+        def step_e2e():
+            sess.reset()
+            for a in range(0, n, chunk):
+                b = min(n, a + chunk)
+                sess.push(hn["seq"][a:b], hn["len"][a:b], hn["cell"][a:b], hn["umi"][a:b], hn["flags"][a:b])
+            return finish_step()
+    else:
+        hrec_t = torch.from_numpy(rec_np.view(np.int64)).pin_memory()
+        hrec = hrec_t.numpy().view(np.uint64)
+        in_bytes = int(hrec.nbytes)
 
-    # the same batch as packed records (hlac_packed_batch: 32 B per 91-bp read, one H2D copy per push), in pinned memory
-    hrec_t = torch.from_numpy(sb.pack_records(hn["seq"], hn["len"], hn["cell"], hn["umi"], hn["flags"]).view(np.int64)).pin_memory()
-    hrec = hrec_t.numpy().view(np.uint64)
-
-    def step_e2e_packed():
-        sess.reset()
-        for a in range(0, n, chunk):
-            sess.push_packed(hrec[a:min(n, a + chunk)])
-        return finish_step()
-
-    step_e2e = step_e2e_packed if args.e2e_format == "packed" else step_e2e_soa
+        def step_e2e():
+            sess.reset()
+            for a in range(0, n, chunk):
+                sess.push_packed(hrec[a:min(n, a + chunk)])
+            return finish_step()
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
@@ -306,7 +430,7 @@ def main():
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize()
-        sess.timing()
+        launches0 = sess.timing()["launches"]   # of the last warm-up step (the session counts its own kernel launches per step)
         sampler = ClockSampler(local_rank)
         sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -323,45 +447,58 @@ def main():
         clocks = sampler.stop()
         ms = e0.elapsed_time(e1)
         tm = sess.timing()
+        assert tm["launches"] == launches0, "kernel launches per step changed between warm-up and the timed steps"
         if world > 1:
             t = torch.tensor([ms, wall * 1e3], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms, wall = float(t[0]), float(t[1]) / 1e3
         return ms, wall, tm, clocks, sess_out
 
-    # NOTE sess.timing() accumulates since the last reset(): the last step's kernel times are what it returns.
+    # NOTE sess.timing() accumulates since the last reset(): the last step's kernel times / launches are what it returns.
     ms_dev, wall_dev, tm_dev, clocks, out_dev = timed(step_device, args.steps, max(args.warmup, 3))
-    if rank == 0 or local:   # the result arrays are views of the session's pinned buffer: keep a copy across the next loop
+    if has_result:   # the result arrays are views of the session's pinned buffer: keep a copy across the next loop
         out_dev = (tuple(a.copy() for a in out_dev[0]), out_dev[1])
     ms_e2e, wall_e2e, tm_e2e, clocks_e2e, out_e2e = timed(step_e2e, args.steps, max(args.warmup, 3))
     ent, met = out_dev
-    if rank == 0 or local:
+    if has_result:
         assert all(np.array_equal(a, b) for a, b in zip(ent, out_e2e[0])), "device-resident and host-fed passes disagree"
-    n_entries, n_molecules = (int(len(ent[0])), int(ent[2].sum())) if ent is not None else (0, 0)
-    d2h_own = (3 * 4 * n_entries + 10 * 8 + 8 + 8) if ent is not None else 0   # COO triplets + counters + key count + nnz
-    if world > 1:   # whole-job totals for the report (outside the timed regions)
-        if local:       # every rank holds its own column block
-            t = torch.tensor([n_entries, n_molecules, d2h_own], device=dev, dtype=torch.int64)
-            dist.all_reduce(t)
-            n_entries, n_molecules, d2h_own = int(t[0]), int(t[1]), int(t[2])
-        t = torch.tensor(list(met if met is not None else sess.entries_arrays(copy=False)[1]), device=dev, dtype=torch.int64)
+    assert met == out_e2e[1], "metrics of the device-resident and host-fed passes disagree"
+    gstats = sess.group_stats()
+    n_entries, n_molecules = (int(len(ent[0])), int(ent[2].sum())) if has_result else (0, 0)
+    d2h_own = (3 * 4 * n_entries + 17 * 8) if has_result else 17 * 8   # COO triplets + the result header (nnz + counters)
+    if world > 1 and local:   # whole-job totals for the report (outside the timed regions): every rank holds its own column block
+        t = torch.tensor([n_entries, n_molecules, d2h_own] + list(met), device=dev, dtype=torch.int64)
         dist.all_reduce(t)
-        met = [int(x) for x in t]
+        n_entries, n_molecules, d2h_own = int(t[0]), int(t[1]), int(t[2])
+        met = [int(x) for x in t[3:]]
+
+    # ---- in-run parity: the assembled matrix against the CPU oracle on whole cells ----
+    from oracle import oracle as orc
+    orc.build()
+    parity = None
+    if world > 1 and not local:
+        # every rank runs the oracle on all reads of a few of ITS cells; rank 0 compares with the columns it assembled
+        mine = np.unique(r["cell"][r["cell"] != synth.NOT_A_CELL])[:: max(1, (args.cells // max(args.parity_cells, 1)))][:args.parity_cells]
+        m = np.isin(r["cell"], mine)
+        _, ent_cpu = run_oracle({k: v[m] for k, v in r.items()}, int(m.sum()), 1, al[:2])
+        gathered = [None] * world if rank == 0 else None
+        dist.gather_object((mine.tolist(), ent_cpu), gathered, dst=0)
+        if rank == 0:
+            cols = np.array(sorted(c for g in gathered for c in g[0]))
+            want = sorted(e for g in gathered for e in g[1])
+            sel = np.isin(ent[1], cols)
+            got = sorted(zip(ent[0][sel].tolist(), ent[1][sel].tolist(), ent[2][sel].tolist()))
+            assert got == want, "assembled multi-GPU matrix differs from the oracle on the sampled cells"
+            parity = {"checked_cells": int(len(cols)), "checked_entries": len(want), "ranks": world, "equal": True}
 
     total_reads = n * world
     per_step_ms = ms_dev / args.steps
     value = total_reads / (per_step_ms / 1e3)
     e2e_ms = ms_e2e / args.steps
-    # host-side gaps (sync for the key count, COO extraction) are inside both event-bracketed regions
-    in_bytes = int(hrec.nbytes) if args.e2e_format == "packed" else sum(int(v.nbytes) for v in hn.values())
-    d2h_bytes = d2h_own
 
     line = None
     if rank == 0:
-        scored = met[0] - met[1] * 0 - met[2] - met[5]
-        nkeys = n_molecules
-        kern = {"map_ms": tm_dev["map_ms"], "sort_ms": tm_dev["sort_ms"], "consensus_ms": tm_dev["consensus_ms"]}
-        # dominant kernel of OURS: the map kernel (the cub sort is library code and reported beside it)
+        kern = {"map_ms": tm_dev["map_ms"], "group_consensus_ms": tm_dev["group_ms"], "coo_ms": tm_dev["coo_ms"]}
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -370,35 +507,63 @@ def main():
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         map_gbs = n * MAP_BYTES_PER_READ / (tm_dev["map_ms"] / 1e3) / 1e9 if tm_dev["map_ms"] > 0 else None
-        roof = {"bound": "hbm", "kernel": "k_count_map", "achieved": map_gbs, "peak": peak, "unit": "GB/s",
-                "frac": (map_gbs / peak) if map_gbs else None, "traffic": MAP_DRAM_BYTES_PER_READ_NCU * n,
-                "traffic_source": "ncu --set full, profiles/r01_count_map_v4_ncu_digest.txt (bytes/read x reads per launch)",
-                "peak_source": peak_src,
-                "algorithmic_bytes_per_read": MAP_BYTES_PER_READ, "launch_ms": tm_dev["map_ms"],
-                "note": "DRAM traffic equals the algorithmic bytes; the kernel is latency-bound (63 % issue-active, 14.7 of 32 lanes "
-                        "active per instruction) — DESIGN.md §5, profiles/"}
+        traffic, traffic_src = None, "no ncu capture of this kernel version under profiles/ yet"
+        try:
+            tj = json.load(open(NCU_TRAFFIC_JSON))
+            traffic = tj["dram_bytes_per_read"] * n
+            traffic_src = "ncu --set full, %s: %.2f B/read measured x reads per launch" % (tj.get("source", NCU_TRAFFIC_JSON), tj["dram_bytes_per_read"])
+        except Exception:
+            pass
+        step_gbs = n * STEP_BYTES_PER_READ / (per_step_ms / 1e3) / 1e9
+        roof = {"bound": "hbm", "kernel": "k_count_map_q", "achieved": map_gbs, "peak": peak, "unit": "GB/s",
+                "frac": (map_gbs / peak) if map_gbs else None, "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": peak_src, "algorithmic_bytes_per_read": MAP_BYTES_PER_READ, "launch_ms": tm_dev["map_ms"],
+                "step": {"algorithmic_bytes_per_read": STEP_BYTES_PER_READ, "achieved": step_gbs, "frac": step_gbs / peak,
+                         "note": "whole step (map + grouping + consensus + COO + the one host sync) on SURVEY.md 8d's 72 B/read, per GPU"},
+                "note": "DRAM traffic ~ the algorithmic bytes; the kernel is latency/divergence-bound, not bandwidth-bound — DESIGN.md §5, profiles/"}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": per_step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u32", "data": "synthetic", "config": config,
                 "e2e": {"value": total_reads / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": in_bytes * world,
-                        "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_ms, "h2d_ms": tm_e2e["h2d_ms"],
+                        "d2h_bytes_per_step": d2h_own, "ms_per_step": e2e_ms, "h2d_ms": tm_e2e["h2d_ms"],
+                        "h2d_gbs_per_gpu": in_bytes / (tm_e2e["h2d_ms"] / 1e3) / 1e9 if tm_e2e["h2d_ms"] > 0 else None,
                         "input_format": "packed records, %d B/read (hlac_count_push_packed)" % (in_bytes // n) if args.e2e_format == "packed"
                         else "five SoA arrays, %d B/read (hlac_count_push)" % (in_bytes // n)},
-                # our own kernels in the timed region per step (device-resident loop); the radix sort between them is
-                # cub (library): histogram + exclusive-sum + one onesweep pass per 8 key bits
-                "gpu_launches": 5 * args.steps,   # k_count_map, k_consensus, k_coo_count, k_coo_scan, k_coo_write
-                "library_launches": (2 + (int(r["umi"].max()).bit_length() + max(1, (n_cells_total - 1).bit_length()) + 7) // 8) * args.steps,
+                # counted by the session itself (hlac_count_timing): every kernel of ours launched in one step, times the steps.
+                # No library kernel runs on the normal path (cub only sorts on the bucket-overflow fallback; fallbacks below).
+                "gpu_launches": int(tm_dev["launches"]) * args.steps, "library_launches": 0 if gstats["fallbacks"] == 0 else None,
+                "launches_per_step": int(tm_dev["launches"]), "group": gstats,
                 "kernels_ms_last_step": kern, "roofline": roof, "clocks": clocks, "clocks_e2e": clocks_e2e,
                 "wall_ms_per_step": wall_dev / args.steps * 1e3,
-                "result": {"matrix_entries": n_entries, "molecules": nkeys, "metrics": met}, "cpus_bound": bound_cpus}
-        # CPU baseline: the oracle (port) on a bounded sample of the same workload, one core like the reference
+                "result": {"matrix_entries": n_entries, "molecules": n_molecules, "metrics": met}, "cpus_bound": bound_cpus}
+        if parity:
+            line["parity_multi_gpu"] = parity
+        if comm is not None:
+            line["comm"] = comm.info
+        # CPU baseline: the oracle (port) on a bounded sample of the same workload, one core like the reference. The sample is
+        # all reads of the first k cells (+ the same share of non-whitelisted reads), so its entries are exactly the columns
+        # < k of the full result: an in-run parity check for free.
         if world == 1:
-            from oracle import oracle as orc
-            orc.build()
-            ns = min(n, args.cpu_sample)
-            dt, ent_cpu = run_oracle(r, ns, 1, al[:2])
+            k = max(1, int(args.cells * min(1.0, args.cpu_sample / n)))
+            m = cell_sample_mask(r, k, args.cells)
+            ns = int(m.sum())
+            dt, ent_cpu = run_oracle({kk: v[m] for kk, v in r.items()}, ns, 1, al[:2])
+            sel = ent[1] < k
+            got = list(zip(ent[0][sel].tolist(), ent[1][sel].tolist(), ent[2][sel].tolist()))
+            assert got == ent_cpu, "GPU count matrix differs from the CPU oracle on the sampled cells"
             line["cpu_baseline"] = {"value": ns / dt, "unit": UNIT, "cores": 1, "kind": "port",
-                                    "sample": "first %d reads of rank 0's shard, single thread (the reference is single-threaded)" % ns}
+                                    "sample": "all %d reads of the first %d of %d cells (+ the same share of non-whitelisted reads), single "
+                                              "thread (the reference is single-threaded); its %d matrix entries equal the GPU's columns < %d" % (ns, k, args.cells, len(ent_cpu), k)}
+    want_geno = args.geno == "on" or (args.geno == "auto" and args.genes == 3 and args.reads == N_READS)
+    if want_geno and rank == 0:
+        del drec
+        sess.close()
+        torch.cuda.empty_cache()
+        try:
+            line["geno"] = geno_record(args, local_rank, peak)
+        except Exception as e:   # the counting line must survive a failure of the second record
+            line["geno"] = {"error": "%s: %s" % (type(e).__name__, e)}
+    if rank == 0:
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

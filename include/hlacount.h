@@ -42,6 +42,7 @@ typedef enum {
 typedef struct hlac_index hlac_index; /* a Pseudoaligner<KmerType> resident on one device (mapping.rs:318)   */
 typedef struct hlac_count hlac_count; /* one map_and_count_pseudo run (mapping.rs:640-821)                   */
 typedef struct hlac_geno hlac_geno;   /* one mapping_wrapper run + its EqClassDb (mapping.rs:310-405)        */
+typedef struct hlac_comm hlac_comm;   /* one rank of a multi-GPU run: this rank's device + the NCCL communicator */
 
 /* A batch of BamCrRead records (mapping.rs:64-75) in structure-of-arrays form. BAM decoding, region / CB / UB
  * handling stay on the host (mapping.rs:231-279); this is what crosses to the GPU.
@@ -124,6 +125,13 @@ int hlac_device_count(int* n);
  * binding (Rust repr(C), ctypes) can assert its own layouts against the library it loaded */
 int hlac_abi_sizes(uint32_t* out, uint32_t cap);
 
+/* Seed-scan stride of map_read's k-mer search ([EXT] debruijn_mapping find_kmer_match, `*kmer_pos += stride`). The
+ * pinned revision is not vendored and the reference's golden matrices reproduce for strides 1..3 (SURVEY.md finding #4);
+ * 1 (every position) is the default, 3 is what later upstream revisions use. Process-wide; sessions adopt the value
+ * current when they are created. Also settable through the environment (HLAC_SEED_STRIDE=1|3). */
+int hlac_set_seed_stride(int stride); /* 1 or 3 */
+int hlac_get_seed_stride(void);
+
 /* ---- index (replaces utils::read_obj(&hla_index), mapping.rs:318 / em.rs:346, and build_index, mapping.rs:652-662,
  * hla.rs:258) ------------------------------------------------------------------------------------------------ */
 /* device = CUDA ordinal, or -1 for a host-only handle that supports inspection (hlac_index_get_info/_node/_tx_name)
@@ -145,6 +153,21 @@ const char* hlac_index_tx_name(const hlac_index*, uint32_t i); /* Pseudoaligner.
 /* node export (parity checks against the .idx fixture): ASCII sequence, ext byte (high nibble right), colour list */
 int hlac_index_node(const hlac_index*, uint32_t node, char* seq, uint32_t seq_cap, uint32_t* len, uint32_t* exts,
                     uint32_t* colours, uint32_t col_cap, uint32_t* n_col);
+
+/* ---- multi-GPU (the reference is single-threaded: mapping.rs:640-648 / :310-316 stay the seam) ----------
+ * Reads are partitioned by barcode so that every (cell, UMI) molecule is complete on one rank; a session with a
+ * communicator attached merges inside its *_finish. One rank = one device. The communicator is NCCL's, loaded at run time
+ * (libnccl.so.2; a copy already in the process - torch's - is reused). Two ways to build one:
+ *   one process per GPU : rank 0 calls hlac_comm_unique_id, ships the 128 bytes to the other ranks by any means
+ *                         (torch.distributed / MPI / a file), every rank calls hlac_comm_init_rank;
+ *   one process, N GPUs : hlac_comm_init_all (comms[i] = rank i on devices[i]); each rank's calls then come from its own
+ *                         host thread (sc_hla_count --devices does this). */
+#define HLAC_COMM_ID_BYTES 128
+int hlac_comm_unique_id(uint8_t id[HLAC_COMM_ID_BYTES]);
+int hlac_comm_init_rank(const uint8_t id[HLAC_COMM_ID_BYTES], int rank, int nranks, int device, hlac_comm** out);
+int hlac_comm_init_all(const int* devices, int n, hlac_comm** comms);
+int hlac_comm_free(hlac_comm*);
+int hlac_comm_info(const hlac_comm*, int* rank, int* nranks, int* device, int* nccl_version);
 
 /* ---- host-side helpers -------------------------------------------------------------------------------------- */
 int hlac_host_alloc(size_t bytes, void** out); /* pinned host memory for batches */
@@ -185,14 +208,24 @@ int hlac_count_last_codes(hlac_count*, uint8_t* codes, uint64_t n);
 /* seed-filter counters since the last reset: l-mer bitmap tests and exact dictionary probes */
 int hlac_count_probe_stats(hlac_count*, uint64_t* bitmap_tests, uint64_t* dict_probes);
 /* count(): UMI consensus into the dense u32 [n_cells][nrows] matrix on the device; returns its device pointer so a
- * caller sharding reads by barcode can all-reduce it (NCCL) before extracting entries. */
+ * caller sharding reads by barcode can all-reduce it itself before extracting entries (hlac_count_attach_comm +
+ * hlac_count_finish do that inside the library). */
 int hlac_count_reduce(hlac_count*, uint32_t** dense_device, uint64_t* n_elems);
 int hlac_count_entries(hlac_count*, hlac_coo* out, hlac_metrics* metrics); /* after reduce (and optional all-reduce) */
-int hlac_count_finish(hlac_count*, hlac_coo* out, hlac_metrics* metrics);  /* reduce + entries */
+/* reduce + entries fused: grouping, consensus, COO extraction and the counters are enqueued back to back, the COO
+ * triplets and counters land in host-mapped pinned memory and the host synchronises once. With a communicator attached
+ * the dense matrices and the metrics of all ranks are summed in between (collective: every rank must call it). */
+int hlac_count_finish(hlac_count*, hlac_coo* out, hlac_metrics* metrics);
+/* multi-GPU counting: this session holds the reads of the barcodes assigned to its rank, with GLOBAL column indices
+ * (n_cells = all columns). root < 0: all-reduce, every rank returns the whole matrix; root >= 0: reduce, only that rank
+ * returns entries (the others get n = 0); metrics are global on every rank. comm == NULL detaches. */
+int hlac_count_attach_comm(hlac_count*, hlac_comm* comm, int root);
+/* scored reads grouped by the last finish / reduce, hash buckets in use, finishes that had to take the sort path */
+int hlac_count_group_stats(hlac_count*, uint64_t* n_keys, uint32_t* n_buckets, uint64_t* fallbacks);
 int hlac_count_reset(hlac_count*);                              /* drop accumulated reads, keep buffers */
 int hlac_coo_free(hlac_coo*);
 /* kernel timing of the session since the last reset, measured with CUDA events on the session stream:
- * ms[0] = map kernel(s), ms[1] = sort, ms[2] = consensus, ms[3] = H2D copies. launches = kernels launched. */
+ * ms[0] = map kernel(s), ms[1] = grouping + consensus, ms[2] = COO extraction, ms[3] = H2D copies. launches = kernels launched. */
 int hlac_count_timing(hlac_count*, float ms[4], uint64_t* launches);
 
 /* ---- genotyping: mapping_wrapper (mapping.rs:310-405) + em_wrapper's numeric half (em.rs:358-434) ---------------- */
@@ -243,6 +276,9 @@ int hlac_class_tables_free(hlac_class_tables*);
  * on the device-resident class vectors. */
 int hlac_geno_set_lean(hlac_geno*, int on);
 int hlac_geno_timing(hlac_geno*, float ms[4], uint64_t* launches);
+/* the last path resolution (inside hlac_geno_finish*): kernel ms, distinct paths, no-truncate merges emulated, vector
+ * elements walked, compulsory bytes (per merge one colour bitset, per path its colour ids in + its class vector out) */
+int hlac_geno_resolve_stats(hlac_geno*, float* ms, uint64_t* paths, uint64_t* merges, uint64_t* element_steps, uint64_t* bytes);
 
 /* squarem(&eq_class_counts) (em.rs:232-311) on the device, f64. */
 int hlac_squarem(const hlac_class_tables* t, int device, double* theta_out, uint32_t* iters_out);

@@ -50,7 +50,7 @@ namespace orc {
 // ---- constants ------------------------------------------------------------------------------------------
 constexpr int K = 24;                          // PINNED by hla_nuc.fasta.idx (min node length 24)
 constexpr int ALLOWED_MISMATCH = 2;            // README.md:108 (goldens pin 1..4)
-constexpr int STRIDE = 1;                      // unpinned (1..3 reproduce goldens)
+static int STRIDE = 1;                         // unpinned (1..3 reproduce goldens); orc_set_stride picks the one under test
 constexpr double LEFT_EXTEND_FRACTION = 0.2;   // unpinned
 // src/config.rs:4-21
 constexpr size_t MIN_SCORE_CALL = 40;
@@ -741,6 +741,10 @@ struct GenoState { EqClassDb db; EqClassCounts ecc; bool finished = false; std::
 // ============================================================================================================
 using namespace orc;
 extern "C" {
+// seed-scan stride of find() in map_read_to_nodes (process-wide; the reference's pinned dependency is not vendored and the
+// goldens hold for 1..3)
+void orc_set_stride(int s) { orc::STRIDE = s < 1 ? 1 : s; }
+int orc_get_stride() { return orc::STRIDE; }
 
 const char* orc_last_error() { return g_err.c_str(); }
 

@@ -81,6 +81,15 @@ def lib():
     return _LIB
 
 
+def set_stride(s):
+    """seed-scan stride of the oracle's map_read (1..3 reproduce the goldens; default 1)"""
+    lib().orc_set_stride(int(s))
+
+
+def get_stride():
+    return lib().orc_get_stride()
+
+
 def _p(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
 
@@ -250,6 +259,17 @@ class Geno:
         cnt = np.zeros(max(nc, 1), dtype=np.uint32)
         lib().orc_geno_table(self.g, w, _p(off), _p(tx), _p(cnt), nc, ntx.value, None)
         return {tuple(int(t) for t in tx[int(off[i]):int(off[i + 1])]): int(cnt[i]) for i in range(nc)}
+
+    def table_raw(self, which):
+        """which: 'reads' or 'umi' -> CSR numpy arrays (off, tx, cnt) in the oracle's own (map) order"""
+        w = 0 if which == "reads" else 1
+        ntx = C.c_uint64()
+        nc = lib().orc_geno_table(self.g, w, None, None, None, 0, 0, C.byref(ntx))
+        off = np.zeros(nc + 1, dtype=np.uint64)
+        tx = np.zeros(max(ntx.value, 1), dtype=np.uint32)
+        cnt = np.zeros(max(nc, 1), dtype=np.uint32)
+        lib().orc_geno_table(self.g, w, _p(off), _p(tx), _p(cnt), nc, ntx.value, None)
+        return off, tx[:ntx.value], cnt[:nc]
 
     def call(self):
         """-> dict(theta, iters, called tx ids, weights rows, pairs rows)"""

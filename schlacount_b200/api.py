@@ -22,6 +22,71 @@ def _vp(a):
     return C.c_void_p(int(a))
 
 
+def set_seed_stride(stride):
+    """hlac_set_seed_stride: 1 (default) or 3; sessions adopt the value current when they are created"""
+    check(lib().hlac_set_seed_stride(C.c_int(int(stride))))
+
+
+def get_seed_stride():
+    return int(lib().hlac_get_seed_stride())
+
+
+class Comm:
+    """hlac_comm: one rank of a multi-GPU run (NCCL communicator owned by the library)."""
+
+    ID_BYTES = 128
+
+    def __init__(self, handle):
+        self.h = handle
+
+    @staticmethod
+    def unique_id():
+        buf = (C.c_uint8 * Comm.ID_BYTES)()
+        check(lib().hlac_comm_unique_id(buf))
+        return bytes(buf)
+
+    @classmethod
+    def init_rank(cls, uid, rank, nranks, device):
+        h = C.c_void_p()
+        buf = (C.c_uint8 * Comm.ID_BYTES).from_buffer_copy(uid)
+        check(lib().hlac_comm_init_rank(buf, C.c_int(rank), C.c_int(nranks), C.c_int(device), C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def init_all(cls, devices):
+        n = len(devices)
+        arr = (C.c_int * n)(*devices)
+        hs = (C.c_void_p * n)()
+        check(lib().hlac_comm_init_all(arr, C.c_int(n), hs))
+        return [cls(C.c_void_p(h)) for h in hs]
+
+    @classmethod
+    def from_torch_distributed(cls, device):
+        """bootstrap over an initialised torch.distributed group: rank 0's id is broadcast as a byte tensor"""
+        import torch
+        import torch.distributed as dist
+        rank, world = dist.get_rank(), dist.get_world_size()
+        on_gpu = dist.get_backend() == "nccl"
+        t = torch.zeros(Comm.ID_BYTES, dtype=torch.uint8)
+        if rank == 0:
+            t = torch.frombuffer(bytearray(cls.unique_id()), dtype=torch.uint8).clone()
+        if on_gpu:
+            t = t.to(torch.device("cuda", device))
+        dist.broadcast(t, 0)
+        return cls.init_rank(bytes(t.cpu().numpy().tobytes()), rank, world, device)
+
+    @property
+    def info(self):
+        r, n, d, v = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        check(lib().hlac_comm_info(self.h, C.byref(r), C.byref(n), C.byref(d), C.byref(v)))
+        return dict(rank=r.value, nranks=n.value, device=d.value, nccl_version=v.value)
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().hlac_comm_free(self.h)
+            self.h = None
+
+
 def pack_reads(seqs, words_per_read=None):
     """DnaString::from_acgt_bytes packing through the library's own packer (hlac_pack_read)."""
     n = len(seqs)
@@ -246,9 +311,30 @@ class CountSession:
         lib().hlac_coo_free(C.byref(coo))
         return out, [getattr(m, k) for k, _ in _lib.Metrics._fields_]
 
+    def attach_comm(self, comm, root=-1):
+        """hlac_count_attach_comm: finish() then merges over the communicator (root < 0: all-reduce)"""
+        check(lib().hlac_count_attach_comm(self.h, comm.h if comm is not None else None, C.c_int(root)))
+        self._comm = comm
+
     def finish(self):
-        self.reduce()
-        return self.entries()
+        """hlac_count_finish -> ([(row, col, val)], metrics)"""
+        (r, c, v), m = self.finish_arrays()
+        return list(zip(r.tolist(), c.tolist(), v.tolist())), m
+
+    def finish_arrays(self, copy=True):
+        """hlac_count_finish as three numpy arrays; copy=False returns views of the session's pinned result buffer"""
+        coo = _lib.Coo()
+        m = _lib.Metrics()
+        check(lib().hlac_count_finish(self.h, C.byref(coo), C.byref(m)))
+        n = int(coo.n)
+        if n:
+            out = tuple(np.ctypeslib.as_array(p, shape=(n,)) for p in (coo.row, coo.col, coo.val))
+            if copy:
+                out = tuple(a.copy() for a in out)
+        else:
+            out = tuple(np.zeros(0, np.uint32) for _ in range(3))
+        lib().hlac_coo_free(C.byref(coo))
+        return out, [getattr(m, k) for k, _ in _lib.Metrics._fields_]
 
     def reset(self):
         check(lib().hlac_count_reset(self.h))
@@ -257,7 +343,12 @@ class CountSession:
         ms = (C.c_float * 4)()
         n = C.c_uint64()
         check(lib().hlac_count_timing(self.h, ms, C.byref(n)))
-        return dict(map_ms=ms[0], sort_ms=ms[1], consensus_ms=ms[2], h2d_ms=ms[3], launches=n.value)
+        return dict(map_ms=ms[0], group_ms=ms[1], coo_ms=ms[2], h2d_ms=ms[3], launches=n.value)
+
+    def group_stats(self):
+        k, b, f = C.c_uint64(), C.c_uint32(), C.c_uint64()
+        check(lib().hlac_count_group_stats(self.h, C.byref(k), C.byref(b), C.byref(f)))
+        return dict(keys=k.value, buckets=b.value, fallbacks=f.value)
 
     def probe_stats(self):
         a, b = C.c_uint64(), C.c_uint64()
@@ -435,6 +526,30 @@ class GenoSession:
         n = C.c_uint64()
         check(lib().hlac_geno_timing(self.h, ms, C.byref(n)))
         return dict(map_ms=ms[0], intern_ms=ms[1], finish_ms=ms[2], h2d_ms=ms[3], launches=n.value)
+
+    def resolve_stats(self):
+        ms = C.c_float()
+        v = [C.c_uint64() for _ in range(4)]
+        check(lib().hlac_geno_resolve_stats(self.h, C.byref(ms), *[C.byref(x) for x in v]))
+        return dict(ms=ms.value, paths=v[0].value, merges=v[1].value, element_steps=v[2].value, bytes=v[3].value)
+
+    def tables_csr(self):
+        """the finished tables as numpy CSR arrays: dict(reads=(off, tx, cnt) or None in lean mode, umi=(off, tx, cnt),
+        reads_explained, nreads)"""
+        t = self.tables
+
+        def csr(n, off, tx, cnt):
+            n = int(n)
+            if not off:
+                return None
+            o = np.ctypeslib.as_array(off, shape=(n + 1,)).copy()
+            tot = int(o[n]) if n else 0
+            return (o, np.ctypeslib.as_array(tx, shape=(max(tot, 1),))[:tot].copy(),
+                    np.ctypeslib.as_array(cnt, shape=(max(n, 1),))[:n].copy())
+        return dict(reads=csr(t.n_read_classes, t.reads_off, t.reads_tx, t.reads_cnt),
+                    umi=csr(t.n_umi_classes, t.umi_off, t.umi_tx, t.umi_cnt),
+                    reads_explained=np.ctypeslib.as_array(t.reads_explained, shape=(max(t.nitems, 1),))[:t.nitems].copy(),
+                    nreads=int(t.nreads))
 
     def squarem(self, device=0):
         theta = np.zeros(self.tables.nitems, dtype=np.float64)

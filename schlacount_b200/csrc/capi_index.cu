@@ -12,6 +12,15 @@ using namespace hlac;
 namespace hlac {
 static thread_local std::string g_last_error;
 void set_last_error(const std::string& m) { g_last_error = m; }
+static int g_seed_stride = 0;   // 0 = not set yet: HLAC_SEED_STRIDE from the environment, else the default
+int seed_stride() {
+  if (g_seed_stride == 0) {
+    const char* e = getenv("HLAC_SEED_STRIDE");
+    const int v = e ? atoi(e) : DEFAULT_SEED_STRIDE;
+    g_seed_stride = (v == 1 || v == 3) ? v : DEFAULT_SEED_STRIDE;
+  }
+  return g_seed_stride;
+}
 }  // namespace hlac
 
 #define HLAC_API_BEGIN try {
@@ -52,6 +61,13 @@ int hlac_abi_sizes(uint32_t* out, uint32_t cap) {
   for (uint32_t i = 0; i < 9 && i < cap; i++) out[i] = v[i];   // the 8th (hlac_eqclassdb) and 9th (hlac_packed_batch) only if the caller made room
   return HLAC_OK;
 }
+
+int hlac_set_seed_stride(int stride) {
+  if (stride != 1 && stride != 3) { set_last_error("seed stride must be 1 or 3 (the kernels are instantiated for these two)"); return HLAC_ERR_ARG; }
+  hlac::g_seed_stride = stride;
+  return HLAC_OK;
+}
+int hlac_get_seed_stride(void) { return hlac::seed_stride(); }
 
 int hlac_device_count(int* n) {
   HLAC_API_BEGIN

@@ -13,7 +13,7 @@ constexpr int K = HLAC_K;                     // Kmer24 (pinned by test/fake_db/
 constexpr uint64_t KMER_MASK = (1ULL << (2 * K)) - 1;
 // map_read constants [EXT debruijn_mapping @ae4aadbc; SURVEY.md Appendix A]. Unpinned ones are named here.
 constexpr int ALLOWED_MISMATCH = 2;           // README.md:108
-constexpr int SEED_STRIDE = 1;                // unpinned by the goldens (1..3)
+constexpr int DEFAULT_SEED_STRIDE = 1;        // unpinned by the goldens (1..3 reproduce both); hlac_set_seed_stride selects 1 or 3
 constexpr int LEFT_EXTEND_NUM = 1, LEFT_EXTEND_DEN = 5;  // floor(0.2 * L)
 // src/config.rs:4-21
 constexpr uint32_t MIN_SCORE_CALL = 40;
@@ -37,6 +37,7 @@ struct Error : std::runtime_error {
 };
 
 void set_last_error(const std::string& m);
+int seed_stride();   // the process-wide seed-scan stride new sessions adopt (hlac_set_seed_stride / HLAC_SEED_STRIDE)
 
 // DnaString::from_acgt_bytes [EXT]: ACGT either case -> 0..3, everything else -> A
 inline uint8_t base_code(char c) {

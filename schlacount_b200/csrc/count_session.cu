@@ -1,12 +1,17 @@
 // Counting session: map_and_count_pseudo's hot loop (src/mapping.rs:740-807) and count() (src/mapping.rs:823-909)
 // on the GPU.
 //
-//   K1  k_count_map_q   queue-staged (default; k_count_map = the earlier tile-staged form): filters (mapping.rs:752-763),
-//                       lazy 4-way map_read policy (mapping.rs:765-793), class -> (gene, slot) (mapping.rs:795-806), emits one
-//                       packed 64-bit key (umi | cell | code) per scored read through a warp-aggregated append.
-//   K3a cub radix sort  keys by (cell, umi)  — the "group by cell then UMI" of mapping.rs:829-841
-//   K3b k_consensus     one thread per (cell, UMI) run: gene majority + allele decision (mapping.rs:843-896)
-//                       accumulated into a dense u32 [n_cells][nrows] matrix.
+//   K1  k_count_map_q       queue-staged: filters (mapping.rs:752-763), lazy 4-way map_read policy (mapping.rs:765-793),
+//                           class -> (gene, slot) (mapping.rs:795-806); every scored read leaves as one packed 64-bit key
+//                           (umi | cell | code) appended to the hash BUCKET of its (cell, UMI) molecule.
+//   K3  k_group_consensus   one block per bucket: the "group by cell then UMI" of mapping.rs:829-841 as a shared-memory
+//                           hash grouping (no global sort: count() only needs the reads of a molecule together, and the
+//                           result is accumulated into a dense matrix, so no order is needed anywhere), then the gene
+//                           majority + allele decision of mapping.rs:843-896 per molecule -> dense u32 [n_cells][nrows].
+//   K4  k_coo_count/_scan/_write  dense matrix -> ordered COO triplets written straight into host-mapped pinned memory,
+//                           together with the counters: the host synchronises ONCE per finish.
+// Fallback (a bucket overflowed: a molecule deeper than a bucket, or a hostile hash pattern): all keys are gathered, sorted
+// with cub and reduced by k_consensus — the round-1 path, kept for exactness, never on the normal path.
 //
 // Laziness: the reference evaluates all four map_read calls eagerly but only consumes them through the if/else-if
 // chain at mapping.rs:772-793; map_read is pure, so evaluating a call only when the chain reaches it yields the
@@ -25,6 +30,7 @@
 #include <memory>
 #include <vector>
 
+#include "comm.hpp"
 #include "device_index.hpp"
 #include "hla_fasta.hpp"
 
@@ -35,6 +41,29 @@ namespace {
 constexpr uint32_t CODE_NONE5 = 31;   // 5-bit "no code"
 constexpr int CODE_BITS = 5;
 constexpr int UMI_BITS = 32;
+constexpr uint32_t BUCKET_CAP = 2048;      // keys per bucket (16 KB of shared memory in k_group_consensus)
+constexpr uint32_t BUCKET_TARGET = 1024;   // buckets are provisioned for at most this many keys on average
+
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
+  x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ULL; x ^= x >> 27; x *= 0x94d049bb133111ebULL; x ^= x >> 31;
+  return x;
+}
+
+// where the keys of the scored reads go: bucket = hash of the molecule (umi, cell), so a molecule is complete in one bucket
+struct BucketStore {
+  uint64_t* keys;                 // [n_buckets][BUCKET_CAP]
+  uint32_t* fill;                 // [n_buckets] keys offered to the bucket (> BUCKET_CAP: the excess went to `ovf`)
+  uint32_t mask;                  // n_buckets - 1 (power of two)
+  uint64_t* ovf;                  // overflow list
+  unsigned long long* ovf_cursor;
+  uint64_t ovf_cap;
+};
+__device__ __forceinline__ void bucket_append(const BucketStore& bs, uint64_t key) {
+  const uint32_t b = (uint32_t)mix64(key >> CODE_BITS) & bs.mask;
+  const uint32_t at = atomicAdd(bs.fill + b, 1u);
+  if (at < BUCKET_CAP) bs.keys[(size_t)b * BUCKET_CAP + at] = key;
+  else { const unsigned long long o = atomicAdd(bs.ovf_cursor, 1ULL); if (o < bs.ovf_cap) bs.ovf[o] = key; }
+}
 
 struct CountMapArgs {
   DevIndexView cds, gen;
@@ -50,8 +79,7 @@ struct CountMapArgs {
   int primary_only;
   uint32_t cell_bits;          // key layout: umi << (5 + cell_bits) | cell << 5 | code
   uint32_t n_cells;            // cell indices >= n_cells are a caller error: dropped and counted in metrics[8]
-  uint64_t* keys;
-  unsigned long long* cursor;  // number of keys appended so far
+  BucketStore bk;
   unsigned long long* metrics; // [6] + [2] seed-filter tests / dictionary probes + [1] out-of-range cell indices + [1] max UMI key
   uint8_t* codes;              // optional per-read debug output
   const uint64_t* rec;         // packed records (hlac_packed_batch) instead of the five arrays above, or NULL
@@ -86,169 +114,15 @@ struct BitmapGlobal {
   __device__ __forceinline__ uint32_t operator()(uint32_t i) const { return __ldg(p + i); }
 };
 
-// Warp-staged kernel. Each WARP owns a tile of 32*R reads and moves it through stages, compacting the surviving reads
-// into dense warp-private task queues in shared memory between stages, so that the lanes of a warp always execute the
-// same kind of work and no block-wide barrier is needed (ncu history in profiles/: thread-per-read version 6.65 of 32
-// lanes active per issued instruction; block-staged version 12.6 lanes but 30 % of stall samples on __syncthreads):
-//   load    filters (mapping.rs:752-763), read rows into shared memory, queue 0
-//   scan p  p = cds-fwd, cds-rev, gen-fwd, gen-rev: first-seed skip-scan for the reads still without a seed
-//           (map_read is None iff its FIRST seed scan fails, so the laziness of mapping.rs:772-790 is a cascade of scans);
-//           reads that find a seed go to the walk queue, the others to the next scan queue (revcomp built at p = 1)
-//   walk    every read with a seed: left extension + forward walk + class code + coverage policy, key append
-// Queue counters are warp-uniform registers (every lane sees the same ballots), so the queues need no atomics.
-template <bool SMEM_BM, int R, int MAP_THREADS, int MINB = 1>
-__global__ void __launch_bounds__(MAP_THREADS, MINB) k_count_map(const CountMapArgs a) {
-  extern __shared__ __align__(16) uint32_t smem[];
-  constexpr int TILE = 32 * R;
-  uint32_t* wbase = smem;
-  if (SMEM_BM) {
-    const uint32_t nb = a.cds.bitmap_words + a.gen.bitmap_words;
-    for (uint32_t i = threadIdx.x; i < a.cds.bitmap_words; i += MAP_THREADS) smem[i] = __ldg(a.cds.bitmap + i);
-    for (uint32_t i = threadIdx.x; i < a.gen.bitmap_words; i += MAP_THREADS) smem[a.cds.bitmap_words + i] = __ldg(a.gen.bitmap + i);
-    wbase = smem + nb;
-    __syncthreads();   // the only block-wide barrier
-  }
-  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t per_warp = TILE * a.row_stride + TILE * 2 + TILE / 2 + 3 * TILE / 4;   // u32 words
-  uint32_t* rows = wbase + warp * per_warp;
-  uint32_t* seed_node = rows + TILE * a.row_stride;
-  uint32_t* seed_info = seed_node + TILE;                                   // off(20) | pos(10) | phase(2)
-  uint16_t* lens = reinterpret_cast<uint16_t*>(seed_info + TILE);
-  uint8_t* q = reinterpret_cast<uint8_t*>(lens + TILE);                     // 3 queues of TILE slots
-  unsigned long long m_reads = 0, m_nonprim = 0, m_notcell = 0, m_cds = 0, m_gen = 0, m_none = 0, m_badcell = 0;
-  uint32_t n_tests = 0, n_probes = 0, umi_max = 0;
-  const uint64_t n_warps = (uint64_t)gridDim.x * (MAP_THREADS / 32);
-  for (uint64_t tile = (uint64_t)blockIdx.x * (MAP_THREADS / 32) + warp; tile * TILE < a.n; tile += n_warps) {
-    const uint64_t base = tile * TILE;
-    unsigned cnt0 = 0, cnt1 = 0, cntw = 0;   // warp-uniform queue lengths
-    __syncwarp();
-    // ---- load: all global loads of a read are issued before any is consumed ----
-#pragma unroll
-    for (int r = 0; r < R; r++) {
-      const unsigned slot = r * 32 + lane;
-      const uint64_t i = base + slot;
-      bool keep = false;
-      if (i < a.n) {
-        const uint8_t fl = __ldg(a.flags + i);
-        const uint32_t cell = __ldg(a.cell + i);
-        const uint16_t L = (uint16_t)min((uint32_t)__ldg(a.len + i), 32u * a.wpr);   // never read past the packed words
-        uint32_t* fw = rows + slot * a.row_stride;
-        for (uint32_t w = 0; w < a.wpr; w++) {
-          const uint64_t v = __ldg(a.seq + i * a.wpr + w);
-          fw[2 * w] = (uint32_t)(v >> 32); fw[2 * w + 1] = (uint32_t)v;
-        }
-        fw[2 * a.wpr] = 0; fw[2 * a.wpr + 1] = 0;
-        lens[slot] = L;
-        m_reads++;
-        const bool primary = fl & HLAC_FLAG_PRIMARY;
-        if (!primary) m_nonprim++;
-        if (primary || !a.primary_only) {
-          if (cell == HLAC_NOT_A_CELL) m_notcell++;
-          else if (cell >= a.n_cells) m_badcell++;
-          else keep = true;
-        }
-        if (a.codes) a.codes[i] = (uint8_t)HLAC_CODE_NONE;
-      }
-      const unsigned ballot = __ballot_sync(0xFFFFFFFFu, keep);
-      if (keep) q[cnt0 + __popc(ballot & ((1u << lane) - 1))] = (uint8_t)slot;
-      cnt0 += __popc(ballot);
-    }
-    __syncwarp();
-    // ---- scan cascade ----
-#pragma unroll 1
-    for (int p = 0; p < 4; p++) {
-      const unsigned nt = (p & 1) ? cnt1 : cnt0;
-      uint8_t* qc = q + ((p & 1) ? TILE : 0);
-      uint8_t* qn = q + ((p & 1) ? 0 : TILE);
-      unsigned cntn = 0;
-      const DevIndexView& ix = p < 2 ? a.cds : a.gen;
-      for (unsigned t0 = 0; t0 < nt; t0 += 32) {
-        const bool task = t0 + lane < nt;
-        bool found = false;
-        unsigned slot = 0;
-        if (task) {
-          slot = qc[t0 + lane];
-          uint32_t* fw = rows + slot * a.row_stride;
-          uint32_t* rc = fw + a.nw;
-          const int L = lens[slot];
-          if (p == 1) make_revcomp(SharedWords{fw}, rc, L, (int)a.nw);
-          SharedWords rd{(p & 1) ? rc : fw};
-          int pos = 0; uint32_t node = 0, off = 0;
-          if (L >= K) {
-            if (SMEM_BM) found = find_seed(ix, rd, BitmapShared{smem + (p < 2 ? 0 : a.cds.bitmap_words)}, pos, L - K, node, off, n_tests, n_probes);
-            else found = find_seed(ix, rd, BitmapGlobal{ix.bitmap}, pos, L - K, node, off, n_tests, n_probes);
-          }
-          if (found) { seed_node[slot] = node; seed_info[slot] = (off << 12) | ((uint32_t)pos << 2) | (uint32_t)p; }
-        }
-        __syncwarp();
-        const unsigned bf = __ballot_sync(0xFFFFFFFFu, task && found), bn = __ballot_sync(0xFFFFFFFFu, task && !found);
-        const unsigned below = (1u << lane) - 1;
-        if (task && found) q[2 * TILE + cntw + __popc(bf & below)] = (uint8_t)slot;
-        if (task && !found) qn[cntn + __popc(bn & below)] = (uint8_t)slot;
-        cntw += __popc(bf); cntn += __popc(bn);
-      }
-      if (p & 1) { cnt0 = cntn; cnt1 = 0; } else { cnt1 = cntn; cnt0 = 0; }
-      __syncwarp();
-    }
-    if (lane == 0) m_none += cnt0;   // all four None (mapping.rs:791-793): survivors of p = 3 sit in queue 0
-    // ---- walk ----
-    for (unsigned t0 = 0; t0 < cntw; t0 += 32) {
-      uint32_t code = CODE_NONE5;
-      uint64_t key = 0;
-      if (t0 + lane < cntw) {
-        const unsigned slot = q[2 * TILE + t0 + lane];
-        const uint64_t i = base + slot;
-        const uint32_t info = seed_info[slot];
-        const int p = (int)(info & 3u), pos = (int)((info >> 2) & 1023u);
-        const uint32_t off = info >> 12, node = seed_node[slot];
-        uint32_t* fw = rows + slot * a.row_stride;
-        const int L = lens[slot];
-        const DevIndexView& ix = p < 2 ? a.cds : a.gen;
-        SharedWords rd{(p & 1) ? fw + a.nw : fw};
-        CountVis vis;
-        uint32_t cov;
-        if (SMEM_BM) cov = walk_from_seed(ix, rd, BitmapShared{smem + (p < 2 ? 0 : a.cds.bitmap_words)}, L, pos, node, off, vis, n_tests, n_probes);
-        else cov = walk_from_seed(ix, rd, BitmapGlobal{ix.bitmap}, L, pos, node, off, vis, n_tests, n_probes);
-        const bool good = cov > MIN_SCORE_COUNT_PSEUDO;
-        if (good) { if (p < 2) m_cds++; else m_gen++; }
-        if (p == 0 || good) code = vis.code();   // a CDS-forward hit is used whatever its coverage (mapping.rs:772-775)
-        if (code != CODE_NONE5) {
-          const uint32_t um = __ldg(a.umi + i);
-          umi_max = max(umi_max, um);
-          key = ((uint64_t)um << (CODE_BITS + a.cell_bits)) | ((uint64_t)__ldg(a.cell + i) << CODE_BITS) | code;
-          if (a.codes) a.codes[i] = (uint8_t)code;
-        }
-      }
-      __syncwarp();
-      const unsigned ballot = __ballot_sync(0xFFFFFFFFu, code != CODE_NONE5);
-      if (ballot) {
-        unsigned long long at = 0;
-        if (lane == 0) at = atomicAdd(a.cursor, (unsigned long long)__popc(ballot));
-        at = __shfl_sync(0xFFFFFFFFu, at, 0);
-        if (code != CODE_NONE5) a.keys[at + __popc(ballot & ((1u << lane) - 1))] = key;
-      }
-    }
-  }
-  // metrics: warp reduce then one atomic per counter per warp
-  unsigned long long m[9] = {m_reads, m_nonprim, m_notcell, m_cds, m_gen, m_none, n_tests, n_probes, m_badcell};
-#pragma unroll
-  for (int k = 0; k < 9; k++) {
-    unsigned long long v = m[k];
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, o);
-    if (lane == 0 && v) atomicAdd(a.metrics + k, v);
-  }
-  for (int o = 16; o > 0; o >>= 1) umi_max = max(umi_max, __shfl_down_sync(0xFFFFFFFFu, umi_max, o));
-  if (lane == 0 && umi_max) atomicMax(a.metrics + 9, (unsigned long long)umi_max);   // how many UMI bits the sort must cover
-}
-
-// Queue-staged variant of the same kernel (shape R = 0). Instead of moving one fixed tile through the stages, each
+// Queue-staged map kernel (ncu history of its predecessors in profiles/: thread-per-read 6.65 of 32 lanes active per issued
+// instruction, block-staged 12.6 lanes but barrier-bound, warp-staged tiles 12.2, this one 14.65). Each
 // warp keeps a pool of NS read slots and two warp-private task queues that persist across refills: SCAN entries are
 // (slot, p) with p = the orientation/index the chain of mapping.rs:772-790 has reached, WALK entries are slots with
 // a seed. A round of either kind only runs when 32 tasks are waiting (or the warp's input is exhausted), so every
 // round starts with all lanes busy whatever fraction of the reads survives each stage; scan rounds mix the four
 // orientations (same code, per-lane operands). The warp streams a contiguous range of the batch and refills the
 // pool with as many reads as there are free slots.
-template <bool SMEM_BM, int MAP_THREADS, int MINB, bool PACKED>
+template <bool SMEM_BM, int MAP_THREADS, int MINB, bool PACKED, int STRIDE>
 __global__ void __launch_bounds__(MAP_THREADS, MINB) k_count_map_q(const CountMapArgs a) {
   extern __shared__ __align__(16) uint32_t smem[];
   constexpr int NS = 64;
@@ -351,8 +225,8 @@ __global__ void __launch_bounds__(MAP_THREADS, MINB) k_count_map_q(const CountMa
         const DevIndexView& ix = p < 2 ? a.cds : a.gen;
         int pos = 0; uint32_t node = 0, off = 0;
         if (L >= K) {
-          if (SMEM_BM) found = find_seed(ix, rd, BitmapShared{smem + (p < 2 ? 0 : a.cds.bitmap_words)}, pos, L - K, node, off, n_tests, n_probes);
-          else found = find_seed(ix, rd, BitmapGlobal{ix.bitmap}, pos, L - K, node, off, n_tests, n_probes);
+          if (SMEM_BM) found = find_seed<STRIDE>(ix, rd, BitmapShared{smem + (p < 2 ? 0 : a.cds.bitmap_words)}, pos, L - K, node, off, n_tests, n_probes);
+          else found = find_seed<STRIDE>(ix, rd, BitmapGlobal{ix.bitmap}, pos, L - K, node, off, n_tests, n_probes);
         }
         if (found) { seed_node[slot] = node; seed_info[slot] = (off << 12) | ((uint32_t)pos << 2) | p; }
       }
@@ -386,8 +260,8 @@ __global__ void __launch_bounds__(MAP_THREADS, MINB) k_count_map_q(const CountMa
         SharedWords rd{(p & 1) ? fw + a.nw : fw};
         CountVis vis;
         uint32_t cov;
-        if (SMEM_BM) cov = walk_from_seed(ix, rd, BitmapShared{smem + (p < 2 ? 0 : a.cds.bitmap_words)}, L, pos, node, off, vis, n_tests, n_probes);
-        else cov = walk_from_seed(ix, rd, BitmapGlobal{ix.bitmap}, L, pos, node, off, vis, n_tests, n_probes);
+        if (SMEM_BM) cov = walk_from_seed<STRIDE>(ix, rd, BitmapShared{smem + (p < 2 ? 0 : a.cds.bitmap_words)}, L, pos, node, off, vis, n_tests, n_probes);
+        else cov = walk_from_seed<STRIDE>(ix, rd, BitmapGlobal{ix.bitmap}, L, pos, node, off, vis, n_tests, n_probes);
         const bool good = cov > MIN_SCORE_COUNT_PSEUDO;
         if (good) { if (p < 2) m_cds++; else m_gen++; }
         if (p == 0 || good) code = vis.code();   // a CDS-forward hit is used whatever its coverage (mapping.rs:772-775)
@@ -404,13 +278,7 @@ __global__ void __launch_bounds__(MAP_THREADS, MINB) k_count_map_q(const CountMa
       nwk = qb;
       if (task) fr[nfree + lane] = (uint8_t)slot;
       nfree += cnt;
-      const unsigned ballot = __ballot_sync(0xFFFFFFFFu, code != CODE_NONE5);
-      if (ballot) {
-        unsigned long long at = 0;
-        if (lane == 0) at = atomicAdd(a.cursor, (unsigned long long)__popc(ballot));
-        at = __shfl_sync(0xFFFFFFFFu, at, 0);
-        if (code != CODE_NONE5) a.keys[at + __popc(ballot & below)] = key;
-      }
+      if (code != CODE_NONE5) bucket_append(a.bk, key);
       __syncwarp();
     }
   }
@@ -425,14 +293,108 @@ __global__ void __launch_bounds__(MAP_THREADS, MINB) k_count_map_q(const CountMa
   if (lane == 0 && umi_max) atomicMax(a.metrics + 9, (unsigned long long)umi_max);
 }
 
-// count() (mapping.rs:842-896) for one (cell, UMI) run of the sorted keys.
+// ---- count() (mapping.rs:842-896) -------------------------------------------------------------------------------
+// the decision for one molecule from its per-candidate counts: nreads scored reads, f = (allele 1, allele 2, gene) reads of
+// the majority candidate gene. Returns the row slot or -1 (no gene above 50 %, mapping.rs:874-875). f64 compares as in
+// the reference (mapping.rs:879-889).
+__device__ __forceinline__ int consensus_slot(uint32_t nreads, const uint32_t f[3]) {
+  const double nr = (double)nreads;
+  const uint32_t ng = f[0] + f[1] + f[2];
+  if (!((double)ng > GENE_CONSENSUS_THRESHOLD * nr)) return -1;
+  if ((double)f[0] > ALLELE_CONSENSUS_THRESHOLD * nr && ALLELE_CONSENSUS_THRESHOLD * nr > (double)f[1]) return 0;
+  if ((double)f[1] > ALLELE_CONSENSUS_THRESHOLD * nr && ALLELE_CONSENSUS_THRESHOLD * nr > (double)f[0]) return 1;
+  return 2;
+}
+
+// One block per bucket (persistent over the bucket list). The keys of the bucket are grouped by molecule with an
+// open-addressing table in shared memory: the first key of a molecule to claim a slot becomes its representative, later
+// keys push themselves onto the representative's list (atomicExch); then one thread per molecule walks its list twice —
+// Boyer-Moore majority gene (only a gene with > 50 % of the molecule's reads can win, and the vote finds it whatever the
+// order), then the candidate's three counts — and adds 1 to the dense matrix. Nothing here depends on the order of the
+// keys, and the dense matrix is order-free, so no sort is needed.
+constexpr int GROUP_THREADS = 256;
+__global__ void __launch_bounds__(GROUP_THREADS) k_group_consensus(const BucketStore bs, uint32_t* __restrict__ dense, uint32_t nrows,
+                                                                   const uint32_t* __restrict__ gene_row0, uint32_t cell_bits,
+                                                                   unsigned long long* n_keys_out) {
+  __shared__ uint64_t k[BUCKET_CAP];
+  __shared__ uint32_t lnk[BUCKET_CAP];          // representative: head of its member list; member: next member (index + 1, 0 = end)
+  __shared__ uint32_t ht[2 * BUCKET_CAP];       // index + 1 of the molecule's representative key
+  if (*bs.ovf_cursor) return;                   // a bucket overflowed: the host takes the sort path for this step
+  const unsigned t = threadIdx.x;
+  unsigned long long my_keys = 0;
+  for (uint32_t b = blockIdx.x; b <= bs.mask; b += gridDim.x) {
+    const uint32_t n = min(bs.fill[b], BUCKET_CAP);
+    if (n == 0) continue;
+    uint32_t hsz = 64;
+    while (hsz < 2 * n) hsz <<= 1;
+    const uint32_t hmask = hsz - 1;
+    __syncthreads();                            // the previous bucket's lists have been read
+    const uint64_t* src = bs.keys + (size_t)b * BUCKET_CAP;
+    for (uint32_t i = t; i < n; i += GROUP_THREADS) { k[i] = src[i]; lnk[i] = 0; }
+    for (uint32_t i = t; i < hsz; i += GROUP_THREADS) ht[i] = 0;
+    if (t == 0) my_keys += n;
+    __syncthreads();
+    for (uint32_t i = t; i < n; i += GROUP_THREADS) {
+      const uint64_t g = k[i] >> CODE_BITS;
+      uint32_t h = (uint32_t)(mix64(g) >> 32) & hmask;
+      for (;;) {
+        uint32_t cur = *(volatile uint32_t*)(ht + h);
+        if (cur == 0) { cur = atomicCAS(ht + h, 0u, i + 1); if (cur == 0) break; }   // claimed: this key represents the molecule
+        if ((k[cur - 1] >> CODE_BITS) == g) { lnk[i] = atomicExch(lnk + cur - 1, i + 1); break; }
+        h = (h + 1) & hmask;
+      }
+    }
+    __syncthreads();
+    for (uint32_t h = t; h < hsz; h += GROUP_THREADS) {
+      const uint32_t rep = ht[h];
+      if (rep == 0) continue;
+      // pass 1: majority-vote candidate gene
+      uint32_t cand = (uint32_t)(k[rep - 1] & 31u) / 3, votes = 1, nreads = 1;
+      for (uint32_t m = lnk[rep - 1]; m; m = lnk[m - 1]) {
+        const uint32_t g = (uint32_t)(k[m - 1] & 31u) / 3;
+        if (votes == 0) { cand = g; votes = 1; }
+        else if (g == cand) votes++;
+        else votes--;
+        nreads++;
+      }
+      // pass 2: the candidate's (allele 1, allele 2, gene) counts
+      uint32_t f[3] = {0, 0, 0};
+      { const uint32_t c = (uint32_t)(k[rep - 1] & 31u); if (c / 3 == cand) f[c % 3]++; }
+      for (uint32_t m = lnk[rep - 1]; m; m = lnk[m - 1]) { const uint32_t c = (uint32_t)(k[m - 1] & 31u); if (c / 3 == cand) f[c % 3]++; }
+      const int slot = consensus_slot(nreads, f);
+      if (slot < 0) continue;
+      const uint32_t cell = (uint32_t)(k[rep - 1] >> CODE_BITS) & ((1u << cell_bits) - 1u);
+      atomicAdd(dense + (size_t)cell * nrows + gene_row0[cand] + slot, 1u);
+    }
+  }
+  if (t == 0 && my_keys) atomicAdd(n_keys_out, my_keys);
+}
+
+// the buckets double: every key of old bucket b goes to new bucket b or b + old_n (one more hash bit)
+__global__ void k_rebucket(const BucketStore from, const BucketStore to) {
+  for (uint32_t b = blockIdx.x; b <= from.mask; b += gridDim.x) {
+    const uint32_t n = min(from.fill[b], BUCKET_CAP);
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) bucket_append(to, from.keys[(size_t)b * BUCKET_CAP + i]);
+  }
+}
+
+// ---- fallback path: gather every key into one array, cub radix sort, one thread per (cell, UMI) run ------------------
+__global__ void k_gather_keys(const BucketStore bs, uint64_t* out, unsigned long long* cursor) {
+  __shared__ unsigned long long base;
+  for (uint32_t b = blockIdx.x; b <= bs.mask; b += gridDim.x) {
+    const uint32_t n = min(bs.fill[b], BUCKET_CAP);
+    __syncthreads();
+    if (threadIdx.x == 0) base = n ? atomicAdd(cursor, (unsigned long long)n) : 0;
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) out[base + i] = bs.keys[(size_t)b * BUCKET_CAP + i];
+  }
+}
 __global__ void k_consensus(const uint64_t* __restrict__ keys, uint64_t n, uint32_t* __restrict__ dense, uint32_t nrows,
                             const uint32_t* __restrict__ gene_row0, uint32_t cell_bits) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint64_t k0 = keys[i], grp = k0 >> CODE_BITS;
   if (i > 0 && (keys[i - 1] >> CODE_BITS) == grp) return;   // not a run head
-  // pass 1: majority-vote candidate gene (only a gene with > 50 % of the UMI's reads can win, mapping.rs:874-875)
   uint32_t cand = 0, votes = 0, nreads = 0;
   for (uint64_t j = i; j < n; j++) {
     const uint64_t k = keys[j];
@@ -443,19 +405,13 @@ __global__ void k_consensus(const uint64_t* __restrict__ keys, uint64_t n, uint3
     else votes--;
     nreads++;
   }
-  // pass 2: the candidate's (allele 1, allele 2, gene) counts
   uint32_t f[3] = {0, 0, 0};
   for (uint64_t j = i; j < i + nreads; j++) {
     const uint32_t c = (uint32_t)(keys[j] & 31u);
     if (c / 3 == cand) f[c % 3]++;
   }
-  const double nr = (double)nreads;
-  const uint32_t ng = f[0] + f[1] + f[2];
-  if (!((double)ng > GENE_CONSENSUS_THRESHOLD * nr)) return;
-  uint32_t slot;
-  if ((double)f[0] > ALLELE_CONSENSUS_THRESHOLD * nr && ALLELE_CONSENSUS_THRESHOLD * nr > (double)f[1]) slot = 0;
-  else if ((double)f[1] > ALLELE_CONSENSUS_THRESHOLD * nr && ALLELE_CONSENSUS_THRESHOLD * nr > (double)f[0]) slot = 1;
-  else slot = 2;
+  const int slot = consensus_slot(nreads, f);
+  if (slot < 0) return;
   const uint32_t cell = (uint32_t)(k0 >> CODE_BITS) & ((1u << cell_bits) - 1u);
   atomicAdd(dense + (size_t)cell * nrows + gene_row0[cand] + slot, 1u);
 }
@@ -473,8 +429,11 @@ __global__ void k_coo_count(const uint32_t* __restrict__ dense, uint64_t n, uint
   __syncthreads();
   if (threadIdx.x == 0) { uint32_t t = 0; for (int w = 0; w < COO_THREADS / 32; w++) t += warp_cnt[w]; block_nnz[blockIdx.x] = t; }
 }
-// single block: exclusive scan of the per-block counts; total to block_off[nblocks]
-__global__ void k_coo_scan(const uint32_t* __restrict__ block_nnz, uint32_t nblocks, uint64_t* block_off) {
+// single block: exclusive scan of the per-block counts; total to block_off[nblocks]. It also publishes the step's scalars
+// to the host-mapped result header: [0] nnz, [1..] a copy of the session counters.
+constexpr int N_COUNTERS = 16;
+__global__ void k_coo_scan(const uint32_t* __restrict__ block_nnz, uint32_t nblocks, uint64_t* block_off,
+                           const unsigned long long* __restrict__ counters, unsigned long long* host_hdr) {
   __shared__ uint64_t carry;
   __shared__ uint64_t part[1024];
   if (threadIdx.x == 0) carry = 0;
@@ -495,10 +454,14 @@ __global__ void k_coo_scan(const uint32_t* __restrict__ block_nnz, uint32_t nblo
     if (threadIdx.x == 1023) carry += part[1023];
     __syncthreads();
   }
-  if (threadIdx.x == 0) block_off[nblocks] = carry;
+  if (threadIdx.x == 0) { block_off[nblocks] = carry; if (host_hdr) host_hdr[0] = carry; }
+  if (host_hdr && threadIdx.x < N_COUNTERS) host_hdr[1 + threadIdx.x] = counters[threadIdx.x];
 }
+// row / col / val may point into host-mapped pinned memory (zero-copy stores: only the non-zeros cross PCIe, and the host
+// needs no second synchronisation to learn how many there are). cap = capacity of the three arrays (entries beyond it are
+// dropped; the host sees nnz > cap and reports it).
 __global__ void k_coo_write(const uint32_t* __restrict__ dense, uint64_t n, uint32_t nrows, const uint64_t* __restrict__ block_off,
-                            uint32_t* row, uint32_t* col, uint32_t* val) {
+                            uint32_t* row, uint32_t* col, uint32_t* val, uint64_t cap) {
   __shared__ uint32_t warp_off[COO_THREADS / 32];
   const uint64_t base = (uint64_t)blockIdx.x * COO_TILE + (uint64_t)threadIdx.x * COO_PER_THREAD;
   uint32_t v[COO_PER_THREAD]; uint32_t c = 0;
@@ -514,7 +477,8 @@ __global__ void k_coo_write(const uint32_t* __restrict__ dense, uint64_t n, uint
 #pragma unroll
   for (int k = 0; k < COO_PER_THREAD; k++) if (v[k]) {
     const uint64_t e = base + k;
-    row[at] = (uint32_t)(e % nrows); col[at] = (uint32_t)(e / nrows); val[at] = v[k]; at++;
+    if (at < cap) { row[at] = (uint32_t)(e % nrows); col[at] = (uint32_t)(e / nrows); val[at] = v[k]; }
+    at++;
   }
 }
 
@@ -547,13 +511,17 @@ struct hlac_count {
   hlac_index* cds = nullptr;
   hlac_index* gen = nullptr;
   int device = 0;
+  int stride = 1;                        // seed-scan stride (hlac_set_seed_stride) the session was created with
   cudaStream_t stream = nullptr;
   bool own_stream = true;
   RowLayout rows;
   uint32_t n_cells = 0;
   int primary_only = 0;
   DevBuf<uint32_t> nodes_cds, nodes_gen, gene_row0, dense;   // node tables with cinfo in place of the colour id
-  DevBuf<uint64_t> keys, keys_sorted;
+  // bucket store of the scored reads' keys; `keys` = overflow list (and the gather target of the fallback path)
+  DevBuf<uint64_t> bk_keys, keys, keys_sorted;
+  DevBuf<uint32_t> bk_fill;
+  uint32_t n_buckets = 0;
   uint64_t host_reads = 0, host_non_primary = 0, host_not_cell = 0;   // reads the host driver filtered out itself (hlac_count_add_filtered)
   struct Stage {   // one staging set for host batches; two of them so the H2D of batch i+1 overlaps the kernel of batch i
     DevBuf<uint64_t> seq, rec; DevBuf<uint16_t> len; DevBuf<uint32_t> cell, umi; DevBuf<uint8_t> flags;
@@ -562,22 +530,28 @@ struct hlac_count {
   cudaStream_t copy_stream = nullptr;
   uint64_t n_push = 0;
   DevBuf<uint8_t> codes;
-  DevBuf<uint32_t> coo_block_nnz, coo_dev; DevBuf<uint64_t> coo_block_off;   // device-side COO extraction
-  uint32_t* coo_host = nullptr; size_t coo_host_cap = 0;                      // pinned, 3 arrays back to back, session-owned
-  DevBuf<unsigned long long> counters;   // [0] cursor, [1..8] metrics
+  DevBuf<uint32_t> coo_block_nnz; DevBuf<uint64_t> coo_block_off;             // device-side COO extraction
+  uint32_t* coo_host = nullptr; size_t coo_cap = 0;                           // pinned + mapped: row[cap] col[cap] val[cap], written by k_coo_write
+  unsigned long long* host_hdr = nullptr;                                     // pinned + mapped: [0] nnz, [1..16] counters
+  // [0] keys grouped, [1..6] metrics, [7] bitmap tests, [8] dictionary probes, [9] bad cells, [10] max UMI key, [11] overflow cursor,
+  // [12] gather cursor (fallback)
+  // [13..15] reads the host driver filtered out itself (uploaded at finish so that a merge sums them like the others)
+  DevBuf<unsigned long long> counters, counters_merged;
   DevBuf<uint8_t> cub_tmp;
   uint64_t reads_pushed = 0, last_n = 0;
   bool smem_bm = false;
   size_t bitmap_smem_bytes = 0;
-  int blocks_per_sm = 1, n_sm = 1;
+  int n_sm = 1;
   bool want_codes = false;
   bool reduced = false;
   uint32_t cell_bits = 1;
   uint32_t cfg_wpr = 0;
-  int cfg_occ = 0, cfg_r = 0, cfg_threads = 0;
+  int cfg_occ = 0, cfg_threads = 0;
   bool cfg_bm = false;
   void* cfg_kern = nullptr; void* cfg_kern_packed = nullptr;
-  uint64_t n_keys = 0;
+  int group_occ = 0;
+  uint64_t fallbacks = 0;                // finishes that had to take the sort path
+  hlac_comm* comm = nullptr; int comm_root = -1;
   // timing
   struct Ev { cudaEvent_t a, b; int kind; };
   std::vector<Ev> events;
@@ -587,6 +561,7 @@ struct hlac_count {
   ~hlac_count() {
     for (auto& e : events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     if (coo_host) cudaFreeHost(coo_host);
+    if (host_hdr) cudaFreeHost(host_hdr);
     for (auto& st : stage) { if (st.copied) cudaEventDestroy(st.copied); if (st.consumed) cudaEventDestroy(st.consumed); }
     if (copy_stream) cudaStreamDestroy(copy_stream);
     if (stream && own_stream) cudaStreamDestroy(stream);
@@ -607,16 +582,59 @@ struct hlac_count {
     }
     events.clear();
   }
+  size_t nd() const { return (size_t)n_cells * std::max<uint32_t>(rows.nrows, 1); }
+  BucketStore store() { return BucketStore{bk_keys.p, bk_fill.p, n_buckets - 1, keys.p, counters.p + 11, keys.cap}; }
   void reset() {
-    HLAC_CUDA(cudaMemsetAsync(counters.p, 0, 11 * sizeof(unsigned long long), stream));
-    reads_pushed = 0; last_n = 0; reduced = false; n_keys = 0; host_reads = host_non_primary = host_not_cell = 0;
+    HLAC_CUDA(cudaMemsetAsync(counters.p, 0, N_COUNTERS * sizeof(unsigned long long), stream));
+    if (n_buckets) HLAC_CUDA(cudaMemsetAsync(bk_fill.p, 0, (size_t)n_buckets * 4, stream));
+    reads_pushed = 0; last_n = 0; reduced = false; host_reads = host_non_primary = host_not_cell = 0;
     drain_events(); ms[0] = ms[1] = ms[2] = ms[3] = 0; launches = 0;
+  }
+
+  // make room for `total` reads in all: buckets provisioned for <= BUCKET_TARGET keys on average (every read could be
+  // scored), the overflow list for every read. Growing re-buckets what is already there (one more hash bit per doubling).
+  void ensure_capacity(uint64_t total) {
+    keys.reserve(std::max<uint64_t>(total, 1), stream, true, keys.cap);   // keeps the overflow entries written so far
+    uint64_t want = 64;
+    while (want * BUCKET_TARGET < total) want <<= 1;
+    if (want > (1ull << 30)) throw Error(HLAC_ERR_LIMIT, "too many reads for one counting session");
+    if (want <= n_buckets) return;
+    DevBuf<uint64_t> nk; DevBuf<uint32_t> nf;
+    nk.reserve((size_t)want * BUCKET_CAP, stream); nf.reserve(want, stream);
+    HLAC_CUDA(cudaMemsetAsync(nf.p, 0, (size_t)want * 4, stream));
+    if (n_buckets && reads_pushed) {
+      const BucketStore from = store();
+      BucketStore to{nk.p, nf.p, (uint32_t)want - 1, keys.p, counters.p + 11, keys.cap};
+      k_rebucket<<<std::min<uint32_t>(n_buckets, (uint32_t)n_sm * 8), 256, 0, stream>>>(from, to);
+      HLAC_CUDA(cudaGetLastError());
+      launches++;
+    }
+    HLAC_CUDA(cudaStreamSynchronize(stream));
+    std::swap(bk_keys.p, nk.p); std::swap(bk_keys.cap, nk.cap);
+    std::swap(bk_fill.p, nf.p); std::swap(bk_fill.cap, nf.cap);
+    n_buckets = (uint32_t)want;
+  }
+
+  using Kern = void (*)(const CountMapArgs);
+  struct Shape { bool bm; int threads; Kern k, k_packed; };
+  template <int S>
+  static const Shape* shapes(int& n) {
+    // measured best first (profiles/r01_count_map_tuning.md): 1024 resident threads per SM with the l-mer bitmaps in
+    // shared memory; the L1 variants take over when the bitmaps do not fit next to the read slots
+    static const Shape sh[] = {
+#define HLAC_QSHAPE(BM, TT, MB) {BM, TT, k_count_map_q<BM, TT, MB, false, S>, k_count_map_q<BM, TT, MB, true, S>}
+        HLAC_QSHAPE(true, 1024, 1), HLAC_QSHAPE(true, 512, 2), HLAC_QSHAPE(false, 256, 4), HLAC_QSHAPE(false, 128, 8),
+#undef HLAC_QSHAPE
+    };
+    n = (int)(sizeof sh / sizeof sh[0]);
+    return sh;
   }
 
   void launch_map(const hlac_batch& b /* device pointers */, const uint64_t* rec = nullptr /* packed records instead of b's arrays */) {
     if (b.n == 0) return;
     if (b.words_per_read == 0 || b.words_per_read > 16) throw Error(HLAC_ERR_ARG, "words_per_read must be 1..16");
-    keys.reserve(reads_pushed + b.n, stream, true, reads_pushed);
+    if (b.n >= (1ull << 32)) throw Error(HLAC_ERR_LIMIT, "the count kernel takes batches below 2^32 reads");
+    ensure_capacity(reads_pushed + b.n);
     if (want_codes) codes.reserve(b.n, stream);
     CountMapArgs a{};
     a.cds = cds->view; a.gen = gen->view;
@@ -624,65 +642,136 @@ struct hlac_count {
     a.seq = b.seq; a.len = b.len; a.cell = b.cell; a.umi = b.umi; a.flags = b.flags;
     a.n = b.n; a.wpr = b.words_per_read; a.nw = 2 * b.words_per_read + 2; a.row_stride = (2 * a.nw) | 1;
     a.primary_only = primary_only; a.n_cells = n_cells; a.cell_bits = cell_bits;
-    a.keys = keys.p; a.cursor = counters.p; a.metrics = counters.p + 1;
+    a.bk = store(); a.metrics = counters.p + 1;
     a.codes = want_codes ? codes.p : nullptr;
     a.rec = rec;
-    // launch shape: (bitmaps in shared memory?, reads per lane per warp tile R, threads per block). Defaults below;
-    // HLAC_COUNT_SHAPE="smem,R,threads" overrides them for tuning runs.
-    using Kern = void (*)(const CountMapArgs);
-    auto smem_for = [&](bool bm, int r, int threads) {
-      const size_t per_warp_words = r == 0 ? (size_t)64 * a.row_stride + 64 * 3 + 64 / 2 + 3 * 64 / 4   // queue-staged kernel
-                                           : (size_t)32 * r * a.row_stride + 32 * r * 2 + 32 * r / 2 + 3 * 32 * r / 4;
+    // launch shape: (bitmaps in shared memory?, threads per block); HLAC_COUNT_SHAPE="smem,threads" overrides for tuning runs
+    auto smem_for = [&](bool bm, int threads) {
+      const size_t per_warp_words = (size_t)64 * a.row_stride + 64 * 3 + 64 / 2 + 3 * 64 / 4;
       return (bm ? bitmap_smem_bytes : 0) + (threads / 32) * per_warp_words * 4;
     };
     if (cfg_wpr != b.words_per_read) {
-      struct Shape { bool bm; int r, threads; Kern k; int minb = 1; Kern k_packed = nullptr; };
-      static const Shape shapes[] = {
-#define HLAC_SHAPE(BM, RR, TT) {BM, RR, TT, k_count_map<BM, RR, TT>}
-          // defaults first: measured best on B200 (profiles/r01_count_map_tuning.md) — the queue-staged kernel (R = 0) at
-          // 1024 resident threads per SM, then the tile-staged shapes (occupancy beats tile size)
-#define HLAC_QSHAPE(BM, TT, MB) {BM, 0, TT, k_count_map_q<BM, TT, MB, false>, 1, k_count_map_q<BM, TT, MB, true>}
-          HLAC_QSHAPE(true, 1024, 1), HLAC_QSHAPE(true, 512, 2), HLAC_QSHAPE(false, 256, 4), HLAC_QSHAPE(false, 128, 8),
-#undef HLAC_QSHAPE
-          HLAC_SHAPE(true, 2, 1024), HLAC_SHAPE(true, 1, 512), HLAC_SHAPE(true, 1, 256), HLAC_SHAPE(true, 4, 512), HLAC_SHAPE(true, 2, 512),
-          HLAC_SHAPE(false, 2, 128), HLAC_SHAPE(false, 1, 128), HLAC_SHAPE(false, 2, 256), HLAC_SHAPE(false, 1, 256), HLAC_SHAPE(false, 4, 128),
-          HLAC_SHAPE(true, 4, 256), HLAC_SHAPE(true, 8, 256), HLAC_SHAPE(false, 4, 256), HLAC_SHAPE(false, 8, 128),
-          {false, 1, 128, k_count_map<false, 1, 128, 12>, 12}, {false, 1, 128, k_count_map<false, 1, 128, 16>, 16},
-          {true, 1, 512, k_count_map<true, 1, 512, 3>, 3}};
-#undef HLAC_SHAPE
+      int ns = 0;
+      const Shape* sh = stride == 3 ? shapes<3>(ns) : shapes<1>(ns);
       const Shape* pick = nullptr;
-      int want_bm = -1, want_r = 0, want_t = 0, want_minb = 1;
-      if (const char* e = getenv("HLAC_COUNT_SHAPE")) sscanf(e, "%d,%d,%d,%d", &want_bm, &want_r, &want_t, &want_minb);
-      for (const Shape& sh : shapes) {
-        if (want_bm >= 0) { if ((int)sh.bm != want_bm || sh.r != want_r || sh.threads != want_t || sh.minb != want_minb) continue; }
-        else if (sh.minb != 1) continue;
-        else if (sh.bm != smem_bm) continue;
-        if (sh.bm && !smem_bm) continue;
-        if (smem_for(sh.bm, sh.r, sh.threads) > 227 * 1024) continue;
-        pick = &sh; break;
+      int want_bm = -1, want_t = 0;
+      if (const char* e = getenv("HLAC_COUNT_SHAPE")) sscanf(e, "%d,%d", &want_bm, &want_t);
+      for (int i = 0; i < ns; i++) {
+        if (want_bm >= 0) { if ((int)sh[i].bm != want_bm || sh[i].threads != want_t) continue; }
+        else if (sh[i].bm != smem_bm) continue;
+        if (sh[i].bm && !smem_bm) continue;
+        if (smem_for(sh[i].bm, sh[i].threads) > 227 * 1024) continue;
+        pick = &sh[i]; break;
       }
       if (!pick) throw Error(HLAC_ERR_LIMIT, "no launch shape of the count kernel fits (reads too long, or bad HLAC_COUNT_SHAPE)");
-      cfg_bm = pick->bm; cfg_r = pick->r; cfg_threads = pick->threads; cfg_kern = (void*)pick->k; cfg_kern_packed = (void*)pick->k_packed;
-      if (pick->k_packed) HLAC_CUDA(cudaFuncSetAttribute(pick->k_packed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(cfg_bm, cfg_r, cfg_threads)));
-      HLAC_CUDA(cudaFuncSetAttribute(pick->k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(cfg_bm, cfg_r, cfg_threads)));
-      HLAC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cfg_occ, pick->k, cfg_threads, smem_for(cfg_bm, cfg_r, cfg_threads)));
+      cfg_bm = pick->bm; cfg_threads = pick->threads; cfg_kern = (void*)pick->k; cfg_kern_packed = (void*)pick->k_packed;
+      const int smem = (int)smem_for(cfg_bm, cfg_threads);
+      HLAC_CUDA(cudaFuncSetAttribute(pick->k_packed, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      HLAC_CUDA(cudaFuncSetAttribute(pick->k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      HLAC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cfg_occ, pick->k, cfg_threads, smem));
       if (cfg_occ < 1) throw Error(HLAC_ERR_LIMIT, "count map kernel does not fit on the device");
       cfg_wpr = b.words_per_read;
     }
-    if (rec && !cfg_kern_packed) throw Error(HLAC_ERR_ARG, "packed records need the queue-staged count kernel (HLAC_COUNT_SHAPE selects a tile-staged shape)");
     Kern kern = (Kern)(rec ? cfg_kern_packed : cfg_kern);
-    const size_t smem = smem_for(cfg_bm, cfg_r, cfg_threads);
-    const int MAP_R = cfg_r ? cfg_r : 2, MAP_THREADS = cfg_threads;
-    if (cfg_r == 0 && b.n >= (1ull << 32)) throw Error(HLAC_ERR_LIMIT, "the queue-staged count kernel takes batches below 2^32 reads");
-    const int occ = cfg_occ;
-    const uint64_t need = (b.n + (uint64_t)MAP_THREADS * MAP_R - 1) / ((uint64_t)MAP_THREADS * MAP_R);
-    const unsigned grid = (unsigned)std::min<uint64_t>(need, (uint64_t)n_sm * occ);
+    const size_t smem = smem_for(cfg_bm, cfg_threads);
+    const uint64_t need = (b.n + (uint64_t)cfg_threads * 2 - 1) / ((uint64_t)cfg_threads * 2);
+    const unsigned grid = (unsigned)std::min<uint64_t>(need, (uint64_t)n_sm * cfg_occ);
     Ev& e = begin(0);
-    kern<<<grid, MAP_THREADS, smem, stream>>>(a);
+    kern<<<grid, cfg_threads, smem, stream>>>(a);
     HLAC_CUDA(cudaGetLastError());
     end(e);
     launches++;
     reads_pushed += b.n; last_n = b.n; reduced = false;
+  }
+
+  // count() into the dense matrix, enqueued only (no host synchronisation)
+  void enqueue_group() {
+    HLAC_CUDA(cudaMemsetAsync(dense.p, 0, nd() * sizeof(uint32_t), stream));
+    if (!n_buckets) return;
+    if (!group_occ) HLAC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&group_occ, k_group_consensus, GROUP_THREADS, 0));
+    Ev& e = begin(1);
+    k_group_consensus<<<std::min<uint32_t>(n_buckets, (uint32_t)(n_sm * std::max(group_occ, 1))), GROUP_THREADS, 0, stream>>>(
+        store(), dense.p, rows.nrows, gene_row0.p, cell_bits, counters.p);
+    HLAC_CUDA(cudaGetLastError());
+    end(e);
+    launches++;
+  }
+  // the round-1 path: gather all keys, radix sort, one thread per run. Synchronous; used when a bucket overflowed.
+  void fallback_group() {
+    unsigned long long c[N_COUNTERS];
+    HLAC_CUDA(cudaMemcpyAsync(c, counters.p, sizeof c, cudaMemcpyDeviceToHost, stream));
+    HLAC_CUDA(cudaStreamSynchronize(stream));
+    const uint64_t n_ovf = c[11];
+    if (n_ovf > keys.cap) throw Error(HLAC_ERR_STATE, "overflow list overran (internal error)");
+    HLAC_CUDA(cudaMemsetAsync(dense.p, 0, nd() * sizeof(uint32_t), stream));
+    unsigned long long cur = n_ovf;   // bucket contents are appended behind the overflow entries
+    HLAC_CUDA(cudaMemcpyAsync(counters.p + 12, &cur, 8, cudaMemcpyHostToDevice, stream));
+    keys.reserve(n_ovf + (uint64_t)std::min<uint64_t>(reads_pushed, (uint64_t)n_buckets * BUCKET_CAP), stream, true, n_ovf);
+    k_gather_keys<<<std::min<uint32_t>(n_buckets, (uint32_t)n_sm * 8), 256, 0, stream>>>(store(), keys.p, counters.p + 12);
+    HLAC_CUDA(cudaGetLastError());
+    HLAC_CUDA(cudaMemcpyAsync(&cur, counters.p + 12, 8, cudaMemcpyDeviceToHost, stream));
+    HLAC_CUDA(cudaStreamSynchronize(stream));
+    const uint64_t nk = cur;
+    if (nk) {
+      keys_sorted.reserve(nk, stream);
+      int umi_bits = 1;
+      while (umi_bits < UMI_BITS && (c[10] >> umi_bits)) umi_bits++;
+      const int end_bit = CODE_BITS + (int)cell_bits + umi_bits;
+      size_t tmp = 0;
+      HLAC_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tmp, keys.p, keys_sorted.p, (uint64_t)nk, CODE_BITS, end_bit, stream));
+      cub_tmp.reserve(tmp, stream);
+      Ev& e1 = begin(1);
+      HLAC_CUDA(cub::DeviceRadixSort::SortKeys(cub_tmp.p, tmp, keys.p, keys_sorted.p, (uint64_t)nk, CODE_BITS, end_bit, stream));
+      k_consensus<<<(unsigned)((nk + 255) / 256), 256, 0, stream>>>(keys_sorted.p, nk, dense.p, rows.nrows, gene_row0.p, cell_bits);
+      HLAC_CUDA(cudaGetLastError());
+      end(e1);
+      launches += 2;
+    }
+    unsigned long long nk_ull = nk;
+    HLAC_CUDA(cudaMemcpyAsync(counters.p, &nk_ull, 8, cudaMemcpyHostToDevice, stream));
+    HLAC_CUDA(cudaStreamSynchronize(stream));
+    fallbacks++;
+  }
+  // dense -> COO into the host-mapped buffers, enqueued only
+  void enqueue_coo() {
+    const uint64_t n = nd();
+    const uint32_t nrows = rows.nrows;
+    // nnz <= min(matrix size, molecules <= reads pushed); with a communicator the matrix holds every rank's molecules
+    const uint64_t cap = comm ? n : std::min<uint64_t>(n, std::max<uint64_t>(reads_pushed, 1));
+    if (!host_hdr) {
+      HLAC_CUDA(cudaHostAlloc((void**)&host_hdr, (1 + N_COUNTERS) * 8, cudaHostAllocMapped | cudaHostAllocPortable));
+      memset(host_hdr, 0, (1 + N_COUNTERS) * 8);
+    }
+    if (nrows && coo_cap < cap) {
+      HLAC_CUDA(cudaStreamSynchronize(stream));
+      if (coo_host) cudaFreeHost(coo_host);
+      coo_host = nullptr; coo_cap = 0;
+      const size_t want = std::min<uint64_t>(n, cap + cap / 2 + 1024);
+      HLAC_CUDA(cudaHostAlloc((void**)&coo_host, want * 12, cudaHostAllocMapped | cudaHostAllocPortable));
+      coo_cap = want;
+    }
+    const uint32_t nb = nrows ? (uint32_t)((n + COO_TILE - 1) / COO_TILE) : 0;
+    coo_block_nnz.reserve(std::max<uint32_t>(nb, 1), stream); coo_block_off.reserve(nb + 1, stream);
+    Ev& e = begin(2);
+    if (nb) k_coo_count<<<nb, COO_THREADS, 0, stream>>>(dense.p, n, coo_block_nnz.p);
+    k_coo_scan<<<1, 1024, 0, stream>>>(coo_block_nnz.p, nb, coo_block_off.p, comm ? counters_merged.p : counters.p, host_hdr);
+    if (nb) k_coo_write<<<nb, COO_THREADS, 0, stream>>>(dense.p, n, nrows, coo_block_off.p, coo_host, coo_host + coo_cap, coo_host + 2 * coo_cap, coo_cap);
+    HLAC_CUDA(cudaGetLastError());
+    end(e);
+    launches += nb ? 3 : 1;
+  }
+  // sum the dense matrices (disjoint columns per rank) and the counters over the communicator
+  // (the counters go to a separate buffer: the local ones stay valid for a redo through the sort path)
+  void enqueue_merge() {
+    const unsigned long long hc[3] = {host_reads, host_non_primary, host_not_cell};
+    HLAC_CUDA(cudaMemcpyAsync(counters.p + 13, hc, sizeof hc, cudaMemcpyHostToDevice, stream));
+    if (!comm) return;
+    counters_merged.reserve(N_COUNTERS, stream);
+    comm_group_begin(comm);
+    if (comm_root < 0) comm_allreduce_sum(comm, dense.p, dense.p, nd(), HLAC_COMM_U32, stream);
+    else comm_reduce_sum(comm, dense.p, dense.p, nd(), HLAC_COMM_U32, comm_root, stream);
+    comm_allreduce_sum(comm, counters.p, counters_merged.p, N_COUNTERS, HLAC_COMM_U64, stream);
+    comm_group_end(comm);
   }
 };
 
@@ -695,6 +784,7 @@ int hlac_count_new(hlac_index* cds, hlac_index* genomic, uint32_t n_cells, int p
   if (n_cells == 0 || n_cells >= (1u << 27)) throw Error(HLAC_ERR_LIMIT, "n_cells must be in 1..2^27-1");
   auto s = std::make_unique<hlac_count>();
   s->cds = cds; s->gen = genomic; s->device = cds->device; s->n_cells = n_cells; s->primary_only = primary_only;
+  s->stride = seed_stride();
   while ((1ull << s->cell_bits) < n_cells) s->cell_bits++;
   DeviceGuard g(s->device);
   s->rows = build_row_layout(cds->host.tx_names);
@@ -713,9 +803,9 @@ int hlac_count_new(hlac_index* cds, hlac_index* genomic, uint32_t n_cells, int p
   node_table(cds->host, s->nodes_cds); node_table(genomic->host, s->nodes_gen);
   std::vector<uint32_t> r0 = s->rows.gene_row0; r0.resize(8, 0);
   s->gene_row0.upload(r0.data(), r0.size(), s->stream);
-  s->counters.reserve(16, s->stream);
-  HLAC_CUDA(cudaMemsetAsync(s->counters.p, 0, 16 * sizeof(unsigned long long), s->stream));
-  s->dense.reserve((size_t)n_cells * std::max<uint32_t>(s->rows.nrows, 1), s->stream);
+  s->counters.reserve(N_COUNTERS, s->stream);
+  HLAC_CUDA(cudaMemsetAsync(s->counters.p, 0, N_COUNTERS * sizeof(unsigned long long), s->stream));
+  s->dense.reserve(s->nd(), s->stream);
   cudaDeviceProp prop; HLAC_CUDA(cudaGetDeviceProperties(&prop, s->device));
   s->n_sm = prop.multiProcessorCount;
   s->bitmap_smem_bytes = ((size_t)cds->view.bitmap_words + genomic->view.bitmap_words) * 4;
@@ -735,14 +825,23 @@ const char* hlac_count_row_name(const hlac_count* s, uint32_t i) { return (s && 
 int hlac_count_reserve(hlac_count* s, uint64_t total_reads) try {
   if (!s) throw Error(HLAC_ERR_ARG, "null session");
   DeviceGuard g(s->device);
-  s->keys.reserve(total_reads, s->stream, true, s->reads_pushed);
-  s->keys_sorted.reserve(total_reads, s->stream);
+  s->ensure_capacity(total_reads);
+  return HLAC_OK;
+} catch (const Error& e) { set_last_error(e.what()); return e.code; } catch (const std::exception& e) { set_last_error(e.what()); return HLAC_ERR_STATE; }
+
+int hlac_count_attach_comm(hlac_count* s, hlac_comm* comm, int root) try {
+  if (!s) throw Error(HLAC_ERR_ARG, "null session");
+  if (comm) {
+    if (comm_device(comm) != s->device) throw Error(HLAC_ERR_ARG, "communicator and session live on different devices");
+    if (root >= comm_nranks(comm)) throw Error(HLAC_ERR_ARG, "root is not a rank of the communicator");
+  }
+  s->comm = comm; s->comm_root = comm ? root : -1;
   return HLAC_OK;
 } catch (const Error& e) { set_last_error(e.what()); return e.code; } catch (const std::exception& e) { set_last_error(e.what()); return HLAC_ERR_STATE; }
 
 static void validate_batch(const hlac_batch* b) {
   if (b->n && (!b->seq || !b->len || !b->cell || !b->umi || !b->flags)) throw Error(HLAC_ERR_ARG, "batch has a null array");
-  if (b->n >= (1ull << 40)) throw Error(HLAC_ERR_LIMIT, "batch too large");
+  if (b->n >= (1ull << 32)) throw Error(HLAC_ERR_LIMIT, "batch too large");
 }
 
 int hlac_count_push_device(hlac_count* s, const hlac_batch* b) try {
@@ -753,15 +852,21 @@ int hlac_count_push_device(hlac_count* s, const hlac_batch* b) try {
   return HLAC_OK;
 } catch (const Error& e) { set_last_error(e.what()); return e.code; } catch (const std::exception& e) { set_last_error(e.what()); return HLAC_ERR_STATE; }
 
+// staging set for the next host batch: waits (on the copy stream) for the kernel that read this set two pushes ago
+static hlac_count::Stage& next_stage(hlac_count* s) {
+  auto& st = s->stage[s->n_push++ & 1];
+  if (!s->copy_stream) HLAC_CUDA(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+  if (!st.copied) { HLAC_CUDA(cudaEventCreateWithFlags(&st.copied, cudaEventDisableTiming)); HLAC_CUDA(cudaEventCreateWithFlags(&st.consumed, cudaEventDisableTiming)); }
+  else HLAC_CUDA(cudaStreamWaitEvent(s->copy_stream, st.consumed, 0));
+  return st;
+}
+
 int hlac_count_push(hlac_count* s, const hlac_batch* b) try {
   if (!s || !b) throw Error(HLAC_ERR_ARG, "null argument");
   validate_batch(b);
   if (b->n == 0) return HLAC_OK;
   DeviceGuard g(s->device);
-  auto& st = s->stage[s->n_push++ & 1];
-  if (!s->copy_stream) HLAC_CUDA(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
-  if (!st.copied) { HLAC_CUDA(cudaEventCreateWithFlags(&st.copied, cudaEventDisableTiming)); HLAC_CUDA(cudaEventCreateWithFlags(&st.consumed, cudaEventDisableTiming)); }
-  else HLAC_CUDA(cudaStreamWaitEvent(s->copy_stream, st.consumed, 0));   // the kernel that read this set two pushes ago
+  auto& st = next_stage(s);
   auto& e = s->begin(3, s->copy_stream);
   st.seq.upload(b->seq, b->n * b->words_per_read, s->copy_stream);
   st.len.upload(b->len, b->n, s->copy_stream);
@@ -799,10 +904,7 @@ int hlac_count_push_packed(hlac_count* s, const hlac_packed_batch* b) try {
   validate_packed(s, b);
   if (b->n == 0) return HLAC_OK;
   DeviceGuard g(s->device);
-  auto& st = s->stage[s->n_push++ & 1];
-  if (!s->copy_stream) HLAC_CUDA(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
-  if (!st.copied) { HLAC_CUDA(cudaEventCreateWithFlags(&st.copied, cudaEventDisableTiming)); HLAC_CUDA(cudaEventCreateWithFlags(&st.consumed, cudaEventDisableTiming)); }
-  else HLAC_CUDA(cudaStreamWaitEvent(s->copy_stream, st.consumed, 0));   // the kernel that read this set two pushes ago
+  auto& st = next_stage(s);
   auto& e = s->begin(3, s->copy_stream);
   st.rec.upload(b->rec, b->n * (b->words_per_read + 1), s->copy_stream);   // ONE copy per push
   s->end(e, s->copy_stream);
@@ -865,86 +967,50 @@ int hlac_count_last_codes(hlac_count* s, uint8_t* codes, uint64_t n) try {
   return HLAC_OK;
 } catch (const Error& e) { set_last_error(e.what()); return e.code; } catch (const std::exception& e) { set_last_error(e.what()); return HLAC_ERR_STATE; }
 
+// count() of this session's reads into its dense matrix. Returns with the matrix complete on the session stream (one
+// synchronisation, to learn whether a bucket overflowed), so that a caller that shards reads by barcode itself can run its
+// own all-reduce on it before hlac_count_entries. hlac_count_finish is the fused form (and merges by itself when a
+// communicator is attached).
 int hlac_count_reduce(hlac_count* s, uint32_t** dense_device, uint64_t* n_elems) try {
   if (!s) throw Error(HLAC_ERR_ARG, "null session");
   DeviceGuard g(s->device);
-  const size_t nd = (size_t)s->n_cells * std::max<uint32_t>(s->rows.nrows, 1);
-  unsigned long long nk = 0, umi_max = 0;
-  HLAC_CUDA(cudaMemcpyAsync(&nk, s->counters.p, sizeof nk, cudaMemcpyDeviceToHost, s->stream));
-  HLAC_CUDA(cudaMemcpyAsync(&umi_max, s->counters.p + 10, sizeof umi_max, cudaMemcpyDeviceToHost, s->stream));
-  HLAC_CUDA(cudaMemsetAsync(s->dense.p, 0, nd * sizeof(uint32_t), s->stream));
+  HLAC_CUDA(cudaMemsetAsync(s->counters.p, 0, 8, s->stream));
+  s->enqueue_group();
+  unsigned long long ovf = 0;
+  HLAC_CUDA(cudaMemcpyAsync(&ovf, s->counters.p + 11, 8, cudaMemcpyDeviceToHost, s->stream));
   HLAC_CUDA(cudaStreamSynchronize(s->stream));
-  s->n_keys = nk;
-  if (nk > 0) {
-    s->keys_sorted.reserve(nk, s->stream);
-    // keys are umi << (5 + cell_bits) | cell << 5 | code: only the UMI bits actually seen need sorting (10-bp UMIs: 21)
-    int umi_bits = 1;
-    while (umi_bits < UMI_BITS && (umi_max >> umi_bits)) umi_bits++;
-    const int end_bit = CODE_BITS + (int)s->cell_bits + umi_bits;
-    size_t tmp = 0;
-    HLAC_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tmp, s->keys.p, s->keys_sorted.p, (uint64_t)nk, CODE_BITS, end_bit, s->stream));
-    s->cub_tmp.reserve(tmp, s->stream);
-    auto& e1 = s->begin(1);
-    HLAC_CUDA(cub::DeviceRadixSort::SortKeys(s->cub_tmp.p, tmp, s->keys.p, s->keys_sorted.p, (uint64_t)nk, CODE_BITS, end_bit, s->stream));
-    s->end(e1);
-    auto& e2 = s->begin(2);
-    k_consensus<<<(unsigned)((nk + 255) / 256), 256, 0, s->stream>>>(s->keys_sorted.p, nk, s->dense.p, s->rows.nrows, s->gene_row0.p, s->cell_bits);
-    HLAC_CUDA(cudaGetLastError());
-    s->end(e2);
-    s->launches += 1;   // k_consensus; the cub sort passes are library kernels and not counted
-  }
+  if (ovf) s->fallback_group();
   s->reduced = true;
   if (dense_device) *dense_device = s->dense.p;
-  if (n_elems) *n_elems = nd;
-  HLAC_CUDA(cudaStreamSynchronize(s->stream));
+  if (n_elems) *n_elems = s->nd();
   return HLAC_OK;
 } catch (const Error& e) { set_last_error(e.what()); return e.code; } catch (const std::exception& e) { set_last_error(e.what()); return HLAC_ERR_STATE; }
+
+// results out of the host-mapped header + COO buffers (after the stream has been synchronised)
+static void publish(hlac_count* s, hlac_coo* out, hlac_metrics* metrics, bool with_entries) {
+  const unsigned long long* ctr = s->host_hdr + 1;
+  const uint64_t nnz = with_entries ? s->host_hdr[0] : 0;
+  if (ctr[9]) throw Error(HLAC_ERR_ARG, std::to_string(ctr[9]) + " reads carried a cell index >= n_cells (the reference panics in TriMat::add_triplet, main.rs:279)");
+  if (nnz > s->coo_cap) throw Error(HLAC_ERR_STATE, "COO buffer overran (internal error)");
+  if (metrics) {
+    metrics->num_reads = ctr[1] + ctr[13]; metrics->num_non_primary = ctr[2] + ctr[14]; metrics->num_not_cell_bc = ctr[3] + ctr[15];
+    metrics->num_cds_align = ctr[4]; metrics->num_gen_align = ctr[5]; metrics->num_not_aligned = ctr[6];
+  }
+  if (out) {
+    // the arrays live in the session's pinned buffer: valid until the next hlac_count_entries / _finish / _free on this
+    // session; hlac_coo_free does not free borrowed arrays
+    out->n = nnz; out->nrows = s->rows.nrows; out->borrowed = 1;
+    out->row = nnz ? s->coo_host : nullptr; out->col = nnz ? s->coo_host + s->coo_cap : nullptr; out->val = nnz ? s->coo_host + 2 * s->coo_cap : nullptr;
+  }
+}
 
 int hlac_count_entries(hlac_count* s, hlac_coo* out, hlac_metrics* metrics) try {
   if (!s) throw Error(HLAC_ERR_ARG, "null session");
   if (!s->reduced) throw Error(HLAC_ERR_STATE, "hlac_count_reduce has not run since the last push");
   DeviceGuard g(s->device);
-  const uint32_t nrows = s->rows.nrows;
-  const uint64_t nd = (uint64_t)s->n_cells * std::max<uint32_t>(nrows, 1);
-  unsigned long long ctr[10];
-  HLAC_CUDA(cudaMemcpyAsync(ctr, s->counters.p, sizeof ctr, cudaMemcpyDeviceToHost, s->stream));
-  uint64_t nnz = 0;
-  if (out && nrows) {
-    // dense -> COO on the device: per-block non-zero counts, one-block scan, ordered write; only the non-zeros cross PCIe
-    const uint32_t nb = (uint32_t)((nd + COO_TILE - 1) / COO_TILE);
-    s->coo_block_nnz.reserve(nb, s->stream); s->coo_block_off.reserve(nb + 1, s->stream);
-    k_coo_count<<<nb, COO_THREADS, 0, s->stream>>>(s->dense.p, nd, s->coo_block_nnz.p);
-    k_coo_scan<<<1, 1024, 0, s->stream>>>(s->coo_block_nnz.p, nb, s->coo_block_off.p);
-    HLAC_CUDA(cudaGetLastError());
-    HLAC_CUDA(cudaMemcpyAsync(&nnz, s->coo_block_off.p + nb, 8, cudaMemcpyDeviceToHost, s->stream));
-    HLAC_CUDA(cudaStreamSynchronize(s->stream));
-    if (nnz) {
-      s->coo_dev.reserve(3 * nnz, s->stream);
-      if (s->coo_host_cap < 3 * nnz) {
-        if (s->coo_host) cudaFreeHost(s->coo_host);
-        s->coo_host = nullptr; s->coo_host_cap = 0;
-        const size_t cap = 3 * nnz + 3 * nnz / 4 + 1024;
-        HLAC_CUDA(cudaHostAlloc((void**)&s->coo_host, cap * 4, cudaHostAllocDefault));
-        s->coo_host_cap = cap;
-      }
-      k_coo_write<<<nb, COO_THREADS, 0, s->stream>>>(s->dense.p, nd, nrows, s->coo_block_off.p, s->coo_dev.p, s->coo_dev.p + nnz, s->coo_dev.p + 2 * nnz);
-      HLAC_CUDA(cudaGetLastError());
-      HLAC_CUDA(cudaMemcpyAsync(s->coo_host, s->coo_dev.p, 3 * nnz * 4, cudaMemcpyDeviceToHost, s->stream));
-    }
-    s->launches += 3;
-  }
+  { hlac_comm* keep = s->comm; s->comm = nullptr; s->enqueue_merge(); s->enqueue_coo(); s->comm = keep; }   // the caller merged (or not) itself
   HLAC_CUDA(cudaStreamSynchronize(s->stream));
-  if (ctr[9]) throw Error(HLAC_ERR_ARG, std::to_string(ctr[9]) + " reads carried a cell index >= n_cells (the reference panics in TriMat::add_triplet, main.rs:279)");
-  if (metrics) {
-    metrics->num_reads = ctr[1] + s->host_reads; metrics->num_non_primary = ctr[2] + s->host_non_primary; metrics->num_not_cell_bc = ctr[3] + s->host_not_cell;
-    metrics->num_cds_align = ctr[4]; metrics->num_gen_align = ctr[5]; metrics->num_not_aligned = ctr[6];
-  }
-  if (out) {
-    // the arrays live in the session's pinned buffer: valid until the next hlac_count_entries / _reset / _free on this
-    // session; hlac_coo_free does not free borrowed arrays
-    out->n = nnz; out->nrows = nrows; out->borrowed = 1;
-    out->row = s->coo_host; out->col = s->coo_host ? s->coo_host + nnz : nullptr; out->val = s->coo_host ? s->coo_host + 2 * nnz : nullptr;
-  }
+  publish(s, out, metrics, true);
   return HLAC_OK;
 } catch (const Error& e) { set_last_error(e.what()); return e.code; } catch (const std::exception& e) { set_last_error(e.what()); return HLAC_ERR_STATE; }
 
@@ -956,11 +1022,33 @@ int hlac_count_add_filtered(hlac_count* s, uint64_t n_reads, uint64_t n_non_prim
   return HLAC_OK;
 }
 
-int hlac_count_finish(hlac_count* s, hlac_coo* out, hlac_metrics* metrics) {
-  int rc = hlac_count_reduce(s, nullptr, nullptr);
-  if (rc != HLAC_OK) return rc;
-  return hlac_count_entries(s, out, metrics);
-}
+// group + consensus -> (merge over the communicator) -> COO + counters into host-mapped memory: everything is enqueued
+// back to back and the host synchronises once. Only if some bucket overflowed (reported in the same header) is the step
+// redone through the sort path.
+int hlac_count_finish(hlac_count* s, hlac_coo* out, hlac_metrics* metrics) try {
+  if (!s) throw Error(HLAC_ERR_ARG, "null session");
+  DeviceGuard g(s->device);
+  const bool extract = !s->comm || s->comm_root < 0 || comm_rank(s->comm) == s->comm_root;
+  HLAC_CUDA(cudaMemsetAsync(s->counters.p, 0, 8, s->stream));
+  s->enqueue_group();
+  for (int attempt = 0;; attempt++) {
+    s->enqueue_merge();
+    s->enqueue_coo();
+    HLAC_CUDA(cudaStreamSynchronize(s->stream));
+    if (s->host_hdr[1 + 11] == 0 || attempt == 1) break;   // [11]: overflowed keys, summed over the ranks when merged
+    // some rank overflowed a bucket: every rank recomputes its own matrix (the in-place all-reduce consumed it), the
+    // overflowing ranks through the sort path
+    unsigned long long ovf = 0;
+    HLAC_CUDA(cudaMemcpyAsync(&ovf, s->counters.p + 11, 8, cudaMemcpyDeviceToHost, s->stream));
+    HLAC_CUDA(cudaStreamSynchronize(s->stream));
+    if (ovf) s->fallback_group();
+    else { HLAC_CUDA(cudaMemsetAsync(s->counters.p, 0, 8, s->stream)); s->enqueue_group(); }
+  }
+  s->reduced = true;
+  publish(s, extract ? out : nullptr, metrics, extract);
+  if (!extract && out) { out->n = 0; out->nrows = s->rows.nrows; out->borrowed = 1; out->row = out->col = out->val = nullptr; }
+  return HLAC_OK;
+} catch (const Error& e) { set_last_error(e.what()); return e.code; } catch (const std::exception& e) { set_last_error(e.what()); return HLAC_ERR_STATE; }
 
 int hlac_count_reset(hlac_count* s) try {
   if (!s) throw Error(HLAC_ERR_ARG, "null session");
@@ -992,6 +1080,19 @@ int hlac_count_probe_stats(hlac_count* s, uint64_t* bitmap_tests, uint64_t* dict
   HLAC_CUDA(cudaStreamSynchronize(s->stream));
   if (bitmap_tests) *bitmap_tests = c[0];
   if (dict_probes) *dict_probes = c[1];
+  return HLAC_OK;
+} catch (const Error& e) { set_last_error(e.what()); return e.code; } catch (const std::exception& e) { set_last_error(e.what()); return HLAC_ERR_STATE; }
+
+// grouped keys (= scored reads) of the last finish / reduce, buckets in use, and how many finishes took the sort path
+int hlac_count_group_stats(hlac_count* s, uint64_t* n_keys, uint32_t* n_buckets, uint64_t* fallbacks) try {
+  if (!s) throw Error(HLAC_ERR_ARG, "null session");
+  DeviceGuard g(s->device);
+  unsigned long long c = 0;
+  HLAC_CUDA(cudaMemcpyAsync(&c, s->counters.p, sizeof c, cudaMemcpyDeviceToHost, s->stream));
+  HLAC_CUDA(cudaStreamSynchronize(s->stream));
+  if (n_keys) *n_keys = c;
+  if (n_buckets) *n_buckets = s->n_buckets;
+  if (fallbacks) *fallbacks = s->fallbacks;
   return HLAC_OK;
 } catch (const Error& e) { set_last_error(e.what()); return e.code; } catch (const std::exception& e) { set_last_error(e.what()); return HLAC_ERR_STATE; }
 

@@ -13,6 +13,9 @@ void hlac_index::upload(int dev) {
   device = dev;
   DeviceGuard g(dev);
   const uint32_t nn = host.n_nodes();
+  // the kernels carry (offset in node, read position, orientation) of a seed in one word: 20 bits of offset
+  for (uint32_t i = 0; i < nn; i++)
+    if (host.len[i] >= (1u << 20) + K) throw Error(HLAC_ERR_LIMIT, "a graph node is longer than 2^20 bases (unbranched sequence of " + std::to_string(host.len[i]) + " bases): the seed record holds a 20-bit node offset");
   std::vector<uint32_t> rec((size_t)nn * 12);
   for (uint32_t i = 0; i < nn; i++) {
     uint32_t* r = &rec[(size_t)i * 12];

@@ -19,7 +19,10 @@
 
 namespace hlac {
 
-static_assert(SEED_STRIDE == 1, "the skip-scan seed filter assumes every read position is a seed candidate");
+// Seed-scan stride (template parameter S of find_seed / walk_from_seed / map_read_walk): the pinned debruijn_mapping
+// rev is not vendored and the reference's goldens reproduce for strides 1..3 (SURVEY.md finding #4), so the stride is a
+// property of the session (hlac_set_seed_stride, default DEFAULT_SEED_STRIDE) and the kernels are instantiated per
+// stride. Candidate positions of one scan are start, start+S, start+2S, ...
 
 struct DevIndexView {
   const uint32_t* seq32;     // node sequences, 16 bases per word
@@ -74,7 +77,9 @@ __device__ __forceinline__ bool dict_get(const DevIndexView& ix, uint64_t kmer, 
 // (A variant that tested four jump targets speculatively per round was measured slower on B200: 15.6 instead of 9.6
 // bitmap tests per read and more registers; so was a warp-synchronous loop whose condition is a vote — every iteration
 // then waits for the few lanes that probe the dictionary; see profiles/r01_count_map_tuning.md.)
-template <typename RD, typename BM>
+// With a stride S > 1 only every S-th position (counted from the scan start) is a candidate, so a jump lands on the next
+// candidate at or beyond the first position the absent l-mer does not rule out.
+template <int S, typename RD, typename BM>
 __device__ __forceinline__ bool find_seed(const DevIndexView& ix, RD rd, BM bm, int& pos, int last, uint32_t& node,
                                           uint32_t& off, uint32_t& n_tests, uint32_t& n_probes) {
   const int l = (int)ix.lmer;
@@ -85,11 +90,11 @@ __device__ __forceinline__ bool find_seed(const DevIndexView& ix, RD rd, BM bm, 
   while (pos <= last) {
     const uint32_t v = ext16(rd, pos + o) >> sh;
     n_tests++;
-    if (!((bm(v >> 5) >> (v & 31)) & 1u)) { pos += o + 1; o = o0; continue; }   // no k-mer can cover this l-mer
+    if (!((bm(v >> 5) >> (v & 31)) & 1u)) { pos += S == 1 ? o + 1 : ((o + S) / S) * S; o = o0; continue; }   // no k-mer can cover this l-mer
     if (o != 0) { o = o > l ? o - l : 0; continue; }
     n_probes++;
     if (dict_get(ix, kmer48(rd, pos), node, off)) return true;
-    pos += 1;
+    pos += S;
     o = o0;
   }
   return false;
@@ -135,7 +140,7 @@ __device__ __forceinline__ int left_extend(const DevIndexView& ix, RD rd, int L,
 // map_read_to_nodes after the first seed: optional left extension, then the forward walk.
 // (pos, node, off) is the first verified seed. V::visit(colour, node) is called for every visited node in the
 // reference's push order (left-extension nodes first, then the forward walk); the last call is the class-defining node.
-template <typename RD, typename BM, typename V>
+template <int S, typename RD, typename BM, typename V>
 __device__ __forceinline__ uint32_t walk_from_seed(const DevIndexView& ix, RD rd, BM bm, int L, int pos, uint32_t node, uint32_t off,
                                                    V& vis, uint32_t& n_tests, uint32_t& n_probes) {
   const int last = L - K;
@@ -187,7 +192,7 @@ __device__ __forceinline__ uint32_t walk_from_seed(const DevIndexView& ix, RD rd
       g = n0.x + K; rem = (int)n0.y - K;
     } else {                             // re-seed scanning forward from the current position
       if (pos > last) break;
-      if (!find_seed(ix, rd, bm, pos, last, node, off, n_tests, n_probes)) break;
+      if (!find_seed<S>(ix, rd, bm, pos, last, node, off, n_tests, n_probes)) break;
       n0 = __ldg(ix.nodes + 3 * (size_t)node);
       ra = __ldg(ix.nodes + 3 * (size_t)node + 1);
       pos += K; cov += K;
@@ -200,13 +205,13 @@ __device__ __forceinline__ uint32_t walk_from_seed(const DevIndexView& ix, RD rd
 }
 
 // map_read_to_nodes, whole: None iff the first seed scan finds nothing (or L < K).
-template <typename RD, typename BM, typename V>
+template <int S, typename RD, typename BM, typename V>
 __device__ __forceinline__ bool map_read_walk(const DevIndexView& ix, RD rd, BM bm, int L, V& vis, uint32_t& cov_out,
                                               uint32_t& n_tests, uint32_t& n_probes) {
   int pos = 0;
   uint32_t node = 0, off = 0;
-  if (L < K || !find_seed(ix, rd, bm, pos, L - K, node, off, n_tests, n_probes)) return false;
-  cov_out = walk_from_seed(ix, rd, bm, L, pos, node, off, vis, n_tests, n_probes);
+  if (L < K || !find_seed<S>(ix, rd, bm, pos, L - K, node, off, n_tests, n_probes)) return false;
+  cov_out = walk_from_seed<S>(ix, rd, bm, L, pos, node, off, vis, n_tests, n_probes);
   return true;
 }
 

@@ -99,6 +99,7 @@ __device__ __forceinline__ void load_read_row(const uint64_t* seq, uint64_t i, u
 // -> (survivors) reverse-complement seed scan -> dense walk queue. mapping.rs:341-363: forward, else reverse
 // complement; the unmapped pass (forward_only) never tries the reverse complement (mapping.rs:383).
 constexpr int GENO_R = 2;
+template <int STRIDE>
 __global__ void __launch_bounds__(GENO_THREADS) k_geno_map(const GenoMapArgs a) {
   extern __shared__ __align__(16) uint32_t smem[];
   constexpr int TILE = 32 * GENO_R;
@@ -148,7 +149,7 @@ __global__ void __launch_bounds__(GENO_THREADS) k_geno_map(const GenoMapArgs a) 
           const int L = lens[slot];
           if (p == 1) make_revcomp(SharedWords{fw}, rc, L, (int)a.nw);
           int pos = 0; uint32_t node = 0, off = 0;
-          if (L >= K) found = find_seed(a.ix, SharedWords{p ? rc : fw}, bm, pos, L - K, node, off, n_tests, n_probes);
+          if (L >= K) found = find_seed<STRIDE>(a.ix, SharedWords{p ? rc : fw}, bm, pos, L - K, node, off, n_tests, n_probes);
           if (found) { seed_node[slot] = node; seed_info[slot] = (off << 12) | ((uint32_t)pos << 2) | (uint32_t)p; }
         }
         __syncwarp();
@@ -169,7 +170,7 @@ __global__ void __launch_bounds__(GENO_THREADS) k_geno_map(const GenoMapArgs a) 
         const int p = (int)(info & 3u), pos = (int)((info >> 2) & 1023u);
         uint32_t* fw = rows + slot * a.row_stride;
         HashVis vis;
-        const uint32_t cov = walk_from_seed(a.ix, SharedWords{p ? fw + a.nw : fw}, bm, (int)lens[slot], pos, seed_node[slot], info >> 12, vis, n_tests, n_probes);
+        const uint32_t cov = walk_from_seed<STRIDE>(a.ix, SharedWords{p ? fw + a.nw : fw}, bm, (int)lens[slot], pos, seed_node[slot], info >> 12, vis, n_tests, n_probes);
         vis.finish();
         a.cov[i] = cov; a.hash_a[i] = vis.a; a.hash_b[i] = vis.b; a.strand[i] = (uint8_t)p;
         some++;
@@ -234,6 +235,7 @@ struct GenoPathArgs {
   uint32_t* arena; unsigned long long* arena_cursor;
 };
 
+template <int STRIDE>
 __global__ void __launch_bounds__(GENO_THREADS) k_geno_paths(const GenoPathArgs a) {
   extern __shared__ __align__(16) uint32_t smem[];
   uint32_t* fw = smem + threadIdx.x * a.row_stride;
@@ -249,10 +251,10 @@ __global__ void __launch_bounds__(GENO_THREADS) k_geno_paths(const GenoPathArgs 
   SharedWords rd{rev ? rc : fw};
   uint32_t cov, t0 = 0, t1 = 0;
   CountVis2 cv;
-  map_read_walk(a.ix, rd, BitmapGlobal{a.ix.bitmap}, L, cv, cov, t0, t1);
+  map_read_walk<STRIDE>(a.ix, rd, BitmapGlobal{a.ix.bitmap}, L, cv, cov, t0, t1);
   const unsigned long long off = atomicAdd(a.arena_cursor, (unsigned long long)cv.n);
   WriteVis wv{a.arena + off};
-  map_read_walk(a.ix, rd, BitmapGlobal{a.ix.bitmap}, L, wv, cov, t0, t1);
+  map_read_walk<STRIDE>(a.ix, rd, BitmapGlobal{a.ix.bitmap}, L, wv, cov, t0, t1);
   a.e.path_off[id] = off; a.e.path_len[id] = cv.n;
 }
 
@@ -584,6 +586,7 @@ struct hlac_geno {
   int device = 0;
   cudaStream_t stream = nullptr;
   int n_sm = 1;
+  int stride = 1;   // seed-scan stride (hlac_set_seed_stride) the session was created with
   // staging + per-batch temporaries
   DevBuf<uint64_t> st_seq, hash_a, hash_b;
   DevBuf<uint16_t> st_len;
@@ -606,8 +609,9 @@ struct hlac_geno {
   // between hlac_geno_finish_begin and _end
   std::vector<uint64_t> fin_src_off; std::vector<uint32_t> fin_cls_len, fin_cls_reads, fin_cls_colour;   // per class, first-seen order
   DevBuf<uint32_t> fin_hist, fin_dvec; bool fin_begun = false;
-  float ms[4] = {0, 0, 0, 0};
+  float ms[5] = {0, 0, 0, 0, 0};   // map, intern, finish (all of it), H2D, path resolution alone
   uint64_t launches = 0;
+  uint64_t res_bytes = 0, res_merges = 0, res_steps = 0, res_paths = 0;   // work of the last path resolution (hlac_geno_resolve_stats)
   struct Ev { cudaEvent_t a, b; int kind; };
   std::vector<Ev> events;
 
@@ -677,14 +681,16 @@ struct hlac_geno {
     const size_t per_warp_words = (size_t)32 * GENO_R * a.row_stride + 32 * GENO_R * 2 + 32 * GENO_R / 2 + 3 * 32 * GENO_R / 4;
     const size_t smem = (GENO_THREADS / 32) * per_warp_words * 4;
     if (smem > 227 * 1024) throw Error(HLAC_ERR_LIMIT, "reads too long for the shared-memory tile of the genotyping kernel");
-    HLAC_CUDA(cudaFuncSetAttribute(k_geno_map, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    HLAC_CUDA(cudaFuncSetAttribute(k_geno_paths, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_paths));
+    auto* const kmap = stride == 3 ? k_geno_map<3> : k_geno_map<1>;
+    auto* const kpaths = stride == 3 ? k_geno_paths<3> : k_geno_paths<1>;
+    HLAC_CUDA(cudaFuncSetAttribute(kmap, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    HLAC_CUDA(cudaFuncSetAttribute(kpaths, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_paths));
     int occ = 1;
-    HLAC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_geno_map, GENO_THREADS, smem));
+    HLAC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kmap, GENO_THREADS, smem));
     const uint64_t per_block = (uint64_t)GENO_THREADS * GENO_R;
     const unsigned grid = (unsigned)std::min<uint64_t>((n + per_block - 1) / per_block, (uint64_t)n_sm * std::max(occ, 1));
     size_t e0 = begin(0);
-    k_geno_map<<<grid, GENO_THREADS, smem, stream>>>(a);
+    kmap<<<grid, GENO_THREADS, smem, stream>>>(a);
     HLAC_CUDA(cudaGetLastError());
     end(e0);
     size_t e1 = begin(1);
@@ -701,7 +707,7 @@ struct hlac_geno {
       GenoPathArgs p{};
       p.ix = idx->view; p.seq = b.seq; p.len = b.len; p.strand = strand.p; p.wpr = a.wpr; p.nw = a.nw; p.row_stride = a.row_stride;
       p.e = entries(); p.first_new = (uint32_t)n_entries; p.n_new = n_new; p.arena = arena.p; p.arena_cursor = ctr.p + 1;
-      k_geno_paths<<<(n_new + GENO_THREADS - 1) / GENO_THREADS, GENO_THREADS, smem_paths, stream>>>(p);
+      kpaths<<<(n_new + GENO_THREADS - 1) / GENO_THREADS, GENO_THREADS, smem_paths, stream>>>(p);
       HLAC_CUDA(cudaGetLastError());
       launches++;
     }
@@ -725,7 +731,7 @@ int hlac_geno_new(hlac_index* idx, hlac_geno** out) try {
   if (!idx || !out) throw Error(HLAC_ERR_ARG, "null argument");
   if (idx->device < 0) throw Error(HLAC_ERR_CUDA, "index is host-only (device -1): genotyping needs a CUDA device, there is no CPU fallback");
   auto s = std::make_unique<hlac_geno>();
-  s->idx = idx; s->device = idx->device;
+  s->idx = idx; s->device = idx->device; s->stride = seed_stride();
   DeviceGuard g(s->device);
   HLAC_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
   s->ctr.reserve(16, s->stream);
@@ -811,9 +817,21 @@ int hlac_geno_finish_begin(hlac_geno* s, uint32_t** umi_hist_device, uint64_t* n
     HLAC_CUDA(cudaStreamSynchronize(s->stream));
     std::vector<uint64_t> voff(E + 1, 0);
     for (uint32_t i = 0; i < E; i++) voff[i + 1] = voff[i] + hlen[i];
+    {   // work of this resolution, for the roofline record: merges, vector elements walked, compulsory bytes
+      std::vector<uint32_t> hpl(E);
+      HLAC_CUDA(cudaMemcpyAsync(hpl.data(), s->e_path_len.p, (size_t)E * 4, cudaMemcpyDeviceToHost, s->stream));
+      HLAC_CUDA(cudaStreamSynchronize(s->stream));
+      const uint64_t bw = ((uint64_t)hx.tx_names.size() + 31) / 32 * 4;
+      s->res_bytes = s->res_merges = s->res_steps = 0; s->res_paths = E;
+      for (uint32_t i = 0; i < E; i++) {
+        const uint64_t m = hpl[i] ? hpl[i] - 1 : 0;
+        s->res_merges += m; s->res_steps += m * hlen[i]; s->res_bytes += m * bw + (uint64_t)hpl[i] * 4 + (uint64_t)hlen[i] * 4;
+      }
+    }
     DevBuf<uint64_t> d_voff, d_vhash, d_vhash2;
     d_voff.upload(voff.data(), E + 1, s->stream); d_vhash.reserve(E, s->stream); d_vhash2.reserve(E, s->stream);
     s->fin_dvec.reserve(std::max<uint64_t>(voff[E], 1), s->stream);
+    const size_t ev_res = s->begin(4);
     {
       uint32_t n_max = 1;
       for (uint32_t i = 0; i < E; i++) n_max = std::max(n_max, hlen[i]);
@@ -870,6 +888,7 @@ int hlac_geno_finish_begin(hlac_geno* s, uint32_t** umi_hist_device, uint64_t* n
       }
     }
     HLAC_CUDA(cudaGetLastError());
+    s->end(ev_res);
     s->end(ev);
     s->launches += 2;
     std::vector<uint64_t> vhash(E), vhash2(E), ford(E); std::vector<uint32_t> cnt(E);
@@ -1218,6 +1237,21 @@ int hlac_geno_timing(hlac_geno* s, float ms[4], uint64_t* launches) try {
   s->drain_events();
   if (ms) for (int i = 0; i < 4; i++) ms[i] = s->ms[i];
   if (launches) *launches = s->launches;
+  return HLAC_OK;
+} catch (const Error& e) { set_last_error(e.what()); return e.code; } catch (const std::exception& e) { set_last_error(e.what()); return HLAC_ERR_STATE; }
+
+// the last path resolution (hlac_geno_finish*): kernel time and the work it did — distinct paths, no-truncate merges,
+// vector elements walked (sum over merges of the vector length) and compulsory bytes (per merge one colour membership
+// bitset, per path its colour ids in and its class vector out)
+int hlac_geno_resolve_stats(hlac_geno* s, float* ms, uint64_t* paths, uint64_t* merges, uint64_t* element_steps, uint64_t* bytes) try {
+  if (!s) throw Error(HLAC_ERR_ARG, "null session");
+  DeviceGuard g(s->device);
+  s->drain_events();
+  if (ms) *ms = s->ms[4];
+  if (paths) *paths = s->res_paths;
+  if (merges) *merges = s->res_merges;
+  if (element_steps) *element_steps = s->res_steps;
+  if (bytes) *bytes = s->res_bytes;
   return HLAC_OK;
 } catch (const Error& e) { set_last_error(e.what()); return e.code; } catch (const std::exception& e) { set_last_error(e.what()); return HLAC_ERR_STATE; }
 

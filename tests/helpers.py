@@ -127,3 +127,40 @@ def read_eqclassdb_bincode(path):
     triples = [take("3I") for _ in range(take("Q")[0])]
     assert pos == len(raw), "trailing bytes"
     return maps[0], maps[1], classes, triples
+
+
+# ---- exact comparison of large class tables (CSR) without building Python tuples ---------------------------------------
+def csr_canonical(off, tx, cnt):
+    """(off, tx, cnt) of a {class vector: count} table -> (fingerprint rows sorted, flat tx in that class order): two tables
+    are equal as maps from ORDERED vectors to counts iff both parts are equal."""
+    off = np.asarray(off, dtype=np.int64)
+    tx = np.asarray(tx, dtype=np.uint64)
+    cnt = np.asarray(cnt, dtype=np.uint64)
+    n = len(off) - 1
+    if n == 0:
+        return np.zeros((0, 3), np.uint64), np.zeros(0, np.uint64)
+    lens = np.diff(off)
+    assert (lens > 0).all()
+    pos = (np.arange(len(tx), dtype=np.int64) - np.repeat(off[:-1], lens)).astype(np.uint64)
+    w = (pos * np.uint64(0x9E3779B97F4A7C15) + np.uint64(0xD1B54A32D192ED03)) | np.uint64(1)
+    with np.errstate(over="ignore"):
+        h = np.add.reduceat((tx + np.uint64(1)) * w, off[:-1])
+    order = np.lexsort((cnt, lens, h))
+    rows = np.stack([h[order], lens[order].astype(np.uint64), cnt[order]], 1)
+    lo = lens[order]
+    starts = off[:-1][order]
+    idx = np.repeat(starts - np.concatenate([[0], np.cumsum(lo)[:-1]]), lo) + np.arange(int(lo.sum()), dtype=np.int64)
+    return rows, tx[idx]
+
+
+def csr_tables_equal(a, b):
+    ra, fa = csr_canonical(*a)
+    rb, fb = csr_canonical(*b)
+    return ra.shape == rb.shape and bool((ra == rb).all()) and np.array_equal(fa, fb)
+
+
+def em_loglik(off, tx, cnt, theta):
+    """EqClassCounts::likelihood (src/em.rs:119-137): sum over classes of count * ln(sum of theta over the class)"""
+    off = np.asarray(off, dtype=np.int64)
+    s = np.add.reduceat(np.asarray(theta, dtype=np.float64)[np.asarray(tx, dtype=np.int64)], off[:-1])
+    return float((np.asarray(cnt, dtype=np.float64) * np.log(s)).sum())

@@ -245,3 +245,65 @@ def test_packed_records_equal_soa(sb, orc, abc, fixture_reads):
     big = sb.CountSession(abc["gc"], abc["gg"], (1 << 23))
     with pytest.raises(sb.HlacError, match="23-bit"):
         big.push_packed(rec[:10])
+
+
+def test_bucket_overflow_takes_the_sort_path(sb, orc, abc):
+    """The grouping kernel holds one hash bucket (2048 keys) in shared memory; a molecule deeper than that (here every read
+    of the batch carries the same barcode and UMI) overflows its bucket and the step is redone through the gather + radix
+    sort + run-consensus path. Results must not depend on which path ran; a normal batch must not take the fallback."""
+    from tools import synth
+    cds, gen = synth.fixture_alleles()
+    r = synth.make_reads(60000, [s for _, s in cds], [s for _, s in gen], 4, 123, err=0.01)
+    r["umi"][:] = 0x1ABCDE
+    r["cell"][:] = 2
+    r["cell"][::50] = H.NOT_A_CELL
+    batch = (r["seq"], r["len"], r["cell"], r["umi"], r["flags"])
+    ent, met, codes, s = _run_gpu(sb, abc, batch, 4, splits=3)
+    ref = orc.count_run(abc["oc"], abc["og"], *batch, want_codes=True)
+    assert np.array_equal(codes, ref["codes"]) and met == ref["metrics"] and ent == ref["entries"]
+    st = s.group_stats()
+    assert st["fallbacks"] == 1 and st["keys"] == int((codes != 255).sum()) > 2048
+    # the legacy two-call form (reduce, then entries) takes the same fallback
+    s.reset()
+    s.push(*batch)
+    s.reduce()
+    assert s.entries() == (ref["entries"], ref["metrics"]) and s.group_stats()["fallbacks"] == 2
+    # mixed: one deep molecule among ordinary ones; and an ordinary batch stays on the fused path
+    r2 = synth.make_reads(120000, [s for _, s in cds], [s for _, s in gen], 40, 124)
+    b2 = tuple(np.concatenate([x, y]) for x, y in zip(batch, (r2["seq"], r2["len"], r2["cell"], r2["umi"], r2["flags"])))
+    ent2, met2, codes2, s2 = _run_gpu(sb, abc, b2, 40, splits=2)
+    ref2 = orc.count_run(abc["oc"], abc["og"], *b2, want_codes=True)
+    assert np.array_equal(codes2, ref2["codes"]) and met2 == ref2["metrics"] and ent2 == ref2["entries"] and s2.group_stats()["fallbacks"] == 1
+    b3 = (r2["seq"], r2["len"], r2["cell"], r2["umi"], r2["flags"])
+    ent3, met3, codes3, s3 = _run_gpu(sb, abc, b3, 40, splits=5)
+    ref3 = orc.count_run(abc["oc"], abc["og"], *b3, want_codes=True)
+    assert ent3 == ref3["entries"] and met3 == ref3["metrics"]
+    st3 = s3.group_stats()
+    assert st3["fallbacks"] == 0 and st3["keys"] == int((codes3 != 255).sum()) and st3["buckets"] >= 128
+
+
+def test_seed_stride_3(sb, orc, abc):
+    """The seed-scan stride of map_read is not pinned by the reference's goldens (strides 1..3 reproduce both, SURVEY.md
+    finding #4; the pinned debruijn_mapping revision is not vendored): the library honours 1 (default) and 3
+    (hlac_set_seed_stride). Reads with substitutions separate the two: with stride 3 only every third position after the
+    scan start may seed, so some reads seed later (or not at all) and get a different coverage / class."""
+    from tools import synth
+    cds, gen = synth.fixture_alleles()
+    r = synth.make_reads(80000, [s for _, s in cds], [s for _, s in gen], 60, 31, err=0.03)
+    batch = (r["seq"], r["len"], r["cell"], r["umi"], r["flags"])
+    out = {}
+    try:
+        for stride in (1, 3):
+            sb.set_seed_stride(stride)
+            orc.set_stride(stride)
+            assert sb.get_seed_stride() == stride
+            ent, met, codes, _ = _run_gpu(sb, abc, batch, 60, splits=2)
+            ref = orc.count_run(abc["oc"], abc["og"], *batch, want_codes=True)
+            assert np.array_equal(codes, ref["codes"]) and met == ref["metrics"] and ent == ref["entries"]
+            out[stride] = (codes, met)
+    finally:
+        sb.set_seed_stride(1)
+        orc.set_stride(1)
+    assert not np.array_equal(out[1][0], out[3][0]), "the workload does not separate stride 1 from stride 3"
+    with pytest.raises(sb.HlacError):
+        sb.set_seed_stride(2)
