@@ -144,6 +144,7 @@ int hlac_index_from_fasta(const char* fasta_path, const char* allele_status, int
  * sequence i starts at word seq_word_start[i]); names are NUL-terminated. */
 int hlac_index_from_sequences(const uint64_t* packed, const uint64_t* seq_word_start, const uint32_t* seq_len,
                               const char* const* names, uint32_t n_seq, int device, hlac_index** out);
+int hlac_index_clone(const hlac_index* src, int device, hlac_index** out); /* the same index resident on another device */
 int hlac_index_free(hlac_index*);
 /* utils::write_obj(&index, hla_index) (hla.rs:260): the bincode Pseudoaligner<Kmer24> the reference reads with -i,
  * including its three boomphf tables (host work, no device needed) */
@@ -331,8 +332,9 @@ int hlac_geno_eqclassdb(hlac_geno*, const hlac_class_tables* t, const uint32_t* 
 
 /* ---- the three reference entry points, whole (host driver in C++; BAM/FASTA I/O on the host) ---------------------- */
 /* mapping_wrapper(hla_index, outdir, bam, locus, use_unmapped) -> counts file path (mapping.rs:310-316).
- * region: samtools-style "chr:start-end" or NULL. The counts file is this library's table format (HLACCNT1) unless the
- * environment has HLAC_COUNTS_FORMAT=bincode, which writes the reference's EqClassDb instead; hlac_em_wrapper reads both. */
+ * region: samtools-style "chr:start-end" or NULL. The counts file is the reference's: bincode of EqClassDb
+ * (mapping.rs:84-90,403), readable by the reference's em_wrapper; HLAC_COUNTS_FORMAT=tables writes this library's compact
+ * table format (HLACCNT1) instead. hlac_em_wrapper reads both. */
 int hlac_mapping_wrapper(const char* hla_index, const char* outdir, const char* bam, const char* region,
                          int use_unmapped, int device, char* counts_path_out, size_t cap);
 /* em_wrapper(hla_index, hla_counts, cds_db, gen_db, outdir) -> (genomic, cds) paths (em.rs:339-345,475) */
@@ -343,6 +345,12 @@ int hlac_em_wrapper(const char* hla_index, const char* hla_counts, const char* c
 int hlac_map_and_count_pseudo(const char* bam, const char* out_dir, const char* barcodes_path, const char* region,
                               const char* cds, const char* genomic, int primary_only, int device, hlac_coo* entries,
                               hlac_metrics* metrics, uint32_t* n_cells_out);
+/* the same run spread over several GPUs of one box (sc_hla_count --devices 0,1,..): one counting session per device,
+ * reads routed by barcode column (column % n_devices), the per-device matrices summed onto devices[0] through a
+ * library-owned NCCL communicator inside hlac_count_finish. Results are identical to the single-device call. */
+int hlac_map_and_count_pseudo_multi(const char* bam, const char* out_dir, const char* barcodes_path, const char* region,
+                                    const char* cds, const char* genomic, int primary_only, const int* devices, int n_devices,
+                                    hlac_coo* entries, hlac_metrics* metrics, uint32_t* n_cells_out);
 /* host BAM reader self-check (BamSeqReader, mapping.rs:231-279): count of CB+UB records in the selection and an
  * FNV-1a checksum over (2-bit sequence, CB, UB, primary) in file order; region NULL = the unmapped tail ("*") */
 int hlac_bam_scan(const char* bam, const char* region, uint64_t* n_records, uint64_t* checksum);

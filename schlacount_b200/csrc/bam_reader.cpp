@@ -284,15 +284,23 @@ bool BamReader::parse(const uint8_t* r, size_t bs, RecView& out) const {
       if (ty == 'Z' && t0 == 'C' && t1 == 'B') { out.cb = (const char*)r + p; out.cb_len = (uint32_t)(e - p); has_cb = true; }
       if (ty == 'Z' && t0 == 'U' && t1 == 'B') { out.ub = (const char*)r + p; out.ub_len = (uint32_t)(e - p); has_ub = true; }
       p = e + 1;
-    } else if (ty == 'A' || ty == 'c' || ty == 'C') p += 1;
-    else if (ty == 's' || ty == 'S') p += 2;
-    else if (ty == 'i' || ty == 'I' || ty == 'f') p += 4;
-    else if (ty == 'B') {
-      if (p + 5 > bs) break;
-      const char sub = (char)r[p]; const int32_t cnt = rd<int32_t>(r + p + 1);
-      const int w = (sub == 'c' || sub == 'C') ? 1 : (sub == 's' || sub == 'S') ? 2 : 4;
-      p += 5 + (size_t)cnt * w;
-    } else throw Error(HLAC_ERR_FORMAT, "bad BAM aux type");
+    } else {
+      size_t w;   // fixed-width values (SAM spec 4.2.4; 'd' is htslib's historical double)
+      if (ty == 'A' || ty == 'c' || ty == 'C') w = 1;
+      else if (ty == 's' || ty == 'S') w = 2;
+      else if (ty == 'i' || ty == 'I' || ty == 'f') w = 4;
+      else if (ty == 'd') w = 8;
+      else if (ty == 'B') {
+        if (p + 5 > bs) throw Error(HLAC_ERR_FORMAT, "BAM aux array header overruns the record");
+        const char sub = (char)r[p]; const int32_t cnt = rd<int32_t>(r + p + 1);
+        const size_t ew = (sub == 'c' || sub == 'C') ? 1 : (sub == 's' || sub == 'S') ? 2 : (sub == 'i' || sub == 'I' || sub == 'f') ? 4 : 0;
+        if (ew == 0) throw Error(HLAC_ERR_FORMAT, "bad BAM aux array element type");
+        if (cnt < 0 || (uint64_t)cnt * ew > bs - p - 5) throw Error(HLAC_ERR_FORMAT, "BAM aux array overruns the record");
+        w = 5 + (size_t)cnt * ew;
+      } else throw Error(HLAC_ERR_FORMAT, "bad BAM aux type");
+      if (w > bs - p) throw Error(HLAC_ERR_FORMAT, "BAM aux value overruns the record");
+      p += w;
+    }
   }
   if (!has_cb || !has_ub) return false;   // mapping.rs:254-270
   out.primary = !((flag & 0x100) || (flag & 0x800));

@@ -122,6 +122,18 @@ int hlac_index_from_sequences(const uint64_t* packed, const uint64_t* seq_word_s
   HLAC_API_END
 }
 
+// a second resident copy of an index on another device (multi-GPU runs replicate the index): the host
+// structures are copied, nothing is rebuilt
+int hlac_index_clone(const hlac_index* src, int device, hlac_index** out) {
+  HLAC_API_BEGIN
+  if (!src || !out) throw Error(HLAC_ERR_ARG, "null argument");
+  auto ix = std::make_unique<hlac_index>();
+  ix->host = src->host;
+  ix->upload(device);
+  *out = ix.release();
+  HLAC_API_END
+}
+
 int hlac_index_free(hlac_index* ix) {
   if (ix) { if (ix->device >= 0) cudaSetDevice(ix->device); delete ix; }
   return HLAC_OK;

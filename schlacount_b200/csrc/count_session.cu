@@ -460,9 +460,10 @@ __global__ void k_coo_scan(const uint32_t* __restrict__ block_nnz, uint32_t nblo
 // row / col / val may point into host-mapped pinned memory (zero-copy stores: only the non-zeros cross PCIe, and the host
 // needs no second synchronisation to learn how many there are). cap = capacity of the three arrays (entries beyond it are
 // dropped; the host sees nnz > cap and reports it).
-__global__ void k_coo_write(const uint32_t* __restrict__ dense, uint64_t n, uint32_t nrows, const uint64_t* __restrict__ block_off,
+__global__ void __launch_bounds__(COO_THREADS) k_coo_write(const uint32_t* __restrict__ dense, uint64_t n, uint32_t nrows, const uint64_t* __restrict__ block_off,
                             uint32_t* row, uint32_t* col, uint32_t* val, uint64_t cap) {
   __shared__ uint32_t warp_off[COO_THREADS / 32];
+  __shared__ uint32_t st_row[COO_TILE], st_col[COO_TILE], st_val[COO_TILE];   // the block's triplets, staged so that the copy-out is coalesced
   const uint64_t base = (uint64_t)blockIdx.x * COO_TILE + (uint64_t)threadIdx.x * COO_PER_THREAD;
   uint32_t v[COO_PER_THREAD]; uint32_t c = 0;
 #pragma unroll
@@ -471,14 +472,20 @@ __global__ void k_coo_write(const uint32_t* __restrict__ dense, uint64_t n, uint
   for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if ((threadIdx.x & 31) >= (unsigned)o) incl += t; }
   if ((threadIdx.x & 31) == 31) warp_off[threadIdx.x >> 5] = incl;
   __syncthreads();
-  uint32_t woff = 0;
-  for (unsigned w = 0; w < (threadIdx.x >> 5); w++) woff += warp_off[w];
-  uint64_t at = block_off[blockIdx.x] + woff + incl - c;
+  uint32_t woff = 0, total = 0;
+  for (unsigned w = 0; w < COO_THREADS / 32; w++) { if (w < (threadIdx.x >> 5)) woff += warp_off[w]; total += warp_off[w]; }
+  uint32_t at = woff + incl - c;
 #pragma unroll
   for (int k = 0; k < COO_PER_THREAD; k++) if (v[k]) {
     const uint64_t e = base + k;
-    if (at < cap) { row[at] = (uint32_t)(e % nrows); col[at] = (uint32_t)(e / nrows); val[at] = v[k]; }
+    st_row[at] = (uint32_t)(e % nrows); st_col[at] = (uint32_t)(e / nrows); st_val[at] = v[k];
     at++;
+  }
+  __syncthreads();
+  const uint64_t out0 = block_off[blockIdx.x];
+  for (uint32_t i = threadIdx.x; i < total; i += COO_THREADS) {
+    const uint64_t o = out0 + i;
+    if (o < cap) { row[o] = st_row[i]; col[o] = st_col[i]; val[o] = st_val[i]; }
   }
 }
 

@@ -14,6 +14,7 @@
 #include <future>
 #include <iostream>
 #include <map>
+#include <memory>
 #include <sstream>
 #include <unordered_map>
 
@@ -102,18 +103,22 @@ std::string fmt_f64(double v) {
 struct BatchBuilder {
   uint32_t wpr = 0; size_t cap; uint64_t n = 0;
   uint64_t* seq = nullptr; uint16_t* len = nullptr; uint32_t* cell = nullptr; uint32_t* umi = nullptr; uint8_t* flags = nullptr;
+  uint64_t* ordinal = nullptr;   // optional (with_ordinal): stream position of every record, for sessions that see a shard
+  uint64_t ordinal_base = 0;     // added to the positions (a second pass continues the numbering of the first)
   std::unordered_map<std::string, uint32_t> umi_ids;   // UMIs that are not <=15 ACGT bases
   bool pinned;   // page-locked buffers for the H2D copies; pageable for the host-only self-check
-  explicit BatchBuilder(size_t capacity, bool pinned_ = true) : cap(capacity), pinned(pinned_) {}
+  bool with_ordinal;
+  explicit BatchBuilder(size_t capacity, bool pinned_ = true, bool with_ordinal_ = false) : cap(capacity), pinned(pinned_), with_ordinal(with_ordinal_) {}
   ~BatchBuilder() { release(); }
   void release() {
-    for (void* p : {(void*)seq, (void*)len, (void*)cell, (void*)umi, (void*)flags}) if (p) { if (pinned) hlac_host_free(p); else free(p); }
-    seq = nullptr; len = nullptr; cell = nullptr; umi = nullptr; flags = nullptr;
+    for (void* p : {(void*)seq, (void*)len, (void*)cell, (void*)umi, (void*)flags, (void*)ordinal}) if (p) { if (pinned) hlac_host_free(p); else free(p); }
+    seq = nullptr; len = nullptr; cell = nullptr; umi = nullptr; flags = nullptr; ordinal = nullptr;
   }
   void alloc(uint32_t words) {
     release(); wpr = words;
     auto get = [&](size_t bytes, void** out) { if (pinned) check(hlac_host_alloc(bytes, out)); else if (!(*out = malloc(bytes))) throw Error(HLAC_ERR_IO, "out of memory"); };
     get(cap * wpr * 8, (void**)&seq); get(cap * 2, (void**)&len); get(cap * 4, (void**)&cell); get(cap * 4, (void**)&umi); get(cap, (void**)&flags);
+    if (with_ordinal) get(cap * 8, (void**)&ordinal);
   }
   uint32_t umi_key(const std::string& u) {
     uint32_t k;
@@ -130,7 +135,7 @@ struct BatchBuilder {
     len[n] = (uint16_t)r.seq.size(); cell[n] = cell_id; umi[n] = umi_key(r.umi); flags[n] = r.primary ? HLAC_FLAG_PRIMARY : 0;
     n++;
   }
-  hlac_batch batch() const { hlac_batch b{}; b.seq = seq; b.len = len; b.cell = cell; b.umi = umi; b.flags = flags; b.n = n; b.words_per_read = wpr; return b; }
+  hlac_batch batch() const { hlac_batch b{}; b.seq = seq; b.len = len; b.cell = cell; b.umi = umi; b.flags = flags; b.n = n; b.words_per_read = wpr; b.ordinal = ordinal; return b; }
 };
 
 // Streams the selected BAM records into a session through pinned batches. `flush` pushes one batch and syncs.
@@ -157,9 +162,10 @@ struct NoCellTry { uint32_t operator()(StrRef) const { return CELL_UNKNOWN; } };
 // off the PCIe link and the GPU and only accounts for them (mapping.rs:752-763), see hlac_count_add_filtered.
 struct HostFilter { bool primary_only = false; uint64_t n_reads = 0, n_non_primary = 0, n_not_cell = 0; };
 
-template <typename CellFn, typename Flush, typename CellTry = NoCellTry>
-uint64_t stream_records(BamReader& bam, BatchBuilder& bb, CellFn cell_of, Flush flush, bool cell_of_is_pure, CellTry cell_try = CellTry(),
-                        HostFilter* filter = nullptr) {
+// route(cell) picks the batch (= device lane) a record goes to; flush(lane) pushes that lane's batch.
+template <typename CellFn, typename Flush, typename Route, typename CellTry = NoCellTry>
+uint64_t stream_records_routed(BamReader& bam, std::vector<BatchBuilder*>& lanes, Route route, CellFn cell_of, Flush flush, bool cell_of_is_pure,
+                               CellTry cell_try = CellTry(), HostFilter* filter = nullptr) {
   if (filter && !cell_of_is_pure) throw Error(HLAC_ERR_STATE, "the host filter needs a pure barcode lookup");
   constexpr size_t CHUNK = 1 << 16, GRAIN = 1024;
   constexpr uint32_t UMI_INTERN = 0xFFFFFFFFu;
@@ -222,8 +228,11 @@ uint64_t stream_records(BamReader& bam, BatchBuilder& bb, CellFn cell_of, Flush 
         if (v.primary || !filter->primary_only) filter->n_not_cell++;
         continue;
       }
+      const uint32_t cell = (cell_of_is_pure || cells[i] != CELL_UNKNOWN) ? cells[i] : cell_of(StrRef{v.cb, v.cb_len}, StrRef{v.ub, v.ub_len});
+      const size_t lane = route(cell, total);
+      BatchBuilder& bb = *lanes[lane];
       if (!bb.fits((size_t)v.l_seq)) {
-        if (bb.n) { flush(); bb.n = 0; }
+        if (bb.n) { flush(lane); bb.n = 0; }
         const uint32_t want = std::max<uint32_t>(3, (uint32_t)((v.l_seq + 31) / 32));
         if (want > bb.wpr) bb.alloc(want);
       }
@@ -231,9 +240,11 @@ uint64_t stream_records(BamReader& bam, BatchBuilder& bb, CellFn cell_of, Flush 
       const uint32_t have = (uint32_t)((v.l_seq + 31) / 32);   // words carrying bases; the rest of both rows is zero
       for (uint32_t j = 0; j < bb.wpr; j++) w[j] = j < have ? words[i * need + j] : 0;
       bb.len[bb.n] = (uint16_t)v.l_seq;
-      bb.cell[bb.n] = (cell_of_is_pure || cells[i] != CELL_UNKNOWN) ? cells[i] : cell_of(StrRef{v.cb, v.cb_len}, StrRef{v.ub, v.ub_len});
-      bb.umi[bb.n] = ukey[i] != UMI_INTERN ? ukey[i] : bb.umi_key(std::string(v.ub, v.ub_len));
+      bb.cell[bb.n] = cell;
+      // interned UMI ids (UMIs that are not <= 15 ACGT bases) come from lane 0's table so that they are unique over all lanes
+      bb.umi[bb.n] = ukey[i] != UMI_INTERN ? ukey[i] : lanes[0]->umi_key(std::string(v.ub, v.ub_len));
       bb.flags[bb.n] = v.primary ? HLAC_FLAG_PRIMARY : 0;
+      if (bb.ordinal) bb.ordinal[bb.n] = bb.ordinal_base + total;   // position in the stream (first-seen class ids are global, mapping.rs:147-154)
       bb.n++;
       total++;
     }
@@ -241,8 +252,15 @@ uint64_t stream_records(BamReader& bam, BatchBuilder& bb, CellFn cell_of, Flush 
     n = next.get();
     t_frame += now() - t0;   // time spent WAITING for the next chunk
   }
-  if (bb.n) { flush(); bb.n = 0; }
+  for (size_t lane = 0; lane < lanes.size(); lane++) if (lanes[lane]->n) { flush(lane); lanes[lane]->n = 0; }
   return total;
+}
+
+template <typename CellFn, typename Flush, typename CellTry = NoCellTry>
+uint64_t stream_records(BamReader& bam, BatchBuilder& bb, CellFn cell_of, Flush flush, bool cell_of_is_pure, CellTry cell_try = CellTry(),
+                        HostFilter* filter = nullptr) {
+  std::vector<BatchBuilder*> lanes{&bb};
+  return stream_records_routed(bam, lanes, [](uint32_t, uint64_t) { return size_t(0); }, cell_of, [&](size_t) { flush(); }, cell_of_is_pure, cell_try, filter);
 }
 
 constexpr const char* COUNTS_MAGIC = "HLACCNT1";
@@ -314,10 +332,12 @@ namespace {
 std::string mapping_impl(hlac_index* index, const char* outdir, const char* bam, const char* region, int use_unmapped) {
   info("Mapping reads from BAM to database");
   GenoHandle g; check(hlac_geno_new(index, &g.p));
-  // HLAC_COUNTS_FORMAT=bincode: write the reference's EqClassDb (mapping.rs:403) instead of the table format; that needs
-  // the per-read class ids from the session and the barcode / UMI strings of every read from here
+  // The hand-over file is the reference's own: bincode of EqClassDb (mapping.rs:84-90,403), so that either side of the pair
+  // mapping_wrapper / em_wrapper can be the reference's. It needs the per-read class ids from the session and the barcode /
+  // UMI strings of every read from here. HLAC_COUNTS_FORMAT=tables writes this library's compact table format instead
+  // (the three tables, no per-read triples), which only hlac_em_wrapper reads.
   const char* fmt = getenv("HLAC_COUNTS_FORMAT");
-  const bool bincode = fmt && std::string(fmt) == "bincode";
+  const bool bincode = !fmt || std::string(fmt) == "bincode";
   if (fmt && !bincode && std::string(fmt) != "tables") throw Error(HLAC_ERR_ARG, "HLAC_COUNTS_FORMAT must be 'tables' or 'bincode'");
   if (bincode) check(hlac_geno_record_reads(g.p, 1));
   std::vector<uint32_t> read_bc, read_umi;             // bincode only: per read, index into bc_names / umi_names
@@ -446,31 +466,66 @@ int hlac_em_wrapper(const char* hla_index, const char* hla_counts, const char* c
   HLAC_API_CATCH
 }
 
-// src/mapping.rs:640-821
-int hlac_map_and_count_pseudo(const char* bam, const char* out_dir, const char* barcodes_path, const char* region, const char* cds,
-                              const char* genomic, int primary_only, int device, hlac_coo* entries, hlac_metrics* metrics,
-                              uint32_t* n_cells_out) {
-  HLAC_API_TRY
-  if (!bam || !out_dir || !barcodes_path || !region || !cds || !genomic) throw Error(HLAC_ERR_ARG, "null argument");
-  IndexHandle gix, cix;
-  check(hlac_index_from_fasta(genomic, nullptr, device, &gix.p)); info("Built genome index for pseudoalignment");
-  check(hlac_index_from_fasta(cds, nullptr, device, &cix.p)); info("Built CDS index for pseudoalignment");
+// src/mapping.rs:640-821 on one or several devices. With several, reads are routed by barcode column (column % n) so that
+// every (cell, UMI) molecule is complete on one device; every device holds a session over ALL columns, and
+// hlac_count_finish sums the matrices onto devices[0] through the communicator the sessions share.
+static void map_and_count_impl(const char* bam, const char* out_dir, const char* barcodes_path, const char* region, const char* cds,
+                               const char* genomic, int primary_only, const std::vector<int>& devices, hlac_coo* entries,
+                               hlac_metrics* metrics, uint32_t* n_cells_out) {
+  const size_t nd = devices.size();
+  if (nd == 0) throw Error(HLAC_ERR_ARG, "no device given");
+  for (size_t i = 0; i < nd; i++) for (size_t j = 0; j < i; j++) if (devices[i] == devices[j]) throw Error(HLAC_ERR_ARG, "a device is listed twice");
+  std::vector<IndexHandle> gix(nd), cix(nd);
+  check(hlac_index_from_fasta(genomic, nullptr, devices[0], &gix[0].p)); info("Built genome index for pseudoalignment");
+  check(hlac_index_from_fasta(cds, nullptr, devices[0], &cix[0].p)); info("Built CDS index for pseudoalignment");
+  for (size_t d = 1; d < nd; d++) { check(hlac_index_clone(gix[0].p, devices[d], &gix[d].p)); check(hlac_index_clone(cix[0].p, devices[d], &cix[d].p)); }
   auto barcodes = load_barcodes(barcodes_path);
   const uint32_t n_cells = (uint32_t)barcodes.size();
   uint32_t max_col = 0; for (auto& kv : barcodes) max_col = std::max(max_col, kv.second);
-  if (max_col >= n_cells) throw Error(HLAC_ERR_ARG, "duplicate lines in the barcode file (a column index exceeds the number of distinct barcodes)");
-  CountHandle s; check(hlac_count_new(cix.p, gix.p, n_cells, primary_only, &s.p));
+  // The reference keeps the LAST line index of a duplicated barcode (main.rs:412-416) and sizes the matrix by the number of
+  // distinct barcodes, so a count landing in a column >= that size panics in TriMat::add_triplet (main.rs:279) - but only if
+  // such a count occurs. Here the file is rejected up front: a deliberate, stricter check (README.md).
+  if (max_col >= n_cells) {
+    throw Error(HLAC_ERR_ARG, "duplicate lines in the barcode file " + std::string(barcodes_path) + ": " + std::to_string(max_col + 1) + " lines but " + std::to_string(n_cells) +
+                              " distinct barcodes (the reference would index past its matrix for the later ones, main.rs:279,412-416); remove the duplicates");
+  }
+  struct CommHandle { hlac_comm* p = nullptr; ~CommHandle() { if (p) hlac_comm_free(p); } };
+  std::vector<CountHandle> sess(nd);
+  std::vector<CommHandle> comms(nd);
+  for (size_t d = 0; d < nd; d++) check(hlac_count_new(cix[d].p, gix[d].p, n_cells, primary_only, &sess[d].p));
+  if (nd > 1) {
+    std::vector<hlac_comm*> raw(nd, nullptr);
+    check(hlac_comm_init_all(devices.data(), (int)nd, raw.data()));
+    for (size_t d = 0; d < nd; d++) { comms[d].p = raw[d]; check(hlac_count_attach_comm(sess[d].p, raw[d], 0)); }
+    info("Counting on " + std::to_string(nd) + " GPUs: reads routed by barcode, matrices summed onto device " + std::to_string(devices[0]));
+  }
   { std::ofstream lab(join(out_dir, "labels.tsv")); if (!lab) throw Error(HLAC_ERR_IO, "cannot write labels.tsv");
-    for (uint32_t i = 0; i < hlac_count_nrows(s.p); i++) lab << hlac_count_row_name(s.p, i) << '\n'; }
+    for (uint32_t i = 0; i < hlac_count_nrows(sess[0].p); i++) lab << hlac_count_row_name(sess[0].p, i) << '\n'; }
   BamReader reader(bam);
   Locus l = parse_locus(region); reader.fetch(l.chrom, l.start, l.end);
-  BatchBuilder bb(BATCH_READS);
+  std::vector<std::unique_ptr<BatchBuilder>> bbs;
+  std::vector<BatchBuilder*> lanes;
+  for (size_t d = 0; d < nd; d++) { bbs.emplace_back(new BatchBuilder(BATCH_READS)); lanes.push_back(bbs.back().get()); }
   // the whitelist is read-only here: the lookup is a pure function and runs on the parser threads
   auto cell_of = [&](StrRef cb, StrRef) { auto it = barcodes.find(cb.str()); return it == barcodes.end() ? HLAC_NOT_A_CELL : it->second; };
   HostFilter filt; filt.primary_only = primary_only != 0;
-  stream_records(reader, bb, cell_of, [&] { hlac_batch b = bb.batch(); check(hlac_count_push(s.p, &b)); check(hlac_count_sync(s.p)); }, true, NoCellTry(), &filt);
-  check(hlac_count_add_filtered(s.p, filt.n_reads, filt.n_non_primary, filt.n_not_cell));
-  hlac_metrics m{}; hlac_coo tmp{}; check(hlac_count_finish(s.p, &tmp, &m));
+  stream_records_routed(reader, lanes, [nd](uint32_t cell, uint64_t) { return (size_t)(cell % nd); }, cell_of,
+                        [&](size_t d) { hlac_batch b = lanes[d]->batch(); check(hlac_count_push(sess[d].p, &b)); check(hlac_count_sync(sess[d].p)); },
+                        true, NoCellTry(), &filt);
+  check(hlac_count_add_filtered(sess[0].p, filt.n_reads, filt.n_non_primary, filt.n_not_cell));
+  hlac_metrics m{}; hlac_coo tmp{};
+  if (nd == 1) check(hlac_count_finish(sess[0].p, &tmp, &m));
+  else {   // the finish is a collective: one host thread per device
+    std::vector<std::future<void>> fut;
+    std::vector<std::string> errs(nd);
+    std::vector<int> rcs(nd, HLAC_OK);
+    for (size_t d = 1; d < nd; d++)
+      fut.push_back(std::async(std::launch::async, [&, d] { hlac_coo c{}; hlac_metrics mm{}; rcs[d] = hlac_count_finish(sess[d].p, &c, &mm); if (rcs[d] != HLAC_OK) errs[d] = hlac_last_error(); }));
+    rcs[0] = hlac_count_finish(sess[0].p, &tmp, &m);
+    if (rcs[0] != HLAC_OK) errs[0] = hlac_last_error();
+    for (auto& f : fut) f.get();
+    for (size_t d = 0; d < nd; d++) if (rcs[d] != HLAC_OK) throw Error(rcs[d], "device " + std::to_string(devices[d]) + ": " + errs[d]);
+  }
   if (entries) {   // the session (and its pinned result buffer) ends with this call: hand out owned copies
     *entries = tmp; entries->borrowed = 0;
     const size_t bytes = std::max<uint64_t>(tmp.n, 1) * 4;
@@ -480,6 +535,23 @@ int hlac_map_and_count_pseudo(const char* bam, const char* out_dir, const char* 
   if (metrics) *metrics = m;
   if (n_cells_out) *n_cells_out = n_cells;
   info("analyzed " + std::to_string(m.num_reads) + " reads. Mapped " + std::to_string(m.num_gen_align + m.num_cds_align) + " with score at least " + std::to_string(MIN_SCORE_COUNT_PSEUDO));
+}
+
+int hlac_map_and_count_pseudo(const char* bam, const char* out_dir, const char* barcodes_path, const char* region, const char* cds,
+                              const char* genomic, int primary_only, int device, hlac_coo* entries, hlac_metrics* metrics,
+                              uint32_t* n_cells_out) {
+  HLAC_API_TRY
+  if (!bam || !out_dir || !barcodes_path || !region || !cds || !genomic) throw Error(HLAC_ERR_ARG, "null argument");
+  map_and_count_impl(bam, out_dir, barcodes_path, region, cds, genomic, primary_only, {device}, entries, metrics, n_cells_out);
+  HLAC_API_CATCH
+}
+
+int hlac_map_and_count_pseudo_multi(const char* bam, const char* out_dir, const char* barcodes_path, const char* region, const char* cds,
+                                    const char* genomic, int primary_only, const int* devices, int n_devices, hlac_coo* entries,
+                                    hlac_metrics* metrics, uint32_t* n_cells_out) {
+  HLAC_API_TRY
+  if (!bam || !out_dir || !barcodes_path || !region || !cds || !genomic || !devices || n_devices < 1) throw Error(HLAC_ERR_ARG, "null argument");
+  map_and_count_impl(bam, out_dir, barcodes_path, region, cds, genomic, primary_only, std::vector<int>(devices, devices + n_devices), entries, metrics, n_cells_out);
   HLAC_API_CATCH
 }
 
@@ -550,7 +622,7 @@ int hlac_main(int argc, const char* const* argv) {
       {"-b", "bam"}, {"--bam", "bam"}, {"-c", "cell_barcodes"}, {"--cell-barcodes", "cell_barcodes"}, {"-o", "out_dir"}, {"--out-dir", "out_dir"},
       {"--pl-tmp", "pl_tmp"}, {"-g", "fastagenomic"}, {"--fasta-genomic", "fastagenomic"}, {"-f", "fastacds"}, {"--fasta-cds", "fastacds"},
       {"-d", "hladbdir"}, {"--hladb-dir", "hladbdir"}, {"-i", "hlaindex"}, {"--hla-index", "hlaindex"}, {"-r", "region"}, {"--region", "region"},
-      {"--log-level", "log_level"}, {"--device", "device"}};
+      {"--log-level", "log_level"}, {"--device", "device"}, {"--devices", "devices"}};
   static const std::map<std::string, std::string> flags = {{"--primary-alignments", "primary"}, {"--use-exact-count", "exact"}, {"--unmapped", "unmapped"}};
   for (int i = 1; i < argc; i++) {
     std::string a = argv[i];
@@ -565,7 +637,19 @@ int hlac_main(int argc, const char* const* argv) {
   if (!opt.count("cell_barcodes")) throw Error(HLAC_ERR_ARG, "You must provide a cell barcodes file");
   if (opt["log_level"] != "info" && opt["log_level"] != "debug" && opt["log_level"] != "error") throw Error(HLAC_ERR_ARG, "Log level must be 'info', 'debug', or 'error'");
   if (flag["exact"]) throw Error(HLAC_ERR_ARG, "--use-exact-count (banded Smith-Waterman, mapping.rs:407-637) is outside this build's hot path");
-  const int device = std::stoi(opt["device"]);
+  // --devices 0,1,2,3 (or 0-3): the counting pass runs on all of them; everything else on the first
+  std::vector<int> devices;
+  if (opt.count("devices")) {
+    std::stringstream ss(opt["devices"]); std::string tok;
+    while (std::getline(ss, tok, ',')) {
+      const size_t dash = tok.find('-');
+      if (tok.empty()) continue;
+      if (dash != std::string::npos && dash > 0) { for (int d = std::stoi(tok.substr(0, dash)); d <= std::stoi(tok.substr(dash + 1)); d++) devices.push_back(d); }
+      else devices.push_back(std::stoi(tok));
+    }
+    if (devices.empty()) throw Error(HLAC_ERR_ARG, "--devices needs a list like 0,1,2,3 or 0-3");
+  } else devices.push_back(std::stoi(opt["device"]));
+  const int device = devices[0];
   const std::string bam = opt["bam"], bcs = opt["cell_barcodes"], out_dir = opt["out_dir"], pl = opt["pl_tmp"];
   // check_inputs_exist (main.rs:302-348)
   for (auto& p : {bam, bcs}) if (!path_exists(p)) throw Error(HLAC_ERR_IO, "Input \"" + p + "\" does not exist");
@@ -602,7 +686,8 @@ int hlac_main(int argc, const char* const* argv) {
   }
   for (auto& p : {cds, genomic}) if (!path_exists(p)) throw Error(HLAC_ERR_IO, "Input file \"" + p + "\" does not exist");
   hlac_coo coo{}; hlac_metrics m{}; uint32_t n_cells = 0;
-  check(hlac_map_and_count_pseudo(bam.c_str(), out_dir.c_str(), bcs.c_str(), opt["region"].c_str(), cds.c_str(), genomic.c_str(), flag["primary"], device, &coo, &m, &n_cells));
+  check(hlac_map_and_count_pseudo_multi(bam.c_str(), out_dir.c_str(), bcs.c_str(), opt["region"].c_str(), cds.c_str(), genomic.c_str(), flag["primary"],
+                                        devices.data(), (int)devices.size(), &coo, &m, &n_cells));
   struct Free { hlac_coo* c; ~Free() { hlac_coo_free(c); } } fr{&coo};
   info("Initialized a " + std::to_string(coo.nrows) + " features x " + std::to_string(n_cells) + " cell barcodes matrix.");
   info("Number of alignments evaluated (with 'CB' and 'UB' tags): " + std::to_string(m.num_reads));

@@ -57,7 +57,7 @@ def test_allele_fasta_cli(tmp_path):
     assert r2.returncode == 1 and "already exists" in r2.stdout
 
 
-@pytest.mark.parametrize("with_index,counts_format", [(True, None), (False, None), (True, "bincode")])
+@pytest.mark.parametrize("with_index,counts_format", [(True, None), (False, None), (True, "tables")])
 def test_call_cli(tmp_path, with_index, counts_format):
     args = ["-b", os.path.join(H.FIX, "test.bam"), "-d", os.path.join(H.FIX, "fake_db"), "-c",
             os.path.join(H.FIX, "barcodes0.tsv"), "-o", str(tmp_path / "r"), "--pl-tmp", str(tmp_path / "p")]
@@ -65,10 +65,12 @@ def test_call_cli(tmp_path, with_index, counts_format):
         args += ["-i", os.path.join(H.FIX, "fake_db", "hla_nuc.fasta.idx")]
     r = _run(args, tmp_path, {"HLAC_COUNTS_FORMAT": counts_format} if counts_format else None)
     assert r.returncode == 0, r.stdout + r.stderr
-    if counts_format == "bincode":   # the hand-over file is then the reference's EqClassDb (mapping.rs:403 -> em.rs:347)
+    if counts_format is None:   # by default the hand-over file is the reference's EqClassDb (mapping.rs:403 -> em.rs:347)
         bcs, umis, classes, triples = H.read_eqclassdb_bincode(tmp_path / "p" / "pseudoaligner.counts.bin")
         assert len(triples) == 2704 and len(classes) == 98 and sorted(classes.values()) == list(range(98))
         assert all(k.endswith(b"-1") for k in bcs) and all(len(k) == 10 for k in umis)
+    else:                       # HLAC_COUNTS_FORMAT=tables: this library's compact table format
+        assert open(tmp_path / "p" / "pseudoaligner.counts.bin", "rb").read(8) == b"HLACCNT1"
     assert H.read_mtx(tmp_path / "r" / "count_matrix.mtx") == H.read_mtx(os.path.join(H.FIX, "test_call.mtx")) == (5, 2, [(1, 0, 1)])
     w = [l.split("\t") for l in open(tmp_path / "p" / "weights.tsv").read().splitlines()]
     assert w[0] == ["allele_name", "em_weight", "reads_explained"]

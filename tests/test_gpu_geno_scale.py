@@ -59,24 +59,29 @@ def _check_em_and_calls(sb, orc, g, o, t):
     theta, iters = g.squarem()
     ref = o.call()
     off, tx, cnt = t["umi"]
-    # (1) exact statements: both runs stop at the same likelihood (SQUAREM's stopping rule is loose, the likelihood is flat
-    # there) and within a few outer iterations of each other
+    # The reference sums over a randomly ordered HashMap (em.rs:84,122) and stops on a loose rule (abs 5e-3 / rel 5e-4,
+    # config.rs:11-12), so the reference itself is only defined up to the spread of its own result under a permutation of the
+    # class order. Measure that envelope with the oracle (theta, likelihood, outer iterations) and require the GPU run to
+    # sit within 1e-6 relative (north-star) or twice the envelope, whichever is wider; on top of that, hard bounds that do
+    # not depend on the envelope: same likelihood to 1e-6 relative, and a proper distribution.
     l_gpu, l_ref = H.em_loglik(off, tx, cnt, theta), H.em_loglik(off, tx, cnt, ref["theta"])
-    assert abs(l_gpu - l_ref) <= 1e-9 * abs(l_ref), (l_gpu, l_ref)
-    assert abs(int(iters) - int(ref["iters"])) <= max(4, ref["iters"] // 10), (iters, ref["iters"])
-    assert abs(theta.sum() - 1.0) < 1e-9
-    # (2) the envelope: the reference sums over a randomly ordered HashMap (em.rs:84,122); the oracle moves by `env` under
-    # a permutation of the class order, and the GPU result must sit within 1e-6 relative or that envelope
     keys = np.arange(len(cnt))
-    env = 0.0
+    env, env_l, env_it = 0.0, 0.0, 0
     rng = np.random.default_rng(3)
     for perm in (keys[::-1], rng.permutation(len(keys))):
-        lens = np.diff(off.astype(np.int64))
         ks = [tuple(tx[int(off[i]):int(off[i + 1])].tolist()) for i in perm]
-        th2, _ = orc.squarem_ordered(len(theta), ks, cnt[perm].tolist())
+        th2, it2 = orc.squarem_ordered(len(theta), ks, cnt[perm].tolist())
         env = max(env, float(np.abs(th2 - ref["theta"]).max()))
+        env_l = max(env_l, abs(H.em_loglik(off, tx, cnt, th2) - l_ref))
+        env_it = max(env_it, abs(int(it2) - int(ref["iters"])))
+    assert abs(l_gpu - l_ref) <= max(1e-9 * abs(l_ref), 2.0 * env_l), (l_gpu, l_ref, env_l)
+    assert abs(l_gpu - l_ref) <= 1e-6 * abs(l_ref), (l_gpu, l_ref)
+    assert abs(int(iters) - int(ref["iters"])) <= max(2, 2 * env_it), (iters, ref["iters"], env_it)
+    assert abs(theta.sum() - 1.0) < 1e-9 and (theta >= 0).all()
     tol = np.maximum(EM_RTOL * np.abs(ref["theta"]), 2.0 * env)
     assert (np.abs(theta - ref["theta"]) <= tol + 1e-15).all(), (float(np.abs(theta - ref["theta"]).max()), env)
+    if env == 0.0:
+        assert iters == ref["iters"]
     call = g.call(theta, on_device=True)
     assert call["called"] == ref["called"]
     assert [p[:2] for p in call["pairs"]] == [p[:2] for p in ref["pairs"]]

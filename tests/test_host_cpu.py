@@ -303,6 +303,45 @@ def test_bam_reader_rejects_damaged_files(sb, tmp_path):
         assert fn(write("ok.bam", raw), b"6:notanumber", C.byref(n), C.byref(h)) != 0                    # locus parse error (locus.rs)
 
 
+def test_bam_aux_arrays_and_overruns(sb, tmp_path):
+    """BAM aux fields the reader has to step over (SAM spec 4.2.4): 'B' arrays of every element width and htslib's 'd'
+    must be skipped exactly; an array whose count is negative or runs past the record is a format error, not a mis-parse
+    that picks up bogus CB/UB tags further on."""
+    import struct
+    from tools import make_bam as mb
+    L = sb.lib()
+    seq = "ACGT" * 22 + "ACG"
+
+    def write(name, extras):
+        p = str(tmp_path / name)
+        w = mb.BgzfWriter(p)
+        hdr = b"@HD\tVN:1.4\tSO:coordinate\n@SQ\tSN:6\tLN:170805979\n"
+        w.write(b"BAM\x01" + struct.pack("<i", len(hdr)) + hdr + struct.pack("<i", 1) + struct.pack("<i", 2) + b"6\0" + struct.pack("<i", 170805979))
+        first = w.tell()
+        for i, ex in enumerate(extras):
+            w.write(mb.record(0, 30_000_000 + 100 * i, 0, seq, b"r%d" % i, b"AAACCCGGGTTTACGT-1", b"ACGTACGTA" + b"ACGT"[i % 4:i % 4 + 1], extra_aux=ex))
+        end = w.tell()
+        w.close()
+        n_intv = (30_000_000 + 100 * len(extras) >> 14) + 1
+        with open(p + ".bai", "wb") as f:
+            f.write(b"BAI\x01" + struct.pack("<i", 1) + struct.pack("<i", 1) + struct.pack("<Ii", 0, 1) + struct.pack("<QQ", first, end) + struct.pack("<i", n_intv))
+            f.write(struct.pack("<%dQ" % n_intv, *([first] * n_intv)) + struct.pack("<Q", 0))
+        return p.encode()
+    good = [b"ZAB" + b"c" + struct.pack("<i", 5) + bytes([1, 2, 3, 0x43, 0x42]),              # bytes that look like a tag inside the array
+            b"ZBB" + b"S" + struct.pack("<i", 3) + struct.pack("<3H", 1, 2, 3),
+            b"ZCB" + b"f" + struct.pack("<i", 2) + struct.pack("<2f", 1.5, 2.5) + b"ZDd" + struct.pack("<d", 3.25),
+            b"ZEB" + b"I" + struct.pack("<i", 0)]
+    n, h = C.c_uint64(), C.c_uint64()
+    region = b"6:28510120-33480577"
+    for fn in (L.hlac_bam_scan, L.hlac_bam_batch_checksum):
+        assert fn(write("good.bam", good), region, C.byref(n), C.byref(h)) == 0, L.hlac_last_error()
+        assert n.value == len(good)
+        for bad in (b"ZAB" + b"I" + struct.pack("<i", -1), b"ZAB" + b"I" + struct.pack("<i", 1 << 28), b"ZAB" + b"x" + struct.pack("<i", 1) + b"\0",
+                    b"ZAB" + b"c"):
+            assert fn(write("bad.bam", [good[0], bad]), region, C.byref(n), C.byref(h)) != 0
+            assert b"aux" in L.hlac_last_error()
+
+
 def test_index_build_equals_oracle_on_synthetic_db(sb, orc, tmp_path):
     """build_index on a 600-allele synthetic IMGT-like database: the product's sort-based host builder and
     the oracle's restatement must produce the same graph (node sequences, extension masks, colour lists) and tx order, and

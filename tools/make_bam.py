@@ -54,12 +54,12 @@ class BgzfWriter:
         self.f.close()
 
 
-def record(tid, pos, flag, seq, name, cb, ub):
+def record(tid, pos, flag, seq, name, cb, ub, extra_aux=b""):
     l = len(seq)
     packed = bytearray((l + 1) // 2)
     for i, ch in enumerate(seq):
         packed[i >> 1] |= NT16[ch] << (0 if i & 1 else 4)
-    aux = b"NHC\x01" + b"HIC\x01" + b"ASC\x59" + b"nMC\x00" + b"CRZ" + cb[:16] + b"\0" + b"CYZ" + b"F" * 16 + b"\0"
+    aux = b"NHC\x01" + b"HIC\x01" + b"ASC\x59" + b"nMC\x00" + extra_aux + b"CRZ" + (cb or b"N" * 16)[:16] + b"\0" + b"CYZ" + b"F" * 16 + b"\0"
     if cb is not None:
         aux += b"CBZ" + cb + b"\0"
     aux += b"URZ" + (ub or b"ACGTACGTAC") + b"\0" + b"UYZ" + b"F" * 10 + b"\0"
