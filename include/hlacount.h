@@ -223,6 +223,9 @@ int hlac_count_finish(hlac_count*, hlac_coo* out, hlac_metrics* metrics);
 int hlac_count_attach_comm(hlac_count*, hlac_comm* comm, int root);
 /* scored reads grouped by the last finish / reduce, hash buckets in use, finishes that had to take the sort path */
 int hlac_count_group_stats(hlac_count*, uint64_t* n_keys, uint32_t* n_buckets, uint64_t* fallbacks);
+/* the launch shape the map kernel last ran with, as text (diagnostics; HLAC_COUNT_SHAPE="smem,threads,slots,idx" forces one,
+ * HLAC_COUNT_TMA=1 enables the bulk-copy record prefetch) */
+int hlac_count_shape(hlac_count*, char* out, size_t cap);
 int hlac_count_reset(hlac_count*);                              /* drop accumulated reads, keep buffers */
 int hlac_coo_free(hlac_coo*);
 /* kernel timing of the session since the last reset, measured with CUDA events on the session stream:

@@ -345,6 +345,11 @@ class CountSession:
         check(lib().hlac_count_timing(self.h, ms, C.byref(n)))
         return dict(map_ms=ms[0], group_ms=ms[1], coo_ms=ms[2], h2d_ms=ms[3], launches=n.value)
 
+    def shape(self):
+        buf = C.create_string_buffer(256)
+        check(lib().hlac_count_shape(self.h, buf, C.c_size_t(256)))
+        return buf.value.decode()
+
     def group_stats(self):
         k, b, f = C.c_uint64(), C.c_uint32(), C.c_uint64()
         check(lib().hlac_count_group_stats(self.h, C.byref(k), C.byref(b), C.byref(f)))

@@ -74,8 +74,8 @@ struct CountMapArgs {
   const uint8_t* flags;
   uint64_t n;
   uint32_t wpr;                // u64 words per read
-  uint32_t nw;                 // u32 words per strand row in shared memory (2*wpr + 2)
-  uint32_t row_stride;         // u32 words per thread (both strands, odd)
+  uint32_t nw;                 // u32 words per strand row in shared memory (2*wpr + 1)
+  uint32_t row_stride;         // u32 words per slot (both strands + the read index, odd)
   int primary_only;
   uint32_t cell_bits;          // key layout: umi << (5 + cell_bits) | cell << 5 | code
   uint32_t n_cells;            // cell indices >= n_cells are a caller error: dropped and counted in metrics[8]
@@ -101,58 +101,124 @@ struct CountVis {
   }
 };
 
-struct SharedWords {
-  const uint32_t* p;
-  __device__ __forceinline__ uint32_t operator[](int i) const { return p[i]; }
-};
-struct BitmapShared {
-  const uint32_t* p;
-  __device__ __forceinline__ uint32_t operator()(uint32_t i) const { return p[i]; }
-};
 struct BitmapGlobal {
   const uint32_t* p;
   __device__ __forceinline__ uint32_t operator()(uint32_t i) const { return __ldg(p + i); }
 };
 
+// ---- bulk-copy (TMA) + mbarrier primitives for the record prefetch --------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+
 // Queue-staged map kernel (ncu history of its predecessors in profiles/: thread-per-read 6.65 of 32 lanes active per issued
-// instruction, block-staged 12.6 lanes but barrier-bound, warp-staged tiles 12.2, this one 14.65). Each
+// instruction, block-staged 12.6 lanes but barrier-bound, warp-staged tiles 12.2, queue-staged 14.65). Each
 // warp keeps a pool of NS read slots and two warp-private task queues that persist across refills: SCAN entries are
 // (slot, p) with p = the orientation/index the chain of mapping.rs:772-790 has reached, WALK entries are slots with
 // a seed. A round of either kind only runs when 32 tasks are waiting (or the warp's input is exhausted), so every
 // round starts with all lanes busy whatever fraction of the reads survives each stage; scan rounds mix the four
 // orientations (same code, per-lane operands). The warp streams a contiguous range of the batch and refills the
 // pool with as many reads as there are free slots.
-template <bool SMEM_BM, int MAP_THREADS, int MINB, bool PACKED, int STRIDE>
+//
+// Shared memory is addressed through explicit 32-bit shared-window addresses (device_index.cuh). One slot is
+// row_stride = 2 * nw + 1 words (odd: lanes on different slots never share a bank): the forward row, the reverse-complement
+// row (nw = 2 * wpr + 1 words each: the packed bases plus one word the 16-base extraction may touch but whose content
+// never reaches a result) and the read's index in the batch; the spare word of the forward row holds the seed's node, the
+// spare word of the reverse row the seed's (offset, position, orientation).
+//
+// PACKED && TMA: the warp's contiguous records are prefetched 32 at a time by ONE bulk asynchronous copy
+// (cp.async.bulk, completion on a per-warp mbarrier) into a per-warp staging tile; the copy of the next tile is issued as
+// soon as the current one has been handed to slots, and lands while the warp runs scan / walk rounds, so a refill reads
+// shared memory instead of waiting on 32 dependent global loads.
+//
+// Shared memory doubles as the L1 carve-out, and the walk's node records / node sequences live in L1: the r02 kernel got
+// 10 % faster by shrinking the slots alone (215 -> 170 KB requested, L1 28 -> 60 KB), and the bulk prefetch, which costs
+// 32 KB of staging, was measured SLOWER on config 2 for that reason (1.25 vs 1.17 ms per 10 M reads). Hence two more
+// knobs: NS (slots per warp: fewer slots = more L1) and IDX_SMEM (for the small indexes of known-genotype counting the
+// node tables and node sequences are staged in shared memory themselves, so only dictionary probes go through L1).
+__host__ __device__ constexpr uint32_t map_nw(uint32_t wpr) { return 2 * wpr + 1; }
+__host__ __device__ constexpr uint32_t map_row_stride(uint32_t wpr) { return 2 * map_nw(wpr) + 1; }
+__host__ __device__ constexpr uint32_t map_warp_bytes(uint32_t wpr, bool tma, uint32_t ns) {
+  // slots + lens u16 + three byte queues, rounded to 16 B; staging tile (32 records of (wpr + 1) u64) + mbarrier
+  return ((ns * map_row_stride(wpr) * 4 + ns * 2 + ns * 3 + 15) & ~15u) + (tma ? 32 * (wpr + 1) * 8 + 16 : 0);
+}
+__host__ __device__ constexpr uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
+
+template <bool SMEM_BM, int MAP_THREADS, int MINB, bool PACKED, int STRIDE, bool TMA, int NS = 64, bool IDX_SMEM = false>
 __global__ void __launch_bounds__(MAP_THREADS, MINB) k_count_map_q(const CountMapArgs a) {
   extern __shared__ __align__(16) uint32_t smem[];
-  constexpr int NS = 64;
-  uint32_t* wbase = smem;
+  static_assert(!TMA || PACKED, "the bulk prefetch reads packed records");
+  static_assert(NS <= 64 && NS % 8 == 0 && NS >= 32, "slot ids are 6-bit queue entries");
+  static_assert(!IDX_SMEM || SMEM_BM, "the staged index sits behind the staged bitmaps");
+  const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
+  uint32_t bm_bytes = 0;
+  uint32_t g_cds_nodes = 0, g_cds_seq = 0, g_gen_nodes = 0, g_gen_seq = 0;   // IDX_SMEM: shared addresses of the staged graphs
   if (SMEM_BM) {
     const uint32_t nb = a.cds.bitmap_words + a.gen.bitmap_words;
     for (uint32_t i = threadIdx.x; i < a.cds.bitmap_words; i += MAP_THREADS) smem[i] = __ldg(a.cds.bitmap + i);
     for (uint32_t i = threadIdx.x; i < a.gen.bitmap_words; i += MAP_THREADS) smem[a.cds.bitmap_words + i] = __ldg(a.gen.bitmap + i);
-    wbase = smem + nb;
+    bm_bytes = align16(nb * 4);
+    if (IDX_SMEM) {
+      const uint32_t w0 = bm_bytes / 4, w1 = w0 + a.cds.n_nodes * 12, w2 = w1 + a.gen.n_nodes * 12, w3 = w2 + align16(a.cds.seq_words * 4) / 4,
+                     w4 = w3 + align16(a.gen.seq_words * 4) / 4;
+      const uint32_t* src;
+      src = reinterpret_cast<const uint32_t*>(a.cds.nodes); for (uint32_t i = threadIdx.x; i < a.cds.n_nodes * 12; i += MAP_THREADS) smem[w0 + i] = __ldg(src + i);
+      src = reinterpret_cast<const uint32_t*>(a.gen.nodes); for (uint32_t i = threadIdx.x; i < a.gen.n_nodes * 12; i += MAP_THREADS) smem[w1 + i] = __ldg(src + i);
+      for (uint32_t i = threadIdx.x; i < a.cds.seq_words; i += MAP_THREADS) smem[w2 + i] = __ldg(a.cds.seq32 + i);
+      for (uint32_t i = threadIdx.x; i < a.gen.seq_words; i += MAP_THREADS) smem[w3 + i] = __ldg(a.gen.seq32 + i);
+      g_cds_nodes = sbase + w0 * 4; g_gen_nodes = sbase + w1 * 4; g_cds_seq = sbase + w2 * 4; g_gen_seq = sbase + w3 * 4;
+      bm_bytes = w4 * 4;
+    }
     __syncthreads();
   }
   const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned below = (1u << lane) - 1;
-  const uint32_t per_warp = NS * a.row_stride + NS * 3 + NS / 2 + 3 * NS / 4;   // u32 words
-  uint32_t* rows = wbase + warp * per_warp;
-  uint32_t* seed_node = rows + NS * a.row_stride;
-  uint32_t* seed_info = seed_node + NS;                                     // off(20) | pos(10) | p(2)
-  uint32_t* ridx = seed_info + NS;                                          // read index within the batch
-  uint16_t* lens = reinterpret_cast<uint16_t*>(ridx + NS);
-  uint8_t* qs = reinterpret_cast<uint8_t*>(lens + NS);                      // scan queue: slot | p << 6
-  uint8_t* qw = qs + NS;                                                    // walk queue
-  uint8_t* fr = qw + NS;                                                    // free-slot stack
-  fr[lane] = (uint8_t)lane; fr[lane + 32] = (uint8_t)(lane + 32);
+  const uint32_t nw = a.nw, rs4 = a.row_stride * 4;
+  const uint32_t wb = sbase + bm_bytes + warp * map_warp_bytes(a.wpr, TMA, NS);   // this warp's region
+  const uint32_t a_lens = wb + NS * rs4;            // u16[NS]
+  const uint32_t a_qs = a_lens + NS * 2;            // scan queue: slot | p << 6
+  const uint32_t a_qw = a_qs + NS;                  // walk queue
+  const uint32_t a_fr = a_qw + NS;                  // free-slot stack
+  const uint32_t a_stage = wb + ((NS * rs4 + NS * 2 + NS * 3 + 15) & ~15u);   // TMA: 32 records
+  const uint32_t a_bar = a_stage + 32 * (a.wpr + 1) * 8;
+  const uint32_t bm_cds = sbase, bm_gen = sbase + a.cds.bitmap_words * 4;
+  for (unsigned k = lane; k < (unsigned)NS; k += 32) sts8(a_fr + k, k);
   unsigned ns = 0, nwk = 0, nfree = NS;                                     // warp-uniform
   unsigned long long m_reads = 0, m_nonprim = 0, m_notcell = 0, m_cds = 0, m_gen = 0, m_none = 0, m_badcell = 0;
   uint32_t n_tests = 0, n_probes = 0, umi_max = 0;
   const uint64_t n_warps = (uint64_t)gridDim.x * (MAP_THREADS / 32);
-  const uint64_t per = (a.n + n_warps - 1) / n_warps;
+  const uint64_t per = ((a.n + n_warps - 1) / n_warps + 31) & ~31ull;      // whole 32-record tiles per warp
   uint64_t cur = min(a.n, ((uint64_t)blockIdx.x * (MAP_THREADS / 32) + warp) * per);
   const uint64_t hi = min(a.n, cur + per);
+  const uint32_t rec_bytes = (a.wpr + 1) * 8;
+  // bulk prefetch state (warp-uniform): records of the staged tile not yet handed out, the tile in flight
+  uint32_t st_n = 0, st_next = 0, fl_n = 0, phase = 0;
+  uint64_t fl_first = cur;   // first record of the tile to request next
+  if (TMA) {
+    if (lane == 0) mbar_init(a_bar, 1);
+    __syncwarp();
+    if (fl_first < hi) {
+      fl_n = (uint32_t)min((uint64_t)32, hi - fl_first);
+      if (lane == 0) bulk_g2s(a_stage, a.rec + fl_first * (a.wpr + 1), fl_n * rec_bytes, a_bar);
+      fl_first += fl_n;
+    }
+  }
   __syncwarp();
   for (;;) {
     const bool more = cur < hi;
@@ -165,34 +231,51 @@ __global__ void __launch_bounds__(MAP_THREADS, MINB) k_count_map_q(const CountMa
     else break;
     if (what == 2) {
       // ---- refill: filters (mapping.rs:752-763) + read rows into free slots ----
-      const unsigned c = (unsigned)min((uint64_t)min(32u, nfree), hi - cur);
+      unsigned c;
+      if (TMA) {
+        if (st_next == st_n) {   // staging tile used up: the one in flight has (long) landed
+          mbar_wait(a_bar, phase); phase ^= 1;
+          st_n = fl_n; st_next = 0; fl_n = 0;
+        }
+        c = min(min(32u, nfree), st_n - st_next);
+      } else c = (unsigned)min((uint64_t)min(32u, nfree), hi - cur);
       bool keep = false;
       unsigned slot = 0;
       if (lane < c) {
         const uint64_t i = cur + lane;
-        slot = fr[nfree - c + lane];
-        uint8_t fl; uint32_t cell; uint16_t L;
-        const uint64_t* words;
+        slot = lds8(a_fr + nfree - c + lane);
+        const uint32_t fw = wb + slot * rs4, rc = fw + nw * 4;
+        uint8_t fl; uint32_t cell; uint32_t L;
         if (PACKED) {   // one record per read: sequence words, then umi | primary | len | cell
-          words = a.rec + i * (a.wpr + 1);
-          const uint32_t meta = (uint32_t)__ldg(words + a.wpr);
+          uint32_t meta;
+          if (TMA) {
+            const uint32_t src = a_stage + (st_next + lane) * rec_bytes;
+            if ((a.wpr & 1) && a.wpr == 3) {   // 32-byte records: two 128-bit loads
+              const uint4 q0 = lds128(src), q1 = lds128(src + 16);
+              sts32(fw, q0.y); sts32(fw + 4, q0.x); sts32(fw + 8, q0.w); sts32(fw + 12, q0.z); sts32(fw + 16, q1.y); sts32(fw + 20, q1.x);
+              meta = q1.z;
+            } else {
+              for (uint32_t w = 0; w < a.wpr; w++) { const uint2 v = lds64(src + 8 * w); sts32(fw + 8 * w, v.y); sts32(fw + 8 * w + 4, v.x); }
+              meta = lds32(src + 8 * a.wpr);
+            }
+          } else {
+            const uint64_t* words = a.rec + i * (a.wpr + 1);
+            meta = (uint32_t)__ldg(words + a.wpr);
+            for (uint32_t w = 0; w < a.wpr; w++) { const uint64_t v = __ldg(words + w); sts32(fw + 8 * w, (uint32_t)(v >> 32)); sts32(fw + 8 * w + 4, (uint32_t)v); }
+          }
           fl = (meta >> 31) ? HLAC_FLAG_PRIMARY : 0;
           cell = meta & HLAC_PACKED_NOT_A_CELL; if (cell == HLAC_PACKED_NOT_A_CELL) cell = HLAC_NOT_A_CELL;
-          L = (uint16_t)min((meta >> 23) & 0xFFu, 32u * a.wpr);
+          L = min((meta >> 23) & 0xFFu, 32u * a.wpr);
         } else {
-          words = a.seq + i * a.wpr;
+          const uint64_t* words = a.seq + i * a.wpr;
           fl = __ldg(a.flags + i);
           cell = __ldg(a.cell + i);
-          L = (uint16_t)min((uint32_t)__ldg(a.len + i), 32u * a.wpr);
+          L = min((uint32_t)__ldg(a.len + i), 32u * a.wpr);   // never read past the packed words
+          for (uint32_t w = 0; w < a.wpr; w++) { const uint64_t v = __ldg(words + w); sts32(fw + 8 * w, (uint32_t)(v >> 32)); sts32(fw + 8 * w + 4, (uint32_t)v); }
         }
-        uint32_t* fw = rows + slot * a.row_stride;
-        for (uint32_t w = 0; w < a.wpr; w++) {
-          const uint64_t v = __ldg(words + w);
-          fw[2 * w] = (uint32_t)(v >> 32); fw[2 * w + 1] = (uint32_t)v;
-        }
-        fw[2 * a.wpr] = 0; fw[2 * a.wpr + 1] = 0;
-        lens[slot] = L; ridx[slot] = (uint32_t)i;
-        make_revcomp(SharedWords{fw}, fw + a.nw, L, (int)a.nw);   // here every lane is busy; in a mixed scan round only the p = 1 lanes would be
+        sts32(fw + 8 * a.wpr, 0);
+        sts16(a_lens + 2 * slot, L); sts32(fw + rs4 - 4, (uint32_t)i);
+        make_revcomp_s(SmemWords{fw}, rc, (int)L, (int)nw);   // here every lane is busy; in a mixed scan round only the p = 1 lanes would be
         m_reads++;
         const bool primary = fl & HLAC_FLAG_PRIMARY;
         if (!primary) m_nonprim++;
@@ -205,9 +288,17 @@ __global__ void __launch_bounds__(MAP_THREADS, MINB) k_count_map_q(const CountMa
       }
       __syncwarp();
       nfree -= c; cur += c;
+      if (TMA) {
+        st_next += c;
+        if (st_next == st_n && fl_first < hi) {   // tile handed out: request the next one, it lands during the rounds that follow
+          fl_n = (uint32_t)min((uint64_t)32, hi - fl_first);
+          if (lane == 0) bulk_g2s(a_stage, a.rec + fl_first * (a.wpr + 1), fl_n * rec_bytes, a_bar);
+          fl_first += fl_n;
+        }
+      }
       const unsigned bk = __ballot_sync(0xFFFFFFFFu, keep), bd = __ballot_sync(0xFFFFFFFFu, lane < c && !keep);
-      if (keep) qs[ns + __popc(bk & below)] = (uint8_t)slot;                 // p = 0
-      if (lane < c && !keep) fr[nfree + __popc(bd & below)] = (uint8_t)slot;
+      if (keep) sts8(a_qs + ns + __popc(bk & below), slot);                 // p = 0
+      if (lane < c && !keep) sts8(a_fr + nfree + __popc(bd & below), slot);
       ns += __popc(bk); nfree += __popc(bd);
       __syncwarp();
     } else if (what == 1) {
@@ -217,27 +308,27 @@ __global__ void __launch_bounds__(MAP_THREADS, MINB) k_count_map_q(const CountMa
       bool found = false;
       unsigned slot = 0, p = 0;
       if (task) {
-        const unsigned e = qs[qb + lane];
+        const unsigned e = lds8(a_qs + qb + lane);
         slot = e & 63u; p = e >> 6;
-        uint32_t* fw = rows + slot * a.row_stride;
-        const int L = lens[slot];
-        SharedWords rd{(p & 1) ? fw + a.nw : fw};
+        const uint32_t fw = wb + slot * rs4, rc = fw + nw * 4;
+        const int L = (int)lds16(a_lens + 2 * slot);
+        SmemWords rd{(p & 1) ? rc : fw};
         const DevIndexView& ix = p < 2 ? a.cds : a.gen;
         int pos = 0; uint32_t node = 0, off = 0;
         if (L >= K) {
-          if (SMEM_BM) found = find_seed<STRIDE>(ix, rd, BitmapShared{smem + (p < 2 ? 0 : a.cds.bitmap_words)}, pos, L - K, node, off, n_tests, n_probes);
+          if (SMEM_BM) found = find_seed<STRIDE>(ix, rd, SmemBitmap{p < 2 ? bm_cds : bm_gen}, pos, L - K, node, off, n_tests, n_probes);
           else found = find_seed<STRIDE>(ix, rd, BitmapGlobal{ix.bitmap}, pos, L - K, node, off, n_tests, n_probes);
         }
-        if (found) { seed_node[slot] = node; seed_info[slot] = (off << 12) | ((uint32_t)pos << 2) | p; }
+        if (found) { sts32(fw + 8 * a.wpr, node); sts32(rc + 8 * a.wpr, (off << 12) | ((uint32_t)pos << 2) | p); }
       }
       __syncwarp();
       ns = qb;
       const bool again = task && !found && p < 3, dead = task && !found && p == 3;
       const unsigned bf = __ballot_sync(0xFFFFFFFFu, task && found), bn = __ballot_sync(0xFFFFFFFFu, again),
                      bz = __ballot_sync(0xFFFFFFFFu, dead);
-      if (task && found) qw[nwk + __popc(bf & below)] = (uint8_t)slot;
-      if (again) qs[ns + __popc(bn & below)] = (uint8_t)(slot | ((p + 1) << 6));
-      if (dead) fr[nfree + __popc(bz & below)] = (uint8_t)slot;             // all four None (mapping.rs:791-793)
+      if (task && found) sts8(a_qw + nwk + __popc(bf & below), slot);
+      if (again) sts8(a_qs + ns + __popc(bn & below), slot | ((p + 1) << 6));
+      if (dead) sts8(a_fr + nfree + __popc(bz & below), slot);             // all four None (mapping.rs:791-793)
       nwk += __popc(bf); ns += __popc(bn); nfree += __popc(bz);
       if (lane == 0) m_none += __popc(bz);
       __syncwarp();
@@ -249,19 +340,20 @@ __global__ void __launch_bounds__(MAP_THREADS, MINB) k_count_map_q(const CountMa
       uint64_t key = 0;
       unsigned slot = 0;
       if (task) {
-        slot = qw[qb + lane];
-        const uint64_t i = ridx[slot];
-        const uint32_t info = seed_info[slot];
+        slot = lds8(a_qw + qb + lane);
+        const uint32_t fw = wb + slot * rs4, rc = fw + nw * 4;
+        const uint64_t i = lds32(fw + rs4 - 4);
+        const uint32_t info = lds32(rc + 8 * a.wpr), node = lds32(fw + 8 * a.wpr);
         const int p = (int)(info & 3u), pos = (int)((info >> 2) & 1023u);
-        const uint32_t off = info >> 12, node = seed_node[slot];
-        uint32_t* fw = rows + slot * a.row_stride;
-        const int L = lens[slot];
+        const uint32_t off = info >> 12;
+        const int L = (int)lds16(a_lens + 2 * slot);
         const DevIndexView& ix = p < 2 ? a.cds : a.gen;
-        SharedWords rd{(p & 1) ? fw + a.nw : fw};
+        SmemWords rd{(p & 1) ? rc : fw};
         CountVis vis;
         uint32_t cov;
-        if (SMEM_BM) cov = walk_from_seed<STRIDE>(ix, rd, BitmapShared{smem + (p < 2 ? 0 : a.cds.bitmap_words)}, L, pos, node, off, vis, n_tests, n_probes);
-        else cov = walk_from_seed<STRIDE>(ix, rd, BitmapGlobal{ix.bitmap}, L, pos, node, off, vis, n_tests, n_probes);
+        if (IDX_SMEM) cov = walk_from_seed<STRIDE>(ix, SmemGraph{p < 2 ? g_cds_nodes : g_gen_nodes, p < 2 ? g_cds_seq : g_gen_seq}, rd, SmemBitmap{p < 2 ? bm_cds : bm_gen}, L, pos, node, off, vis, n_tests, n_probes);
+        else if (SMEM_BM) cov = walk_from_seed<STRIDE>(ix, GlobalGraph{ix.nodes, ix.seq32}, rd, SmemBitmap{p < 2 ? bm_cds : bm_gen}, L, pos, node, off, vis, n_tests, n_probes);
+        else cov = walk_from_seed<STRIDE>(ix, GlobalGraph{ix.nodes, ix.seq32}, rd, BitmapGlobal{ix.bitmap}, L, pos, node, off, vis, n_tests, n_probes);
         const bool good = cov > MIN_SCORE_COUNT_PSEUDO;
         if (good) { if (p < 2) m_cds++; else m_gen++; }
         if (p == 0 || good) code = vis.code();   // a CDS-forward hit is used whatever its coverage (mapping.rs:772-775)
@@ -276,7 +368,7 @@ __global__ void __launch_bounds__(MAP_THREADS, MINB) k_count_map_q(const CountMa
       }
       __syncwarp();
       nwk = qb;
-      if (task) fr[nfree + lane] = (uint8_t)slot;
+      if (task) sts8(a_fr + nfree + lane, slot);
       nfree += cnt;
       if (code != CODE_NONE5) bucket_append(a.bk, key);
       __syncwarp();
@@ -553,9 +645,9 @@ struct hlac_count {
   bool reduced = false;
   uint32_t cell_bits = 1;
   uint32_t cfg_wpr = 0;
-  int cfg_occ = 0, cfg_threads = 0;
-  bool cfg_bm = false;
-  void* cfg_kern = nullptr; void* cfg_kern_packed = nullptr;
+  int cfg_occ = 0;
+  const void* cfg_shape = nullptr;
+  bool cfg_tma_fits = false, last_tma = false; size_t last_smem = 0;
   int group_occ = 0;
   uint64_t fallbacks = 0;                // finishes that had to take the sort path
   hlac_comm* comm = nullptr; int comm_root = -1;
@@ -623,14 +715,17 @@ struct hlac_count {
   }
 
   using Kern = void (*)(const CountMapArgs);
-  struct Shape { bool bm; int threads; Kern k, k_packed; };
+  // launch shapes: (bitmaps in shared memory?, threads per block, slots per warp, index graphs in shared memory?) with the
+  // three input variants (five arrays, packed records, packed records through the bulk prefetch)
+  struct Shape { bool bm; int threads, ns; bool idx; Kern k, k_packed, k_tma; };
   template <int S>
   static const Shape* shapes(int& n) {
-    // measured best first (profiles/r01_count_map_tuning.md): 1024 resident threads per SM with the l-mer bitmaps in
-    // shared memory; the L1 variants take over when the bitmaps do not fit next to the read slots
+    // in order of preference (measured on config 2, profiles/r02_count_map_tuning.md); the first one that fits is used
     static const Shape sh[] = {
-#define HLAC_QSHAPE(BM, TT, MB) {BM, TT, k_count_map_q<BM, TT, MB, false, S>, k_count_map_q<BM, TT, MB, true, S>}
-        HLAC_QSHAPE(true, 1024, 1), HLAC_QSHAPE(true, 512, 2), HLAC_QSHAPE(false, 256, 4), HLAC_QSHAPE(false, 128, 8),
+#define HLAC_QSHAPE(BM, TT, MB, NSL, IDX) {BM, TT, NSL, IDX, k_count_map_q<BM, TT, MB, false, S, false, NSL, IDX>, k_count_map_q<BM, TT, MB, true, S, false, NSL, IDX>, \
+                                          k_count_map_q<BM, TT, MB, true, S, true, NSL, IDX>}
+        HLAC_QSHAPE(true, 1024, 1, 64, true), HLAC_QSHAPE(true, 1024, 1, 48, true), HLAC_QSHAPE(true, 1024, 1, 56, false), HLAC_QSHAPE(true, 1024, 1, 64, false),
+        HLAC_QSHAPE(true, 1024, 1, 40, false), HLAC_QSHAPE(true, 512, 2, 64, false), HLAC_QSHAPE(false, 256, 4, 64, false), HLAC_QSHAPE(false, 128, 8, 64, false),
 #undef HLAC_QSHAPE
     };
     n = (int)(sizeof sh / sizeof sh[0]);
@@ -647,42 +742,56 @@ struct hlac_count {
     a.cds = cds->view; a.gen = gen->view;
     a.cds.nodes = reinterpret_cast<const uint4*>(nodes_cds.p); a.gen.nodes = reinterpret_cast<const uint4*>(nodes_gen.p);
     a.seq = b.seq; a.len = b.len; a.cell = b.cell; a.umi = b.umi; a.flags = b.flags;
-    a.n = b.n; a.wpr = b.words_per_read; a.nw = 2 * b.words_per_read + 2; a.row_stride = (2 * a.nw) | 1;
+    a.n = b.n; a.wpr = b.words_per_read; a.nw = map_nw(a.wpr); a.row_stride = map_row_stride(a.wpr);
     a.primary_only = primary_only; a.n_cells = n_cells; a.cell_bits = cell_bits;
     a.bk = store(); a.metrics = counters.p + 1;
     a.codes = want_codes ? codes.p : nullptr;
     a.rec = rec;
     // launch shape: (bitmaps in shared memory?, threads per block); HLAC_COUNT_SHAPE="smem,threads" overrides for tuning runs
-    auto smem_for = [&](bool bm, int threads) {
-      const size_t per_warp_words = (size_t)64 * a.row_stride + 64 * 3 + 64 / 2 + 3 * 64 / 4;
-      return (bm ? bitmap_smem_bytes : 0) + (threads / 32) * per_warp_words * 4;
+    // the bulk (TMA) prefetch needs 16-byte record granularity: (wpr + 1) even, a 16-byte aligned record array. It is opt-in
+    // (HLAC_COUNT_TMA=1): its staging tiles come out of the L1 carve-out and it was measured slower on config 2.
+    const char* tma_env = getenv("HLAC_COUNT_TMA");
+    const bool tma_ok = rec && (a.wpr & 1) && ((uintptr_t)rec & 15) == 0 && tma_env && atoi(tma_env) != 0;
+    const size_t idx_bytes = (size_t)12 * 4 * (cds->view.n_nodes + gen->view.n_nodes) + align16(cds->view.seq_words * 4) + align16(gen->view.seq_words * 4);
+    auto smem_for = [&](const Shape& sh, bool tma) {
+      return (sh.bm ? (bitmap_smem_bytes + 15) & ~(size_t)15 : 0) + (sh.idx ? idx_bytes : 0) + (size_t)(sh.threads / 32) * map_warp_bytes(a.wpr, tma, sh.ns);
     };
     if (cfg_wpr != b.words_per_read) {
       int ns = 0;
       const Shape* sh = stride == 3 ? shapes<3>(ns) : shapes<1>(ns);
       const Shape* pick = nullptr;
-      int want_bm = -1, want_t = 0;
-      if (const char* e = getenv("HLAC_COUNT_SHAPE")) sscanf(e, "%d,%d", &want_bm, &want_t);
+      int want_bm = -1, want_t = 0, want_ns = 64, want_idx = 0;   // HLAC_COUNT_SHAPE="smem,threads,slots,idx" forces a shape (tuning runs)
+      if (const char* e = getenv("HLAC_COUNT_SHAPE")) sscanf(e, "%d,%d,%d,%d", &want_bm, &want_t, &want_ns, &want_idx);
       for (int i = 0; i < ns; i++) {
-        if (want_bm >= 0) { if ((int)sh[i].bm != want_bm || sh[i].threads != want_t) continue; }
+        if (want_bm >= 0) { if ((int)sh[i].bm != want_bm || sh[i].threads != want_t || sh[i].ns != want_ns || (int)sh[i].idx != want_idx) continue; }
         else if (sh[i].bm != smem_bm) continue;
         if (sh[i].bm && !smem_bm) continue;
-        if (smem_for(sh[i].bm, sh[i].threads) > 227 * 1024) continue;
+        if (smem_for(sh[i], false) > 227 * 1024) continue;
         pick = &sh[i]; break;
       }
       if (!pick) throw Error(HLAC_ERR_LIMIT, "no launch shape of the count kernel fits (reads too long, or bad HLAC_COUNT_SHAPE)");
-      cfg_bm = pick->bm; cfg_threads = pick->threads; cfg_kern = (void*)pick->k; cfg_kern_packed = (void*)pick->k_packed;
-      const int smem = (int)smem_for(cfg_bm, cfg_threads);
-      HLAC_CUDA(cudaFuncSetAttribute(pick->k_packed, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      HLAC_CUDA(cudaFuncSetAttribute(pick->k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      HLAC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cfg_occ, pick->k, cfg_threads, smem));
+      cfg_shape = pick;
+      cfg_tma_fits = smem_for(*pick, true) <= 227 * 1024;
+      HLAC_CUDA(cudaFuncSetAttribute(pick->k_packed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(*pick, false)));
+      HLAC_CUDA(cudaFuncSetAttribute(pick->k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(*pick, false)));
+      if (cfg_tma_fits) HLAC_CUDA(cudaFuncSetAttribute(pick->k_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(*pick, true)));
+      HLAC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cfg_occ, pick->k, pick->threads, smem_for(*pick, false)));
       if (cfg_occ < 1) throw Error(HLAC_ERR_LIMIT, "count map kernel does not fit on the device");
+      if (cfg_tma_fits) {
+        int occ_t = 0;
+        HLAC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_t, pick->k_tma, pick->threads, smem_for(*pick, true)));
+        if (occ_t < cfg_occ) cfg_tma_fits = false;   // never trade resident warps for the prefetch
+      }
       cfg_wpr = b.words_per_read;
     }
-    Kern kern = (Kern)(rec ? cfg_kern_packed : cfg_kern);
-    const size_t smem = smem_for(cfg_bm, cfg_threads);
+    const Shape& shp = *(const Shape*)cfg_shape;
+    const int cfg_threads = shp.threads;
+    const bool tma = tma_ok && cfg_tma_fits;
+    Kern kern = rec ? (tma ? shp.k_tma : shp.k_packed) : shp.k;
+    const size_t smem = smem_for(shp, tma);
     const uint64_t need = (b.n + (uint64_t)cfg_threads * 2 - 1) / ((uint64_t)cfg_threads * 2);
     const unsigned grid = (unsigned)std::min<uint64_t>(need, (uint64_t)n_sm * cfg_occ);
+    last_tma = tma; last_smem = smem;
     Ev& e = begin(0);
     kern<<<grid, cfg_threads, smem, stream>>>(a);
     HLAC_CUDA(cudaGetLastError());
@@ -1087,6 +1196,18 @@ int hlac_count_probe_stats(hlac_count* s, uint64_t* bitmap_tests, uint64_t* dict
   HLAC_CUDA(cudaStreamSynchronize(s->stream));
   if (bitmap_tests) *bitmap_tests = c[0];
   if (dict_probes) *dict_probes = c[1];
+  return HLAC_OK;
+} catch (const Error& e) { set_last_error(e.what()); return e.code; } catch (const std::exception& e) { set_last_error(e.what()); return HLAC_ERR_STATE; }
+
+// the launch shape the map kernel last ran with, as text: "smem_bitmaps=1 threads=1024 slots=64 idx_smem=1 tma=0 smem_bytes=..."
+int hlac_count_shape(hlac_count* s, char* out, size_t cap) try {
+  if (!s || !out || cap == 0) throw Error(HLAC_ERR_ARG, "null argument");
+  const hlac_count::Shape* sh = (const hlac_count::Shape*)s->cfg_shape;
+  char buf[256];
+  if (!sh) snprintf(buf, sizeof buf, "none (nothing pushed yet)");
+  else snprintf(buf, sizeof buf, "smem_bitmaps=%d threads=%d slots=%d idx_smem=%d tma=%d smem_bytes=%zu blocks_per_sm=%d stride=%d", (int)sh->bm, sh->threads, sh->ns,
+                (int)sh->idx, (int)s->last_tma, s->last_smem, s->cfg_occ, s->stride);
+  snprintf(out, cap, "%s", buf);
   return HLAC_OK;
 } catch (const Error& e) { set_last_error(e.what()); return e.code; } catch (const std::exception& e) { set_last_error(e.what()); return HLAC_ERR_STATE; }
 

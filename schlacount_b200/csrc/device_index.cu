@@ -38,4 +38,5 @@ void hlac_index::upload(int dev) {
   view.lmer = host.lmer;
   view.bitmap_words = (uint32_t)host.bitmap.size();
   view.n_nodes = nn;
+  view.seq_words = (uint32_t)host.seq32.size();
 }

@@ -34,6 +34,7 @@ struct DevIndexView {
   uint32_t lmer;
   uint32_t bitmap_words;
   uint32_t n_nodes;
+  uint32_t seq_words;        // u32 words of seq32 (incl. the padding the 16-base extraction may read)
 };
 
 // (w[i] : w[i+1]) << 2*(pos%16), high word: the 16 bases starting at `pos`
@@ -54,10 +55,49 @@ __device__ __forceinline__ uint32_t base_at(P w, int pos) {
   return (w[pos >> 4] >> (30 - 2 * (pos & 15))) & 3u;
 }
 
+// Shared memory through explicit 32-bit shared-window addresses (ld.shared / st.shared). With ordinary pointers into an
+// `extern __shared__` array and the register file full (64 registers x 1024 threads), ptxas re-materialises the window base
+// (S2R SR_CgaCtaId + MOV + LEA) at every use - inside the seed-scan loop that was 3 of 28 instructions per l-mer test and
+// an S2R latency on the critical path of each iteration (SASS of the r01 kernel). An address computed once with
+// __cvta_generic_to_shared stays a plain register.
+__device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds16(uint32_t a) { uint16_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint2 lds64(uint32_t a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
+__device__ __forceinline__ uint4 lds128(uint32_t a) { uint4 v; asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v; }
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((uint16_t)v) : "memory"); }
+__device__ __forceinline__ void sts8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+struct SmemWords {   // a row of u32 words at shared address a
+  uint32_t a;
+  __device__ __forceinline__ uint32_t operator[](int i) const { return lds32(a + 4u * (uint32_t)i); }
+};
+struct SmemBitmap {
+  uint32_t a;
+  __device__ __forceinline__ uint32_t operator()(uint32_t i) const { return lds32(a + 4u * i); }
+};
+
 // read-only global words through the non-coherent path
 struct GWords {
   const uint32_t* p;
   __device__ __forceinline__ uint32_t operator[](int i) const { return __ldg(p + i); }
+};
+
+// Where a walk reads node records and node sequences from: the read-only global path (L1 / L2), or - for the small
+// indexes of known-genotype counting - a copy staged in shared memory next to the l-mer bitmaps.
+struct GlobalGraph {
+  const uint4* nodes; const uint32_t* seq32;
+  __device__ __forceinline__ uint4 n0(uint32_t node) const { return __ldg(nodes + 3 * (size_t)node); }
+  __device__ __forceinline__ uint4 ra(uint32_t node) const { return __ldg(nodes + 3 * (size_t)node + 1); }
+  __device__ __forceinline__ uint4 la(uint32_t node) const { return __ldg(nodes + 3 * (size_t)node + 2); }
+  __device__ __forceinline__ GWords seq() const { return GWords{seq32}; }
+};
+struct SmemGraph {
+  uint32_t a_nodes, a_seq;
+  __device__ __forceinline__ uint4 n0(uint32_t node) const { return lds128(a_nodes + 48u * node); }
+  __device__ __forceinline__ uint4 ra(uint32_t node) const { return lds128(a_nodes + 48u * node + 16u); }
+  __device__ __forceinline__ uint4 la(uint32_t node) const { return lds128(a_nodes + 48u * node + 32u); }
+  __device__ __forceinline__ SmemWords seq() const { return SmemWords{a_seq}; }
 };
 
 __device__ __forceinline__ bool dict_get(const DevIndexView& ix, uint64_t kmer, uint32_t& node, uint32_t& off) {
@@ -85,32 +125,36 @@ __device__ __forceinline__ bool find_seed(const DevIndexView& ix, RD rd, BM bm, 
   const int l = (int)ix.lmer;
   const int sh = 32 - 2 * l;
   const int o0 = K - l;
-  int o = o0;
+  int q = pos + o0;   // read position of the l-mer under test: right to left inside the window [pos, pos + K)
   // one flat loop, one l-mer test per iteration (no nested per-window loop: lanes of a warp advance independently)
   while (pos <= last) {
-    const uint32_t v = ext16(rd, pos + o) >> sh;
+    const uint32_t v = ext16(rd, q) >> sh;
     n_tests++;
-    if (!((bm(v >> 5) >> (v & 31)) & 1u)) { pos += S == 1 ? o + 1 : ((o + S) / S) * S; o = o0; continue; }   // no k-mer can cover this l-mer
-    if (o != 0) { o = o > l ? o - l : 0; continue; }
+    if (!((bm(v >> 5) >> (v & 31)) & 1u)) {   // no k-mer can cover this l-mer: every window up to q is ruled out
+      pos = S == 1 ? q + 1 : pos + ((q - pos + S) / S) * S;
+      q = pos + o0;
+      continue;
+    }
+    if (q != pos) { q = max(q - l, pos); continue; }
     n_probes++;
     if (dict_get(ix, kmer48(rd, pos), node, off)) return true;
     pos += S;
-    o = o0;
+    q = pos + o0;
   }
   return false;
 }
 
 // Left extension: only when the first seed sits at or beyond floor(0.2*L). Walks the read
 // leftwards from the seed through predecessor nodes; returns the coverage it adds and visits the nodes it enters.
-template <typename RD, typename V>
-__device__ __forceinline__ int left_extend(const DevIndexView& ix, RD rd, int L, int pos, uint32_t node, uint32_t off, const uint4& n0, V& vis) {
+template <typename G, typename RD, typename V>
+__device__ __forceinline__ int left_extend(G gr, RD rd, int L, int pos, uint32_t node, uint32_t off, const uint4& n0, V& vis) {
   int cov = 0;
   if (pos >= (L * LEFT_EXTEND_NUM) / LEFT_EXTEND_DEN) {
     int lp = pos - 1;
     uint32_t pn = node;
     uint4 p0 = n0;
     int po = off > 0 ? (int)off - 1 : 0;
-    GWords ns{ix.seq32};
+    const auto ns = gr.seq();
     for (;;) {
       const int m = min(lp + 1, po + 1);
       int matched = 0, snp = 0;
@@ -125,11 +169,11 @@ __device__ __forceinline__ int left_extend(const DevIndexView& ix, RD rd, int L,
       if (lp + 1 - matched == 0 || brk) break;
       lp -= matched;
       const uint32_t b = base_at(rd, lp);
-      const uint4 la = __ldg(ix.nodes + 3 * (size_t)pn + 2);
+      const uint4 la = gr.la(pn);
       const uint32_t nxt = b == 0 ? la.x : b == 1 ? la.y : b == 2 ? la.z : la.w;
       if (nxt == NONE32) break;
       pn = nxt;
-      p0 = __ldg(ix.nodes + 3 * (size_t)pn);
+      p0 = gr.n0(pn);
       po = (int)p0.y - K;
       vis.visit(p0.w, pn);
     }
@@ -140,20 +184,20 @@ __device__ __forceinline__ int left_extend(const DevIndexView& ix, RD rd, int L,
 // map_read_to_nodes after the first seed: optional left extension, then the forward walk.
 // (pos, node, off) is the first verified seed. V::visit(colour, node) is called for every visited node in the
 // reference's push order (left-extension nodes first, then the forward walk); the last call is the class-defining node.
-template <int S, typename RD, typename BM, typename V>
-__device__ __forceinline__ uint32_t walk_from_seed(const DevIndexView& ix, RD rd, BM bm, int L, int pos, uint32_t node, uint32_t off,
+template <int S, typename G, typename RD, typename BM, typename V>
+__device__ __forceinline__ uint32_t walk_from_seed(const DevIndexView& ix, G gr, RD rd, BM bm, int L, int pos, uint32_t node, uint32_t off,
                                                    V& vis, uint32_t& n_tests, uint32_t& n_probes) {
   const int last = L - K;
   int cov = 0;
-  uint4 n0 = __ldg(ix.nodes + 3 * (size_t)node);
-  uint4 ra = __ldg(ix.nodes + 3 * (size_t)node + 1);   // right-edge table, fetched with the node so its latency hides behind the compare
-  cov += left_extend(ix, rd, L, pos, node, off, n0, vis);
+  uint4 n0 = gr.n0(node);
+  uint4 ra = gr.ra(node);   // right-edge table, fetched with the node so its latency hides behind the compare
+  cov += left_extend(gr, rd, L, pos, node, off, n0, vis);
   // ---- forward walk, flattened: one loop whose body compares <= 16 bases inside the current node and then, if the node
   // is exhausted (or the per-node mismatch budget is), takes the edge or re-seeds. Equivalent to the reference's
   // node loop with an inner base loop: a hop is `pos -= K-1; cov -= K-1` followed by `pos += K; cov += K` = +1/+1,
   // the per-node budget `snp` resets at every node entry, tolerated mismatches count as covered, the breaking one
   // does not. ----
-  GWords ns{ix.seq32};
+  const auto ns = gr.seq();
   pos += K;
   cov += K;
   vis.visit(n0.w, node);
@@ -186,15 +230,15 @@ __device__ __forceinline__ uint32_t walk_from_seed(const DevIndexView& ix, RD rd
     }
     if (nxt != NONE32) {                 // exact base at the node boundary selects the edge
       node = nxt;
-      n0 = __ldg(ix.nodes + 3 * (size_t)node);
-      ra = __ldg(ix.nodes + 3 * (size_t)node + 1);
+      n0 = gr.n0(node);
+      ra = gr.ra(node);
       pos += 1; cov += 1;
       g = n0.x + K; rem = (int)n0.y - K;
     } else {                             // re-seed scanning forward from the current position
       if (pos > last) break;
       if (!find_seed<S>(ix, rd, bm, pos, last, node, off, n_tests, n_probes)) break;
-      n0 = __ldg(ix.nodes + 3 * (size_t)node);
-      ra = __ldg(ix.nodes + 3 * (size_t)node + 1);
+      n0 = gr.n0(node);
+      ra = gr.ra(node);
       pos += K; cov += K;
       g = n0.x + off + K; rem = (int)n0.y - (int)off - K;
     }
@@ -211,7 +255,7 @@ __device__ __forceinline__ bool map_read_walk(const DevIndexView& ix, RD rd, BM 
   int pos = 0;
   uint32_t node = 0, off = 0;
   if (L < K || !find_seed<S>(ix, rd, bm, pos, L - K, node, off, n_tests, n_probes)) return false;
-  cov_out = walk_from_seed<S>(ix, rd, bm, L, pos, node, off, vis, n_tests, n_probes);
+  cov_out = walk_from_seed<S>(ix, GlobalGraph{ix.nodes, ix.seq32}, rd, bm, L, pos, node, off, vis, n_tests, n_probes);
   return true;
 }
 
@@ -234,6 +278,21 @@ __device__ __forceinline__ void make_revcomp(P fwd, uint32_t* rc, int L, int nw)
       out = revcomp16(ext16(fwd, 0) >> (2 * (16 - nb))) & ~(0xFFFFFFFFu >> (2 * nb));
     }
     rc[j] = out;
+  }
+}
+
+// the same, writing the row through its shared-window address
+template <typename P>
+__device__ __forceinline__ void make_revcomp_s(P fwd, uint32_t rc_addr, int L, int nw) {
+  for (int j = 0; j < nw; j++) {
+    const int st = L - 16 * (j + 1);
+    uint32_t out = 0;
+    if (st >= 0) out = revcomp16(ext16(fwd, st));
+    else if (st > -16) {
+      const int nb = 16 + st;
+      out = revcomp16(ext16(fwd, 0) >> (2 * (16 - nb))) & ~(0xFFFFFFFFu >> (2 * nb));
+    }
+    sts32(rc_addr + 4u * (uint32_t)j, out);
   }
 }
 

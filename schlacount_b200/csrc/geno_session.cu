@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(GENO_THREADS) k_geno_map(const GenoMapArgs a) 
         const int p = (int)(info & 3u), pos = (int)((info >> 2) & 1023u);
         uint32_t* fw = rows + slot * a.row_stride;
         HashVis vis;
-        const uint32_t cov = walk_from_seed<STRIDE>(a.ix, SharedWords{p ? fw + a.nw : fw}, bm, (int)lens[slot], pos, seed_node[slot], info >> 12, vis, n_tests, n_probes);
+        const uint32_t cov = walk_from_seed<STRIDE>(a.ix, GlobalGraph{a.ix.nodes, a.ix.seq32}, SharedWords{p ? fw + a.nw : fw}, bm, (int)lens[slot], pos, seed_node[slot], info >> 12, vis, n_tests, n_probes);
         vis.finish();
         a.cov[i] = cov; a.hash_a[i] = vis.a; a.hash_b[i] = vis.b; a.strand[i] = (uint8_t)p;
         some++;

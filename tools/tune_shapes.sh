@@ -1,6 +1,9 @@
 #!/bin/bash
-# tries the launch shapes of k_count_map (HLAC_COUNT_SHAPE=smem_bitmaps,R,threads[,min_blocks]) on 4 M reads;
-# results of the r01 sweep: profiles/r01_count_map_tuning.md
-for s in 1,2,1024 1,1,512 1,1,256 1,4,512 1,2,512 0,2,128 0,1,128 0,2,256 0,1,256 0,4,128; do
-  echo -n "$s  "; HLAC_COUNT_SHAPE=$s python tools/prof_step.py 4000000 4 2>&1 | tail -1 | sed -e 's/.*map_ms.: \([0-9.]*\).*/\1/'
+# tries the launch shapes of k_count_map_q (HLAC_COUNT_SHAPE=smem_bitmaps,threads,slots_per_warp,idx_in_smem; HLAC_COUNT_TMA=1 =
+# bulk-copy record prefetch) on config 2's read mix; results: profiles/r02_count_map_tuning.md
+N=${1:-10000000}
+for s in 1,1024,64,1 1,1024,48,1 1,1024,56,0 1,1024,64,0 1,1024,40,0 1,512,64,0 0,256,64,0 0,128,64,0; do
+  for t in 0 1; do
+    echo -n "shape $s tma $t  "; HLAC_COUNT_TMA=$t HLAC_COUNT_SHAPE=$s python tools/prof_step.py $N 6 2>&1 | tail -1 | sed -e 's/.*| \(smem_bitmaps.*\)/\1/'
+  done
 done
