@@ -225,9 +225,10 @@ __global__ void __launch_bounds__(MAP_THREADS, MINB) k_count_map_q(const CountMa
     int what;   // 0 walk, 1 scan, 2 refill
     if (nwk >= 32) what = 0;
     else if (ns >= 32) what = 1;
-    else if (more) what = 2;
-    else if (ns > 0) what = 1;
+    else if (more && nfree > 0) what = 2;   // (with fewer than 64 slots both queues can be short of a full round while no slot is free)
+    else if (ns >= nwk && ns > 0) what = 1;
     else if (nwk > 0) what = 0;
+    else if (ns > 0) what = 1;
     else break;
     if (what == 2) {
       // ---- refill: filters (mapping.rs:752-763) + read rows into free slots ----

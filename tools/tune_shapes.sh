@@ -4,6 +4,6 @@
 N=${1:-10000000}
 for s in 1,1024,64,1 1,1024,48,1 1,1024,56,0 1,1024,64,0 1,1024,40,0 1,512,64,0 0,256,64,0 0,128,64,0; do
   for t in 0 1; do
-    echo -n "shape $s tma $t  "; HLAC_COUNT_TMA=$t HLAC_COUNT_SHAPE=$s python tools/prof_step.py $N 6 2>&1 | tail -1 | sed -e 's/.*| \(smem_bitmaps.*\)/\1/'
+    echo -n "shape $s tma $t  "; HLAC_COUNT_TMA=$t HLAC_COUNT_SHAPE=$s timeout 90 python tools/prof_step.py $N 6 2>&1 | tail -1 | sed -e 's/.*| \(smem_bitmaps.*\)/\1/'
   done
 done
