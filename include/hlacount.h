@@ -269,6 +269,14 @@ typedef struct {
   uint64_t* off; /* n_paths + 1 */
   uint32_t* colours;
 } hlac_paths;
+/* Multi-GPU genotyping inside the library (collective: every rank calls hlac_geno_finish*): reads are partitioned by
+ * barcode and pushed with their global ordinals (hlac_batch.ordinal); with a communicator attached hlac_geno_finish_begin
+ * all-gathers the ranks' distinct colour paths, builds their union on the device (hash table keyed by the path hash;
+ * first-seen ordinals by min, read counts by sum, colour paths compared on every duplicate), resolves only the union paths
+ * this rank owns (hash mod n_ranks) and all-gathers the class fingerprints, and all-reduces the per-class UMI histogram, so
+ * every rank returns the tables of the whole run. hlac_geno_export_paths / hlac_paths_merge / hlac_geno_import_paths below
+ * are the same merge done by the caller through host memory (no communicator needed). */
+int hlac_geno_attach_comm(hlac_geno*, hlac_comm* comm);
 int hlac_geno_export_paths(hlac_geno*, hlac_paths* out);
 int hlac_paths_merge(const hlac_paths* parts, uint32_t n_parts, hlac_paths* out);
 int hlac_geno_import_paths(hlac_geno*, const hlac_paths* merged);

@@ -83,6 +83,16 @@ void comm_allgather(hlac_comm* c, const void* send, void* recv, size_t count_per
 void comm_broadcast(hlac_comm* c, void* buf, size_t count, int dtype, int root, cudaStream_t st) {
   HLAC_NCCL(nccl().Broadcast(buf, buf, count, dt(dtype), root, c->c, st));
 }
+void comm_allgatherv(hlac_comm* c, const void* send, void* recv, const size_t* counts, const size_t* displs, int dtype, cudaStream_t st) {
+  const size_t esz = dtype == HLAC_COMM_U32 ? 4 : dtype == HLAC_COMM_U64 ? 8 : 1;
+  HLAC_NCCL(nccl().GroupStart());
+  for (int r = 0; r < c->nranks; r++) {
+    if (counts[r] == 0) continue;
+    char* slot = (char*)recv + displs[r] * esz;
+    HLAC_NCCL(nccl().Broadcast(r == c->rank ? send : slot, slot, counts[r], dt(dtype), r, c->c, st));
+  }
+  HLAC_NCCL(nccl().GroupEnd());
+}
 }  // namespace hlac
 
 #define HLAC_API_TRY try {

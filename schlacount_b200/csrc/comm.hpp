@@ -22,4 +22,7 @@ void comm_allreduce_min(hlac_comm*, const void* send, void* recv, size_t count, 
 void comm_reduce_sum(hlac_comm*, const void* send, void* recv, size_t count, int dtype, int root, cudaStream_t);
 void comm_allgather(hlac_comm*, const void* send, void* recv, size_t count_per_rank, int dtype, cudaStream_t);
 void comm_broadcast(hlac_comm*, void* buf, size_t count, int dtype, int root, cudaStream_t);
+// variable-size all-gather: rank r contributes counts[r] elements, which land at recv + displs[r] elements on every rank
+// (one grouped launch of per-rank broadcasts). `send` is this rank's contribution (may alias its slot in recv).
+void comm_allgatherv(hlac_comm*, const void* send, void* recv, const size_t* counts, const size_t* displs, int dtype, cudaStream_t);
 }  // namespace hlac

@@ -405,79 +405,64 @@ __device__ __forceinline__ int consensus_slot(uint32_t nreads, const uint32_t f[
 // Boyer-Moore majority gene (only a gene with > 50 % of the molecule's reads can win, and the vote finds it whatever the
 // order), then the candidate's three counts — and adds 1 to the dense matrix. Nothing here depends on the order of the
 // keys, and the dense matrix is order-free, so no sort is needed.
-// The keys of a bucket are contiguous, so each bucket arrives by ONE bulk asynchronous copy (cp.async.bulk, completion on
-// an mbarrier) into one of two key buffers: the copy of the block's next bucket is issued before the current one is
-// processed and lands behind its grouping, so the global-memory latency of a bucket is paid once per block, not per bucket.
+// (A variant that brought each bucket in by one bulk asynchronous copy - cp.async.bulk + mbarrier, double-buffered so that
+// the next bucket lands behind the current one's grouping - was measured SLOWER on config 2: 0.180 vs 0.147 ms per 4.3 M keys.
+// A bucket is ~2 KB, its coalesced load costs one L2 round trip of the 20-odd a block pays, and the second key buffer takes
+// the kernel from 5 to 4 blocks per SM; the kernel is bound by its shared-memory atomics, not by the loads.)
 constexpr int GROUP_THREADS = 256;
-constexpr size_t GROUP_SMEM = 2 * BUCKET_CAP * 8 + BUCKET_CAP * 4 + 2 * BUCKET_CAP * 4 + 16;
 __global__ void __launch_bounds__(GROUP_THREADS) k_group_consensus(const BucketStore bs, uint32_t* __restrict__ dense, uint32_t nrows,
                                                                    const uint32_t* __restrict__ gene_row0, uint32_t cell_bits,
                                                                    unsigned long long* n_keys_out) {
-  extern __shared__ __align__(16) uint64_t gsm[];
-  uint64_t* kbuf = gsm;                                                  // [2][BUCKET_CAP]
-  uint32_t* lnk = reinterpret_cast<uint32_t*>(gsm + 2 * BUCKET_CAP);     // representative: head of its member list; member: next member (index + 1, 0 = end)
-  uint32_t* ht = lnk + BUCKET_CAP;                                       // [2 * BUCKET_CAP] index + 1 of the molecule's representative key
-  const uint32_t a_k = (uint32_t)__cvta_generic_to_shared(kbuf);
-  const uint32_t a_bar = (uint32_t)__cvta_generic_to_shared(ht + 2 * BUCKET_CAP);   // two mbarriers
+  __shared__ uint64_t k[BUCKET_CAP];
+  __shared__ uint32_t lnk[BUCKET_CAP];          // representative: head of its member list; member: next member (index + 1, 0 = end)
+  __shared__ uint32_t ht[2 * BUCKET_CAP];       // index + 1 of the molecule's representative key
   if (*bs.ovf_cursor) return;                   // a bucket overflowed: the host takes the sort path for this step
   const unsigned t = threadIdx.x;
-  if (t == 0) { mbar_init(a_bar, 1); mbar_init(a_bar + 8, 1); }
-  __syncthreads();
   unsigned long long my_keys = 0;
-  uint32_t b = blockIdx.x, buf = 0, phase0 = 0, phase1 = 0;
-  uint32_t n = b <= bs.mask ? min(bs.fill[b], BUCKET_CAP) : 0;
-  if (t == 0 && n) bulk_g2s(a_k, bs.keys + (size_t)b * BUCKET_CAP, (n * 8 + 15) & ~15u, a_bar);
-  while (b <= bs.mask) {
-    const uint32_t b_next = b + gridDim.x;
-    const uint32_t n_next = b_next <= bs.mask ? min(bs.fill[b_next], BUCKET_CAP) : 0;
-    // the other buffer was released by the barrier that ended the previous iteration
-    if (t == 0 && n_next) bulk_g2s(a_k + (buf ^ 1) * BUCKET_CAP * 8, bs.keys + (size_t)b_next * BUCKET_CAP, (n_next * 8 + 15) & ~15u, a_bar + (buf ^ 1) * 8);
-    if (n) {
-      const uint64_t* k = kbuf + buf * BUCKET_CAP;
-      uint32_t hsz = 64;
-      while (hsz < 2 * n) hsz <<= 1;
-      const uint32_t hmask = hsz - 1;
-      for (uint32_t i = t; i < n; i += GROUP_THREADS) lnk[i] = 0;
-      for (uint32_t i = t; i < hsz; i += GROUP_THREADS) ht[i] = 0;
-      if (t == 0) my_keys += n;
-      mbar_wait(a_bar + buf * 8, buf ? phase1 : phase0);   // this bucket's keys have landed
-      if (buf) phase1 ^= 1; else phase0 ^= 1;
-      __syncthreads();
-      for (uint32_t i = t; i < n; i += GROUP_THREADS) {
-        const uint64_t g = k[i] >> CODE_BITS;
-        uint32_t h = (uint32_t)(mix64(g) >> 32) & hmask;
-        for (;;) {
-          uint32_t cur = *(volatile uint32_t*)(ht + h);
-          if (cur == 0) { cur = atomicCAS(ht + h, 0u, i + 1); if (cur == 0) break; }   // claimed: this key represents the molecule
-          if ((k[cur - 1] >> CODE_BITS) == g) { lnk[i] = atomicExch(lnk + cur - 1, i + 1); break; }
-          h = (h + 1) & hmask;
-        }
-      }
-      __syncthreads();
-      for (uint32_t h = t; h < hsz; h += GROUP_THREADS) {
-        const uint32_t rep = ht[h];
-        if (rep == 0) continue;
-        // pass 1: majority-vote candidate gene
-        uint32_t cand = (uint32_t)(k[rep - 1] & 31u) / 3, votes = 1, nreads = 1;
-        for (uint32_t m = lnk[rep - 1]; m; m = lnk[m - 1]) {
-          const uint32_t g = (uint32_t)(k[m - 1] & 31u) / 3;
-          if (votes == 0) { cand = g; votes = 1; }
-          else if (g == cand) votes++;
-          else votes--;
-          nreads++;
-        }
-        // pass 2: the candidate's (allele 1, allele 2, gene) counts
-        uint32_t f[3] = {0, 0, 0};
-        { const uint32_t c = (uint32_t)(k[rep - 1] & 31u); if (c / 3 == cand) f[c % 3]++; }
-        for (uint32_t m = lnk[rep - 1]; m; m = lnk[m - 1]) { const uint32_t c = (uint32_t)(k[m - 1] & 31u); if (c / 3 == cand) f[c % 3]++; }
-        const int slot = consensus_slot(nreads, f);
-        if (slot < 0) continue;
-        const uint32_t cell = (uint32_t)(k[rep - 1] >> CODE_BITS) & ((1u << cell_bits) - 1u);
-        atomicAdd(dense + (size_t)cell * nrows + gene_row0[cand] + slot, 1u);
+  for (uint32_t b = blockIdx.x; b <= bs.mask; b += gridDim.x) {
+    const uint32_t n = min(bs.fill[b], BUCKET_CAP);
+    if (n == 0) continue;
+    uint32_t hsz = 64;
+    while (hsz < 2 * n) hsz <<= 1;
+    const uint32_t hmask = hsz - 1;
+    __syncthreads();                            // the previous bucket's lists have been read
+    const uint64_t* src = bs.keys + (size_t)b * BUCKET_CAP;
+    for (uint32_t i = t; i < n; i += GROUP_THREADS) { k[i] = src[i]; lnk[i] = 0; }
+    for (uint32_t i = t; i < hsz; i += GROUP_THREADS) ht[i] = 0;
+    if (t == 0) my_keys += n;
+    __syncthreads();
+    for (uint32_t i = t; i < n; i += GROUP_THREADS) {
+      const uint64_t g = k[i] >> CODE_BITS;
+      uint32_t h = (uint32_t)(mix64(g) >> 32) & hmask;
+      for (;;) {
+        uint32_t cur = *(volatile uint32_t*)(ht + h);
+        if (cur == 0) { cur = atomicCAS(ht + h, 0u, i + 1); if (cur == 0) break; }   // claimed: this key represents the molecule
+        if ((k[cur - 1] >> CODE_BITS) == g) { lnk[i] = atomicExch(lnk + cur - 1, i + 1); break; }
+        h = (h + 1) & hmask;
       }
     }
-    __syncthreads();   // everyone is done with this key buffer, the lists and the table
-    b = b_next; n = n_next; buf ^= 1;
+    __syncthreads();
+    for (uint32_t h = t; h < hsz; h += GROUP_THREADS) {
+      const uint32_t rep = ht[h];
+      if (rep == 0) continue;
+      // pass 1: majority-vote candidate gene
+      uint32_t cand = (uint32_t)(k[rep - 1] & 31u) / 3, votes = 1, nreads = 1;
+      for (uint32_t m = lnk[rep - 1]; m; m = lnk[m - 1]) {
+        const uint32_t g = (uint32_t)(k[m - 1] & 31u) / 3;
+        if (votes == 0) { cand = g; votes = 1; }
+        else if (g == cand) votes++;
+        else votes--;
+        nreads++;
+      }
+      // pass 2: the candidate's (allele 1, allele 2, gene) counts
+      uint32_t f[3] = {0, 0, 0};
+      { const uint32_t c = (uint32_t)(k[rep - 1] & 31u); if (c / 3 == cand) f[c % 3]++; }
+      for (uint32_t m = lnk[rep - 1]; m; m = lnk[m - 1]) { const uint32_t c = (uint32_t)(k[m - 1] & 31u); if (c / 3 == cand) f[c % 3]++; }
+      const int slot = consensus_slot(nreads, f);
+      if (slot < 0) continue;
+      const uint32_t cell = (uint32_t)(k[rep - 1] >> CODE_BITS) & ((1u << cell_bits) - 1u);
+      atomicAdd(dense + (size_t)cell * nrows + gene_row0[cand] + slot, 1u);
+    }
   }
   if (t == 0 && my_keys) atomicAdd(n_keys_out, my_keys);
 }
@@ -824,12 +809,9 @@ struct hlac_count {
   void enqueue_group() {
     HLAC_CUDA(cudaMemsetAsync(dense.p, 0, nd() * sizeof(uint32_t), stream));
     if (!n_buckets) return;
-    if (!group_occ) {
-      HLAC_CUDA(cudaFuncSetAttribute(k_group_consensus, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GROUP_SMEM));
-      HLAC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&group_occ, k_group_consensus, GROUP_THREADS, GROUP_SMEM));
-    }
+    if (!group_occ) HLAC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&group_occ, k_group_consensus, GROUP_THREADS, 0));
     Ev& e = begin(1);
-    k_group_consensus<<<std::min<uint32_t>(n_buckets, (uint32_t)(n_sm * std::max(group_occ, 1))), GROUP_THREADS, GROUP_SMEM, stream>>>(
+    k_group_consensus<<<std::min<uint32_t>(n_buckets, (uint32_t)(n_sm * std::max(group_occ, 1))), GROUP_THREADS, 0, stream>>>(
         store(), dense.p, rows.nrows, gene_row0.p, cell_bits, counters.p);
     HLAC_CUDA(cudaGetLastError());
     end(e);

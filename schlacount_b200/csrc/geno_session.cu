@@ -32,7 +32,9 @@
 #include <vector>
 
 #include "caller.hpp"
+#include "comm.hpp"
 #include "device_index.hpp"
+#include "scan.cuh"
 
 using namespace hlac;
 
@@ -536,22 +538,6 @@ __global__ void k_gather_classes(const uint32_t* __restrict__ vec, const uint64_
   for (uint64_t k = threadIdx.x; k < len; k += blockDim.x) out[b + k] = vec[a + k];
 }
 
-// per class: which of the (<= 128) candidate alleles it contains -> 128-bit mask; one warp per class
-__global__ void k_class_cand_mask(const uint32_t* __restrict__ vec, const uint64_t* __restrict__ src_off, const uint32_t* __restrict__ len,
-                                  uint32_t n, const uint8_t* __restrict__ cand_idx, uint64_t* mask) {
-  const uint32_t c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const unsigned lane = threadIdx.x & 31;
-  if (c >= n) return;
-  const uint32_t* v = vec + src_off[c];
-  uint64_t lo = 0, hi = 0;
-  for (uint32_t k = lane; k < len[c]; k += 32) {
-    const uint8_t ci = cand_idx[v[k]];
-    if (ci < 64) lo |= 1ull << ci; else if (ci < 128) hi |= 1ull << (ci - 64);
-  }
-  for (int o = 16; o > 0; o >>= 1) { lo |= __shfl_down_sync(0xFFFFFFFFu, lo, o); hi |= __shfl_down_sync(0xFFFFFFFFu, hi, o); }
-  if (lane == 0) { mask[2 * (size_t)c] = lo; mask[2 * (size_t)c + 1] = hi; }
-}
-
 // reads_explained[t] += reads of every class whose (sorted) member list is colour list `col` (mapping.rs:196-198)
 __global__ void k_reads_explained(const uint32_t* __restrict__ cols, const unsigned long long* __restrict__ totals, uint32_t n,
                                   const uint64_t* __restrict__ col_off, const uint32_t* __restrict__ col_tx, unsigned long long* expl) {
@@ -579,7 +565,121 @@ __global__ void k_umi_min(const uint64_t* __restrict__ keys, const uint32_t* __r
   atomicAdd(umi_hist + best, 1u);
 }
 
+// ---- multi-rank union of the interned paths, on the device (hlac_geno_attach_comm) -------------------------
+// one warp per path: its colour ids from wherever the arena holds them to their place in a compact array
+__global__ void k_pack_colours(const uint32_t* __restrict__ arena, const uint64_t* __restrict__ path_off, const uint32_t* __restrict__ path_len,
+                               const uint64_t* __restrict__ dst_off, uint32_t n, uint32_t* out) {
+  const uint32_t p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned lane = threadIdx.x & 31;
+  if (p >= n) return;
+  const uint32_t* src = arena + path_off[p];
+  uint32_t* dst = out + dst_off[p];
+  for (uint32_t k = lane; k < path_len[p]; k += 32) dst[k] = src[k];
+}
+// every gathered entry inserts its hash A; the winner of a slot leaves its entry index there (the representative)
+__global__ void k_union_insert(PathTable t, const uint64_t* __restrict__ g_hash_a, uint64_t n) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned long long key = g_hash_a[i];
+  uint64_t h = mix64(key) & t.mask;
+  for (;;) {
+    const unsigned long long cur = t.keys[h];
+    if (cur == key) return;
+    if (cur == 0) {
+      const unsigned long long old = atomicCAS(t.keys + h, 0ULL, key);
+      if (old == 0) { t.ids[h] = (uint32_t)i; return; }
+      if (old == key) return;
+    }
+    h = (h + 1) & t.mask;
+  }
+}
+// occupied slots get dense union ids (the numbering is local to a rank: nothing global depends on it)
+__global__ void k_union_number(PathTable t, uint64_t cap, unsigned long long* counter, uint32_t* rep_of_uid) {
+  const uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= cap || t.keys[h] == 0) return;
+  const uint32_t uid = (uint32_t)atomicAdd(counter, 1ULL);
+  rep_of_uid[uid] = t.ids[h];
+  t.ids[h] = uid;
+}
+struct UnionOut { uint64_t* hash_a; uint64_t* hash_b; unsigned long long* first_ord; uint32_t* count; uint64_t* path_off; uint32_t* path_len; };
+// every gathered entry folds into its union path: min of first-seen ordinals, sum of read counts; the entry must be the same
+// path as the representative (hash B, length and the colour ids themselves), else two different paths collided on hash A
+__global__ void k_union_fill(PathTable t, const uint64_t* __restrict__ g_hash_a, const uint64_t* __restrict__ g_hash_b,
+                             const unsigned long long* __restrict__ g_ord, const uint32_t* __restrict__ g_cnt, const uint32_t* __restrict__ g_len,
+                             const uint64_t* __restrict__ g_coff, const uint32_t* __restrict__ g_col, uint64_t n, const uint32_t* __restrict__ rep_of_uid,
+                             UnionOut u, unsigned long long* collisions, unsigned long long* overflow) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned long long key = g_hash_a[i];
+  uint64_t h = mix64(key) & t.mask;
+  while (t.keys[h] != key) h = (h + 1) & t.mask;
+  const uint32_t uid = t.ids[h], rep = rep_of_uid[uid];
+  atomicMin(u.first_ord + uid, g_ord[i]);
+  const uint32_t old = atomicAdd(u.count + uid, g_cnt[i]);
+  if (old + g_cnt[i] < old) atomicAdd(overflow, 1ULL);
+  if (i == rep) { u.hash_a[uid] = key; u.hash_b[uid] = g_hash_b[i]; u.path_off[uid] = g_coff[i]; u.path_len[uid] = g_len[i]; }
+  else {
+    bool bad = g_hash_b[i] != g_hash_b[rep] || g_len[i] != g_len[rep];
+    for (uint32_t k = 0; k < g_len[i] && !bad; k++) bad = g_col[g_coff[i] + k] != g_col[g_coff[rep] + k];
+    if (bad) atomicAdd(collisions, 1ULL);
+  }
+}
+// local path id -> union id
+__global__ void k_local_to_union(PathTable t, const uint64_t* __restrict__ local_hash_a, uint32_t n, uint32_t* map) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned long long key = local_hash_a[i];
+  uint64_t h = mix64(key) & t.mask;
+  while (t.keys[h] != key) h = (h + 1) & t.mask;
+  map[i] = t.ids[h];
+}
+// paths this rank resolves: hash A mod n_ranks == rank (every rank derives the same partition from the union alone)
+__global__ void k_owned_mask(const uint64_t* __restrict__ hash_a, uint32_t n, uint32_t n_ranks, uint32_t rank, const uint32_t* __restrict__ len_in, uint32_t* len_owned,
+                             uint32_t* owner_count) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t o = (uint32_t)(hash_a[i] % n_ranks);
+  len_owned[i] = o == rank ? len_in[i] : 0u;
+  atomicAdd(owner_count + o, 1u);
+}
+// an owner's resolved fingerprints, packed for the exchange: (hash A, vector hash 1, vector hash 2) per owned path
+__global__ void k_pack_fingerprints(const uint64_t* __restrict__ hash_a, const uint64_t* __restrict__ vh1, const uint64_t* __restrict__ vh2, uint32_t n, uint32_t n_ranks,
+                                    uint32_t rank, uint64_t* out, unsigned long long* cursor) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || (uint32_t)(hash_a[i] % n_ranks) != rank) return;
+  const unsigned long long at = atomicAdd(cursor, 1ULL);
+  out[3 * at] = hash_a[i]; out[3 * at + 1] = vh1[i]; out[3 * at + 2] = vh2[i];
+}
+__global__ void k_unpack_fingerprints(PathTable t, const uint64_t* __restrict__ in, uint64_t n, uint64_t* vh1, uint64_t* vh2) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned long long key = in[3 * i];
+  uint64_t h = mix64(key) & t.mask;
+  while (t.keys[h] != key) h = (h + 1) & t.mask;
+  const uint32_t uid = t.ids[h];
+  vh1[uid] = in[3 * i + 1]; vh2[uid] = in[3 * i + 2];
+}
+// per class: which of the (<= 128) candidate alleles it contains. A class vector is a permutation of the colour list of its
+// path's last node, so membership is read off that (sorted) colour list - the resolved vector itself is not needed, which
+// matters when the vector lives on another rank.
+__global__ void k_class_cand_mask_colour(const uint32_t* __restrict__ cls_colour, uint32_t n, const uint64_t* __restrict__ col_off, const uint32_t* __restrict__ col_tx,
+                                         const uint8_t* __restrict__ cand_idx, uint64_t* mask) {
+  const uint32_t c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned lane = threadIdx.x & 31;
+  if (c >= n) return;
+  const uint32_t col = cls_colour[c];
+  uint64_t lo = 0, hi = 0;
+  for (uint64_t q = col_off[col] + lane; q < col_off[col + 1]; q += 32) {
+    const uint8_t ci = cand_idx[col_tx[q]];
+    if (ci < 64) lo |= 1ull << ci; else if (ci < 128) hi |= 1ull << (ci - 64);
+  }
+  for (int o = 16; o > 0; o >>= 1) { lo |= __shfl_down_sync(0xFFFFFFFFu, lo, o); hi |= __shfl_down_sync(0xFFFFFFFFu, hi, o); }
+  if (lane == 0) { mask[2 * (size_t)c] = lo; mask[2 * (size_t)c + 1] = hi; }
+}
+
 }  // namespace
+
+static inline double now_ms() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
 
 struct hlac_geno {
   hlac_index* idx = nullptr;
@@ -607,13 +707,18 @@ struct hlac_geno {
   std::vector<uint32_t> class_of_path;
   bool finished = false;
   // between hlac_geno_finish_begin and _end
-  std::vector<uint64_t> fin_src_off; std::vector<uint32_t> fin_cls_len, fin_cls_reads, fin_cls_colour;   // per class, first-seen order
+  std::vector<uint64_t> fin_src_off; std::vector<uint32_t> fin_cls_len, fin_cls_reads, fin_cls_colour, fin_cls_owner;   // per class, first-seen order
   DevBuf<uint32_t> fin_hist, fin_dvec; bool fin_begun = false;
   float ms[5] = {0, 0, 0, 0, 0};   // map, intern, finish (all of it), H2D, path resolution alone
   uint64_t launches = 0;
   uint64_t res_bytes = 0, res_merges = 0, res_steps = 0, res_paths = 0;   // work of the last path resolution (hlac_geno_resolve_stats)
   struct Ev { cudaEvent_t a, b; int kind; };
   std::vector<Ev> events;
+  // multi-GPU (hlac_geno_attach_comm): the finish merges the ranks' paths, resolves 1/n of the union and sums the histograms
+  hlac_comm* comm = nullptr;
+  bool merged = false;                 // this session's entries are already the union of all ranks
+  double merge_ms = 0, exchange_ms = 0;
+  DevBuf<uint64_t> scan_tmp;
 
   ~hlac_geno() {
     for (auto& e : events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
@@ -662,12 +767,95 @@ struct hlac_geno {
     e_path_len.reserve(ne, stream, true, n_entries); e_rep.reserve(ne, stream, true, n_entries);
   }
 
+  // Phase 1 + 2 of the multi-rank finish: all-gather every rank's distinct paths (variable-size, NCCL broadcasts in one
+  // group), build the union in a fresh hash table on the device, fold first-seen ordinals (min) and read counts (sum), adopt
+  // the union as this session's entries and renumber the local records. Collective.
+  void merge_over_comm() {
+    const int N = comm_nranks(comm), R = comm_rank(comm);
+    const double t_begin = now_ms();
+    const uint64_t E0 = n_entries;
+    // local colours compacted in path order
+    DevBuf<uint64_t> l_off; l_off.reserve(E0 + 1, stream);
+    exclusive_scan_u32(e_path_len.p, l_off.p, E0, scan_tmp, stream);
+    // sizes of every rank: (paths, colour ids)
+    DevBuf<uint64_t> d_sizes; d_sizes.reserve(2 * (size_t)N + 2, stream);
+    const uint64_t e0 = E0;
+    HLAC_CUDA(cudaMemcpyAsync(d_sizes.p + 2 * N, &e0, 8, cudaMemcpyHostToDevice, stream));
+    HLAC_CUDA(cudaMemcpyAsync(d_sizes.p + 2 * N + 1, l_off.p + E0, 8, cudaMemcpyDeviceToDevice, stream));
+    comm_allgather(comm, d_sizes.p + 2 * N, d_sizes.p, 2, HLAC_COMM_U64, stream);
+    std::vector<uint64_t> sizes(2 * (size_t)N);
+    HLAC_CUDA(cudaMemcpyAsync(sizes.data(), d_sizes.p, sizes.size() * 8, cudaMemcpyDeviceToHost, stream));
+    HLAC_CUDA(cudaStreamSynchronize(stream));
+    std::vector<size_t> ecnt(N), edis(N), ccnt(N), cdis(N);
+    uint64_t T = 0, C = 0;
+    for (int r = 0; r < N; r++) { ecnt[r] = sizes[2 * r]; edis[r] = T; T += ecnt[r]; ccnt[r] = sizes[2 * r + 1]; cdis[r] = C; C += ccnt[r]; }
+    if (T >= 0xFFFFFFFFull) throw Error(HLAC_ERR_LIMIT, "too many paths over all ranks");
+    DevBuf<uint32_t> l_col; l_col.reserve(std::max<uint64_t>(sizes[2 * R + 1], 1), stream);
+    if (E0) k_pack_colours<<<(unsigned)(((uint64_t)E0 * 32 + 255) / 256), 256, 0, stream>>>(arena.p, e_path_off.p, e_path_len.p, l_off.p, (uint32_t)E0, l_col.p);
+    // gathered arrays
+    DevBuf<uint64_t> g_a, g_b, g_coff; DevBuf<unsigned long long> g_ord; DevBuf<uint32_t> g_cnt, g_len, g_col;
+    g_a.reserve(std::max<uint64_t>(T, 1), stream); g_b.reserve(std::max<uint64_t>(T, 1), stream); g_ord.reserve(std::max<uint64_t>(T, 1), stream);
+    g_cnt.reserve(std::max<uint64_t>(T, 1), stream); g_len.reserve(std::max<uint64_t>(T, 1), stream); g_col.reserve(std::max<uint64_t>(C, 1), stream);
+    g_coff.reserve(T + 1, stream);
+    comm_allgatherv(comm, e_hash_a.p, g_a.p, ecnt.data(), edis.data(), HLAC_COMM_U64, stream);
+    comm_allgatherv(comm, e_hash_b.p, g_b.p, ecnt.data(), edis.data(), HLAC_COMM_U64, stream);
+    comm_allgatherv(comm, e_first_ord.p, g_ord.p, ecnt.data(), edis.data(), HLAC_COMM_U64, stream);
+    comm_allgatherv(comm, e_count.p, g_cnt.p, ecnt.data(), edis.data(), HLAC_COMM_U32, stream);
+    comm_allgatherv(comm, e_path_len.p, g_len.p, ecnt.data(), edis.data(), HLAC_COMM_U32, stream);
+    comm_allgatherv(comm, l_col.p, g_col.p, ccnt.data(), cdis.data(), HLAC_COMM_U32, stream);
+    exclusive_scan_u32(g_len.p, g_coff.p, T, scan_tmp, stream);   // ranks are concatenated in the same order in both arrays
+    // the union table
+    uint64_t cap = 1u << 16;
+    while (cap < T * 2) cap <<= 1;
+    DevBuf<unsigned long long> nk; DevBuf<uint32_t> ni, rep_of_uid, l2u; DevBuf<unsigned long long> cnts;
+    nk.reserve(cap, stream); ni.reserve(cap, stream); rep_of_uid.reserve(std::max<uint64_t>(T, 1), stream); cnts.reserve(4, stream);
+    HLAC_CUDA(cudaMemsetAsync(nk.p, 0, cap * sizeof(unsigned long long), stream));
+    HLAC_CUDA(cudaMemsetAsync(cnts.p, 0, 4 * sizeof(unsigned long long), stream));
+    PathTable nt{nk.p, ni.p, cap - 1};
+    if (T) k_union_insert<<<(unsigned)((T + 255) / 256), 256, 0, stream>>>(nt, g_a.p, T);
+    k_union_number<<<(unsigned)((cap + 255) / 256), 256, 0, stream>>>(nt, cap, cnts.p, rep_of_uid.p);
+    unsigned long long c4[4];
+    HLAC_CUDA(cudaMemcpyAsync(c4, cnts.p, sizeof c4, cudaMemcpyDeviceToHost, stream));
+    HLAC_CUDA(cudaStreamSynchronize(stream));
+    const uint64_t U = c4[0];
+    DevBuf<uint64_t> u_a, u_b, u_off; DevBuf<unsigned long long> u_ord; DevBuf<uint32_t> u_cnt, u_len, u_rep;
+    const size_t un = std::max<uint64_t>(U, 1);
+    u_a.reserve(un, stream); u_b.reserve(un, stream); u_off.reserve(un, stream); u_ord.reserve(un, stream); u_cnt.reserve(un, stream); u_len.reserve(un, stream); u_rep.reserve(un, stream);
+    HLAC_CUDA(cudaMemsetAsync(u_ord.p, 0xFF, un * 8, stream));
+    HLAC_CUDA(cudaMemsetAsync(u_cnt.p, 0, un * 4, stream));
+    HLAC_CUDA(cudaMemsetAsync(u_rep.p, 0, un * 4, stream));
+    if (T) k_union_fill<<<(unsigned)((T + 255) / 256), 256, 0, stream>>>(nt, g_a.p, g_b.p, g_ord.p, g_cnt.p, g_len.p, g_coff.p, g_col.p, T, rep_of_uid.p,
+                                                                        UnionOut{u_a.p, u_b.p, u_ord.p, u_cnt.p, u_off.p, u_len.p}, cnts.p + 1, cnts.p + 2);
+    // local records: local path id -> union id
+    l2u.reserve(std::max<uint64_t>(E0, 1), stream);
+    if (E0) k_local_to_union<<<(unsigned)((E0 + 255) / 256), 256, 0, stream>>>(nt, e_hash_a.p, (uint32_t)E0, l2u.p);
+    if (n_records_ub) k_remap<<<(unsigned)((n_records_ub + 255) / 256), 256, 0, stream>>>(rec_path.p, n_records_ub, l2u.p);
+    if (record_reads && reads_pushed) k_remap<<<(unsigned)((reads_pushed + 255) / 256), 256, 0, stream>>>(read_path.p, reads_pushed, l2u.p);
+    HLAC_CUDA(cudaGetLastError());
+    HLAC_CUDA(cudaMemcpyAsync(c4, cnts.p, sizeof c4, cudaMemcpyDeviceToHost, stream));
+    HLAC_CUDA(cudaStreamSynchronize(stream));
+    if (c4[1]) throw Error(HLAC_ERR_STATE, "path hash collision detected while merging ranks (equal 64-bit hash A, different colour paths)");
+    if (c4[2]) throw Error(HLAC_ERR_LIMIT, "more than 2^32 reads on one path");
+    // adopt the union
+    auto take = [](auto& dst, auto& src) { std::swap(dst.p, src.p); std::swap(dst.cap, src.cap); };
+    take(e_hash_a, u_a); take(e_hash_b, u_b); take(e_path_off, u_off); take(e_first_ord, u_ord); take(e_count, u_cnt); take(e_path_len, u_len); take(e_rep, u_rep);
+    take(arena, g_col); take(t_keys, nk); take(t_ids, ni);
+    t_cap = cap; n_entries = U; arena_used = C;
+    const unsigned long long c2[2] = {U, C};
+    HLAC_CUDA(cudaMemcpyAsync(ctr.p, c2, sizeof c2, cudaMemcpyHostToDevice, stream));
+    HLAC_CUDA(cudaStreamSynchronize(stream));
+    launches += 7;
+    merged = true;
+    merge_ms = now_ms() - t_begin;
+  }
+
   void push_device(const hlac_batch& b, int forward_only) {
     if (b.n == 0) return;
     if (!b.seq || !b.len || !b.cell || !b.umi) throw Error(HLAC_ERR_ARG, "batch has a null array");
     if (b.words_per_read == 0 || b.words_per_read > 16) throw Error(HLAC_ERR_ARG, "words_per_read must be 1..16");
     if (b.n >= (1ull << 32)) throw Error(HLAC_ERR_LIMIT, "batch too large");
     finished = false;
+    if (merged) throw Error(HLAC_ERR_STATE, "this session has already merged its paths with the other ranks: no more pushes");
     const uint64_t n = b.n;
     cov.reserve(n, stream); hash_a.reserve(n, stream); hash_b.reserve(n, stream); strand.reserve(n, stream);
     ensure_table(n_entries + n);
@@ -748,6 +936,14 @@ int hlac_geno_free(hlac_geno* s) {
   return HLAC_OK;
 }
 
+int hlac_geno_attach_comm(hlac_geno* s, hlac_comm* comm) try {
+  if (!s) throw Error(HLAC_ERR_ARG, "null session");
+  if (comm && comm_device(comm) != s->device) throw Error(HLAC_ERR_ARG, "communicator and session live on different devices");
+  if (s->merged) throw Error(HLAC_ERR_STATE, "this session has already merged its paths");
+  s->comm = comm;
+  return HLAC_OK;
+} catch (const Error& e) { set_last_error(e.what()); return e.code; } catch (const std::exception& e) { set_last_error(e.what()); return HLAC_ERR_STATE; }
+
 int hlac_geno_record_reads(hlac_geno* s, int on) {
   if (!s) { set_last_error("null session"); return HLAC_ERR_ARG; }
   if (s->reads_pushed) { set_last_error("hlac_geno_record_reads must be called before the first push"); return HLAC_ERR_STATE; }
@@ -798,6 +994,11 @@ int hlac_geno_finish_begin(hlac_geno* s, uint32_t** umi_hist_device, uint64_t* n
   const bool dbg = getenv("HLAC_DEBUG_TIMING") != nullptr; double t_last = now_s();
   const HostIndex& hx = s->idx->host;
   const uint32_t nitems = (uint32_t)hx.tx_names.size();
+  // multi-GPU: every rank's paths become one union (identical on all ranks up to numbering); from here on E counts union paths
+  hlac_comm* const comm = s->comm;
+  const int n_ranks = comm ? comm_nranks(comm) : 1, my_rank = comm ? comm_rank(comm) : 0;
+  if (comm && !s->merged) s->merge_over_comm();
+  HLAC_TICK("merge paths over the ranks");
   const uint32_t E = (uint32_t)s->n_entries;
   const uint64_t R = s->n_records_ub;
   (void)nitems;
@@ -815,17 +1016,33 @@ int hlac_geno_finish_begin(hlac_geno* s, uint32_t** umi_hist_device, uint64_t* n
     HLAC_CUDA(cudaMemcpyAsync(hlen.data(), clen.p, (size_t)E * 4, cudaMemcpyDeviceToHost, s->stream));
     HLAC_CUDA(cudaMemcpyAsync(hlast.data(), clast.p, (size_t)E * 4, cudaMemcpyDeviceToHost, s->stream));
     HLAC_CUDA(cudaStreamSynchronize(s->stream));
+    // multi-GPU: this rank resolves the paths with hash A mod n_ranks == rank; olen = vector length of an owned path, else 0
+    std::vector<uint32_t> olen_store; std::vector<uint32_t> owner_count(n_ranks, 0);
+    if (comm) {
+      DevBuf<uint32_t> d_olen, d_oc; d_olen.reserve(E, s->stream); d_oc.reserve(n_ranks, s->stream);
+      HLAC_CUDA(cudaMemsetAsync(d_oc.p, 0, (size_t)n_ranks * 4, s->stream));
+      k_owned_mask<<<(E + 255) / 256, 256, 0, s->stream>>>(s->e_hash_a.p, E, (uint32_t)n_ranks, (uint32_t)my_rank, clen.p, d_olen.p, d_oc.p);
+      HLAC_CUDA(cudaGetLastError());
+      olen_store.resize(E);
+      HLAC_CUDA(cudaMemcpyAsync(olen_store.data(), d_olen.p, (size_t)E * 4, cudaMemcpyDeviceToHost, s->stream));
+      HLAC_CUDA(cudaMemcpyAsync(owner_count.data(), d_oc.p, (size_t)n_ranks * 4, cudaMemcpyDeviceToHost, s->stream));
+      HLAC_CUDA(cudaStreamSynchronize(s->stream));
+      s->launches++;
+    }
+    const std::vector<uint32_t>& olen = comm ? olen_store : hlen;
     std::vector<uint64_t> voff(E + 1, 0);
-    for (uint32_t i = 0; i < E; i++) voff[i + 1] = voff[i] + hlen[i];
+    for (uint32_t i = 0; i < E; i++) voff[i + 1] = voff[i] + olen[i];
     {   // work of this resolution, for the roofline record: merges, vector elements walked, compulsory bytes
       std::vector<uint32_t> hpl(E);
       HLAC_CUDA(cudaMemcpyAsync(hpl.data(), s->e_path_len.p, (size_t)E * 4, cudaMemcpyDeviceToHost, s->stream));
       HLAC_CUDA(cudaStreamSynchronize(s->stream));
       const uint64_t bw = ((uint64_t)hx.tx_names.size() + 31) / 32 * 4;
       s->res_bytes = s->res_merges = s->res_steps = 0; s->res_paths = E;
+      s->res_paths = 0;
       for (uint32_t i = 0; i < E; i++) {
+        if (olen[i] == 0) continue;   // resolved by another rank
         const uint64_t m = hpl[i] ? hpl[i] - 1 : 0;
-        s->res_merges += m; s->res_steps += m * hlen[i]; s->res_bytes += m * bw + (uint64_t)hpl[i] * 4 + (uint64_t)hlen[i] * 4;
+        s->res_paths++; s->res_merges += m; s->res_steps += m * hlen[i]; s->res_bytes += m * bw + (uint64_t)hpl[i] * 4 + (uint64_t)hlen[i] * 4;
       }
     }
     DevBuf<uint64_t> d_voff, d_vhash, d_vhash2;
@@ -834,7 +1051,7 @@ int hlac_geno_finish_begin(hlac_geno* s, uint32_t** umi_hist_device, uint64_t* n
     const size_t ev_res = s->begin(4);
     {
       uint32_t n_max = 1;
-      for (uint32_t i = 0; i < E; i++) n_max = std::max(n_max, hlen[i]);
+      for (uint32_t i = 0; i < E; i++) n_max = std::max(n_max, olen[i]);
       const uint32_t bitset_words = ((uint32_t)hx.tx_names.size() + 31) / 32;
       const bool narrow = hx.tx_names.size() <= 65535;   // tx ids fit in 16 bits
       auto smem_for = [&](uint32_t cap) { return (size_t)((bitset_words + 3u) & ~3u) * 4 + (size_t)((cap + 7u) & ~7u) * (narrow ? 2 + 2 + 2 : 4 + 4 + 2) + 16; };
@@ -861,7 +1078,10 @@ int hlac_geno_finish_begin(hlac_geno* s, uint32_t** umi_hist_device, uint64_t* n
         std::vector<uint32_t> caps;
         for (uint32_t cap = n_max; ; cap = (cap + 1) / 2) { caps.push_back(cap); if (cap <= 2048 || caps.size() == 4) break; }
         std::vector<std::vector<uint32_t>> groups(caps.size());
-        for (uint32_t i = 0; i < E; i++) { size_t gsel = 0; while (gsel + 1 < caps.size() && hlen[i] <= caps[gsel + 1]) gsel++; groups[gsel].push_back(i); }
+        for (uint32_t i = 0; i < E; i++) {
+          if (olen[i] == 0) continue;   // another rank's path
+          size_t gsel = 0; while (gsel + 1 < caps.size() && olen[i] <= caps[gsel + 1]) gsel++; groups[gsel].push_back(i);
+        }
         DevBuf<unsigned int> d_next; d_next.reserve(caps.size(), s->stream);
         HLAC_CUDA(cudaMemsetAsync(d_next.p, 0, caps.size() * 4, s->stream));
         std::vector<std::unique_ptr<DevBuf<uint32_t>>> d_ids;
@@ -883,12 +1103,28 @@ int hlac_geno_finish_begin(hlac_geno* s, uint32_t** umi_hist_device, uint64_t* n
         HLAC_CUDA(cudaStreamSynchronize(s->stream));   // d_next / d_ids go out of scope
       } else {
         if (force && std::string(force) == "par") throw Error(HLAC_ERR_LIMIT, "HLAC_RESOLVE=par but the class vectors do not fit in shared memory");
+        if (comm) throw Error(HLAC_ERR_LIMIT, "the sequential path resolution (class vectors beyond shared memory, or HLAC_RESOLVE=seq) is single-GPU only");
         k_resolve_paths<<<(E + 127) / 128, 128, 0, s->stream>>>(s->arena.p, s->e_path_off.p, s->e_path_len.p, s->idx->col_off.p, s->idx->col_tx.p, E,
                                                                d_voff.p, s->fin_dvec.p, d_vhash.p, d_vhash2.p);
       }
     }
     HLAC_CUDA(cudaGetLastError());
     s->end(ev_res);
+    if (comm) {   // every rank contributes the fingerprints (hash A, vector hash pair) of the paths it resolved
+      const double t0 = now_ms();
+      std::vector<size_t> cnt3(n_ranks), dis3(n_ranks); size_t tot = 0;
+      for (int r = 0; r < n_ranks; r++) { cnt3[r] = (size_t)owner_count[r] * 3; dis3[r] = tot; tot += cnt3[r]; }
+      DevBuf<uint64_t> d_send, d_all; DevBuf<unsigned long long> d_cur;
+      d_send.reserve(std::max<size_t>(cnt3[my_rank], 1), s->stream); d_all.reserve(std::max<size_t>(tot, 1), s->stream); d_cur.reserve(1, s->stream);
+      HLAC_CUDA(cudaMemsetAsync(d_cur.p, 0, 8, s->stream));
+      k_pack_fingerprints<<<(E + 255) / 256, 256, 0, s->stream>>>(s->e_hash_a.p, d_vhash.p, d_vhash2.p, E, (uint32_t)n_ranks, (uint32_t)my_rank, d_send.p, d_cur.p);
+      comm_allgatherv(comm, d_send.p, d_all.p, cnt3.data(), dis3.data(), HLAC_COMM_U64, s->stream);
+      k_unpack_fingerprints<<<(unsigned)((tot / 3 + 255) / 256), 256, 0, s->stream>>>(s->table(), d_all.p, tot / 3, d_vhash.p, d_vhash2.p);
+      HLAC_CUDA(cudaGetLastError());
+      HLAC_CUDA(cudaStreamSynchronize(s->stream));
+      s->launches += 2;
+      s->exchange_ms = now_ms() - t0;
+    }
     s->end(ev);
     s->launches += 2;
     std::vector<uint64_t> vhash(E), vhash2(E), ford(E); std::vector<uint32_t> cnt(E);
@@ -915,7 +1151,8 @@ int hlac_geno_finish_begin(hlac_geno* s, uint32_t** umi_hist_device, uint64_t* n
       tmp_cls[p] = found;
       rep_of_path[p] = classes[found].rep;
     }
-    {
+    if (!comm) {   // (with several ranks the representative's vector may live on another rank: identity then rests on the
+                   // 128-bit vector hash + length + last colour alone)
       DevBuf<uint32_t> d_rep; DevBuf<unsigned long long> d_bad;
       d_rep.upload(rep_of_path.data(), E, s->stream); d_bad.reserve(1, s->stream);
       HLAC_CUDA(cudaMemsetAsync(d_bad.p, 0, 8, s->stream));
@@ -927,18 +1164,28 @@ int hlac_geno_finish_begin(hlac_geno* s, uint32_t** umi_hist_device, uint64_t* n
       s->launches++;
       if (bad) throw Error(HLAC_ERR_STATE, "class vector hash collision detected");
     }
+    std::vector<uint64_t> hhash;   // multi-GPU: a class is represented by its path with the smallest hash A (the same path on every
+                                   // rank whatever the local numbering), whose owner holds the class vector
+    if (comm) {
+      hhash.resize(E);
+      HLAC_CUDA(cudaMemcpyAsync(hhash.data(), s->e_hash_a.p, (size_t)E * 8, cudaMemcpyDeviceToHost, s->stream));
+      HLAC_CUDA(cudaStreamSynchronize(s->stream));
+      for (uint32_t p = 0; p < E; p++) { Cls& c = classes[tmp_cls[p]]; if (hhash[p] < hhash[c.rep]) c.rep = p; }
+    }
     std::vector<uint32_t> order(classes.size());
     for (uint32_t i = 0; i < order.size(); i++) order[i] = i;
     std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return classes[a].ord < classes[b].ord; });
     std::vector<uint32_t> rank(classes.size());
     for (uint32_t r = 0; r < order.size(); r++) rank[order[r]] = r;
     cls_reads.resize(classes.size()); s->fin_cls_colour.resize(classes.size()); s->fin_src_off.resize(classes.size()); s->fin_cls_len.resize(classes.size());
+    s->fin_cls_owner.assign(classes.size(), 0);
     for (uint32_t c = 0; c < classes.size(); c++) {
       const uint32_t r = classes[c].rep;
       s->fin_cls_colour[rank[c]] = hlast[r];
-      s->fin_src_off[rank[c]] = voff[r];
+      s->fin_src_off[rank[c]] = voff[r];   // (valid on the rank that owns the representative)
       s->fin_cls_len[rank[c]] = hlen[r];
       cls_reads[rank[c]] = classes[c].reads;
+      if (comm) s->fin_cls_owner[rank[c]] = (uint32_t)(hhash[r] % (uint64_t)n_ranks);
     }
     for (uint32_t p = 0; p < E; p++) s->class_of_path[p] = rank[tmp_cls[p]];
     n_classes_out = classes.size();
@@ -967,6 +1214,11 @@ int hlac_geno_finish_begin(hlac_geno* s, uint32_t** umi_hist_device, uint64_t* n
   }
   HLAC_TICK("sort records + umi min");
   if (!E) { s->fin_hist.reserve(1, s->stream); HLAC_CUDA(cudaMemsetAsync(s->fin_hist.p, 0, 4, s->stream)); HLAC_CUDA(cudaStreamSynchronize(s->stream)); }
+  if (comm) {   // every (barcode, UMI) group is complete on one rank (reads are partitioned by barcode): the histograms add up
+    comm_allreduce_sum(comm, s->fin_hist.p, s->fin_hist.p, std::max<size_t>(n_classes_out, 1), HLAC_COMM_U32, s->stream);
+    HLAC_CUDA(cudaStreamSynchronize(s->stream));
+    HLAC_TICK("all-reduce of the UMI histogram");
+  }
   s->fin_begun = true;
   if (umi_hist_device) *umi_hist_device = s->fin_hist.p;
   if (n_classes) *n_classes = n_classes_out;
@@ -1003,11 +1255,39 @@ int hlac_geno_finish_end(hlac_geno* s, hlac_class_tables* out) try {
   else out->reads_tx = (uint32_t*)malloc(std::max<uint64_t>(ntx, 1) * 4);
   if (nc) {
     DevBuf<uint64_t> d_src, d_dst; DevBuf<uint32_t> d_out;
-    if (!s->lean) {
+    if (!s->lean && !s->comm) {
       d_src.upload(s->fin_src_off.data(), nc, s->stream); d_dst.upload(out->reads_off, nc + 1, s->stream); d_out.reserve(std::max<uint64_t>(ntx, 1), s->stream);
       k_gather_classes<<<(unsigned)nc, 256, 0, s->stream>>>(s->fin_dvec.p, d_src.p, d_dst.p, d_out.p);
       HLAC_CUDA(cudaGetLastError());
       HLAC_CUDA(cudaMemcpyAsync(out->reads_tx, d_out.p, ntx * 4, cudaMemcpyDeviceToHost, s->stream));
+    } else if (!s->lean) {
+      // multi-GPU: a class vector lives on the rank that resolved the class's representative path. Every rank packs the
+      // vectors it holds (in class order), one variable-size all-gather brings them together, a second gather puts them in
+      // class order.
+      const int N = comm_nranks(s->comm), Rk = comm_rank(s->comm);
+      std::vector<size_t> cnt(N, 0), dis(N, 0);
+      std::vector<uint64_t> pack_src, pack_dst, all_src(nc);
+      for (size_t c = 0; c < nc; c++) {
+        const uint32_t o = s->fin_cls_owner[c];
+        all_src[c] = cnt[o];   // offset inside the owner's block, made absolute below
+        if ((int)o == Rk) { pack_src.push_back(s->fin_src_off[c]); pack_dst.push_back(cnt[o]); }
+        cnt[o] += s->fin_cls_len[c];
+      }
+      size_t tot = 0; for (int r = 0; r < N; r++) { dis[r] = tot; tot += cnt[r]; }
+      for (size_t c = 0; c < nc; c++) all_src[c] += dis[s->fin_cls_owner[c]];
+      pack_dst.push_back(cnt[Rk]);
+      DevBuf<uint64_t> d_ps, d_pd; DevBuf<uint32_t> d_pack, d_all;
+      d_pack.reserve(std::max<size_t>(cnt[Rk], 1), s->stream); d_all.reserve(std::max<size_t>(tot, 1), s->stream);
+      if (pack_src.size()) {
+        d_ps.upload(pack_src.data(), pack_src.size(), s->stream); d_pd.upload(pack_dst.data(), pack_dst.size(), s->stream);
+        k_gather_classes<<<(unsigned)pack_src.size(), 256, 0, s->stream>>>(s->fin_dvec.p, d_ps.p, d_pd.p, d_pack.p);
+      }
+      comm_allgatherv(s->comm, d_pack.p, d_all.p, cnt.data(), dis.data(), HLAC_COMM_U32, s->stream);
+      d_src.upload(all_src.data(), nc, s->stream); d_dst.upload(out->reads_off, nc + 1, s->stream); d_out.reserve(std::max<uint64_t>(ntx, 1), s->stream);
+      k_gather_classes<<<(unsigned)nc, 256, 0, s->stream>>>(d_all.p, d_src.p, d_dst.p, d_out.p);
+      HLAC_CUDA(cudaGetLastError());
+      HLAC_CUDA(cudaMemcpyAsync(out->reads_tx, d_out.p, ntx * 4, cudaMemcpyDeviceToHost, s->stream));
+      HLAC_CUDA(cudaStreamSynchronize(s->stream));   // the packing buffers go out of scope
     }
     // reads_explained (mapping.rs:196-198): per colour totals, then one pass over the used colour lists on the device
     std::map<uint32_t, unsigned long long> per_colour;
@@ -1078,10 +1358,9 @@ int hlac_geno_call(hlac_geno* s, const hlac_class_tables* t, const double* theta
   if (nc && !rk.cands.empty()) {
     std::vector<uint8_t> cand_idx(t->nitems, 0xFF);
     for (size_t k = 0; k < rk.cands.size(); k++) cand_idx[rk.cands[k]] = (uint8_t)k;
-    DevBuf<uint8_t> d_ci; DevBuf<uint64_t> d_src, d_mask; DevBuf<uint32_t> d_len;
-    d_ci.upload(cand_idx.data(), cand_idx.size(), s->stream); d_src.upload(s->fin_src_off.data(), nc, s->stream);
-    d_len.upload(s->fin_cls_len.data(), nc, s->stream); d_mask.reserve(2 * nc, s->stream);
-    k_class_cand_mask<<<(unsigned)((nc * 32 + 255) / 256), 256, 0, s->stream>>>(s->fin_dvec.p, d_src.p, d_len.p, (uint32_t)nc, d_ci.p, d_mask.p);
+    DevBuf<uint8_t> d_ci; DevBuf<uint64_t> d_mask; DevBuf<uint32_t> d_col;
+    d_ci.upload(cand_idx.data(), cand_idx.size(), s->stream); d_col.upload(s->fin_cls_colour.data(), nc, s->stream); d_mask.reserve(2 * nc, s->stream);
+    k_class_cand_mask_colour<<<(unsigned)((nc * 32 + 255) / 256), 256, 0, s->stream>>>(d_col.p, (uint32_t)nc, s->idx->col_off.p, s->idx->col_tx.p, d_ci.p, d_mask.p);
     HLAC_CUDA(cudaGetLastError());
     HLAC_CUDA(cudaMemcpyAsync(mask.data(), d_mask.p, 2 * nc * 8, cudaMemcpyDeviceToHost, s->stream));
     HLAC_CUDA(cudaStreamSynchronize(s->stream));
