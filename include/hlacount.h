@@ -145,6 +145,7 @@ int hlac_index_from_fasta(const char* fasta_path, const char* allele_status, int
 int hlac_index_from_sequences(const uint64_t* packed, const uint64_t* seq_word_start, const uint32_t* seq_len,
                               const char* const* names, uint32_t n_seq, int device, hlac_index** out);
 int hlac_index_clone(const hlac_index* src, int device, hlac_index** out); /* the same index resident on another device */
+int hlac_index_device(const hlac_index*);                                  /* CUDA ordinal, -1 = host-only handle */
 int hlac_index_free(hlac_index*);
 /* utils::write_obj(&index, hla_index) (hla.rs:260): the bincode Pseudoaligner<Kmer24> the reference reads with -i,
  * including its three boomphf tables (host work, no device needed) */
@@ -341,6 +342,12 @@ int hlac_geno_eqclassdb(hlac_geno*, const hlac_class_tables* t, const uint32_t* 
                         uint64_t n_reads, const uint64_t* bc_off, const uint8_t* bc_bytes, uint32_t n_bc,
                         const uint64_t* umi_off, const uint8_t* umi_bytes, uint32_t n_umi, hlac_eqclassdb* out);
 
+/* the same from explicit per-read class ids (first-seen eq_class ids as hlac_geno_read_class_ids returns them, 0xFFFFFFFF =
+ * not counted), e.g. assembled by a driver that spread the reads over several sessions */
+int hlac_eqclassdb_from_ids(const hlac_class_tables* t, const uint32_t* class_ids, const uint32_t* read_bc, const uint32_t* read_umi,
+                            uint64_t n_reads, const uint64_t* bc_off, const uint8_t* bc_bytes, uint32_t n_bc,
+                            const uint64_t* umi_off, const uint8_t* umi_bytes, uint32_t n_umi, hlac_eqclassdb* out);
+
 /* ---- the three reference entry points, whole (host driver in C++; BAM/FASTA I/O on the host) ---------------------- */
 /* mapping_wrapper(hla_index, outdir, bam, locus, use_unmapped) -> counts file path (mapping.rs:310-316).
  * region: samtools-style "chr:start-end" or NULL. The counts file is the reference's: bincode of EqClassDb
@@ -362,6 +369,10 @@ int hlac_map_and_count_pseudo(const char* bam, const char* out_dir, const char* 
 int hlac_map_and_count_pseudo_multi(const char* bam, const char* out_dir, const char* barcodes_path, const char* region,
                                     const char* cds, const char* genomic, int primary_only, const int* devices, int n_devices,
                                     hlac_coo* entries, hlac_metrics* metrics, uint32_t* n_cells_out);
+/* mapping_wrapper on several GPUs of one box (sc_hla_count --devices): one genotyping session per device, reads routed by
+ * barcode with their stream ordinals, hlac_geno_attach_comm merges inside the finish; the counts file is the same. */
+int hlac_mapping_wrapper_multi(const char* hla_index, const char* outdir, const char* bam, const char* region, int use_unmapped,
+                               const int* devices, int n_devices, char* counts_path_out, size_t cap);
 /* host BAM reader self-check (BamSeqReader, mapping.rs:231-279): count of CB+UB records in the selection and an
  * FNV-1a checksum over (2-bit sequence, CB, UB, primary) in file order; region NULL = the unmapped tail ("*") */
 int hlac_bam_scan(const char* bam, const char* region, uint64_t* n_records, uint64_t* checksum);

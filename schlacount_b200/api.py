@@ -419,6 +419,11 @@ class GenoSession:
         self._n_last = n
 
     # ---- multi-GPU merge ----
+    def attach_comm(self, comm):
+        """hlac_geno_attach_comm: finish() / finish_begin() then merge with the other ranks inside the library (collective)"""
+        check(lib().hlac_geno_attach_comm(self.h, comm.h if comm is not None else None))
+        self._comm = comm
+
     def export_paths(self):
         """-> dict of numpy arrays (hash_a, hash_b, first_ord, count, off, colours): picklable, for an all-gather"""
         p = _lib.Paths()

@@ -134,6 +134,8 @@ int hlac_index_clone(const hlac_index* src, int device, hlac_index** out) {
   HLAC_API_END
 }
 
+int hlac_index_device(const hlac_index* ix) { return ix ? ix->device : -1; }
+
 int hlac_index_free(hlac_index* ix) {
   if (ix) { if (ix->device >= 0) cudaSetDevice(ix->device); delete ix; }
   return HLAC_OK;

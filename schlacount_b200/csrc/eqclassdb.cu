@@ -259,12 +259,22 @@ int hlac_eqclassdb_counts(const hlac_eqclassdb* db, uint32_t nitems, int device,
 int hlac_geno_eqclassdb(hlac_geno* s, const hlac_class_tables* t, const uint32_t* read_bc, const uint32_t* read_umi, uint64_t n_reads,
                         const uint64_t* bc_off, const uint8_t* bc_bytes, uint32_t n_bc, const uint64_t* umi_off, const uint8_t* umi_bytes,
                         uint32_t n_umi, hlac_eqclassdb* out) {
-  HLAC_API_TRY
-  if (!s || !t || !out || (n_reads && (!read_bc || !read_umi)) || !bc_off || !umi_off) throw Error(HLAC_ERR_ARG, "null argument");
-  if (!t->reads_off || !t->reads_tx) throw Error(HLAC_ERR_STATE, "the tables are lean: counts_reads (the class vectors) is not on the host");
-  if (t->n_read_classes >= NONE32) throw Error(HLAC_ERR_LIMIT, "too many classes");
+  if (!s) { set_last_error("null argument"); return HLAC_ERR_ARG; }
   std::vector<uint32_t> ids(std::max<uint64_t>(n_reads, 1));
   { const int rc = hlac_geno_read_class_ids(s, ids.data(), n_reads); if (rc != HLAC_OK) return rc; }
+  return hlac_eqclassdb_from_ids(t, ids.data(), read_bc, read_umi, n_reads, bc_off, bc_bytes, n_bc, umi_off, umi_bytes, n_umi, out);
+}
+
+// the same from explicit per-read class ids (first-seen eq_class ids, 0xFFFFFFFF = read not counted): what a driver that
+// spread the reads over several sessions assembles from their hlac_geno_read_class_ids
+int hlac_eqclassdb_from_ids(const hlac_class_tables* t, const uint32_t* class_ids, const uint32_t* read_bc, const uint32_t* read_umi, uint64_t n_reads,
+                            const uint64_t* bc_off, const uint8_t* bc_bytes, uint32_t n_bc, const uint64_t* umi_off, const uint8_t* umi_bytes,
+                            uint32_t n_umi, hlac_eqclassdb* out) {
+  HLAC_API_TRY
+  if (!t || !out || (n_reads && (!read_bc || !read_umi || !class_ids)) || !bc_off || !umi_off) throw Error(HLAC_ERR_ARG, "null argument");
+  if (!t->reads_off || !t->reads_tx) throw Error(HLAC_ERR_STATE, "the tables are lean: counts_reads (the class vectors) is not on the host");
+  if (t->n_read_classes >= NONE32) throw Error(HLAC_ERR_LIMIT, "too many classes");
+  const uint32_t* ids = class_ids;
   memset(out, 0, sizeof *out);
   struct Guard { hlac_eqclassdb* d; bool ok = false; ~Guard() { if (!ok) hlac_eqclassdb_free(d); } } guard{out};
   // ids in first-counted order, like EqClassDb::count (mapping.rs:128-163)

@@ -328,18 +328,31 @@ constexpr size_t BATCH_READS = 1 << 20;
 
 namespace {
 
-// mapping_wrapper's body (mapping.rs:320-404) on an index that is already resident on the device
-std::string mapping_impl(hlac_index* index, const char* outdir, const char* bam, const char* region, int use_unmapped) {
+// mapping_wrapper's body (mapping.rs:320-404) on an index that is already resident on the device(s). With several devices
+// (index[d] resident on device d) reads are routed by barcode (first-seen barcode id % n) with their stream ordinals, every
+// device runs its own session, and the sessions merge inside hlac_geno_finish through a communicator.
+std::string mapping_impl(const std::vector<hlac_index*>& index, const char* outdir, const char* bam, const char* region, int use_unmapped) {
   info("Mapping reads from BAM to database");
-  GenoHandle g; check(hlac_geno_new(index, &g.p));
+  const size_t nd = index.size();
+  std::vector<GenoHandle> g(nd);
+  struct CommHandle { hlac_comm* p = nullptr; ~CommHandle() { if (p) hlac_comm_free(p); } };
+  std::vector<CommHandle> comms(nd);
+  for (size_t d = 0; d < nd; d++) check(hlac_geno_new(index[d], &g[d].p));
+  if (nd > 1) {
+    std::vector<int> devs(nd); std::vector<hlac_comm*> raw(nd, nullptr);
+    for (size_t d = 0; d < nd; d++) { hlac_index_info unused; (void)unused; devs[d] = hlac_index_device(index[d]); }
+    check(hlac_comm_init_all(devs.data(), (int)nd, raw.data()));
+    for (size_t d = 0; d < nd; d++) { comms[d].p = raw[d]; check(hlac_geno_attach_comm(g[d].p, raw[d])); }
+    info("Genotyping on " + std::to_string(nd) + " GPUs: reads routed by barcode, paths merged over NCCL");
+  }
   // The hand-over file is the reference's own: bincode of EqClassDb (mapping.rs:84-90,403), so that either side of the pair
-  // mapping_wrapper / em_wrapper can be the reference's. It needs the per-read class ids from the session and the barcode /
+  // mapping_wrapper / em_wrapper can be the reference's. It needs the per-read class ids from the session(s) and the barcode /
   // UMI strings of every read from here. HLAC_COUNTS_FORMAT=tables writes this library's compact table format instead
   // (the three tables, no per-read triples), which only hlac_em_wrapper reads.
   const char* fmt = getenv("HLAC_COUNTS_FORMAT");
   const bool bincode = !fmt || std::string(fmt) == "bincode";
   if (fmt && !bincode && std::string(fmt) != "tables") throw Error(HLAC_ERR_ARG, "HLAC_COUNTS_FORMAT must be 'tables' or 'bincode'");
-  if (bincode) check(hlac_geno_record_reads(g.p, 1));
+  if (bincode) for (size_t d = 0; d < nd; d++) check(hlac_geno_record_reads(g[d].p, 1));
   std::vector<uint32_t> read_bc, read_umi;             // bincode only: per read, index into bc_names / umi_names
   std::vector<std::string> bc_names, umi_names;
   std::unordered_map<std::string, uint32_t> umi_idx;
@@ -358,13 +371,16 @@ std::string mapping_impl(hlac_index* index, const char* outdir, const char* bam,
     }
     return id;
   };
-  BatchBuilder bb(BATCH_READS);
+  std::vector<std::unique_ptr<BatchBuilder>> bbs;
+  std::vector<BatchBuilder*> lanes;
+  for (size_t d = 0; d < nd; d++) { bbs.emplace_back(new BatchBuilder(BATCH_READS, true, nd > 1)); lanes.push_back(bbs.back().get()); }
   std::string counts = outdir;   // PathBuf::set_extension("counts.bin") (mapping.rs:328-329)
   { size_t slash = counts.rfind('/'), dot = counts.rfind('.');
     if (dot != std::string::npos && (slash == std::string::npos || dot > slash) && dot != slash + 1) counts.erase(dot);
     counts += ".counts.bin"; }
   auto report = [&](const char* what, uint64_t rid) {
-    uint64_t some = 0, lng = 0; check(hlac_geno_stats(g.p, &some, &lng, nullptr, nullptr, nullptr));
+    uint64_t some = 0, lng = 0;
+    for (size_t d = 0; d < nd; d++) { uint64_t a = 0, b = 0; check(hlac_geno_stats(g[d].p, &a, &b, nullptr, nullptr, nullptr)); some += a; lng += b; }
     info("analyzed " + std::to_string(rid) + what + " reads. Mapped " + std::to_string(some) + ", used " + std::to_string(lng) +
          " with score at least " + std::to_string(MIN_SCORE_CALL));
   };
@@ -373,24 +389,49 @@ std::string mapping_impl(hlac_index* index, const char* outdir, const char* bam,
   // barcodes seen in earlier chunks are resolved on the parser threads (read-only lookups; inserts only happen in the ordered
   // append, between two parallel stages); the bincode hand-over needs every record to pass through cell_of
   auto cell_try = [&](StrRef cb) { if (bincode) return CELL_UNKNOWN; auto it = bc_ids.find(cb.str()); return it == bc_ids.end() ? CELL_UNKNOWN : it->second; };
-  uint64_t rid = stream_records(reader, bb, cell_of, [&] { hlac_batch b = bb.batch(); check(hlac_geno_push(g.p, &b, 0)); }, false, cell_try);
+  auto route = [nd](uint32_t cell, uint64_t) { return (size_t)(cell % nd); };
+  uint64_t rid = stream_records_routed(reader, lanes, route, cell_of, [&](size_t d) { hlac_batch b = lanes[d]->batch(); check(hlac_geno_push(g[d].p, &b, 0)); }, false, cell_try);
   report("", rid);
   if (use_unmapped) {
     reader.fetch_unmapped();
-    uint64_t rid2 = stream_records(reader, bb, cell_of, [&] { hlac_batch b = bb.batch(); check(hlac_geno_push(g.p, &b, 1)); }, false, cell_try);
+    for (auto* l : lanes) l->ordinal_base = rid;   // the unmapped pass continues the stream
+    uint64_t rid2 = stream_records_routed(reader, lanes, route, cell_of, [&](size_t d) { hlac_batch b = lanes[d]->batch(); check(hlac_geno_push(g[d].p, &b, 1)); }, false, cell_try);
     report(" unaligned", rid2);
   }
   hlac_class_tables t{};
-  check(hlac_geno_finish(g.p, &t));
   struct Free { hlac_class_tables* t; ~Free() { hlac_class_tables_free(t); } } fr{&t};
+  if (nd == 1) check(hlac_geno_finish(g[0].p, &t));
+  else {   // the finish is a collective: one host thread per device; device 0's tables are the result
+    std::vector<std::future<void>> fut;
+    std::vector<std::string> errs(nd);
+    std::vector<int> rcs(nd, HLAC_OK);
+    for (size_t d = 1; d < nd; d++)
+      fut.push_back(std::async(std::launch::async, [&, d] {
+        hlac_class_tables td{}; rcs[d] = hlac_geno_finish(g[d].p, &td); if (rcs[d] != HLAC_OK) errs[d] = hlac_last_error(); hlac_class_tables_free(&td); }));
+    rcs[0] = hlac_geno_finish(g[0].p, &t);
+    if (rcs[0] != HLAC_OK) errs[0] = hlac_last_error();
+    for (auto& f : fut) f.get();
+    for (size_t d = 0; d < nd; d++) if (rcs[d] != HLAC_OK) throw Error(rcs[d], "device " + std::to_string(d) + ": " + errs[d]);
+  }
   if (bincode) {
     auto csr = [](const std::vector<std::string>& v, std::vector<uint64_t>& off, std::string& bytes) {
       off.assign(1, 0); for (auto& x : v) { bytes += x; off.push_back(bytes.size()); } };
     std::vector<uint64_t> boff, uoff; std::string bbytes, ubytes;
     csr(bc_names, boff, bbytes); csr(umi_names, uoff, ubytes);
+    // per-read class ids in stream order: every session knows its own reads in its own push order (= stream order within a lane)
+    std::vector<uint32_t> ids(std::max<size_t>(read_bc.size(), 1));
+    if (nd == 1) { if (!read_bc.empty()) check(hlac_geno_read_class_ids(g[0].p, ids.data(), read_bc.size())); }
+    else {
+      std::vector<std::vector<uint32_t>> per(nd);
+      std::vector<uint64_t> cnt(nd, 0);
+      for (uint32_t b : read_bc) cnt[b % nd]++;
+      for (size_t d = 0; d < nd; d++) { per[d].resize(std::max<uint64_t>(cnt[d], 1)); if (cnt[d]) check(hlac_geno_read_class_ids(g[d].p, per[d].data(), cnt[d])); }
+      std::vector<uint64_t> cur(nd, 0);
+      for (size_t i = 0; i < read_bc.size(); i++) { const size_t d = read_bc[i] % nd; ids[i] = per[d][cur[d]++]; }
+    }
     hlac_eqclassdb db{};
-    check(hlac_geno_eqclassdb(g.p, &t, read_bc.data(), read_umi.data(), read_bc.size(), boff.data(), (const uint8_t*)bbytes.data(), (uint32_t)bc_names.size(),
-                              uoff.data(), (const uint8_t*)ubytes.data(), (uint32_t)umi_names.size(), &db));
+    check(hlac_eqclassdb_from_ids(&t, ids.data(), read_bc.data(), read_umi.data(), read_bc.size(), boff.data(), (const uint8_t*)bbytes.data(), (uint32_t)bc_names.size(),
+                                  uoff.data(), (const uint8_t*)ubytes.data(), (uint32_t)umi_names.size(), &db));
     struct FreeDb { hlac_eqclassdb* d; ~FreeDb() { hlac_eqclassdb_free(d); } } fdb{&db};
     check(hlac_eqclassdb_write(counts.c_str(), &db));
   } else write_tables(counts, t);
@@ -450,7 +491,22 @@ int hlac_mapping_wrapper(const char* hla_index, const char* outdir, const char* 
   info("Reading database index from disk");
   IndexHandle ix; check(hlac_index_from_idx_file(hla_index, device, &ix.p));
   info("Finished reading index!");
-  copy_out(mapping_impl(ix.p, outdir, bam, region, use_unmapped), counts_path_out, cap);
+  copy_out(mapping_impl({ix.p}, outdir, bam, region, use_unmapped), counts_path_out, cap);
+  HLAC_API_CATCH
+}
+
+int hlac_mapping_wrapper_multi(const char* hla_index, const char* outdir, const char* bam, const char* region, int use_unmapped,
+                               const int* devices, int n_devices, char* counts_path_out, size_t cap) {
+  HLAC_API_TRY
+  if (!hla_index || !outdir || !bam || !devices || n_devices < 1) throw Error(HLAC_ERR_ARG, "null argument");
+  info("Reading database index from disk");
+  std::vector<IndexHandle> ix(n_devices);
+  std::vector<hlac_index*> raw(n_devices);
+  check(hlac_index_from_idx_file(hla_index, devices[0], &ix[0].p));
+  for (int d = 1; d < n_devices; d++) check(hlac_index_clone(ix[0].p, devices[d], &ix[d].p));
+  for (int d = 0; d < n_devices; d++) raw[d] = ix[d].p;
+  info("Finished reading index!");
+  copy_out(mapping_impl(raw, outdir, bam, region, use_unmapped), counts_path_out, cap);
   HLAC_API_CATCH
 }
 
@@ -681,7 +737,10 @@ int hlac_main(int argc, const char* const* argv) {
       info("Reading database index from disk");
       check(hlac_index_from_idx_file(index.c_str(), device, &ix.p));
     }
-    const std::string counts = mapping_impl(ix.p, join(pl, "pseudoaligner").c_str(), bam.c_str(), opt["region"].c_str(), flag["unmapped"]);
+    std::vector<IndexHandle> more(devices.size());
+    std::vector<hlac_index*> ixs{ix.p};
+    for (size_t d = 1; d < devices.size(); d++) { check(hlac_index_clone(ix.p, devices[d], &more[d].p)); ixs.push_back(more[d].p); }
+    const std::string counts = mapping_impl(ixs, join(pl, "pseudoaligner").c_str(), bam.c_str(), opt["region"].c_str(), flag["unmapped"]);
     em_impl(ix.p, counts.c_str(), join(db, "hla_nuc.fasta").c_str(), join(db, "hla_gen.fasta").c_str(), pl.c_str(), device, genomic, cds);
   }
   for (auto& p : {cds, genomic}) if (!path_exists(p)) throw Error(HLAC_ERR_IO, "Input file \"" + p + "\" does not exist");

@@ -110,6 +110,75 @@ def test_count_comm_two_gpus_vs_oracle(sb, orc, root):
         assert out[1][rep][0] == (ref["entries"] if root < 0 else [])
 
 
+@pytest.mark.parametrize("lean", [False, True])
+def test_geno_comm_two_gpus_vs_oracle(sb, orc, tmp_path, lean):
+    """hlac_geno_attach_comm: mapped part + forward-only "unmapped" tail (mapping.rs:380-393) partitioned by barcode over two
+    GPUs with global ordinals; the finish merges inside the library (path union on the device over NCCL all-gathers, each rank
+    resolves the union paths it owns, fingerprints exchanged, UMI histogram all-reduced). Both ranks must return the ORACLE's
+    tables of the whole stream, first-seen class ids included, and identical EM / calls."""
+    if _n_gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    from tools import synth
+    db = str(tmp_path / "db")
+    names = synth.make_db(db, 400, 61, extra_genes=("DRB1", "DQB1"))
+    donor = [names[3], names[250], names[405], names[777], names[801], names[1100], names[1300], names[1599], names[1601], names[1999]]
+    r = synth.reads_for_db(90_000, db, donor, 800, 62, frac_cds=0.5, frac_gen=0.05)
+    r["cell"][r["cell"] == synth.NOT_A_CELL] = 7
+    n = len(r["len"])
+    tail = n - n // 4
+    fa, st = os.path.join(db, "hla_nuc.fasta"), os.path.join(db, "Allele_status.txt")
+    oix = orc.Index.from_fasta(fa, st)
+    o = orc.Geno(oix)
+    ci0, _ = o.push(r["seq"][:tail], r["len"][:tail], r["cell"][:tail], r["umi"][:tail])
+    ci1, _ = o.push(r["seq"][tail:], r["len"][tail:], r["cell"][tail:], r["umi"][tail:], forward_only=True)
+    o.finish()
+    ocid = np.concatenate([ci0, ci1])
+    ref = o.call()
+    comms = sb.Comm.init_all([0, 1])
+    ordinal = np.arange(n, dtype=np.uint64)
+    out, err = [None, None], [None, None]
+
+    def run(rank):
+        try:
+            gix = sb.Index.from_fasta(fa, st, device=rank)
+            g = sb.GenoSession(gix, record_reads=True, lean=lean)
+            g.attach_comm(comms[rank])
+            mine = []
+            for lo, hi, fo in ((0, tail, False), (tail, n, True)):
+                idx = np.nonzero((r["cell"][lo:hi] % 2) == rank)[0] + lo
+                for part in np.array_split(idx, 2):
+                    g.push(r["seq"][part], r["len"][part], r["cell"][part], r["umi"][part], forward_only=fo, ordinal=ordinal[part])
+                mine.append(idx)
+            mine = np.concatenate(mine)
+            g.finish(raw=True)
+            t = g.tables_csr()
+            theta, iters = g.squarem(device=rank)
+            out[rank] = dict(t=t, cid=g.read_class_ids(len(mine)), mine=mine, theta=theta, iters=iters, call=g.call(theta, on_device=True))
+            g.close()
+        except Exception as e:   # surface worker failures in the main thread
+            err[rank] = e
+    th = [threading.Thread(target=run, args=(k,)) for k in range(2)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    for c in comms:
+        c.close()
+    assert err == [None, None], err
+    for rank in range(2):
+        t = out[rank]["t"]
+        assert t["nreads"] == o.nreads and np.array_equal(t["reads_explained"], o.reads_explained())
+        assert H.csr_tables_equal(t["umi"], o.table_raw("umi"))
+        if lean:
+            assert t["reads"] is None
+        else:
+            assert H.csr_tables_equal(t["reads"], o.table_raw("reads"))
+        assert np.array_equal(out[rank]["cid"], ocid[out[rank]["mine"]])       # GLOBAL first-seen class ids
+        assert out[rank]["call"]["called"] == ref["called"]
+    assert out[0]["iters"] == out[1]["iters"] and np.array_equal(out[0]["theta"], out[1]["theta"])   # identical tables, deterministic EM
+    assert len(ref["called"]) >= 5
+
+
 def test_cli_devices_two_gpus(tmp_path):
     """sc_hla_count --devices 0,1 on the reference's fixture: count_matrix.mtx byte-identical to the golden
     (src/main.rs:432-466) and to the single-device run."""
@@ -124,3 +193,20 @@ def test_cli_devices_two_gpus(tmp_path):
     assert open(tmp_path / "one" / "count_matrix.mtx").read() == gold == open(tmp_path / "two" / "count_matrix.mtx").read()
     assert open(tmp_path / "one" / "summary.tsv").read() == open(tmp_path / "two" / "summary.tsv").read()
     assert "Counting on 2 GPUs" in (r.stdout + r.stderr)
+
+
+def test_cli_devices_genotyping_two_gpus(tmp_path):
+    """sc_hla_count -d <db> --devices 0,1 (test_call, src/main.rs:468-500): genotyping sessions on both GPUs merged inside
+    the finish; every output file - the bincode EqClassDb hand-over included - identical to the single-device run."""
+    if _n_gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    exe = os.path.join(H.ROOT, "schlacount_b200", "sc_hla_count")
+    for name, extra in (("one", []), ("two", ["--devices", "0,1"])):
+        args = ["-b", os.path.join(H.FIX, "test.bam"), "-d", os.path.join(H.FIX, "fake_db"), "-c", os.path.join(H.FIX, "barcodes0.tsv"),
+                "-o", str(tmp_path / name), "--pl-tmp", str(tmp_path / (name + "_p")), "-i", os.path.join(H.FIX, "fake_db", "hla_nuc.fasta.idx")]
+        r = subprocess.run([exe] + args + extra, capture_output=True, text=True, cwd=tmp_path)
+        assert r.returncode == 0, r.stdout + r.stderr
+    assert "Genotyping on 2 GPUs" in (r.stdout + r.stderr)
+    assert H.read_mtx(tmp_path / "two" / "count_matrix.mtx") == H.read_mtx(os.path.join(H.FIX, "test_call.mtx"))
+    for f in ("weights.tsv", "pairs.tsv", "cds_pseudoaln.fasta", "gen_pseudoaln.fasta", "pseudoaligner.counts.bin"):
+        assert open(tmp_path / "one_p" / f, "rb").read() == open(tmp_path / "two_p" / f, "rb").read(), f

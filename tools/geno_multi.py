@@ -1,8 +1,11 @@
 """Multi-GPU genotyping (BASELINE config 5 shape): run under torchrun, one rank per GPU.
    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/geno_multi.py [alleles_per_gene] [reads]
-Reads (incl. an unmapped-style forward-only tail) are partitioned by barcode with their global ordinals; ranks
-all-gather their distinct colour paths, adopt the union, all-reduce the per-class UMI histogram over NCCL and every
-rank runs EM + caller on identical tables. Rank 0 checks the result against a single-GPU run of the whole stream."""
+Reads (incl. an unmapped-style forward-only tail) are partitioned by barcode with their global ordinals; the sessions
+carry the library's own NCCL communicator (hlac_geno_attach_comm), so hlac_geno_finish merges by itself: path union on the
+device over all-gathers, every rank resolves the union paths it owns, fingerprints exchanged, UMI histogram all-reduced;
+every rank runs EM + caller on identical tables. HLAC_GENO_MULTI_LEGACY=1 runs the round-1 protocol instead (paths
+exported to the host, pickled through torch.distributed, merged on the host, every rank resolves everything).
+Rank 0 checks the result against a single-GPU run of the whole stream."""
 import json
 import os
 import sys
@@ -54,23 +57,39 @@ class _W:
         self.__cuda_array_interface__ = {"shape": (max(nelem, 1),), "typestr": "<i4", "data": (ptr, False), "version": 2}
 
 
+legacy = bool(os.environ.get("HLAC_GENO_MULTI_LEGACY"))
+comm = sb.Comm.from_torch_distributed(local) if (world > 1 and not legacy) else None
 g, t_push = run((cell % world) == rank)
+if world > 1:
+    dist.barrier()
+torch.cuda.synchronize()
 t0 = time.time()
-if world > 1:
-    parts = [None] * world
-    dist.all_gather_object(parts, g.export_paths())
-    n_union = g.import_merged_paths(parts)
-else:
+if comm is not None:
+    g.attach_comm(comm)
+    tab = g.finish(raw=True)
     n_union = g.stats()["n_paths"]
-ptr, nc = g.finish_begin()
-if world > 1:
-    dist.all_reduce(torch.as_tensor(_W(ptr, nc), device=dev))
-    torch.cuda.synchronize()   # the session reads the histogram back on its own stream
-tab = g.finish_end(raw=True)
+else:
+    if world > 1:
+        parts = [None] * world
+        dist.all_gather_object(parts, g.export_paths())
+        n_union = g.import_merged_paths(parts)
+    else:
+        n_union = g.stats()["n_paths"]
+    ptr, nc = g.finish_begin()
+    if world > 1:
+        dist.all_reduce(torch.as_tensor(_W(ptr, nc), device=dev))
+        torch.cuda.synchronize()   # the session reads the histogram back on its own stream
+    tab = g.finish_end(raw=True)
+torch.cuda.synchronize()
 t_fin = time.time() - t0
+if world > 1:
+    tt = torch.tensor([t_push, t_fin], device=dev, dtype=torch.float64)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_push, t_fin = float(tt[0]), float(tt[1])
 theta, iters = g.squarem(device=local)
 call = g.call(theta)
-out = dict(world=world, reads=n, alleles=len(names), push_s=t_push, merge_finish_s=t_fin, union_paths=n_union, tables=tab,
+out = dict(world=world, reads=n, alleles=len(names), protocol="legacy-host" if (legacy or world == 1) else "in-library", push_s=t_push, merge_finish_s=t_fin,
+           union_paths=n_union, resolve=g.resolve_stats(), timing=g.timing(), tables=tab,
            em_iters=iters, called=[gix.tx_names[i] for i in call["called"]])
 if rank == 0:
     ref, _ = run(np.ones(n, bool))
