@@ -8,8 +8,8 @@ appended to per-molecule hash buckets) -> k_group_consensus (shared-memory group
 (-> summed over the ranks through the library's own NCCL communicator when N > 1: hlac_count_attach_comm) -> ordered COO
 triplets + metrics written into host-mapped memory; the host synchronises once per step.
   value : reads/s with the batch already resident in HBM (timed with CUDA events on the session stream).
-  e2e   : the same through hlac_count_push_packed with pinned HOST buffers: H2D of every input byte and the result on
-          the host inside the timed region.
+  e2e   : the same through hlac_count_push_wire with pinned HOST buffers (bit-packed 28-byte records): H2D of every
+          input byte and the result on the host inside the timed region.
 N > 1: reads are partitioned by barcode, every rank maps its own 10 M-read shard (weak scaling) against
 GLOBAL column indices; hlac_count_finish merges inside the timed region (--merge reduce: dense matrices summed onto rank
 0, which extracts the whole matrix; allreduce: every rank ends with the whole matrix; none: shard-local column blocks, no
@@ -290,9 +290,9 @@ def main():
     ap.add_argument("--chunk", type=int, default=1_000_000, help="e2e push chunk in reads (0 = whole batch)")
     ap.add_argument("--genes", type=int, default=3, choices=[3, 4, 5, 6, 7, 8],
                     help="3 = the six fixture alleles (config 2); 8 = 2 synthetic alleles x 8 genes (config 4 shape)")
-    ap.add_argument("--e2e-format", default="packed", choices=["packed", "soa"],
-                    help="host input format of the end-to-end leg: packed 32-byte records (hlac_count_push_packed) or the five "
-                         "SoA arrays (hlac_count_push, 35 B/read)")
+    ap.add_argument("--e2e-format", default="wire", choices=["wire", "packed", "soa"],
+                    help="input format of both legs: wire = bit-packed 28-byte records (hlac_count_push_wire), packed = 32-byte "
+                         "records (hlac_count_push_packed), soa = the five SoA arrays (hlac_count_push, 35 B/read)")
     ap.add_argument("--merge", default="reduce", choices=["reduce", "allreduce", "none"],
                     help="N > 1: 'reduce' = global columns, the ranks' dense matrices summed onto rank 0 inside hlac_count_finish "
                          "(library-owned NCCL communicator), rank 0 extracts the whole COO; 'allreduce' = every rank ends with the "
@@ -316,7 +316,7 @@ def main():
                   "single": "", "none": ", per-rank column blocks, no data-path collective",
                   "reduce": ", one matrix assembled on rank 0: ncclReduce of the dense matrices inside hlac_count_finish",
                   "allreduce": ", every rank assembles the whole matrix: ncclAllReduce inside hlac_count_finish"}[merge]),
-              "l2": "inputs (%.0f MB/step) exceed the 126 MB L2; no explicit flush" % (args.reads * 32 / 1e6),
+              "l2": "inputs (%.0f MB/step) exceed the 126 MB L2; no explicit flush" % (args.reads * 28 / 1e6),
               "seed": SEED}
 
     if args.impl == "reference":
@@ -389,39 +389,50 @@ def main():
     def finish_step():   # ONE call: grouping + consensus (+ merge over the ranks) + COO + metrics, one host synchronisation
         return sess.finish_arrays(copy=False)
 
-    # device-resident inputs (packed records: the format the end-to-end leg ships)
+    # the same records for both legs: resident in HBM for `value`, in pinned host memory for `e2e`
     u2i = {np.dtype("uint64"): np.int64, np.dtype("uint16"): np.int16, np.dtype("uint32"): np.int32, np.dtype("uint8"): np.uint8}
-    rec_np = sb.pack_records(r["seq"], r["len"], r["cell"], r["umi"], r["flags"])
-    drec = torch.from_numpy(rec_np.view(np.int64)).to(dev)
-
-    def step_device():
-        sess.reset()
-        sess.push_packed(drec)
-        return finish_step()
-
-    # pinned host inputs
     chunk = args.chunk or n
-    if args.e2e_format == "soa":
+    fmt = args.e2e_format
+    if fmt == "soa":
+        d = {k: torch.from_numpy(v.view(u2i[v.dtype])).to(dev) for k, v in r.items()}
         h = {k: torch.from_numpy(v.view(u2i[v.dtype])).pin_memory() for k, v in r.items()}
         hn = {k: v.numpy().view(r[k].dtype) for k, v in h.items()}
         in_bytes = sum(int(v.nbytes) for v in hn.values())
-
-        def step_e2e():
-            sess.reset()
-            for a in range(0, n, chunk):
-                b = min(n, a + chunk)
-                sess.push(hn["seq"][a:b], hn["len"][a:b], hn["cell"][a:b], hn["umi"][a:b], hn["flags"][a:b])
-            return finish_step()
-    else:
+        push_dev = lambda: sess.push(d["seq"], d["len"], d["cell"], d["umi"], d["flags"])
+        push_host = lambda a, b: sess.push(hn["seq"][a:b], hn["len"][a:b], hn["cell"][a:b], hn["umi"][a:b], hn["flags"][a:b])
+        fmt_name = "five SoA arrays, %d B/read (hlac_count_push)"
+    elif fmt == "packed":
+        rec_np = sb.pack_records(r["seq"], r["len"], r["cell"], r["umi"], r["flags"])
+        drec = torch.from_numpy(rec_np.view(np.int64)).to(dev)
         hrec_t = torch.from_numpy(rec_np.view(np.int64)).pin_memory()
         hrec = hrec_t.numpy().view(np.uint64)
         in_bytes = int(hrec.nbytes)
+        push_dev = lambda: sess.push_packed(drec)
+        push_host = lambda a, b: sess.push_packed(hrec[a:b])
+        fmt_name = "packed records, %d B/read (hlac_count_push_packed)"
+    else:
+        read_len = int(r["len"][0])
+        cell_bits = max(1, int(n_cells_total).bit_length())          # columns 0..n_cells-1 and the all-ones not-a-cell value
+        umi_bits = max(1, int(r["umi"].max()).bit_length())
+        rec_np = sb.pack_wire(r["seq"], r["len"], r["cell"], r["umi"], r["flags"], read_len, cell_bits, umi_bits)
+        drec = torch.from_numpy(rec_np.view(np.int32)).to(dev)
+        hrec_t = torch.from_numpy(rec_np.view(np.int32)).pin_memory()
+        hrec = hrec_t.numpy().view(np.uint32)
+        in_bytes = int(hrec.nbytes)
+        push_dev = lambda: sess.push_wire(drec, read_len, cell_bits, umi_bits)
+        push_host = lambda a, b: sess.push_wire(hrec[a:b], read_len, cell_bits, umi_bits)
+        fmt_name = "wire records, %%d B/read (hlac_count_push_wire: %d-bp bases + primary + %d-bit cell + %d-bit UMI key)" % (read_len, cell_bits, umi_bits)
 
-        def step_e2e():
-            sess.reset()
-            for a in range(0, n, chunk):
-                sess.push_packed(hrec[a:min(n, a + chunk)])
-            return finish_step()
+    def step_device():
+        sess.reset()
+        push_dev()
+        return finish_step()
+
+    def step_e2e():
+        sess.reset()
+        for a in range(0, n, chunk):
+            push_host(a, min(n, a + chunk))
+        return finish_step()
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
@@ -527,12 +538,11 @@ def main():
                 "e2e": {"value": total_reads / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": in_bytes * world,
                         "d2h_bytes_per_step": d2h_own, "ms_per_step": e2e_ms, "h2d_ms": tm_e2e["h2d_ms"],
                         "h2d_gbs_per_gpu": in_bytes / (tm_e2e["h2d_ms"] / 1e3) / 1e9 if tm_e2e["h2d_ms"] > 0 else None,
-                        "input_format": "packed records, %d B/read (hlac_count_push_packed)" % (in_bytes // n) if args.e2e_format == "packed"
-                        else "five SoA arrays, %d B/read (hlac_count_push)" % (in_bytes // n)},
+                        "input_format": fmt_name % (in_bytes // n)},
                 # counted by the session itself (hlac_count_timing): every kernel of ours launched in one step, times the steps.
                 # No library kernel runs on the normal path (cub only sorts on the bucket-overflow fallback; fallbacks below).
                 "gpu_launches": int(tm_dev["launches"]) * args.steps, "library_launches": 0 if gstats["fallbacks"] == 0 else None,
-                "launches_per_step": int(tm_dev["launches"]), "group": gstats,
+                "launches_per_step": int(tm_dev["launches"]), "group": gstats, "map_kernel_shape": sess.shape(),
                 "kernels_ms_last_step": kern, "roofline": roof, "clocks": clocks, "clocks_e2e": clocks_e2e,
                 "wall_ms_per_step": wall_dev / args.steps * 1e3,
                 "result": {"matrix_entries": n_entries, "molecules": n_molecules, "metrics": met}, "cpus_bound": bound_cpus}
@@ -556,7 +566,6 @@ def main():
                                               "thread (the reference is single-threaded); its %d matrix entries equal the GPU's columns < %d" % (ns, k, args.cells, len(ent_cpu), k)}
     want_geno = args.geno == "on" or (args.geno == "auto" and args.genes == 3 and args.reads == N_READS)
     if want_geno and rank == 0:
-        del drec
         sess.close()
         torch.cuda.empty_cache()
         try:

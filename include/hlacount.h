@@ -84,6 +84,19 @@ typedef struct {
   uint32_t words_per_read;
 } hlac_packed_batch;
 
+/* The leanest host->device form for counting ("wire records"): end to end the path is bound by the H2D copy, so every byte
+ * counts. A batch of equal-length reads as n records of words_per_record u32 words each, a big-endian bit stream per record
+ * (bit 0 = MSB of word 0): 2 * read_len bits of bases (the device's own row layout: base j in word j / 16 at bits
+ * 31-2(j%16)..30-2(j%16)), then primary (1 bit), cell (cell_bits; all ones = not in the whitelist), UMI key (umi_bits),
+ * zero padding. A 91-bp read with a 10-bp UMI (21-bit key) and <= 131 070 columns is 7 words = 28 bytes (hlac_packed_batch:
+ * 32, the five arrays of hlac_batch: 35). hlac_pack_wire converts an hlac_batch. */
+typedef struct {
+  const uint32_t* rec; /* n * words_per_record u32 */
+  uint64_t n;
+  uint32_t read_len, cell_bits, umi_bits;
+  uint32_t words_per_record; /* hlac_wire_words(read_len, cell_bits, umi_bits) */
+} hlac_wire_batch;
+
 typedef struct { /* mapping.rs:108-116 `Metrics` */
   uint64_t num_reads, num_non_primary, num_not_cell_bc, num_cds_align, num_gen_align, num_not_aligned;
 } hlac_metrics;
@@ -121,7 +134,7 @@ typedef struct {
 const char* hlac_last_error(void);
 int hlac_device_count(int* n);
 /* sizeof of hlac_batch, hlac_metrics, hlac_coo, hlac_index_info, hlac_class_tables, hlac_paths, hlac_calls (cap >= 7)
- * and hlac_eqclassdb, hlac_packed_batch (written if cap >= 8 / 9), so that a
+ * and hlac_eqclassdb, hlac_packed_batch, hlac_wire_batch (written if cap >= 8 / 9 / 10), so that a
  * binding (Rust repr(C), ctypes) can assert its own layouts against the library it loaded */
 int hlac_abi_sizes(uint32_t* out, uint32_t cap);
 
@@ -195,6 +208,13 @@ int hlac_count_push_device(hlac_count*, const hlac_batch* device_batch);
  * DEVICE memory for _push_packed_device. Results are identical to pushing the equivalent hlac_batch. */
 int hlac_count_push_packed(hlac_count*, const hlac_packed_batch* host_batch);
 int hlac_count_push_packed_device(hlac_count*, const hlac_packed_batch* device_batch);
+/* the same push for wire records; rec is HOST memory for _push_wire, DEVICE memory for _push_wire_device */
+uint32_t hlac_wire_words(uint32_t read_len, uint32_t cell_bits, uint32_t umi_bits);
+int hlac_count_push_wire(hlac_count*, const hlac_wire_batch* host_batch);
+int hlac_count_push_wire_device(hlac_count*, const hlac_wire_batch* device_batch);
+/* host helper: hlac_batch (host pointers; every read read_len bases, cells < 2^cell_bits - 1, UMI keys < 2^umi_bits) -> wire
+ * records; rec must hold b->n * hlac_wire_words(..) u32 */
+int hlac_pack_wire(const hlac_batch* b, uint32_t read_len, uint32_t cell_bits, uint32_t umi_bits, uint32_t* rec);
 /* host helper: hlac_batch (host pointers, len <= 255, cell < HLAC_PACKED_NOT_A_CELL or HLAC_NOT_A_CELL) -> packed records;
  * rec must hold b->n * (b->words_per_read + 1) u64 */
 int hlac_pack_records(const hlac_batch* b, uint64_t* rec);

@@ -38,6 +38,11 @@ class PackedBatch(C.Structure):
     _fields_ = [("rec", C.c_void_p), ("n", C.c_uint64), ("words_per_read", C.c_uint32)]
 
 
+class WireBatch(C.Structure):
+    _fields_ = [("rec", C.c_void_p), ("n", C.c_uint64), ("read_len", C.c_uint32), ("cell_bits", C.c_uint32), ("umi_bits", C.c_uint32),
+                ("words_per_record", C.c_uint32)]
+
+
 class Metrics(C.Structure):
     _fields_ = [(k, C.c_uint64) for k in ("num_reads", "num_non_primary", "num_not_cell_bc", "num_cds_align",
                                           "num_gen_align", "num_not_aligned")]
@@ -99,6 +104,8 @@ def lib():
         L.hlac_count_row_name.argtypes = [C.c_void_p, C.c_uint32]
         L.hlac_count_nrows.restype = C.c_uint32
         L.hlac_count_nrows.argtypes = [C.c_void_p]
+        L.hlac_wire_words.restype = C.c_uint32
+        L.hlac_wire_words.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32]
         _LIB = L
     return _LIB
 

@@ -205,6 +205,15 @@ def pack_records(seq, lens, cell, umi, flags):
     return rec
 
 
+def pack_wire(seq, lens, cell, umi, flags, read_len, cell_bits, umi_bits):
+    """hlac_pack_wire: the five SoA arrays -> u32 [n, words] wire records (bases, primary, cell, UMI key as one bit stream)"""
+    b, keep = make_batch(seq, lens, cell, umi, flags)
+    words = int(lib().hlac_wire_words(read_len, cell_bits, umi_bits))
+    rec = np.zeros((int(b.n), words), dtype=np.uint32)
+    check(lib().hlac_pack_wire(C.byref(b), C.c_uint32(read_len), C.c_uint32(cell_bits), C.c_uint32(umi_bits), _vp(rec)))
+    return rec
+
+
 class CountSession:
     """hlac_count: one map_and_count_pseudo run (src/mapping.rs:640-821)."""
 
@@ -263,6 +272,22 @@ class CountSession:
             pb.words_per_read = (rec.shape[1] - 1) if words_per_read is None else words_per_read
             pb.rec = rec.data_ptr()
             check(lib().hlac_count_push_packed_device(self.h, C.byref(pb)))
+        self._keep = rec
+
+    def push_wire(self, rec, read_len, cell_bits, umi_bits, n=None):
+        """wire records (pack_wire): a numpy u32 [n, words] array = host buffer, a torch CUDA tensor = device buffer"""
+        wb = _lib.WireBatch()
+        wb.read_len, wb.cell_bits, wb.umi_bits = read_len, cell_bits, umi_bits
+        wb.words_per_record = int(lib().hlac_wire_words(read_len, cell_bits, umi_bits))
+        if isinstance(rec, np.ndarray):
+            rec = np.ascontiguousarray(rec, dtype=np.uint32)
+            wb.n = rec.shape[0] if n is None else n
+            wb.rec = rec.ctypes.data
+            check(lib().hlac_count_push_wire(self.h, C.byref(wb)))
+        else:
+            wb.n = rec.shape[0] if n is None else n
+            wb.rec = rec.data_ptr()
+            check(lib().hlac_count_push_wire_device(self.h, C.byref(wb)))
         self._keep = rec
 
     def sync(self):

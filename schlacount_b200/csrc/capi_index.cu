@@ -56,9 +56,9 @@ const char* hlac_last_error(void) { return g_last_error.c_str(); }
 // sizeof of every struct that crosses the ABI, in header order (bindings check their own layouts against this)
 int hlac_abi_sizes(uint32_t* out, uint32_t cap) {
   const uint32_t v[] = {(uint32_t)sizeof(hlac_batch), (uint32_t)sizeof(hlac_metrics), (uint32_t)sizeof(hlac_coo), (uint32_t)sizeof(hlac_index_info),
-                        (uint32_t)sizeof(hlac_class_tables), (uint32_t)sizeof(hlac_paths), (uint32_t)sizeof(hlac_calls), (uint32_t)sizeof(hlac_eqclassdb), (uint32_t)sizeof(hlac_packed_batch)};
+                        (uint32_t)sizeof(hlac_class_tables), (uint32_t)sizeof(hlac_paths), (uint32_t)sizeof(hlac_calls), (uint32_t)sizeof(hlac_eqclassdb), (uint32_t)sizeof(hlac_packed_batch), (uint32_t)sizeof(hlac_wire_batch)};
   if (!out || cap < 7) { set_last_error("hlac_abi_sizes needs room for 7 values"); return HLAC_ERR_ARG; }
-  for (uint32_t i = 0; i < 9 && i < cap; i++) out[i] = v[i];   // the 8th (hlac_eqclassdb) and 9th (hlac_packed_batch) only if the caller made room
+  for (uint32_t i = 0; i < 10 && i < cap; i++) out[i] = v[i];   // the 8th (hlac_eqclassdb) and 9th (hlac_packed_batch) only if the caller made room
   return HLAC_OK;
 }
 

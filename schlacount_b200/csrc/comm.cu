@@ -123,6 +123,12 @@ int hlac_comm_init_rank(const uint8_t id[HLAC_COMM_ID_BYTES], int rank, int nran
   auto c = std::make_unique<hlac_comm>();
   c->rank = rank; c->nranks = nranks; c->device = device;
   HLAC_NCCL(nccl().CommInitRank(&c->c, nranks, u, rank));
+  {   // NCCL connects its transports lazily, at the first collective (seconds): pay that here, not inside the first merge
+    DevBuf<uint32_t> one; one.reserve(1);
+    HLAC_CUDA(cudaMemset(one.p, 0, 4));
+    HLAC_NCCL(nccl().AllReduce(one.p, one.p, 1, ncclUint32, ncclSum, c->c, (cudaStream_t)0));
+    HLAC_CUDA(cudaStreamSynchronize(0));
+  }
   *out = c.release();
   HLAC_API_CATCH
 }
@@ -137,6 +143,16 @@ int hlac_comm_init_all(const int* devices, int n, hlac_comm** comms) {
     auto c = new hlac_comm();
     c->c = cs[i]; c->rank = i; c->nranks = n; c->device = devices[i];
     comms[i] = c;
+  }
+  {   // first collective (lazy transport setup) now: all ranks from this thread, in one group
+    std::vector<uint32_t*> bufs(n, nullptr);
+    int prev = 0; HLAC_CUDA(cudaGetDevice(&prev));
+    for (int i = 0; i < n; i++) { HLAC_CUDA(cudaSetDevice(devices[i])); HLAC_CUDA(cudaMalloc(&bufs[i], 4)); HLAC_CUDA(cudaMemset(bufs[i], 0, 4)); }
+    HLAC_NCCL(nccl().GroupStart());
+    for (int i = 0; i < n; i++) { HLAC_CUDA(cudaSetDevice(devices[i])); HLAC_NCCL(nccl().AllReduce(bufs[i], bufs[i], 1, ncclUint32, ncclSum, cs[i], (cudaStream_t)0)); }
+    HLAC_NCCL(nccl().GroupEnd());
+    for (int i = 0; i < n; i++) { HLAC_CUDA(cudaSetDevice(devices[i])); HLAC_CUDA(cudaStreamSynchronize(0)); cudaFree(bufs[i]); }
+    cudaSetDevice(prev);
   }
   HLAC_API_CATCH
 }

@@ -83,7 +83,16 @@ struct CountMapArgs {
   unsigned long long* metrics; // [6] + [2] seed-filter tests / dictionary probes + [1] out-of-range cell indices + [1] max UMI key
   uint8_t* codes;              // optional per-read debug output
   const uint64_t* rec;         // packed records (hlac_packed_batch) instead of the five arrays above, or NULL
+  const uint32_t* wire;        // wire records (hlac_wire_batch): bit-packed u32 words, or NULL
+  uint32_t wire_words, wire_len, wire_cell_bits, wire_umi_bits;
 };
+
+// nbits (1..32) of a big-endian bit stream held in u32 words, starting at bit `pos` (bit 0 = MSB of word 0)
+__device__ __forceinline__ uint32_t wire_bits(const uint32_t* __restrict__ w, uint32_t pos, uint32_t nbits, uint32_t n_words) {
+  const uint32_t i = pos >> 5, sh = pos & 31;
+  const uint32_t hi = __ldg(w + i), lo = (i + 1 < n_words) ? __ldg(w + i + 1) : 0u;
+  return __funnelshift_l(lo, hi, sh) >> (32 - nbits);
+}
 
 // The session keeps its own copy of each index's node table in which the colour id (word 3 of the node record) is
 // replaced by that colour's cinfo word, so a node visit needs no dependent table lookup.
@@ -160,9 +169,11 @@ __host__ __device__ constexpr uint32_t map_warp_bytes(uint32_t wpr, bool tma, ui
 }
 __host__ __device__ constexpr uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
 
-template <bool SMEM_BM, int MAP_THREADS, int MINB, bool PACKED, int STRIDE, bool TMA, int NS = 64, bool IDX_SMEM = false>
+enum { IN_SOA = 0, IN_PACKED = 1, IN_WIRE = 2 };
+template <bool SMEM_BM, int MAP_THREADS, int MINB, int INPUT, int STRIDE, bool TMA, int NS = 64, bool IDX_SMEM = false>
 __global__ void __launch_bounds__(MAP_THREADS, MINB) k_count_map_q(const CountMapArgs a) {
   extern __shared__ __align__(16) uint32_t smem[];
+  constexpr bool PACKED = INPUT == IN_PACKED;
   static_assert(!TMA || PACKED, "the bulk prefetch reads packed records");
   static_assert(NS <= 64 && NS % 8 == 0 && NS >= 32, "slot ids are 6-bit queue entries");
   static_assert(!IDX_SMEM || SMEM_BM, "the staged index sits behind the staged bitmaps");
@@ -267,6 +278,15 @@ __global__ void __launch_bounds__(MAP_THREADS, MINB) k_count_map_q(const CountMa
           fl = (meta >> 31) ? HLAC_FLAG_PRIMARY : 0;
           cell = meta & HLAC_PACKED_NOT_A_CELL; if (cell == HLAC_PACKED_NOT_A_CELL) cell = HLAC_NOT_A_CELL;
           L = min((meta >> 23) & 0xFFu, 32u * a.wpr);
+        } else if (INPUT == IN_WIRE) {   // bit-packed: bases, then primary (1), cell (cell_bits, all ones = not a cell), umi
+          const uint32_t* words = a.wire + i * a.wire_words;
+          const uint32_t nsw = (2 * a.wire_len + 31) >> 5;   // words carrying bases (the last may end in meta bits: never read as bases)
+          for (uint32_t w = 0; w < 2 * a.wpr; w++) sts32(fw + 4 * w, w < nsw ? __ldg(words + w) : 0u);
+          const uint32_t pos = 2 * a.wire_len;
+          fl = wire_bits(words, pos, 1, a.wire_words) ? HLAC_FLAG_PRIMARY : 0;
+          cell = wire_bits(words, pos + 1, a.wire_cell_bits, a.wire_words);
+          if (cell == (a.wire_cell_bits == 32 ? 0xFFFFFFFFu : (1u << a.wire_cell_bits) - 1u)) cell = HLAC_NOT_A_CELL;
+          L = a.wire_len;
         } else {
           const uint64_t* words = a.seq + i * a.wpr;
           fl = __ldg(a.flags + i);
@@ -361,6 +381,11 @@ __global__ void __launch_bounds__(MAP_THREADS, MINB) k_count_map_q(const CountMa
         if (code != CODE_NONE5) {
           uint32_t um, cl;
           if (PACKED) { const uint64_t meta = __ldg(a.rec + i * (a.wpr + 1) + a.wpr); um = (uint32_t)(meta >> 32); cl = (uint32_t)meta & HLAC_PACKED_NOT_A_CELL; }
+          else if (INPUT == IN_WIRE) {
+            const uint32_t* words = a.wire + i * a.wire_words;
+            cl = wire_bits(words, 2 * a.wire_len + 1, a.wire_cell_bits, a.wire_words);
+            um = wire_bits(words, 2 * a.wire_len + 1 + a.wire_cell_bits, a.wire_umi_bits, a.wire_words);
+          }
           else { um = __ldg(a.umi + i); cl = __ldg(a.cell + i); }
           umi_max = max(umi_max, um);
           key = ((uint64_t)um << (CODE_BITS + a.cell_bits)) | ((uint64_t)cl << CODE_BITS) | code;
@@ -628,7 +653,7 @@ struct hlac_count {
   uint32_t n_buckets = 0;
   uint64_t host_reads = 0, host_non_primary = 0, host_not_cell = 0;   // reads the host driver filtered out itself (hlac_count_add_filtered)
   struct Stage {   // one staging set for host batches; two of them so the H2D of batch i+1 overlaps the kernel of batch i
-    DevBuf<uint64_t> seq, rec; DevBuf<uint16_t> len; DevBuf<uint32_t> cell, umi; DevBuf<uint8_t> flags;
+    DevBuf<uint64_t> seq, rec; DevBuf<uint16_t> len; DevBuf<uint32_t> cell, umi, wire; DevBuf<uint8_t> flags;
     cudaEvent_t copied = nullptr, consumed = nullptr;
   } stage[2];
   cudaStream_t copy_stream = nullptr;
@@ -722,13 +747,13 @@ struct hlac_count {
   using Kern = void (*)(const CountMapArgs);
   // launch shapes: (bitmaps in shared memory?, threads per block, slots per warp, index graphs in shared memory?) with the
   // three input variants (five arrays, packed records, packed records through the bulk prefetch)
-  struct Shape { bool bm; int threads, ns; bool idx; Kern k, k_packed, k_tma; };
+  struct Shape { bool bm; int threads, ns; bool idx; Kern k, k_packed, k_tma, k_wire; };
   template <int S>
   static const Shape* shapes(int& n) {
     // in order of preference (measured on config 2, profiles/r02_count_map_tuning.md); the first one that fits is used
     static const Shape sh[] = {
-#define HLAC_QSHAPE(BM, TT, MB, NSL, IDX) {BM, TT, NSL, IDX, k_count_map_q<BM, TT, MB, false, S, false, NSL, IDX>, k_count_map_q<BM, TT, MB, true, S, false, NSL, IDX>, \
-                                          k_count_map_q<BM, TT, MB, true, S, true, NSL, IDX>}
+#define HLAC_QSHAPE(BM, TT, MB, NSL, IDX) {BM, TT, NSL, IDX, k_count_map_q<BM, TT, MB, IN_SOA, S, false, NSL, IDX>, k_count_map_q<BM, TT, MB, IN_PACKED, S, false, NSL, IDX>, \
+                                          k_count_map_q<BM, TT, MB, IN_PACKED, S, true, NSL, IDX>, k_count_map_q<BM, TT, MB, IN_WIRE, S, false, NSL, IDX>}
         HLAC_QSHAPE(true, 1024, 1, 64, true), HLAC_QSHAPE(true, 1024, 1, 48, true), HLAC_QSHAPE(true, 1024, 1, 56, false), HLAC_QSHAPE(true, 1024, 1, 64, false),
         HLAC_QSHAPE(true, 1024, 1, 40, false), HLAC_QSHAPE(true, 512, 2, 64, false), HLAC_QSHAPE(false, 256, 4, 64, false), HLAC_QSHAPE(false, 128, 8, 64, false),
 #undef HLAC_QSHAPE
@@ -737,7 +762,8 @@ struct hlac_count {
     return sh;
   }
 
-  void launch_map(const hlac_batch& b /* device pointers */, const uint64_t* rec = nullptr /* packed records instead of b's arrays */) {
+  void launch_map(const hlac_batch& b /* device pointers */, const uint64_t* rec = nullptr /* packed records instead of b's arrays */,
+                  const hlac_wire_batch* wire = nullptr /* wire records (device pointer inside) instead of both */) {
     if (b.n == 0) return;
     if (b.words_per_read == 0 || b.words_per_read > 16) throw Error(HLAC_ERR_ARG, "words_per_read must be 1..16");
     if (b.n >= (1ull << 32)) throw Error(HLAC_ERR_LIMIT, "the count kernel takes batches below 2^32 reads");
@@ -752,6 +778,7 @@ struct hlac_count {
     a.bk = store(); a.metrics = counters.p + 1;
     a.codes = want_codes ? codes.p : nullptr;
     a.rec = rec;
+    if (wire) { a.wire = wire->rec; a.wire_words = wire->words_per_record; a.wire_len = wire->read_len; a.wire_cell_bits = wire->cell_bits; a.wire_umi_bits = wire->umi_bits; }
     // launch shape: (bitmaps in shared memory?, threads per block); HLAC_COUNT_SHAPE="smem,threads" overrides for tuning runs
     // the bulk (TMA) prefetch needs 16-byte record granularity: (wpr + 1) even, a 16-byte aligned record array. It is opt-in
     // (HLAC_COUNT_TMA=1): its staging tiles come out of the L1 carve-out and it was measured slower on config 2.
@@ -778,6 +805,7 @@ struct hlac_count {
       cfg_shape = pick;
       cfg_tma_fits = smem_for(*pick, true) <= 227 * 1024;
       HLAC_CUDA(cudaFuncSetAttribute(pick->k_packed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(*pick, false)));
+      HLAC_CUDA(cudaFuncSetAttribute(pick->k_wire, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(*pick, false)));
       HLAC_CUDA(cudaFuncSetAttribute(pick->k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(*pick, false)));
       if (cfg_tma_fits) HLAC_CUDA(cudaFuncSetAttribute(pick->k_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(*pick, true)));
       HLAC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cfg_occ, pick->k, pick->threads, smem_for(*pick, false)));
@@ -792,7 +820,7 @@ struct hlac_count {
     const Shape& shp = *(const Shape*)cfg_shape;
     const int cfg_threads = shp.threads;
     const bool tma = tma_ok && cfg_tma_fits;
-    Kern kern = rec ? (tma ? shp.k_tma : shp.k_packed) : shp.k;
+    Kern kern = wire ? shp.k_wire : rec ? (tma ? shp.k_tma : shp.k_packed) : shp.k;
     const size_t smem = smem_for(shp, tma);
     const uint64_t need = (b.n + (uint64_t)cfg_threads * 2 - 1) / ((uint64_t)cfg_threads * 2);
     const unsigned grid = (unsigned)std::min<uint64_t>(need, (uint64_t)n_sm * cfg_occ);
@@ -1034,6 +1062,72 @@ int hlac_count_push_packed(hlac_count* s, const hlac_packed_batch* b) try {
   hlac_batch d{}; d.n = b->n; d.words_per_read = b->words_per_read;
   s->launch_map(d, st.rec.p);
   HLAC_CUDA(cudaEventRecord(st.consumed, s->stream));
+  return HLAC_OK;
+} catch (const Error& e) { set_last_error(e.what()); return e.code; } catch (const std::exception& e) { set_last_error(e.what()); return HLAC_ERR_STATE; }
+
+// ---- wire records: the bit-packed host->device format (hlac_wire_batch) ------------------------------------------------
+static void validate_wire(const hlac_count* s, const hlac_wire_batch* b) {
+  if (b->n && !b->rec) throw Error(HLAC_ERR_ARG, "null record array");
+  if (b->n >= (1ull << 32)) throw Error(HLAC_ERR_LIMIT, "batch too large");
+  if (b->read_len == 0 || b->read_len > 512) throw Error(HLAC_ERR_ARG, "read_len must be 1..512");
+  if (b->cell_bits == 0 || b->cell_bits > 27 || b->umi_bits == 0 || b->umi_bits > 32) throw Error(HLAC_ERR_ARG, "cell_bits must be 1..27 and umi_bits 1..32");
+  if (b->words_per_record != hlac_wire_words(b->read_len, b->cell_bits, b->umi_bits)) throw Error(HLAC_ERR_ARG, "words_per_record does not match the field widths");
+  if ((uint64_t)s->n_cells > (1ull << b->cell_bits) - 1) throw Error(HLAC_ERR_LIMIT, "cell_bits too narrow for this session's columns (the all-ones value is 'not a cell')");
+}
+
+uint32_t hlac_wire_words(uint32_t read_len, uint32_t cell_bits, uint32_t umi_bits) { return (2 * read_len + 1 + cell_bits + umi_bits + 31) / 32; }
+
+int hlac_count_push_wire_device(hlac_count* s, const hlac_wire_batch* b) try {
+  if (!s || !b) throw Error(HLAC_ERR_ARG, "null argument");
+  validate_wire(s, b);
+  DeviceGuard g(s->device);
+  hlac_batch d{}; d.n = b->n; d.words_per_read = (b->read_len + 31) / 32;
+  s->launch_map(d, nullptr, b);
+  return HLAC_OK;
+} catch (const Error& e) { set_last_error(e.what()); return e.code; } catch (const std::exception& e) { set_last_error(e.what()); return HLAC_ERR_STATE; }
+
+int hlac_count_push_wire(hlac_count* s, const hlac_wire_batch* b) try {
+  if (!s || !b) throw Error(HLAC_ERR_ARG, "null argument");
+  validate_wire(s, b);
+  if (b->n == 0) return HLAC_OK;
+  DeviceGuard g(s->device);
+  auto& st = next_stage(s);
+  auto& e = s->begin(3, s->copy_stream);
+  st.wire.upload(b->rec, b->n * b->words_per_record, s->copy_stream);   // ONE copy per push, 28 bytes per 91-bp read
+  s->end(e, s->copy_stream);
+  HLAC_CUDA(cudaEventRecord(st.copied, s->copy_stream));
+  HLAC_CUDA(cudaStreamWaitEvent(s->stream, st.copied, 0));
+  hlac_batch d{}; d.n = b->n; d.words_per_read = (b->read_len + 31) / 32;
+  hlac_wire_batch w = *b; w.rec = st.wire.p;
+  s->launch_map(d, nullptr, &w);
+  HLAC_CUDA(cudaEventRecord(st.consumed, s->stream));
+  return HLAC_OK;
+} catch (const Error& e) { set_last_error(e.what()); return e.code; } catch (const std::exception& e) { set_last_error(e.what()); return HLAC_ERR_STATE; }
+
+// host helper: hlac_batch (host pointers, every read read_len bases) -> wire records
+int hlac_pack_wire(const hlac_batch* b, uint32_t read_len, uint32_t cell_bits, uint32_t umi_bits, uint32_t* rec) try {
+  if (!b || (b->n && (!rec || !b->seq || !b->len || !b->cell || !b->umi || !b->flags))) throw Error(HLAC_ERR_ARG, "null argument");
+  if (read_len == 0 || read_len > 32 * b->words_per_read || cell_bits == 0 || cell_bits > 27 || umi_bits == 0 || umi_bits > 32) throw Error(HLAC_ERR_ARG, "bad field widths");
+  const uint32_t W = hlac_wire_words(read_len, cell_bits, umi_bits), wpr = b->words_per_read;
+  const uint32_t not_cell = (1u << cell_bits) - 1u;
+  for (uint64_t i = 0; i < b->n; i++) {
+    if (b->len[i] != read_len) throw Error(HLAC_ERR_LIMIT, "wire records hold reads of one length per batch (read " + std::to_string(i) + " has " + std::to_string(b->len[i]) + " bases)");
+    uint32_t cell = b->cell[i];
+    if (cell == HLAC_NOT_A_CELL) cell = not_cell;
+    else if (cell >= not_cell) throw Error(HLAC_ERR_LIMIT, "cell index does not fit cell_bits");
+    if (umi_bits < 32 && (b->umi[i] >> umi_bits)) throw Error(HLAC_ERR_LIMIT, "UMI key does not fit umi_bits");
+    uint32_t* r = rec + i * W;
+    for (uint32_t w = 0; w < W; w++) r[w] = 0;
+    const uint32_t nsw = (2 * read_len + 31) / 32;
+    for (uint32_t w = 0; w < nsw; w++) { const uint64_t v = b->seq[i * wpr + (w >> 1)]; r[w] = (w & 1) ? (uint32_t)v : (uint32_t)(v >> 32); }
+    if ((2 * read_len) & 31) r[nsw - 1] &= ~(0xFFFFFFFFu >> ((2 * read_len) & 31));   // bits beyond the read stay free for the fields
+    auto put = [&](uint32_t pos, uint32_t nbits, uint32_t v) {   // big-endian bit stream
+      for (uint32_t k = 0; k < nbits; k++) if ((v >> (nbits - 1 - k)) & 1u) r[(pos + k) >> 5] |= 0x80000000u >> ((pos + k) & 31);
+    };
+    put(2 * read_len, 1, (b->flags[i] & HLAC_FLAG_PRIMARY) ? 1u : 0u);
+    put(2 * read_len + 1, cell_bits, cell);
+    put(2 * read_len + 1 + cell_bits, umi_bits, b->umi[i]);
+  }
   return HLAC_OK;
 } catch (const Error& e) { set_last_error(e.what()); return e.code; } catch (const std::exception& e) { set_last_error(e.what()); return HLAC_ERR_STATE; }
 

@@ -67,6 +67,10 @@ struct HashVis {   // order-sensitive hashes of the colour path: four 32-bit mul
 };
 struct CountVis2 { uint32_t n = 0; __device__ __forceinline__ void visit(uint32_t, uint32_t) { n++; } };
 struct WriteVis { uint32_t* out; uint32_t n = 0; __device__ __forceinline__ void visit(uint32_t colour, uint32_t) { out[n++] = colour; } };
+struct CompareVis {   // the walk's colour path against a stored one
+  const uint32_t* want; uint32_t n_want; uint32_t k = 0; bool ok = true;
+  __device__ __forceinline__ void visit(uint32_t colour, uint32_t) { if (k >= n_want || want[k] != colour) ok = false; k++; }
+};
 
 struct SharedWords {
   const uint32_t* p;
@@ -260,12 +264,35 @@ __global__ void __launch_bounds__(GENO_THREADS) k_geno_paths(const GenoPathArgs 
   a.e.path_off[id] = off; a.e.path_len[id] = cv.n;
 }
 
+// Exactness of the interning: a read joins an interned path when its two 64-bit path hashes match. This kernel removes the
+// residual doubt: every counted read is walked again and its colour path compared, id by id, with the stored path it was
+// assigned to; a single mismatch fails the push. (One extra walk per counted read; HLAC_GENO_VERIFY=0 skips it.)
+template <int STRIDE>
+__global__ void __launch_bounds__(GENO_THREADS) k_geno_verify(const GenoPathArgs a, const uint32_t* __restrict__ cov, const uint32_t* __restrict__ pid, uint64_t n,
+                                                               unsigned long long* mismatches) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  uint32_t* fw = smem + threadIdx.x * a.row_stride;
+  uint32_t* rc = fw + a.nw;
+  const uint64_t i = (uint64_t)blockIdx.x * GENO_THREADS + threadIdx.x;
+  if (i >= n || cov[i] <= MIN_SCORE_CALL) return;
+  const uint32_t id = pid[i];
+  load_read_row(a.seq, i, a.wpr, fw);
+  const int L = min((int)a.len[i], (int)(32 * a.wpr));
+  const bool rev = a.strand[i] != 0;
+  if (rev) make_revcomp(SharedWords{fw}, rc, L, (int)a.nw);
+  SharedWords rd{rev ? rc : fw};
+  uint32_t c2, t0 = 0, t1 = 0;
+  CompareVis cv{a.arena + a.e.path_off[id], a.e.path_len[id]};
+  const bool some = map_read_walk<STRIDE>(a.ix, rd, BitmapGlobal{a.ix.bitmap}, L, cv, c2, t0, t1);
+  if (!some || !cv.ok || cv.k != cv.n_want || c2 != cov[i]) atomicAdd(mismatches, 1ULL);
+}
+
 struct Record { uint32_t bc, umi, path; };
 
 __global__ void k_intern_lookup(PathTable t, PathEntries e, const uint32_t* __restrict__ cov, const uint64_t* __restrict__ ha,
                                 const uint64_t* __restrict__ hb, const uint32_t* __restrict__ cell, const uint32_t* __restrict__ umi,
                                 uint64_t n, uint64_t ord0, const uint64_t* __restrict__ ordinal, uint64_t* rec_key, uint32_t* rec_path, unsigned long long* rec_cursor,
-                                uint32_t* read_path, unsigned long long* collisions) {
+                                uint32_t* read_path, unsigned long long* collisions, uint32_t* batch_pid) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned lane = threadIdx.x & 31;
   bool counted = false; uint32_t id = NONE32;
@@ -280,6 +307,7 @@ __global__ void k_intern_lookup(PathTable t, PathEntries e, const uint32_t* __re
     atomicAdd(e.count + id, 1u);
   }
   if (i < n && read_path) read_path[i] = id;
+  if (i < n && batch_pid) batch_pid[i] = id;
   const unsigned ballot = __ballot_sync(0xFFFFFFFFu, counted);
   if (ballot) {
     unsigned long long at = 0;
@@ -690,7 +718,8 @@ struct hlac_geno {
   // staging + per-batch temporaries
   DevBuf<uint64_t> st_seq, hash_a, hash_b;
   DevBuf<uint16_t> st_len;
-  DevBuf<uint32_t> st_cell, st_umi, cov;
+  DevBuf<uint32_t> st_cell, st_umi, cov, batch_pid;
+  bool verify = true;   // re-walk every counted read against its interned path (HLAC_GENO_VERIFY=0 turns it off)
   DevBuf<uint64_t> st_ord;
   DevBuf<uint8_t> strand;
   // path table
@@ -899,16 +928,28 @@ struct hlac_geno {
       HLAC_CUDA(cudaGetLastError());
       launches++;
     }
+    if (verify) batch_pid.reserve(n, stream);
     k_intern_lookup<<<g1, 256, 0, stream>>>(table(), entries(), cov.p, hash_a.p, hash_b.p, b.cell, b.umi, n, reads_pushed, b.ordinal,
-                                            rec_key.p, rec_path.p, ctr.p + 2, record_reads ? read_path.p + reads_pushed : nullptr, ctr.p + 3);
+                                            rec_key.p, rec_path.p, ctr.p + 2, record_reads ? read_path.p + reads_pushed : nullptr, ctr.p + 3,
+                                            verify ? batch_pid.p : nullptr);
     HLAC_CUDA(cudaGetLastError());
     launches++;
+    if (verify) {
+      auto* const kver = stride == 3 ? k_geno_verify<3> : k_geno_verify<1>;
+      HLAC_CUDA(cudaFuncSetAttribute(kver, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_paths));
+      GenoPathArgs p{};
+      p.ix = idx->view; p.seq = b.seq; p.len = b.len; p.strand = strand.p; p.wpr = a.wpr; p.nw = a.nw; p.row_stride = a.row_stride;
+      p.e = entries(); p.arena = arena.p;
+      kver<<<g1, GENO_THREADS, smem_paths, stream>>>(p, cov.p, batch_pid.p, n, ctr.p + 3);
+      HLAC_CUDA(cudaGetLastError());
+      launches++;
+    }
     unsigned long long c2[3];
     HLAC_CUDA(cudaMemcpyAsync(c2, ctr.p + 1, sizeof c2, cudaMemcpyDeviceToHost, stream));
     end(e1);
     HLAC_CUDA(cudaStreamSynchronize(stream));
     n_entries = ne; arena_used = c2[0]; n_records_ub = c2[1];
-    if (c2[2]) throw Error(HLAC_ERR_STATE, "path hash collision detected (64-bit hash A equal, hash B different)");
+    if (c2[2]) throw Error(HLAC_ERR_STATE, "path hash collision detected (a read's colour path differs from the interned path its hashes matched)");
     reads_pushed += n; last_n = n;
   }
 };
@@ -920,6 +961,7 @@ int hlac_geno_new(hlac_index* idx, hlac_geno** out) try {
   if (idx->device < 0) throw Error(HLAC_ERR_CUDA, "index is host-only (device -1): genotyping needs a CUDA device, there is no CPU fallback");
   auto s = std::make_unique<hlac_geno>();
   s->idx = idx; s->device = idx->device; s->stride = seed_stride();
+  if (const char* e = getenv("HLAC_GENO_VERIFY")) s->verify = atoi(e) != 0;
   DeviceGuard g(s->device);
   HLAC_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
   s->ctr.reserve(16, s->stream);

@@ -307,3 +307,48 @@ def test_seed_stride_3(sb, orc, abc):
     assert not np.array_equal(out[1][0], out[3][0]), "the workload does not separate stride 1 from stride 3"
     with pytest.raises(sb.HlacError):
         sb.set_seed_stride(2)
+
+
+def test_wire_records_equal_soa(sb, orc, abc, fixture_reads):
+    """hlac_count_push_wire (bit-packed records: 28 bytes per 91-bp read, one H2D copy per push) must give exactly what the
+    five-array push gives - host and device buffers, several pushes, --primary-alignments, non-whitelisted reads - and the
+    oracle's result; other field widths and read lengths too."""
+    import torch
+    from tools import synth
+    cds, gen = synth.fixture_alleles()
+    r = synth.make_reads(70000, [s for _, s in cds], [s for _, s in gen], 300, 23)
+    b = (r["seq"], r["len"], r["cell"], r["umi"], r["flags"])
+    for primary_only in (False, True):
+        ref = orc.count_run(abc["oc"], abc["og"], *b, primary_only=primary_only, want_codes=True)
+        for cb, ub in ((9, 21), (17, 32)):
+            rec = sb.pack_wire(*b, 91, cb, ub)
+            assert rec.shape[1] == (7 if (cb, ub) == (9, 21) else 8)
+            for device in (False, True):
+                s = sb.CountSession(abc["gc"], abc["gg"], 300, primary_only)
+                s.record_codes(True)
+                codes = []
+                for part in np.array_split(np.arange(len(rec)), 3):
+                    chunk = rec[part[0]:part[-1] + 1]
+                    s.push_wire(torch.from_numpy(chunk.view(np.int32)).cuda() if device else chunk, 91, cb, ub)
+                    codes.append(s.last_codes(len(chunk)))
+                ent, met = s.finish()
+                assert np.array_equal(np.concatenate(codes), ref["codes"]) and met == ref["metrics"] and ent == ref["entries"]
+    # a read length whose bases end in the middle of a word next to the fields, and one that fills its words exactly
+    rng = np.random.default_rng(3)
+    rc = lambda s: s[::-1].translate(str.maketrans("ACGT", "TGCA"))
+    for L in (64, 75, 128):
+        reads = []
+        for i in range(4000):
+            src = (cds if rng.random() < 0.7 else gen)[int(rng.integers(0, 6))][1]
+            st = int(rng.integers(0, len(src) - L))
+            sq = src[st:st + L]
+            reads.append((rc(sq) if rng.random() < 0.5 else sq, b"c%d" % int(rng.integers(0, 9)), b"ACGTACGT%s" % (b"ACGT"[i % 4:i % 4 + 1]), i % 11 != 0))
+        bc = {b"c%d" % i: i for i in range(8)}    # c8 is not in the list
+        batch = H.make_batch(reads, bc, pack=sb.pack_reads)
+        ref = orc.count_run(abc["oc"], abc["og"], *batch)
+        s = sb.CountSession(abc["gc"], abc["gg"], 8)
+        s.push_wire(sb.pack_wire(*batch, L, 4, 19), L, 4, 19)
+        assert s.finish() == (ref["entries"], ref["metrics"])
+    with pytest.raises(sb.HlacError, match="cell_bits"):   # 300 columns do not fit 8 bits + the not-a-cell value
+        s300 = sb.CountSession(abc["gc"], abc["gg"], 300)
+        s300.push_wire(np.zeros((1, 7), np.uint32), 91, 8, 21)

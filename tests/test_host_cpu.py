@@ -181,10 +181,10 @@ def test_locus_parsing_follows_the_reference_regex(sb):
 def test_ctypes_layouts_match_the_library(sb):
     """The ctypes mirrors of the ABI structs must have the sizes the compiled header has (guards against drift)."""
     from schlacount_b200 import _lib
-    out = (C.c_uint32 * 9)()
-    assert sb.lib().hlac_abi_sizes(out, C.c_uint32(9)) == 0
+    out = (C.c_uint32 * 10)()
+    assert sb.lib().hlac_abi_sizes(out, C.c_uint32(10)) == 0
     mine = [C.sizeof(x) for x in (_lib.Batch, _lib.Metrics, _lib.Coo, _lib.IndexInfo, _lib.ClassTables, _lib.Paths, _lib.Calls,
-                                  _lib.EqClassDbC, _lib.PackedBatch)]
+                                  _lib.EqClassDbC, _lib.PackedBatch, _lib.WireBatch)]
     assert list(out) == mine
     old = (C.c_uint32 * 7)()   # a binding built against the 7-value form still works
     assert sb.lib().hlac_abi_sizes(old, C.c_uint32(7)) == 0 and list(old) == mine[:7]
@@ -275,6 +275,33 @@ def test_pack_records_layout(sb):
         sb.pack_records(np.zeros((1, 7), np.uint64), np.array([256], np.uint16), cell[:1], umi[:1], flags[:1])
     with pytest.raises(sb.HlacError):   # 23-bit cell field
         sb.pack_records(seq[:1], lens[:1], np.array([1 << 23], np.uint32), umi[:1], flags[:1])
+
+
+def test_pack_wire_layout(sb):
+    """hlac_pack_wire: a record is one big-endian bit stream - 2 * read_len bits of bases (the batch's own 2-bit codes), then
+    primary, cell (all ones = not a cell), UMI key - checked against a bit-by-bit restatement."""
+    rng = np.random.default_rng(9)
+    for L, cb, ub in ((91, 14, 21), (91, 17, 21), (64, 5, 32), (33, 27, 9), (150, 20, 25)):
+        n = 40
+        seqs = ["".join("ACGT"[int(x)] for x in rng.integers(0, 4, size=L)) for _ in range(n)]
+        seq, lens = sb.pack_reads(seqs)
+        cell = rng.integers(0, (1 << cb) - 1, size=n).astype(np.uint32)
+        cell[::7] = 0xFFFFFFFF
+        umi = rng.integers(0, 1 << ub, size=n, dtype=np.uint64).astype(np.uint32)
+        flags = rng.integers(0, 2, size=n).astype(np.uint8)
+        rec = sb.pack_wire(seq, lens, cell, umi, flags, L, cb, ub)
+        W = (2 * L + 1 + cb + ub + 31) // 32
+        assert rec.shape == (n, W) and W == sb.lib().hlac_wire_words(L, cb, ub)
+        for i in range(n):
+            bits = "".join(format(int(w), "032b") for w in rec[i])
+            want = "".join(format("ACGT".index(c), "02b") for c in seqs[i]) + str(int(flags[i] & 1)) + \
+                format((1 << cb) - 1 if cell[i] == 0xFFFFFFFF else int(cell[i]), "0%db" % cb) + format(int(umi[i]), "0%db" % ub)
+            assert bits[:len(want)] == want and set(bits[len(want):]) <= {"0"}
+    assert sb.lib().hlac_wire_words(91, 14, 21) == 7   # 28 bytes per 91-bp read
+    with pytest.raises(sb.HlacError):   # ragged batch
+        sb.pack_wire(seq, np.where(np.arange(n) == 3, L - 1, lens).astype(np.uint16), cell, umi, flags, L, cb, ub)
+    with pytest.raises(sb.HlacError):   # a cell equal to the not-a-cell sentinel
+        sb.pack_wire(seq, lens, np.full(n, (1 << cb) - 1, np.uint32), umi, flags, L, cb, ub)
 
 
 def test_bam_reader_rejects_damaged_files(sb, tmp_path):

@@ -59,36 +59,39 @@ class _W:
 
 legacy = bool(os.environ.get("HLAC_GENO_MULTI_LEGACY"))
 comm = sb.Comm.from_torch_distributed(local) if (world > 1 and not legacy) else None
-g, t_push = run((cell % world) == rank)
-if world > 1:
-    dist.barrier()
-torch.cuda.synchronize()
-t0 = time.time()
-if comm is not None:
-    g.attach_comm(comm)
-    tab = g.finish(raw=True)
-    n_union = g.stats()["n_paths"]
-else:
+for rep in range(2):   # the second pass is the warm one (kernel attributes, the per-index colour bitsets, allocator)
+    g, t_push = run((cell % world) == rank)
     if world > 1:
-        parts = [None] * world
-        dist.all_gather_object(parts, g.export_paths())
-        n_union = g.import_merged_paths(parts)
-    else:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.time()
+    if comm is not None:
+        g.attach_comm(comm)
+        tab = g.finish(raw=True)
         n_union = g.stats()["n_paths"]
-    ptr, nc = g.finish_begin()
+    else:
+        if world > 1:
+            parts = [None] * world
+            dist.all_gather_object(parts, g.export_paths())
+            n_union = g.import_merged_paths(parts)
+        else:
+            n_union = g.stats()["n_paths"]
+        ptr, nc = g.finish_begin()
+        if world > 1:
+            dist.all_reduce(torch.as_tensor(_W(ptr, nc), device=dev))
+            torch.cuda.synchronize()   # the session reads the histogram back on its own stream
+        tab = g.finish_end(raw=True)
+    torch.cuda.synchronize()
+    t_fin = time.time() - t0
     if world > 1:
-        dist.all_reduce(torch.as_tensor(_W(ptr, nc), device=dev))
-        torch.cuda.synchronize()   # the session reads the histogram back on its own stream
-    tab = g.finish_end(raw=True)
-torch.cuda.synchronize()
-t_fin = time.time() - t0
-if world > 1:
-    tt = torch.tensor([t_push, t_fin], device=dev, dtype=torch.float64)
-    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    t_push, t_fin = float(tt[0]), float(tt[1])
+        tt = torch.tensor([t_push, t_fin], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_push, t_fin = float(tt[0]), float(tt[1])
+    if rep == 0:
+        cold = dict(push_s=t_push, merge_finish_s=t_fin)
 theta, iters = g.squarem(device=local)
 call = g.call(theta)
-out = dict(world=world, reads=n, alleles=len(names), protocol="legacy-host" if (legacy or world == 1) else "in-library", push_s=t_push, merge_finish_s=t_fin,
+out = dict(world=world, reads=n, alleles=len(names), cold_first_pass=cold, protocol="legacy-host" if (legacy or world == 1) else "in-library", push_s=t_push, merge_finish_s=t_fin,
            union_paths=n_union, resolve=g.resolve_stats(), timing=g.timing(), tables=tab,
            em_iters=iters, called=[gix.tx_names[i] for i in call["called"]])
 if rank == 0:
