@@ -13,7 +13,7 @@
 namespace hlac {
 
 struct Ranked {
-  struct W { uint32_t i; double w; std::string gene; uint64_t exp; };
+  struct W { uint32_t i; double w; uint32_t gene; uint64_t exp; };   // gene = rank of the gene string (lexicographic)
   std::vector<W> wn;                 // sorted by descending weight, then (stably) by gene (em.rs:370-371)
   std::vector<int32_t> cand_of;      // tx -> index into cands, or -1
   std::vector<uint32_t> cands;       // per gene the leading alleles with reads_explained > MIN_READS_CALL (<= WEIGHTS_TO_OUTPUT)
@@ -21,9 +21,16 @@ struct Ranked {
 
 inline Ranked rank_alleles(const std::vector<std::string>& names, uint32_t nitems, const uint64_t* reads_explained, const double* theta) {
   Ranked r;
-  for (uint32_t i = 0; i < nitems; i++) r.wn.push_back({i, theta[i], names[i].substr(0, names[i].find('*')), reads_explained[i]});
-  std::stable_sort(r.wn.begin(), r.wn.end(), [](const Ranked::W& a, const Ranked::W& b) { return -a.w < -b.w; });
-  std::stable_sort(r.wn.begin(), r.wn.end(), [](const Ranked::W& a, const Ranked::W& b) { return a.gene < b.gene; });
+  // gene strings -> ranks in string order (a handful of genes), so that the two stable sorts of em.rs:370-371 (by descending
+  // weight, then by gene string) become one stable sort on (gene rank, descending weight) over plain numbers
+  std::vector<std::string> gene_of(nitems);
+  std::set<std::string> gs;
+  for (uint32_t i = 0; i < nitems; i++) { gene_of[i] = names[i].substr(0, names[i].find('*')); gs.insert(gene_of[i]); }
+  const std::vector<std::string> sorted_genes(gs.begin(), gs.end());
+  r.wn.reserve(nitems);
+  for (uint32_t i = 0; i < nitems; i++)
+    r.wn.push_back({i, theta[i], (uint32_t)(std::lower_bound(sorted_genes.begin(), sorted_genes.end(), gene_of[i]) - sorted_genes.begin()), reads_explained[i]});
+  std::stable_sort(r.wn.begin(), r.wn.end(), [](const Ranked::W& a, const Ranked::W& b) { return a.gene != b.gene ? a.gene < b.gene : -a.w < -b.w; });
   r.cand_of.assign(nitems, -1);
   for (size_t s = 0; s < r.wn.size();) {
     size_t e = s; while (e < r.wn.size() && r.wn[e].gene == r.wn[s].gene) e++;

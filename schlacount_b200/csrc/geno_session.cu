@@ -705,6 +705,27 @@ __global__ void k_class_cand_mask_colour(const uint32_t* __restrict__ cls_colour
   if (lane == 0) { mask[2 * (size_t)c] = lo; mask[2 * (size_t)c + 1] = hi; }
 }
 
+// pair_reads_explained (em.rs:36-44) for every pair of candidate alleles at once: a class with read count r and candidate
+// set M adds r to single[a] for a in M and to both[a][b] for a < b in M; reads in classes containing a OR b are then
+// single[a] + single[b] - both[a][b]. One thread per class (a class holds a handful of candidates).
+__global__ void k_pair_matrix(const uint64_t* __restrict__ mask, const uint32_t* __restrict__ cls_reads, uint32_t n, unsigned long long* single, unsigned long long* both) {
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  const uint64_t m[2] = {mask[2 * (size_t)c], mask[2 * (size_t)c + 1]};
+  if ((m[0] | m[1]) == 0) return;
+  const unsigned long long r = cls_reads[c];
+  for (int wa = 0; wa < 2; wa++)
+    for (uint64_t ba = m[wa]; ba; ba &= ba - 1) {
+      const int a = wa * 64 + __ffsll((long long)ba) - 1;
+      atomicAdd(single + a, r);
+      for (int wb = wa; wb < 2; wb++)
+        for (uint64_t bb = wb == wa ? (ba & (ba - 1)) : m[wb]; bb; bb &= bb - 1) {
+          const int b = wb * 64 + __ffsll((long long)bb) - 1;
+          atomicAdd(both + a * 128 + b, r);
+        }
+    }
+}
+
 }  // namespace
 
 static inline double now_ms() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
@@ -1179,19 +1200,25 @@ int hlac_geno_finish_begin(hlac_geno* s, uint32_t** umi_hist_device, uint64_t* n
     // ---- host: intern equal vectors by (hash pair, length, last colour); exact equality is verified on the device ----
     struct Cls { uint32_t rep; uint64_t ord; uint32_t reads; };
     std::vector<Cls> classes; std::vector<uint32_t> tmp_cls(E), rep_of_path(E);
-    std::unordered_map<uint64_t, std::vector<uint32_t>> by_hash;
-    for (uint32_t p = 0; p < E; p++) {
-      auto& cand = by_hash[vhash[p]];
-      uint32_t found = NONE32;
-      for (uint32_t c : cand) {
-        const uint32_t r = classes[c].rep;
-        if (vhash2[r] == vhash2[p] && hlen[r] == hlen[p] && hlast[r] == hlast[p]) { found = c; break; }
+    {   // open-addressing table over the first vector hash; candidates compare (second hash, length, last colour)
+      uint64_t cap = 64; while (cap < 2 * (uint64_t)E) cap <<= 1;
+      std::vector<uint32_t> slot(cap, NONE32);   // class index
+      classes.reserve(E / 2 + 16);
+      for (uint32_t p = 0; p < E; p++) {
+        uint64_t h = (vhash[p] * 0x9E3779B97F4A7C15ULL) >> 20 & (cap - 1);
+        uint32_t found = NONE32;
+        for (;; h = (h + 1) & (cap - 1)) {
+          const uint32_t c = slot[h];
+          if (c == NONE32) break;
+          const uint32_t r = classes[c].rep;
+          if (vhash[r] == vhash[p] && vhash2[r] == vhash2[p] && hlen[r] == hlen[p] && hlast[r] == hlast[p]) { found = c; break; }
+        }
+        if (found == NONE32) { found = (uint32_t)classes.size(); classes.push_back({p, ford[p], 0}); slot[h] = found; }
+        classes[found].ord = std::min(classes[found].ord, ford[p]);
+        classes[found].reads += cnt[p];
+        tmp_cls[p] = found;
+        rep_of_path[p] = classes[found].rep;
       }
-      if (found == NONE32) { found = (uint32_t)classes.size(); classes.push_back({p, ford[p], 0}); cand.push_back(found); }
-      classes[found].ord = std::min(classes[found].ord, ford[p]);
-      classes[found].reads += cnt[p];
-      tmp_cls[p] = found;
-      rep_of_path[p] = classes[found].rep;
     }
     if (!comm) {   // (with several ranks the representative's vector may live on another rank: identity then rests on the
                    // 128-bit vector hash + length + last colour alone)
@@ -1332,10 +1359,10 @@ int hlac_geno_finish_end(hlac_geno* s, hlac_class_tables* out) try {
       HLAC_CUDA(cudaStreamSynchronize(s->stream));   // the packing buffers go out of scope
     }
     // reads_explained (mapping.rs:196-198): per colour totals, then one pass over the used colour lists on the device
-    std::map<uint32_t, unsigned long long> per_colour;
+    std::vector<unsigned long long> per_colour(hx.n_colours(), 0);
     for (size_t c = 0; c < nc; c++) per_colour[s->fin_cls_colour[c]] += cls_reads[c];
     std::vector<uint32_t> cols; std::vector<unsigned long long> tots;
-    for (auto& kv : per_colour) { cols.push_back(kv.first); tots.push_back(kv.second); }
+    for (uint32_t col = 0; col < per_colour.size(); col++) if (per_colour[col]) { cols.push_back(col); tots.push_back(per_colour[col]); }
     DevBuf<uint32_t> d_cols; DevBuf<unsigned long long> d_tots, d_expl;
     d_cols.upload(cols.data(), cols.size(), s->stream); d_tots.upload(tots.data(), tots.size(), s->stream); d_expl.reserve(std::max<uint32_t>(nitems, 1), s->stream);
     HLAC_CUDA(cudaMemsetAsync(d_expl.p, 0, (size_t)std::max<uint32_t>(nitems, 1) * 8, s->stream));
@@ -1350,17 +1377,15 @@ int hlac_geno_finish_end(hlac_geno* s, hlac_class_tables* out) try {
   // counts_umi key = sort + dedup of the UMI's class (mapping.rs:205-207). A class vector is a permutation of the
   // colour list of its path's last node, and colour lists are sorted, duplicate-free and pairwise distinct, so the key
   // IS that colour list: accumulate per colour id, then emit in lexicographic order of the lists.
-  std::map<uint32_t, uint64_t> by_colour;
+  // (The reference's HashMap has no order; the classes are emitted in ascending colour id - the index's own, identical on
+  // every rank and run.)
+  std::vector<uint64_t> by_colour(hx.n_colours(), 0);
   for (size_t c = 0; c < nc; c++) if (umi_hist[c]) by_colour[s->fin_cls_colour[c]] += umi_hist[c];
-  std::vector<uint32_t> used; used.reserve(by_colour.size());
-  for (auto& kv : by_colour) used.push_back(kv.first);
-  std::sort(used.begin(), used.end(), [&](uint32_t a, uint32_t b) {
-    return std::lexicographical_compare(hx.col_tx.begin() + hx.col_off[a], hx.col_tx.begin() + hx.col_off[a + 1],
-                                        hx.col_tx.begin() + hx.col_off[b], hx.col_tx.begin() + hx.col_off[b + 1]);
-  });
-  uint64_t utx = 0; for (uint32_t c : used) utx += hx.col_off[c + 1] - hx.col_off[c];
+  std::vector<uint32_t> used;
+  uint64_t utx = 0;
+  for (uint32_t col = 0; col < by_colour.size(); col++) if (by_colour[col]) { used.push_back(col); utx += hx.col_off[col + 1] - hx.col_off[col]; }
   out->n_umi_classes = used.size();
-  out->umi_off = (uint64_t*)calloc(used.size() + 1, 8); out->umi_tx = (uint32_t*)calloc(std::max<uint64_t>(utx, 1), 4); out->umi_cnt = (uint32_t*)calloc(std::max<size_t>(used.size(), 1), 4);
+  out->umi_off = (uint64_t*)calloc(used.size() + 1, 8); out->umi_tx = (uint32_t*)malloc(std::max<uint64_t>(utx, 1) * 4); out->umi_cnt = (uint32_t*)calloc(std::max<size_t>(used.size(), 1), 4);
   q = 0; size_t c = 0;
   for (uint32_t col : used) {
     const size_t len = hx.col_off[col + 1] - hx.col_off[col];
@@ -1396,24 +1421,26 @@ int hlac_geno_call(hlac_geno* s, const hlac_class_tables* t, const double* theta
   const Ranked rk = rank_alleles(names, t->nitems, t->reads_explained, theta);
   if (rk.cands.size() > 128) throw Error(HLAC_ERR_LIMIT, "more than 128 candidate alleles");
   const size_t nc = s->fin_cls_reads.size();
-  std::vector<uint64_t> mask(std::max<size_t>(2 * nc, 2), 0);
+  std::vector<unsigned long long> single(128, 0), both(128 * 128, 0);
   if (nc && !rk.cands.empty()) {
     std::vector<uint8_t> cand_idx(t->nitems, 0xFF);
     for (size_t k = 0; k < rk.cands.size(); k++) cand_idx[rk.cands[k]] = (uint8_t)k;
-    DevBuf<uint8_t> d_ci; DevBuf<uint64_t> d_mask; DevBuf<uint32_t> d_col;
+    DevBuf<uint8_t> d_ci; DevBuf<uint64_t> d_mask; DevBuf<uint32_t> d_col, d_reads; DevBuf<unsigned long long> d_acc;
     d_ci.upload(cand_idx.data(), cand_idx.size(), s->stream); d_col.upload(s->fin_cls_colour.data(), nc, s->stream); d_mask.reserve(2 * nc, s->stream);
+    d_reads.upload(s->fin_cls_reads.data(), nc, s->stream); d_acc.reserve(128 + 128 * 128, s->stream);
+    HLAC_CUDA(cudaMemsetAsync(d_acc.p, 0, (128 + 128 * 128) * sizeof(unsigned long long), s->stream));
     k_class_cand_mask_colour<<<(unsigned)((nc * 32 + 255) / 256), 256, 0, s->stream>>>(d_col.p, (uint32_t)nc, s->idx->col_off.p, s->idx->col_tx.p, d_ci.p, d_mask.p);
+    k_pair_matrix<<<(unsigned)((nc + 255) / 256), 256, 0, s->stream>>>(d_mask.p, d_reads.p, (uint32_t)nc, d_acc.p, d_acc.p + 128);
     HLAC_CUDA(cudaGetLastError());
-    HLAC_CUDA(cudaMemcpyAsync(mask.data(), d_mask.p, 2 * nc * 8, cudaMemcpyDeviceToHost, s->stream));
+    HLAC_CUDA(cudaMemcpyAsync(single.data(), d_acc.p, 128 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
+    HLAC_CUDA(cudaMemcpyAsync(both.data(), d_acc.p + 128, 128 * 128 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
     HLAC_CUDA(cudaStreamSynchronize(s->stream));
-    s->launches++;
+    s->launches += 2;
   }
   auto pair_explained = [&](uint32_t a, uint32_t b) {
-    const int ka = rk.cand_of[a], kb = rk.cand_of[b];
-    const uint64_t lo = (ka < 64 ? 1ull << ka : 0) | (kb < 64 ? 1ull << kb : 0), hi = (ka >= 64 ? 1ull << (ka - 64) : 0) | (kb >= 64 ? 1ull << (kb - 64) : 0);
-    uint64_t e = 0;
-    for (size_t c = 0; c < nc; c++) if ((mask[2 * c] & lo) | (mask[2 * c + 1] & hi)) e += s->fin_cls_reads[c];
-    return (uint32_t)e;
+    int ka = rk.cand_of[a], kb = rk.cand_of[b];
+    if (ka > kb) std::swap(ka, kb);
+    return (uint32_t)(ka == kb ? single[ka] : single[ka] + single[kb] - both[ka * 128 + kb]);
   };
   call_from_ranked(rk, t->nreads, pair_explained, out);
   return HLAC_OK;

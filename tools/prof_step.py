@@ -20,12 +20,19 @@ cf, gf = os.path.join(synth.FIX, "cds_ABC.fa"), os.path.join(synth.FIX, "genomic
 gc, gg = sb.Index.from_fasta(cf), sb.Index.from_fasta(gf)
 s = sb.CountSession(gc, gg, 10000)
 view = {np.dtype("uint64"): np.int64, np.dtype("uint16"): np.int16, np.dtype("uint32"): np.int32, np.dtype("uint8"): np.uint8}
-drec = torch.from_numpy(sb.pack_records(r["seq"], r["len"], r["cell"], r["umi"], r["flags"]).view(np.int64)).cuda()
+fmt = os.environ.get("HLAC_PROF_FORMAT", "wire")
+if fmt == "wire":
+    drec = torch.from_numpy(sb.pack_wire(r["seq"], r["len"], r["cell"], r["umi"], r["flags"], 91, 14, 21).view(np.int32)).cuda()
+else:
+    drec = torch.from_numpy(sb.pack_records(r["seq"], r["len"], r["cell"], r["umi"], r["flags"]).view(np.int64)).cuda()
 s.reserve(n)
 ms = []
 for _ in range(steps):
     s.reset()
-    s.push_packed(drec)
+    if fmt == "wire":
+        s.push_wire(drec, 91, 14, 21)
+    else:
+        s.push_packed(drec)
     ent, met = s.finish_arrays(copy=False)
     ms.append(s.timing()["map_ms"])
 print("ok", len(ent[0]), met, s.timing(), s.probe_stats(), "|", s.shape(), "| map_ms min %.4f" % min(ms[1:] or ms))
