@@ -412,15 +412,30 @@ __global__ void k_colour_bitsets(const uint64_t* __restrict__ col_off, const uin
 constexpr int RES_ITEMS = 8;
 // T = uint16_t when every tx id fits in 16 bits (halves the shared memory), else uint32_t. 256 threads per block: 1024-thread
 // blocks for the long vectors (which only fit one or two blocks per SM) were measured slower (0.44 s vs 0.33 s).
+//
+// r02: where the displaced elements go. The r-th match (at position p_r) swaps with position r; what sat at position r is
+// either an original non-match or, if position r is itself an earlier match position, whatever that earlier swap left
+// there: C(r) = C(rank of the match at r). Following that chain one link at a time (r01) is a serial pointer chase whose
+// length is ~ r / (number of non-matches before r) - thousands of dependent shared-memory loads when a single allele drops
+// out at the front of a 2 000-element vector; the ncu capture of r01 showed 17 % of the kernel's instructions there at
+// 2.9 active lanes and 53 % of the stall samples on the barrier behind it. Inside a stretch between two consecutive
+// non-matches the link length is constant (= the number of non-matches so far, j), so the whole stretch is crossed with one
+// division: from position m, with u the last non-match before m, the chain next touches m - (floor((m - u - 1) / j) + 1) j.
+// A chain now costs at most one hop per non-match it passes. The positions of the non-matches (needed for u) are written,
+// during the scan, into the half of the output vector the matches do not use (matches fill B from the front, the list of
+// non-match positions fills it from the back); the gather then runs in two phases (source index into rk, then move).
+// Membership of an element in the colour being merged is only ever needed for left-to-right maxima, and is read straight
+// from the per-index colour bitsets (global memory, L1-resident rows) when they exist, so the per-merge copy of the bitset
+// into shared memory (11 % of r01's instructions) is gone as well.
 template <typename T, int RES_THREADS>
 __global__ void __launch_bounds__(RES_THREADS) k_resolve_paths_par(const uint32_t* __restrict__ arena, const uint64_t* __restrict__ path_off,
     const uint32_t* __restrict__ path_len, const uint64_t* __restrict__ col_off, const uint32_t* __restrict__ col_tx, uint32_t n_paths,
     const uint64_t* __restrict__ vec_off, uint32_t* vec, uint64_t* vec_hash, uint64_t* vec_hash2, uint32_t n_max, uint32_t bitset_words,
     unsigned int* next_path, const uint32_t* __restrict__ ids, const uint32_t* __restrict__ col_bits) {
   extern __shared__ __align__(16) uint32_t sm[];
-  uint32_t* bits = sm;                                // membership bitset of the current v2 over tx ids
+  uint32_t* bits = sm;                                // membership bitset of the current v2 over tx ids (only without col_bits)
   const uint32_t n_pad = (n_max + 7u) & ~7u;          // 16-byte aligned arrays, readable in whole 8-element groups
-  T* A = reinterpret_cast<T*>(bits + ((bitset_words + 3u) & ~3u));   // current vector
+  T* A = reinterpret_cast<T*>(bits + (col_bits ? 0u : ((bitset_words + 3u) & ~3u)));   // current vector
   T* B = A + n_pad;                                   // next vector
   uint16_t* rk = reinterpret_cast<uint16_t*>(B + n_pad);   // per position: rank + 1 of the match sitting there, 0 if none
   __shared__ uint32_t w_max[2][RES_THREADS / 32], w_cnt[2][RES_THREADS / 32], w_last[2][RES_THREADS / 32];
@@ -440,20 +455,19 @@ __global__ void __launch_bounds__(RES_THREADS) k_resolve_paths_par(const uint32_
     for (uint32_t k = t; k < n; k += RES_THREADS) A[k] = (T)col_tx[col_off[last] + k];
     for (uint32_t sidx = 0; sidx + 1 < plen; sidx++) {
       const uint32_t c = path[sidx];
-      const uint32_t* v2 = col_tx + col_off[c];
-      const uint32_t n2 = (uint32_t)(col_off[c + 1] - col_off[c]);
-      __syncthreads();   // the previous merge has finished with `bits`; orders the A writes of the previous merge / the load
-      if (col_bits) {    // membership bitset of this colour, precomputed once per index: a coalesced copy
-        const uint32_t* src = col_bits + (size_t)c * bitset_words;
-        for (uint32_t k = t; k < bitset_words; k += RES_THREADS) bits[k] = src[k];
-      } else {
+      const uint32_t* mem_row = col_bits ? col_bits + (size_t)c * bitset_words : bits;
+      __syncthreads();   // the previous merge has finished with `bits` / B / rk; orders the A writes of the previous merge / the load
+      if (!col_bits) {   // no precomputed colour bitsets: build this colour's in shared memory
+        const uint32_t* v2 = col_tx + col_off[c];
+        const uint32_t n2 = (uint32_t)(col_off[c + 1] - col_off[c]);
         for (uint32_t k = t; k < bitset_words; k += RES_THREADS) bits[k] = 0;
         __syncthreads();
         for (uint32_t k = t; k < n2; k += RES_THREADS) { const uint32_t x = v2[k]; atomicOr(&bits[x >> 5], 1u << (x & 31)); }
+        __syncthreads();
       }
-      __syncthreads();
-      // matches: left-to-right maxima of A that are members of v2. The r-th match is scattered to B[r] right away.
-      // Each thread owns RES_ITEMS consecutive elements of a tile (thread-local scan, then warp and block scans).
+      // matches: left-to-right maxima of A that are members of v2. The r-th match is scattered to B[r] right away, the
+      // position of the j-th non-match to B[n - 1 - j]. Each thread owns RES_ITEMS consecutive elements of a tile
+      // (thread-local scan, then warp and block scans).
       uint32_t carry = 0, base = 0, last_pos = 0;   // values are compared as x + 1 so that 0 means "nothing yet"
       int par = 0;
       for (uint32_t t0 = 0; t0 < n; t0 += RES_THREADS * RES_ITEMS, par ^= 1) {
@@ -488,7 +502,8 @@ __global__ void __launch_bounds__(RES_THREADS) k_resolve_paths_par(const uint32_
 #pragma unroll
         for (int k = 0; k < RES_ITEMS; k++) {
           const uint32_t prev = k ? max(excl, pm[k - 1]) : excl;
-          const bool match = i0 + k < n && x[k] + 1 > prev && ((bits[x[k] >> 5] >> (x[k] & 31)) & 1u);
+          bool match = i0 + k < n && x[k] + 1 > prev;                                        // a left-to-right maximum ...
+          if (match) match = (mem_row[x[k] >> 5] >> (x[k] & 31)) & 1u;                        // ... that is a member of v2
           if (match) { mflags |= 1u << k; cnt++; my_last = i0 + k + 1; }
         }
         uint32_t incl = cnt;   // warp inclusive scan of the per-thread match counts
@@ -509,6 +524,7 @@ __global__ void __launch_bounds__(RES_THREADS) k_resolve_paths_par(const uint32_
           const bool match = (mflags >> k) & 1u;
           rkv[k] = match ? rank + 1 : 0u;
           if (match) { B[rank] = (T)x[k]; rank++; }
+          else if (i0 + k < n) B[n - 1 - (i0 + k - rank)] = (T)(i0 + k);   // the (i0 + k - rank)-th non-match sits here
         }
         if (i0 < n) *reinterpret_cast<uint4*>(rk + i0) = make_uint4(rkv[0] | (rkv[1] << 16), rkv[2] | (rkv[3] << 16), rkv[4] | (rkv[5] << 16), rkv[6] | (rkv[7] << 16));
         carry = tile_max; base += tile_cnt;
@@ -516,15 +532,26 @@ __global__ void __launch_bounds__(RES_THREADS) k_resolve_paths_par(const uint32_
       __syncthreads();
       const uint32_t M = base;
       if (M == 0 || last_pos == M) continue;   // nothing moves: the matches already occupy 0..M-1 (last_pos = last match position + 1)
+      // phase 1: for every position behind the matches, where its new element comes from
       for (uint32_t i = M + t; i < n; i += RES_THREADS) {
-        uint32_t out;
-        if (rk[i]) {                                       // a match left from here: the displaced element arrives
-          uint32_t m = rk[i] - 1u;
-          while (rk[m] && (uint32_t)(rk[m] - 1u) < m) m = rk[m] - 1u;
-          out = A[m];
-        } else out = A[i];
-        B[i] = (T)out;
+        uint32_t src = i;
+        if (rk[i]) {                                       // a match left from here: a displaced element arrives
+          uint32_t m = rk[i] - 1u;                         // ... the content of position m when the match got there
+          for (;;) {
+            const uint32_t r1 = rk[m];
+            if (r1 == 0) break;                            // an original non-match: this is the element
+            const uint32_t j = m - (r1 - 1u);              // non-matches before m = link length of this stretch
+            if (j == 0) break;
+            const uint32_t u = B[n - j];                   // position of the last non-match before m (the (j-1)-th, 0-based)
+            m -= ((m - u - 1u) / j + 1u) * j;
+          }
+          src = m;
+        }
+        rk[i] = (uint16_t)src;
       }
+      __syncthreads();
+      // phase 2: move
+      for (uint32_t i = M + t; i < n; i += RES_THREADS) B[i] = A[rk[i]];
       __syncthreads();
       T* tmp = A; A = B; B = tmp;
     }
@@ -1117,7 +1144,11 @@ int hlac_geno_finish_begin(hlac_geno* s, uint32_t** umi_hist_device, uint64_t* n
       for (uint32_t i = 0; i < E; i++) n_max = std::max(n_max, olen[i]);
       const uint32_t bitset_words = ((uint32_t)hx.tx_names.size() + 31) / 32;
       const bool narrow = hx.tx_names.size() <= 65535;   // tx ids fit in 16 bits
-      auto smem_for = [&](uint32_t cap) { return (size_t)((bitset_words + 3u) & ~3u) * 4 + (size_t)((cap + 7u) & ~7u) * (narrow ? 2 + 2 + 2 : 4 + 4 + 2) + 16; };
+      // colour membership bitsets: once per index, if they fit comfortably (n_colours x ceil(n_tx/32) words); the kernel then
+      // reads membership from them and needs no bitset of its own in shared memory
+      const bool bits_global = ((s->idx->col_bits.p && s->idx->col_bits_words == bitset_words) ||
+                                (size_t)hx.n_colours() * bitset_words * 4 <= (size_t)4 << 30) && !getenv("HLAC_NO_COLOUR_BITSETS");
+      auto smem_for = [&](uint32_t cap) { return (bits_global ? 0 : (size_t)((bitset_words + 3u) & ~3u) * 4) + (size_t)((cap + 7u) & ~7u) * (narrow ? 2 + 2 + 2 : 4 + 4 + 2) + 16; };
       const size_t smem_par = smem_for(n_max);
       const char* force = getenv("HLAC_RESOLVE");   // "seq" / "par" for testing both kernels
       const bool par_ok = n_max < 65535 && smem_par <= 220 * 1024;
@@ -1129,7 +1160,7 @@ int hlac_geno_finish_begin(hlac_geno* s, uint32_t** umi_hist_device, uint64_t* n
         // colour membership bitsets: once per index, if they fit comfortably (n_colours x ceil(n_tx/32) words)
         hlac_index* ixp = s->idx;
         const uint32_t ncol = hx.n_colours();
-        if (!ixp->col_bits.p && (size_t)ncol * bitset_words * 4 <= (size_t)4 << 30 && !getenv("HLAC_NO_COLOUR_BITSETS")) {
+        if (bits_global && !(ixp->col_bits.p && ixp->col_bits_words == bitset_words)) {
           ixp->col_bits.reserve((size_t)ncol * bitset_words, s->stream);
           HLAC_CUDA(cudaMemsetAsync(ixp->col_bits.p, 0, (size_t)ncol * bitset_words * 4, s->stream));
           k_colour_bitsets<<<(unsigned)(((uint64_t)ncol * 32 + 255) / 256), 256, 0, s->stream>>>(ixp->col_off.p, ixp->col_tx.p, ncol, bitset_words, ixp->col_bits.p);
@@ -1137,7 +1168,7 @@ int hlac_geno_finish_begin(hlac_geno* s, uint32_t** umi_hist_device, uint64_t* n
           ixp->col_bits_words = bitset_words;
           s->launches++;
         }
-        const uint32_t* col_bits = (ixp->col_bits.p && ixp->col_bits_words == bitset_words) ? ixp->col_bits.p : nullptr;
+        const uint32_t* col_bits = bits_global ? ixp->col_bits.p : nullptr;
         std::vector<uint32_t> caps;
         for (uint32_t cap = n_max; ; cap = (cap + 1) / 2) { caps.push_back(cap); if (cap <= 2048 || caps.size() == 4) break; }
         std::vector<std::vector<uint32_t>> groups(caps.size());

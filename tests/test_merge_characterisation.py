@@ -94,3 +94,71 @@ def test_merge_with_the_same_set_twice_is_idempotent():
         c = sorted(rng.sample(range(universe), rng.randint(1, universe)))
         once = merge_reference(v, c)
         assert merge_reference(once, c) == once
+
+
+def _merge_with_stretch_hops(A, v2):
+    """The r02 form of the data-parallel merge (k_resolve_paths_par): matches to the front, the list of non-match positions
+    written from the back of the output vector, and every displaced element located by crossing whole stretches between
+    consecutive non-matches with one division instead of following the chain link by link."""
+    n = len(A)
+    s2 = set(v2)
+    rk, B, rank, pm = [0] * n, [None] * n, 0, -1
+    for i, x in enumerate(A):
+        match = x > pm and x in s2
+        pm = max(pm, x)
+        if match:
+            rk[i] = rank + 1
+            B[rank] = x
+            rank += 1
+        else:
+            B[n - 1 - (i - rank)] = i          # position of the (i - rank)-th non-match
+    M = rank
+    last_pos = max([i + 1 for i in range(n) if rk[i]] or [0])
+    if M == 0 or last_pos == M:
+        return list(A)
+    src = list(range(n))
+    for i in range(M, n):
+        if rk[i]:
+            m = rk[i] - 1
+            while rk[m]:
+                j = m - (rk[m] - 1)            # non-matches before m = link length inside this stretch
+                if j == 0:
+                    break
+                u = B[n - j]                   # the last non-match before m
+                m -= ((m - u - 1) // j + 1) * j
+            src[i] = m
+    for i in range(M, n):
+        B[i] = A[src[i]]
+    return B
+
+
+def test_stretch_hops_equal_the_sequential_walk():
+    import random
+    rng = random.Random(7)
+
+    def seq(v1, v2):
+        v1 = list(v1)
+        f = i = j = 0
+        while i < len(v1) and j < len(v2):
+            if v1[i] < v2[j]:
+                i += 1
+            elif v1[i] > v2[j]:
+                j += 1
+            else:
+                v1[i], v1[f] = v1[f], v1[i]
+                i += 1
+                j += 1
+                f += 1
+        return v1
+    for _ in range(6000):
+        n = rng.randint(1, 80)
+        A = sorted(rng.sample(range(300), n))
+        for _ in range(rng.randint(1, 8)):
+            p = rng.choice([0.05, 0.5, 0.9, 0.98])
+            v2 = sorted(x for x in range(300) if rng.random() < p)
+            want = seq(A, v2)
+            assert _merge_with_stretch_hops(A, v2) == want
+            A = want
+    # the case the hops are for: one allele missing at the front of a long sorted vector (a chain of length n - 1)
+    A = list(range(2000))
+    assert _merge_with_stretch_hops(A, A[1:]) == seq(A, A[1:]) == A[1:] + [0]
