@@ -423,6 +423,31 @@ def main():
         push_host = lambda a, b: sess.push_wire(hrec[a:b], read_len, cell_bits, umi_bits)
         fmt_name = "wire records, %%d B/read (hlac_count_push_wire: %d-bp bases + primary + %d-bit cell + %d-bit UMI key)" % (read_len, cell_bits, umi_bits)
 
+    def h2d_ceiling():
+        """What the platform gives when every rank does nothing but copy its pinned input to its GPU at the same time: the
+        ceiling of the end-to-end leg (GB/s per GPU; the slowest rank counts)."""
+        if fmt == "soa":
+            return None
+        dst = torch.empty_like(drec)
+        for _ in range(2):
+            dst.copy_(hrec_t, non_blocking=True)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(5):
+            dst.copy_(hrec_t, non_blocking=True)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t[0])
+        del dst
+        return in_bytes / (ms / 1e3) / 1e9
+
     def step_device():
         sess.reset()
         push_dev()
@@ -470,6 +495,7 @@ def main():
     if has_result:   # the result arrays are views of the session's pinned buffer: keep a copy across the next loop
         out_dev = (tuple(a.copy() for a in out_dev[0]), out_dev[1])
     ms_e2e, wall_e2e, tm_e2e, clocks_e2e, out_e2e = timed(step_e2e, args.steps, max(args.warmup, 3))
+    ceiling = h2d_ceiling()
     ent, met = out_dev
     if has_result:
         assert all(np.array_equal(a, b) for a, b in zip(ent, out_e2e[0])), "device-resident and host-fed passes disagree"
@@ -538,6 +564,9 @@ def main():
                 "e2e": {"value": total_reads / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": in_bytes * world,
                         "d2h_bytes_per_step": d2h_own, "ms_per_step": e2e_ms, "h2d_ms": tm_e2e["h2d_ms"],
                         "h2d_gbs_per_gpu": in_bytes / (tm_e2e["h2d_ms"] / 1e3) / 1e9 if tm_e2e["h2d_ms"] > 0 else None,
+                        "h2d_ceiling_gbs_per_gpu": ceiling,
+                        "h2d_ceiling_note": "all %d ranks copying their pinned input and nothing else, slowest rank; the e2e leg cannot beat "
+                                            "bytes / this (%.2f ms per step)" % (world, in_bytes / ceiling / 1e6) if ceiling else None,
                         "input_format": fmt_name % (in_bytes // n)},
                 # counted by the session itself (hlac_count_timing): every kernel of ours launched in one step, times the steps.
                 # No library kernel runs on the normal path (cub only sorts on the bucket-overflow fallback; fallbacks below).

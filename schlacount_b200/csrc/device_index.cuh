@@ -159,11 +159,23 @@ __device__ __forceinline__ int left_extend(G gr, RD rd, int L, int pos, uint32_t
       const int m = min(lp + 1, po + 1);
       int matched = 0, snp = 0;
       bool brk = false;
-      for (int i = 0; i < m; i++) {
-        if (base_at(ns, (int)p0.x + po - i) != base_at(rd, lp - i)) {
-          if (++snp > ALLOWED_MISMATCH) { brk = true; break; }
+      // read bases lp, lp-1, ... against node bases po, po-1, ...: <= 16 at a time, XOR + popcount, exact "stop at the third
+      // mismatch" (tolerated mismatches count as covered, the breaking one does not) - the same arithmetic as the forward
+      // walk, mirrored: the base nearest the seed sits in the low bits
+      while (matched < m) {
+        const int c = min(16, m - matched);
+        const uint32_t wr = ext16(rd, lp - matched - c + 1) >> (32 - 2 * c);
+        const uint32_t wn = ext16(ns, (int)p0.x + po - matched - c + 1) >> (32 - 2 * c);
+        uint32_t x = wr ^ wn;
+        x = (x | (x >> 1)) & 0x55555555u;
+        const int pc = __popc(x);
+        if (snp + pc > ALLOWED_MISMATCH) {
+          for (int t = snp; t < ALLOWED_MISMATCH; t++) x &= x - 1;   // drop the mismatches still tolerated
+          matched += (__ffs((int)x) - 1) >> 1;                        // bases before the breaking one
+          brk = true;
+          break;
         }
-        matched++;
+        snp += pc; matched += c;
       }
       cov += matched;
       if (lp + 1 - matched == 0 || brk) break;
