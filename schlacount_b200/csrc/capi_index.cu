@@ -47,6 +47,15 @@ HostIndex::PairSorter sorter_for(int device) {
   if (device < 0 || cudaGetDeviceCount(&ndev) != cudaSuccess || device >= ndev) return nullptr;
   return device_sort_pairs;
 }
+// build_index: on the device when there is one (HLAC_INDEX_BUILD=host forces the host threads + device sort of round 1),
+// on the host for device-less handles, tiny inputs and the rare graphs the device build declines
+void build_index_for(const std::vector<Bases>& seqs, const std::vector<std::string>& names, HostIndex& host, int device) {
+  const char* how = getenv("HLAC_INDEX_BUILD");
+  const bool want_host = how && std::string(how) == "host";
+  if (sorter_for(device) && !want_host && device_build_index(seqs, names, host, device)) return;
+  std::unique_ptr<DeviceGuard> g; if (sorter_for(device)) g = std::make_unique<DeviceGuard>(device);
+  HostIndex::build(seqs, names, host, sorter_for(device));
+}
 }  // namespace
 
 extern "C" {
@@ -96,8 +105,7 @@ int hlac_index_from_fasta(const char* fasta_path, const char* allele_status, int
   std::vector<Bases> seqs; std::vector<std::string> names;
   read_hla_cds(fasta_path, keep, allele_status != nullptr, seqs, names);
   auto ix = std::make_unique<hlac_index>();
-  { std::unique_ptr<DeviceGuard> g; if (sorter_for(device)) g = std::make_unique<DeviceGuard>(device);
-    HostIndex::build(seqs, names, ix->host, sorter_for(device)); }
+  build_index_for(seqs, names, ix->host, device);
   ix->upload(device);
   *out = ix.release();
   HLAC_API_END
@@ -115,8 +123,7 @@ int hlac_index_from_sequences(const uint64_t* packed, const uint64_t* seq_word_s
     nm[i] = names[i];
   }
   auto ix = std::make_unique<hlac_index>();
-  { std::unique_ptr<DeviceGuard> g; if (sorter_for(device)) g = std::make_unique<DeviceGuard>(device);
-    HostIndex::build(seqs, nm, ix->host, sorter_for(device)); }
+  build_index_for(seqs, nm, ix->host, device);
   ix->upload(device);
   *out = ix.release();
   HLAC_API_END

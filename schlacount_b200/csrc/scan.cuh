@@ -9,7 +9,7 @@
 namespace hlac {
 namespace scan_detail {
 constexpr int T = 256, PER = 8, TILE = T * PER;
-__global__ void __launch_bounds__(T) k_tile_sums(const uint32_t* __restrict__ in, uint64_t n, uint64_t* tile_sum) {
+static __global__ void __launch_bounds__(T) k_tile_sums(const uint32_t* __restrict__ in, uint64_t n, uint64_t* tile_sum) {
   __shared__ uint64_t w[T / 32];
   const uint64_t base = (uint64_t)blockIdx.x * TILE + (uint64_t)threadIdx.x * PER;
   uint64_t s = 0;
@@ -21,7 +21,7 @@ __global__ void __launch_bounds__(T) k_tile_sums(const uint32_t* __restrict__ in
   if (threadIdx.x == 0) { uint64_t t = 0; for (int k = 0; k < T / 32; k++) t += w[k]; tile_sum[blockIdx.x] = t; }
 }
 // one block: exclusive scan of the tile sums in place; total to tile_sum[n_tiles]
-__global__ void __launch_bounds__(1024) k_scan_tiles(uint64_t* tile_sum, uint32_t n_tiles) {
+static __global__ void __launch_bounds__(1024) k_scan_tiles(uint64_t* tile_sum, uint32_t n_tiles) {
   __shared__ uint64_t part[1024];
   __shared__ uint64_t carry;
   if (threadIdx.x == 0) carry = 0;
@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(uint64_t* tile_sum, uint32_
   }
   if (threadIdx.x == 0) tile_sum[n_tiles] = carry;
 }
-__global__ void __launch_bounds__(T) k_tile_scan(const uint32_t* __restrict__ in, uint64_t n, const uint64_t* __restrict__ tile_off, uint64_t* out) {
+static __global__ void __launch_bounds__(T) k_tile_scan(const uint32_t* __restrict__ in, uint64_t n, const uint64_t* __restrict__ tile_off, uint64_t* out) {
   __shared__ uint64_t w[T / 32];
   const uint64_t base = (uint64_t)blockIdx.x * TILE + (uint64_t)threadIdx.x * PER;
   uint32_t v[PER]; uint64_t s = 0;

@@ -316,3 +316,39 @@ def test_squarem_persistent_vs_host_loop(sb, orc, monkeypatch):
             assert np.abs(th - th_h).max() < 5e-3                      # EM_ABS_TH
             l, lh = loglik(ds, th), loglik(ds, th_h)
             assert abs(l - lh) <= 1e-6 * abs(lh), (l, lh)
+
+
+@pytest.mark.parametrize("n_per_gene,extra,seed", [(80, (), 51), (400, ("DRB1", "DQB1"), 52), (1500, ("DRB1", "DPA1", "DPB1", "DQA1", "DQB1"), 53)])
+def test_device_index_build_equals_host_build(sb, orc, tmp_path, monkeypatch, n_per_gene, extra, seed):
+    """build_index as kernels (device_build.cu: occurrences, sort, colour interning, unitig compaction by pointer jumping,
+    adjacency / dictionary / l-mer bitmap) must produce the index the host build produces - same nodes in the same order, same
+    colour numbering - i.e. the same bincode Pseudoaligner file byte for byte (the host build reproduces the reference's own
+    hla_nuc.fasta.idx, tests/test_host_cpu.py), the same derived sizes, and the oracle's node set."""
+    from tools import synth
+    db = str(tmp_path / "db")
+    synth.make_db(db, n_per_gene, seed, extra_genes=extra)
+    fa, st = os.path.join(db, "hla_nuc.fasta"), os.path.join(db, "Allele_status.txt")
+    monkeypatch.delenv("HLAC_INDEX_BUILD", raising=False)
+    dev = sb.Index.from_fasta(fa, st)
+    monkeypatch.setenv("HLAC_INDEX_BUILD", "host")
+    host = sb.Index.from_fasta(fa, st)
+    monkeypatch.delenv("HLAC_INDEX_BUILD", raising=False)
+    assert dev.info == host.info and dev.tx_names == host.tx_names
+    a, b = str(tmp_path / "dev.idx"), str(tmp_path / "host.idx")
+    dev.write_idx(a)
+    host.write_idx(b)
+    assert open(a, "rb").read() == open(b, "rb").read()
+    if n_per_gene <= 400:
+        oix = orc.Index.from_fasta(fa, st)
+        assert sorted(dev.nodes()) == sorted(oix.nodes())
+    # and it maps like the host-built one: same coverage and classes on reads of the database
+    names = dev.tx_names
+    r = synth.reads_for_db(20_000, db, [names[1], names[len(names) // 2], names[-2]], 50, seed)
+    out = []
+    for ix in (dev, host):
+        g = sb.GenoSession(ix, record_reads=True)
+        g.push(r["seq"], r["len"], r["cell"], r["umi"])
+        cov = g.last_cov()
+        t = g.finish(raw=True)
+        out.append((cov, g.read_class_ids(len(cov)), t))
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1]) and out[0][2] == out[1][2]
