@@ -1,7 +1,9 @@
 // C ABI: error state, index construction, host helpers (include/hlacount.h). Product code.
 #include <cub/device/device_radix_sort.cuh>
 
+#include <cstdio>
 #include <cstring>
+#include <ctime>
 #include <memory>
 
 #include "device_index.hpp"
@@ -49,10 +51,10 @@ HostIndex::PairSorter sorter_for(int device) {
 }
 // build_index: on the device when there is one (HLAC_INDEX_BUILD=host forces the host threads + device sort of round 1),
 // on the host for device-less handles, tiny inputs and the rare graphs the device build declines
-void build_index_for(const std::vector<Bases>& seqs, const std::vector<std::string>& names, HostIndex& host, int device) {
+void build_index_for(const std::vector<Bases>& seqs, const std::vector<std::string>& names, HostIndex& host, int device, DeviceIndexParts* keep) {
   const char* how = getenv("HLAC_INDEX_BUILD");
   const bool want_host = how && std::string(how) == "host";
-  if (sorter_for(device) && !want_host && device_build_index(seqs, names, host, device)) return;
+  if (sorter_for(device) && !want_host && device_build_index(seqs, names, host, device, keep)) return;
   std::unique_ptr<DeviceGuard> g; if (sorter_for(device)) g = std::make_unique<DeviceGuard>(device);
   HostIndex::build(seqs, names, host, sorter_for(device));
 }
@@ -103,10 +105,17 @@ int hlac_index_from_fasta(const char* fasta_path, const char* allele_status, int
   std::set<std::string> keep;
   if (allele_status) keep = load_allele_status(allele_status);
   std::vector<Bases> seqs; std::vector<std::string> names;
+  const bool dbg = getenv("HLAC_DEBUG_TIMING") != nullptr;
+  auto now = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + ts.tv_nsec * 1e-9; };
+  double t0 = now();
   read_hla_cds(fasta_path, keep, allele_status != nullptr, seqs, names);
+  if (dbg) { fprintf(stderr, "[hlac timing] index: read_hla_cds                 %.3f s\n", now() - t0); t0 = now(); }
   auto ix = std::make_unique<hlac_index>();
-  build_index_for(seqs, names, ix->host, device);
-  ix->upload(device);
+  DeviceIndexParts parts;
+  build_index_for(seqs, names, ix->host, device, &parts);
+  if (dbg) { fprintf(stderr, "[hlac timing] index: build                        %.3f s\n", now() - t0); t0 = now(); }
+  ix->upload(device, &parts);
+  if (dbg) { fprintf(stderr, "[hlac timing] index: make resident                %.3f s\n", now() - t0); t0 = now(); }
   *out = ix.release();
   HLAC_API_END
 }
@@ -123,8 +132,9 @@ int hlac_index_from_sequences(const uint64_t* packed, const uint64_t* seq_word_s
     nm[i] = names[i];
   }
   auto ix = std::make_unique<hlac_index>();
-  build_index_for(seqs, nm, ix->host, device);
-  ix->upload(device);
+  DeviceIndexParts parts;
+  build_index_for(seqs, nm, ix->host, device, &parts);
+  ix->upload(device, &parts);
   *out = ix.release();
   HLAC_API_END
 }
@@ -137,6 +147,13 @@ int hlac_index_clone(const hlac_index* src, int device, hlac_index** out) {
   auto ix = std::make_unique<hlac_index>();
   ix->host = src->host;
   ix->upload(device);
+  if (src->dict_device_only && device >= 0) {   // the dictionary exists on the source device only
+    DeviceGuard g(device);
+    ix->dict.reserve(src->dict.cap);
+    HLAC_CUDA(cudaMemcpyPeer(ix->dict.p, device, src->dict.p, src->device, ((size_t)16 << src->host.dict_bits)));
+    ix->view.dict = reinterpret_cast<const uint4*>(ix->dict.p);
+    ix->dict_device_only = true;
+  }
   *out = ix.release();
   HLAC_API_END
 }

@@ -23,6 +23,7 @@
 #include <cstdlib>
 
 #include "cuda_util.hpp"
+#include "device_index.hpp"
 #include "host_index.hpp"
 #include "scan.cuh"
 
@@ -266,7 +267,7 @@ inline unsigned blocks(uint64_t n, unsigned t = 256) { return (unsigned)((n + t 
 
 }  // namespace
 
-bool device_build_index(const std::vector<Bases>& seqs, const std::vector<std::string>& names, HostIndex& ix, int device) {
+bool device_build_index(const std::vector<Bases>& seqs, const std::vector<std::string>& names, HostIndex& ix, int device, DeviceIndexParts* keep) {
   const bool dbg = getenv("HLAC_DEBUG_TIMING") != nullptr;
   auto t_last = std::chrono::steady_clock::now();
   auto tick = [&](const char* what) {
@@ -423,7 +424,12 @@ bool device_build_index(const std::vector<Bases>& seqs, const std::vector<std::s
   { std::vector<uint32_t> e; fetch(e, nexts.p, nn); ix.exts.resize(nn); for (size_t i = 0; i < nn; i++) ix.exts[i] = (uint8_t)e[i]; }
   fetch(ix.col_off, col_off.p, ncol + 1); fetch(ix.col_tx, col_tx.p, ncoltx);
   fetch(ix.radj, radj.p, nn * 4); fetch(ix.ladj, ladj.p, nn * 4);
-  fetch(ix.dict, dict.p, (size_t)4 << dict_bits); fetch(ix.bitmap, bitmap.p, (size_t)((1ULL << (2 * lmer)) / 32));
+  fetch(ix.bitmap, bitmap.p, (size_t)((1ULL << (2 * lmer)) / 32));
+  if (keep) {   // the resident copies stay where they are; the dictionary (the largest part, read by kernels only) is not downloaded
+    auto give = [](auto& dst, auto& src) { std::swap(dst.p, src.p); std::swap(dst.cap, src.cap); };
+    give(keep->seq32, seq32); give(keep->dict, dict); give(keep->bitmap, bitmap); give(keep->col_tx, col_tx); give(keep->col_off, col_off);
+    keep->device = device; keep->valid = true;
+  } else fetch(ix.dict, dict.p, (size_t)4 << dict_bits);
   tick("download");
   return true;
 }

@@ -4,7 +4,7 @@
 
 using namespace hlac;
 
-void hlac_index::upload(int dev) {
+void hlac_index::upload(int dev, DeviceIndexParts* parts) {
   if (dev == -1) { device = -1; return; }   // host-only handle: inspection (hlac_index_node/info) but no compute
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
@@ -22,12 +22,19 @@ void hlac_index::upload(int dev) {
     r[0] = host.start[i]; r[1] = host.len[i]; r[2] = host.exts[i]; r[3] = host.colour[i];
     for (int b = 0; b < 4; b++) { r[4 + b] = host.radj[(size_t)i * 4 + b]; r[8 + b] = host.ladj[(size_t)i * 4 + b]; }
   }
-  seq32.upload(host.seq32.data(), host.seq32.size());
-  dict.upload(host.dict.data(), host.dict.size());
+  auto take = [](auto& dst, auto& src) { std::swap(dst.p, src.p); std::swap(dst.cap, src.cap); };
+  if (parts && parts->valid && parts->device == dev) {   // built on this device: adopt the buffers instead of copying them back up
+    take(seq32, parts->seq32); take(dict, parts->dict); take(bitmap, parts->bitmap); take(col_tx, parts->col_tx); take(col_off, parts->col_off);
+    dict_device_only = host.dict.empty();
+    parts->valid = false;
+  } else {
+    seq32.upload(host.seq32.data(), host.seq32.size());
+    if (!host.dict.empty()) dict.upload(host.dict.data(), host.dict.size());
+    bitmap.upload(host.bitmap.data(), host.bitmap.size());
+    col_tx.upload(host.col_tx.data(), host.col_tx.size());
+    col_off.upload(host.col_off.data(), host.col_off.size());
+  }
   nodes.upload(rec.data(), rec.size());
-  bitmap.upload(host.bitmap.data(), host.bitmap.size());
-  col_tx.upload(host.col_tx.data(), host.col_tx.size());
-  col_off.upload(host.col_off.data(), host.col_off.size());
   HLAC_CUDA(cudaDeviceSynchronize());
   view.seq32 = seq32.p;
   view.nodes = reinterpret_cast<const uint4*>(nodes.p);

@@ -50,7 +50,10 @@ struct HostIndex {
 
 // build_index as kernels on `device` (device_build.cu): fills `out` exactly as HostIndex::build would (same node and colour
 // numbering). Returns false when it declines (tiny input, closed cycles of interior links): the caller then builds on the host.
-bool device_build_index(const std::vector<Bases>& seqs, const std::vector<std::string>& names, HostIndex& out, int device);
+// `keep` (optional) receives the device buffers of the parts that hlac_index::upload would otherwise copy back up (the
+// dictionary is then not downloaded at all: nothing on the host reads it).
+struct DeviceIndexParts;
+bool device_build_index(const std::vector<Bases>& seqs, const std::vector<std::string>& names, HostIndex& out, int device, DeviceIndexParts* keep = nullptr);
 
 // multiplicative hash shared by host build and device probe
 inline uint32_t dict_hash(uint64_t kmer, uint32_t bits) { return (uint32_t)((kmer * 0x9E3779B97F4A7C15ULL) >> (64 - bits)); }
