@@ -1,6 +1,4 @@
 // C ABI: error state, index construction, host helpers (include/hlacount.h). Product code.
-#include <cub/device/device_radix_sort.cuh>
-
 #include <cstdio>
 #include <cstring>
 #include <ctime>
@@ -8,6 +6,7 @@
 
 #include "device_index.hpp"
 #include "hla_fasta.hpp"
+#include "radix_sort.cuh"
 
 using namespace hlac;
 
@@ -35,14 +34,11 @@ int seed_stride() {
 namespace {
 // build_index's dominant step on the device: stable radix sort of the (k-mer, payload) occurrence pairs
 void device_sort_pairs(uint64_t* keys, uint64_t* vals, size_t n) {
-  DevBuf<uint64_t> k0, k1, v0, v1; DevBuf<uint8_t> tmp;
+  DevBuf<uint64_t> k0, k1, v0, v1; RadixSortScratch rs;
   k0.upload(keys, n); v0.upload(vals, n); k1.reserve(n); v1.reserve(n);
-  size_t bytes = 0;
-  HLAC_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, k0.p, k1.p, v0.p, v1.p, (uint64_t)n, 0, 2 * K));
-  tmp.reserve(bytes);
-  HLAC_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, k0.p, k1.p, v0.p, v1.p, (uint64_t)n, 0, 2 * K));
-  HLAC_CUDA(cudaMemcpy(keys, k1.p, n * 8, cudaMemcpyDeviceToHost));
-  HLAC_CUDA(cudaMemcpy(vals, v1.p, n * 8, cudaMemcpyDeviceToHost));
+  const bool second = radix_sort_pairs(k0.p, k1.p, v0.p, v1.p, (uint64_t)n, 0, 2 * K, rs, (cudaStream_t)0);
+  HLAC_CUDA(cudaMemcpy(keys, second ? k1.p : k0.p, n * 8, cudaMemcpyDeviceToHost));
+  HLAC_CUDA(cudaMemcpy(vals, second ? v1.p : v0.p, n * 8, cudaMemcpyDeviceToHost));
 }
 HostIndex::PairSorter sorter_for(int device) {
   int ndev = 0;

@@ -11,7 +11,7 @@
 //   K4  k_coo_count/_scan/_write  dense matrix -> ordered COO triplets written straight into host-mapped pinned memory,
 //                           together with the counters: the host synchronises ONCE per finish.
 // Fallback (a bucket overflowed: a molecule deeper than a bucket, or a hostile hash pattern): all keys are gathered, sorted
-// with cub and reduced by k_consensus — the round-1 path, kept for exactness, never on the normal path.
+// (radix_sort.cuh) and reduced by k_consensus, one thread per (cell, UMI) run — kept for exactness, never on the normal path.
 //
 // Laziness: the reference evaluates all four map_read calls eagerly but only consumes them through the if/else-if
 // chain at mapping.rs:772-793; map_read is pure, so evaluating a call only when the chain reaches it yields the
@@ -23,8 +23,6 @@
 // 2-element sorted list [p,q] they can only ever swap it to [q,p] (which then misses the table), and that happens
 // iff some other visited node's colour contains q but not p. So per colour we precompute `cinfo`: the code it
 // yields as a final class and a per-gene "would swap" mask; the walk ORs the masks.
-#include <cub/device/device_radix_sort.cuh>
-
 #include <algorithm>
 #include <cstring>
 #include <memory>
@@ -33,6 +31,7 @@
 #include "comm.hpp"
 #include "device_index.hpp"
 #include "hla_fasta.hpp"
+#include "radix_sort.cuh"
 
 using namespace hlac;
 
@@ -500,7 +499,7 @@ __global__ void k_rebucket(const BucketStore from, const BucketStore to) {
   }
 }
 
-// ---- fallback path: gather every key into one array, cub radix sort, one thread per (cell, UMI) run ------------------
+// ---- fallback path: gather every key into one array, radix sort, one thread per (cell, UMI) run ------------------
 __global__ void k_gather_keys(const BucketStore bs, uint64_t* out, unsigned long long* cursor) {
   __shared__ unsigned long long base;
   for (uint32_t b = blockIdx.x; b <= bs.mask; b += gridDim.x) {
@@ -648,7 +647,7 @@ struct hlac_count {
   int primary_only = 0;
   DevBuf<uint32_t> nodes_cds, nodes_gen, gene_row0, dense;   // node tables with cinfo in place of the colour id
   // bucket store of the scored reads' keys; `keys` = overflow list (and the gather target of the fallback path)
-  DevBuf<uint64_t> bk_keys, keys, keys_sorted;
+  DevBuf<uint64_t> bk_keys, keys, keys_sorted, keys_tmp;
   DevBuf<uint32_t> bk_fill;
   uint32_t n_buckets = 0;
   uint64_t host_reads = 0, host_non_primary = 0, host_not_cell = 0;   // reads the host driver filtered out itself (hlac_count_add_filtered)
@@ -666,7 +665,7 @@ struct hlac_count {
   // [12] gather cursor (fallback)
   // [13..15] reads the host driver filtered out itself (uploaded at finish so that a merge sums them like the others)
   DevBuf<unsigned long long> counters, counters_merged;
-  DevBuf<uint8_t> cub_tmp;
+  RadixSortScratch rs_scratch;
   uint64_t reads_pushed = 0, last_n = 0;
   bool smem_bm = false;
   size_t bitmap_smem_bytes = 0;
@@ -853,25 +852,24 @@ struct hlac_count {
     const uint64_t n_ovf = c[11];
     if (n_ovf > keys.cap) throw Error(HLAC_ERR_STATE, "overflow list overran (internal error)");
     HLAC_CUDA(cudaMemsetAsync(dense.p, 0, nd() * sizeof(uint32_t), stream));
+    // work arrays of the sort (the overflow list itself stays intact: a later finish of the same session needs it again)
+    const uint64_t upper = n_ovf + std::min<uint64_t>(reads_pushed, (uint64_t)n_buckets * BUCKET_CAP);
+    keys_sorted.reserve(std::max<uint64_t>(upper, 1), stream); keys_tmp.reserve(std::max<uint64_t>(upper, 1), stream);
+    if (n_ovf) HLAC_CUDA(cudaMemcpyAsync(keys_sorted.p, keys.p, n_ovf * 8, cudaMemcpyDeviceToDevice, stream));
     unsigned long long cur = n_ovf;   // bucket contents are appended behind the overflow entries
     HLAC_CUDA(cudaMemcpyAsync(counters.p + 12, &cur, 8, cudaMemcpyHostToDevice, stream));
-    keys.reserve(n_ovf + (uint64_t)std::min<uint64_t>(reads_pushed, (uint64_t)n_buckets * BUCKET_CAP), stream, true, n_ovf);
-    k_gather_keys<<<std::min<uint32_t>(n_buckets, (uint32_t)n_sm * 8), 256, 0, stream>>>(store(), keys.p, counters.p + 12);
+    k_gather_keys<<<std::min<uint32_t>(n_buckets, (uint32_t)n_sm * 8), 256, 0, stream>>>(store(), keys_sorted.p, counters.p + 12);
     HLAC_CUDA(cudaGetLastError());
     HLAC_CUDA(cudaMemcpyAsync(&cur, counters.p + 12, 8, cudaMemcpyDeviceToHost, stream));
     HLAC_CUDA(cudaStreamSynchronize(stream));
     const uint64_t nk = cur;
     if (nk) {
-      keys_sorted.reserve(nk, stream);
       int umi_bits = 1;
       while (umi_bits < UMI_BITS && (c[10] >> umi_bits)) umi_bits++;
       const int end_bit = CODE_BITS + (int)cell_bits + umi_bits;
-      size_t tmp = 0;
-      HLAC_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tmp, keys.p, keys_sorted.p, (uint64_t)nk, CODE_BITS, end_bit, stream));
-      cub_tmp.reserve(tmp, stream);
       Ev& e1 = begin(1);
-      HLAC_CUDA(cub::DeviceRadixSort::SortKeys(cub_tmp.p, tmp, keys.p, keys_sorted.p, (uint64_t)nk, CODE_BITS, end_bit, stream));
-      k_consensus<<<(unsigned)((nk + 255) / 256), 256, 0, stream>>>(keys_sorted.p, nk, dense.p, rows.nrows, gene_row0.p, cell_bits);
+      const bool second = radix_sort_pairs<uint64_t, uint32_t>(keys_sorted.p, keys_tmp.p, nullptr, nullptr, (uint64_t)nk, CODE_BITS, end_bit, rs_scratch, stream);
+      k_consensus<<<(unsigned)((nk + 255) / 256), 256, 0, stream>>>(second ? keys_tmp.p : keys_sorted.p, nk, dense.p, rows.nrows, gene_row0.p, cell_bits);
       HLAC_CUDA(cudaGetLastError());
       end(e1);
       launches += 2;

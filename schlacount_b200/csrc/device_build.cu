@@ -2,8 +2,8 @@
 //
 // The stranded k = 24 coloured compacted de Bruijn graph from the allele sequences, as kernels:
 //   1  k_enum            one (k-mer, tx << 16 | left-ext mask << 8 | right-ext mask) pair per k-mer occurrence
-//   2  radix sort        stable, by k-mer (cub: the one library call of the build; occurrences are generated in ascending tx order,
-//                        so every k-mer's tx list comes out sorted)
+//   2  radix sort        stable, by k-mer (radix_sort.cuh; occurrences are generated in ascending tx order, so every k-mer's tx list
+//                        comes out sorted)
 //   3  k_heads + scan    distinct k-mers; k_uniq_summary (one warp per k-mer): ext masks, size and hash of its de-duplicated tx list
 //   4  colours           k_col_insert: hash table keyed by (list hash, list size), per slot the smallest k-mer rank that uses it;
 //                        the k-mers that define a colour, scanned in k-mer order, give the colour ids in first-appearance order
@@ -16,8 +16,6 @@
 //                        k_lmers (+ popcount) for the presence bitmap of the skip-scan seed filter
 // Everything lands in a HostIndex (the .idx writer and the inspection calls work on it) that hlac_index::upload then makes resident.
 // Declines (returns false, the caller builds on the host) for tiny inputs and for graphs with closed cycles of interior links.
-#include <cub/device/device_radix_sort.cuh>
-
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -25,6 +23,7 @@
 #include "cuda_util.hpp"
 #include "device_index.hpp"
 #include "host_index.hpp"
+#include "radix_sort.cuh"
 #include "scan.cuh"
 
 namespace hlac {
@@ -297,14 +296,9 @@ bool device_build_index(const std::vector<Bases>& seqs, const std::vector<std::s
   HLAC_CUDA(cudaGetLastError());
   tick("upload + enumerate");
   // ---- 2: stable sort by k-mer ----
-  {
-    DevBuf<uint8_t> tmp; size_t bytes = 0;
-    HLAC_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, k0.p, k1.p, v0.p, v1.p, total, 0, 2 * K, st));
-    tmp.reserve(bytes, st);
-    HLAC_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, k0.p, k1.p, v0.p, v1.p, total, 0, 2 * K, st));
-    HLAC_CUDA(cudaStreamSynchronize(st));
-  }
-  const uint64_t* keys = k1.p; const uint64_t* vals = v1.p;
+  RadixSortScratch rs;
+  const bool second = radix_sort_pairs(k0.p, k1.p, v0.p, v1.p, total, 0, 2 * K, rs, st);
+  const uint64_t* keys = second ? k1.p : k0.p; const uint64_t* vals = second ? v1.p : v0.p;
   tick("sort occurrences");
   // ---- 3: distinct k-mers ----
   DevBuf<uint32_t> hflag, dflag; DevBuf<uint64_t> hexcl, dscan;

@@ -5,8 +5,6 @@
 // The reference iterates a std HashMap (summation order unspecified, hence the 1e-6 tolerance); here the scatter is a
 // deterministic gather over the transposed CSR (one warp per tx, fixed tree order), so runs are reproducible.
 // No tensor cores: nothing here is a dense contraction.
-#include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_scan.cuh>
 
 #include <algorithm>
 #include <cmath>
@@ -20,6 +18,8 @@
 
 #include "caller.hpp"
 #include "device_index.hpp"
+#include "radix_sort.cuh"
+#include "scan.cuh"
 
 using namespace hlac;
 
@@ -315,13 +315,12 @@ __global__ void k_entry_class(const uint64_t* __restrict__ off, uint64_t nc, uin
   if (c >= nc) return;
   for (uint64_t q = off[c] + (threadIdx.x & 31); q < off[c + 1]; q += 32) cls_of_entry[q] = (uint32_t)c;
 }
-__global__ void k_tx_hist(const uint32_t* __restrict__ tx, uint64_t nnz, uint32_t n, unsigned long long* hist1 /* [n + 1], slot t + 1 */,
-                          unsigned int* bad) {
+__global__ void k_tx_hist(const uint32_t* __restrict__ tx, uint64_t nnz, uint32_t n, uint32_t* hist /* [n] */, unsigned int* bad) {
   const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= nnz) return;
   const uint32_t t = tx[q];
   if (t >= n) { *bad = 1; return; }
-  atomicAdd(hist1 + t + 1, 1ull);
+  atomicAdd(hist + t, 1u);
 }
 
 struct EmDevice {
@@ -380,19 +379,19 @@ int hlac_squarem(const hlac_class_tables* t, int device, double* theta_out, uint
   em.toff.reserve(n + 1, st); em.tcls.reserve(std::max<uint64_t>(nnz, 1), st);
   HLAC_CUDA(cudaMemsetAsync(em.toff.p, 0, ((size_t)n + 1) * 8, st));
   if (nnz) {
-    DevBuf<uint32_t> cls_of_entry, keys_sorted; DevBuf<unsigned int> bad; DevBuf<uint8_t> tmp;
-    cls_of_entry.reserve(nnz, st); keys_sorted.reserve(nnz, st); bad.reserve(1, st);
+    DevBuf<uint32_t> cls_of_entry, cls_b, keys_a, keys_b, tx_hist; DevBuf<unsigned int> bad; DevBuf<uint64_t> scan_tmp; RadixSortScratch rs;
+    cls_of_entry.reserve(nnz, st); cls_b.reserve(nnz, st); keys_a.reserve(nnz, st); keys_b.reserve(nnz, st); tx_hist.reserve(n, st); bad.reserve(1, st);
     HLAC_CUDA(cudaMemsetAsync(bad.p, 0, 4, st));
+    HLAC_CUDA(cudaMemsetAsync(tx_hist.p, 0, (size_t)n * 4, st));
     k_entry_class<<<(unsigned)((nc * 32 + 255) / 256), 256, 0, st>>>(em.off.p, nc, cls_of_entry.p);
-    k_tx_hist<<<(unsigned)((nnz + 255) / 256), 256, 0, st>>>(em.tx.p, nnz, n, reinterpret_cast<unsigned long long*>(em.toff.p), bad.p);
+    k_tx_hist<<<(unsigned)((nnz + 255) / 256), 256, 0, st>>>(em.tx.p, nnz, n, tx_hist.p, bad.p);
     HLAC_CUDA(cudaGetLastError());
+    exclusive_scan_u32(tx_hist.p, em.toff.p, n, scan_tmp, st);   // toff[t] = entries of tx < t, toff[n] = nnz
+    // (tx, class) pairs sorted by tx, stable: entries are generated in class order, so every tx's class list comes out ascending
     int bits = 1; while (bits < 32 && (1ull << bits) < n) bits++;
-    size_t tb = 0, tb2 = 0;
-    HLAC_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, em.tx.p, keys_sorted.p, cls_of_entry.p, em.tcls.p, nnz, 0, bits, st));
-    HLAC_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tb2, em.toff.p, em.toff.p, (size_t)n + 1, st));
-    tmp.reserve(std::max(tb, tb2), st);
-    HLAC_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, em.tx.p, keys_sorted.p, cls_of_entry.p, em.tcls.p, nnz, 0, bits, st));
-    HLAC_CUDA(cub::DeviceScan::InclusiveSum(tmp.p, tb2, em.toff.p, em.toff.p, (size_t)n + 1, st));
+    HLAC_CUDA(cudaMemcpyAsync(keys_a.p, em.tx.p, nnz * 4, cudaMemcpyDeviceToDevice, st));
+    const bool second = radix_sort_pairs(keys_a.p, keys_b.p, cls_of_entry.p, cls_b.p, (uint64_t)nnz, 0, bits, rs, st);
+    HLAC_CUDA(cudaMemcpyAsync(em.tcls.p, second ? cls_b.p : cls_of_entry.p, nnz * 4, cudaMemcpyDeviceToDevice, st));
     unsigned int hbad = 0;
     HLAC_CUDA(cudaMemcpyAsync(&hbad, bad.p, 4, cudaMemcpyDeviceToHost, st));
     HLAC_CUDA(cudaMemcpyAsync(toff.data(), em.toff.p, ((size_t)n + 1) * 8, cudaMemcpyDeviceToHost, st));

@@ -9,7 +9,6 @@
 // lets the GPU em_wrapper consume a counts file written by the reference's mapping_wrapper. The grouping by
 // (barcode, umi), the per-UMI lowest class id and the per-class histograms run on the GPU; only the
 // sort + dedup of the (few) distinct class vectors into counts_umi keys is host code.
-#include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
 #include <cstdio>
@@ -20,6 +19,7 @@
 
 #include "common.hpp"
 #include "cuda_util.hpp"
+#include "radix_sort.cuh"
 
 using namespace hlac;
 
@@ -211,11 +211,9 @@ int hlac_eqclassdb_counts(const hlac_eqclassdb* db, uint32_t nitems, int device,
     k_make_keys<<<grid, 256, 0, stream>>>(d_bc.p, d_umi.p, n, d_keys.p);
     k_class_hist<<<grid, 256, 0, stream>>>(d_cls.p, n, d_rh.p);
     HLAC_CUDA(cudaGetLastError());
-    size_t tb = 0;
-    HLAC_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, d_keys.p, d_keys_sorted.p, d_cls.p, d_cls_sorted.p, n, 0, 64, stream));
-    tmp.reserve(tb, stream);
-    HLAC_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, d_keys.p, d_keys_sorted.p, d_cls.p, d_cls_sorted.p, n, 0, 64, stream));
-    k_umi_lowest<<<grid, 256, 0, stream>>>(d_keys_sorted.p, d_cls_sorted.p, n, d_uh.p);
+    RadixSortScratch rs;
+    const bool second = radix_sort_pairs(d_keys.p, d_keys_sorted.p, d_cls.p, d_cls_sorted.p, (uint64_t)n, 0, 64, rs, stream);
+    k_umi_lowest<<<grid, 256, 0, stream>>>(second ? d_keys_sorted.p : d_keys.p, second ? d_cls_sorted.p : d_cls.p, n, d_uh.p);
     k_explained<<<(unsigned)(((uint64_t)nc * 32 + 255) / 256), 256, 0, stream>>>(d_off.p, d_tx.p, d_rh.p, nc, d_expl.p);
     HLAC_CUDA(cudaGetLastError());
     HLAC_CUDA(cudaMemcpyAsync(reads_hist.data(), d_rh.p, (size_t)nc * 4, cudaMemcpyDeviceToHost, stream));

@@ -18,11 +18,9 @@
 //   K3a k_resolve_paths   thread per distinct path: exact emulation of the merges -> class vector (+ its hash)
 //       host              interns equal vectors, orders classes by first-seen ordinal (= eq_class_id order,
 //                         mapping.rs:147-154), sums counts_reads, builds path -> class-rank table
-//   K3b radix sort + k_umi_min   group records by (barcode, umi); the UMI's class is the lowest class id among its
+//   K3b radix sort (radix_sort.cuh) + k_umi_min   group records by (barcode, umi); the UMI's class is the lowest class id among its
 //                         reads (mapping.rs:165-167,184-193), then sort+dedup on the host per distinct class
 //                         (mapping.rs:205-207); counts_umi histogram by atomicAdd
-#include <cub/device/device_radix_sort.cuh>
-
 #include <algorithm>
 #include <cstdio>
 #include <ctime>
@@ -34,6 +32,7 @@
 #include "caller.hpp"
 #include "comm.hpp"
 #include "device_index.hpp"
+#include "radix_sort.cuh"
 #include "scan.cuh"
 
 using namespace hlac;
@@ -1294,18 +1293,17 @@ int hlac_geno_finish_begin(hlac_geno* s, uint32_t** umi_hist_device, uint64_t* n
     s->fin_hist.reserve(std::max<size_t>(classes.size(), 1), s->stream);
     HLAC_CUDA(cudaMemsetAsync(s->fin_hist.p, 0, std::max<size_t>(classes.size(), 1) * 4, s->stream));
     if (R) {
-      DevBuf<uint32_t> d_rank_of_path, d_ranks, d_ranks_sorted; DevBuf<uint64_t> d_keys_sorted; DevBuf<uint8_t> tmp;
+      DevBuf<uint32_t> d_rank_of_path, d_ranks, d_ranks_b; DevBuf<uint64_t> d_keys_a, d_keys_b; RadixSortScratch rs;
       uint32_t* const hist = s->fin_hist.p;
       d_rank_of_path.upload(s->class_of_path.data(), E, s->stream);
-      d_ranks.reserve(R, s->stream); d_ranks_sorted.reserve(R, s->stream); d_keys_sorted.reserve(R, s->stream);
+      d_ranks.reserve(R, s->stream); d_ranks_b.reserve(R, s->stream); d_keys_a.reserve(R, s->stream); d_keys_b.reserve(R, s->stream);
       size_t e3 = s->begin(2);
       k_map_rank<<<(unsigned)((R + 255) / 256), 256, 0, s->stream>>>(s->rec_path.p, d_rank_of_path.p, R, d_ranks.p);
       HLAC_CUDA(cudaGetLastError());
-      size_t tb = 0;
-      HLAC_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, s->rec_key.p, d_keys_sorted.p, d_ranks.p, d_ranks_sorted.p, R, 0, 64, s->stream));
-      tmp.reserve(tb, s->stream);
-      HLAC_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, s->rec_key.p, d_keys_sorted.p, d_ranks.p, d_ranks_sorted.p, R, 0, 64, s->stream));
-      k_umi_min<<<(unsigned)((R + 255) / 256), 256, 0, s->stream>>>(d_keys_sorted.p, d_ranks_sorted.p, R, hist);
+      // group the records by (barcode, UMI): stable radix sort of a copy of the keys (the records themselves stay as pushed)
+      HLAC_CUDA(cudaMemcpyAsync(d_keys_a.p, s->rec_key.p, R * 8, cudaMemcpyDeviceToDevice, s->stream));
+      const bool second = radix_sort_pairs(d_keys_a.p, d_keys_b.p, d_ranks.p, d_ranks_b.p, R, 0, 64, rs, s->stream);
+      k_umi_min<<<(unsigned)((R + 255) / 256), 256, 0, s->stream>>>(second ? d_keys_b.p : d_keys_a.p, second ? d_ranks_b.p : d_ranks.p, R, hist);
       HLAC_CUDA(cudaGetLastError());
       s->end(e3);
       s->launches += 3;
