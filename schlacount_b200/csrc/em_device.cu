@@ -142,7 +142,6 @@ struct SqArgs {
   uint32_t n; uint64_t nc;
   double* th[4];                                                     // theta0, theta1, theta2, theta_sq (roles rotate)
   double* r; double* v; double* norm;
-  double* cw;                                                        // per class count / norm: the gather adds these, one division per class
   double* cpart; double* tpart;                                      // per-segment partial sums
   double* part;                                                      // [2][gridDim.x] block partials
   unsigned* bar;                                                     // [0] arrivals, [1] generation
@@ -212,7 +211,7 @@ __device__ __forceinline__ double sq_class_norm(const SqArgs& a, const double* t
     double s = 0.0;
     for (uint64_t sg = s0 + lane; sg < s1; sg += 32) s += __ldcg(a.cpart + sg);
     s = warp_sum(s);
-    if (lane == 0) { a.norm[c] = s; a.cw[c] = (double)__ldg(a.cnt + c) / s; if (want_ll && s1 != s0) ll += (double)__ldg(a.cnt + c) * log(s); }
+    if (lane == 0) { a.norm[c] = s; if (want_ll && s1 != s0) ll += (double)__ldg(a.cnt + c) * log(s); }
   }
   return ll;
 }
@@ -232,12 +231,9 @@ __device__ __forceinline__ void sq_f(const SqArgs& a, const double* src, double*
     const double th = __ldcg(src + t);
     double s = 0.0;
 #pragma unroll 4
-    // theta2[t] += theta[t] / norm[c] * count[c] over the classes of t (em.rs:88-95), as theta[t] * sum(count[c] / norm[c]): the
-    // division is done once per class in sq_class_norm instead of once per table entry (9.3 M entries vs 13 k classes at
-    // config-3 scale; the r02 ncu capture had 35 % of the kernel's instructions in this loop)
-    for (uint64_t q = b + lane; q < e; q += 32) s += a.cw[__ldg(a.tcls + q)];
+    for (uint64_t q = b + lane; q < e; q += 32) { const uint32_t c = __ldg(a.tcls + q); s += th / a.norm[c] * (double)__ldg(a.cnt + c); }
     s = warp_sum(s);
-    if (lane == 0) a.tpart[sg] = th * s;
+    if (lane == 0) a.tpart[sg] = s;
   }
   grid_barrier(a.bar);
   double mine = 0.0;
@@ -404,8 +400,7 @@ int hlac_squarem(const hlac_class_tables* t, int device, double* theta_out, uint
   }
   EM_TICK("transpose (device)");
   em.norm.reserve(std::max<uint64_t>(nc, 1), st); em.llt.reserve(std::max<uint64_t>(nc, 1), st); em.raw.reserve(n, st); em.scal.reserve(8, st);
-  DevBuf<double> th0, th1, th2, thsq, r, v, rsq, vsq, cw;
-  cw.reserve(std::max<uint64_t>(nc, 1), st);
+  DevBuf<double> th0, th1, th2, thsq, r, v, rsq, vsq;
   for (auto* b : {&th0, &th1, &th2, &thsq, &r, &v, &rsq, &vsq}) b->reserve(n, st);
   std::vector<double> init(n, 1.0 / (double)n);   // em.rs:49-51
   th0.upload(init.data(), n, st);
@@ -442,7 +437,7 @@ int hlac_squarem(const hlac_class_tables* t, int device, double* theta_out, uint
     HLAC_CUDA(cudaMemsetAsync(bar.p, 0, 2 * sizeof(unsigned), st));
     SqArgs a{};
     a.off = em.off.p; a.tx = em.tx.p; a.cnt = em.cnt.p; a.toff = em.toff.p; a.tcls = em.tcls.p; a.n = n; a.nc = nc;
-    a.th[0] = th0.p; a.th[1] = th1.p; a.th[2] = th2.p; a.th[3] = thsq.p; a.r = r.p; a.v = v.p; a.norm = em.norm.p; a.cw = cw.p;
+    a.th[0] = th0.p; a.th[1] = th1.p; a.th[2] = th2.p; a.th[3] = thsq.p; a.r = r.p; a.v = v.p; a.norm = em.norm.p;
     a.cseg_begin = d_cb.p; a.cseg_row = d_cr.p; a.crow_seg = d_crs.p; a.n_cseg = cs.begin.size();
     a.tseg_begin = d_tb.p; a.tseg_row = d_tr.p; a.trow_seg = d_trs.p; a.n_tseg = ts.begin.size();
     a.cpart = cpart.p; a.tpart = tpart.p;
