@@ -298,7 +298,7 @@ def main():
                          "(library-owned NCCL communicator), rank 0 extracts the whole COO; 'allreduce' = every rank ends with the "
                          "whole matrix; 'none' = shard-local column blocks, no data-path collective")
     ap.add_argument("--geno", default="auto", choices=["auto", "on", "off"],
-                    help="config-3 genotyping record (rank 0): auto = on for the default workload")
+                    help="config-3 genotyping record (rank 0): auto = on for the default single-GPU workload")
     ap.add_argument("--geno-alleles-per-gene", type=int, default=3750, help="x 8 genes = 30 000 alleles (config 3)")
     ap.add_argument("--geno-reads", type=int, default=2_000_000)
     ap.add_argument("--parity-cells", type=int, default=6, help="N > 1: cells per rank whose assembled columns are checked against the oracle")
@@ -593,7 +593,7 @@ def main():
             line["cpu_baseline"] = {"value": ns / dt, "unit": UNIT, "cores": 1, "kind": "port",
                                     "sample": "all %d reads of the first %d of %d cells (+ the same share of non-whitelisted reads), single "
                                               "thread (the reference is single-threaded); its %d matrix entries equal the GPU's columns < %d" % (ns, k, args.cells, len(ent_cpu), k)}
-    want_geno = args.geno == "on" or (args.geno == "auto" and args.genes == 3 and args.reads == N_READS)
+    want_geno = args.geno == "on" or (args.geno == "auto" and world == 1 and args.genes == 3 and args.reads == N_READS)
     if want_geno and rank == 0:
         sess.close()
         torch.cuda.empty_cache()
