@@ -880,11 +880,12 @@ struct hlac_count {
     fallbacks++;
   }
   // dense -> COO into the host-mapped buffers, enqueued only
-  void enqueue_coo() {
+  void enqueue_coo(bool merged_by_caller = false) {
     const uint64_t n = nd();
     const uint32_t nrows = rows.nrows;
-    // nnz <= min(matrix size, molecules <= reads pushed); with a communicator the matrix holds every rank's molecules
-    const uint64_t cap = comm ? n : std::min<uint64_t>(n, std::max<uint64_t>(reads_pushed, 1));
+    // nnz <= min(matrix size, molecules <= reads pushed); a merged matrix (communicator, or a caller that all-reduced the
+    // dense matrix between hlac_count_reduce and hlac_count_entries) holds every rank's molecules: bounded by its size only
+    const uint64_t cap = (comm || merged_by_caller) ? n : std::min<uint64_t>(n, std::max<uint64_t>(reads_pushed, 1));
     if (!host_hdr) {
       HLAC_CUDA(cudaHostAlloc((void**)&host_hdr, (1 + N_COUNTERS) * 8, cudaHostAllocMapped | cudaHostAllocPortable));
       memset(host_hdr, 0, (1 + N_COUNTERS) * 8);
@@ -1221,7 +1222,7 @@ int hlac_count_entries(hlac_count* s, hlac_coo* out, hlac_metrics* metrics) try 
   if (!s) throw Error(HLAC_ERR_ARG, "null session");
   if (!s->reduced) throw Error(HLAC_ERR_STATE, "hlac_count_reduce has not run since the last push");
   DeviceGuard g(s->device);
-  { hlac_comm* keep = s->comm; s->comm = nullptr; s->enqueue_merge(); s->enqueue_coo(); s->comm = keep; }   // the caller merged (or not) itself
+  { hlac_comm* keep = s->comm; s->comm = nullptr; s->enqueue_merge(); s->enqueue_coo(true); s->comm = keep; }   // the caller merged (or not) itself
   HLAC_CUDA(cudaStreamSynchronize(s->stream));
   publish(s, out, metrics, true);
   return HLAC_OK;
