@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(MAP_THREADS, MINB) k_count_map_q(const CountMa
   const uint32_t bm_cds = sbase, bm_gen = sbase + a.cds.bitmap_words * 4;
   for (unsigned k = lane; k < (unsigned)NS; k += 32) sts8(a_fr + k, k);
   unsigned ns = 0, nwk = 0, nfree = NS;                                     // warp-uniform
-  unsigned long long m_reads = 0, m_nonprim = 0, m_notcell = 0, m_cds = 0, m_gen = 0, m_none = 0, m_badcell = 0;
+  uint32_t m_reads = 0, m_nonprim = 0, m_notcell = 0, m_cds = 0, m_gen = 0, m_none = 0, m_badcell = 0;   // per thread: a batch is < 2^32 reads
   uint32_t n_tests = 0, n_probes = 0, umi_max = 0;
   const uint64_t n_warps = (uint64_t)gridDim.x * (MAP_THREADS / 32);
   const uint64_t per = ((a.n + n_warps - 1) / n_warps + 31) & ~31ull;      // whole 32-record tiles per warp
