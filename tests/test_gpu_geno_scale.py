@@ -167,3 +167,37 @@ def test_config5_shape_multi_rank_vs_oracle(sb, orc, db30k, world):
         assert np.array_equal(g.read_class_ids(len(mine)), ocid[mine])
         if rank == 0:
             _check_em_and_calls(sb, orc, g, o, t)
+
+
+def test_more_than_65535_alleles(sb, orc, tmp_path, monkeypatch):
+    """70 000 alleles: tx ids no longer fit 16 bits, so the data-parallel path resolution runs in its uint32_t instantiation
+    (HLAC_RESOLVE=par makes the test fail rather than fall back if it cannot) and the colour bitsets are 2 188 words per colour.
+    Coverage, first-seen class ids, the three tables and the calls against the oracle. (The five extra genes are made 33 %
+    divergent from their templates here so that no colour spans several genes: class vectors stay below the 22 000 elements
+    that fit shared memory at 10 bytes per element.)"""
+    from tools import synth
+    monkeypatch.setenv("HLAC_RESOLVE", "par")
+    db = str(tmp_path / "db70k")
+    names = synth.make_db(db, 8750, 91, extra_genes=GENES, extra_div=3)
+    assert len(names) == 70000
+    donor = [names[g * 8750 + o] for g in range(8) for o in ((5 + 31 * g) % 8750, (4000 + 77 * g) % 8750)]
+    fa, st = os.path.join(db, "hla_nuc.fasta"), os.path.join(db, "Allele_status.txt")
+    gix, oix = sb.Index.from_fasta(fa, st), orc.Index.from_fasta(fa, st)
+    assert gix.info["n_tx"] == 70000 == oix.n_tx and gix.info["n_nodes"] == oix.n_nodes and gix.info["n_colours"] == oix.n_colours
+    r = synth.reads_for_db(8_000, db, donor, 300, 92)
+    n = len(r["len"])
+    g = sb.GenoSession(gix, record_reads=True)
+    g.push(r["seq"], r["len"], r["cell"], r["umi"])
+    cov = g.last_cov()
+    g.finish(raw=True)
+    o, ocid, ocov = _oracle_run(orc, oix, r, [(slice(0, n), False)])
+    assert np.array_equal(cov, ocov) and np.array_equal(g.read_class_ids(n), ocid)
+    t = _check_tables(g, o)
+    assert int(np.diff(t["reads"][0].astype(np.int64)).max()) > 8000 and int(t["reads"][1].max()) > 65535
+    theta, iters = g.squarem()
+    ref = o.call()
+    off, tx, cnt = t["umi"]
+    l_gpu, l_ref = H.em_loglik(off, tx, cnt, theta), H.em_loglik(off, tx, cnt, ref["theta"])
+    assert abs(l_gpu - l_ref) <= 1e-7 * abs(l_ref)
+    assert np.abs(theta - ref["theta"]).max() < 5e-3
+    assert g.call(theta, on_device=True)["called"] == ref["called"]

@@ -398,3 +398,102 @@ def test_header_is_plain_c(tmp_path):
                    '  return (int)(HLAC_PACKED_META(1u, 1, 91, 5) >> 63); }\n')
     subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(H.ROOT, "include"),
                            "-fsyntax-only", str(src)])
+
+
+def _caller_restated(names, theta, reads_explained, counts_reads, nreads):
+    """src/em.rs:361-434 restated directly from the Rust, independently of csrc/caller.hpp and of the oracle's call_genotypes
+    (a third implementation: the other two were written by the same hand). -> (called tx ids sorted, weights rows, pairs rows)"""
+    import itertools
+    wn = [(i, w, names[i], names[i].split("*")[0], reads_explained[i]) for i, w in enumerate(theta)]
+    wn.sort(key=lambda x: -x[1])              # sort_by(-wa partial_cmp -wb): stable
+    wn.sort(key=lambda x: x[3].encode())      # sort_by_key(gene): stable wrt weight
+    called, weights_rows, pairs_rows = set(), [], []
+    for _, grp in itertools.groupby(wn, key=lambda x: x[3]):
+        ws = list(grp)
+        written = 0
+        for (i, w, _, _, exp) in ws:
+            if exp > 100:                     # MIN_READS_CALL
+                weights_rows.append((i, w, float(exp) / float(nreads)))
+                written += 1
+                if written == 10:             # WEIGHTS_TO_OUTPUT
+                    break
+            else:
+                break
+        if written == 0:
+            continue
+        pairs, stop = [], False
+        for i in range(written - 1):
+            for j in range(i + 1, written):
+                a, b = ws[i][0], ws[j][0]
+                exp = sum(c for cls, c in counts_reads.items() if a in cls or b in cls)   # pair_reads_explained (em.rs:36-44)
+                if exp > 100:
+                    pairs.append((a, b, float(exp) / float(nreads), float(max(ws[i][4], ws[j][4])) / float(nreads)))
+                else:
+                    stop = True               # break 'outer
+                    break
+            if stop:
+                break
+        if pairs:
+            pairs.sort(key=lambda p: -p[2])
+            pairs_rows += [(a, b, f) for a, b, f, _ in pairs[:5]]   # PAIRS_TO_OUTPUT
+            if pairs[0][2] * 0.15 > pairs[0][2] - pairs[0][3]:      # HOMOZYGOUS_TH
+                called |= {pairs[0][0], pairs[0][1]}
+            else:
+                called.add(ws[0][0])
+        else:
+            called.add(ws[0][0])
+    return sorted(called), weights_rows, pairs_rows
+
+
+def test_caller_against_an_independent_restatement(sb):
+    """hlac_call_genotypes (csrc/caller.hpp) on random class tables vs a restatement of em.rs:361-434 written from the Rust
+    alone: weights.tsv rows, pairs.tsv rows and the called set must be identical (ties, the 100-read cut-offs, the
+    break-outer on the first failing pair, the homozygosity rule and the 10 / 5 row limits all occur)."""
+    from schlacount_b200 import _lib
+    rng = np.random.default_rng(12)
+    genes = ["A", "B", "C", "DRB1", "DQA1"]
+    names = ["%s*%02d:%02d" % (g, 1 + k // 4, 1 + k % 4) for g in genes for k in range(14)]
+    n = len(names)
+    seqs = ["".join("ACGT"[int(x)] for x in rng.integers(0, 4, size=40)) for _ in names]
+    ix = sb.Index.from_sequences(seqs, names, device=-1)   # host-only handle: the caller needs the tx names only
+    assert ix.tx_names == names
+    n_pairs_seen = n_both = n_single = 0
+    for trial in range(60):
+        classes = {}
+        for _ in range(int(rng.integers(5, 60))):
+            g = int(rng.integers(0, len(genes)))
+            members = rng.choice(14, size=int(rng.integers(1, 6)), replace=False) + 14 * g
+            if rng.random() < 0.1:
+                members = np.concatenate([members, rng.choice(n, size=2, replace=False)])   # a class across genes
+            key = tuple(int(x) for x in dict.fromkeys(rng.permutation(members).tolist()))   # unsorted, like a read-level class
+            classes[key] = classes.get(key, 0) + int(rng.integers(1, 120 if trial % 3 else 400))
+        nreads = sum(classes.values())
+        expl = [sum(c for k, c in classes.items() if t in k) for t in range(n)]
+        theta = rng.random(n)
+        theta[rng.random(n) < 0.3] = 0.0
+        if trial % 5 == 0:
+            theta[:8] = theta[0]                                                   # ties in the weights
+        theta = theta / theta.sum()
+        keys = list(classes)
+        off = np.zeros(len(keys) + 1, np.uint64)
+        for i, k in enumerate(keys):
+            off[i + 1] = off[i] + len(k)
+        tx = np.asarray([t for k in keys for t in k], np.uint32)
+        cnt = np.asarray([classes[k] for k in keys], np.uint32)
+        ex = np.asarray(expl, np.uint64)
+        t = _lib.ClassTables()
+        t.nitems, t.nreads, t.n_read_classes = n, nreads, len(keys)
+        t.reads_off, t.reads_tx, t.reads_cnt = (off.ctypes.data_as(C.POINTER(C.c_uint64)), tx.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                                cnt.ctypes.data_as(C.POINTER(C.c_uint32)))
+        t.reads_explained = ex.ctypes.data_as(C.POINTER(C.c_uint64))
+        th = np.ascontiguousarray(theta, np.float64)
+        c = _lib.Calls()
+        assert sb.lib().hlac_call_genotypes(ix.h, C.byref(t), th.ctypes.data_as(C.c_void_p), C.byref(c)) == 0, sb.lib().hlac_last_error()
+        got = ([c.called[i] for i in range(c.n_called)], [(c.w_tx[i], c.w_em[i], c.w_frac[i]) for i in range(c.n_weights)],
+               [(c.p_a[i], c.p_b[i], c.p_frac[i]) for i in range(c.n_pairs)])
+        sb.lib().hlac_calls_free(C.byref(c))
+        want = _caller_restated(names, theta.tolist(), expl, classes, nreads)
+        assert got[0] == want[0] and got[1] == want[1] and got[2] == want[2], (trial, got, want)
+        n_pairs_seen += len(want[2])
+        n_both += sum(1 for _ in want[0])
+    assert n_pairs_seen > 50 and n_both > 100

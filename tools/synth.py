@@ -128,11 +128,12 @@ def _mutate(rng, seq, n_sub, lo, hi):
     return s.decode()
 
 
-def make_db(out_dir, n_per_gene, seed, genes=("A", "B", "C"), extra_genes=()):
+def make_db(out_dir, n_per_gene, seed, genes=("A", "B", "C"), extra_genes=(), extra_div=8):
     """Writes hla_nuc.fasta, hla_gen.fasta, Allele_status.txt for a synthetic DB derived from the six fixture alleles.
     Every allele is a fixture allele of its gene with 1-6 substitutions concentrated in the exon 2-3 stretch of the CDS
     (positions 74-620) and, independently, in the genomic copy. `extra_genes` (e.g. DRB1, DQA1 ...) are fabricated from
-    the A/B/C templates by ~12 % divergence so that they behave as separate genes. Names follow src/hla.rs:49.
+    the A/B/C templates by ~12 % divergence (1 / extra_div of the bases substituted) so that they behave as separate genes
+    that still share some k-mers with their template. Names follow src/hla.rs:49.
     -> list of allele names in FASTA order."""
     os.makedirs(out_dir, exist_ok=True)
     rng = np.random.default_rng(seed)
@@ -143,7 +144,7 @@ def make_db(out_dir, n_per_gene, seed, genes=("A", "B", "C"), extra_genes=()):
     templates = dict(by_gene)
     for k, eg in enumerate(extra_genes):
         base = by_gene[("A", "B", "C")[k % 3]]
-        templates[eg] = [(_mutate(rng, s, len(s) // 8, 0, len(s)), _mutate(rng, g, len(g) // 8, 0, len(g))) for s, g in base]
+        templates[eg] = [(_mutate(rng, s, len(s) // extra_div, 0, len(s)), _mutate(rng, g, len(g) // extra_div, 0, len(g))) for s, g in base]
     nuc, gn, status, names = [], [], [], []
     hid = 10000
     for gene in list(genes) + list(extra_genes):
