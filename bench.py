@@ -287,7 +287,10 @@ def main():
     ap.add_argument("--cells", type=int, default=N_CELLS, help="barcodes per GPU")
     ap.add_argument("--cpu-sample", type=int, default=1_500_000, help="reads of the workload timed on the CPU oracle")
     ap.add_argument("--ref-procs", type=int, default=0, help="--impl reference: worker processes (0 = all cores)")
-    ap.add_argument("--chunk", type=int, default=1_000_000, help="e2e push chunk in reads (0 = whole batch)")
+    ap.add_argument("--chunk", type=int, default=-1,
+                    help="e2e push size in reads: -1 (default) = a tapering schedule (40 %, 30 %, 15 %, 7.5 %, 5 %, 2.5 % of the batch: few "
+                         "copies, and a short last one so that little map work is left when the last byte has landed), 0 = whole batch, "
+                         "N = equal chunks of N reads")
     ap.add_argument("--genes", type=int, default=3, choices=[3, 4, 5, 6, 7, 8],
                     help="3 = the six fixture alleles (config 2); 8 = 2 synthetic alleles x 8 genes (config 4 shape)")
     ap.add_argument("--e2e-format", default="wire", choices=["wire", "packed", "soa"],
@@ -391,7 +394,12 @@ def main():
 
     # the same records for both legs: resident in HBM for `value`, in pinned host memory for `e2e`
     u2i = {np.dtype("uint64"): np.int64, np.dtype("uint16"): np.int16, np.dtype("uint32"): np.int32, np.dtype("uint8"): np.uint8}
-    chunk = args.chunk or n
+    if args.chunk < 0:
+        cuts = [0] + [int(n * f) for f in (0.40, 0.70, 0.85, 0.925, 0.975)] + [n]
+    else:
+        step = args.chunk or n
+        cuts = list(range(0, n, step)) + [n]
+    cuts = sorted(set(cuts))
     fmt = args.e2e_format
     if fmt == "soa":
         d = {k: torch.from_numpy(v.view(u2i[v.dtype])).to(dev) for k, v in r.items()}
@@ -455,8 +463,8 @@ def main():
 
     def step_e2e():
         sess.reset()
-        for a in range(0, n, chunk):
-            push_host(a, min(n, a + chunk))
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            push_host(a, b)
         return finish_step()
 
     def timed(fn, steps, warmup):
@@ -567,7 +575,8 @@ def main():
                         "h2d_ceiling_gbs_per_gpu": ceiling,
                         "h2d_ceiling_note": "all %d ranks copying their pinned input and nothing else, slowest rank; the e2e leg cannot beat "
                                             "bytes / this (%.2f ms per step)" % (world, in_bytes / ceiling / 1e6) if ceiling else None,
-                        "input_format": fmt_name % (in_bytes // n)},
+                        "input_format": fmt_name % (in_bytes // n), "pushes_per_step": len(cuts) - 1,
+                        "push_reads": [b - a for a, b in zip(cuts[:-1], cuts[1:])]},
                 # counted by the session itself (hlac_count_timing): every kernel of ours launched in one step, times the steps.
                 # No library kernel runs on the normal path (cub only sorts on the bucket-overflow fallback; fallbacks below).
                 "gpu_launches": int(tm_dev["launches"]) * args.steps, "library_launches": 0 if gstats["fallbacks"] == 0 else None,

@@ -172,13 +172,15 @@ def test_config5_shape_multi_rank_vs_oracle(sb, orc, db30k, world):
 def test_more_than_65535_alleles(sb, orc, tmp_path, monkeypatch):
     """70 000 alleles: tx ids no longer fit 16 bits, so the data-parallel path resolution runs in its uint32_t instantiation
     (HLAC_RESOLVE=par makes the test fail rather than fall back if it cannot) and the colour bitsets are 2 188 words per colour.
-    Coverage, first-seen class ids, the three tables and the calls against the oracle. (The five extra genes are made 33 %
-    divergent from their templates here so that no colour spans several genes: class vectors stay below the 22 000 elements
-    that fit shared memory at 10 bytes per element.)"""
+    Coverage, first-seen class ids, the three tables and the calls against the oracle. (The reference keeps eight genes,
+    so > 65 535 alleles means > 8 191 per gene; the fixture's A, B and C share 24-mers on their conserved exons, which would make
+    colours of 3 x 8 750 alleles -- more than the 22 000 elements of 10 bytes that fit the kernel's 220 KB of shared memory, where
+    the library falls back to its sequential resolution. Here only A keeps the fixture's alleles; the other seven genes are
+    fabricated 33 % divergent from the templates, so no colour spans two genes and the widest vector is one gene's 8 750.)"""
     from tools import synth
     monkeypatch.setenv("HLAC_RESOLVE", "par")
     db = str(tmp_path / "db70k")
-    names = synth.make_db(db, 8750, 91, extra_genes=GENES, extra_div=3)
+    names = synth.make_db(db, 8750, 91, genes=("A",), extra_genes=("B", "C") + GENES, extra_div=3)
     assert len(names) == 70000
     donor = [names[g * 8750 + o] for g in range(8) for o in ((5 + 31 * g) % 8750, (4000 + 77 * g) % 8750)]
     fa, st = os.path.join(db, "hla_nuc.fasta"), os.path.join(db, "Allele_status.txt")
