@@ -76,6 +76,7 @@ struct CountMapArgs {
   uint32_t nw;                 // u32 words per strand row in shared memory (2*wpr + 1)
   uint32_t row_stride;         // u32 words per slot (both strands + the read index, odd)
   int primary_only;
+  int scan_budget;   // l-mer tests of an orientation's first look (k_count_map_q scan rounds)
   uint32_t cell_bits;          // key layout: umi << (5 + cell_bits) | cell << 5 | code
   uint32_t n_cells;            // cell indices >= n_cells are a caller error: dropped and counted in metrics[8]
   BucketStore bk;
@@ -163,8 +164,8 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __host__ __device__ constexpr uint32_t map_nw(uint32_t wpr) { return 2 * wpr + 1; }
 __host__ __device__ constexpr uint32_t map_row_stride(uint32_t wpr) { return 2 * map_nw(wpr) + 1; }
 __host__ __device__ constexpr uint32_t map_warp_bytes(uint32_t wpr, bool tma, uint32_t ns) {
-  // slots + lens u16 + three byte queues, rounded to 16 B; staging tile (32 records of (wpr + 1) u64) + mbarrier
-  return ((ns * map_row_stride(wpr) * 4 + ns * 2 + ns * 3 + 15) & ~15u) + (tma ? 32 * (wpr + 1) * 8 + 16 : 0);
+  // slots + lens u16 + four byte queues, rounded to 16 B; staging tile (32 records of (wpr + 1) u64) + mbarrier
+  return ((ns * map_row_stride(wpr) * 4 + ns * 2 + ns * 4 + 15) & ~15u) + (tma ? 32 * (wpr + 1) * 8 + 16 : 0);
 }
 __host__ __device__ constexpr uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
 
@@ -202,14 +203,15 @@ __global__ void __launch_bounds__(MAP_THREADS, MINB) k_count_map_q(const CountMa
   const uint32_t nw = a.nw, rs4 = a.row_stride * 4;
   const uint32_t wb = sbase + bm_bytes + warp * map_warp_bytes(a.wpr, TMA, NS);   // this warp's region
   const uint32_t a_lens = wb + NS * rs4;            // u16[NS]
-  const uint32_t a_qs = a_lens + NS * 2;            // scan queue: slot | p << 6
+  const uint32_t a_qs = a_lens + NS * 2;            // scan queue (first look): slot | p << 6
   const uint32_t a_qw = a_qs + NS;                  // walk queue
   const uint32_t a_fr = a_qw + NS;                  // free-slot stack
-  const uint32_t a_stage = wb + ((NS * rs4 + NS * 2 + NS * 3 + 15) & ~15u);   // TMA: 32 records
+  const uint32_t a_ql = a_fr + NS;                  // scan queue (long scans): slot | p << 6, scan state in the reverse row's spare word
+  const uint32_t a_stage = wb + ((NS * rs4 + NS * 2 + NS * 4 + 15) & ~15u);   // TMA: 32 records
   const uint32_t a_bar = a_stage + 32 * (a.wpr + 1) * 8;
   const uint32_t bm_cds = sbase, bm_gen = sbase + a.cds.bitmap_words * 4;
   for (unsigned k = lane; k < (unsigned)NS; k += 32) sts8(a_fr + k, k);
-  unsigned ns = 0, nwk = 0, nfree = NS;                                     // warp-uniform
+  unsigned ns = 0, nl = 0, nwk = 0, nfree = NS;                             // warp-uniform
   uint32_t m_reads = 0, m_nonprim = 0, m_notcell = 0, m_cds = 0, m_gen = 0, m_none = 0, m_badcell = 0;   // per thread: a batch is < 2^32 reads
   uint32_t n_tests = 0, n_probes = 0, umi_max = 0;
   const uint64_t n_warps = (uint64_t)gridDim.x * (MAP_THREADS / 32);
@@ -232,13 +234,13 @@ __global__ void __launch_bounds__(MAP_THREADS, MINB) k_count_map_q(const CountMa
   __syncwarp();
   for (;;) {
     const bool more = cur < hi;
-    int what;   // 0 walk, 1 scan, 2 refill
+    int what;   // 0 walk, 1 scan (first look), 2 refill, 3 scan (long)
     if (nwk >= 32) what = 0;
+    else if (nl >= 32) what = 3;
     else if (ns >= 32) what = 1;
-    else if (more && nfree > 0) what = 2;   // (with fewer than 64 slots both queues can be short of a full round while no slot is free)
-    else if (ns >= nwk && ns > 0) what = 1;
-    else if (nwk > 0) what = 0;
-    else if (ns > 0) what = 1;
+    else if (more && nfree >= 16) what = 2;   // no full round waiting: with 64 slots fewer than 16 free ones leave some queue >= 17 tasks
+    else if (nwk + nl + ns > 0) what = (nwk >= nl && nwk >= ns) ? 0 : (nl >= ns ? 3 : 1);
+    else if (more) what = 2;                  // every slot is free
     else break;
     if (what == 2) {
       // ---- refill: filters (mapping.rs:752-763) + read rows into free slots ----
@@ -321,35 +323,45 @@ __global__ void __launch_bounds__(MAP_THREADS, MINB) k_count_map_q(const CountMa
       if (lane < c && !keep) sts8(a_fr + nfree + __popc(bd & below), slot);
       ns += __popc(bk); nfree += __popc(bd);
       __syncwarp();
-    } else if (what == 1) {
-      // ---- scan round: first-seed skip-scan of (slot, p) ----
-      const unsigned cnt = min(32u, ns), qb = ns - cnt;
+    } else if (what != 0) {
+      // ---- scan round: first-seed skip-scan of (slot, p). An orientation either seeds within its first window (three l-mer
+      // tests and a dictionary probe) or, mostly, scans the whole read in vain (~20 tests), so a task's first look is bounded
+      // by a.scan_budget tests; what is still scanning then moves to the long queue, whose rounds run to the end. Rounds of
+      // either kind are homogeneous: lanes that seeded do not sit out the other lanes' long scans.
+      const bool lng = what == 3;
+      const unsigned have = lng ? nl : ns;
+      const unsigned cnt = min(32u, have), qb = have - cnt;
       const bool task = lane < cnt;
-      bool found = false;
+      int res = SEED_NONE;
       unsigned slot = 0, p = 0;
       if (task) {
-        const unsigned e = lds8(a_qs + qb + lane);
+        const unsigned e = lds8((lng ? a_ql : a_qs) + qb + lane);
         slot = e & 63u; p = e >> 6;
         const uint32_t fw = wb + slot * rs4, rc = fw + nw * 4;
         const int L = (int)lds16(a_lens + 2 * slot);
         SmemWords rd{(p & 1) ? rc : fw};
         const DevIndexView& ix = p < 2 ? a.cds : a.gen;
-        int pos = 0; uint32_t node = 0, off = 0;
+        int pos = 0, q = K - (int)ix.lmer; uint32_t node = 0, off = 0;
+        if (lng) { const uint32_t st = lds32(rc + 8 * a.wpr); pos = (int)(st & 0xFFFFu); q = (int)(st >> 16); }
         if (L >= K) {
-          if (SMEM_BM) found = find_seed<STRIDE>(ix, rd, SmemBitmap{p < 2 ? bm_cds : bm_gen}, pos, L - K, node, off, n_tests, n_probes);
-          else found = find_seed<STRIDE>(ix, rd, BitmapGlobal{ix.bitmap}, pos, L - K, node, off, n_tests, n_probes);
+          const int budget = lng ? 0x7FFFFFFF : a.scan_budget;
+          if (SMEM_BM) res = find_seed_step<STRIDE, true>(ix, rd, SmemBitmap{p < 2 ? bm_cds : bm_gen}, pos, q, L - K, budget, node, off, n_tests, n_probes);
+          else res = find_seed_step<STRIDE, true>(ix, rd, BitmapGlobal{ix.bitmap}, pos, q, L - K, budget, node, off, n_tests, n_probes);
         }
-        if (found) { sts32(fw + 8 * a.wpr, node); sts32(rc + 8 * a.wpr, (off << 12) | ((uint32_t)pos << 2) | p); }
+        if (res == SEED_FOUND) { sts32(fw + 8 * a.wpr, node); sts32(rc + 8 * a.wpr, (off << 12) | ((uint32_t)pos << 2) | p); }
+        else if (res == SEED_MORE) sts32(rc + 8 * a.wpr, (uint32_t)pos | ((uint32_t)q << 16));
       }
       __syncwarp();
-      ns = qb;
-      const bool again = task && !found && p < 3, dead = task && !found && p == 3;
-      const unsigned bf = __ballot_sync(0xFFFFFFFFu, task && found), bn = __ballot_sync(0xFFFFFFFFu, again),
-                     bz = __ballot_sync(0xFFFFFFFFu, dead);
-      if (task && found) sts8(a_qw + nwk + __popc(bf & below), slot);
+      if (lng) nl = qb; else ns = qb;
+      const bool found = task && res == SEED_FOUND, cont = task && res == SEED_MORE;
+      const bool again = task && res == SEED_NONE && p < 3, dead = task && res == SEED_NONE && p == 3;
+      const unsigned bf = __ballot_sync(0xFFFFFFFFu, found), bn = __ballot_sync(0xFFFFFFFFu, again),
+                     bz = __ballot_sync(0xFFFFFFFFu, dead), bc = __ballot_sync(0xFFFFFFFFu, cont);
+      if (found) sts8(a_qw + nwk + __popc(bf & below), slot);
       if (again) sts8(a_qs + ns + __popc(bn & below), slot | ((p + 1) << 6));
+      if (cont) sts8(a_ql + nl + __popc(bc & below), slot | (p << 6));
       if (dead) sts8(a_fr + nfree + __popc(bz & below), slot);             // all four None (mapping.rs:791-793)
-      nwk += __popc(bf); ns += __popc(bn); nfree += __popc(bz);
+      nwk += __popc(bf); ns += __popc(bn); nl += __popc(bc); nfree += __popc(bz);
       if (lane == 0) m_none += __popc(bz);
       __syncwarp();
     } else {
@@ -645,6 +657,7 @@ struct hlac_count {
   RowLayout rows;
   uint32_t n_cells = 0;
   int primary_only = 0;
+  int scan_budget = 7;   // HLAC_SCAN_BUDGET (measured on config 2: 3 -> 1.15 ms, 5 -> 1.07, 6-8 -> 1.025, 12 -> 1.05, unbounded -> 1.10)
   DevBuf<uint32_t> nodes_cds, nodes_gen, gene_row0, dense;   // node tables with cinfo in place of the colour id
   // bucket store of the scored reads' keys; `keys` = overflow list (and the gather target of the fallback path)
   DevBuf<uint64_t> bk_keys, keys, keys_sorted, keys_tmp;
@@ -773,7 +786,7 @@ struct hlac_count {
     a.cds.nodes = reinterpret_cast<const uint4*>(nodes_cds.p); a.gen.nodes = reinterpret_cast<const uint4*>(nodes_gen.p);
     a.seq = b.seq; a.len = b.len; a.cell = b.cell; a.umi = b.umi; a.flags = b.flags;
     a.n = b.n; a.wpr = b.words_per_read; a.nw = map_nw(a.wpr); a.row_stride = map_row_stride(a.wpr);
-    a.primary_only = primary_only; a.n_cells = n_cells; a.cell_bits = cell_bits;
+    a.primary_only = primary_only; a.scan_budget = scan_budget; a.n_cells = n_cells; a.cell_bits = cell_bits;
     a.bk = store(); a.metrics = counters.p + 1;
     a.codes = want_codes ? codes.p : nullptr;
     a.rec = rec;
@@ -932,6 +945,7 @@ int hlac_count_new(hlac_index* cds, hlac_index* genomic, uint32_t n_cells, int p
   if (n_cells == 0 || n_cells >= (1u << 27)) throw Error(HLAC_ERR_LIMIT, "n_cells must be in 1..2^27-1");
   auto s = std::make_unique<hlac_count>();
   s->cds = cds; s->gen = genomic; s->device = cds->device; s->n_cells = n_cells; s->primary_only = primary_only;
+  if (const char* e = getenv("HLAC_SCAN_BUDGET")) s->scan_budget = std::max(1, atoi(e));
   s->stride = seed_stride();
   while ((1ull << s->cell_bits) < n_cells) s->cell_bits++;
   DeviceGuard g(s->device);

@@ -119,15 +119,19 @@ __device__ __forceinline__ bool dict_get(const DevIndexView& ix, uint64_t kmer, 
 // then waits for the few lanes that probe the dictionary; see profiles/r01_count_map_tuning.md.)
 // With a stride S > 1 only every S-th position (counted from the scan start) is a candidate, so a jump lands on the next
 // candidate at or beyond the first position the absent l-mer does not rule out.
-template <int S, typename RD, typename BM>
-__device__ __forceinline__ bool find_seed(const DevIndexView& ix, RD rd, BM bm, int& pos, int last, uint32_t& node,
-                                          uint32_t& off, uint32_t& n_tests, uint32_t& n_probes) {
+// find_seed_step is the resumable form: (pos, q) is the scan state (q = read position of the l-mer under test, K - l beyond
+// pos when a window is entered), `budget` bounds the l-mer tests of this call. Returns SEED_FOUND, SEED_NONE (scan exhausted) or
+// SEED_MORE (budget used up; call again with the same pos, q).
+enum { SEED_NONE = 0, SEED_FOUND = 1, SEED_MORE = 2 };
+template <int S, bool BOUNDED, typename RD, typename BM>
+__device__ __forceinline__ int find_seed_step(const DevIndexView& ix, RD rd, BM bm, int& pos, int& q, int last, int budget, uint32_t& node,
+                                              uint32_t& off, uint32_t& n_tests, uint32_t& n_probes) {
   const int l = (int)ix.lmer;
   const int sh = 32 - 2 * l;
   const int o0 = K - l;
-  int q = pos + o0;   // read position of the l-mer under test: right to left inside the window [pos, pos + K)
   // one flat loop, one l-mer test per iteration (no nested per-window loop: lanes of a warp advance independently)
   while (pos <= last) {
+    if (BOUNDED && budget-- <= 0) return SEED_MORE;
     const uint32_t v = ext16(rd, q) >> sh;
     n_tests++;
     if (!((bm(v >> 5) >> (v & 31)) & 1u)) {   // no k-mer can cover this l-mer: every window up to q is ruled out
@@ -137,12 +141,24 @@ __device__ __forceinline__ bool find_seed(const DevIndexView& ix, RD rd, BM bm, 
     }
     if (q != pos) { q = max(q - l, pos); continue; }
     n_probes++;
-    if (dict_get(ix, kmer48(rd, pos), node, off)) return true;
+    if (dict_get(ix, kmer48(rd, pos), node, off)) return SEED_FOUND;
     pos += S;
     q = pos + o0;
   }
-  return false;
+  return SEED_NONE;
 }
+template <int S, typename RD, typename BM>
+__device__ __forceinline__ bool find_seed(const DevIndexView& ix, RD rd, BM bm, int& pos, int last, uint32_t& node,
+                                          uint32_t& off, uint32_t& n_tests, uint32_t& n_probes) {
+  int q = pos + K - (int)ix.lmer;   // right to left inside the window [pos, pos + K)
+  return find_seed_step<S, false>(ix, rd, bm, pos, q, last, 0, node, off, n_tests, n_probes) == SEED_FOUND;
+}
+
+// (r02, measured and removed: the same scan as a warp-collective call - one straight-line, predicated l-mer test per
+// iteration, the loop condition a REDUX vote, the lanes whose window passed leaving together to probe the dictionary together.
+// It fixes what the ncu capture shows here - the flat loop's lanes only reconverge at the loop exit, so the loop runs at ~15
+// active lanes and the probe at 3 - but every iteration then costs ~45 instructions for the whole warp instead of ~25 for the
+// lanes that take it, and the round still lasts as long as its slowest lane: 1.15 ms per 10 M reads against 1.025.)
 
 // Left extension: only when the first seed sits at or beyond floor(0.2*L). Walks the read
 // leftwards from the seed through predecessor nodes; returns the coverage it adds and visits the nodes it enters.

@@ -570,6 +570,125 @@ __global__ void __launch_bounds__(RES_THREADS) k_resolve_paths_par(const uint32_
   }
 }
 
+// r02b: the same merge with ONE WARP per path, for the vectors of up to RES_WARP_MAX elements (most of them: the ncu capture
+// of the block kernel showed its shortest-vector launch taking half the time at ~5 600 warp-instructions per merge whatever
+// the length, since all 8 warps run the whole tile code and meet at two block barriers for a vector that fills a fraction of
+// one 2 048-element tile). A warp walks its vector in tiles of 32 lanes x 8 elements with the running maximum / match count
+// carried in registers: no block barrier, no cross-warp partials, instruction count proportional to the length. The warps
+// of a block are independent (own slice of shared memory, own path from the shared work counter). Needs the per-index
+// colour bitsets in global memory.
+constexpr uint32_t RES_WARP_MAX = 2048;
+template <typename T, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) k_resolve_paths_warp(const uint32_t* __restrict__ arena, const uint64_t* __restrict__ path_off,
+    const uint32_t* __restrict__ path_len, const uint64_t* __restrict__ col_off, const uint32_t* __restrict__ col_tx, uint32_t n_paths,
+    const uint64_t* __restrict__ vec_off, uint32_t* vec, uint64_t* vec_hash, uint64_t* vec_hash2, uint32_t cap /* multiple of 8 */,
+    uint32_t bitset_words, unsigned int* next_path, const uint32_t* __restrict__ ids, const uint32_t* __restrict__ col_bits) {
+  extern __shared__ __align__(16) uint32_t sm[];
+  constexpr unsigned FULL = 0xFFFFFFFFu;
+  const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  unsigned char* mine = reinterpret_cast<unsigned char*>(sm) + (size_t)w * cap * (2 * sizeof(T) + 2);
+  T* A = reinterpret_cast<T*>(mine);
+  T* B = A + cap;
+  uint16_t* rk = reinterpret_cast<uint16_t*>(B + cap);
+  for (;;) {
+    unsigned slot = 0;
+    if (lane == 0) slot = atomicAdd(next_path, 1u);
+    slot = __shfl_sync(FULL, slot, 0);
+    if (slot >= n_paths) return;
+    const uint32_t id = ids[slot];
+    const uint32_t* path = arena + path_off[id];
+    const uint32_t plen = path_len[id];
+    const uint32_t last = path[plen - 1];
+    const uint64_t cb = col_off[last];
+    const uint32_t n = (uint32_t)(col_off[last + 1] - cb);
+    __syncwarp();   // the previous path's output loop has finished reading A
+    for (uint32_t k = lane; k < n; k += 32) A[k] = (T)col_tx[cb + k];
+    for (uint32_t sidx = 0; sidx + 1 < plen; sidx++) {
+      const uint32_t* mem_row = col_bits + (size_t)path[sidx] * bitset_words;
+      __syncwarp();
+      uint32_t carry = 0, base = 0, last_pos = 0;   // values are compared as x + 1 so that 0 means "nothing yet"
+      for (uint32_t t0 = 0; t0 < n; t0 += 256) {
+        const uint32_t i0 = t0 + lane * RES_ITEMS;
+        uint32_t x[RES_ITEMS], pm[RES_ITEMS];
+#pragma unroll
+        for (int k = 0; k < RES_ITEMS; k++) x[k] = 0u;
+        if (i0 < n) {
+          if (sizeof(T) == 2) {
+            const uint4 q = *reinterpret_cast<const uint4*>(A + i0);
+            x[0] = q.x & 0xFFFFu; x[1] = q.x >> 16; x[2] = q.y & 0xFFFFu; x[3] = q.y >> 16; x[4] = q.z & 0xFFFFu; x[5] = q.z >> 16; x[6] = q.w & 0xFFFFu; x[7] = q.w >> 16;
+          } else {
+            const uint4 q0 = *reinterpret_cast<const uint4*>(A + i0), q1 = *reinterpret_cast<const uint4*>(A + i0 + 4);
+            x[0] = q0.x; x[1] = q0.y; x[2] = q0.z; x[3] = q0.w; x[4] = q1.x; x[5] = q1.y; x[6] = q1.z; x[7] = q1.w;
+          }
+        }
+        uint32_t run = 0;
+#pragma unroll
+        for (int k = 0; k < RES_ITEMS; k++) { run = max(run, i0 + k < n ? x[k] + 1 : 0u); pm[k] = run; }
+        uint32_t v = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(FULL, v, o); if (lane >= (unsigned)o) v = max(v, u); }
+        uint32_t before = __shfl_up_sync(FULL, v, 1);
+        if (lane == 0) before = 0;
+        const uint32_t excl = max(carry, before);
+        carry = max(carry, __shfl_sync(FULL, v, 31));
+        unsigned mflags = 0, cnt = 0;
+        uint32_t my_last = 0;
+#pragma unroll
+        for (int k = 0; k < RES_ITEMS; k++) {
+          const uint32_t prev = k ? max(excl, pm[k - 1]) : excl;
+          bool match = i0 + k < n && x[k] + 1 > prev;
+          if (match) match = (__ldg(mem_row + (x[k] >> 5)) >> (x[k] & 31)) & 1u;
+          if (match) { mflags |= 1u << k; cnt++; my_last = i0 + k + 1; }
+        }
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(FULL, incl, o); if (lane >= (unsigned)o) incl += u; }
+        last_pos = max(last_pos, __reduce_max_sync(FULL, my_last));
+        uint32_t rank = base + incl - cnt;
+        base += __shfl_sync(FULL, incl, 31);
+        uint32_t rkv[RES_ITEMS];
+#pragma unroll
+        for (int k = 0; k < RES_ITEMS; k++) {
+          const bool match = (mflags >> k) & 1u;
+          rkv[k] = match ? rank + 1 : 0u;
+          if (match) { B[rank] = (T)x[k]; rank++; }
+          else if (i0 + k < n) B[n - 1 - (i0 + k - rank)] = (T)(i0 + k);
+        }
+        if (i0 < n) *reinterpret_cast<uint4*>(rk + i0) = make_uint4(rkv[0] | (rkv[1] << 16), rkv[2] | (rkv[3] << 16), rkv[4] | (rkv[5] << 16), rkv[6] | (rkv[7] << 16));
+      }
+      const uint32_t M = base;
+      if (M == 0 || last_pos == M) continue;   // nothing moves (uniform over the warp)
+      __syncwarp();
+      for (uint32_t i = M + lane; i < n; i += 32) {
+        uint32_t src = i;
+        const uint32_t r0 = rk[i];
+        if (r0) {
+          uint32_t m = r0 - 1u;
+          for (;;) {
+            const uint32_t r1 = rk[m];
+            if (r1 == 0) break;
+            const uint32_t j = m - (r1 - 1u);
+            if (j == 0) break;
+            const uint32_t u = B[n - j];
+            m -= ((m - u - 1u) / j + 1u) * j;
+          }
+          src = m;
+        }
+        rk[i] = (uint16_t)src;   // i >= M, while the chains only read rk below M
+      }
+      __syncwarp();
+      for (uint32_t i = M + lane; i < n; i += 32) B[i] = A[rk[i]];   // only now: the back of B held the non-match positions
+      T* tmp = A; A = B; B = tmp;
+    }
+    __syncwarp();
+    uint32_t* dst = vec + vec_off[id];
+    unsigned long long h1 = 0, h2 = 0;
+    for (uint32_t k = lane; k < n; k += 32) { const uint32_t x = A[k]; dst[k] = x; h1 += vec_h1(x, k); h2 += vec_h2(x, k); }
+    for (int o = 16; o > 0; o >>= 1) { h1 += __shfl_down_sync(FULL, h1, o); h2 += __shfl_down_sync(FULL, h2, o); }
+    if (lane == 0) { vec_hash[id] = h1; vec_hash2[id] = h2; }
+  }
+}
+
 // every path's vector must equal its class representative's vector element by element (interning is by hash)
 __global__ void k_verify_classes(const uint32_t* __restrict__ vec, const uint64_t* __restrict__ vec_off, const uint32_t* __restrict__ rep_of_path,
                                  uint32_t n, unsigned long long* mismatches) {
@@ -1121,8 +1240,8 @@ int hlac_geno_finish_begin(hlac_geno* s, uint32_t** umi_hist_device, uint64_t* n
     const std::vector<uint32_t>& olen = comm ? olen_store : hlen;
     std::vector<uint64_t> voff(E + 1, 0);
     for (uint32_t i = 0; i < E; i++) voff[i + 1] = voff[i] + olen[i];
+    std::vector<uint32_t> hpl(E);   // path lengths (nodes)
     {   // work of this resolution, for the roofline record: merges, vector elements walked, compulsory bytes
-      std::vector<uint32_t> hpl(E);
       HLAC_CUDA(cudaMemcpyAsync(hpl.data(), s->e_path_len.p, (size_t)E * 4, cudaMemcpyDeviceToHost, s->stream));
       HLAC_CUDA(cudaStreamSynchronize(s->stream));
       const uint64_t bw = ((uint64_t)hx.tx_names.size() + 31) / 32 * 4;
@@ -1168,32 +1287,73 @@ int hlac_geno_finish_begin(hlac_geno* s, uint32_t** umi_hist_device, uint64_t* n
           s->launches++;
         }
         const uint32_t* col_bits = bits_global ? ixp->col_bits.p : nullptr;
-        std::vector<uint32_t> caps;
-        for (uint32_t cap = n_max; ; cap = (cap + 1) / 2) { caps.push_back(cap); if (cap <= 2048 || caps.size() == 4) break; }
-        std::vector<std::vector<uint32_t>> groups(caps.size());
+        // groups: vectors of up to RES_WARP_MAX elements go to the warp-per-path kernel (four capacity classes), longer ones
+        // to the block-per-path kernel (up to four classes, halving from the longest)
+        struct Group { bool warp; uint32_t cap; std::vector<uint32_t> ids; };
+        std::vector<Group> groups;
+        constexpr int RES_WARPS = 4;
+        const bool use_warp = bits_global && !getenv("HLAC_RESOLVE_NO_WARP");
+        uint32_t warp_max = RES_WARP_MAX;
+        if (const char* e = getenv("HLAC_RESOLVE_WARP_MAX")) warp_max = std::min<uint32_t>(8192, std::max<uint32_t>(256, (uint32_t)atoi(e)));   // A/B switch
+        if (!narrow) warp_max = std::min<uint32_t>(warp_max, 4096);   // 4 warps x 10 bytes x cap of shared memory per block
+        if (use_warp) for (uint32_t cap = 256; cap <= warp_max; cap *= 2) groups.push_back({true, cap, {}});
+        const size_t first_block = groups.size();
+        {
+          std::vector<uint32_t> caps;
+          for (uint32_t cap = n_max; ; cap = (cap + 1) / 2) { caps.push_back(cap); if (cap <= 2048 || caps.size() == 4) break; }
+          for (size_t k = caps.size(); k-- > 0;) groups.push_back({false, caps[k], {}});   // ascending capacity
+        }
         for (uint32_t i = 0; i < E; i++) {
           if (olen[i] == 0) continue;   // another rank's path
-          size_t gsel = 0; while (gsel + 1 < caps.size() && olen[i] <= caps[gsel + 1]) gsel++; groups[gsel].push_back(i);
+          size_t gsel = (use_warp && olen[i] <= groups[first_block - 1].cap) ? 0 : first_block;
+          while (gsel + 1 < groups.size() && olen[i] > groups[gsel].cap) gsel++;
+          groups[gsel].ids.push_back(i);
         }
-        DevBuf<unsigned int> d_next; d_next.reserve(caps.size(), s->stream);
-        HLAC_CUDA(cudaMemsetAsync(d_next.p, 0, caps.size() * 4, s->stream));
+        DevBuf<unsigned int> d_next; d_next.reserve(groups.size(), s->stream);
+        HLAC_CUDA(cudaMemsetAsync(d_next.p, 0, groups.size() * 4, s->stream));
         std::vector<std::unique_ptr<DevBuf<uint32_t>>> d_ids;
-        for (size_t gsel = caps.size(); gsel-- > 0;) {   // short vectors first
-          if (groups[gsel].empty()) continue;
-          const size_t smem_g = smem_for(caps[gsel]);
-          HLAC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_par));
-          int occ = 1;
-          HLAC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, RES_THREADS, smem_g));
+        auto wkern = narrow ? k_resolve_paths_warp<uint16_t, RES_WARPS> : k_resolve_paths_warp<uint32_t, RES_WARPS>;
+        const bool dbg = getenv("HLAC_DEBUG_TIMING") != nullptr;
+        std::vector<cudaEvent_t> gev;
+        for (size_t gsel = 0; gsel < groups.size(); gsel++) {   // short vectors first
+          Group& g = groups[gsel];
+          if (dbg) { cudaEvent_t e; HLAC_CUDA(cudaEventCreate(&e)); HLAC_CUDA(cudaEventRecord(e, s->stream)); gev.push_back(e); }
+          if (g.ids.empty()) continue;
           d_ids.emplace_back(new DevBuf<uint32_t>());
-          d_ids.back()->upload(groups[gsel].data(), groups[gsel].size(), s->stream);
-          const unsigned grid = (unsigned)std::min<uint64_t>(groups[gsel].size(), (uint64_t)s->n_sm * std::max(occ, 1));
-          kern<<<grid, RES_THREADS, smem_g, s->stream>>>(s->arena.p, s->e_path_off.p, s->e_path_len.p, s->idx->col_off.p, s->idx->col_tx.p,
-                                                        (uint32_t)groups[gsel].size(), d_voff.p, s->fin_dvec.p, d_vhash.p, d_vhash2.p, caps[gsel],
-                                                        bitset_words, d_next.p + gsel, d_ids.back()->p, col_bits);
+          d_ids.back()->upload(g.ids.data(), g.ids.size(), s->stream);
+          int occ = 1;
+          if (g.warp) {
+            const size_t smem_g = (size_t)RES_WARPS * g.cap * (narrow ? 6 : 10);
+            HLAC_CUDA(cudaFuncSetAttribute(wkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
+            HLAC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, wkern, RES_WARPS * 32, smem_g));
+            const unsigned grid = (unsigned)std::min<uint64_t>((g.ids.size() + RES_WARPS - 1) / RES_WARPS, (uint64_t)s->n_sm * std::max(occ, 1));
+            wkern<<<grid, RES_WARPS * 32, smem_g, s->stream>>>(s->arena.p, s->e_path_off.p, s->e_path_len.p, s->idx->col_off.p, s->idx->col_tx.p,
+                                                              (uint32_t)g.ids.size(), d_voff.p, s->fin_dvec.p, d_vhash.p, d_vhash2.p, g.cap,
+                                                              bitset_words, d_next.p + gsel, d_ids.back()->p, col_bits);
+          } else {
+            const size_t smem_g = smem_for(g.cap);
+            HLAC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_par));
+            HLAC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, RES_THREADS, smem_g));
+            const unsigned grid = (unsigned)std::min<uint64_t>(g.ids.size(), (uint64_t)s->n_sm * std::max(occ, 1));
+            kern<<<grid, RES_THREADS, smem_g, s->stream>>>(s->arena.p, s->e_path_off.p, s->e_path_len.p, s->idx->col_off.p, s->idx->col_tx.p,
+                                                          (uint32_t)g.ids.size(), d_voff.p, s->fin_dvec.p, d_vhash.p, d_vhash2.p, g.cap,
+                                                          bitset_words, d_next.p + gsel, d_ids.back()->p, col_bits);
+          }
           HLAC_CUDA(cudaGetLastError());
           s->launches++;
         }
+        if (dbg) { cudaEvent_t e; HLAC_CUDA(cudaEventCreate(&e)); HLAC_CUDA(cudaEventRecord(e, s->stream)); gev.push_back(e); }
         HLAC_CUDA(cudaStreamSynchronize(s->stream));   // d_next / d_ids go out of scope
+        if (dbg) {
+          for (size_t gsel = 0; gsel < groups.size(); gsel++) {
+            float ms = 0; cudaEventElapsedTime(&ms, gev[gsel], gev[gsel + 1]);
+            uint64_t merges = 0, steps = 0;
+            for (uint32_t i : groups[gsel].ids) { merges += hpl[i] - 1; steps += (uint64_t)(hpl[i] - 1) * olen[i]; }
+            fprintf(stderr, "[hlac] resolve group %zu (%s, cap %u): %zu paths, %llu merges, %llu element steps, %.3f ms\n", gsel, groups[gsel].warp ? "warp" : "block",
+                    groups[gsel].cap, groups[gsel].ids.size(), (unsigned long long)merges, (unsigned long long)steps, ms);
+          }
+          for (cudaEvent_t e : gev) cudaEventDestroy(e);
+        }
       } else {
         if (force && std::string(force) == "par") throw Error(HLAC_ERR_LIMIT, "HLAC_RESOLVE=par but the class vectors do not fit in shared memory");
         if (comm) throw Error(HLAC_ERR_LIMIT, "the sequential path resolution (class vectors beyond shared memory, or HLAC_RESOLVE=seq) is single-GPU only");
