@@ -1431,9 +1431,24 @@ int hlac_geno_finish_begin(hlac_geno* s, uint32_t** umi_hist_device, uint64_t* n
       HLAC_CUDA(cudaStreamSynchronize(s->stream));
       for (uint32_t p = 0; p < E; p++) { Cls& c = classes[tmp_cls[p]]; if (hhash[p] < hhash[c.rep]) c.rep = p; }
     }
+    HLAC_TICK("intern + verify classes");
+    // class ids in first-seen order (first-seen ordinals are unique): LSD radix sort of the class indices by ordinal, 16 bits a pass
     std::vector<uint32_t> order(classes.size());
-    for (uint32_t i = 0; i < order.size(); i++) order[i] = i;
-    std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return classes[a].ord < classes[b].ord; });
+    {
+      const size_t nc = classes.size();
+      uint64_t max_ord = 0;
+      for (const Cls& c : classes) max_ord = std::max(max_ord, c.ord);
+      std::vector<uint32_t> other(nc), hist(65536);
+      for (uint32_t i = 0; i < nc; i++) order[i] = i;
+      for (int shift = 0; shift < 64 && (shift == 0 || (max_ord >> shift) != 0); shift += 16) {
+        std::fill(hist.begin(), hist.end(), 0u);
+        for (uint32_t i = 0; i < nc; i++) hist[(classes[order[i]].ord >> shift) & 0xFFFFu]++;
+        uint32_t run = 0;
+        for (uint32_t d = 0; d < 65536; d++) { const uint32_t h = hist[d]; hist[d] = run; run += h; }
+        for (uint32_t i = 0; i < nc; i++) other[hist[(classes[order[i]].ord >> shift) & 0xFFFFu]++] = order[i];
+        order.swap(other);
+      }
+    }
     std::vector<uint32_t> rank(classes.size());
     for (uint32_t r = 0; r < order.size(); r++) rank[order[r]] = r;
     cls_reads.resize(classes.size()); s->fin_cls_colour.resize(classes.size()); s->fin_src_off.resize(classes.size()); s->fin_cls_len.resize(classes.size());
@@ -1448,7 +1463,7 @@ int hlac_geno_finish_begin(hlac_geno* s, uint32_t** umi_hist_device, uint64_t* n
     }
     for (uint32_t p = 0; p < E; p++) s->class_of_path[p] = rank[tmp_cls[p]];
     n_classes_out = classes.size();
-    HLAC_TICK("intern + verify + order classes");
+    HLAC_TICK("order classes");
     // ---- K3b: group records by (barcode, umi), lowest class id per UMI ----
     s->fin_hist.reserve(std::max<size_t>(classes.size(), 1), s->stream);
     HLAC_CUDA(cudaMemsetAsync(s->fin_hist.p, 0, std::max<size_t>(classes.size(), 1) * 4, s->stream));
