@@ -1784,6 +1784,11 @@ int hlac_class_tables_free(hlac_class_tables* t) {
 }
 
 int hlac_geno_timing(hlac_geno* s, float ms[4], uint64_t* launches) try {
+  if (getenv("HLAC_DEBUG_TIMING")) {
+    const AllocStats& a = g_alloc.st;
+    fprintf(stderr, "[hlac] device allocations so far: %llu (%llu from the cache) %.1f ms (longest %.1f ms), %llu frees %.1f ms (longest %.1f ms), %zu MB cached\n",
+            a.n_malloc, a.n_reused, 1e3 * a.t_malloc, 1e3 * a.max_malloc, a.n_free, 1e3 * a.t_free, 1e3 * a.max_free, g_alloc.cached_bytes >> 20);
+  }
   if (!s) throw Error(HLAC_ERR_ARG, "null session");
   DeviceGuard g(s->device);
   s->drain_events();
