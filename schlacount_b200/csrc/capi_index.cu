@@ -157,7 +157,7 @@ int hlac_index_clone(const hlac_index* src, int device, hlac_index** out) {
 int hlac_index_device(const hlac_index* ix) { return ix ? ix->device : -1; }
 
 int hlac_index_free(hlac_index* ix) {
-  if (ix) { if (ix->device >= 0) cudaSetDevice(ix->device); delete ix; }
+  if (ix) { int prev = 0; cudaGetDevice(&prev); if (ix->device >= 0) cudaSetDevice(ix->device); delete ix; cudaSetDevice(prev); }   // the caller's current device is left as it was
   return HLAC_OK;
 }
 

@@ -159,7 +159,7 @@ int hlac_comm_init_all(const int* devices, int n, hlac_comm** comms) {
 
 int hlac_comm_free(hlac_comm* c) {
   if (c) {
-    if (c->c) { cudaSetDevice(c->device); nccl().CommDestroy(c->c); }
+    if (c->c) { int prev = 0; cudaGetDevice(&prev); cudaSetDevice(c->device); nccl().CommDestroy(c->c); cudaSetDevice(prev); }
     delete c;
   }
   return HLAC_OK;

@@ -978,7 +978,7 @@ int hlac_count_new(hlac_index* cds, hlac_index* genomic, uint32_t n_cells, int p
 } catch (const Error& e) { set_last_error(e.what()); return e.code; } catch (const std::exception& e) { set_last_error(e.what()); return HLAC_ERR_STATE; }
 
 int hlac_count_free(hlac_count* s) {
-  if (s) { cudaSetDevice(s->device); delete s; }
+  if (s) { int prev = 0; cudaGetDevice(&prev); cudaSetDevice(s->device); delete s; cudaSetDevice(prev); }   // the caller's current device is left as it was
   return HLAC_OK;
 }
 uint32_t hlac_count_nrows(const hlac_count* s) { return s ? s->rows.nrows : 0; }

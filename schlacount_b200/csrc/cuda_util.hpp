@@ -33,7 +33,7 @@ struct AllocCache {
   std::multimap<std::pair<int, size_t>, void*> free_blocks;   // (device, bytes) -> block
   std::unordered_map<void*, std::pair<int, size_t>> live;     // block -> (device, bytes)
   size_t cached_bytes = 0, limit = (size_t)8192 << 20;
-  bool limit_read = false;
+  bool limit_read = false, poison = false;   // HLAC_ALLOC_POISON=1: every block is handed out filled with 0xA5
   AllocStats st;
 };
 inline AllocCache g_alloc;
@@ -53,7 +53,7 @@ inline cudaError_t dev_malloc(void** p, size_t bytes) {
   AllocCache& c = g_alloc;
   const double t0 = alloc_now();
   std::lock_guard<std::mutex> lk(c.mu);
-  if (!c.limit_read) { c.limit_read = true; if (const char* e = getenv("HLAC_ALLOC_CACHE_MB")) c.limit = (size_t)strtoull(e, nullptr, 10) << 20; }
+  if (!c.limit_read) { c.limit_read = true; if (const char* e = getenv("HLAC_ALLOC_CACHE_MB")) c.limit = (size_t)strtoull(e, nullptr, 10) << 20; c.poison = getenv("HLAC_ALLOC_POISON") != nullptr; }
   int dev = 0; cudaGetDevice(&dev);
   bytes = bytes < ((size_t)1 << 20) ? ((bytes + 255) & ~(size_t)255) : ((bytes + 65535) & ~(size_t)65535);
   if (bytes == 0) bytes = 256;
@@ -67,6 +67,7 @@ inline cudaError_t dev_malloc(void** p, size_t bytes) {
     if (e == cudaErrorMemoryAllocation) { (void)cudaGetLastError(); alloc_cache_trim_locked(c, 0); e = cudaMalloc(p, bytes); }
   }
   if (e == cudaSuccess) c.live[*p] = {dev, bytes};
+  if (e == cudaSuccess && c.poison) { cudaDeviceSynchronize(); cudaMemset(*p, 0xA5, bytes); cudaDeviceSynchronize(); }   // debugging aid: nothing may rely on zeroed memory
   const double dt = alloc_now() - t0;
   c.st.n_malloc++; c.st.t_malloc += dt; if (dt > c.st.max_malloc) c.st.max_malloc = dt;
   return e;

@@ -1140,7 +1140,7 @@ int hlac_geno_new(hlac_index* idx, hlac_geno** out) try {
 } catch (const Error& e) { set_last_error(e.what()); return e.code; } catch (const std::exception& e) { set_last_error(e.what()); return HLAC_ERR_STATE; }
 
 int hlac_geno_free(hlac_geno* s) {
-  if (s) { cudaSetDevice(s->device); delete s; }
+  if (s) { int prev = 0; cudaGetDevice(&prev); cudaSetDevice(s->device); delete s; cudaSetDevice(prev); }   // the caller's current device is left as it was
   return HLAC_OK;
 }
 

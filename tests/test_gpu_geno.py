@@ -126,7 +126,7 @@ def _device_u32(ptr, n):
 
     class _W:
         __cuda_array_interface__ = {"shape": (max(n, 1),), "typestr": "<i4", "data": (ptr, False), "version": 2}
-    return torch.as_tensor(_W(), device="cuda")
+    return torch.as_tensor(_W(), device=torch.device("cuda", 0))   # the session's device: a view, never a cross-device copy
 
 
 @pytest.mark.parametrize("world", [2, 3])

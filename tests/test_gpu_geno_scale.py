@@ -148,13 +148,15 @@ def test_config5_shape_multi_rank_vs_oracle(sb, orc, db30k, world):
     assert sum(int(p["count"].sum()) for p in parts) == o.nreads
     for g in sess:
         g.import_merged_paths(parts)
-    hists = []
+    hists, ptrs = [], []
     for g in sess:
         ptr, nc = g.finish_begin()
+        ptrs.append(ptr)
 
         class _W:
             __cuda_array_interface__ = {"shape": (max(nc, 1),), "typestr": "<i4", "data": (ptr, False), "version": 2}
-        hists.append(torch.as_tensor(_W(), device="cuda"))
+        hists.append(torch.as_tensor(_W(), device=torch.device("cuda", 0)))   # the sessions' device: a view, not a copy
+    assert all(h.data_ptr() == p for h, p in zip(hists, ptrs))   # torch aliases the library's histogram (it would copy across devices)
     total = sum(hists[1:], hists[0].clone())    # the all-reduce(sum)
     for h in hists:
         h.copy_(total)

@@ -58,7 +58,7 @@ def test_count_partition_and_merge_emulated_vs_oracle(sb, orc, world):
         class _W:
             __cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (ptr, False), "version": 2}
         sess.append(s)
-        dense.append(torch.as_tensor(_W(), device="cuda"))
+        dense.append(torch.as_tensor(_W(), device=torch.device("cuda", 0)))   # the sessions' device: a view, never a cross-device copy
     total = sum(dense[1:], dense[0].clone())
     # disjoint columns: at most one rank has a non-zero in any cell
     assert int(sum((d != 0).to(torch.int32) for d in dense).max()) <= 1
