@@ -138,6 +138,12 @@ int hlac_device_count(int* n);
  * binding (Rust repr(C), ctypes) can assert its own layouts against the library it loaded */
 int hlac_abi_sizes(uint32_t* out, uint32_t cap);
 
+/* Device memory of the library comes from a process-wide cache of freed blocks (no reference counterpart: the reference
+ * has no device). hlac_device_cache_trim returns every cached (= currently unused) block of every device to the driver
+ * and reports how many bytes that were; live sessions and indexes are not touched. HLAC_ALLOC_CACHE_MB bounds the cache
+ * (default 8192, 0 = no caching). Either pointer may be null. */
+int hlac_device_cache_trim(uint64_t* bytes_released, uint64_t* bytes_live);
+
 /* Seed-scan stride of map_read's k-mer search ([EXT] debruijn_mapping find_kmer_match, `*kmer_pos += stride`). The
  * pinned revision is not vendored and the reference's golden matrices reproduce for strides 1..3 (SURVEY.md finding #4);
  * 1 (every position) is the default, 3 is what later upstream revisions use. Process-wide; sessions adopt the value

@@ -608,6 +608,13 @@ class GenoSession:
         return out
 
 
+def device_cache_trim():
+    """hlac_device_cache_trim: returns the library's cached (unused) device blocks to the driver -> (bytes released, bytes live)"""
+    rel, live = C.c_uint64(), C.c_uint64()
+    check(lib().hlac_device_cache_trim(C.byref(rel), C.byref(live)))
+    return rel.value, live.value
+
+
 def squarem(nitems, classes, device=0):
     """hlac_squarem on an explicit {class tuple: count} table (classes iterated in sorted order) -> (theta, iters)"""
     keys = sorted(classes)

@@ -69,6 +69,16 @@ int hlac_abi_sizes(uint32_t* out, uint32_t cap) {
   return HLAC_OK;
 }
 
+int hlac_device_cache_trim(uint64_t* bytes_released, uint64_t* bytes_live) try {
+  hlac::AllocCache& c = hlac::g_alloc;
+  std::lock_guard<std::mutex> lk(c.mu);
+  const uint64_t before = c.cached_bytes;
+  hlac::alloc_cache_trim_locked(c, 0);
+  if (bytes_released) *bytes_released = before - c.cached_bytes;
+  if (bytes_live) { uint64_t live = 0; for (const auto& kv : c.live) live += kv.second.second; *bytes_live = live; }
+  return HLAC_OK;
+} catch (const std::exception& e) { set_last_error(e.what()); return HLAC_ERR_STATE; }
+
 int hlac_set_seed_stride(int stride) {
   if (stride != 1 && stride != 3) { set_last_error("seed stride must be 1 or 3 (the kernels are instantiated for these two)"); return HLAC_ERR_ARG; }
   hlac::g_seed_stride = stride;

@@ -115,6 +115,28 @@ def test_reset_and_repeat(sb, abc, fixture_reads):
     assert t["launches"] >= 2 and t["map_ms"] > 0
 
 
+def test_device_memory_cache(sb, abc, fixture_reads):
+    """Device buffers are recycled through the library's cache of freed blocks (cuda_util.hpp): a closed session's memory is
+    handed to the next one, hlac_device_cache_trim gives it back to the driver, and results do not depend on either."""
+    bc = H.load_barcodes(os.path.join(H.FIX, "barcodes7.tsv"))
+    batch = H.make_batch(fixture_reads, bc, pack=sb.pack_reads)
+    s = sb.CountSession(abc["gc"], abc["gg"], len(bc))
+    s.push(*batch)
+    e1, m1 = s.finish()
+    s.close()
+    released, live = sb.device_cache_trim()
+    assert released > 0 and live > 0          # the session's blocks were cached; the two indexes are still alive
+    assert sb.device_cache_trim()[0] == 0     # nothing left to release
+    s = sb.CountSession(abc["gc"], abc["gg"], len(bc))   # fresh blocks from the driver
+    s.push(*batch)
+    e2, m2 = s.finish()
+    s.close()
+    s = sb.CountSession(abc["gc"], abc["gg"], len(bc))   # recycled blocks
+    s.push(*batch)
+    e3, m3 = s.finish()
+    assert e1 == e2 == e3 and m1 == m2 == m3
+
+
 def test_abi_argument_errors(sb, abc):
     """Errors surface as negative status + message, never as a crash or a silent fallback."""
     import ctypes as C
