@@ -70,7 +70,7 @@ int hlac_abi_sizes(uint32_t* out, uint32_t cap) {
 }
 
 int hlac_device_cache_trim(uint64_t* bytes_released, uint64_t* bytes_live) try {
-  hlac::AllocCache& c = hlac::g_alloc;
+  hlac::AllocCache& c = hlac::alloc_cache();
   std::lock_guard<std::mutex> lk(c.mu);
   const uint64_t before = c.cached_bytes;
   hlac::alloc_cache_trim_locked(c, 0);

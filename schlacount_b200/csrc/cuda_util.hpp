@@ -36,7 +36,8 @@ struct AllocCache {
   bool limit_read = false, poison = false;   // HLAC_ALLOC_POISON=1: every block is handed out filled with 0xA5
   AllocStats st;
 };
-inline AllocCache g_alloc;
+// never destroyed: buffers may still be freed while the process is shutting down (static destructors of other objects)
+inline AllocCache& alloc_cache() { static AllocCache* const c = new AllocCache; return *c; }
 inline double alloc_now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec; }
 inline void alloc_cache_trim_locked(AllocCache& c, size_t keep_bytes) {   // frees cached blocks (largest first per key order is not needed: any)
   while (c.cached_bytes > keep_bytes && !c.free_blocks.empty()) {
@@ -50,7 +51,7 @@ inline void alloc_cache_trim_locked(AllocCache& c, size_t keep_bytes) {   // fre
   }
 }
 inline cudaError_t dev_malloc(void** p, size_t bytes) {
-  AllocCache& c = g_alloc;
+  AllocCache& c = alloc_cache();
   const double t0 = alloc_now();
   std::lock_guard<std::mutex> lk(c.mu);
   if (!c.limit_read) { c.limit_read = true; if (const char* e = getenv("HLAC_ALLOC_CACHE_MB")) c.limit = (size_t)strtoull(e, nullptr, 10) << 20; c.poison = getenv("HLAC_ALLOC_POISON") != nullptr; }
@@ -74,7 +75,7 @@ inline cudaError_t dev_malloc(void** p, size_t bytes) {
 }
 inline void dev_free(void* p) {
   if (!p) return;
-  AllocCache& c = g_alloc;
+  AllocCache& c = alloc_cache();
   const double t0 = alloc_now();
   std::unique_lock<std::mutex> lk(c.mu);
   auto it = c.live.find(p);

@@ -26,6 +26,7 @@
 #include <ctime>
 #include <map>
 #include <memory>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -1591,10 +1592,30 @@ int hlac_geno_finish_end(hlac_geno* s, hlac_class_tables* out) try {
   out->n_umi_classes = used.size();
   out->umi_off = (uint64_t*)calloc(used.size() + 1, 8); out->umi_tx = (uint32_t*)malloc(std::max<uint64_t>(utx, 1) * 4); out->umi_cnt = (uint32_t*)calloc(std::max<size_t>(used.size(), 1), 4);
   q = 0; size_t c = 0;
-  for (uint32_t col : used) {
-    const size_t len = hx.col_off[col + 1] - hx.col_off[col];
-    memcpy(out->umi_tx + q, hx.col_tx.data() + hx.col_off[col], len * 4);
-    q += len; out->umi_cnt[c] = (uint32_t)by_colour[col]; out->umi_off[++c] = q;
+  for (uint32_t col : used) { q += hx.col_off[col + 1] - hx.col_off[col]; out->umi_cnt[c] = (uint32_t)by_colour[col]; out->umi_off[++c] = q; }
+  {   // the lists themselves (tens of MB into fresh pages at IMGT scale: the page faults are the cost, and they parallelise)
+    unsigned n_threads = utx >= (1u << 20) ? std::min(8u, std::max(1u, std::thread::hardware_concurrency())) : 1u;
+    if (const char* e = getenv("HLAC_HOST_THREADS")) n_threads = utx >= (1u << 20) ? (unsigned)std::max(1, atoi(e)) : 1u;
+    auto copy_range = [&](size_t a, size_t b) {
+      for (size_t k = a; k < b; k++) {
+        const uint32_t col = used[k];
+        memcpy(out->umi_tx + out->umi_off[k], hx.col_tx.data() + hx.col_off[col], (size_t)(hx.col_off[col + 1] - hx.col_off[col]) * 4);
+      }
+    };
+    if (n_threads <= 1) copy_range(0, used.size());
+    else {   // chunks of about equal bytes
+      std::vector<std::thread> th;
+      size_t a = 0;
+      for (unsigned t = 0; t < n_threads; t++) {
+        const uint64_t want = utx * (t + 1) / n_threads;
+        size_t b = a;
+        while (b < used.size() && out->umi_off[b] < want) b++;
+        if (t + 1 == n_threads) b = used.size();
+        if (b > a) th.emplace_back(copy_range, a, b);
+        a = b;
+      }
+      for (auto& x : th) x.join();
+    }
   }
   HLAC_TICK("assemble counts_umi");
   s->finished = true; s->fin_begun = false;
@@ -1785,9 +1806,9 @@ int hlac_class_tables_free(hlac_class_tables* t) {
 
 int hlac_geno_timing(hlac_geno* s, float ms[4], uint64_t* launches) try {
   if (getenv("HLAC_DEBUG_TIMING")) {
-    const AllocStats& a = g_alloc.st;
+    const AllocStats& a = alloc_cache().st;
     fprintf(stderr, "[hlac] device allocations so far: %llu (%llu from the cache) %.1f ms (longest %.1f ms), %llu frees %.1f ms (longest %.1f ms), %zu MB cached\n",
-            a.n_malloc, a.n_reused, 1e3 * a.t_malloc, 1e3 * a.max_malloc, a.n_free, 1e3 * a.t_free, 1e3 * a.max_free, g_alloc.cached_bytes >> 20);
+            a.n_malloc, a.n_reused, 1e3 * a.t_malloc, 1e3 * a.max_malloc, a.n_free, 1e3 * a.t_free, 1e3 * a.max_free, alloc_cache().cached_bytes >> 20);
   }
   if (!s) throw Error(HLAC_ERR_ARG, "null session");
   DeviceGuard g(s->device);
