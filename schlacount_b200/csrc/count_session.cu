@@ -138,12 +138,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 
 // Queue-staged map kernel (ncu history of its predecessors in profiles/: thread-per-read 6.65 of 32 lanes active per issued
 // instruction, block-staged 12.6 lanes but barrier-bound, warp-staged tiles 12.2, queue-staged 14.65). Each
-// warp keeps a pool of NS read slots and two warp-private task queues that persist across refills: SCAN entries are
-// (slot, p) with p = the orientation/index the chain of mapping.rs:772-790 has reached, WALK entries are slots with
-// a seed. A round of either kind only runs when 32 tasks are waiting (or the warp's input is exhausted), so every
+// warp keeps a pool of NS read slots and three warp-private task queues that persist across refills: SCAN entries are
+// (slot, p) with p = the orientation/index the chain of mapping.rs:772-790 has reached (their first look, bounded by
+// scan_budget l-mer tests), LONG entries are the same tasks still scanning after their first look, WALK entries are slots
+// with a seed. A round of any kind only runs when 32 tasks are waiting (or nothing else can be done), so every
 // round starts with all lanes busy whatever fraction of the reads survives each stage; scan rounds mix the four
-// orientations (same code, per-lane operands). The warp streams a contiguous range of the batch and refills the
-// pool with as many reads as there are free slots.
+// orientations (same code, per-lane operands) but not short and long scans. The warp streams a contiguous range of the
+// batch and refills the pool when at least 16 slots are free.
 //
 // Shared memory is addressed through explicit 32-bit shared-window addresses (device_index.cuh). One slot is
 // row_stride = 2 * nw + 1 words (odd: lanes on different slots never share a bank): the forward row, the reverse-complement
