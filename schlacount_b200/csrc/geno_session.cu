@@ -1288,8 +1288,7 @@ int hlac_geno_finish_begin(hlac_geno* s, uint32_t** umi_hist_device, uint64_t* n
           s->launches++;
         }
         const uint32_t* col_bits = bits_global ? ixp->col_bits.p : nullptr;
-        // groups: vectors of up to RES_WARP_MAX elements go to the warp-per-path kernel (four capacity classes), longer ones
-        // to the block-per-path kernel (up to four classes, halving from the longest)
+        // groups: vectors of up to RES_WARP_MAX elements go to the warp-per-path kernel, longer ones to the block-per-path kernel
         struct Group { bool warp; uint32_t cap; std::vector<uint32_t> ids; };
         std::vector<Group> groups;
         constexpr int RES_WARPS = 4;
@@ -1297,9 +1296,17 @@ int hlac_geno_finish_begin(hlac_geno* s, uint32_t** umi_hist_device, uint64_t* n
         uint32_t warp_max = RES_WARP_MAX;
         if (const char* e = getenv("HLAC_RESOLVE_WARP_MAX")) warp_max = std::min<uint32_t>(8192, std::max<uint32_t>(256, (uint32_t)atoi(e)));   // A/B switch
         if (!narrow) warp_max = std::min<uint32_t>(warp_max, 4096);   // 4 warps x 10 bytes x cap of shared memory per block
-        if (use_warp) for (uint32_t cap = 256; cap <= warp_max; cap *= 2) groups.push_back({true, cap, {}});
+        // capacity classes: shared memory per path is proportional to the class capacity and decides how many paths an SM
+        // works on at once, so the classes are fine (warp kernel: steps of 256 elements; block kernel: x 1.25), not octaves -
+        // e.g. the 74 k paths of 1 025..1 641 elements of the config-3 database run 21 instead of 16 to an SM
+        const bool fine = !getenv("HLAC_RESOLVE_COARSE");
+        if (use_warp) for (uint32_t cap = 256; cap <= warp_max; cap = fine ? cap + 256 : cap * 2) groups.push_back({true, cap, {}});
         const size_t first_block = groups.size();
-        {
+        if (fine) {
+          uint32_t cap = use_warp ? warp_max : 1024;
+          while (cap < n_max && groups.size() - first_block < 15) { cap = std::min<uint32_t>(n_max, (cap + cap / 4 + 63) & ~63u); groups.push_back({false, cap, {}}); }
+          if (groups.size() == first_block || groups.back().cap < n_max) groups.push_back({false, n_max, {}});
+        } else {
           std::vector<uint32_t> caps;
           for (uint32_t cap = n_max; ; cap = (cap + 1) / 2) { caps.push_back(cap); if (cap <= 2048 || caps.size() == 4) break; }
           for (size_t k = caps.size(); k-- > 0;) groups.push_back({false, caps[k], {}});   // ascending capacity
