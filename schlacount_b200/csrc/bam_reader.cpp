@@ -1,5 +1,7 @@
 #include "bam_reader.hpp"
 
+#include "inflate_fast.hpp"
+
 #include <zlib.h>
 
 #include <algorithm>
@@ -17,17 +19,25 @@ namespace {
 template <typename T>
 T rd(const uint8_t* p) { T v; memcpy(&v, p, sizeof(T)); return v; }
 
+void zlib_inflate(const std::vector<uint8_t>& cdata, std::vector<uint8_t>& out) {
+  z_stream zs{};
+  zs.next_in = const_cast<Bytef*>(cdata.data()); zs.avail_in = (uInt)cdata.size(); zs.next_out = out.data(); zs.avail_out = (uInt)out.size();
+  if (inflateInit2(&zs, -15) != Z_OK) throw Error(HLAC_ERR_FORMAT, "inflateInit2 failed");
+  const int rc = inflate(&zs, Z_FINISH);
+  inflateEnd(&zs);
+  if (rc != Z_STREAM_END) throw Error(HLAC_ERR_FORMAT, "BGZF inflate failed");
+}
+// One BGZF block. The library's own decoder (inflate_fast.cpp, ~1.5 x zlib's rate on BAM data) goes first; whatever it
+// declines - and any block whose CRC32 does not come out right after it - is inflated again by zlib, and the CRC32 decides.
 std::vector<uint8_t> inflate_block(const std::vector<uint8_t>& cdata, uint32_t isize, uint32_t crc) {
+  static const bool use_fast = !getenv("HLAC_ZLIB_INFLATE");
   std::vector<uint8_t> out(isize);
+  auto crc_ok = [&] { return (uint32_t)crc32(crc32(0L, Z_NULL, 0), out.data(), (uInt)out.size()) == crc; };
   if (isize) {
-    z_stream zs{};
-    zs.next_in = const_cast<Bytef*>(cdata.data()); zs.avail_in = (uInt)cdata.size(); zs.next_out = out.data(); zs.avail_out = isize;
-    if (inflateInit2(&zs, -15) != Z_OK) throw Error(HLAC_ERR_FORMAT, "inflateInit2 failed");
-    const int rc = inflate(&zs, Z_FINISH);
-    inflateEnd(&zs);
-    if (rc != Z_STREAM_END) throw Error(HLAC_ERR_FORMAT, "BGZF inflate failed");
+    if (use_fast && inflate_raw_fast(cdata.data(), cdata.size(), out.data(), isize) && crc_ok()) return out;
+    zlib_inflate(cdata, out);
   }
-  if ((uint32_t)crc32(crc32(0L, Z_NULL, 0), out.data(), (uInt)out.size()) != crc) throw Error(HLAC_ERR_FORMAT, "BGZF block fails its CRC32");
+  if (!crc_ok()) throw Error(HLAC_ERR_FORMAT, "BGZF block fails its CRC32");
   return out;
 }
 }  // namespace

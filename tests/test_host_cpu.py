@@ -400,6 +400,42 @@ def test_header_is_plain_c(tmp_path):
                            "-fsyntax-only", str(src)])
 
 
+def test_inflate_decoder_against_zlib(tmp_path):
+    """csrc/inflate_fast.cpp (the BAM reader's own DEFLATE decoder) against zlib: tests/native/inflate_check.cpp deflates a dozen
+    kinds of data at every level / strategy / memory level and with mid-stream flushes, and takes the BGZF blocks of the
+    fixture BAMs; every stream must decode to the identical bytes (a few may be declined, never wrong), damaged and
+    truncated streams must not write outside their buffers. Built with ASan + UBSan when the toolchain has them."""
+    import subprocess
+    exe = str(tmp_path / "inflate_check")
+    base = ["g++", "-O1", "-g", "-std=c++17", "-Wall", os.path.join(H.ROOT, "tests", "native", "inflate_check.cpp"),
+            os.path.join(H.ROOT, "schlacount_b200", "csrc", "inflate_fast.cpp"), "-lz", "-o", exe]
+    if subprocess.call(base[:5] + ["-fsanitize=address,undefined"] + base[5:], stderr=subprocess.DEVNULL) != 0:
+        subprocess.check_call(base)
+    bams = [os.path.join(H.FIX, f) for f in sorted(os.listdir(H.FIX)) if f.endswith(".bam")]
+    assert bams
+    out = subprocess.run([exe] + bams, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.startswith("ok:") and " 0 declined" in out.stdout, out.stdout + out.stderr
+
+
+def test_bam_reader_same_records_with_either_inflate(sb, monkeypatch):
+    """the reader's result does not depend on which decoder inflates the blocks (HLAC_ZLIB_INFLATE=1 selects zlib; read once
+    per process, so the comparison runs in two subprocesses)"""
+    import subprocess
+    import sys
+    code = ("import ctypes as C, sys; sys.path.insert(0, %r); from schlacount_b200._lib import lib; L = lib(); n, h = C.c_uint64(), C.c_uint64();"
+            "assert L.hlac_bam_scan(%r, b'6:28510120-33480577', C.byref(n), C.byref(h)) == 0; print(n.value, h.value)"
+            % (H.ROOT, os.path.join(H.FIX, "test.bam").encode()))
+    outs = []
+    for zl in ("", "1"):
+        env = dict(os.environ)
+        env.pop("HLAC_ZLIB_INFLATE", None)
+        if zl:
+            env["HLAC_ZLIB_INFLATE"] = zl
+        outs.append(subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300).stdout.strip())
+    assert outs[0] == outs[1] and outs[0].split()[0] == "2864", outs
+
+
 def _caller_restated(names, theta, reads_explained, counts_reads, nreads):
     """src/em.rs:361-434 restated directly from the Rust, independently of csrc/caller.hpp and of the oracle's call_genotypes
     (a third implementation: the other two were written by the same hand). -> (called tx ids sorted, weights rows, pairs rows)"""
